@@ -1,0 +1,458 @@
+// tcgen05 / TMEM / TMA persistent GEMM for sm_100a:  C[M,N] = epi(A[M,K] @ W[N,K]^T), fp32 accumulate.
+//
+// Structure (one CTA per SM, 256 threads, static persistent tile schedule):
+//   warp 0      : TMA producer  -- cp.async.bulk.tensor.2d of a 128x64 A tile and a BNx64 W tile per stage
+//                                  (SWIZZLE_128B, K-major), mbarrier complete_tx
+//   warp 1      : MMA issuer    -- one elected lane issues 4 x tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16)
+//                                  per stage into a TMEM accumulator; tcgen05.commit frees the smem stage and, after the
+//                                  last K block, publishes the accumulator
+//   warp 2      : TMEM allocator (2*BN columns: double-buffered accumulator so the epilogue of tile i overlaps
+//                                  the main loop of tile i+1)
+//   warps 4..7  : epilogue      -- tcgen05.ld 32x32b (one accumulator row per thread), bias / activation / residual,
+//                                  vectorised global stores
+// Replaces the cuBLAS calls behind every nn.Linear on the reference path (see include/dynam3d_b200.h).
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 x 16-bit = 128 B = one SWIZZLE_128B atom row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 256;
+
+template <int BN>
+struct Cfg {
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN;  // 256 or 512: power of two >= 32
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct Epilogue {
+  void* C;
+  long long ldc;
+  const float* bias;
+  const float* residual;
+  long long ldres;
+  int act;
+  int out_kind;
+};
+
+// ---------------- PTX wrappers ----------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major operand, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor):
+// [0,14) start>>4 | [16,30) LBO>>4 (=1, ignored for swizzled K-major) | [32,46) SBO>>4 (=64) | [46,48) version=1 | [61,64) layout=2
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// UMMA instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1<<4), a/b format (0=f16,1=bf16) at 7/10,
+// K-major A and B (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).
+__device__ __forceinline__ uint32_t make_idesc(int kind, int n) {
+  uint32_t d = 0;
+  d |= 1u << 4;
+  d |= (uint32_t)kind << 7;
+  d |= (uint32_t)kind << 10;
+  d |= (uint32_t)(n >> 3) << 17;
+  d |= (uint32_t)(BM >> 4) << 24;
+  return d;
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case D3D_ACT_QUICK_GELU: return quick_gelu(v);
+    case D3D_ACT_GELU: return gelu_erf(v);
+    case D3D_ACT_SILU: return silu(v);
+    default: return v;
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Epilogue ep, int M, int N,
+                    int K, int in_kind) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
+  // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem ptr (4 B)
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + 2 + a); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * C::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles_m = (M + BM - 1) / BM;
+  const int tiles_n = (N + BN - 1) / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "n"(C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * BM;
+        const int n0 = (tile % tiles_n) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+          mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+          tma_load_2d(sa, &tmA, full_bar(stage), kb * BK, m0);
+          tma_load_2d(sa + C::A_BYTES, &tmB, full_bar(stage), kb * BK, n0);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(in_kind, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+          const uint64_t da = make_smem_desc(sa);
+          const uint64_t db = make_smem_desc(sa + C::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 16 elements (32 B) along K inside the 128 B swizzle atom: +2 in the (addr >> 4) field
+            umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));  // frees this smem stage when the MMAs above retire
+          if (kb == num_kb - 1) umma_commit(tfull_bar(acc));
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (warps 4..7 <-> TMEM lane quadrants 0..3) =====================
+    const int q = warp & 3;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      const int m0 = (tile / tiles_n) * BM;
+      const int n0 = (tile % tiles_n) * BN;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < M;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + (uint32_t)c, r);
+        tmem_ld_wait();
+        const int col0 = n0 + c;
+        if (row_ok && col0 < N) {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          if (ep.bias) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < N) v[i] += __ldg(ep.bias + col0 + i);
+          }
+          if (ep.act == D3D_ACT_SWIGLU) {
+            // row-interleaved gate/up: acc cols (2j, 2j+1) -> out col j
+            const long long ocol0 = col0 >> 1;
+            const int nout = N >> 1;
+            float o[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = silu(v[2 * i]) * v[2 * i + 1];
+            if (ep.out_kind == D3D_OUT_F32) {
+              float* dst = (float*)ep.C + (long long)row * ep.ldc + ocol0;
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (ocol0 + i < nout) dst[i] = o[i];
+            } else {
+              uint32_t* dst = (uint32_t*)((uint16_t*)ep.C + (long long)row * ep.ldc + ocol0);
+              if (ocol0 + 16 <= nout) {
+                uint4 p0 = make_uint4(pack16x2(o[0], o[1], ep.out_kind), pack16x2(o[2], o[3], ep.out_kind),
+                                      pack16x2(o[4], o[5], ep.out_kind), pack16x2(o[6], o[7], ep.out_kind));
+                uint4 p1 = make_uint4(pack16x2(o[8], o[9], ep.out_kind), pack16x2(o[10], o[11], ep.out_kind),
+                                      pack16x2(o[12], o[13], ep.out_kind), pack16x2(o[14], o[15], ep.out_kind));
+                reinterpret_cast<uint4*>(dst)[0] = p0;
+                reinterpret_cast<uint4*>(dst)[1] = p1;
+              } else {
+                for (int i = 0; i < 16; ++i)
+                  if (ocol0 + i < nout) st16(ep.C, (size_t)((long long)row * ep.ldc + ocol0 + i), o[i], ep.out_kind);
+              }
+            }
+          } else {
+            if (ep.act != D3D_ACT_NONE) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], ep.act);
+            }
+            const bool full = col0 + 32 <= N;
+            if (ep.residual) {
+              const float* res = ep.residual + (long long)row * ep.ldres + col0;
+              if (full) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  float4 t = reinterpret_cast<const float4*>(res)[i];
+                  v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+                }
+              } else {
+                for (int i = 0; i < 32; ++i)
+                  if (col0 + i < N) v[i] += res[i];
+              }
+            }
+            if (ep.out_kind == D3D_OUT_F32) {
+              float* dst = (float*)ep.C + (long long)row * ep.ldc + col0;
+              if (full) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+              } else {
+                for (int i = 0; i < 32; ++i)
+                  if (col0 + i < N) dst[i] = v[i];
+              }
+            } else {
+              uint16_t* dst = (uint16_t*)ep.C + (long long)row * ep.ldc + col0;
+              if (full) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  uint4 p = make_uint4(pack16x2(v[8 * i], v[8 * i + 1], ep.out_kind), pack16x2(v[8 * i + 2], v[8 * i + 3], ep.out_kind),
+                                       pack16x2(v[8 * i + 4], v[8 * i + 5], ep.out_kind), pack16x2(v[8 * i + 6], v[8 * i + 7], ep.out_kind));
+                  reinterpret_cast<uint4*>(dst)[i] = p;
+                }
+              } else {
+                for (int i = 0; i < 32; ++i)
+                  if (col0 + i < N) st16(ep.C, (size_t)((long long)row * ep.ldc + col0 + i), v[i], ep.out_kind);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------- host side ----------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+int make_tmap(CUtensorMap* map, const void* base, int kind, long long rows, long long cols, long long ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    d3d_set_error("cuTensorMapEncodeTiled entry point not available");
+    return D3D_ECUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, kind == D3D_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, dims,
+                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    d3d_set_error("cuTensorMapEncodeTiled failed (%d): base=%p rows=%lld cols=%lld ld=%lld", (int)r, base, rows, cols, ld);
+    return D3D_ECUDA;
+  }
+  return 0;
+}
+
+template <int BN>
+int launch(const d3d_gemm_args& a, cudaStream_t st) {
+  using C = Cfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    D3D_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  CUtensorMap tmA, tmB;
+  D3D_TRY(make_tmap(&tmA, a.A, a.in_kind, a.M, a.K, a.lda, BM));
+  D3D_TRY(make_tmap(&tmB, a.W, a.in_kind, a.N, a.K, a.ldw, BN));
+  Epilogue ep{a.C, a.ldc, a.bias, a.residual, a.ldres, a.act, a.out_kind};
+  const int tiles = d3d_cdiv(a.M, BM) * d3d_cdiv(a.N, BN);
+  const int grid = tiles < d3d_num_sms() ? tiles : d3d_num_sms();
+  gemm_tcgen05_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tmA, tmB, ep, a.M, a.N, a.K, a.in_kind);
+  D3D_CHECK_LAUNCH();
+  return 0;
+}
+
+__global__ void gemm_simt_kernel(d3d_gemm_args a) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool swiglu = a.act == D3D_ACT_SWIGLU;
+  const int nout = swiglu ? a.N / 2 : a.N;
+  if (idx >= (long long)a.M * nout) return;
+  const int m = (int)(idx / nout), j = (int)(idx % nout);
+  auto dot = [&](int n) {
+    float acc = 0.f;
+    for (int k = 0; k < a.K; ++k) acc += ld16(a.A, (size_t)m * a.lda + k, a.in_kind) * ld16(a.W, (size_t)n * a.ldw + k, a.in_kind);
+    if (a.bias) acc += a.bias[n];
+    return acc;
+  };
+  float v;
+  if (swiglu) {
+    v = silu(dot(2 * j)) * dot(2 * j + 1);
+  } else {
+    v = apply_act(dot(j), a.act);
+    if (a.residual) v += a.residual[(size_t)m * a.ldres + j];
+  }
+  if (a.out_kind == D3D_OUT_F32) ((float*)a.C)[(size_t)m * a.ldc + j] = v;
+  else st16(a.C, (size_t)m * a.ldc + j, v, a.out_kind);
+}
+
+int validate(const d3d_gemm_args& a) {
+  D3D_REQUIRE(a.A && a.W && a.C, "null operand");
+  D3D_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "empty problem");
+  D3D_REQUIRE(a.in_kind == D3D_F16 || a.in_kind == D3D_BF16, "in_kind");
+  D3D_REQUIRE(a.out_kind == D3D_F16 || a.out_kind == D3D_BF16 || a.out_kind == D3D_OUT_F32, "out_kind");
+  D3D_REQUIRE(a.lda >= a.K && a.ldw >= a.K, "leading dimension < K");
+  D3D_REQUIRE((a.lda % 8) == 0 && (a.ldw % 8) == 0, "lda/ldw must be multiples of 8 elements (16 B TMA stride)");
+  D3D_REQUIRE(((uintptr_t)a.A % 16) == 0 && ((uintptr_t)a.W % 16) == 0, "A/W must be 16-byte aligned");
+  D3D_REQUIRE(a.act != D3D_ACT_SWIGLU || ((a.N % 2) == 0 && a.residual == nullptr), "swiglu needs even N, no residual");
+  const int esz = a.out_kind == D3D_OUT_F32 ? 4 : 2;
+  D3D_REQUIRE(((uintptr_t)a.C % 16) == 0 && ((a.ldc * esz) % 16) == 0, "C rows must be 16-byte aligned");
+  D3D_REQUIRE(!a.residual || (((uintptr_t)a.residual % 16) == 0 && (a.ldres % 4) == 0), "residual rows must be 16-byte aligned");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int d3d_gemm(const d3d_gemm_args* args_h, void* stream) {
+  D3D_REQUIRE(args_h != nullptr, "args");
+  const d3d_gemm_args& a = *args_h;
+  D3D_TRY(validate(a));
+  cudaStream_t st = (cudaStream_t)stream;
+  // wide tiles once there is enough work to fill the machine with them; 128-wide otherwise
+  const long long tiles256 = (long long)d3d_cdiv(a.M, BM) * d3d_cdiv(a.N, 256);
+  if (a.N >= 256 && tiles256 >= 2LL * d3d_num_sms()) return launch<256>(a, st);
+  return launch<128>(a, st);
+}
+
+extern "C" int d3d_gemm_simt(const d3d_gemm_args* args_h, void* stream) {
+  D3D_REQUIRE(args_h != nullptr, "args");
+  const d3d_gemm_args& a = *args_h;
+  D3D_TRY(validate(a));
+  const int nout = a.act == D3D_ACT_SWIGLU ? a.N / 2 : a.N;
+  const long long total = (long long)a.M * nout;
+  gemm_simt_kernel<<<d3d_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(a);
+  D3D_CHECK_LAUNCH();
+  return 0;
+}

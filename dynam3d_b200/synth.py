@@ -1,0 +1,137 @@
+"""Seeded synthetic inputs for the Dynam3D per-step hot path.
+
+Used by the tests, `bench.py` and `__graft_entry__.smoke()`; numpy only (no CUDA, no oracle).
+
+* RGB: uniform uint8.
+* Depth: z-depth ray-cast of an axis-aligned room + a few boxes from the agent pose, divided by 10 m,
+  quantised to 1/4096 (so values are exact in fp32 on any host), ~2 % zeros (exercises the column-max fill).
+* Pose: habitat axes (x right, y up, z back), y = 1.25 m; trajectory = 0.25 m forward + turns of 15..60 deg.
+* Segmentation (FastSAM stand-in): dense int64 labels on the 24x24 patch grid.
+* Weights: `hash_uniform` -- a counter-based generator written with exact integer tensor ops so that the
+  CPU oracle and the GPU engine get bit-identical parameters without shipping checkpoints.
+"""
+import math
+
+import numpy as np
+
+ROOM = np.array([[-4.0, 4.0], [-3.0, 3.0], [0.0, 3.0]])  # internal frame X, Y(forward@0), Z(up)
+
+
+def _boxes(rng, n=3):
+    out = []
+    for _ in range(n):
+        c = np.array([rng.uniform(-3, 3), rng.uniform(-2, 2), 0.0])
+        s = np.array([rng.uniform(0.3, 1.0), rng.uniform(0.3, 1.0), rng.uniform(0.5, 2.0)])
+        out.append(np.stack([c - s * [1, 1, 0], c + s], 1))
+    return out
+
+
+def _ray_box_exit(o, d, box):
+    """distance along d (per ray) at which a ray starting INSIDE `box` leaves it."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t1 = (box[:, 0][None] - o[None]) / d
+        t2 = (box[:, 1][None] - o[None]) / d
+    t = np.where(d > 0, t2, t1)
+    t = np.where(d == 0, np.inf, t)
+    return t.min(axis=-1)
+
+
+def _ray_box_hit(o, d, box):
+    """entry distance of rays starting OUTSIDE `box` (inf when missed)."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t1 = (box[:, 0][None] - o[None]) / d
+        t2 = (box[:, 1][None] - o[None]) / d
+    tmin = np.nanmax(np.minimum(t1, t2), axis=-1)
+    tmax = np.nanmin(np.maximum(t1, t2), axis=-1)
+    return np.where((tmax >= tmin) & (tmin > 0), tmin, np.inf)
+
+
+def render_depth(position_hab, heading, size=256, hfov=90.0, boxes=(), zero_frac=0.02, rng=None):
+    """[size,size,1] fp32 depth in [0,1] (z-depth / 10 m), habitat camera at `position_hab` looking along `heading`."""
+    px, py, pz = position_hab[0], -position_hab[2], position_hab[1]
+    o = np.array([px, py, pz], dtype=np.float64)
+    fwd = np.array([-math.sin(heading), math.cos(heading), 0.0])
+    right = np.array([math.cos(heading), math.sin(heading), 0.0])
+    up = np.array([0.0, 0.0, 1.0])
+    t = math.tan(math.radians(hfov) / 2)
+    c = ((np.arange(size) + 0.5) / (size / 2) - 1.0) * t
+    r = (1.0 - (np.arange(size) + 0.5) / (size / 2)) * t
+    d = fwd[None, None] + c[None, :, None] * right[None, None] + r[:, None, None] * up[None, None]
+    d = d.reshape(-1, 3)
+    depth = _ray_box_exit(o, d, ROOM)
+    for bx in boxes:
+        depth = np.minimum(depth, _ray_box_hit(o, d, bx))
+    depth = np.clip(depth / 10.0, 0.0, 1.0)
+    depth = np.round(depth * 4096.0) / 4096.0
+    depth = depth.reshape(size, size).astype(np.float32)
+    if rng is not None and zero_frac > 0:
+        depth[rng.random((size, size)) < zero_frac] = 0.0
+    return depth[..., None]
+
+
+def make_segmentation(rng, n_seg, kind="blocks", grid=24):
+    """Dense labels 0..G-1 on the patch grid, [grid, grid] int64."""
+    if n_seg == 1:
+        return np.zeros((grid, grid), np.int64)
+    if kind == "blocks":
+        shapes = {16: (6, 6), 48: (3, 4), 4: (12, 12), 36: (4, 4), 64: (3, 3), 144: (2, 2), 576: (1, 1)}
+        bh, bw = shapes[n_seg]
+        lab = (np.arange(grid)[:, None] // bh) * (grid // bw) + (np.arange(grid)[None, :] // bw)
+        return lab.astype(np.int64)
+    # voronoi: irregular segment sizes
+    seeds = rng.uniform(0, grid, size=(n_seg, 2))
+    yy, xx = np.meshgrid(np.arange(grid) + 0.5, np.arange(grid) + 0.5, indexing="ij")
+    d = (yy[..., None] - seeds[:, 0]) ** 2 + (xx[..., None] - seeds[:, 1]) ** 2
+    lab = d.argmin(-1)
+    _, dense = np.unique(lab, return_inverse=True)
+    return dense.reshape(grid, grid).astype(np.int64)
+
+
+def make_trajectory(rng, n_steps, start=(0.0, 1.25, 0.0)):
+    """positions [n,3] fp32 (habitat axes) and headings [n] python floats."""
+    pos = np.array(start, dtype=np.float64)
+    heading = float(rng.uniform(0, 2 * math.pi))
+    P, Hd = [], []
+    for _ in range(n_steps):
+        P.append(pos.astype(np.float32))
+        Hd.append(heading)
+        heading = (heading + math.radians(float(rng.choice([-60, -45, -30, -15, 15, 30, 45, 60])))) % (2 * math.pi)
+        step = np.array([-math.sin(heading) * 0.25, 0.0, -math.cos(heading) * 0.25])
+        nxt = pos + step
+        if abs(nxt[0]) < 3.5 and abs(nxt[2]) < 2.5:
+            pos = nxt
+    return np.stack(P, 0), Hd
+
+
+def make_episode(seed, n_steps=1, num_views=1, rgb_size=224, depth_size=256, n_seg=16, seg_kind="blocks", pano_depth=True):
+    """One synthetic episode.  Returns a list of per-step dicts:
+    rgb u8 [V,rgb,rgb,3]; depth f32 [V,depth,depth,1]; segm i64 [V,24,24]; position f32 [3]; heading float."""
+    rng = np.random.default_rng(seed)
+    boxes = _boxes(rng)
+    pos, head = make_trajectory(rng, n_steps)
+    steps = []
+    for t in range(n_steps):
+        rgb = rng.integers(0, 256, size=(num_views, rgb_size, rgb_size, 3), dtype=np.uint8)
+        depth = np.stack([render_depth(pos[t], head[t] + (ix * (-math.pi / 6) if pano_depth else 0.0), depth_size, boxes=boxes, rng=rng)
+                          for ix in range(num_views)], 0)
+        segm = np.stack([make_segmentation(rng, n_seg, seg_kind) for _ in range(num_views)], 0)
+        steps.append({"rgb": rgb, "depth": depth, "segm": segm, "position": pos[t].copy(), "heading": float(head[t])})
+    return steps
+
+
+# ------------------------------------------------------------------------------------------------
+# counter-based deterministic weights (torch, device agnostic, bit-identical on CPU and CUDA)
+# ------------------------------------------------------------------------------------------------
+def hash_uniform(shape, seed, scale=1.0, device="cpu", dtype=None):
+    """uniform(-scale, scale) from a 64-bit integer mix of (seed, index); exact integer math, so CPU == CUDA."""
+    import torch
+    n = int(np.prod(shape)) if len(shape) else 1
+    x = torch.arange(n, dtype=torch.int64, device=device)
+    x = x + (int(seed) * 0x9E3779B97F4A7C15 % (1 << 63))
+    x = (x ^ (x >> 30)) * 0x3F4A7C159E3779B9
+    x = (x ^ (x >> 27)) * 0x14057B7EF767814F
+    x = x ^ (x >> 31)
+    u = ((x >> 11) & 0xFFFFFF).to(torch.float32) * (1.0 / 16777216.0)  # 24 bits -> [0,1), exact in fp32
+    w = (u * 2.0 - 1.0) * float(scale)
+    w = w.reshape(shape)
+    return w if dtype is None else w.to(dtype)

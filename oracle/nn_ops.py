@@ -1,0 +1,139 @@
+"""TEST INFRASTRUCTURE ONLY -- fp32 PyTorch (CPU) restatement of the neural blocks on Dynam3D's hot path.
+
+`rnd` is the 16-bit rounding hook that mirrors where the CUDA engine stores fp16/bf16
+(the A operand of every tensor-core GEMM, fp16 QKV / attention outputs).  With `rnd=None` this is
+a plain fp32 restatement of the reference modules (used to pin the oracle against the reference
+run on CPU); with `rnd=round_fp16` it is the precision-matched oracle the `-m gpu` parity tests use.
+The reference itself runs these blocks under `torch.cuda.amp.autocast()` (ss_trainer_Dynam3D.py:385),
+i.e. with fp16 GEMM operands, so 16-bit operand rounding is the reference path's own precision.
+
+FF    = Dynam3D_VLN/vlnce_baselines/models/feature_fields.py
+CLIPM = Dynam3D_VLN/vlnce_baselines/models/encoders/clip/model.py
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+def round_fp16(t):
+    return t.to(torch.float16).to(torch.float32)
+
+
+def round_bf16(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def _id(t):
+    return t
+
+
+def linear(x, w, b=None, rnd=None):
+    """y = rnd(x) @ rnd(w)^T + b, fp32 accumulate."""
+    r = rnd or _id
+    y = r(x) @ r(w.to(torch.float32)).t()
+    if b is not None:
+        y = y + b.to(torch.float32)
+    return y
+
+
+def layer_norm(x, w, b, eps):
+    return F.layer_norm(x.to(torch.float32), (x.shape[-1],), w.to(torch.float32), b.to(torch.float32), eps)
+
+
+def gelu(x):
+    return F.gelu(x)  # exact (erf) GELU, nn.GELU() default / activation="gelu"
+
+
+def quick_gelu(x):
+    return x * torch.sigmoid(1.702 * x)  # CLIPM:162-164
+
+
+def mlp_ln_gelu(x, P, prefix, rnd=None):
+    """nn.Sequential(Linear, LayerNorm, GELU, Linear) (FF:139-143,148-152,157-161; POL:83-111)."""
+    h = linear(x, P[prefix + ".0.weight"], P[prefix + ".0.bias"], rnd)
+    h = layer_norm(h, P[prefix + ".1.weight"], P[prefix + ".1.bias"], 1e-5)
+    h = gelu(h)
+    return linear(h, P[prefix + ".3.weight"], P[prefix + ".3.bias"], rnd)
+
+
+def mha_varlen(x, w_in, b_in, w_out, b_out, n_head, seq_lens, rnd=None, causal=False):
+    """Multi-head self-attention over packed sequences x [T, d] (block-diagonal by `seq_lens`)."""
+    r = rnd or _id
+    T, d = x.shape
+    hd = d // n_head
+    qkv = r(linear(x, w_in, b_in, rnd))  # engine stores QKV in 16 bit
+    q, k, v = qkv.split(d, dim=-1)
+    out = torch.empty(T, d, dtype=torch.float32)
+    s = 0
+    scale = 1.0 / math.sqrt(hd)
+    for n in seq_lens:
+        qs = q[s:s + n].view(n, n_head, hd).transpose(0, 1)
+        ks = k[s:s + n].view(n, n_head, hd).transpose(0, 1)
+        vs = v[s:s + n].view(n, n_head, hd).transpose(0, 1)
+        att = (qs @ ks.transpose(1, 2)) * scale
+        if causal:
+            att = att.masked_fill(torch.ones(n, n, dtype=torch.bool).triu(1), float("-inf"))
+        att = torch.softmax(att, dim=-1)
+        out[s:s + n] = (att @ vs).transpose(0, 1).reshape(n, d)
+        s += n
+    out = r(out)  # attention output stored in 16 bit (A operand of out-proj)
+    return linear(out, w_out, b_out, rnd)
+
+
+def post_norm_encoder(x, P, prefix, seq_lens, n_head=12, n_layers=2, final_eps=1e-12, rnd=None):
+    """nn.TransformerEncoder(TransformerEncoderLayer(d, nhead, 4d, activation='gelu', batch_first=True),
+    num_layers=2, norm=LayerNorm(eps=1e-12)) in eval mode (FF:134-137,146,155): post-norm layers,
+    layer-norm eps 1e-5, final norm eps 1e-12; x is a packed [T, d] batch of independent sequences."""
+    for l in range(n_layers):
+        p = f"{prefix}.layers.{l}."
+        sa = mha_varlen(x, P[p + "self_attn.in_proj_weight"], P[p + "self_attn.in_proj_bias"],
+                        P[p + "self_attn.out_proj.weight"], P[p + "self_attn.out_proj.bias"], n_head, seq_lens, rnd)
+        x = layer_norm(x + sa, P[p + "norm1.weight"], P[p + "norm1.bias"], 1e-5)
+        h = gelu(linear(x, P[p + "linear1.weight"], P[p + "linear1.bias"], rnd))
+        h = linear(h, P[p + "linear2.weight"], P[p + "linear2.bias"], rnd)
+        x = layer_norm(x + h, P[p + "norm2.weight"], P[p + "norm2.bias"], 1e-5)
+    return layer_norm(x, P[prefix + ".norm.weight"], P[prefix + ".norm.bias"], final_eps)
+
+
+# ------------------------------------------------------------------------------------------------
+# CLIP ViT (CLIPM:153-238) -- restated functionally on an OpenAI-layout state dict
+# ------------------------------------------------------------------------------------------------
+def vit_forward(images, P, n_layers, n_head, patch=14, rnd=None, ln_post_on_patches=True, n_layers_run=None,
+                return_hidden=False):
+    """images [N,3,R,R] fp32 (already normalised).  Returns (cls [N,out], patch [N,g*g,out]).
+
+    `ln_post_on_patches=False` is the Pretrain variant (Q8, src_3dff/models/encoders/clip/model.py:231-236).
+    `n_layers_run` / `return_hidden` give the hidden state after k blocks (LLaVA's vision_feature_layer=-2).
+    """
+    r = rnd or _id
+    N = images.shape[0]
+    w = P["conv1.weight"].to(torch.float32)  # [width,3,p,p]
+    width = w.shape[0]
+    g = images.shape[-1] // patch
+    cols = F.unfold(images.to(torch.float32), kernel_size=patch, stride=patch).transpose(1, 2)  # [N, g*g, 3*p*p]
+    x = r(cols) @ r(w.reshape(width, -1)).t()
+    cls = P["class_embedding"].to(torch.float32).expand(N, 1, width)
+    x = torch.cat([cls, x], dim=1) + P["positional_embedding"].to(torch.float32)
+    x = layer_norm(x, P["ln_pre.weight"], P["ln_pre.bias"], 1e-5)
+    T = g * g + 1
+    x = x.reshape(N * T, width)
+    run = n_layers if n_layers_run is None else n_layers_run
+    for l in range(run):
+        p = f"transformer.resblocks.{l}."
+        h = layer_norm(x, P[p + "ln_1.weight"], P[p + "ln_1.bias"], 1e-5)
+        x = x + mha_varlen(h, P[p + "attn.in_proj_weight"], P[p + "attn.in_proj_bias"],
+                           P[p + "attn.out_proj.weight"], P[p + "attn.out_proj.bias"], n_head, [T] * N, rnd)
+        h = layer_norm(x, P[p + "ln_2.weight"], P[p + "ln_2.bias"], 1e-5)
+        h = r(quick_gelu(linear(h, P[p + "mlp.c_fc.weight"], P[p + "mlp.c_fc.bias"], rnd)))
+        x = x + linear(h, P[p + "mlp.c_proj.weight"], P[p + "mlp.c_proj.bias"], rnd)
+    x = x.reshape(N, T, width)
+    if return_hidden:
+        return x
+    proj = P["proj"].to(torch.float32)  # [width, out]
+    x_cls = linear(layer_norm(x[:, 0], P["ln_post.weight"], P["ln_post.bias"], 1e-5), proj.t(), None, rnd)
+    xp = x[:, 1:]
+    if ln_post_on_patches:
+        xp = layer_norm(xp, P["ln_post.weight"], P["ln_post.bias"], 1e-5)
+    x_patch = linear(xp, proj.t(), None, rnd)
+    return x_cls, x_patch

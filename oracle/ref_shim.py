@@ -1,0 +1,164 @@
+"""TEST INFRASTRUCTURE ONLY -- loader for the *unmodified* reference modules.
+
+Loads `Feature_Fields` (Dynam3D_VLN/vlnce_baselines/models/feature_fields.py)
+and the OpenAI-CLIP `VisionTransformer`
+(Dynam3D_VLN/vlnce_baselines/models/encoders/clip/model.py) straight from the
+read-only reference tree, in THIS container only, so that
+`oracle/make_golden.py` can (a) validate the restatement in `oracle/` and
+(b) write golden vectors under `tests/golden/`.
+
+Nothing in the product package (`dynam3d_b200/`), `bench.py` or the `-m gpu`
+tests imports this file: `/root/reference` does not exist on the GPU box.
+
+The reference needs four third-party modules that are not installed here; they
+are replaced by minimal stand-ins injected into `sys.modules`:
+
+* `torch_kdtree.build_kd_tree` (feature_fields.py:7,246,606) -> exact
+  brute-force K-NN, squared L2 in fp32, ascending, lowest index on ties.
+* `open3d` (feature_fields.py:8) -> empty module (the habitat branch never
+  touches it).
+* `configargparse` (feature_fields.py:24) -> argparse.
+* `vlnce_baselines.models.fastsam` (feature_fields.py:17) -> stub classes; the
+  segmentation (FastSAM output) is an INPUT of the hot path, so
+  `get_patch_segm` is replaced by a function returning the synthetic map.
+
+* `torch.cuda.get_device_properties` / `torch.cuda.memory_allocated` (free-memory probe in the merge branch,
+  feature_fields.py:678-680) are patched to report 80 GB / 0 B when no CUDA device exists, which selects the
+  same (grad-enabled) encoder call the reference makes on a GPU with > 10 GB free.
+
+Two NumPy-1.x-only comparisons (`ndarray == []`, feature_fields.py:557,567) are
+rewritten in memory to `len(...) == 0`; NumPy >= 1.25 raises on them.
+"""
+import argparse
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF_ROOT = os.environ.get("DYNAM3D_REFERENCE", "/root/reference")
+FF_PATH = os.path.join(REF_ROOT, "Dynam3D_VLN/vlnce_baselines/models/feature_fields.py")
+CLIP_MODEL_PATH = os.path.join(REF_ROOT, "Dynam3D_VLN/vlnce_baselines/models/encoders/clip/model.py")
+PRETRAIN_CLIP_MODEL_PATH = os.path.join(REF_ROOT, "Dynam3D_Pretrain/src_3dff/models/encoders/clip/model.py")
+
+
+def reference_available():
+    return os.path.isfile(FF_PATH) and os.path.isfile(CLIP_MODEL_PATH)
+
+
+class _BruteForceTree:
+    """Stand-in for torch_kdtree's tree object (query semantics used at feature_fields.py:606,610)."""
+
+    def __init__(self, points):
+        self.points = points.detach().to(torch.float32).clone()
+
+    def query(self, q, nr_nns_searches=1):
+        k = int(nr_nns_searches)
+        q = q.detach().to(torch.float32)
+        n_q = q.shape[0]
+        if k == 0:
+            return (torch.zeros((n_q, 0), dtype=torch.float32), torch.zeros((n_q, 0), dtype=torch.int64))
+        p = self.points.numpy()
+        qq = q.numpy()
+        dx = (qq[:, None, 0] - p[None, :, 0]).astype(np.float32)
+        dy = (qq[:, None, 1] - p[None, :, 1]).astype(np.float32)
+        dz = (qq[:, None, 2] - p[None, :, 2]).astype(np.float32)
+        d2 = ((dx * dx).astype(np.float32) + (dy * dy).astype(np.float32)).astype(np.float32)
+        d2 = (d2 + (dz * dz).astype(np.float32)).astype(np.float32)
+        order = np.argsort(d2, axis=1, kind="stable")[:, :k]
+        dist = np.take_along_axis(d2, order, axis=1)
+        return torch.from_numpy(dist), torch.from_numpy(order.astype(np.int64))
+
+
+def _install_stubs():
+    if "torch_kdtree" not in sys.modules:
+        m = types.ModuleType("torch_kdtree")
+        m.build_kd_tree = lambda pts: _BruteForceTree(pts)
+        sys.modules["torch_kdtree"] = m
+    if "open3d" not in sys.modules:
+        sys.modules["open3d"] = types.ModuleType("open3d")
+    if "configargparse" not in sys.modules:
+        m = types.ModuleType("configargparse")
+        m.ArgumentParser = argparse.ArgumentParser
+        sys.modules["configargparse"] = m
+    for name in ("vlnce_baselines", "vlnce_baselines.models"):
+        if name not in sys.modules:
+            pkg = types.ModuleType(name)
+            pkg.__path__ = []
+            sys.modules[name] = pkg
+    if "vlnce_baselines.models.fastsam" not in sys.modules:
+        m = types.ModuleType("vlnce_baselines.models.fastsam")
+
+        class FastSAM:  # noqa: D401 - stub
+            def __init__(self, *a, **k):
+                pass
+
+        class FastSAMPrompt:
+            def __init__(self, *a, **k):
+                pass
+
+        m.FastSAM = FastSAM
+        m.FastSAMPrompt = FastSAMPrompt
+        sys.modules["vlnce_baselines.models.fastsam"] = m
+
+
+def _patch_cuda_probe():
+    if torch.cuda.is_available() or getattr(torch.cuda, "_d3d_probe_patched", False):
+        return
+    props = types.SimpleNamespace(total_memory=80 * 1024 ** 3)
+    torch.cuda.get_device_properties = lambda *a, **k: props
+    torch.cuda.memory_allocated = lambda *a, **k: 0
+    torch.cuda._d3d_probe_patched = True
+
+
+_FF_MODULE = None
+
+
+def load_reference_feature_fields_module():
+    """Exec the reference feature_fields.py (with the two NumPy-2 rewrites) and return the module."""
+    global _FF_MODULE
+    if _FF_MODULE is not None:
+        return _FF_MODULE
+    _install_stubs()
+    _patch_cuda_probe()
+    with open(FF_PATH, "r") as f:
+        src = f.read()
+    n1 = src.count("if self.global_patch_position[b] == []:")
+    n2 = src.count("if self.global_patch_fts[b] == []:")
+    assert n1 == 1 and n2 == 1, "reference source changed; update the in-memory rewrite"
+    src = src.replace("if self.global_patch_position[b] == []:", "if len(self.global_patch_position[b]) == 0:")
+    src = src.replace("if self.global_patch_fts[b] == []:", "if len(self.global_patch_fts[b]) == 0:")
+    mod = types.ModuleType("ref_feature_fields")
+    mod.__file__ = FF_PATH
+    exec(compile(src, FF_PATH, "exec"), mod.__dict__)
+    _FF_MODULE = mod
+    return mod
+
+
+def make_reference_feature_fields(batch_size=1, seed=0):
+    """Instantiate the reference Feature_Fields on CPU with seeded default init."""
+    mod = load_reference_feature_fields_module()
+    argv = sys.argv
+    sys.argv = [argv[0]]
+    try:
+        torch.manual_seed(seed)
+        ff = mod.Feature_Fields(batch_size=batch_size, device="cpu")
+    finally:
+        sys.argv = argv
+    ff.eval()
+    return ff
+
+
+def attach_segmentation(ff, segm_fn):
+    """Replace FastSAM (`get_patch_segm`, feature_fields.py:400-430) by `segm_fn(batch_image)->int64 [N,24,24]`."""
+    ff.get_patch_segm = lambda batch_image, *a, **k: segm_fn(batch_image)
+
+
+def load_reference_clip_model_module(pretrain=False):
+    path = PRETRAIN_CLIP_MODEL_PATH if pretrain else CLIP_MODEL_PATH
+    spec = importlib.util.spec_from_file_location("ref_clip_model_pre" if pretrain else "ref_clip_model", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
