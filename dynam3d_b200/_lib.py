@@ -35,6 +35,46 @@ class GemmArgs(ctypes.Structure):
 
 _lib = None
 
+_P, _I, _L, _F = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
+_IP, _FP = ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_float)
+
+# argument types of every exported entry (mirrors include/dynam3d_b200.h); tests/test_abi.py checks the symbol list
+SIGNATURES = {
+    "d3d_version": [], "d3d_sm_count": [], "d3d_check_device": [_I],
+    "d3d_gemm": [_P, _P], "d3d_gemm_simt": [_P, _P],
+    "d3d_depth_preprocess": [_P, _P, _I, _I, _I, _F, _F, _P],
+    "d3d_depth_patch_grid": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _IP, _IP, _F, _F, _P],
+    "d3d_unproject_habitat": [_P, _P, _I, _I, _I, _FP, _FP, _FP, _F, _P, _P, _P, _P],
+    "d3d_patch_3d_info": [_P, _I, _I, _I, _FP, _FP, _FP, _F, _P, _P],
+    "d3d_frustum_cull": [_P, _P, _P, _P, _I, _I, _P, _I, _I, _I, _P, _F, _F, _F, _F, _F, _F, _F, _P, _P, _P],
+    "d3d_knn3d": [_P, _I, _P, _I, _I, _P, _P, _P],
+    "d3d_seq_centroid": [_P, _P, _P, _I, _P, _P],
+    "d3d_env_export": [_P, _P, _P, _I, _P, _F, _I, _P, _P, _P, _P],
+    "d3d_layernorm": [_P, _L, _P, _P, _P, _F, _I, _I, _I, _P, _L, _P, _L, _I, _P],
+    "d3d_rmsnorm": [_P, _L, _P, _P, _F, _I, _I, _P, _L, _P, _L, _I, _P],
+    "d3d_rope": [_P, _L, _P, _P, _I, _I, _I, _I, _P],
+    "d3d_embed_gather": [_P, _I, _P, _I, _I, _P, _L, _P],
+    "d3d_preprocess_im2col": [_P, _I, _I, _I, _I, _I, _FP, _FP, _P, _I, _I, _P],
+    "d3d_vit_embed_ln": [_P, _P, _P, _P, _P, _F, _I, _I, _I, _P, _P],
+    "d3d_scatter_rows": [_P, _L, _P, _P, _L, _P, _I, _I, _P],
+    "d3d_add_inplace": [_P, _P, _L, _I, _P],
+    "d3d_cast16": [_P, _L, _P, _L, _I, _I, _I, _P],
+    "d3d_attention_simt": [_P, _L, _P, _L, _P, _I, _I, _I, _I, _I, _I, _F, _P],
+    "d3d_attention_mma": [_P, _L, _P, _L, _P, _I, _I, _I, _I, _I, _I, _F, _P],
+}
+OPTIONAL = {"d3d_attention_mma"}
+
+
+def _declare(lib_):
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib_, name, None)
+        if fn is None:
+            if name in OPTIONAL:
+                continue
+            raise D3DLibraryError(f"{LIB_PATH} does not export {name}: stale build?")
+        fn.argtypes = argtypes
+        fn.restype = ctypes.c_int
+
 
 def lib():
     """Load the library once; raise if it is not built (run `python -c 'import __graft_entry__ as g; g.build()'`)."""
@@ -44,6 +84,7 @@ def lib():
             raise D3DLibraryError(f"{LIB_PATH} not found: the CUDA extension is not built and there is no CPU fallback")
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.d3d_last_error.restype = ctypes.c_char_p
+        _declare(_lib)
     return _lib
 
 

@@ -260,7 +260,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int nout = N >> 1;
             float o[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = silu(v[2 * i]) * v[2 * i + 1];
+            for (int i = 0; i < 16; ++i) o[i] = __fdividef(v[2 * i], 1.0f + __expf(-v[2 * i])) * v[2 * i + 1];
             if (ep.out_kind == D3D_OUT_F32) {
               float* dst = (float*)ep.C + (long long)row * ep.ldc + ocol0;
 #pragma unroll
@@ -281,9 +281,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               }
             }
           } else {
-            if (ep.act != D3D_ACT_NONE) {
+            if (ep.act == D3D_ACT_QUICK_GELU) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], ep.act);
+              for (int i = 0; i < 32; ++i) v[i] = __fdividef(v[i], 1.0f + __expf(-1.702f * v[i]));
+            } else if (ep.act == D3D_ACT_GELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+            } else if (ep.act == D3D_ACT_SILU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = __fdividef(v[i], 1.0f + __expf(-v[i]));
             }
             const bool full = col0 + 32 <= N;
             if (ep.residual) {

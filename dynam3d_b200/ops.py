@@ -29,5 +29,235 @@ def gemm(a, w, out=None, bias=None, act=L.ACT_NONE, residual=None, out_dtype=Non
         L.kind_of(a.dtype), L.kind_of(out.dtype), L.ptr(bias), int(act),
         L.ptr(residual), residual.stride(0) if residual is not None else 0)
     fn = L.lib().d3d_gemm_simt if simt else L.lib().d3d_gemm
-    L.check(fn(ctypes.byref(args), L.stream_ptr()))
+    L.check(fn(ctypes.cast(ctypes.byref(args), ctypes.c_void_p), L.stream_ptr()))
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# geometry (see include/dynam3d_b200.h for the reference call sites)
+# ------------------------------------------------------------------------------------------------
+import math
+
+import numpy as np
+
+_c_int_p = ctypes.POINTER(ctypes.c_int)
+_c_float_p = ctypes.POINTER(ctypes.c_float)
+
+
+def _hp_f32(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a, a.ctypes.data_as(_c_float_p)
+
+
+def _hp_i32(a):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    return a, a.ctypes.data_as(_c_int_p)
+
+
+def nearest_index_table(dst, src):
+    """cv2.resize(INTER_NEAREST) source indices: floor(x * (1 / (dst/src))) clamped (host, double arithmetic)."""
+    ifx = 1.0 / (float(dst) / float(src))
+    return np.array([min(int(math.floor(x * ifx)), src - 1) for x in range(dst)], dtype=np.int32)
+
+
+def pixel_tables(hfov, vfov, W=24, H=24):
+    """Per-column / per-row tangent tables built with the reference's own expressions (FF:283-287)."""
+    half_W, half_H = W // 2, H // 2
+    tan_h = math.tan(math.pi * hfov / 360.0)
+    tan_v = math.tan(math.pi * vfov / 360.0)
+    tan_x = (np.array([i / half_W + 1 / W for i in range(-half_W, half_W)], np.float32) * tan_h).astype(np.float32)
+    tan_z = (np.array([i / half_H - 1 / H for i in range(half_H, -half_H, -1)], np.float32) * tan_v).astype(np.float32)
+    neg_atan_x = (-np.arctan(tan_x)).astype(np.float32)
+    return tan_x, tan_z, neg_atan_x, float(np.float32(tan_h))
+
+
+def depth_preprocess(obs, lo=0.0, hi=10.0, out=None):
+    """obs [n,H,W] (or [n,H,W,1]) fp32 -> metres [n,H,W]."""
+    n, H, W = obs.shape[0], obs.shape[1], obs.shape[2]
+    assert obs.dtype == torch.float32 and obs.is_contiguous()
+    if out is None:
+        out = torch.empty((n, H, W), device=obs.device, dtype=torch.float32)
+    L.check(L.lib().d3d_depth_preprocess(L.ptr(obs), L.ptr(out), n, H, W, ctypes.c_float(lo), ctypes.c_float(hi), L.stream_ptr()))
+    return out
+
+
+def depth_patch_grid(obs, batch, views, gh=24, gw=24, literal_q1=True, lo=0.0, hi=10.0):
+    """obs [n_img,H,W(,1)] fp32 -> [batch*views, gh*gw] metres on the patch grid (POL:336-341)."""
+    H, W = obs.shape[1], obs.shape[2]
+    assert obs.dtype == torch.float32 and obs.is_contiguous()
+    if literal_q1:
+        ri, ci = nearest_index_table(gh, W), np.zeros(gw, np.int32)
+    else:
+        ri, ci = nearest_index_table(gh, H), nearest_index_table(gw, W)
+    out = torch.empty((batch * views, gh * gw), device=obs.device, dtype=torch.float32)
+    ri, rp = _hp_i32(ri)
+    ci, cp = _hp_i32(ci)
+    L.check(L.lib().d3d_depth_patch_grid(L.ptr(obs), L.ptr(out), batch, views, H, W, gh, gw, int(bool(literal_q1)), rp, cp,
+                                         ctypes.c_float(lo), ctypes.c_float(hi), L.stream_ptr()))
+    return out
+
+
+def pose_rows(positions_hab, headings, num_views):
+    """[B*V,6] fp32 rows (x, -z, y, cos(theta), sin(theta), theta), theta = ix*(-pi/6)+heading (FF:521-526,550)."""
+    rows = []
+    for pos, h in zip(positions_hab, headings):
+        for ix in range(num_views):
+            th = ix * (-math.pi / 6) + float(h)
+            rows.append([float(pos[0]), -float(pos[2]), float(pos[1]), math.cos(th), math.sin(th), th])
+    return np.asarray(rows, dtype=np.float32)
+
+
+def camera_rows(position_hab, headings):
+    """[V,5] fp32 rows (x, -z, y, cos(-h), sin(-h)) for the cull / export kernels (FF:95-99, 830-836)."""
+    rows = [[float(position_hab[0]), -float(position_hab[2]), float(position_hab[1]), math.cos(-float(h)), math.sin(-float(h))]
+            for h in headings]
+    return np.asarray(rows, dtype=np.float32)
+
+
+def unproject_habitat(depth, pose, hfov=90.0, vfov=90.0, W=24, H=24):
+    """depth [n,W*H] metres, pose [n,6] (device) -> xyz [n,W*H,3], dir [n,W*H], scale [n,W*H]."""
+    n = depth.shape[0]
+    tx, tz, na, th = pixel_tables(hfov, vfov, W, H)
+    xyz = torch.empty((n, W * H, 3), device=depth.device, dtype=torch.float32)
+    d = torch.empty((n, W * H), device=depth.device, dtype=torch.float32)
+    s = torch.empty((n, W * H), device=depth.device, dtype=torch.float32)
+    tx, txp = _hp_f32(tx); tz, tzp = _hp_f32(tz); na, nap = _hp_f32(na)
+    L.check(L.lib().d3d_unproject_habitat(L.ptr(depth), L.ptr(pose), n, W, H, txp, tzp, nap, ctypes.c_float(th),
+                                          L.ptr(xyz), L.ptr(d), L.ptr(s), L.stream_ptr()))
+    return xyz, d, s
+
+
+def patch_3d_info(depth, hfov=90.0, vfov=90.0, W=24, H=24):
+    n = depth.shape[0]
+    tx, tz, na, th = pixel_tables(hfov, vfov, W, H)
+    out = torch.empty((5, n, W * H), device=depth.device, dtype=torch.float32)
+    tx, txp = _hp_f32(tx); tz, tzp = _hp_f32(tz); na, nap = _hp_f32(na)
+    L.check(L.lib().d3d_patch_3d_info(L.ptr(depth), n, W, H, txp, tzp, nap, ctypes.c_float(th), L.ptr(out), L.stream_ptr()))
+    return out
+
+
+def frustum_cull(xyz, direction, scale, fts16, n_patches, depth, cam, hfov=90.0, vfov=90.0, near=0.0, far=3.0, eps=0.1,
+                 mask=None, n_deleted=None):
+    """In-place tombstoning of the first `n_patches` rows; returns (mask u8 [n_patches], n_deleted int32 [1])."""
+    V, H, W = depth.shape
+    fx = float(np.float32(W / np.tan(np.deg2rad(hfov) / 2.0) / 2.0))
+    fy = float(np.float32(H / np.tan(np.deg2rad(vfov) / 2.0) / 2.0))
+    if mask is None:
+        mask = torch.empty((max(n_patches, 1),), device=xyz.device, dtype=torch.uint8)
+    if n_deleted is None:
+        n_deleted = torch.zeros((1,), device=xyz.device, dtype=torch.int32)
+    f = ctypes.c_float
+    L.check(L.lib().d3d_frustum_cull(L.ptr(xyz), L.ptr(direction), L.ptr(scale), L.ptr(fts16), n_patches,
+                                     fts16.shape[1] if fts16 is not None else 0, L.ptr(depth), V, H, W, L.ptr(cam),
+                                     f(fx), f(fy), f(W / 2.0), f(H / 2.0), f(near), f(far), f(eps), L.ptr(mask), L.ptr(n_deleted),
+                                     L.stream_ptr()))
+    return mask[:n_patches], n_deleted
+
+
+def knn3d(refs, queries, k):
+    """Exact K-NN (squared L2, ascending, lowest index on ties): -> (d2 [Q,k] fp32, idx [Q,k] int32)."""
+    assert refs.dtype == torch.float32 and queries.dtype == torch.float32 and refs.is_contiguous() and queries.is_contiguous()
+    Q = queries.shape[0]
+    d2 = torch.empty((Q, k), device=refs.device, dtype=torch.float32)
+    idx = torch.empty((Q, k), device=refs.device, dtype=torch.int32)
+    L.check(L.lib().d3d_knn3d(L.ptr(refs), refs.shape[0], L.ptr(queries), Q, k, L.ptr(d2), L.ptr(idx), L.stream_ptr()))
+    return d2, idx
+
+
+def seq_centroid(xyz, member, cu_seqlens, n_seq):
+    out = torch.empty((n_seq, 3), device=xyz.device, dtype=torch.float32)
+    L.check(L.lib().d3d_seq_centroid(L.ptr(xyz), L.ptr(member), L.ptr(cu_seqlens), n_seq, L.ptr(out), L.stream_ptr()))
+    return out
+
+
+def env_export(pos, fts, ids, agent, radius, out_rel, out_fts, out_count):
+    L.check(L.lib().d3d_env_export(L.ptr(pos), L.ptr(fts), L.ptr(ids), ids.numel(), L.ptr(agent), ctypes.c_float(radius), fts.shape[1],
+                                   L.ptr(out_rel), L.ptr(out_fts), L.ptr(out_count), L.stream_ptr()))
+
+
+# ------------------------------------------------------------------------------------------------
+# normalisation / elementwise / attention
+# ------------------------------------------------------------------------------------------------
+def layernorm(x, gamma, beta, eps, out32=None, out16=None, act=L.ACT_NONE, row_index=None, n_rows=None):
+    T = n_rows if n_rows is not None else (row_index.numel() if row_index is not None else x.shape[0])
+    D = x.shape[1]
+    assert x.dtype == torch.float32 and x.stride(1) == 1
+    L.check(L.lib().d3d_layernorm(L.ptr(x), x.stride(0), L.ptr(row_index), L.ptr(gamma), L.ptr(beta), ctypes.c_float(eps), T, D, int(act),
+                                  L.ptr(out32), out32.stride(0) if out32 is not None else 0,
+                                  L.ptr(out16), out16.stride(0) if out16 is not None else 0,
+                                  L.kind_of(out16.dtype) if out16 is not None else 0, L.stream_ptr()))
+
+
+def rmsnorm(x, w, eps, out32=None, out16=None, row_index=None, n_rows=None):
+    T = n_rows if n_rows is not None else (row_index.numel() if row_index is not None else x.shape[0])
+    D = x.shape[1]
+    assert x.dtype == torch.float32 and x.stride(1) == 1
+    L.check(L.lib().d3d_rmsnorm(L.ptr(x), x.stride(0), L.ptr(row_index), L.ptr(w), ctypes.c_float(eps), T, D,
+                                L.ptr(out32), out32.stride(0) if out32 is not None else 0,
+                                L.ptr(out16), out16.stride(0) if out16 is not None else 0,
+                                L.kind_of(out16.dtype) if out16 is not None else 0, L.stream_ptr()))
+
+
+def rope(qkv, pos, inv_freq, H, Dh):
+    L.check(L.lib().d3d_rope(L.ptr(qkv), qkv.stride(0), L.ptr(pos), L.ptr(inv_freq), qkv.shape[0], H, Dh, L.kind_of(qkv.dtype), L.stream_ptr()))
+
+
+def embed_gather(table, ids, out):
+    L.check(L.lib().d3d_embed_gather(L.ptr(table), L.kind_of(table.dtype), L.ptr(ids), ids.numel(), table.shape[1], L.ptr(out), out.stride(0),
+                                     L.stream_ptr()))
+
+
+CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
+CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+
+
+def preprocess_im2col(img_u8, R=336, patch=14, out_dtype=torch.float16, mean=CLIP_MEAN, std=CLIP_STD):
+    """img_u8 [N,H,W,3] uint8 (device) -> im2col patches [N*(R/patch)^2, kpad] with kpad = 3*patch^2 rounded up to 8."""
+    N, Hin, Win, _ = img_u8.shape
+    assert img_u8.dtype == torch.uint8 and img_u8.is_contiguous()
+    k = 3 * patch * patch
+    kpad = (k + 7) // 8 * 8
+    g = R // patch
+    out = torch.empty((N * g * g, kpad), device=img_u8.device, dtype=out_dtype)
+    m, mp = _hp_f32(mean)
+    s, sp = _hp_f32(std)
+    L.check(L.lib().d3d_preprocess_im2col(L.ptr(img_u8), N, Hin, Win, R, patch, mp, sp, L.ptr(out), kpad, L.kind_of(out_dtype), L.stream_ptr()))
+    return out
+
+
+def vit_embed_ln(conv, cls, pos, gamma, beta, eps, N, tokens, out):
+    L.check(L.lib().d3d_vit_embed_ln(L.ptr(conv), L.ptr(cls), L.ptr(pos), L.ptr(gamma), L.ptr(beta), ctypes.c_float(eps), N, tokens,
+                                     conv.shape[1], L.ptr(out), L.stream_ptr()))
+
+
+def scatter_rows(src, dst, n, src_idx=None, dst_idx=None):
+    L.check(L.lib().d3d_scatter_rows(L.ptr(src), src.stride(0), L.ptr(src_idx), L.ptr(dst), dst.stride(0), L.ptr(dst_idx), n, src.shape[1],
+                                     L.stream_ptr()))
+
+
+def add_inplace(a, b):
+    assert a.is_contiguous() and b.is_contiguous() and a.numel() == b.numel()
+    L.check(L.lib().d3d_add_inplace(L.ptr(a), L.ptr(b), a.numel() // a.shape[-1], a.shape[-1], L.stream_ptr()))
+
+
+def cast16(x, out):
+    L.check(L.lib().d3d_cast16(L.ptr(x), x.stride(0), L.ptr(out), out.stride(0), x.shape[0], x.shape[1], L.kind_of(out.dtype), L.stream_ptr()))
+
+
+def attention_simt(qkv, out, cu_seqlens, n_seq, max_len, H, Dh, causal=False, scale=None):
+    scale = (1.0 / math.sqrt(Dh)) if scale is None else scale
+    L.check(L.lib().d3d_attention_simt(L.ptr(qkv), qkv.stride(0), L.ptr(out), out.stride(0), L.ptr(cu_seqlens), n_seq, max_len, H, Dh,
+                                       int(bool(causal)), L.kind_of(qkv.dtype), ctypes.c_float(scale), L.stream_ptr()))
+
+
+def attention(qkv, out, cu_seqlens, n_seq, max_len, H, Dh, causal=False, uniform_len=None, impl="auto"):
+    """Self-attention over packed sequences.  `impl`: 'simt' (fp32 CUDA cores), 'mma' (tensor cores), or 'auto'."""
+    fn = getattr(L.lib(), "d3d_attention_mma", None) if impl in ("auto", "mma") else None
+    if impl == "mma" and fn is None:
+        raise L.D3DError("tensor-core attention kernel not built")
+    if fn is not None and Dh in (64, 96) and max_len >= 64:
+        scale = 1.0 / math.sqrt(Dh)
+        L.check(fn(L.ptr(qkv), qkv.stride(0), L.ptr(out), out.stride(0), L.ptr(cu_seqlens), n_seq, max_len, H, Dh, int(bool(causal)),
+                   L.kind_of(qkv.dtype), ctypes.c_float(scale), L.stream_ptr()))
+        return
+    attention_simt(qkv, out, cu_seqlens, n_seq, max_len, H, Dh, causal)

@@ -135,3 +135,40 @@ def hash_uniform(shape, seed, scale=1.0, device="cpu", dtype=None):
     w = (u * 2.0 - 1.0) * float(scale)
     w = w.reshape(shape)
     return w if dtype is None else w.to(dtype)
+
+
+def _u(shape, seed, std, device="cpu"):
+    return hash_uniform(shape, seed, scale=std * math.sqrt(3.0), device=device)
+
+
+def vit_state_dict(seed, width=1024, layers=24, patch=14, resolution=336, out_dim=768, device="cpu", half_round=True):
+    """OpenAI-CLIP-layout visual state dict with CLIP's init scales; weights rounded to fp16-representable values
+    (the reference stores the tower in fp16, CLIPM:389-410)."""
+    import torch
+    r = (lambda t: t.to(torch.float16).to(torch.float32)) if half_round else (lambda t: t)
+    s = seed * 1000
+    attn_std, proj_std, fc_std = width ** -0.5, (width ** -0.5) * ((2 * layers) ** -0.5), (2 * width) ** -0.5
+    tokens = (resolution // patch) ** 2 + 1
+    sd = {
+        "conv1.weight": r(_u((width, 3, patch, patch), s + 1, (3 * patch * patch) ** -0.5, device)),
+        "class_embedding": _u((width,), s + 2, width ** -0.5, device),
+        "positional_embedding": _u((tokens, width), s + 3, width ** -0.5, device),
+        "ln_pre.weight": 1.0 + _u((width,), s + 4, 0.05, device), "ln_pre.bias": _u((width,), s + 5, 0.05, device),
+        "ln_post.weight": 1.0 + _u((width,), s + 6, 0.05, device), "ln_post.bias": _u((width,), s + 7, 0.05, device),
+        "proj": r(_u((width, out_dim), s + 8, width ** -0.5, device)),
+    }
+    for l in range(layers):
+        p, b = f"transformer.resblocks.{l}.", s + 100 + 20 * l
+        sd[p + "ln_1.weight"] = 1.0 + _u((width,), b + 1, 0.05, device)
+        sd[p + "ln_1.bias"] = _u((width,), b + 2, 0.05, device)
+        sd[p + "attn.in_proj_weight"] = r(_u((3 * width, width), b + 3, attn_std, device))
+        sd[p + "attn.in_proj_bias"] = r(_u((3 * width,), b + 4, 0.02, device))
+        sd[p + "attn.out_proj.weight"] = r(_u((width, width), b + 5, proj_std, device))
+        sd[p + "attn.out_proj.bias"] = r(_u((width,), b + 6, 0.02, device))
+        sd[p + "ln_2.weight"] = 1.0 + _u((width,), b + 7, 0.05, device)
+        sd[p + "ln_2.bias"] = _u((width,), b + 8, 0.05, device)
+        sd[p + "mlp.c_fc.weight"] = r(_u((4 * width, width), b + 9, fc_std, device))
+        sd[p + "mlp.c_fc.bias"] = r(_u((4 * width,), b + 10, 0.02, device))
+        sd[p + "mlp.c_proj.weight"] = r(_u((width, 4 * width), b + 11, proj_std, device))
+        sd[p + "mlp.c_proj.bias"] = r(_u((width,), b + 12, 0.02, device))
+    return sd

@@ -74,6 +74,103 @@ int d3d_gemm(const d3d_gemm_args* args_h, void* stream);
 /* Plain CUDA-core reference GEMM with the same contract (debug / self-check only, slow). */
 int d3d_gemm_simt(const d3d_gemm_args* args_h, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Geometry of the 3D-token path (HBM-bound fp32; bit-exact against oracle/geometry.py).
+ * ------------------------------------------------------------------------------------------------ */
+
+/* preprocess_depth on full-resolution images (POL:171-186, call site POL:350): zeros -> column max, then
+ * (lo*100 + d*(hi-lo)*100)/100 metres.  obs/out [n_img,H,W] fp32. */
+int d3d_depth_preprocess(const float* obs, float* out, int n_img, int H, int W, float lo, float hi, void* stream);
+
+/* cv2.resize(INTER_NEAREST) to the gh x gw patch grid + preprocess_depth (POL:336-341).  obs [n_img,H,W] fp32,
+ * out [batch*views, gh*gw].  row_idx_h/col_idx_h: host tables of source indices (cv2's floor(x*src/dst)).
+ * literal_q1 != 0 reproduces the reference's `observations['depth'][b][i]` indexing:
+ * out[b,i,r,c] = obs[b, i, row_idx[r]] (image row i), in which case col_idx_h is ignored. */
+int d3d_depth_patch_grid(const float* obs, float* out, int batch, int views, int H, int W, int gh, int gw, int literal_q1,
+                         const int* row_idx_h, const int* col_idx_h, float lo, float hi, void* stream);
+
+/* project_depth_to_3d_habitat + world offset (FF:276-293, 548-554).  depth [n,W*H] metres; pose [n,6] =
+ * (x, y, z internal frame, cos(theta), sin(theta), theta) fp32 with theta = ix*(-pi/6)+heading; tan_x_h[W],
+ * tan_z_h[H], neg_atan_x_h[W]: host tables built with the reference's expressions (FF:283-286); tan_h = tan(hfov/2).
+ * Outputs xyz [n,W*H,3], dir [n,W*H] (mod 2pi), scale [n,W*H]. */
+int d3d_unproject_habitat(const float* depth, const float* pose, int n_units, int W, int H, const float* tan_x_h,
+                          const float* tan_z_h, const float* neg_atan_x_h, float tan_h, float* xyz, float* dir, float* scale,
+                          void* stream);
+
+/* get_patch_3d_info (FF:296-326): out5 [5,n,W*H] = rel_x, rel_y, rel_z, direction mod 2pi, scale. */
+int d3d_patch_3d_info(const float* depth, int n_units, int W, int H, const float* tan_x_h, const float* tan_z_h,
+                      const float* neg_atan_x_h, float tan_h, float* out5, void* stream);
+
+/* delete_old_features_from_camera_frustum, numeric part (FF:88-115, 347-360) for all views of a step at once:
+ * a stored patch is culled if for ANY view it projects inside the HxW image, lies in [near, far] and in front of
+ * the observed depth + eps.  Culled rows are tombstoned in place (xyz=-10000, dir=scale=0, fts16 row=0);
+ * mask[n] (1 = culled now) and *n_deleted are written for the host bookkeeping (FF:362-393).
+ * depth [n_views,H,W] metres; cam [n_views,5] = (x, y, z internal, cos(-heading), sin(-heading)). */
+int d3d_frustum_cull(float* xyz, float* dir, float* scale, void* fts16, int n_patches, int fts_dim, const float* depth,
+                     int n_views, int H, int W, const float* cam, float fx, float fy, float cx, float cy, float near_,
+                     float far_, float eps, uint8_t* mask, int* n_deleted, void* stream);
+
+/* Exact K-NN in 3-D, replaces torch_kdtree build_kd_tree + query (FF:246,606,610; PFF:364,540,584):
+ * squared L2 ((dx*dx+dy*dy)+dz*dz in fp32), ascending, lowest index on ties.  k <= 8, n_ref >= k.
+ * refs [n_ref,3], queries [n_q,3] -> out_d2 [n_q,k] fp32, out_idx [n_q,k] int32. */
+int d3d_knn3d(const float* refs, int n_ref, const float* queries, int n_q, int k, float* out_d2, int* out_idx, void* stream);
+
+/* centroid of gathered points per sequence (FF:583, 663, 715): fp64 accumulate, one rounding; empty -> NaN.
+ * member[cu_seqlens[s] .. cu_seqlens[s+1]) are row indices into xyz [*,3]; out [n_seq,3]. */
+int d3d_seq_centroid(const float* xyz, const int* member, const int* cu_seqlens, int n_seq, float* out, void* stream);
+
+/* get_environment_features for one episode and one token level (FF:818-862): gather rows `ids` (dict order) from
+ * pos [*,3] / fts [*,width] fp32, move to the agent frame, keep rows with |rel| <= radius, order preserved.
+ * agent [5] = (x, y, z internal, cos(-heading), sin(-heading)).  out_rel [n_ids,3], out_fts [n_ids,width], *out_count. */
+int d3d_env_export(const float* pos, const float* fts, const int* ids, int n_ids, const float* agent, float radius, int width,
+                   float* out_rel, float* out_fts, int* out_count, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Normalisation / elementwise / gather kernels between the GEMMs (fp32 math; 16-bit outputs feed GEMM A operands).
+ * Row widths D must be one of 128, 256, 512, 768, 1024, 3072, 4096.
+ * ------------------------------------------------------------------------------------------------ */
+
+/* torch.nn.LayerNorm (CLIPM:153-159; FF:141,146,151,155,159; POL:85-109): y = act(LN(x[row_index?row_index[r]:r])*gamma+beta),
+ * act in {D3D_ACT_NONE, D3D_ACT_GELU}; writes out32 [T,ld32] and/or out16 [T,ld16] (either may be NULL). */
+int d3d_layernorm(const float* x, int64_t ldx, const int* row_index, const float* gamma, const float* beta, float eps, int T,
+                  int D, int act, float* out32, int64_t ld32, void* out16, int64_t ld16, int kind16, void* stream);
+
+/* HF LlamaRMSNorm / Phi3RMSNorm (llava language model, POL:123-127): y = w * x * rsqrt(mean(x^2)+eps). */
+int d3d_rmsnorm(const float* x, int64_t ldx, const int* row_index, const float* w, float eps, int T, int D, float* out32,
+                int64_t ld32, void* out16, int64_t ld16, int kind16, void* stream);
+
+/* HF apply_rotary_pos_emb (rotate_half form) in place on q and k of a packed [T, 3*H*Dh] 16-bit QKV buffer;
+ * pos [T] int32 token positions, inv_freq [Dh/2] fp32. */
+int d3d_rope(void* qkv, int64_t ld, const int* pos, const float* inv_freq, int T, int H, int Dh, int kind, void* stream);
+
+/* embed_tokens (POL:439): out[t, :D] = table16[ids[t], :D] as fp32. */
+int d3d_embed_gather(const void* table, int kind, const int* ids, int T, int D, float* out, int64_t ldo, void* stream);
+
+/* CLIPEncoder preprocessing + im2col of the 14x14/14 patch embedding (ENC:267-284; CLIPM:220-222):
+ * img u8 NHWC [N,Hin,Win,3] -> bicubic resize to RxR (A=-0.75, align_corners=False, rounded to u8 like torchvision;
+ * identity when Hin==Win==R) -> /255 -> (x-mean)/std -> 16-bit -> out [N*(R/patch)^2, kpad], col = c*p*p+ky*p+kx,
+ * zero padded to kpad (multiple of 8). */
+int d3d_preprocess_im2col(const uint8_t* img, int N, int Hin, int Win, int R, int patch, const float* mean3_h,
+                          const float* std3_h, void* out, int kpad, int kind, void* stream);
+
+/* ViT token assembly + ln_pre (CLIPM:223-225): out[n,0] = LN(cls+pos[0]); out[n,1+i] = LN(conv[n*(tokens-1)+i]+pos[1+i]). */
+int d3d_vit_embed_ln(const float* conv, const float* cls, const float* pos, const float* gamma, const float* beta, float eps,
+                     int N, int tokens, int D, float* out, void* stream);
+
+/* dst[dst_idx?dst_idx[r]:r] = src[src_idx?src_idx[r]:r] for n fp32 rows of width D (slot writes FF:644-648,688,730,756). */
+int d3d_scatter_rows(const float* src, int64_t lds, const int* src_idx, float* dst, int64_t ldd, const int* dst_idx, int n, int D,
+                     void* stream);
+/* a[i] += b[i] over n_rows*D contiguous fp32 (patch_features + patch_position_fts, POL:453). */
+int d3d_add_inplace(float* a, const float* b, int64_t n_rows, int D, void* stream);
+/* fp32 -> 16-bit cast of a [T,D] matrix. */
+int d3d_cast16(const float* in, int64_t ldi, void* out, int64_t ldo, int T, int D, int kind, void* stream);
+
+/* Variable-length multi-head self-attention, fp32 CUDA-core online-softmax version (nn.MultiheadAttention inside
+ * nn.TransformerEncoderLayer, FF:134-137; also exact fallback for CLIPM:181-183 / HF attention).
+ * qkv [T, 3*H*Dh] 16-bit packed (q|k|v), out [T, H*Dh] 16-bit, cu_seqlens [n_seq+1] int32, Dh in {64, 96}. */
+int d3d_attention_simt(const void* qkv, int64_t ld, void* out, int64_t ldo, const int* cu_seqlens, int n_seq, int max_len, int H,
+                       int Dh, int causal, int kind, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -137,3 +137,16 @@ def vit_forward(images, P, n_layers, n_head, patch=14, rnd=None, ln_post_on_patc
         xp = layer_norm(xp, P["ln_post.weight"], P["ln_post.bias"], 1e-5)
     x_patch = linear(xp, proj.t(), None, rnd)
     return x_cls, x_patch
+
+
+def clip_preprocess(img_u8, R=336, rnd=None):
+    """CLIPEncoder.forward preprocessing (ENC:267-284) on a uint8 NHWC batch -> normalised fp32 [N,3,R,R].
+    torchvision 0.14 (the reference's pin) resizes uint8 tensors in float32 WITHOUT antialias and rounds back to uint8."""
+    r = rnd or _id
+    x = torch.as_tensor(img_u8).permute(0, 3, 1, 2).to(torch.float32)
+    if x.shape[-1] != R or x.shape[-2] != R:
+        x = F.interpolate(x, size=(R, R), mode="bicubic", align_corners=False).round().clamp(0, 255)
+    x = x / 255.0
+    mean = torch.tensor([0.48145466, 0.4578275, 0.40821073]).view(1, 3, 1, 1)
+    std = torch.tensor([0.26862954, 0.26130258, 0.27577711]).view(1, 3, 1, 1)
+    return r((x - mean) / std)  # `image.type(self.dtype)`: fp16 (CLIPM:338-339)

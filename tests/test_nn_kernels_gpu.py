@@ -1,0 +1,97 @@
+"""Norm / RoPE / attention / preprocessing kernels vs plain PyTorch fp32 references of the same ops (floating point)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("T,D", [(577, 1024), (37, 768), (600, 3072), (5, 4096)])
+def test_layernorm_rmsnorm(T, D):
+    from dynam3d_b200 import ops
+    x = torch.randn(T, D, device="cuda") * 3 + 0.5
+    g = torch.randn(D, device="cuda"); b = torch.randn(D, device="cuda")
+    o32 = torch.empty_like(x); o16 = torch.empty(T, D, device="cuda", dtype=torch.float16)
+    ops.layernorm(x, g, b, 1e-5, out32=o32, out16=o16)
+    ref = F.layer_norm(x, (D,), g, b, 1e-5)
+    assert (o32 - ref).abs().max().item() < 2e-5 * max(1, ref.abs().max().item())  # fp32, different reduction order
+    assert torch.equal(o16, o32.half())
+    ops.layernorm(x, g, b, 1e-12, out32=o32, act=2)
+    assert (o32 - F.gelu(F.layer_norm(x, (D,), g, b, 1e-12))).abs().max().item() < 5e-5
+    idx = torch.randint(0, T, (11,), device="cuda", dtype=torch.int32)
+    og = torch.empty(11, D, device="cuda")
+    ops.layernorm(x, g, b, 1e-5, out32=og, row_index=idx)
+    assert (og - ref[idx.long()]).abs().max().item() < 2e-5 * max(1, ref.abs().max().item())
+    ob = torch.empty(T, D, device="cuda", dtype=torch.bfloat16)
+    ops.rmsnorm(x, g, 1e-5, out32=o32, out16=ob)
+    ref = g * (x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-5))
+    assert (o32 - ref).abs().max().item() < 2e-5 * max(1, ref.abs().max().item())
+    assert torch.equal(ob, o32.bfloat16())
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_rope_matches_hf_formula(dtype):
+    from dynam3d_b200 import ops
+    T, H, Dh = 70, 4, 96
+    qkv = torch.randn(T, 3 * H * Dh, device="cuda").to(dtype)
+    pos = torch.arange(T, device="cuda", dtype=torch.int32) % 50
+    inv_freq = (1.0 / (10000.0 ** (torch.arange(0, Dh, 2).float() / Dh))).cuda()
+    ref = qkv.float().clone()
+    freqs = pos.float()[:, None] * inv_freq[None]
+    emb = torch.cat([freqs, freqs], -1)
+    cos, sin = emb.cos()[:, None, :], emb.sin()[:, None, :]
+    for part in (0, 1):
+        x = ref[:, part * H * Dh:(part + 1) * H * Dh].view(T, H, Dh)
+        rot = torch.cat([-x[..., Dh // 2:], x[..., :Dh // 2]], -1)
+        ref[:, part * H * Dh:(part + 1) * H * Dh] = (x * cos + rot * sin).reshape(T, H * Dh)
+    ops.rope(qkv, pos, inv_freq, H, Dh)
+    tol = 4e-3 if dtype == torch.float16 else 3e-2  # one 16-bit rounding of values up to ~4
+    assert (qkv.float() - ref).abs().max().item() < tol
+    assert torch.equal(qkv[:, 2 * H * Dh:].float(), ref[:, 2 * H * Dh:])  # v untouched
+
+
+@pytest.mark.parametrize("impl", ["simt", "auto"])
+@pytest.mark.parametrize("lens,H,Dh,causal,dtype", [
+    ([577, 577], 16, 64, False, torch.float16),
+    ([1, 2, 33, 64, 65, 300, 130], 12, 64, False, torch.float16),
+    ([600, 75], 4, 96, True, torch.bfloat16),
+    ([128], 2, 96, True, torch.float16),
+])
+def test_attention_matches_torch(lens, H, Dh, causal, dtype, impl):
+    from dynam3d_b200 import ops
+    T = sum(lens)
+    qkv = (torch.randn(T, 3 * H * Dh, device="cuda") * 0.7).to(dtype)
+    out = torch.zeros(T, H * Dh, device="cuda", dtype=dtype)
+    cu = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), device="cuda", dtype=torch.int32)
+    ops.attention(qkv, out, cu, len(lens), max(lens), H, Dh, causal=causal, impl=impl)
+    s = 0
+    for n in lens:
+        q, k, v = [t.view(n, H, Dh).transpose(0, 1).float() for t in qkv[s:s + n].split(H * Dh, -1)]
+        ref = F.scaled_dot_product_attention(q[None], k[None], v[None], is_causal=causal)[0].transpose(0, 1).reshape(n, H * Dh)
+        tol = 3e-3 if dtype == torch.float16 else 2e-2  # 16-bit output rounding (+ 16-bit P on the tensor-core path)
+        assert (out[s:s + n].float() - ref).abs().max().item() < tol, (n, impl)
+        s += n
+
+
+@pytest.mark.parametrize("size", [336, 224])
+def test_preprocess_im2col(size):
+    from dynam3d_b200 import ops
+    g = torch.Generator().manual_seed(size)
+    img = torch.randint(0, 256, (3, size, size, 3), generator=g, dtype=torch.uint8)
+    cols = ops.preprocess_im2col(img.cuda()).cpu().float()
+    x = img.permute(0, 3, 1, 2).float()
+    if size != 336:  # torchvision 0.14 Resize on a uint8 tensor: float bicubic, then round + clamp back to uint8 (ENC:268)
+        x = F.interpolate(x, size=(336, 336), mode="bicubic", align_corners=False).round().clamp(0, 255)
+    x = x / 255.0
+    mean = torch.tensor(ops.CLIP_MEAN).view(1, 3, 1, 1); std = torch.tensor(ops.CLIP_STD).view(1, 3, 1, 1)
+    x = ((x - mean) / std).half().float()
+    ref = F.unfold(x, 14, stride=14).transpose(1, 2).reshape(-1, 588)
+    assert cols.shape == (3 * 576, 592) and torch.all(cols[:, 588:] == 0)
+    diff = (cols[:, :588] - ref).abs()
+    # a resized pixel may land on the other side of a .5 rounding boundary (1/255/std ~ 0.015): allow <= 1e-4 of pixels
+    bad = (diff > 2e-3).float().mean().item()
+    assert bad <= (1e-4 if size != 336 else 0.0), bad
+    assert diff.max().item() < 0.02
