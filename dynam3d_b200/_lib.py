@@ -61,8 +61,14 @@ SIGNATURES = {
     "d3d_cast16": [_P, _L, _P, _L, _I, _I, _I, _P],
     "d3d_attention_simt": [_P, _L, _P, _L, _P, _I, _I, _I, _I, _I, _I, _F, _P],
     "d3d_attention_mma": [_P, _L, _P, _L, _P, _I, _I, _I, _I, _I, _I, _F, _P],
+    "d3d_pool_features": [_P, _P, _P, _P, _P, _P, _I, _I, _P, _I, _P],
+    "d3d_pool_assemble": [_P, _P, _I, _P, _P, _P, _I, _I, _P, _P],
+    "d3d_disc_input": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P],
+    "d3d_patch_info_rows": [_P, _L, _P, _I, _P],
+    "d3d_concat2_cast": [_P, _P, _I, _I, _P, _I, _P],
+    "d3d_pos3_rows": [_P, _I, _P, _I, _P],
 }
-OPTIONAL = {"d3d_attention_mma"}
+OPTIONAL = set()
 
 
 def _declare(lib_):

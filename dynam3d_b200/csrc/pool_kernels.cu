@@ -1,0 +1,166 @@
+// Token builders for the layer-wise pooling of the 3D memory (patch -> instance -> zone, FF:580-597, 662-676, 717-727,
+// 743-753) and the merge-discriminator input (FF:613-617).  Sequences from several episodes are packed into one batch;
+// every sequence carries its own base pointers (an episode's patch / instance pool), so one launch serves all episodes.
+#include "common.cuh"
+
+namespace {
+
+// feature row (16-bit, 8 wide, K padded for the tensor-core GEMM):
+//   mode 0 (patch -> instance, FF:584-591): [xyz - centre (3), |xyz|, sin(dir), cos(dir), scale, 0]
+//   mode 1 (instance -> zone,  FF:719-723): [xyz - centre (3), |xyz|, 0, 0, 0, 0]
+// |xyz| is the norm of the ABSOLUTE position.  Aggregate-token rows (src < 0) are zero.
+__global__ void pool_features_kernel(const long long* __restrict__ seq_xyz, const long long* __restrict__ seq_dir,
+                                     const long long* __restrict__ seq_scale, const float* __restrict__ centre,
+                                     const int* __restrict__ tok_seq, const int* __restrict__ tok_src, int T, int mode,
+                                     void* __restrict__ out, int kind) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int src = tok_src[t];
+  if (src >= 0) {
+    const int s = tok_seq[t];
+    const float* xyz = reinterpret_cast<const float*>(seq_xyz[s]) + (size_t)src * 3;
+    const float x = xyz[0], y = xyz[1], z = xyz[2];
+    f[0] = x - centre[(size_t)s * 3];
+    f[1] = y - centre[(size_t)s * 3 + 1];
+    f[2] = z - centre[(size_t)s * 3 + 2];
+    f[3] = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+    if (mode == 0) {
+      const float d = reinterpret_cast<const float*>(seq_dir[s])[src];
+      f[4] = sinf(d);
+      f[5] = cosf(d);
+      f[6] = reinterpret_cast<const float*>(seq_scale[s])[src];
+    }
+  }
+  uint4 p = make_uint4(pack16x2(f[0], f[1], kind), pack16x2(f[2], f[3], kind), pack16x2(f[4], f[5], kind), pack16x2(f[6], f[7], kind));
+  reinterpret_cast<uint4*>(out)[t] = p;
+}
+
+// X[t] = (src < 0) ? agg : emb[t] + fts[src]   (FF:592-593, 674-676, 725-727); fts rows are fp16 (patches) or fp32 (instances)
+__global__ void pool_assemble_kernel(const float* __restrict__ emb, const long long* __restrict__ seq_fts, int fts_is_f32,
+                                     const int* __restrict__ tok_seq, const int* __restrict__ tok_src, const float* __restrict__ agg, int T,
+                                     int D, float* __restrict__ X) {
+  const int t = blockIdx.x;
+  if (t >= T) return;
+  const int src = tok_src[t];
+  float* dst = X + (size_t)t * D;
+  if (src < 0) {
+    for (int c = threadIdx.x; c < D; c += blockDim.x) dst[c] = agg[c];
+    return;
+  }
+  const int s = tok_seq[t];
+  const float* e = emb + (size_t)t * D;
+  if (fts_is_f32) {
+    const float* f = reinterpret_cast<const float*>(seq_fts[s]) + (size_t)src * D;
+    for (int c = threadIdx.x; c < D; c += blockDim.x) dst[c] = f[c] + e[c];
+  } else {
+    const __half* f = reinterpret_cast<const __half*>(seq_fts[s]) + (size_t)src * D;
+    for (int c = threadIdx.x; c < D; c += blockDim.x) dst[c] = __half2float(f[c]) + e[c];
+  }
+}
+
+// merge-discriminator input rows (FF:613-617): row (g, j) = [inst_fts[idx[g,j]] | view_fts[g] | centre[g] - inst_pos[idx[g,j]] | 0 pad]
+__global__ void disc_input_kernel(const float* __restrict__ inst_fts, const float* __restrict__ inst_pos, const int* __restrict__ idx,
+                                  const float* __restrict__ view_fts, const float* __restrict__ centre, int G, int K, int D, int ldo,
+                                  void* __restrict__ out, int kind) {
+  const int r = blockIdx.x;  // g * K + j
+  if (r >= G * K) return;
+  const int g = r / K;
+  const int id = idx[r];
+  const float* a = inst_fts + (size_t)id * D;
+  const float* b = view_fts + (size_t)g * D;
+  const size_t o = (size_t)r * ldo;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    st16(out, o + c, a[c], kind);
+    st16(out, o + D + c, b[c], kind);
+  }
+  for (int c = threadIdx.x; c < ldo - 2 * D; c += blockDim.x) {
+    float v = 0.f;
+    if (c < 3) v = centre[(size_t)g * 3 + c] - inst_pos[(size_t)id * 3 + c];
+    st16(out, o + 2 * D + c, v, kind);
+  }
+}
+
+// 6-d patch info rows for the policy's patch_position_embedding (POL:432-433):
+// [rel_x, rel_y, rel_z, sin(direction), cos(direction), scale, 0, 0] from the [5, n, P] planes of d3d_patch_3d_info
+__global__ void patch_info_rows_kernel(const float* __restrict__ info5, long long plane, long long n, void* __restrict__ out, int kind) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float d = info5[3 * plane + i];
+  uint4 p = make_uint4(pack16x2(info5[i], info5[plane + i], kind), pack16x2(info5[2 * plane + i], sinf(d), kind),
+                       pack16x2(cosf(d), info5[4 * plane + i], kind), 0u);
+  reinterpret_cast<uint4*>(out)[i] = p;
+}
+
+// out16[r] = [a[r] (D fp32) | b[r] (D fp32)] as 16-bit (instance/zone projector input, POL:434-435)
+__global__ void concat2_cast_kernel(const float* __restrict__ a, const float* __restrict__ b, int n, int D, void* __restrict__ out, int kind) {
+  const int r = blockIdx.x;
+  if (r >= n) return;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    st16(out, (size_t)r * 2 * D + c, a[(size_t)r * D + c], kind);
+    st16(out, (size_t)r * 2 * D + D + c, b[(size_t)r * D + c], kind);
+  }
+}
+
+// out16[r] = [x[r,0], x[r,1], x[r,2], 0...] (8 wide) -- 3-d relative positions as a GEMM A operand (POL:89-99)
+__global__ void pos3_rows_kernel(const float* __restrict__ x, int n, void* __restrict__ out, int kind) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  uint4 p = make_uint4(pack16x2(x[(size_t)r * 3], x[(size_t)r * 3 + 1], kind), pack16x2(x[(size_t)r * 3 + 2], 0.f, kind), 0u, 0u);
+  reinterpret_cast<uint4*>(out)[r] = p;
+}
+
+}  // namespace
+
+extern "C" int d3d_pool_features(const int64_t* seq_xyz, const int64_t* seq_dir, const int64_t* seq_scale, const float* centre,
+                                 const int* tok_seq, const int* tok_src, int T, int mode, void* out16, int kind, void* stream) {
+  if (T == 0) return 0;
+  D3D_REQUIRE(seq_xyz && centre && tok_seq && tok_src && out16, "args");
+  D3D_REQUIRE(mode == 1 || (seq_dir && seq_scale), "mode 0 needs direction and scale pools");
+  pool_features_kernel<<<d3d_cdiv(T, 128), 128, 0, (cudaStream_t)stream>>>((const long long*)seq_xyz, (const long long*)seq_dir,
+                                                                           (const long long*)seq_scale, centre, tok_seq, tok_src, T, mode,
+                                                                           out16, kind);
+  D3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int d3d_pool_assemble(const float* emb, const int64_t* seq_fts, int fts_is_f32, const int* tok_seq, const int* tok_src,
+                                 const float* agg, int T, int D, float* X, void* stream) {
+  if (T == 0) return 0;
+  D3D_REQUIRE(emb && seq_fts && tok_seq && tok_src && agg && X, "args");
+  pool_assemble_kernel<<<T, 256, 0, (cudaStream_t)stream>>>(emb, (const long long*)seq_fts, fts_is_f32, tok_seq, tok_src, agg, T, D, X);
+  D3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int d3d_disc_input(const float* inst_fts, const float* inst_pos, const int* idx, const float* view_fts, const float* centre,
+                              int G, int K, int D, int ldo, void* out16, int kind, void* stream) {
+  if (G * K == 0) return 0;
+  D3D_REQUIRE(inst_fts && inst_pos && idx && view_fts && centre && out16, "args");
+  D3D_REQUIRE(ldo >= 2 * D + 3, "row too narrow");
+  disc_input_kernel<<<G * K, 256, 0, (cudaStream_t)stream>>>(inst_fts, inst_pos, idx, view_fts, centre, G, K, D, ldo, out16, kind);
+  D3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int d3d_patch_info_rows(const float* info5, int64_t n, void* out16, int kind, void* stream) {
+  if (n == 0) return 0;
+  D3D_REQUIRE(info5 && out16, "args");
+  patch_info_rows_kernel<<<d3d_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(info5, n, n, out16, kind);
+  D3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int d3d_concat2_cast(const float* a, const float* b, int n, int D, void* out16, int kind, void* stream) {
+  if (n == 0) return 0;
+  concat2_cast_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(a, b, n, D, out16, kind);
+  D3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int d3d_pos3_rows(const float* x, int n, void* out16, int kind, void* stream) {
+  if (n == 0) return 0;
+  pos3_rows_kernel<<<d3d_cdiv(n, 128), 128, 0, (cudaStream_t)stream>>>(x, n, out16, kind);
+  D3D_CHECK_LAUNCH();
+  return 0;
+}

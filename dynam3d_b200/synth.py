@@ -172,3 +172,24 @@ def vit_state_dict(seed, width=1024, layers=24, patch=14, resolution=336, out_di
         sd[p + "mlp.c_proj.weight"] = r(_u((width, 4 * width), b + 11, proj_std, device))
         sd[p + "mlp.c_proj.bias"] = r(_u((width,), b + 12, 0.02, device))
     return sd
+
+
+def lm_state_dict(seed, hidden=3072, layers=32, ffn=8192, vocab=32064, device="cpu", round_to=None):
+    """Llama-layout state dict of the llava-phi-3-mini language model shape (random init, std 0.02), rounded to the
+    16-bit storage type (`round_to` = torch.float16 / torch.bfloat16) like the checkpoint (POL:125 loads bf16)."""
+    import torch
+    r = (lambda t: t.to(round_to).to(torch.float32)) if round_to is not None else (lambda t: t)
+    s = seed * 100000
+    sd = {"model.embed_tokens.weight": r(_u((vocab, hidden), s + 1, 0.02, device)),
+          "model.norm.weight": 1.0 + _u((hidden,), s + 2, 0.05, device),
+          "lm_head.weight": r(_u((vocab, hidden), s + 3, 0.02, device))}
+    for l in range(layers):
+        p, b = f"model.layers.{l}.", s + 100 + 20 * l
+        sd[p + "input_layernorm.weight"] = 1.0 + _u((hidden,), b + 1, 0.05, device)
+        sd[p + "post_attention_layernorm.weight"] = 1.0 + _u((hidden,), b + 2, 0.05, device)
+        for j, n in enumerate(("q", "k", "v", "o")):
+            sd[p + f"self_attn.{n}_proj.weight"] = r(_u((hidden, hidden), b + 3 + j, 0.02, device))
+        sd[p + "mlp.gate_proj.weight"] = r(_u((ffn, hidden), b + 8, 0.02, device))
+        sd[p + "mlp.up_proj.weight"] = r(_u((ffn, hidden), b + 9, 0.02, device))
+        sd[p + "mlp.down_proj.weight"] = r(_u((hidden, ffn), b + 10, 0.02, device))
+    return sd

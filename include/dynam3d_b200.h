@@ -171,6 +171,33 @@ int d3d_cast16(const float* in, int64_t ldi, void* out, int64_t ldo, int T, int 
 int d3d_attention_simt(const void* qkv, int64_t ld, void* out, int64_t ldo, const int* cu_seqlens, int n_seq, int max_len, int H,
                        int Dh, int causal, int kind, float scale, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Token builders for the layer-wise pooling (patch -> instance -> zone) and the merge discriminator.
+ * Sequences of several episodes are packed in one batch; seq_* are per-sequence base addresses (device pointers
+ * stored as int64) of the owning episode's pools; tok_seq[t] / tok_src[t] give each packed token's sequence and its
+ * row in that pool (-1 = the learned aggregate token that heads every sequence).
+ * ------------------------------------------------------------------------------------------------ */
+
+/* 7-d / 4-d position feature rows (FF:584-591 mode 0; FF:719-723 mode 1), 8 wide 16-bit (GEMM A operand, K padded):
+ * [xyz-centre, |xyz|, sin(dir), cos(dir), scale, 0] or [xyz-centre, |xyz|, 0,0,0,0]; centre [n_seq,3]. */
+int d3d_pool_features(const int64_t* seq_xyz, const int64_t* seq_dir, const int64_t* seq_scale, const float* centre,
+                      const int* tok_seq, const int* tok_src, int T, int mode, void* out16, int kind, void* stream);
+
+/* X[t] = aggregate token (src<0) or emb[t] + fts[src] (FF:592-593, 674-676, 725-727); fts rows fp16 or fp32 of width D. */
+int d3d_pool_assemble(const float* emb, const int64_t* seq_fts, int fts_is_f32, const int* tok_seq, const int* tok_src,
+                      const float* agg, int T, int D, float* X, void* stream);
+
+/* instance_merge_discriminator input (FF:613-617): row (g,j) = [inst_fts[idx[g,j]] | view_fts[g] | centre[g]-inst_pos[idx[g,j]] | 0],
+ * 16-bit rows of ldo >= 2*D+3 elements; idx [G,K] int32. */
+int d3d_disc_input(const float* inst_fts, const float* inst_pos, const int* idx, const float* view_fts, const float* centre,
+                   int G, int K, int D, int ldo, void* out16, int kind, void* stream);
+
+/* Policy-side A operands (POL:432-435): patch info rows [rel_x, rel_y, rel_z, sin(dir), cos(dir), scale, 0, 0] from the
+ * [5,n] planes of d3d_patch_3d_info; [a | b] concatenation cast to 16 bit; 3-d positions padded to 8. */
+int d3d_patch_info_rows(const float* info5, int64_t n, void* out16, int kind, void* stream);
+int d3d_concat2_cast(const float* a, const float* b, int n, int D, void* out16, int kind, void* stream);
+int d3d_pos3_rows(const float* x, int n, void* out16, int kind, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

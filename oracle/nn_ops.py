@@ -150,3 +150,62 @@ def clip_preprocess(img_u8, R=336, rnd=None):
     mean = torch.tensor([0.48145466, 0.4578275, 0.40821073]).view(1, 3, 1, 1)
     std = torch.tensor([0.26862954, 0.26130258, 0.27577711]).view(1, 3, 1, 1)
     return r((x - mean) / std)  # `image.type(self.dtype)`: fp16 (CLIPM:338-339)
+
+
+# ------------------------------------------------------------------------------------------------
+# llava-phi-3-mini language model prefill (HF LlamaForCausalLM / Phi3ForCausalLM math; call site POL:463)
+# pinned against transformers' LlamaForCausalLM on a small config in tests/test_oracle_lm.py
+# ------------------------------------------------------------------------------------------------
+def rms_norm(x, w, eps):
+    x = x.to(torch.float32)
+    return w.to(torch.float32) * (x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps))
+
+
+def rope_tables(positions, head_dim, theta=10000.0):
+    inv_freq = 1.0 / (theta ** (torch.arange(0, head_dim, 2, dtype=torch.float32) / head_dim))
+    freqs = positions.to(torch.float32)[:, None] * inv_freq[None, :]
+    emb = torch.cat([freqs, freqs], dim=-1)
+    return emb.cos(), emb.sin()
+
+
+def apply_rope(x, cos, sin):
+    """x [T, H, Dh]; HF rotate_half convention."""
+    half = x.shape[-1] // 2
+    rot = torch.cat([-x[..., half:], x[..., :half]], dim=-1)
+    return x * cos[:, None, :] + rot * sin[:, None, :]
+
+
+def lm_prefill(embeds, seq_lens, P, n_layers, n_heads, eps=1e-5, theta=10000.0, rnd=None, prefix="model."):
+    """embeds [T, D] fp32 packed sequences -> logits of each sequence's LAST token [B, vocab] (Llama-layout names:
+    {prefix}layers.N.self_attn.{q,k,v,o}_proj.weight, mlp.{gate,up,down}_proj.weight, input_layernorm, post_attention_layernorm,
+    {prefix}norm.weight, lm_head.weight)."""
+    r = rnd or _id
+    x = embeds.to(torch.float32)
+    T, D = x.shape
+    hd = D // n_heads
+    pos = torch.cat([torch.arange(n) for n in seq_lens])
+    cos, sin = rope_tables(pos, hd, theta)
+    scale = 1.0 / math.sqrt(hd)
+    for l in range(n_layers):
+        p = f"{prefix}layers.{l}."
+        h = rms_norm(x, P[p + "input_layernorm.weight"], eps)
+        q = r(linear(h, P[p + "self_attn.q_proj.weight"], None, rnd)).view(T, n_heads, hd)
+        k = r(linear(h, P[p + "self_attn.k_proj.weight"], None, rnd)).view(T, n_heads, hd)
+        v = r(linear(h, P[p + "self_attn.v_proj.weight"], None, rnd)).view(T, n_heads, hd)
+        q, k = r(apply_rope(q, cos, sin)), r(apply_rope(k, cos, sin))
+        att = torch.empty(T, n_heads, hd)
+        s = 0
+        for n in seq_lens:
+            qs, ks, vs = (t[s:s + n].transpose(0, 1) for t in (q, k, v))
+            a = (qs @ ks.transpose(1, 2)) * scale
+            a = a.masked_fill(torch.ones(n, n, dtype=torch.bool).triu(1), float("-inf"))
+            att[s:s + n] = (torch.softmax(a, dim=-1) @ vs).transpose(0, 1)
+            s += n
+        x = x + linear(r(att.reshape(T, D)), P[p + "self_attn.o_proj.weight"], None, rnd)
+        h = rms_norm(x, P[p + "post_attention_layernorm.weight"], eps)
+        g = linear(h, P[p + "mlp.gate_proj.weight"], None, rnd)
+        u = linear(h, P[p + "mlp.up_proj.weight"], None, rnd)
+        x = x + linear(r(F.silu(g) * u), P[p + "mlp.down_proj.weight"], None, rnd)
+    last = torch.tensor([sum(seq_lens[:i + 1]) - 1 for i in range(len(seq_lens))])
+    h = rms_norm(x[last], P[prefix + "norm.weight"], eps)
+    return linear(h, P["lm_head.weight"], None, rnd)

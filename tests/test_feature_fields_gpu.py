@@ -1,0 +1,93 @@
+"""The B200 `Feature_Fields` engine vs the CPU oracle (oracle/ff_oracle.py, precision-matched fp16 operand rounding):
+discrete state must be IDENTICAL (patch ids, instance ids + member lists, zone keys / ids, K-NN indices, merge decisions);
+exported token features are floating point (tolerance stated)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _params(seed, merge_bias):
+    """Reference-named parameters with PyTorch-like init scales, generated identically for oracle and engine."""
+    from dynam3d_b200 import synth
+    from dynam3d_b200.feature_fields import Feature_Fields
+    ff = Feature_Fields(batch_size=1)
+    sd = {}
+    for i, (k, v) in enumerate(ff.state_dict().items()):
+        if v.dim() >= 2:
+            fan_in = v.shape[-1]
+            sd[k] = synth.hash_uniform(tuple(v.shape), seed * 1000 + i, scale=fan_in ** -0.5)
+        elif "norm" in k and k.endswith("weight") or k.endswith(".1.weight"):
+            sd[k] = 1.0 + synth.hash_uniform(tuple(v.shape), seed * 1000 + i, scale=0.05)
+        else:
+            sd[k] = synth.hash_uniform(tuple(v.shape), seed * 1000 + i, scale=0.05)
+    sd["instance_merge_discriminator.3.bias"] = sd["instance_merge_discriminator.3.bias"] + torch.tensor([0.0, merge_bias])
+    return sd
+
+
+def _compare_snap(a, b):
+    from oracle.ref_compare import snapshots_equal
+    return snapshots_equal(a, b)
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(seed=3, n_steps=4, V=1, n_seg=16, kind="voronoi", B=1),
+    dict(seed=5, n_steps=6, V=1, n_seg=48, kind="blocks", B=2),
+    dict(seed=6, n_steps=2, V=12, n_seg=16, kind="voronoi", B=1),
+])
+def test_engine_matches_oracle(cfg):
+    from dynam3d_b200 import ops, synth
+    from dynam3d_b200.feature_fields import Feature_Fields
+    from oracle import geometry as G
+    from oracle import nn_ops as NN
+    from oracle.ff_oracle import FeatureFieldsOracle
+    B, V = cfg["B"], cfg["V"]
+    sd = _params(cfg["seed"], merge_bias=0.0)
+    eng = Feature_Fields(batch_size=B)
+    eng.load_state_dict(sd, strict=True)
+    orc = FeatureFieldsOracle(sd, batch_size=B, rnd=NN.round_fp16)
+    episodes = [synth.make_episode(cfg["seed"] * 10 + b, n_steps=cfg["n_steps"], num_views=V, n_seg=cfg["n_seg"], seg_kind=cfg["kind"])
+                for b in range(B)]
+    rng = np.random.default_rng(cfg["seed"])
+    n_merge = n_dec = 0
+    for t in range(cfg["n_steps"]):
+        obs_depth = np.concatenate([episodes[b][t]["depth"] for b in range(B)], 0)  # [B*V,256,256,1]
+        pos = [episodes[b][t]["position"] for b in range(B)]
+        head = [episodes[b][t]["heading"] for b in range(B)]
+        segm = np.stack([episodes[b][t]["segm"] for b in range(B)], 0)
+        grid = (rng.standard_normal((B, V, 576, 768)) * 0.5).astype(np.float16)
+        # oracle inputs
+        d576 = G.depth_patch_grid(obs_depth, B, V, q1_fix=True)
+        full = G.preprocess_depth(obs_depth, (0.0, 10.0)).reshape(B, V, 256, 256)
+        orc.delete_old_features_from_camera_frustum(full, pos, head, num_of_views=V)
+        orc.update_feature_fields(d576, grid, segm, pos, head, num_of_views=V)
+        # engine: same path through the C ABI
+        obs_d = torch.from_numpy(obs_depth[..., 0]).cuda()
+        d576_e = ops.depth_patch_grid(obs_d, B, V, literal_q1=False).view(B, V, 576)
+        full_e = ops.depth_preprocess(obs_d).view(B, V, 256, 256)
+        eng.delete_old_features_from_camera_frustum(full_e, pos, head, num_of_views=V)
+        eng.update_feature_fields(d576_e, torch.from_numpy(grid).cuda(), batch_position=pos, batch_heading=head, num_of_views=V,
+                                  batch_patch_segm=segm)
+        for b in range(B):
+            assert _compare_snap(orc.snapshot(b), eng.snapshot(b)) == [], f"step {t} episode {b}"
+            last_o, last_e = orc.eps[b].last_knn, eng.eps[b].last.get("knn")
+            if last_o is not None:
+                assert np.array_equal(last_o[1], last_e[1]) and np.array_equal(last_o[0], last_e[0]), "K-NN indices / distances"
+                mo, lo = orc.eps[b].last_merge
+                assert np.array_equal(mo.astype(bool), eng.eps[b].last["merge"])
+                n_merge += int(mo.any(-1).sum()); n_dec += mo.size
+                margin = np.abs(lo[..., 1] - lo[..., 0]).min() if lo.size else 1.0
+                assert margin > 1e-3, "fixture has a near-tie merge decision; pick another seed"
+        env_o = orc.get_environment_features(pos, head)
+        env_e = eng.get_environment_features(pos, head)
+        for k in env_o:
+            for b in range(B):
+                a, e = env_o[k][b], env_e[k][b].cpu().numpy()
+                assert a.shape == e.shape, (t, k, b, a.shape, e.shape)
+                if "position" in k:
+                    assert np.array_equal(a, e, equal_nan=True), (t, k)
+                else:
+                    # fp16-operand GEMMs, fp32 accumulate / LayerNorm: matched rounding points, different summation order
+                    assert np.allclose(a, e, atol=3e-3, rtol=0), (t, k, np.abs(a - e).max())
+    print(f"cfg {cfg}: merge decisions {n_merge}/{n_dec}")

@@ -1,0 +1,38 @@
+"""Phi-3-mini-shaped LM prefill on the C ABI vs the precision-matched CPU oracle (oracle/nn_ops.lm_prefill)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(hidden, layers, heads, ffn, vocab, lens, dtype, seed=5):
+    from dynam3d_b200 import synth
+    from dynam3d_b200.phi3 import LMEngine, LMWeights
+    from oracle import nn_ops as NN
+    rnd = NN.round_fp16 if dtype == torch.float16 else NN.round_bf16
+    sd = synth.lm_state_dict(seed, hidden, layers, ffn, vocab, round_to=dtype)
+    emb = synth.hash_uniform((sum(lens), hidden), 100 + seed, 1.0)
+    eng = LMEngine(LMWeights.from_state_dict(sd, dtype=dtype), n_heads=heads, max_tokens=sum(lens))
+    cu = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int32, device="cuda")
+    pos = torch.cat([torch.arange(n, dtype=torch.int32) for n in lens]).cuda()
+    last = (cu[1:] - 1).to(torch.int32).contiguous()
+    logits = eng.prefill(emb.cuda().clone(), cu, pos, len(lens), max(lens), last).cpu()
+    want = NN.lm_prefill(emb, lens, sd, layers, heads, rnd=rnd)
+    f32 = NN.lm_prefill(emb, lens, sd, layers, heads, rnd=None)
+    e, ef = (logits - want).abs().max().item(), (logits - f32).abs().max().item()
+    print(f"lm L={layers} H={hidden} {dtype}: |logit|max={want.abs().max().item():.3f} err_vs_matched={e:.2e} vs_fp32={ef:.2e}")
+    assert torch.equal(logits.argmax(-1), want.argmax(-1))
+    return e, ef
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_lm_small(dtype):
+    e, ef = _run(768, 3, 8, 1536, 2048, [70, 33, 130], dtype)
+    assert e <= (1e-3 if dtype == torch.float16 else 8e-3)
+
+
+def test_lm_phi3_width_4_layers_fp16():
+    # true Phi-3-mini widths (3072 / 32 heads x 96 / 8192 / 32064), 4 of the 32 layers: north-star tolerance 1e-3
+    e, ef = _run(3072, 4, 32, 8192, 32064, [600], torch.float16)
+    assert e <= 1e-3
