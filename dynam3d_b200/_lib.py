@@ -94,7 +94,12 @@ def lib():
     return _lib
 
 
+N_CALLS = 0  # successful kernel-launching C-ABI calls (each launches >= 1 kernel); bench.py reports it as gpu_launches
+
+
 def check(rc):
+    global N_CALLS
+    N_CALLS += 1
     if rc != 0:
         raise D3DError(f"libdynam3d_b200 error {rc}: {lib().d3d_last_error().decode()}")
 

@@ -9,6 +9,9 @@ import torch
 from . import _lib as L
 
 
+GEMM_PROFILE = None  # set to a list to record (flops, start_event, end_event) per tensor-core GEMM launch (bench.py roofline)
+
+
 def gemm(a, w, out=None, bias=None, act=L.ACT_NONE, residual=None, out_dtype=None, simt=False):
     """out = epi(a @ w.T).  a [M,K], w [N,K] fp16/bf16 row-major; see d3d_gemm in include/dynam3d_b200.h."""
     assert a.is_cuda and w.is_cuda and a.dtype == w.dtype and a.dim() == 2 and w.dim() == 2
@@ -29,6 +32,13 @@ def gemm(a, w, out=None, bias=None, act=L.ACT_NONE, residual=None, out_dtype=Non
         L.kind_of(a.dtype), L.kind_of(out.dtype), L.ptr(bias), int(act),
         L.ptr(residual), residual.stride(0) if residual is not None else 0)
     fn = L.lib().d3d_gemm_simt if simt else L.lib().d3d_gemm
+    if GEMM_PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.check(fn(ctypes.cast(ctypes.byref(args), ctypes.c_void_p), L.stream_ptr()))
+        e1.record()
+        GEMM_PROFILE.append((2.0 * M * N * K, e0, e1))
+        return out
     L.check(fn(ctypes.cast(ctypes.byref(args), ctypes.c_void_p), L.stream_ptr()))
     return out
 

@@ -1,0 +1,326 @@
+"""B200-native `Dynam3D_VLN` / `Policy_Dynam3D_VLN`: one navigation step = CLIP patch encode -> 3D token memory
+update -> llava-phi-3-mini prefill -> next-action logits.
+
+Mirrors Dynam3D_VLN/vlnce_baselines/models/Policy_Dynam3D_VLN.py (= POL): same sub-module / parameter names
+(`feature_fields`, `patch_position_embedding`, `instance_position_embedding`, `zone_position_embedding`,
+`instance_projector`, `zone_projector`, `rgb_encoder`, `llava`), same `forward(...)` signature (POL:329), same prompt
+template and splice (POL:436,456), `get_gt_text` / `convert_text_to_action` (POL:294-326, 472-505).
+
+Differences that are deliberate and documented in DESIGN.md:
+  * weights come from state dicts handed to `load_*` (no network here: the reference downloads CLIP / LLaVA from hubs);
+  * FastSAM, the depth ResNet / waypoint predictor and the training branch (`is_train=True`) are SURVEY.md 8(f) "next" rows;
+    segmentation is an input (`observations['patch_segm']` or `feature_fields.segmenter`);
+  * Q13: for num_of_views > 1 the reference's splice is shape-inconsistent; the LLM sees the 576 patch tokens of view 0
+    plus all instance / zone tokens, and the prompt reserves exactly that many `<image>` slots.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import ops
+from .clip_vit import ViTEngine, ViTWeights
+from .feature_fields import Feature_Fields
+from .phi3 import LMEngine, LMWeights
+
+
+def _mlp_container(d_in, d_hidden, d_out):
+    return nn.Sequential(nn.Linear(d_in, d_hidden), nn.LayerNorm(d_hidden), nn.GELU(), nn.Linear(d_hidden, d_out))
+
+
+class CLIPEncoder(nn.Module):
+    """Drop-in for ENC:245-284: forward({'rgb': uint8 [N,H,W,3]}) -> (view_fts [N,768], grid_fts [N,576,768]) fp16."""
+
+    def __init__(self, model_name="ViT-L/14@336px", device="cuda", max_images=12):
+        super().__init__()
+        self.device = device
+        self.engine = None
+        self.max_images = max_images
+        self.is_blind = False
+
+    def load_openai_state_dict(self, sd, prefix="", n_head=16, resolution=336):
+        self.engine = ViTEngine(ViTWeights.from_openai_state_dict(sd, self.device, torch.float16, prefix), n_head, resolution, self.max_images)
+
+    def forward(self, observations, ln_post_on_patches=True):
+        if self.engine is None:
+            raise L.D3DLibraryError("CLIPEncoder has no weights: call load_openai_state_dict first")
+        rgb = observations["rgb"]
+        if not rgb.is_cuda:
+            rgb = rgb.to(self.device, non_blocking=True)
+        return self.engine.forward(rgb.contiguous(), ln_post_on_patches=ln_post_on_patches)
+
+
+class _Llava:
+    """Engine-side stand-in for LlavaForConditionalGeneration (POL:123-127): vision tower + projector + language model."""
+
+    def __init__(self):
+        self.tower = None
+        self.lm = None
+        self.proj = None
+
+    def load_state_dict(self, sd, device="cuda", lm_dtype=torch.float16, max_images=1, max_tokens=2048):
+        """Accepts HF llava keys: [model.]vision_tower.vision_model.*, [model.]multi_modal_projector.linear_{1,2}.*,
+        [model.]language_model.[model.]*, lm_head.weight (transformers 4.46 and 5.x layouts)."""
+        def find(suffix):
+            for k in sd:
+                if k.endswith(suffix):
+                    return k[: -len(suffix)]
+            raise KeyError(suffix)
+        vt = find("vision_model.embeddings.class_embedding")
+        self.tower = ViTEngine(ViTWeights.from_hf_clip_state_dict(sd, device, torch.float16, vt + "vision_model."), 16, 336, max_images)
+        pj = find("multi_modal_projector.linear_1.weight")
+        c16 = lambda t: t.detach().to(device=device, dtype=torch.float32).to(torch.float16).contiguous()
+        f32 = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()
+        self.proj = {"w1": c16(sd[pj + "multi_modal_projector.linear_1.weight"]), "b1": f32(sd[pj + "multi_modal_projector.linear_1.bias"]),
+                     "w2": c16(sd[pj + "multi_modal_projector.linear_2.weight"]), "b2": f32(sd[pj + "multi_modal_projector.linear_2.bias"])}
+        lm_prefix = find("embed_tokens.weight")
+        head = [k for k in sd if k.endswith("lm_head.weight")][0]
+        self.lm = LMEngine(LMWeights.from_state_dict(sd, device, lm_dtype, lm_prefix, head), n_heads=32, max_tokens=max_tokens)
+
+    def image_features(self, rgb_u8):
+        """get_image_features (POL:448-452): hidden_states[-2] of the tower without CLS -> linear_1 -> GELU -> linear_2; fp32 [N*576, 3072]."""
+        hid = self.tower.forward(rgb_u8, n_layers_run=len(self.tower.w.layers) - 1, project=False)  # [N, 577, 1024] fp32
+        N = hid.shape[0]
+        a16 = torch.empty((N * 576, hid.shape[2]), device=hid.device, dtype=torch.float16)
+        ops.cast16(hid[:, 1:].reshape(N * 576, hid.shape[2]), a16)
+        h = ops.gemm(a16, self.proj["w1"], bias=self.proj["b1"], act=L.ACT_GELU)
+        return ops.gemm(h, self.proj["w2"], bias=self.proj["b2"], out_dtype=torch.float32)
+
+
+class Dynam3D_VLN(nn.Module):
+    IMAGE_TOKEN = "<image>"
+
+    def __init__(self, observation_space=None, model_config=None, num_actions=None, device="cuda", q1_fix=False, q7_fix=False):
+        super().__init__()
+        self.device = torch.device(device)
+        self.q1_fix = q1_fix
+        self.feature_fields = Feature_Fields(batch_size=1, device=self.device, q7_fix=q7_fix)
+        width = 768
+        self.patch_position_embedding = _mlp_container(6, width * 4, width * 4)
+        self.instance_position_embedding = _mlp_container(3, width, width)
+        self.zone_position_embedding = _mlp_container(3, width, width)
+        self.instance_projector = _mlp_container(width * 2, width * 4, width * 4)
+        self.zone_projector = _mlp_container(width * 2, width * 4, width * 4)
+        for p in self.parameters():
+            p.requires_grad_(False)
+        self.rgb_encoder = CLIPEncoder("ViT-L/14@336px", self.device)
+        self.depth_encoder = None  # SURVEY.md 8(f) rank 3 (waypoint branch), not part of this step
+        self.llava = _Llava()
+        self.tokenize = None      # callable(str) -> list[int]; the real one is the llava-phi-3 tokenizer (POL:131)
+        self.detokenize = None    # callable(list[int]) -> str
+        self._PW = None
+
+    # -- properties the habitat `Net` interface expects (POL:159-169)
+    @property
+    def output_size(self):
+        return 1
+
+    @property
+    def is_blind(self):
+        return False
+
+    @property
+    def num_recurrent_layers(self):
+        return 1
+
+    def load_policy_state_dict(self, sd, strict=True):
+        """`net.*` keys of a trainer checkpoint that this module owns (feature_fields.*, *_embedding.*, *_projector.*)."""
+        own = {k: v for k, v in sd.items() if k.split(".")[0] in ("feature_fields", "patch_position_embedding", "instance_position_embedding",
+                                                                   "zone_position_embedding", "instance_projector", "zone_projector")}
+        ff = {k[len("feature_fields."):]: v for k, v in own.items() if k.startswith("feature_fields.")}
+        if ff:
+            self.feature_fields.load_state_dict(ff, strict=strict)
+        rest = {k: v for k, v in own.items() if not k.startswith("feature_fields.")}
+        missing = super().load_state_dict(rest, strict=False)
+        self._PW = None
+        return missing
+
+    def _policy_weights(self):
+        if self._PW is None:
+            dev = self.device
+            f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
+
+            def mlp(seq, kpad=None):
+                w0 = seq[0].weight.detach().float().cpu()
+                if kpad is not None and w0.shape[1] < kpad:
+                    w0 = torch.cat([w0, torch.zeros(w0.shape[0], kpad - w0.shape[1])], 1)
+                return {"w0": w0.to(dev).half().contiguous(), "b0": f32(seq[0].bias), "g": f32(seq[1].weight), "b": f32(seq[1].bias),
+                        "w3": seq[3].weight.detach().float().to(dev).half().contiguous(), "b3": f32(seq[3].bias)}
+            self._PW = {"patch_pos": mlp(self.patch_position_embedding, 8), "inst_pos": mlp(self.instance_position_embedding, 8),
+                        "zone_pos": mlp(self.zone_position_embedding, 8), "inst_proj": mlp(self.instance_projector),
+                        "zone_proj": mlp(self.zone_projector)}
+        return self._PW
+
+    # ------------------------------------------------------------------ POL:171-186 (kept for API parity; runs on device)
+    def preprocess_depth(self, depth, depth_scale=(0.0, 10.0)):
+        d = depth.to(self.device, dtype=torch.float32)
+        n = d.shape[0]
+        return ops.depth_preprocess(d.reshape(n, d.shape[1], d.shape[2]).contiguous(), depth_scale[0], depth_scale[1]).unsqueeze(-1)
+
+    # ------------------------------------------------------------------ POL:294-326 / 472-505 (host string logic)
+    def get_gt_text(self, target_angles, target_distances, stop_actions):
+        target_angles = [round(np.degrees(a)) for a in target_angles]
+        out = ["" for _ in target_angles]
+        aps, dps, mts = 15, 0.25, 4
+        ff = self.feature_fields
+        for b in range(len(target_angles)):
+            if stop_actions[b] == True:  # noqa: E712 (mirrors the reference comparison)
+                out[b] = "stop.<|end|>"
+            else:
+                ang, dist = target_angles[b], target_distances[b]
+                steps = round(ang / aps)
+                move = " move " + str(round(dist / dps)) + " steps.<|end|>"
+                if mts <= steps < 360 // aps:
+                    if steps < 180 // aps:
+                        out[b] = "turn left " + str(steps) + " steps," + move
+                        ff.keep_target_waypoint[b] = [(np.radians(ang - mts * aps) + math.pi * 2) % (math.pi * 2), dist]
+                    else:
+                        out[b] = "turn right " + str(round((360 - ang) / aps)) + " steps," + move
+                        ff.keep_target_waypoint[b] = [(np.radians(ang + mts * aps) + math.pi * 2) % (math.pi * 2), dist]
+                else:
+                    if steps < mts:
+                        out[b] = "turn left " + str(steps) + " steps," + move
+                    else:
+                        out[b] = "turn right " + str(round((360 - ang) / aps)) + " steps," + move
+                    ff.keep_target_waypoint[b] = None
+            h, n = ff.history_actions[b], len("turn left 4 steps")
+            if h[-2][:n] == out[b][:n] and h[-4][:n] == out[b][:n] and h[-3][:n] == out[-1][:n]:
+                out[b] = "error.<|end|>"
+        return out
+
+    def convert_text_to_action(self, generated_text):
+        aps, dps, mts = 15, 0.25, 4
+        acts = []
+        for txt in generated_text:
+            angle = distance = 0.0
+            if "stop" in txt or "error" in txt:
+                acts.append(-100)
+                continue
+            start = end = 0
+            if "left" in txt or "right" in txt:
+                word = "left" if "left" in txt else "right"
+                start, end = txt.find(word) + len(word), txt.find("steps,")
+                if end == -1:
+                    acts.append(-100)
+                    continue
+                turn = math.radians(min(mts, int(txt[start:end])) * aps)
+                angle = turn if word == "left" else math.pi * 2.0 - turn
+            if "move" in txt and int(txt[start:end]) < mts:
+                start, end = txt.find("move") + len("move"), txt.find("steps.")
+                distance = int(txt[start:end]) * dps
+            acts.append((angle, distance))
+        return acts
+
+    # ------------------------------------------------------------------ building blocks of forward
+    def _mlp(self, A0, m):
+        h = ops.gemm(A0, m["w0"], bias=m["b0"], out_dtype=torch.float32)
+        a16 = torch.empty(h.shape, device=h.device, dtype=torch.float16)
+        ops.layernorm(h, m["g"], m["b"], 1e-5, out16=a16, act=L.ACT_GELU)
+        return ops.gemm(a16, m["w3"], bias=m["b3"], out_dtype=torch.float32)
+
+    def _project_tokens(self, fts, rel, pos_mlp, proj_mlp):
+        """POL:434-435: projector(cat[fts, position_embedding(rel)]) -> fp32 [n, 3072]."""
+        n = fts.shape[0]
+        if n == 0:
+            return torch.zeros((0, 3072), device=self.device, dtype=torch.float32)
+        a = torch.empty((n, 8), device=self.device, dtype=torch.float16)
+        ops.pos3_rows(rel.contiguous(), a)
+        pe = self._mlp(a, pos_mlp)
+        cat = torch.empty((n, 1536), device=self.device, dtype=torch.float16)
+        ops.concat2_cast(fts.contiguous(), pe, cat)
+        return self._mlp(cat, proj_mlp)
+
+    def build_prompt(self, n_image_tokens, instruction, history):
+        return ("<|user|>\n" + self.IMAGE_TOKEN * n_image_tokens + "\nInstruction:\n" + instruction + "\nHistory actions:\n" + "".join(history) +
+                "<|end|>\n<|assistant|>\nNext action:\n")
+
+    def encode_step(self, observations, agent_positions, agent_heading_angles, depth_scale=(0.0, 10.0), delete_old_features=True, num_of_views=1):
+        """Stages a1-a14 (POL:336-363, 432-435): returns per-episode projected tokens (patch, instance, zone), all fp32 [*, 3072]."""
+        ff = self.feature_fields
+        B, V = ff.batch_size, num_of_views
+        P = ff.args.input_height * ff.args.input_width
+        dev = self.device
+        depth = observations["depth"]
+        depth = depth.to(dev, dtype=torch.float32, non_blocking=True)
+        n_img, H, W = depth.shape[0], depth.shape[1], depth.shape[2]
+        depth = depth.reshape(n_img, H, W).contiguous()
+        rgb = observations["rgb"].to(dev, non_blocking=True).contiguous()
+        d576 = ops.depth_patch_grid(depth, B, V, ff.args.input_height, ff.args.input_width, literal_q1=not self.q1_fix)  # POL:336-341
+        _, grid = self.rgb_encoder({"rgb": rgb})  # POL:343-345, stays on device
+        if delete_old_features:
+            full = ops.depth_preprocess(depth, depth_scale[0], depth_scale[1]).view(B, V, H, W)  # POL:350
+            ff.delete_old_features_from_camera_frustum(full, agent_positions, agent_heading_angles, num_of_views=V)
+        segm = observations.get("patch_segm") if hasattr(observations, "get") else None
+        ff.update_feature_fields(d576.view(B, V, P), grid.reshape(B, V, P, 768), batch_image=rgb, batch_position=agent_positions,
+                                 batch_heading=agent_heading_angles, num_of_views=V, batch_patch_segm=segm)
+        env = ff.get_environment_features(agent_positions, agent_heading_angles)
+        info5 = ops.patch_3d_info(d576, ff.args.input_hfov, ff.args.input_vfov, ff.args.input_width, ff.args.input_height)
+        PW = self._policy_weights()
+        # patch tokens of the view the LLM sees (Q13: view 0 of every episode)
+        sel = torch.arange(B, device=dev) * V
+        rows = torch.empty((B * P, 8), device=dev, dtype=torch.float16)
+        ops.patch_info_rows(info5[:, sel].contiguous(), rows)
+        patch_pos = self._mlp(rows, PW["patch_pos"])  # POL:432-433
+        patch = self.llava.image_features(rgb[sel].contiguous())  # POL:448-452
+        ops.add_inplace(patch, patch_pos)  # POL:453
+        inst = [self._project_tokens(env["batch_instance_fts"][b], env["batch_instance_relative_position"][b], PW["inst_pos"], PW["inst_proj"])
+                for b in range(B)]
+        zone = [self._project_tokens(env["batch_zone_fts"][b], env["batch_zone_relative_position"][b], PW["zone_pos"], PW["zone_proj"])
+                for b in range(B)]
+        return patch.view(B, P, 3072), inst, zone
+
+    def forward_logits(self, observations, instructions, agent_positions, agent_heading_angles, depth_scale=(0.0, 10.0),
+                       delete_old_features=True, num_of_views=1, input_ids=None):
+        """The measured hot path: stages a1-a16 up to the next-action logits [B, vocab] (prefill of POL:463)."""
+        ff = self.feature_fields
+        B = ff.batch_size
+        patch, inst, zone = self.encode_step(observations, agent_positions, agent_heading_angles, depth_scale, delete_old_features, num_of_views)
+        lm = self.llava.lm
+        seqs, lens = [], []
+        for b in range(B):
+            n_img = patch.shape[1] + inst[b].shape[0] + zone[b].shape[0]
+            if input_ids is not None:
+                ids = list(input_ids[b])
+            else:
+                if self.tokenize is None:
+                    raise RuntimeError("no tokenizer: set .tokenize or pass input_ids (prompt ids with n_img image slots after 2 tokens)")
+                ids = self.tokenize(self.build_prompt(n_img, instructions[b], ff.history_actions[b]))
+            ids = torch.tensor(ids, dtype=torch.int32)
+            head, tail = ids[:2], ids[n_img + 2:]  # POL:456 literal splice
+            eh = torch.empty((len(head), lm.w.hidden), device=self.device, dtype=torch.float32)
+            et = torch.empty((len(tail), lm.w.hidden), device=self.device, dtype=torch.float32)
+            lm.embed(head.to(self.device), eh)
+            lm.embed(tail.to(self.device), et)
+            seqs += [eh, patch[b], inst[b], zone[b], et]
+            lens.append(len(head) + n_img + len(tail))
+        X = torch.cat(seqs, 0)
+        cu = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int32, device=self.device)
+        pos = torch.cat([torch.arange(n, dtype=torch.int32) for n in lens]).to(self.device)
+        last = (cu[1:] - 1).to(torch.int32).contiguous()
+        self.last_seq_lens = lens
+        return lm.prefill(X, cu, pos, B, max(lens), last)
+
+    def forward(self, observations, instructions, agent_positions, agent_heading_angles, depth_scale=(0.0, 10.0), gt_text=None,
+                delete_old_features=True, num_of_views=1, is_train=False, input_ids=None, return_logits=False):
+        if is_train:
+            raise NotImplementedError("training branch (POL:366-427) is a SURVEY.md 8(f) 'next' row")
+        logits = self.forward_logits(observations, instructions, agent_positions, agent_heading_angles, depth_scale, delete_old_features,
+                                     num_of_views, input_ids)
+        if return_logits or self.detokenize is None:
+            return logits
+        raise NotImplementedError("greedy decode with KV cache (POL:463-469) is the next SURVEY.md 8(f) row; use return_logits=True")
+
+
+class Policy_Dynam3D_VLN(nn.Module):
+    """Same shape as the registered policy (POL:34-63): `.net` is the step module, `from_config` builds it."""
+
+    def __init__(self, observation_space=None, action_space=None, model_config=None, **kw):
+        super().__init__()
+        self.net = Dynam3D_VLN(observation_space, model_config, getattr(action_space, "n", None), **kw)
+        self.dim_actions = getattr(action_space, "n", None)
+
+    @classmethod
+    def from_config(cls, config=None, observation_space=None, action_space=None, **kw):
+        return cls(observation_space, action_space, getattr(config, "MODEL", None), **kw)

@@ -193,3 +193,102 @@ def lm_state_dict(seed, hidden=3072, layers=32, ffn=8192, vocab=32064, device="c
         sd[p + "mlp.up_proj.weight"] = r(_u((ffn, hidden), b + 9, 0.02, device))
         sd[p + "mlp.down_proj.weight"] = r(_u((hidden, ffn), b + 10, 0.02, device))
     return sd
+
+
+def llava_state_dict(seed, clip_layers=24, lm_layers=32, device="cpu", lm_round_to=None, clip_width=1024, lm_hidden=3072, lm_ffn=8192,
+                     vocab=32064):
+    """HF-llava-style state dict (vision_tower.vision_model.*, multi_modal_projector.*, language_model.*) with random init."""
+    import torch
+    ov = vit_state_dict(seed + 1, width=clip_width, layers=clip_layers, device=device)
+    sd = {}
+    p = "vision_tower.vision_model."
+    sd[p + "embeddings.patch_embedding.weight"] = ov["conv1.weight"]
+    sd[p + "embeddings.class_embedding"] = ov["class_embedding"]
+    sd[p + "embeddings.position_embedding.weight"] = ov["positional_embedding"]
+    sd[p + "pre_layrnorm.weight"], sd[p + "pre_layrnorm.bias"] = ov["ln_pre.weight"], ov["ln_pre.bias"]
+    sd[p + "post_layernorm.weight"], sd[p + "post_layernorm.bias"] = ov["ln_post.weight"], ov["ln_post.bias"]
+    for l in range(clip_layers):
+        s, d = f"transformer.resblocks.{l}.", p + f"encoder.layers.{l}."
+        sd[d + "layer_norm1.weight"], sd[d + "layer_norm1.bias"] = ov[s + "ln_1.weight"], ov[s + "ln_1.bias"]
+        sd[d + "layer_norm2.weight"], sd[d + "layer_norm2.bias"] = ov[s + "ln_2.weight"], ov[s + "ln_2.bias"]
+        w, b = ov[s + "attn.in_proj_weight"], ov[s + "attn.in_proj_bias"]
+        for i, n in enumerate("qkv"):
+            sd[d + f"self_attn.{n}_proj.weight"] = w[i * clip_width:(i + 1) * clip_width].clone()
+            sd[d + f"self_attn.{n}_proj.bias"] = b[i * clip_width:(i + 1) * clip_width].clone()
+        sd[d + "self_attn.out_proj.weight"], sd[d + "self_attn.out_proj.bias"] = ov[s + "attn.out_proj.weight"], ov[s + "attn.out_proj.bias"]
+        sd[d + "mlp.fc1.weight"], sd[d + "mlp.fc1.bias"] = ov[s + "mlp.c_fc.weight"], ov[s + "mlp.c_fc.bias"]
+        sd[d + "mlp.fc2.weight"], sd[d + "mlp.fc2.bias"] = ov[s + "mlp.c_proj.weight"], ov[s + "mlp.c_proj.bias"]
+    r16 = lambda t: t.to(torch.float16).to(torch.float32)
+    s0 = seed * 7919
+    sd["multi_modal_projector.linear_1.weight"] = r16(_u((lm_hidden, clip_width), s0 + 1, clip_width ** -0.5, device))
+    sd["multi_modal_projector.linear_1.bias"] = _u((lm_hidden,), s0 + 2, 0.02, device)
+    sd["multi_modal_projector.linear_2.weight"] = r16(_u((lm_hidden, lm_hidden), s0 + 3, lm_hidden ** -0.5, device))
+    sd["multi_modal_projector.linear_2.bias"] = _u((lm_hidden,), s0 + 4, 0.02, device)
+    for k, v in lm_state_dict(seed + 2, lm_hidden, lm_layers, lm_ffn, vocab, device, lm_round_to).items():
+        sd["language_model." + k] = v
+    return sd
+
+
+def policy_state_dict(seed, merge_bias=0.0):
+    """Reference-named policy parameters (feature_fields.* + the five projection MLPs, POL:79-111), PyTorch-like init scales."""
+    import torch
+    import torch.nn as nn
+    w = 768
+    enc_layer = nn.TransformerEncoderLayer(d_model=w, nhead=12, dim_feedforward=4 * w, batch_first=True)
+
+    def mlp(i, h, o):
+        return nn.Sequential(nn.Linear(i, h), nn.LayerNorm(h), nn.GELU(), nn.Linear(h, o))
+    shapes = {}
+    ff = nn.ModuleDict({
+        "patch_to_instance_position_embedding": mlp(7, w, w),
+        "aggregate_patch_to_instance_encoder": nn.TransformerEncoder(enc_layer, 2, norm=nn.LayerNorm(w, eps=1e-12), enable_nested_tensor=False),
+        "instance_to_zone_position_embedding": mlp(4, w, w),
+        "aggregate_instance_to_zone_encoder": nn.TransformerEncoder(enc_layer, 2, norm=nn.LayerNorm(w, eps=1e-12), enable_nested_tensor=False),
+        "instance_merge_discriminator": mlp(2 * w + 3, 4 * w, 2)})
+    for k, v in ff.state_dict().items():
+        shapes["feature_fields." + k] = tuple(v.shape)
+    shapes["feature_fields.aggregate_patch_to_instance_embedding"] = (1, w)
+    shapes["feature_fields.aggregate_instance_to_zone_embedding"] = (1, w)
+    for name, m in (("patch_position_embedding", mlp(6, 4 * w, 4 * w)), ("instance_position_embedding", mlp(3, w, w)),
+                    ("zone_position_embedding", mlp(3, w, w)), ("instance_projector", mlp(2 * w, 4 * w, 4 * w)),
+                    ("zone_projector", mlp(2 * w, 4 * w, 4 * w))):
+        for k, v in m.state_dict().items():
+            shapes[name + "." + k] = tuple(v.shape)
+    sd = {}
+    for i, (k, shp) in enumerate(sorted(shapes.items())):
+        if len(shp) >= 2:
+            sd[k] = hash_uniform(shp, seed * 1000 + i, scale=shp[-1] ** -0.5)
+        elif ("norm" in k and k.endswith("weight")) or k.endswith(".1.weight"):
+            sd[k] = 1.0 + hash_uniform(shp, seed * 1000 + i, scale=0.05)
+        else:
+            sd[k] = hash_uniform(shp, seed * 1000 + i, scale=0.05)
+    sd["feature_fields.instance_merge_discriminator.3.bias"] = sd["feature_fields.instance_merge_discriminator.3.bias"] + torch.tensor([0.0, merge_bias])
+    return sd
+
+
+class ToyTokenizer:
+    """Stand-in for the llava-phi-3 tokenizer (not available offline): special tokens are single ids, other text is one id
+    per character.  Only the SHAPE of the prompt matters for the hot path (ids index a random embedding table)."""
+    SPECIAL = {"<|user|>": 32010, "<|end|>": 32007, "<|assistant|>": 32001, "<image>": 32038}
+
+    def __call__(self, text):
+        ids, i = [1], 0  # BOS like LlamaTokenizer
+        while i < len(text):
+            for tok, tid in self.SPECIAL.items():
+                if text.startswith(tok, i):
+                    ids.append(tid)
+                    i += len(tok)
+                    break
+            else:
+                ids.append(3 + (ord(text[i]) * 131) % 31990)
+                i += 1
+        return ids
+
+
+def make_instruction(seed, n_chars=64):
+    rng = np.random.default_rng(seed)
+    words = ["walk", "past", "the", "table", "turn", "left", "right", "at", "door", "stop", "near", "sofa", "exit", "hall"]
+    s = ""
+    while len(s) < n_chars:
+        s += words[int(rng.integers(len(words)))] + " "
+    return s[:n_chars]
