@@ -1,0 +1,155 @@
+"""TEST INFRASTRUCTURE ONLY -- writes tests/golden/*.npz by running the UNMODIFIED reference (via ref_shim) in this container.
+
+    python -m oracle.make_golden
+
+The fixtures let the CPU suite and the GPU box (where /root/reference does not exist) check the oracle AND the CUDA engine
+against outputs of the reference itself:
+  * ff_traj_<name>.npz   -- per-step discrete state of the reference `Feature_Fields` (patch->instance map, member lists,
+                            dict orders, zone keys/ids, tombstones) + exported token tensors, with the exact inputs.
+  * geometry.npz         -- project_depth_to_3d_habitat / get_patch_3d_info / frustum-mask vectors of the reference functions.
+  * vit_small.npz        -- reference `VisionTransformer` (VLN and Pretrain variants) outputs on a seeded small config.
+"""
+import json
+import os
+
+import numpy as np
+import torch
+
+from dynam3d_b200 import synth
+from . import geometry as G
+from . import ref_compare as RC
+from . import ref_shim
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+FF_CONFIGS = {
+    "v1_seg16": dict(seed=3, n_steps=5, num_views=1, n_seg=16, seg_kind="voronoi", merge_bias=0.3, weight_seed=0),
+    "v1_seg48": dict(seed=5, n_steps=8, num_views=1, n_seg=48, seg_kind="blocks", merge_bias=0.3, weight_seed=0),
+    "v12_seg16": dict(seed=6, n_steps=2, num_views=12, n_seg=16, seg_kind="voronoi", merge_bias=0.3, weight_seed=0),
+}
+
+
+def pack_snapshot(prefix, snap, out):
+    out[prefix + "n"] = np.array([snap["n_patches"], snap["n_inst_slots"], snap["n_zone_slots"]], np.int64)
+    p2i = np.array(sorted(snap["p2i"].items()), np.int64).reshape(-1, 2)
+    out[prefix + "p2i"] = p2i
+    out[prefix + "i2p_order"] = np.array(snap["i2p_order"], np.int64)
+    out[prefix + "i2p_len"] = np.array([len(snap["i2p"][k]) for k in snap["i2p_order"]], np.int64)
+    out[prefix + "i2p_cat"] = np.concatenate([np.asarray(snap["i2p"][k], np.int64) for k in snap["i2p_order"]] + [np.zeros(0, np.int64)])
+    out[prefix + "z2i_order"] = np.array(snap["z2i_order"], np.int64)
+    out[prefix + "z2i_len"] = np.array([len(snap["z2i"][k]) for k in snap["z2i_order"]], np.int64)
+    out[prefix + "z2i_cat"] = np.concatenate([np.asarray(snap["z2i"][k], np.int64) for k in snap["z2i_order"]] + [np.zeros(0, np.int64)])
+    keys = sorted(snap["zone_key_to_id"].items(), key=lambda kv: kv[1])
+    out[prefix + "zone_keys"] = np.array([list(k) for k, _ in keys], np.float32).reshape(-1, 3)
+    out[prefix + "zone_ids"] = np.array([v for _, v in keys], np.int64)
+    out[prefix + "tomb"] = np.packbits(snap["patch_tomb"])
+
+
+def unpack_snapshot(prefix, z):
+    n = z[prefix + "n"]
+    i2p, off = {}, 0
+    for k, ln in zip(z[prefix + "i2p_order"].tolist(), z[prefix + "i2p_len"].tolist()):
+        i2p[k] = z[prefix + "i2p_cat"][off:off + ln]
+        off += ln
+    z2i, off = {}, 0
+    for k, ln in zip(z[prefix + "z2i_order"].tolist(), z[prefix + "z2i_len"].tolist()):
+        z2i[k] = z[prefix + "z2i_cat"][off:off + ln]
+        off += ln
+    return {"n_patches": int(n[0]), "n_inst_slots": int(n[1]), "n_zone_slots": int(n[2]),
+            "p2i": {int(a): int(b) for a, b in z[prefix + "p2i"]}, "i2p": i2p, "i2p_order": z[prefix + "i2p_order"].tolist(),
+            "z2i": z2i, "z2i_order": z[prefix + "z2i_order"].tolist(),
+            "zone_key_to_id": {tuple(float(x) for x in k): int(v) for k, v in zip(z[prefix + "zone_keys"], z[prefix + "zone_ids"])},
+            "patch_tomb": np.unpackbits(z[prefix + "tomb"])[: int(n[0])].astype(bool)}
+
+
+def make_ff():
+    for name, cfg in FF_CONFIGS.items():
+        steps = RC.make_inputs(cfg["seed"], cfg["n_steps"], cfg["num_views"], cfg["n_seg"], cfg["seg_kind"])
+        ff, orc, recs = RC.run_pair(**cfg, steps=steps)
+        out = {"config": np.frombuffer(json.dumps(cfg).encode(), np.uint8)}
+        for t, (r, st) in enumerate(zip(recs, steps)):
+            assert RC.snapshots_equal(r["ref"], r["orc"]) == []
+            # inputs (depth is quantised to 1/4096 by synth -> exact as uint16); grid features / weights are hash-generated
+            q = np.round(st["depth"][..., 0] * 4096.0)
+            assert np.array_equal((q / 4096.0).astype(np.float32), st["depth"][..., 0])
+            out[f"s{t}_depth_u16"] = q.astype(np.uint16)
+            out[f"s{t}_segm"] = np.asarray(st["segm"]).astype(np.uint16)
+            out[f"s{t}_pose"] = np.array(list(st["position"]) + [st["heading"]], np.float64)
+            pack_snapshot(f"s{t}_", r["ref"], out)
+            e = r["env_ref"]
+            out[f"s{t}_inst_rel"] = e["batch_instance_relative_position"][0].numpy()
+            out[f"s{t}_zone_rel"] = e["batch_zone_relative_position"][0].numpy()
+            out[f"s{t}_inst_fts_sum"] = e["batch_instance_fts"][0].numpy().sum(-1)  # per-token checksums keep the file small
+            out[f"s{t}_zone_fts_sum"] = e["batch_zone_fts"][0].numpy().sum(-1)
+            if r["knn"] is not None:
+                out[f"s{t}_knn_idx"], out[f"s{t}_knn_d2"] = r["knn"][1], r["knn"][0]
+                out[f"s{t}_merge"] = r["merge"][0].astype(np.uint8)
+                lg = r["merge"][1]
+                out[f"s{t}_margin"] = np.array([np.abs(lg[..., 1] - lg[..., 0]).min() if lg.size else 1.0])
+        np.savez_compressed(os.path.join(OUT, f"ff_traj_{name}.npz"), **out)
+        print("wrote", name, len(recs), "steps", "min margin", min(float(out[k][0]) for k in out if k.endswith("_margin")))
+
+
+def load_ff_fixture(path):
+    """-> (cfg, steps (inputs), golden per-step dicts)."""
+    z = np.load(path)
+    cfg = json.loads(bytes(z["config"]).decode())
+    steps, gold = [], []
+    for t in range(cfg["n_steps"]):
+        pose = z[f"s{t}_pose"]
+        st = {"depth": (z[f"s{t}_depth_u16"].astype(np.float32) / np.float32(4096.0))[..., None], "segm": z[f"s{t}_segm"].astype(np.int64),
+              "position": pose[:3].astype(np.float32), "heading": float(pose[3]),
+              "grid": synth.hash_uniform((1, cfg["num_views"], 576, 768), cfg["seed"] * 100 + t, 0.9).numpy().astype(np.float16)}
+        steps.append(st)
+        g = {"snap": unpack_snapshot(f"s{t}_", z)}
+        for k in ("inst_rel", "zone_rel", "inst_fts_sum", "zone_fts_sum", "knn_idx", "knn_d2", "merge"):
+            if f"s{t}_{k}" in z:
+                g[k] = z[f"s{t}_{k}"]
+        gold.append(g)
+    return cfg, steps, gold
+
+
+def make_geometry():
+    mod = ref_shim.load_reference_feature_fields_module()
+    ff = ref_shim.make_reference_feature_fields()
+    rng = np.random.default_rng(0)
+    depth = rng.uniform(0.1, 10, size=(4, 576)).astype(np.float32)
+    headings = np.array([0.3, 2.0, 4.0, 6.2])
+    out = {"depth": depth, "headings": headings}
+    for i, h in enumerate(headings):
+        rx, ry, rz, d, s = ff.project_depth_to_3d_habitat(depth[i:i + 1], float(h))
+        out[f"unproj{i}"] = np.stack([rx[0], ry[0], rz[0], d, s]).astype(np.float32)
+    info = ff.get_patch_3d_info(depth)
+    out["info5"] = np.stack([a[..., 0].numpy() for a in info])
+    pts = rng.uniform(-5, 5, size=(20000, 3)).astype(np.float32)
+    dimg = (np.round(rng.uniform(0.5, 6, size=(256, 256)) * 64) / 64).astype(np.float32)
+    cam = np.array([0.5, -0.25, 1.25], np.float32)
+    m, dep, u, v = mod.get_frustum_mask_habitat(torch.from_numpy(pts), 256, 256, 90.0, 90.0, cam, 1.1, far=3.0)
+    m = m & (dep < torch.from_numpy(dimg)[v % 256, u % 256] + 0.1)
+    out.update(cull_pts=pts, cull_depth=dimg.astype(np.float16), cull_cam=cam, cull_heading=np.array([1.1]), cull_mask=np.packbits(m.numpy()))
+    np.savez_compressed(os.path.join(OUT, "geometry.npz"), **out)
+    print("wrote geometry")
+
+
+def make_vit():
+    out = {}
+    width, layers, heads, res, od = 256, 3, 4, 112, 128
+    sd = synth.vit_state_dict(9, width=width, layers=layers, resolution=res, out_dim=od)
+    x = synth.hash_uniform((2, 3, res, res), 77, 2.0)
+    for pre in (False, True):
+        mod = ref_shim.load_reference_clip_model_module(pretrain=pre)
+        vit = mod.VisionTransformer(res, 14, width, layers, heads, od).eval()
+        vit.load_state_dict(sd, strict=True)
+        with torch.no_grad():
+            c, p = vit(x)
+        out["cls_pre" if pre else "cls"] = c.numpy()
+        out["patch_pre" if pre else "patch"] = p.numpy()
+    np.savez_compressed(os.path.join(OUT, "vit_small.npz"), **out)
+    print("wrote vit_small")
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    make_geometry()
+    make_vit()
+    make_ff()

@@ -60,36 +60,55 @@ def snapshots_equal(a, b):
     return problems
 
 
-def run_pair(seed=1, n_steps=4, num_views=1, n_seg=16, seg_kind="blocks", merge_bias=0.0, q1_fix=False, weight_seed=0):
+def make_inputs(seed, n_steps, num_views, n_seg, seg_kind, depth_size=256):
+    """Deterministic step inputs: synthetic episode + hash-generated CLIP grid features (fp16)."""
+    steps = synth.make_episode(seed, n_steps=n_steps, num_views=num_views, n_seg=n_seg, seg_kind=seg_kind, depth_size=depth_size)
+    for t, st in enumerate(steps):
+        st["grid"] = synth.hash_uniform((1, num_views, 576, 768), seed * 100 + t, 0.9).numpy().astype(np.float16)
+    return steps
+
+
+def ff_params(weight_seed, merge_bias):
+    sd = synth.policy_state_dict(weight_seed, merge_bias)
+    return {k[len("feature_fields."):]: v for k, v in sd.items() if k.startswith("feature_fields.")}
+
+
+def run_pair(seed=1, n_steps=4, num_views=1, n_seg=16, seg_kind="blocks", merge_bias=0.0, q1_fix=False, weight_seed=0, steps=None,
+             with_reference=True):
     """Returns (reference ff, oracle, per-step records).  Each record: snapshots + exported env tokens of both."""
-    ff = ref_shim.make_reference_feature_fields(batch_size=1, seed=weight_seed)
-    params = tune_discriminator({k: v.detach().clone() for k, v in ff.state_dict().items()}, merge_bias)
-    ff.load_state_dict(params, strict=True)
+    params = ff_params(weight_seed, merge_bias)
+    ff = None
+    if with_reference:
+        ff = ref_shim.make_reference_feature_fields(batch_size=1, seed=weight_seed)
+        ff.load_state_dict(params, strict=True)
+        ff.reset(1)
+        ff.initialize_camera_setting(90.0, 90.0)
     orc = FeatureFieldsOracle(params, batch_size=1, rnd=None)
-    ff.reset(1)
-    ff.initialize_camera_setting(90.0, 90.0)
     orc.initialize_camera_setting(90.0, 90.0)
-    steps = synth.make_episode(seed, n_steps=n_steps, num_views=num_views, n_seg=n_seg, seg_kind=seg_kind)
-    rng = np.random.default_rng(seed + 77)
+    if steps is None:
+        steps = make_inputs(seed, n_steps, num_views, n_seg, seg_kind)
     records = []
     for st in steps:
         V = num_views
-        grid = (rng.standard_normal((1, V, 576, 768)) * 0.5).astype(np.float16)
+        grid = st["grid"]
         obs_depth = st["depth"]  # [V,H,W,1]
         d576 = G.depth_patch_grid(obs_depth, 1, V, q1_fix=q1_fix)  # [1,V,576]
         full = G.preprocess_depth(obs_depth, (0.0, 10.0)).reshape(1, V, obs_depth.shape[1], obs_depth.shape[2])
-        pos = [st["position"].astype(np.float32)]
-        head = [st["heading"]]
-        segm = torch.from_numpy(st["segm"]).view(V, 1, 24, 24)
-        ref_shim.attach_segmentation(ff, lambda img, s=segm: s)
-        with torch.no_grad():
-            ff.delete_old_features_from_camera_frustum(torch.from_numpy(full), pos, head, num_of_views=V)
-            ff.update_feature_fields(d576.copy(), grid.astype(np.float32), batch_image=np.zeros((1, V, 4, 4, 3), np.uint8),
-                                     batch_position=pos, batch_heading=head, num_of_views=V)
-            env_ref = ff.get_environment_features(pos, head)
+        pos = [np.asarray(st["position"], np.float32)]
+        head = [float(st["heading"])]
+        rec = {}
+        if with_reference:
+            segm = torch.from_numpy(np.asarray(st["segm"])).view(V, 1, 24, 24)
+            ref_shim.attach_segmentation(ff, lambda img, s=segm: s)
+            with torch.no_grad():
+                ff.delete_old_features_from_camera_frustum(torch.from_numpy(full), pos, head, num_of_views=V)
+                ff.update_feature_fields(d576.copy(), grid.astype(np.float32), batch_image=np.zeros((1, V, 4, 4, 3), np.uint8),
+                                         batch_position=pos, batch_heading=head, num_of_views=V)
+                rec["env_ref"] = ff.get_environment_features(pos, head)
+            rec["ref"] = reference_snapshot(ff)
         orc.delete_old_features_from_camera_frustum(full, pos, head, num_of_views=V)
-        orc.update_feature_fields(d576, grid, st["segm"][None], pos, head, num_of_views=V)
-        env_orc = orc.get_environment_features(pos, head)
-        records.append({"ref": reference_snapshot(ff), "orc": orc.snapshot(), "env_ref": env_ref, "env_orc": env_orc,
-                        "knn": orc.eps[0].last_knn, "merge": getattr(orc.eps[0], "last_merge", None)})
+        orc.update_feature_fields(d576, grid, np.asarray(st["segm"])[None], pos, head, num_of_views=V)
+        rec.update({"orc": orc.snapshot(), "env_orc": orc.get_environment_features(pos, head), "knn": orc.eps[0].last_knn,
+                    "merge": getattr(orc.eps[0], "last_merge", None)})
+        records.append(rec)
     return ff, orc, records
