@@ -225,12 +225,16 @@ def run_engine(args):
     ops.GEMM_PROFILE = []
     calls0 = L.N_CALLS
     barrier()
+    if args.profile_range:
+        torch.cuda.profiler.start()  # ncu --profile-from-start off: only the timed steps are captured
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.warmup, args.warmup + args.steps):
         one_step(i, dev_in)
     e1.record()
     barrier()
+    if args.profile_range:
+        torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1)
     launches = L.N_CALLS - calls0
     prof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
@@ -295,6 +299,7 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--episodes", type=int, default=EPISODES_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-range", action="store_true", help="cudaProfilerStart/Stop around the timed region (for ncu)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

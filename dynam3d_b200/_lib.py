@@ -67,6 +67,10 @@ SIGNATURES = {
     "d3d_patch_info_rows": [_P, _L, _P, _I, _P],
     "d3d_concat2_cast": [_P, _P, _I, _I, _P, _I, _P],
     "d3d_pos3_rows": [_P, _I, _P, _I, _P],
+    "d3d_copy_blocks": [_P, _P, _P, _I, _P],
+    "d3d_scatter_rows_ptr": [_P, _L, _P, _P, _I, _I, _P],
+    "d3d_knn2_batched": [_P, _P, _P, _I, _P, _P, _P],
+    "d3d_disc_input_batched": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P],
 }
 OPTIONAL = set()
 
@@ -111,9 +115,31 @@ def require_device(dev=0):
     check(lib().d3d_check_device(int(dev)))
 
 
+_STREAM = None  # cached stream handle inside `stream_scope()` (torch.cuda.current_stream() costs ~15 us per query)
+
+
 def stream_ptr():
+    if _STREAM is not None:
+        return _STREAM
     import torch
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class stream_scope:
+    """Caches the current stream for the duration of a host-side hot loop; nests; do not switch streams inside."""
+
+    def __enter__(self):
+        global _STREAM
+        import torch
+        self.prev = _STREAM
+        if _STREAM is None:
+            _STREAM = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        return self
+
+    def __exit__(self, *a):
+        global _STREAM
+        _STREAM = self.prev
+        return False
 
 
 def ptr(t):

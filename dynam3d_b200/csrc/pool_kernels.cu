@@ -164,3 +164,133 @@ extern "C" int d3d_pos3_rows(const float* x, int n, void* out16, int kind, void*
   D3D_CHECK_LAUNCH();
   return 0;
 }
+
+// ================================================================================================
+// batched (pointer-table) variants: one launch serves every episode of the rank
+// ================================================================================================
+namespace {
+
+// copy n independent byte blocks (16-byte aligned, sizes multiple of 16): grid (chunks, n)
+__global__ void copy_blocks_kernel(const long long* __restrict__ src, const long long* __restrict__ dst, const long long* __restrict__ nbytes) {
+  const int b = blockIdx.y;
+  const uint4* s = reinterpret_cast<const uint4*>(src[b]);
+  uint4* d = reinterpret_cast<uint4*>(dst[b]);
+  const long long n16 = nbytes[b] >> 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x) d[i] = s[i];
+}
+
+// dst_row[r] (absolute row address) <- src[src_idx ? src_idx[r] : r], fp32 rows of width D
+__global__ void scatter_rows_ptr_kernel(const float* __restrict__ src, long long lds, const int* __restrict__ src_idx,
+                                        const long long* __restrict__ dst_row, int n, int D) {
+  const int r = blockIdx.x;
+  if (r >= n) return;
+  const long long s = src_idx ? src_idx[r] : r;
+  float* d = reinterpret_cast<float*>(dst_row[r]);
+  for (int c = threadIdx.x; c < D; c += blockDim.x) d[c] = src[s * lds + c];
+}
+
+__device__ __forceinline__ float dist2b(float qx, float qy, float qz, float rx, float ry, float rz) {
+  const float dx = __fsub_rn(qx, rx), dy = __fsub_rn(qy, ry), dz = __fsub_rn(qz, rz);
+  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// K = 2 nearest per query, each query with its own reference set (its episode's instance slots); one warp per query.
+// Same arithmetic and (d2, index) lexicographic order as knn_warp_kernel.  Missing neighbours (n_ref < 2): d2 = +inf, idx = -1.
+__global__ void __launch_bounds__(128) knn2_batched_kernel(const long long* __restrict__ ref_ptr, const int* __restrict__ n_ref,
+                                                           const float* __restrict__ qry, int n_q, float* __restrict__ out_d,
+                                                           int* __restrict__ out_i) {
+  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (q >= n_q) return;
+  const float* refs = reinterpret_cast<const float*>(ref_ptr[q]);
+  const int n = n_ref[q];
+  const float qx = qry[(size_t)q * 3], qy = qry[(size_t)q * 3 + 1], qz = qry[(size_t)q * 3 + 2];
+  float d0 = INFINITY, d1 = INFINITY;
+  int i0 = 0x7fffffff, i1 = 0x7fffffff;
+  for (int r = lane; r < n; r += 32) {
+    const float d = dist2b(qx, qy, qz, refs[(size_t)r * 3], refs[(size_t)r * 3 + 1], refs[(size_t)r * 3 + 2]);
+    if (d < d0 || (d == d0 && r < i0)) { d1 = d0; i1 = i0; d0 = d; i0 = r; }
+    else if (d < d1 || (d == d1 && r < i1)) { d1 = d; i1 = r; }
+  }
+  for (int j = 0; j < 2; ++j) {
+    unsigned long long key = ((unsigned long long)__float_as_uint(d0) << 32) | (unsigned)i0;
+    unsigned long long best = key;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+      best = other < best ? other : best;
+    }
+    if (lane == 0) {
+      const int bi = (int)(best & 0xffffffffu);
+      out_d[(size_t)q * 2 + j] = __uint_as_float((unsigned)(best >> 32));
+      out_i[(size_t)q * 2 + j] = bi == 0x7fffffff ? -1 : bi;
+    }
+    if (key == best) { d0 = d1; i0 = i1; d1 = INFINITY; i1 = 0x7fffffff; }
+  }
+}
+
+// batched discriminator rows: row (q, j) for j < K from per-query instance pools; idx < 0 -> zero row
+__global__ void disc_input_batched_kernel(const long long* __restrict__ fts_ptr, const long long* __restrict__ pos_ptr,
+                                          const int* __restrict__ idx, const float* __restrict__ view_fts, const float* __restrict__ centre,
+                                          int Q, int K, int D, int ldo, void* __restrict__ out, int kind) {
+  const int r = blockIdx.x;
+  if (r >= Q * K) return;
+  const int q = r / K;
+  const int id = idx[r];
+  const size_t o = (size_t)r * ldo;
+  if (id < 0) {
+    for (int c = threadIdx.x; c < ldo; c += blockDim.x) st16(out, o + c, 0.f, kind);
+    return;
+  }
+  const float* a = reinterpret_cast<const float*>(fts_ptr[q]) + (size_t)id * D;
+  const float* p = reinterpret_cast<const float*>(pos_ptr[q]) + (size_t)id * 3;
+  const float* b = view_fts + (size_t)q * D;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    st16(out, o + c, a[c], kind);
+    st16(out, o + D + c, b[c], kind);
+  }
+  for (int c = threadIdx.x; c < ldo - 2 * D; c += blockDim.x) {
+    float v = 0.f;
+    if (c < 3) v = centre[(size_t)q * 3 + c] - p[c];
+    st16(out, o + 2 * D + c, v, kind);
+  }
+}
+
+}  // namespace
+
+extern "C" int d3d_copy_blocks(const int64_t* src_ptr, const int64_t* dst_ptr, const int64_t* nbytes, int n, void* stream) {
+  if (n == 0) return 0;
+  D3D_REQUIRE(src_ptr && dst_ptr && nbytes, "args");
+  copy_blocks_kernel<<<dim3(32, n), 256, 0, (cudaStream_t)stream>>>((const long long*)src_ptr, (const long long*)dst_ptr, (const long long*)nbytes);
+  D3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int d3d_scatter_rows_ptr(const float* src, int64_t lds, const int* src_idx, const int64_t* dst_row_ptr, int n, int D, void* stream) {
+  if (n == 0) return 0;
+  D3D_REQUIRE(src && dst_row_ptr, "args");
+  scatter_rows_ptr_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(src, lds, src_idx, (const long long*)dst_row_ptr, n, D);
+  D3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int d3d_knn2_batched(const int64_t* ref_ptr, const int* n_ref, const float* queries, int n_q, float* out_d2, int* out_idx,
+                                void* stream) {
+  if (n_q == 0) return 0;
+  D3D_REQUIRE(ref_ptr && n_ref && queries && out_d2 && out_idx, "args");
+  knn2_batched_kernel<<<d3d_cdiv((long long)n_q * 32, 128), 128, 0, (cudaStream_t)stream>>>((const long long*)ref_ptr, n_ref, queries, n_q, out_d2,
+                                                                                          out_idx);
+  D3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int d3d_disc_input_batched(const int64_t* fts_ptr, const int64_t* pos_ptr, const int* idx, const float* view_fts,
+                                      const float* centre, int Q, int K, int D, int ldo, void* out16, int kind, void* stream) {
+  if (Q * K == 0) return 0;
+  D3D_REQUIRE(fts_ptr && pos_ptr && idx && view_fts && centre && out16, "args");
+  D3D_REQUIRE(ldo >= 2 * D + 3, "row too narrow");
+  disc_input_batched_kernel<<<Q * K, 256, 0, (cudaStream_t)stream>>>((const long long*)fts_ptr, (const long long*)pos_ptr, idx, view_fts, centre, Q,
+                                                                      K, D, ldo, out16, kind);
+  D3D_CHECK_LAUNCH();
+  return 0;
+}

@@ -29,6 +29,7 @@ from . import ops
 
 F32 = np.float32
 D = 768
+_TORCH_DT = {np.int32: torch.int32, np.int64: torch.int64, np.float32: torch.float32, np.uint8: torch.uint8, np.float16: torch.float16}
 
 
 class _Args:
@@ -74,6 +75,7 @@ class _Episode:
         self.p2i = np.full((8192,), -1, np.int64)  # patch id -> instance id (-1 = not a key), FF:168
         self.n_p2i = 0
         self.i2p = {}  # instance id -> member patch ids (insertion ordered like the reference dict), FF:172
+        self.inst_alive = np.zeros((1024,), bool)  # id in i2p
         self.inst_pos = _Pool(3, torch.float32, device, 1024)
         self.inst_fts = _Pool(D, torch.float32, device, 1024)
         self.inst_pos_h = np.zeros((1024, 3), F32)
@@ -81,10 +83,15 @@ class _Episode:
         self.zone_pos = _Pool(3, torch.float32, device, 256)
         self.zone_fts = _Pool(D, torch.float32, device, 256)
         self.n_zone = 0
-        self.zone_key_to_id = {}
+        self.zone_code_to_id = {}  # voxel code (int) -> zone id; `zone_key_to_id` exposes the reference's float-tuple keys
         self.z2i = {}
+        self.zone_alive = np.zeros((256,), bool)  # id in z2i
         self.tree = False
         self.last = {}
+
+    @property
+    def zone_key_to_id(self):
+        return {_code_to_key(c): z for c, z in self.zone_code_to_id.items()}
 
     def grow_host(self, n_patch=None, n_inst=None):
         if n_patch is not None and n_patch > len(self.patch_pos_h):
@@ -99,15 +106,40 @@ class _Episode:
                 cap *= 2
             a = np.zeros((cap, 3), F32); a[: len(self.inst_pos_h)] = self.inst_pos_h; self.inst_pos_h = a
 
+    @staticmethod
+    def _lowest_free(alive, n_keys, n):
+        """FF:433-475: the n lowest non-negative ints that are not dict keys (`alive` marks the keys)."""
+        need = n_keys + n
+        if need > len(alive):
+            return None
+        return np.flatnonzero(~alive[:need])[:n].astype(np.int64)
 
-def _lowest_free_from_dict(d, n):
-    """FF:448-475: the n lowest non-negative ints that are not keys of `d`."""
-    if len(d) == 0:
-        return np.arange(n, dtype=np.int64)
-    used = np.zeros(len(d) + n, bool)
-    keys = np.fromiter((k for k in d.keys() if k < len(d) + n), dtype=np.int64)
-    used[keys] = True
-    return np.flatnonzero(~used)[:n].astype(np.int64)
+    def free_instance_ids(self, n):
+        if len(self.i2p) + n > len(self.inst_alive):
+            a = np.zeros((max(2 * len(self.inst_alive), len(self.i2p) + n),), bool); a[: len(self.inst_alive)] = self.inst_alive; self.inst_alive = a
+        return self._lowest_free(self.inst_alive, len(self.i2p), n)
+
+    def free_zone_ids(self, n):
+        if len(self.z2i) + n > len(self.zone_alive):
+            a = np.zeros((max(2 * len(self.zone_alive), len(self.z2i) + n),), bool); a[: len(self.zone_alive)] = self.zone_alive; self.zone_alive = a
+        return self._lowest_free(self.zone_alive, len(self.z2i), n)
+
+
+_VOFF, _VM = 1 << 20, 1 << 21
+
+
+def _voxel_codes(pos, length=2.0):
+    """Integer code of the 2 m voxel of each position, monotone in the lexicographic (x, y, z) order of the reference's
+    float keys `(p // L) * L + L/2` (FF:694-695), so np.unique(codes) == torch.unique(keys, dim=0) order."""
+    with np.errstate(all="ignore"):
+        v = np.floor(np.asarray(pos, dtype=F32) / F32(length)).astype(np.int64) + _VOFF
+    return (v[:, 0] * _VM + v[:, 1]) * _VM + v[:, 2]
+
+
+def _code_to_key(c, length=2.0):
+    z = c % _VM; c //= _VM
+    y = c % _VM; x = c // _VM
+    return tuple(float(F32(F32(F32(v - _VOFF) * F32(length)) + F32(length / 2))) for v in (x, y, z))
 
 
 def _zone_keys(pos, length=2.0):
@@ -149,6 +181,7 @@ class Feature_Fields(nn.Module):
                                                           nn.Linear(4 * width, 2))
         for p in self.parameters():
             p.requires_grad_(False)
+        self._ring, self._ring_i, self._tomb = None, 0, None
         self.segmenter = None  # callable(batch_image) -> int64 [N,24,24]; FastSAM (FF:400-430) is outside the hot path
         self._W = None
         self.reset(batch_size)
@@ -298,33 +331,64 @@ class Feature_Fields(nn.Module):
         ops.layernorm(X, e["norm"][0], e["norm"][1], e["eps"], out32=out, row_index=cu_dev[:n_seq])
         return out
 
-    def _run_sequences(self, member_rows, xyz_ptrs, dir_ptrs, scale_ptrs, fts_ptrs, fts_is_f32, centre_dev, mode, level):
+    # ------------------------------------------------------------------ packed host->device uploads (one copy per call)
+    def _upload(self, arrays):
+        """Upload several small numpy arrays with ONE pinned staging copy; returns device views (16-byte aligned)."""
+        offs, total = [], 0
+        for a in arrays:
+            offs.append(total)
+            total += (a.nbytes + 15) // 16 * 16
+        total = max(total, 16)
+        ring = self._ring
+        if ring is None or ring[0].numel() < total:
+            cap = max(1 << 20, 1 << (total - 1).bit_length())
+            self._ring = ring = [torch.empty(cap, dtype=torch.uint8).pin_memory() for _ in range(64)]
+            self._ring_i = 0
+        host = ring[self._ring_i % len(ring)]
+        self._ring_i += 1
+        hv = host.numpy()
+        for a, o in zip(arrays, offs):
+            hv[o:o + a.nbytes] = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
+        devbuf = torch.empty(total, dtype=torch.uint8, device=self.device)
+        devbuf.copy_(host[:total], non_blocking=True)
+        out = []
+        for a, o in zip(arrays, offs):
+            t = devbuf[o:o + a.nbytes].view(_TORCH_DT[a.dtype.type])
+            out.append(t.view(a.shape) if a.ndim > 1 else t)
+        return out
+
+    def _run_sequences(self, member_rows, xyz_ptrs, dir_ptrs, scale_ptrs, fts_ptrs, fts_is_f32, centre, mode, level):
         """Generic packed pooling: sequence s gathers rows `member_rows[s]` (np int arrays) from its own base pointers.
-        centre_dev: device fp32 [n_seq,3].  Returns fp32 [n_seq,768] (token 0 of each encoded sequence)."""
+        centre: device fp32 [n_seq,3] or a numpy [n_seq,3] (uploaded with the index arrays).
+        Returns fp32 [n_seq,768] (token 0 of each encoded sequence)."""
         W = self._weights()
         mlp, agg, enc = (W["p2i_mlp"], W["p2i_agg"], W["p2i_enc"]) if level == 0 else (W["i2z_mlp"], W["i2z_agg"], W["i2z_enc"])
         n_seq = len(member_rows)
-        lens = np.array([len(m) + 1 for m in member_rows], dtype=np.int64)
+        lens = np.fromiter((len(m) + 1 for m in member_rows), dtype=np.int64, count=n_seq)
         cu = np.zeros(n_seq + 1, np.int32)
         cu[1:] = np.cumsum(lens)
         T = int(cu[-1])
         tok_src = np.full(T, -1, np.int32)
         tok_seq = np.repeat(np.arange(n_seq, dtype=np.int32), lens)
-        for s, m in enumerate(member_rows):
-            tok_src[cu[s] + 1: cu[s + 1]] = m
+        if T > n_seq:
+            body = np.ones(T, bool)
+            body[cu[:-1]] = False
+            tok_src[body] = np.concatenate(member_rows)
+        ptrs = np.stack([np.asarray(xyz_ptrs, np.int64), np.asarray(dir_ptrs if dir_ptrs is not None else xyz_ptrs, np.int64),
+                         np.asarray(scale_ptrs if scale_ptrs is not None else xyz_ptrs, np.int64), np.asarray(fts_ptrs, np.int64)])
+        arrs = [tok_src, tok_seq, cu, ptrs]
+        if isinstance(centre, np.ndarray):
+            arrs.append(np.ascontiguousarray(centre, dtype=F32))
+        up = self._upload(arrs)
+        tok_src_d, tok_seq_d, cu_d, ptrs_d = up[:4]
+        centre_dev = up[4] if isinstance(centre, np.ndarray) else centre
         dev = self.device
-        up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=True)
-        tok_src_d, tok_seq_d, cu_d = up(tok_src), up(tok_seq), up(cu)
-        xyz_p = up(np.asarray(xyz_ptrs, np.int64))
-        dir_p = up(np.asarray(dir_ptrs, np.int64)) if dir_ptrs is not None else None
-        sc_p = up(np.asarray(scale_ptrs, np.int64)) if scale_ptrs is not None else None
-        fts_p = up(np.asarray(fts_ptrs, np.int64))
         A0 = torch.empty((T, 8), device=dev, dtype=self.compute_dtype)
-        ops.pool_features(xyz_p, dir_p, sc_p, centre_dev, tok_seq_d, tok_src_d, T, mode, A0)
+        ops.pool_features(ptrs_d[0], ptrs_d[1], ptrs_d[2], centre_dev, tok_seq_d, tok_src_d, T, mode, A0)
         emb = self._mlp(A0, mlp)
         X = torch.empty((T, D), device=dev, dtype=torch.float32)
-        ops.pool_assemble(emb, fts_p, fts_is_f32, tok_seq_d, tok_src_d, agg, T, X)
-        return self._encode(X, cu_d, n_seq, int(lens.max()), enc)
+        ops.pool_assemble(emb, ptrs_d[3], fts_is_f32, tok_seq_d, tok_src_d, agg, T, X)
+        return self._encode(X, cu_d, n_seq, int(lens.max()), enc), centre_dev
 
     # ------------------------------------------------------------------ FF:296-326
     def get_patch_3d_info(self, batch_depth_map):
@@ -348,62 +412,85 @@ class Feature_Fields(nn.Module):
             raise NotImplementedError("posed-dataset branch (FF:343-344) is outside the hot path built here")
         depth = self._as_dev(batch_depth, torch.float32).contiguous()
         V = num_of_views
-        masks = []
-        for b in range(self.batch_size):
-            ep = self.eps[b]
-            if ep.n_patch == 0:
-                masks.append(None)
-                continue
-            heads = [float(batch_heading[b]) + (ix * (-math.pi / 6) if self.q7_fix else 0.0) for ix in range(V)]  # Q7
-            cam = torch.from_numpy(ops.camera_rows(batch_position[b], heads)).to(self.device, non_blocking=True)
-            m, _ = ops.frustum_cull(ep.patch_pos.t, ep.patch_dir.t, ep.patch_scale.t, ep.patch_fts.t, ep.n_patch, depth[b], cam,
-                                    self.args.input_hfov, self.args.input_vfov, 0.0, self.args.deleted_frustum_distance, 0.1)
-            masks.append(m.to("cpu", non_blocking=True))
-        torch.cuda.current_stream().synchronize()
-        for b in range(self.batch_size):
-            ep = self.eps[b]
-            if masks[b] is not None:
-                self._host_cull(ep, np.flatnonzero(masks[b].numpy()))
-            ep.tree = ep.n_inst > 0
+        with L.stream_scope():
+            cams = np.concatenate([ops.camera_rows(batch_position[b], [float(batch_heading[b]) + (ix * (-math.pi / 6) if self.q7_fix else 0.0)
+                                                                      for ix in range(V)]) for b in range(self.batch_size)], 0)  # Q7
+            cam_d = self._upload([cams])[0]
+            masks = []
+            for b in range(self.batch_size):
+                ep = self.eps[b]
+                if ep.n_patch == 0:
+                    masks.append(None)
+                    continue
+                m, _ = ops.frustum_cull(ep.patch_pos.t, ep.patch_dir.t, ep.patch_scale.t, ep.patch_fts.t, ep.n_patch, depth[b], cam_d[b * V:(b + 1) * V],
+                                        self.args.input_hfov, self.args.input_vfov, 0.0, self.args.deleted_frustum_distance, 0.1)
+                masks.append(m.to("cpu", non_blocking=True))
+            torch.cuda.current_stream().synchronize()
+            rows_i, rows_z = [], []
+            for b in range(self.batch_size):
+                ep = self.eps[b]
+                if masks[b] is not None:
+                    di, dz = self._host_cull(ep, np.flatnonzero(masks[b].numpy()))
+                    rows_i += [(ep, i) for i in di]
+                    rows_z += [(ep, z) for z in dz]
+                ep.tree = ep.n_inst > 0
+            # tombstone dead instance / zone slots on the device (FF:378-379, 392-393): one batched scatter per tensor kind
+            if rows_i or rows_z:
+                const = self._tomb_rows()
+                for rows, pos_attr, fts_attr in ((rows_i, "inst_pos", "inst_fts"), (rows_z, "zone_pos", "zone_fts")):
+                    if not rows:
+                        continue
+                    pp = np.fromiter((getattr(e, pos_attr).t.data_ptr() + 12 * i for e, i in rows), np.int64, len(rows))
+                    fp = np.fromiter((getattr(e, fts_attr).t.data_ptr() + 4 * D * i for e, i in rows), np.int64, len(rows))
+                    zi = np.zeros(len(rows), np.int32)
+                    pp_d, fp_d, zi_d = self._upload([pp, fp, zi])
+                    L.check(L.lib().d3d_scatter_rows_ptr(L.ptr(const[0]), 3, L.ptr(zi_d), L.ptr(pp_d), len(rows), 3, L.stream_ptr()))
+                    L.check(L.lib().d3d_scatter_rows_ptr(L.ptr(const[1]), D, L.ptr(zi_d), L.ptr(fp_d), len(rows), D, L.stream_ptr()))
+
+    def _tomb_rows(self):
+        if self._tomb is None:
+            self._tomb = (torch.full((1, 3), -10000.0, device=self.device), torch.zeros((1, D), device=self.device))
+        return self._tomb
 
     def _host_cull(self, ep, deleted):
-        """FF:362-393 for the culled array rows `deleted` (ascending): patch -> instance -> zone bookkeeping."""
+        """FF:362-393 for the culled array rows `deleted` (ascending): patch -> instance -> zone bookkeeping.
+        Returns (dead instance slots, dead zone slots).  The reference pops in ascending patch order; dict *removal* order does
+        not change the insertion order of the survivors, so grouping by instance yields the same state."""
         if len(deleted) == 0:
-            return
+            return [], []
         ep.patch_pos_h[deleted] = -10000.0
         keyed = deleted[ep.p2i[deleted] >= 0]  # Q2: array index used as patch id
         if len(keyed) == 0:
-            return
+            return [], []
         owners = ep.p2i[keyed]
         ep.p2i[keyed] = -1
         ep.n_p2i -= len(keyed)
+        gone = np.zeros(ep.n_patch, bool)
+        gone[keyed] = True
         dead_inst, dead_zone = [], []
         for iid in np.unique(owners).tolist():
-            rm = keyed[owners == iid]
-            keep = ep.i2p[iid][~np.isin(ep.i2p[iid], rm)]
-            ep.i2p[iid] = keep
-            if len(keep) == 0:
-                ep.i2p.pop(iid)
-                key = tuple(_zone_keys(ep.inst_pos_h[iid]).tolist())
-                ep.inst_pos_h[iid] = -10000.0
-                dead_inst.append(iid)
-                if key in ep.zone_key_to_id:
-                    zid = ep.zone_key_to_id[key]
-                    ep.z2i[zid] = ep.z2i[zid][ep.z2i[zid] != iid]
-                    if len(ep.z2i[zid]) == 0:
-                        ep.zone_key_to_id.pop(key)
-                        ep.z2i.pop(zid)
-                        dead_zone.append(zid)
-        # NOTE the reference pops instances in ascending patch order; dict *removal* order does not affect the
-        # insertion order of the survivors, so processing grouped by instance id yields the same state.
-        if dead_inst:
-            idx = torch.tensor(dead_inst, device=self.device, dtype=torch.long)
-            ep.inst_pos.t[idx] = -10000.0
-            ep.inst_fts.t[idx] = 0.0
-        if dead_zone:
-            idx = torch.tensor(dead_zone, device=self.device, dtype=torch.long)
-            ep.zone_pos.t[idx] = -10000.0
-            ep.zone_fts.t[idx] = 0.0
+            m = ep.i2p[iid]
+            keep = m[~gone[m]]
+            if len(keep):
+                ep.i2p[iid] = keep
+                continue
+            ep.i2p.pop(iid)
+            ep.inst_alive[iid] = False
+            code = int(_voxel_codes(ep.inst_pos_h[iid:iid + 1])[0])
+            ep.inst_pos_h[iid] = -10000.0
+            dead_inst.append(iid)
+            zid = ep.zone_code_to_id.get(code)
+            if zid is not None:
+                z = ep.z2i[zid]
+                z = z[z != iid]
+                if len(z):
+                    ep.z2i[zid] = z
+                else:
+                    ep.zone_code_to_id.pop(code)
+                    ep.z2i.pop(zid)
+                    ep.zone_alive[zid] = False
+                    dead_zone.append(zid)
+        return dead_inst, dead_zone
 
     # ------------------------------------------------------------------ FF:493-815
     def update_feature_fields(self, batch_depth, batch_grid_ft, batch_image=None, batch_position=None, batch_heading=None,
@@ -420,151 +507,155 @@ class Feature_Fields(nn.Module):
                 raise RuntimeError("no segmentation: pass batch_patch_segm or set .segmenter (FastSAM is not part of this engine)")
             batch_patch_segm = self.segmenter(batch_image)
         segm = np.asarray(batch_patch_segm.cpu() if torch.is_tensor(batch_patch_segm) else batch_patch_segm).reshape(B, V, P).astype(np.int64)
-        depth = self._as_dev(batch_depth, torch.float32).reshape(B, V, P).contiguous()
-        grid = self._as_dev(batch_grid_ft, torch.float16).reshape(B, V, P, D).contiguous()
-        pose = torch.from_numpy(ops.pose_rows(batch_position, batch_heading, V)).to(self.device, non_blocking=True)
-        xyz_all, dir_all, scale_all = ops.unproject_habitat(depth.view(B * V, P), pose, self.args.input_hfov, self.args.input_vfov,
-                                                            self.args.input_width, self.args.input_height)
-        for ix in range(V):
-            self._update_view(ix, V, segm[:, ix], xyz_all.view(B, V, P, 3)[:, ix], dir_all.view(B, V, P)[:, ix],
-                              scale_all.view(B, V, P)[:, ix], grid[:, ix])
+        with L.stream_scope():
+            depth = self._as_dev(batch_depth, torch.float32).reshape(B * V, P).contiguous()
+            grid = self._as_dev(batch_grid_ft, torch.float16).reshape(B * V * P, D).contiguous()
+            pose = self._upload([ops.pose_rows(batch_position, batch_heading, V)])[0]
+            xyz, direction, scale = ops.unproject_habitat(depth, pose, self.args.input_hfov, self.args.input_vfov,
+                                                          self.args.input_width, self.args.input_height)
+            xyz_h = xyz.to("cpu", non_blocking=True)  # host mirror of the step's patch positions (one copy per step)
+            torch.cuda.current_stream().synchronize()
+            xyz_h = xyz_h.numpy().reshape(B, V, P, 3)
+            stage = {"xyz": xyz.view(B * V * P, 3), "dir": direction.view(-1), "scale": scale.view(-1), "fts": grid}
+            for ix in range(V):
+                self._update_view(ix, V, P, segm[:, ix], stage, xyz_h[:, ix])
 
-    def _update_view(self, ix, V, segm, xyz, direction, scale, grid):
-        """One panorama view for all episodes in lock step.  xyz [B,P,3], direction/scale [B,P], grid [B,P,768] are (strided) views."""
+    def _update_view(self, ix, V, P, segm, stage, xyz_h):
+        """One panorama view for all episodes in lock step.  `stage` holds the step's unprojected patches / CLIP features for all
+        (episode, view) units, unit u = b*V+ix occupying rows [u*P, (u+1)*P)."""
         B = self.batch_size
-        P = xyz.shape[1]
         dev = self.device
         W = self._weights()
-        # 1. append the view's patches to the episode pools (FF:557-570)
-        base_rows = []
+        lib = L.lib()
+        # 1. append the view's patches to the episode pools (FF:557-570): one batched block copy
+        base_rows, src, dst, nb = [], [], [], []
         for b, ep in enumerate(self.eps):
             n0 = ep.n_patch
             for pool in (ep.patch_pos, ep.patch_dir, ep.patch_scale, ep.patch_fts):
                 pool.ensure(n0 + P)
             ep.grow_host(n_patch=n0 + P)
-            ep.patch_pos.t[n0:n0 + P].copy_(xyz[b])
-            ep.patch_dir.t[n0:n0 + P].copy_(direction[b])
-            ep.patch_scale.t[n0:n0 + P].copy_(scale[b])
-            ep.patch_fts.t[n0:n0 + P].copy_(grid[b])
+            u = b * V + ix
+            for key, pool, rb in (("xyz", ep.patch_pos, 12), ("dir", ep.patch_dir, 4), ("scale", ep.patch_scale, 4), ("fts", ep.patch_fts, 2 * D)):
+                src.append(stage[key].data_ptr() + u * P * rb)
+                dst.append(pool.t.data_ptr() + n0 * rb)
+                nb.append(P * rb)
+            ep.patch_pos_h[n0:n0 + P] = xyz_h[b]
             base_rows.append(n0)
             ep.n_patch = n0 + P
         # 2. packed sequences: one per (episode, segment); members keep patch order (boolean-mask semantics, FF:582)
-        member_rows, owner, seg_of = [], [], []
+        member_rows, owner, splits_all = [], [], []
         for b in range(B):
             order = np.argsort(segm[b], kind="stable")
             counts = np.bincount(segm[b])
             if (counts == 0).any():
                 raise ValueError("patch_segm labels must be dense 0..G-1 (FF:411-422 relabels them)")
             splits = np.split(order, np.cumsum(counts)[:-1])
-            for g, m in enumerate(splits):
-                member_rows.append((base_rows[b] + m).astype(np.int32))
-                owner.append(b)
-                seg_of.append(g)
+            splits_all.append(splits)
+            off = (b * V + ix) * P
+            member_rows += [(off + m).astype(np.int32) for m in splits]
+            owner += [b] * len(splits)
         n_seq = len(member_rows)
         owner = np.asarray(owner)
-        seq_start = np.searchsorted(owner, np.arange(B))  # first sequence of each episode
+        seq_start = np.searchsorted(owner, np.arange(B))
         seq_end = np.searchsorted(owner, np.arange(B), side="right")
-        # centroids on device (fp64 accumulate), one launch per episode pool
-        centres = torch.empty((n_seq, 3), device=dev, dtype=torch.float32)
-        for b, ep in enumerate(self.eps):
-            s0, s1 = seq_start[b], seq_end[b]
-            mem = np.concatenate(member_rows[s0:s1])
-            cu = np.zeros(s1 - s0 + 1, np.int32)
-            cu[1:] = np.cumsum([len(m) for m in member_rows[s0:s1]])
-            c = ops.seq_centroid(ep.patch_pos.t, torch.from_numpy(mem).to(dev, non_blocking=True),
-                                 torch.from_numpy(cu).to(dev, non_blocking=True), s1 - s0)
-            centres[s0:s1].copy_(c)
-        ptr = lambda t: t.data_ptr()
-        view_fts = self._run_sequences(member_rows, [ptr(self.eps[b].patch_pos.t) for b in owner], [ptr(self.eps[b].patch_dir.t) for b in owner],
-                                       [ptr(self.eps[b].patch_scale.t) for b in owner], [ptr(self.eps[b].patch_fts.t) for b in owner],
-                                       False, centres, 0, 0)
-        # 3. K-NN proposals + merge discriminator for episodes that already have instances (FF:604-621)
-        Ks = [min(len(ep.i2p), self.args.num_proposal_instances) if ep.tree else 0 for ep in self.eps]
-        idx_d = torch.zeros((n_seq, 2), device=dev, dtype=torch.int32)
-        d2_d = torch.zeros((n_seq, 2), device=dev, dtype=torch.float32)
-        row_off, rows = [], 0
-        for b in range(B):
-            row_off.append(rows)
-            rows += (seq_end[b] - seq_start[b]) * Ks[b]
-        logits_d = None
-        if rows > 0:
-            A = torch.empty((rows, 1544), device=dev, dtype=self.compute_dtype)
-            for b, ep in enumerate(self.eps):
-                K, s0, s1 = Ks[b], seq_start[b], seq_end[b]
-                if K == 0:
-                    continue
-                G = s1 - s0
-                # results of episode b are stored densely ([G,K]) at the start of its [G,2] region
-                d2v = d2_d[s0:s1].view(-1)[: G * K].view(G, K)
-                idv = idx_d[s0:s1].view(-1)[: G * K].view(G, K)
-                L.check(L.lib().d3d_knn3d(L.ptr(ep.inst_pos.t), ep.n_inst, L.ptr(centres[s0:s1]), G, K, L.ptr(d2v), L.ptr(idv), L.stream_ptr()))
-                ops.disc_input(ep.inst_fts.t, ep.inst_pos.t, idv, view_fts[s0:s1], centres[s0:s1], G, K, A[row_off[b]: row_off[b] + G * K])
-            logits_d = self._mlp(A, W["disc"])
-        # 4. ONE device->host copy per view: centroids, patch xyz (host mirror), K-NN results, logits
-        centres_h = centres.to("cpu", non_blocking=True)
-        xyz_h = [self.eps[b].patch_pos.t[base_rows[b]: base_rows[b] + P].to("cpu", non_blocking=True) for b in range(B)]
-        idx_h = idx_d.to("cpu", non_blocking=True)
-        d2_h = d2_d.to("cpu", non_blocking=True)
-        logits_h = logits_d.contiguous().to("cpu", non_blocking=True) if logits_d is not None else None
+        cu_m = np.zeros(n_seq + 1, np.int32)
+        cu_m[1:] = np.cumsum([len(m) for m in member_rows])
+        inst_ptr = np.fromiter((self.eps[b].inst_pos.t.data_ptr() for b in owner), np.int64, n_seq)
+        fts_ptr = np.fromiter((self.eps[b].inst_fts.t.data_ptr() for b in owner), np.int64, n_seq)
+        n_ref = np.fromiter((self.eps[b].n_inst if self.eps[b].tree else 0 for b in owner), np.int32, n_seq)
+        up = self._upload([np.asarray(src, np.int64), np.asarray(dst, np.int64), np.asarray(nb, np.int64), np.concatenate(member_rows), cu_m,
+                           inst_ptr, fts_ptr, n_ref])
+        L.check(lib.d3d_copy_blocks(L.ptr(up[0]), L.ptr(up[1]), L.ptr(up[2]), len(src), L.stream_ptr()))
+        centres = ops.seq_centroid(stage["xyz"], up[3], up[4], n_seq)  # fp64 accumulate, all episodes in one launch
+        sx, sd, ss, sf = (stage[k].data_ptr() for k in ("xyz", "dir", "scale", "fts"))
+        view_fts, _ = self._run_sequences(member_rows, [sx] * n_seq, [sd] * n_seq, [ss] * n_seq, [sf] * n_seq, False, centres, 0, 0)
+        # 3. K-NN proposals + merge discriminator (FF:604-621), all episodes in one launch each; K = 2 columns are always
+        #    computed, the host uses the first min(#live, 2) of them (further columns can only be tombstones or absent)
+        res = torch.empty((n_seq, 12), device=dev, dtype=torch.float32)  # [centre(3) | d2(2) | idx(2, int bits) | logits(4) | pad]
+        any_tree = bool(n_ref.max() > 0) if n_seq else False
+        d2_d = torch.empty((n_seq, 2), device=dev, dtype=torch.float32)
+        idx_d = torch.empty((n_seq, 2), device=dev, dtype=torch.int32)
+        if any_tree:
+            L.check(lib.d3d_knn2_batched(L.ptr(up[5]), L.ptr(up[7]), L.ptr(centres), n_seq, L.ptr(d2_d), L.ptr(idx_d), L.stream_ptr()))
+            A = torch.empty((2 * n_seq, 1544), device=dev, dtype=self.compute_dtype)
+            L.check(lib.d3d_disc_input_batched(L.ptr(up[6]), L.ptr(up[5]), L.ptr(idx_d), L.ptr(view_fts), L.ptr(centres), n_seq, 2, D, 1544,
+                                               L.ptr(A), L.kind_of(A.dtype), L.stream_ptr()))
+            logits_d = self._mlp(A, W["disc"])  # [2*n_seq, 2]
+            res[:, 7:11] = logits_d.reshape(n_seq, 4)
+            res[:, 3:5] = d2_d
+            res[:, 5:7] = idx_d.view(torch.float32)
+        res[:, 0:3] = centres
+        # 4. ONE device->host copy per view
+        res_h = res.to("cpu", non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        centres_h, idx_h, d2_h = centres_h.numpy(), idx_h.numpy(), d2_h.numpy()
+        res_h = res_h.numpy()
+        centres_h = np.ascontiguousarray(res_h[:, 0:3])
+        d2_h = np.ascontiguousarray(res_h[:, 3:5])
+        idx_h = np.ascontiguousarray(res_h[:, 5:7]).view(np.int32)
+        logits_h = np.ascontiguousarray(res_h[:, 7:11]).reshape(n_seq, 2, 2)
         # 5. host bookkeeping per episode (FF:623-756), collecting the device work it implies
-        new_src, new_dst = [[] for _ in range(B)], [[] for _ in range(B)]
-        merged = []  # (b, iid, member ids, position)
-        zones = []   # (b, slot, member slots, use_keys, zone_pos)
+        new_src, new_fts_dst, new_pos_dst = [], [], []
+        merged, zones = [], []
         for b, ep in enumerate(self.eps):
             s0, s1 = seq_start[b], seq_end[b]
-            G = s1 - s0
-            ep.patch_pos_h[base_rows[b]: base_rows[b] + P] = xyz_h[b].numpy()
-            cen = centres_h[s0:s1]
-            K = Ks[b]
-            lg = logits_h[row_off[b]: row_off[b] + G * K].numpy().reshape(G, K, 2) if K > 0 else np.zeros((G, 0, 2), F32)
-            self._host_update(ep, b, segm[b], base_rows[b], cen, idx_h[s0:s1].reshape(-1)[: G * K].reshape(G, K),
-                              d2_h[s0:s1].reshape(-1)[: G * K].reshape(G, K), lg, s0, new_src[b], new_dst[b], merged, zones)
-        # 6. device writes implied by the bookkeeping
-        for b, ep in enumerate(self.eps):
-            if new_dst[b]:
-                ep.inst_pos.ensure(ep.n_inst)
-                ep.inst_fts.ensure(ep.n_inst)
-                src = torch.tensor(new_src[b], device=dev, dtype=torch.int32)
-                dst = torch.tensor(new_dst[b], device=dev, dtype=torch.int32)
-                ops.scatter_rows(view_fts, ep.inst_fts.t, len(new_dst[b]), src, dst)
-                ops.scatter_rows(centres, ep.inst_pos.t, len(new_dst[b]), src, dst)
+            K = min(len(ep.i2p), self.args.num_proposal_instances) if ep.tree else 0
+            n_before = ep.n_inst
+            news = self._host_update(ep, b, splits_all[b], centres_h[s0:s1], idx_h[s0:s1, :K], d2_h[s0:s1, :K], logits_h[s0:s1, :K], merged, zones)
+            if news:
+                if ep.n_inst > n_before:
+                    ep.inst_pos.ensure(ep.n_inst)
+                    ep.inst_fts.ensure(ep.n_inst)
+                fp, pp = ep.inst_fts.t.data_ptr(), ep.inst_pos.t.data_ptr()
+                for g, iid in news:
+                    new_src.append(s0 + g)
+                    new_fts_dst.append(fp + 4 * D * iid)
+                    new_pos_dst.append(pp + 12 * iid)
+        # 6. device writes implied by the bookkeeping: batched scatters across episodes
+        if new_src:
+            a, bb, c = self._upload([np.asarray(new_src, np.int32), np.asarray(new_fts_dst, np.int64), np.asarray(new_pos_dst, np.int64)])
+            L.check(lib.d3d_scatter_rows_ptr(L.ptr(view_fts), D, L.ptr(a), L.ptr(bb), len(new_src), D, L.stream_ptr()))
+            L.check(lib.d3d_scatter_rows_ptr(L.ptr(centres), 3, L.ptr(a), L.ptr(c), len(new_src), 3, L.stream_ptr()))
         if merged:
-            pos = torch.from_numpy(np.stack([m[3] for m in merged]).astype(F32)).to(dev, non_blocking=True)
             eps_ = [self.eps[m[0]] for m in merged]
-            fts = self._run_sequences([m[2].astype(np.int32) for m in merged], [ptr(e.patch_pos.t) for e in eps_], [ptr(e.patch_dir.t) for e in eps_],
-                                      [ptr(e.patch_scale.t) for e in eps_], [ptr(e.patch_fts.t) for e in eps_], False, pos, 0, 0)
-            for j, (b, iid, _, _) in enumerate(merged):
-                ep = self.eps[b]
-                ep.inst_fts.t[iid].copy_(fts[j])
-                ep.inst_pos.t[iid].copy_(pos[j])
+            pos_np = np.stack([m[3] for m in merged]).astype(F32)
+            fts, pos_d = self._run_sequences([m[2].astype(np.int32) for m in merged], [e.patch_pos.t.data_ptr() for e in eps_],
+                                             [e.patch_dir.t.data_ptr() for e in eps_], [e.patch_scale.t.data_ptr() for e in eps_],
+                                             [e.patch_fts.t.data_ptr() for e in eps_], False, pos_np, 0, 0)
+            fd = np.fromiter((e.inst_fts.t.data_ptr() + 4 * D * m[1] for e, m in zip(eps_, merged)), np.int64, len(merged))
+            pd = np.fromiter((e.inst_pos.t.data_ptr() + 12 * m[1] for e, m in zip(eps_, merged)), np.int64, len(merged))
+            fd_d, pd_d = self._upload([fd, pd])
+            L.check(lib.d3d_scatter_rows_ptr(L.ptr(fts), D, None, L.ptr(fd_d), len(merged), D, L.stream_ptr()))
+            L.check(lib.d3d_scatter_rows_ptr(L.ptr(pos_d), 3, None, L.ptr(pd_d), len(merged), 3, L.stream_ptr()))
         if zones:
-            zpos = torch.from_numpy(np.stack([z[4] for z in zones]).astype(F32)).to(dev, non_blocking=True)
             key_arrays = {}
             xyz_ptrs, fts_ptrs = [], []
             for (b, slot, members, use_keys, _) in zones:
                 ep = self.eps[b]
-                if use_keys:  # Q5: an updated zone is embedded from its members' voxel-centre keys
-                    if b not in key_arrays:
-                        key_arrays[b] = torch.from_numpy(_zone_keys(ep.inst_pos_h[: ep.n_inst])).to(dev, non_blocking=True)
-                    xyz_ptrs.append(ptr(key_arrays[b]))
-                else:
-                    xyz_ptrs.append(ptr(ep.inst_pos.t))
-                fts_ptrs.append(ptr(ep.inst_fts.t))
-            zf = self._run_sequences([z[2].astype(np.int32) for z in zones], xyz_ptrs, None, None, fts_ptrs, True, zpos, 1, 1)
-            for j, (b, slot, _, _, _) in enumerate(zones):
-                ep = self.eps[b]
                 ep.zone_pos.ensure(slot + 1)
                 ep.zone_fts.ensure(slot + 1)
-                ep.zone_fts.t[slot].copy_(zf[j])
-                ep.zone_pos.t[slot].copy_(zpos[j])
+                if use_keys:  # Q5: an updated zone is embedded from its members' voxel-centre keys
+                    if b not in key_arrays:
+                        key_arrays[b] = self._upload([_zone_keys(ep.inst_pos_h[: ep.n_inst])])[0]
+                    xyz_ptrs.append(key_arrays[b].data_ptr())
+                else:
+                    xyz_ptrs.append(ep.inst_pos.t.data_ptr())
+                fts_ptrs.append(ep.inst_fts.t.data_ptr())
+            zpos_np = np.stack([z[4] for z in zones]).astype(F32)
+            zf, zpos_d = self._run_sequences([z[2].astype(np.int32) for z in zones], xyz_ptrs, None, None, fts_ptrs, True, zpos_np, 1, 1)
+            fd = np.fromiter((self.eps[z[0]].zone_fts.t.data_ptr() + 4 * D * z[1] for z in zones), np.int64, len(zones))
+            pd = np.fromiter((self.eps[z[0]].zone_pos.t.data_ptr() + 12 * z[1] for z in zones), np.int64, len(zones))
+            fd_d, pd_d = self._upload([fd, pd])
+            L.check(lib.d3d_scatter_rows_ptr(L.ptr(zf), D, None, L.ptr(fd_d), len(zones), D, L.stream_ptr()))
+            L.check(lib.d3d_scatter_rows_ptr(L.ptr(zpos_d), 3, None, L.ptr(pd_d), len(zones), 3, L.stream_ptr()))
         for ep in self.eps:
             ep.tree = ep.n_inst > 0
 
-    def _host_update(self, ep, b, segm, base_row, cen, idx, d2, logits, s0, new_src, new_dst, merged, zones):
+    def _host_update(self, ep, b, splits, cen, idx, d2, logits, merged, zones):
+        """FF:623-756 / 759-812 for one episode and one view.  Returns [(segment, instance id)] of the NEW instances."""
         G = len(cen)
-        P = len(segm)
+        P = sum(len(m) for m in splits)
+        news = []
+        patch_ids = np.flatnonzero(ep.p2i[: ep.n_p2i + P] < 0)[:P].astype(np.int64)  # FF:433-445 lowest free patch ids
         if ep.tree:
             K = idx.shape[1]
             if K > 0 and float(d2.astype(np.float64).sum()) > 1e6:  # Q9: K-shrink heuristic (FF:607-610)
@@ -573,75 +664,75 @@ class Feature_Fields(nn.Module):
             merge_target = logits[..., 1] > logits[..., 0]  # argmax of the 2-way softmax, first max wins
             ep.last = {"knn": (d2.copy(), idx.copy()), "merge": merge_target.copy(), "logits": logits.copy()}
             is_new = ~merge_target.any(-1) if K > 0 else np.ones(G, bool)
-            new_ids = _lowest_free_from_dict(ep.i2p, int(is_new.sum()))
-            patch_ids = np.flatnonzero(ep.p2i[: ep.n_p2i + P] < 0)[:P].astype(np.int64)  # FF:433-445
-            order = np.argsort(segm, kind="stable")
-            splits = np.split(order, np.cumsum(np.bincount(segm, minlength=G))[:-1])
+            new_ids = ep.free_instance_ids(int(is_new.sum()))
+            first = merge_target.argmax(-1) if K > 0 else None  # nearest accepted proposal only (FF:653,691)
             ni = 0
             touched = {}
             for g in range(G):
-                members = patch_ids[np.sort(splits[g])]
+                members = patch_ids[splits[g]]
                 if is_new[g]:
                     iid = int(new_ids[ni]); ni += 1
-                    ep.i2p[iid] = members
-                    ep.p2i[members] = iid
-                    ep.n_p2i += len(members)
                     if iid >= ep.n_inst:
                         ep.n_inst = iid + 1
                         ep.grow_host(n_inst=ep.n_inst)
+                    ep.i2p[iid] = members
+                    ep.inst_alive[iid] = True
                     ep.inst_pos_h[iid] = cen[g]
-                    new_src.append(s0 + g)
-                    new_dst.append(iid)
+                    news.append((g, iid))
                 else:
-                    j = int(np.flatnonzero(merge_target[g])[0])  # nearest accepted proposal only (FF:653,691)
-                    iid = int(idx[g, j])
+                    iid = int(idx[g, first[g]])
                     if iid not in ep.i2p:
                         raise KeyError(f"merge target instance {iid} is not alive (the reference raises here too, FF:658)")
                     ep.i2p[iid] = np.concatenate([ep.i2p[iid], members])
-                    ep.p2i[members] = iid
-                    ep.n_p2i += len(members)
                     touched[iid] = True
+                ep.p2i[members] = iid
+            ep.n_p2i += P
             for iid in touched:  # only the state after the last merge survives (FF:663,688 overwrite)
                 ids = ep.i2p[iid]
                 pos = _mean64(ep.patch_pos_h[ids])  # Q2: ids index the patch arrays directly
                 ep.inst_pos_h[iid] = pos
                 merged.append((b, iid, ids, pos))
-            slot_keys = _zone_keys(ep.inst_pos_h[: ep.n_inst])
+            slot_pos = ep.inst_pos_h[: ep.n_inst]
         else:
             ep.last = {}
-            ids = _lowest_free_from_dict(ep.i2p, G)
-            patch_ids = np.flatnonzero(ep.p2i[: ep.n_p2i + P] < 0)[:P].astype(np.int64)
+            ids = ep.free_instance_ids(G)
             ep.n_inst = G
             ep.grow_host(n_inst=G)
             ep.inst_pos_h[:G] = cen
             for g in range(G):
-                members = patch_ids[segm == g]
+                members = patch_ids[splits[g]]
                 iid = int(ids[g])
                 ep.i2p[iid] = members
+                ep.inst_alive[iid] = True
                 ep.p2i[members] = iid
-                ep.n_p2i += len(members)
-                new_src.append(s0 + g)
-                new_dst.append(g)
-            slot_keys = _zone_keys(cen)
-        # zones (FF:693-756 / 777-812)
-        view_keys = _zone_keys(cen)
-        uniq = np.unique(view_keys, axis=0)
-        zone_ids = _lowest_free_from_dict(ep.z2i, len(uniq))
+                news.append((g, iid))
+            ep.n_p2i += P
+            slot_pos = cen
+        # zones (FF:693-756 / 777-812): group the instance slots by voxel once, then visit the view's voxels in key order
+        slot_code = _voxel_codes(slot_pos)
+        order = np.argsort(slot_code, kind="stable")
+        sorted_code = slot_code[order]
+        uniq = np.unique(_voxel_codes(cen))
+        lo = np.searchsorted(sorted_code, uniq, side="left")
+        hi = np.searchsorted(sorted_code, uniq, side="right")
+        zone_ids = ep.free_zone_ids(len(uniq))
         zi = 0
-        for key_arr in uniq:
-            key = tuple(key_arr.tolist())
-            members = np.flatnonzero((slot_keys[:, 0] == key_arr[0]) & (slot_keys[:, 1] == key_arr[1]) & (slot_keys[:, 2] == key_arr[2]))
-            if key not in ep.zone_key_to_id:
+        for j, code in enumerate(uniq.tolist()):
+            members = order[lo[j]:hi[j]]  # ascending slot order (stable sort)
+            zid = ep.zone_code_to_id.get(code)
+            if zid is None:
                 zid = int(zone_ids[zi]); zi += 1
-                ep.zone_key_to_id[key] = zid
+                ep.zone_code_to_id[code] = zid
                 ep.z2i[zid] = members
+                ep.zone_alive[zid] = True
                 slot = ep.n_zone  # Q3: a new zone is always appended, whatever its id
                 ep.n_zone += 1
-                zones.append((b, slot, members, False, _mean64(ep.inst_pos_h[members])))
+                zones.append((b, slot, members, False, _mean64(slot_pos[members])))
             else:
-                zid = ep.zone_key_to_id[key]
                 ep.z2i[zid] = members
-                zones.append((b, zid, members, True, _mean64(slot_keys[members])))  # Q5
+                key = np.asarray(_code_to_key(code), F32)
+                zones.append((b, zid, members, True, _mean64(np.repeat(key[None], max(len(members), 0), 0))))  # Q5
+        return news
 
     # ------------------------------------------------------------------ FF:818-862
     def get_environment_features(self, agent_position, agent_heading_angle, instance_distance=5.0, zone_distance=100.0):

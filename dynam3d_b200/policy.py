@@ -274,6 +274,12 @@ class Dynam3D_VLN(nn.Module):
     def forward_logits(self, observations, instructions, agent_positions, agent_heading_angles, depth_scale=(0.0, 10.0),
                        delete_old_features=True, num_of_views=1, input_ids=None):
         """The measured hot path: stages a1-a16 up to the next-action logits [B, vocab] (prefill of POL:463)."""
+        with L.stream_scope():
+            return self._forward_logits(observations, instructions, agent_positions, agent_heading_angles, depth_scale, delete_old_features,
+                                        num_of_views, input_ids)
+
+    def _forward_logits(self, observations, instructions, agent_positions, agent_heading_angles, depth_scale, delete_old_features,
+                        num_of_views, input_ids):
         ff = self.feature_fields
         B = ff.batch_size
         patch, inst, zone = self.encode_step(observations, agent_positions, agent_heading_angles, depth_scale, delete_old_features, num_of_views)

@@ -171,6 +171,11 @@ int d3d_cast16(const float* in, int64_t ldi, void* out, int64_t ldo, int T, int 
 int d3d_attention_simt(const void* qkv, int64_t ld, void* out, int64_t ldo, const int* cu_seqlens, int n_seq, int max_len, int H,
                        int Dh, int causal, int kind, float scale, void* stream);
 
+/* Tensor-core flash attention (mma.sync m16n8k16, online softmax, fp32 accumulate) with the same contract as
+ * d3d_attention_simt; used for CLIP ViT (CLIPM:181-183) and the causal Phi-3 prefill.  Rows must be 16-byte aligned. */
+int d3d_attention_mma(const void* qkv, int64_t ld, void* out, int64_t ldo, const int* cu_seqlens, int n_seq, int max_len, int H,
+                      int Dh, int causal, int kind, float scale, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Token builders for the layer-wise pooling (patch -> instance -> zone) and the merge discriminator.
  * Sequences of several episodes are packed in one batch; seq_* are per-sequence base addresses (device pointers
@@ -197,6 +202,18 @@ int d3d_disc_input(const float* inst_fts, const float* inst_pos, const int* idx,
 int d3d_patch_info_rows(const float* info5, int64_t n, void* out16, int kind, void* stream);
 int d3d_concat2_cast(const float* a, const float* b, int n, int D, void* out16, int kind, void* stream);
 int d3d_pos3_rows(const float* x, int n, void* out16, int kind, void* stream);
+
+/* Pointer-table (batched over episodes) variants: one launch serves every episode of the rank. */
+/* n independent 16-byte-aligned block copies (append a view's patches to the episode pools, FF:557-570). */
+int d3d_copy_blocks(const int64_t* src_ptr, const int64_t* dst_ptr, const int64_t* nbytes, int n, void* stream);
+/* *(float*)dst_row_ptr[r] <- src[src_idx?src_idx[r]:r] (fp32 rows of width D): slot writes across episodes (FF:644-648,688,730,756). */
+int d3d_scatter_rows_ptr(const float* src, int64_t lds, const int* src_idx, const int64_t* dst_row_ptr, int n, int D, void* stream);
+/* 2-NN of every query against ITS OWN reference set ref_ptr[q] ([n_ref[q],3] fp32), same arithmetic / tie-break as d3d_knn3d;
+ * missing neighbours: d2=+inf, idx=-1.  out [n_q,2]. */
+int d3d_knn2_batched(const int64_t* ref_ptr, const int* n_ref, const float* queries, int n_q, float* out_d2, int* out_idx, void* stream);
+/* d3d_disc_input with per-query instance pools (fts_ptr[q], pos_ptr[q]); rows with idx<0 are zero. */
+int d3d_disc_input_batched(const int64_t* fts_ptr, const int64_t* pos_ptr, const int* idx, const float* view_fts, const float* centre,
+                           int Q, int K, int D, int ldo, void* out16, int kind, void* stream);
 
 #ifdef __cplusplus
 }

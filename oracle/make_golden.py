@@ -24,7 +24,7 @@ OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 
 
 FF_CONFIGS = {
     "v1_seg16": dict(seed=3, n_steps=5, num_views=1, n_seg=16, seg_kind="voronoi", merge_bias=0.3, weight_seed=0),
-    "v1_seg48": dict(seed=5, n_steps=8, num_views=1, n_seg=48, seg_kind="blocks", merge_bias=0.3, weight_seed=0),
+    "v1_seg48": dict(seed=22, n_steps=6, num_views=1, n_seg=48, seg_kind="blocks", merge_bias=0.55, weight_seed=0),
     "v12_seg16": dict(seed=6, n_steps=2, num_views=12, n_seg=16, seg_kind="voronoi", merge_bias=0.3, weight_seed=0),
 }
 

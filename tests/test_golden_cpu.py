@@ -1,0 +1,52 @@
+"""CPU suite: the oracle restatement vs golden vectors produced by the UNMODIFIED reference (oracle/make_golden.py).
+These run everywhere (no GPU, no /root/reference)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_geometry_vs_reference_vectors():
+    from oracle import geometry as G
+    z = np.load(os.path.join(GOLD, "geometry.npz"))
+    for i, h in enumerate(z["headings"]):
+        rx, ry, rz, d, s = G.unproject_habitat(z["depth"][i], float(h))
+        assert np.array_equal(np.stack([rx, ry, rz, d, s]), z[f"unproj{i}"])
+    assert np.array_equal(np.stack(G.patch_3d_info(z["depth"])), z["info5"])
+    n = len(z["cull_pts"])
+    want = np.unpackbits(z["cull_mask"])[:n].astype(bool)
+    got = G.frustum_mask_habitat(z["cull_pts"], z["cull_depth"].astype(np.float32), z["cull_cam"], float(z["cull_heading"][0]))
+    assert np.array_equal(got, want) and 100 < want.sum() < n
+
+
+def test_vit_restatement_vs_reference_vectors():
+    from dynam3d_b200 import synth
+    from oracle import nn_ops as NN
+    z = np.load(os.path.join(GOLD, "vit_small.npz"))
+    sd = synth.vit_state_dict(9, width=256, layers=3, resolution=112, out_dim=128)
+    x = synth.hash_uniform((2, 3, 112, 112), 77, 2.0)
+    for pre in (False, True):
+        c, p = NN.vit_forward(x, sd, 3, 4, rnd=None, ln_post_on_patches=not pre)
+        assert np.abs(c.numpy() - z["cls_pre" if pre else "cls"]).max() < 2e-5
+        assert np.abs(p.numpy() - z["patch_pre" if pre else "patch"]).max() < 2e-5
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "ff_traj_*.npz"))), ids=os.path.basename)
+def test_feature_fields_oracle_vs_reference_trajectory(path):
+    from oracle import ref_compare as RC
+    from oracle.make_golden import load_ff_fixture
+    cfg, steps, gold = load_ff_fixture(path)
+    _, orc, recs = RC.run_pair(**cfg, steps=steps, with_reference=False)
+    for t, (r, g) in enumerate(zip(recs, gold)):
+        assert RC.snapshots_equal(g["snap"], r["orc"]) == [], f"step {t}"
+        e = r["env_orc"]
+        assert np.allclose(e["batch_instance_relative_position"][0], g["inst_rel"], atol=2e-5, equal_nan=True)
+        assert np.allclose(e["batch_zone_relative_position"][0], g["zone_rel"], atol=2e-5, equal_nan=True)
+        assert np.allclose(e["batch_instance_fts"][0].sum(-1), g["inst_fts_sum"], atol=2e-3)
+        assert np.allclose(e["batch_zone_fts"][0].sum(-1), g["zone_fts_sum"], atol=2e-3)
+        if "knn_idx" in g:
+            assert np.array_equal(r["knn"][1], g["knn_idx"]) and np.array_equal(r["merge"][0].astype(np.uint8), g["merge"])
