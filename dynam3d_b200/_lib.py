@@ -21,6 +21,21 @@ class D3DError(RuntimeError):
     pass
 
 
+class Mlp(ctypes.Structure):
+    _fields_ = [("w0", ctypes.c_void_p), ("b0", ctypes.c_void_p), ("ln_g", ctypes.c_void_p), ("ln_b", ctypes.c_void_p),
+                ("w3", ctypes.c_void_p), ("b3", ctypes.c_void_p),
+                ("k_pad", ctypes.c_int), ("d_hidden", ctypes.c_int), ("d_out", ctypes.c_int), ("kind", ctypes.c_int)]
+
+
+class EncoderLayer(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ("w_in", "b_in", "w_out", "b_out", "n1_g", "n1_b", "w1", "b1", "w2", "b2", "n2_g", "n2_b")]
+
+
+class PoolLevel(ctypes.Structure):
+    _fields_ = [("mlp", Mlp), ("agg", ctypes.c_void_p), ("layers", EncoderLayer * 2), ("norm_g", ctypes.c_void_p), ("norm_b", ctypes.c_void_p),
+                ("norm_eps", ctypes.c_float), ("n_layers", ctypes.c_int), ("d_model", ctypes.c_int), ("n_head", ctypes.c_int)]
+
+
 class GemmArgs(ctypes.Structure):
     _fields_ = [
         ("A", ctypes.c_void_p), ("lda", ctypes.c_int64),
@@ -61,6 +76,7 @@ SIGNATURES = {
     "d3d_cast16": [_P, _L, _P, _L, _I, _I, _I, _P],
     "d3d_attention_simt": [_P, _L, _P, _L, _P, _I, _I, _I, _I, _I, _I, _F, _P],
     "d3d_attention_mma": [_P, _L, _P, _L, _P, _I, _I, _I, _I, _I, _I, _F, _P],
+    "d3d_attention_tc": [_P, _L, _L, _P, _L, _P, _I, _I, _I, _I, _I, _I, _F, _P],
     "d3d_pool_features": [_P, _P, _P, _P, _P, _P, _I, _I, _P, _I, _P],
     "d3d_pool_assemble": [_P, _P, _I, _P, _P, _P, _I, _I, _P, _P],
     "d3d_disc_input": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P],
@@ -71,6 +87,9 @@ SIGNATURES = {
     "d3d_scatter_rows_ptr": [_P, _L, _P, _P, _I, _I, _P],
     "d3d_knn2_batched": [_P, _P, _P, _I, _P, _P, _P],
     "d3d_disc_input_batched": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P],
+    "d3d_pool_workspace_bytes": [_I, _I, _I],
+    "d3d_mlp_ln_gelu": [_P, _P, _L, _I, _P, _P, _P, _L, _P],
+    "d3d_pool_tokens": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, ctypes.c_size_t, _P, _P],
 }
 OPTIONAL = set()
 
@@ -83,7 +102,7 @@ def _declare(lib_):
                 continue
             raise D3DLibraryError(f"{LIB_PATH} does not export {name}: stale build?")
         fn.argtypes = argtypes
-        fn.restype = ctypes.c_int
+        fn.restype = ctypes.c_size_t if name == "d3d_pool_workspace_bytes" else ctypes.c_int
 
 
 def lib():

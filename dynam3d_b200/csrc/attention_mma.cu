@@ -1,15 +1,24 @@
 // Tensor-core flash attention (online softmax) over packed variable-length sequences: mma.sync m16n8k16, fp32 accumulate.
-// One CTA = 64 queries of one (sequence, head): 4 warps x 16 query rows; K/V streamed in 64-key tiles through shared
-// memory (ldmatrix / ldmatrix.trans fragments); S = QK^T and O += PV stay in registers (P re-used as the A fragment).
+// One CTA = 128 queries of one (sequence, head): 8 warps x 16 query rows; K/V streamed in 64-key tiles through a
+// double-buffered cp.async pipeline in shared memory (ldmatrix / ldmatrix.trans fragments); S = QK^T and O += PV stay in registers (P re-used as the A fragment).
 // Used for CLIP ViT (CLIPM:181-183: 577 tokens, 16 heads x 64) and the Phi-3 prefill (causal, 32 heads x 96).
 // TODO(next round): tcgen05 version (S and O in TMEM); this legacy-HMMA kernel is ~8 % of the step's FLOPs.
 #include "common.cuh"
 
 namespace {
 
-constexpr int BQ = 64;
+constexpr int NWARPS = 8;
+constexpr int BQ = 16 * NWARPS;  // 128 query rows per CTA
 constexpr int BKV = 64;
-constexpr int NTHREADS = 128;
+constexpr int NTHREADS = 32 * NWARPS;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+  // 16-byte async copy; src_bytes = 0 zero-fills (rows past the end of the sequence)
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
@@ -36,9 +45,9 @@ __global__ void __launch_bounds__(NTHREADS) attn_mma_kernel(const uint16_t* __re
   constexpr int LDS = D + 8;  // padded row (halves): 16-byte aligned rows, conflict-free ldmatrix
   constexpr int KS = D / 16;  // k-steps over head dim
   constexpr int DT = D / 8;   // output n-tiles
-  __shared__ __align__(16) uint16_t sQ[BQ * LDS];
-  __shared__ __align__(16) uint16_t sK[BKV * LDS];
-  __shared__ __align__(16) uint16_t sV[BKV * LDS];
+  extern __shared__ __align__(16) uint16_t smem_attn[];
+  uint16_t* sQ = smem_attn;                       // [BQ][LDS]
+  uint16_t* sKV = smem_attn + BQ * LDS;           // 2 stages x {K [BKV][LDS], V [BKV][LDS]}
 
   const int seq = blockIdx.z, h = blockIdx.y;
   const int b = cu[seq], len = cu[seq + 1] - b;
@@ -73,22 +82,34 @@ __global__ void __launch_bounds__(NTHREADS) attn_mma_kernel(const uint16_t* __re
   const int row0 = q0 + warp * 16 + g, row1 = row0 + 8;
 
   const int kmax = causal ? min(len, q0 + BQ) : len;
-  for (int c0 = 0; c0 < kmax; c0 += BKV) {
-    __syncthreads();
+  const int n_tiles = (kmax + BKV - 1) / BKV;
+  auto load_tile = [&](int tile, int stage) {
+    const int c0 = tile * BKV;
+    uint16_t* dK = sKV + stage * 2 * BKV * LDS;
+    uint16_t* dV = dK + BKV * LDS;
     for (int i = threadIdx.x; i < BKV * CPR; i += NTHREADS) {
       const int r = i / CPR, c = i % CPR;
-      uint4 kv = make_uint4(0, 0, 0, 0), vv = kv;
-      if (c0 + r < len) {
-        const uint16_t* rowp = qkv + (size_t)(b + c0 + r) * ld;
-        kv = *reinterpret_cast<const uint4*>(rowp + koff + c * 8);
-        vv = *reinterpret_cast<const uint4*>(rowp + voff + c * 8);
-      }
-      *reinterpret_cast<uint4*>(&sK[r * LDS + c * 8]) = kv;
-      *reinterpret_cast<uint4*>(&sV[r * LDS + c * 8]) = vv;
+      const bool ok = c0 + r < len;
+      const uint16_t* rowp = qkv + (size_t)(b + (ok ? c0 + r : 0)) * ld;
+      cp_async16(smem_u32(&dK[r * LDS + c * 8]), rowp + koff + c * 8, ok ? 16 : 0);
+      cp_async16(smem_u32(&dV[r * LDS + c * 8]), rowp + voff + c * 8, ok ? 16 : 0);
+    }
+    cp_async_commit();
+  };
+  load_tile(0, 0);
+  for (int tile = 0; tile < n_tiles; ++tile) {
+    const int c0 = tile * BKV;
+    if (tile + 1 < n_tiles) {
+      load_tile(tile + 1, (tile + 1) & 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
     __syncthreads();
-    if (causal && c0 > q0 + warp * 16 + 15) continue;  // whole tile above the diagonal for this warp (warp-uniform)
-
+    const uint16_t* sK = sKV + (tile & 1) * 2 * BKV * LDS;
+    const uint16_t* sV = sK + BKV * LDS;
+    const bool active = !(causal && c0 > q0 + warp * 16 + 15);  // whole tile above the diagonal for this warp (warp-uniform)
+    if (active) {
     // ---- S = Q K^T (16 x 64 per warp) ----
     float s[8][4];
 #pragma unroll
@@ -156,6 +177,8 @@ __global__ void __launch_bounds__(NTHREADS) attn_mma_kernel(const uint16_t* __re
         mma16816<KIND>(o[2 * dp + 1], pf[kk], b2, b3);
       }
     }
+    }  // active
+    __syncthreads();  // everyone is done with this stage before tile+2 overwrites it
   }
   const float inv0 = l0 > 0.f ? 1.0f / l0 : 0.f, inv1 = l1 > 0.f ? 1.0f / l1 : 0.f;
 #pragma unroll
@@ -171,10 +194,17 @@ int launch(const void* qkv, long long ld, void* out, long long ldo, const int* c
            float scale, cudaStream_t st) {
   dim3 grid(d3d_cdiv(max_len, BQ), H, n_seq);
   const float sl2 = scale * 1.4426950408889634f;
+  constexpr int SMEM = (BQ + 4 * BKV) * (D + 8) * 2;
+  static bool attr_set = false;
+  if (!attr_set) {
+    D3D_CHECK_CUDA(cudaFuncSetAttribute(attn_mma_kernel<D, D3D_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    D3D_CHECK_CUDA(cudaFuncSetAttribute(attn_mma_kernel<D, D3D_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    attr_set = true;
+  }
   if (kind == D3D_BF16)
-    attn_mma_kernel<D, D3D_BF16><<<grid, NTHREADS, 0, st>>>((const uint16_t*)qkv, ld, (uint16_t*)out, ldo, cu, H, causal, sl2);
+    attn_mma_kernel<D, D3D_BF16><<<grid, NTHREADS, SMEM, st>>>((const uint16_t*)qkv, ld, (uint16_t*)out, ldo, cu, H, causal, sl2);
   else
-    attn_mma_kernel<D, D3D_F16><<<grid, NTHREADS, 0, st>>>((const uint16_t*)qkv, ld, (uint16_t*)out, ldo, cu, H, causal, sl2);
+    attn_mma_kernel<D, D3D_F16><<<grid, NTHREADS, SMEM, st>>>((const uint16_t*)qkv, ld, (uint16_t*)out, ldo, cu, H, causal, sl2);
   D3D_CHECK_LAUNCH();
   return 0;
 }

@@ -18,6 +18,7 @@ Design (B200-first, not a translation):
     The reference's index quirks are reproduced literally.
 There is no CPU fallback: without the CUDA library / an sm_100 device construction fails.
 """
+import ctypes
 import math
 
 import numpy as np
@@ -181,7 +182,7 @@ class Feature_Fields(nn.Module):
                                                           nn.Linear(4 * width, 2))
         for p in self.parameters():
             p.requires_grad_(False)
-        self._ring, self._ring_i, self._tomb = None, 0, None
+        self._ring, self._ring_i, self._tomb, self._ws = None, 0, None, None
         self.segmenter = None  # callable(batch_image) -> int64 [N,24,24]; FastSAM (FF:400-430) is outside the hot path
         self._W = None
         self.reset(batch_size)
@@ -295,7 +296,26 @@ class Feature_Fields(nn.Module):
             "i2z_enc": enc(self.aggregate_instance_to_zone_encoder),
             "disc": mlp(self.instance_merge_discriminator, 1544),
         }
-        # the discriminator's last layer has N = 2: pad nothing, the GEMM masks columns
+        kind = L.kind_of(dt)
+
+        def c_mlp(m):
+            return L.Mlp(m["w0"].data_ptr(), m["b0"].data_ptr(), m["g"].data_ptr(), m["b"].data_ptr(), m["w3"].data_ptr(), m["b3"].data_ptr(),
+                         m["w0"].shape[1], m["w0"].shape[0], m["w3"].shape[0], kind)
+
+        def c_level(m, agg, e):
+            lv = L.PoolLevel()
+            lv.mlp = c_mlp(m)
+            lv.agg = agg.data_ptr()
+            for i, l in enumerate(e["layers"]):
+                lv.layers[i] = L.EncoderLayer(l["w_in"].data_ptr(), l["b_in"].data_ptr(), l["w_out"].data_ptr(), l["b_out"].data_ptr(),
+                                              l["n1"][0].data_ptr(), l["n1"][1].data_ptr(), l["w1"].data_ptr(), l["b1"].data_ptr(),
+                                              l["w2"].data_ptr(), l["b2"].data_ptr(), l["n2"][0].data_ptr(), l["n2"][1].data_ptr())
+            lv.norm_g, lv.norm_b, lv.norm_eps = e["norm"][0].data_ptr(), e["norm"][1].data_ptr(), e["eps"]
+            lv.n_layers, lv.d_model, lv.n_head = len(e["layers"]), D, D // 64
+            return lv
+        self._W["c_levels"] = (c_level(self._W["p2i_mlp"], self._W["p2i_agg"], self._W["p2i_enc"]),
+                               c_level(self._W["i2z_mlp"], self._W["i2z_agg"], self._W["i2z_enc"]))
+        self._W["c_disc"] = c_mlp(self._W["disc"])
         return self._W
 
     # ------------------------------------------------------------------ neural blocks (packed variable-length batches)
@@ -382,13 +402,27 @@ class Feature_Fields(nn.Module):
         up = self._upload(arrs)
         tok_src_d, tok_seq_d, cu_d, ptrs_d = up[:4]
         centre_dev = up[4] if isinstance(centre, np.ndarray) else centre
-        dev = self.device
-        A0 = torch.empty((T, 8), device=dev, dtype=self.compute_dtype)
-        ops.pool_features(ptrs_d[0], ptrs_d[1], ptrs_d[2], centre_dev, tok_seq_d, tok_src_d, T, mode, A0)
-        emb = self._mlp(A0, mlp)
-        X = torch.empty((T, D), device=dev, dtype=torch.float32)
-        ops.pool_assemble(emb, ptrs_d[3], fts_is_f32, tok_seq_d, tok_src_d, agg, T, X)
-        return self._encode(X, cu_d, n_seq, int(lens.max()), enc), centre_dev
+        out = torch.empty((n_seq, D), device=self.device, dtype=torch.float32)
+        ws = self._workspace(int(L.lib().d3d_pool_workspace_bytes(T, D, D)))
+        lv = W["c_levels"][level]
+        L.check(L.lib().d3d_pool_tokens(ctypes.addressof(lv), L.ptr(ptrs_d), L.ptr(centre_dev), L.ptr(tok_seq_d), L.ptr(tok_src_d), L.ptr(cu_d), T, n_seq,
+                                        int(lens.max()), mode, int(fts_is_f32), L.ptr(ws), ws.numel(), L.ptr(out), L.stream_ptr()))
+        return out, centre_dev
+
+    def _workspace(self, nbytes):
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = torch.empty(max(nbytes, 64 << 20), device=self.device, dtype=torch.uint8)
+        return self._ws
+
+    def _disc_logits(self, A):
+        """instance_merge_discriminator on 16-bit rows A [R,1544] -> fp32 logits [R,2] (FF:618)."""
+        R = A.shape[0]
+        W = self._weights()
+        h32 = torch.empty((R, 4 * D), device=self.device, dtype=torch.float32)
+        h16 = torch.empty((R, 4 * D), device=self.device, dtype=self.compute_dtype)
+        out = torch.empty((R, 4), device=self.device, dtype=torch.float32)
+        L.check(L.lib().d3d_mlp_ln_gelu(ctypes.addressof(W["c_disc"]), L.ptr(A), A.stride(0), R, L.ptr(h32), L.ptr(h16), L.ptr(out), 4, L.stream_ptr()))
+        return out[:, :2]
 
     # ------------------------------------------------------------------ FF:296-326
     def get_patch_3d_info(self, batch_depth_map):
@@ -580,7 +614,7 @@ class Feature_Fields(nn.Module):
             A = torch.empty((2 * n_seq, 1544), device=dev, dtype=self.compute_dtype)
             L.check(lib.d3d_disc_input_batched(L.ptr(up[6]), L.ptr(up[5]), L.ptr(idx_d), L.ptr(view_fts), L.ptr(centres), n_seq, 2, D, 1544,
                                                L.ptr(A), L.kind_of(A.dtype), L.stream_ptr()))
-            logits_d = self._mlp(A, W["disc"])  # [2*n_seq, 2]
+            logits_d = self._disc_logits(A)  # [2*n_seq, 2]
             res[:, 7:11] = logits_d.reshape(n_seq, 4)
             res[:, 3:5] = d2_d
             res[:, 5:7] = idx_d.view(torch.float32)
@@ -716,6 +750,15 @@ class Feature_Fields(nn.Module):
         lo = np.searchsorted(sorted_code, uniq, side="left")
         hi = np.searchsorted(sorted_code, uniq, side="right")
         zone_ids = ep.free_zone_ids(len(uniq))
+        # per-voxel member centroids in fp64 (exact for fp32 inputs, so any summation order gives the same fp32 result)
+        cnt = (hi - lo).astype(np.float64)
+        csum = np.concatenate([np.zeros((1, 3)), np.cumsum(slot_pos[order].astype(np.float64), axis=0)], 0) if len(order) else np.zeros((1, 3))
+        with np.errstate(all="ignore"):
+            mean_pos = ((csum[hi] - csum[lo]) / cnt[:, None]).astype(F32)  # empty voxel -> 0/0 = NaN (Q5)
+        v = uniq.copy()
+        vz = v % _VM; v //= _VM
+        vy = v % _VM; vx = v // _VM
+        keys = ((np.stack([vx, vy, vz], 1) - _VOFF).astype(F32) * F32(self.args.zone_x_length) + F32(self.args.zone_x_length / 2)).astype(F32)
         zi = 0
         for j, code in enumerate(uniq.tolist()):
             members = order[lo[j]:hi[j]]  # ascending slot order (stable sort)
@@ -727,11 +770,10 @@ class Feature_Fields(nn.Module):
                 ep.zone_alive[zid] = True
                 slot = ep.n_zone  # Q3: a new zone is always appended, whatever its id
                 ep.n_zone += 1
-                zones.append((b, slot, members, False, _mean64(slot_pos[members])))
+                zones.append((b, slot, members, False, mean_pos[j]))
             else:
                 ep.z2i[zid] = members
-                key = np.asarray(_code_to_key(code), F32)
-                zones.append((b, zid, members, True, _mean64(np.repeat(key[None], max(len(members), 0), 0))))  # Q5
+                zones.append((b, zid, members, True, keys[j] if len(members) else np.full(3, np.nan, F32)))  # Q5: mean of identical keys
         return news
 
     # ------------------------------------------------------------------ FF:818-862

@@ -176,6 +176,11 @@ int d3d_attention_simt(const void* qkv, int64_t ld, void* out, int64_t ldo, cons
 int d3d_attention_mma(const void* qkv, int64_t ld, void* out, int64_t ldo, const int* cu_seqlens, int n_seq, int max_len, int H,
                       int Dh, int causal, int kind, float scale, void* stream);
 
+/* tcgen05 flash attention (S = QK^T and O = PV on the 5th-gen tensor cores, accumulators in TMEM, Q/K/V tiles by TMA), head_dim 64,
+ * same packed-QKV contract as d3d_attention_simt; n_rows = total rows T of the qkv matrix (for the TMA descriptor). */
+int d3d_attention_tc(const void* qkv, int64_t ld, int64_t n_rows, void* out, int64_t ldo, const int* cu_seqlens, int n_seq,
+                     int max_len, int H, int Dh, int causal, int kind, float scale, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Token builders for the layer-wise pooling (patch -> instance -> zone) and the merge discriminator.
  * Sequences of several episodes are packed in one batch; seq_* are per-sequence base addresses (device pointers
@@ -214,6 +219,41 @@ int d3d_knn2_batched(const int64_t* ref_ptr, const int* n_ref, const float* quer
 /* d3d_disc_input with per-query instance pools (fts_ptr[q], pos_ptr[q]); rows with idx<0 are zero. */
 int d3d_disc_input_batched(const int64_t* fts_ptr, const int64_t* pos_ptr, const int* idx, const float* view_fts, const float* centre,
                            int Q, int K, int D, int ldo, void* out16, int kind, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * One-call pooling pass (host orchestration inside the library): all segments / zones of a view, all episodes.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {            /* nn.Sequential(Linear, LayerNorm, GELU, Linear) (FF:139-143,148-152,157-161; POL:83-111) */
+  const void* w0; const float* b0;      /* [d_hidden, k_pad] 16-bit (K zero-padded to a multiple of 8), [d_hidden] */
+  const float* ln_g; const float* ln_b; /* [d_hidden] */
+  const void* w3; const float* b3;      /* [d_out, d_hidden] 16-bit, [d_out] */
+  int k_pad, d_hidden, d_out, kind;
+} d3d_mlp;
+typedef struct {            /* one nn.TransformerEncoderLayer, post-norm, GELU (FF:134-137) */
+  const void* w_in; const float* b_in;    /* [3d, d], [3d] */
+  const void* w_out; const float* b_out;  /* [d, d], [d] */
+  const float* n1_g; const float* n1_b;
+  const void* w1; const float* b1;        /* [4d, d], [4d] */
+  const void* w2; const float* b2;        /* [d, 4d], [d] */
+  const float* n2_g; const float* n2_b;
+} d3d_encoder_layer;
+typedef struct {            /* position MLP + aggregate token + 2-layer encoder + final norm of one pooling level */
+  d3d_mlp mlp;
+  const float* agg;                       /* [d] learned aggregate token (FF:145,154) */
+  d3d_encoder_layer layers[2];
+  const float* norm_g; const float* norm_b; float norm_eps;
+  int n_layers, d_model, n_head;
+} d3d_pool_level;
+
+size_t d3d_pool_workspace_bytes(int T, int d_model, int d_hidden_mlp);
+/* out[T, ldo] = Linear(GELU(LN(Linear(A0)))) with fp32 accumulate; hidden32 [T,d_hidden] fp32 and hidden16 [T,d_hidden] 16-bit scratch. */
+int d3d_mlp_ln_gelu(const d3d_mlp* m_h, const void* A0, int64_t lda, int T, void* hidden32, void* hidden16, float* out, int64_t ldo,
+                    void* stream);
+/* features -> MLP -> assemble -> encoder -> out [n_seq, d_model] (token 0 of every sequence).  seq_ptrs [4, n_seq] int64 device
+ * table (xyz, dir, scale, fts base addresses per sequence); other arguments as d3d_pool_features / d3d_pool_assemble. */
+int d3d_pool_tokens(const d3d_pool_level* lvl_h, const int64_t* seq_ptrs, const float* centre, const int* tok_seq, const int* tok_src,
+                    const int* cu_seqlens, int T, int n_seq, int max_len, int mode, int fts_is_f32, void* workspace,
+                    size_t workspace_bytes, float* out, void* stream);
 
 #ifdef __cplusplus
 }
