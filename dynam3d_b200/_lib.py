@@ -65,6 +65,7 @@ SIGNATURES = {
     "d3d_knn3d": [_P, _I, _P, _I, _I, _P, _P, _P],
     "d3d_seq_centroid": [_P, _P, _P, _I, _P, _P],
     "d3d_env_export": [_P, _P, _P, _I, _P, _F, _I, _P, _P, _P, _P],
+    "d3d_segm_relabel": [_P, _I, _I, _I, _I, _I, _I, _IP, _IP, _P, _P, _P],
     "d3d_layernorm": [_P, _L, _P, _P, _P, _F, _I, _I, _I, _P, _L, _P, _L, _I, _P],
     "d3d_rmsnorm": [_P, _L, _P, _P, _F, _I, _I, _P, _L, _P, _L, _I, _P],
     "d3d_rope": [_P, _L, _P, _P, _I, _I, _I, _I, _P],
@@ -90,6 +91,12 @@ SIGNATURES = {
     "d3d_pool_workspace_bytes": [_I, _I, _I],
     "d3d_mlp_ln_gelu": [_P, _P, _L, _I, _P, _P, _P, _L, _P],
     "d3d_pool_tokens": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, ctypes.c_size_t, _P, _P],
+    "d3d_ffh_create": [_I, _I, _F], "d3d_ffh_destroy": [_P], "d3d_ffh_reset": [_P, _I], "d3d_ffh_pop": [_P, _I],
+    "d3d_ffh_counts": [_P, _I, _P], "d3d_ffh_cull": [_P, _I, _P, _L, _P, _P, _P, _P], "d3d_ffh_set_tree": [_P],
+    "d3d_ffh_begin_view": [_P] * 3 + [_I] + [_P] * 11,
+    "d3d_ffh_finish_view": [_P, _P, _P, _P], "d3d_ffh_fetch_view": [_P] * 17, "d3d_ffh_zone_key_array": [_P, _I, _P],
+    "d3d_ffh_get_map": [_P, _I, _I, _P, _P, _P, _P], "d3d_ffh_get_p2i": [_P, _I, _P], "d3d_ffh_get_patch_pos": [_P, _I, _P],
+    "d3d_ffh_get_zone_keys": [_P, _I, _P, _P, _P], "d3d_ffh_get_last": [_P, _I, _P, _P, _P, _P],
 }
 OPTIONAL = set()
 
@@ -102,7 +109,7 @@ def _declare(lib_):
                 continue
             raise D3DLibraryError(f"{LIB_PATH} does not export {name}: stale build?")
         fn.argtypes = argtypes
-        fn.restype = ctypes.c_size_t if name == "d3d_pool_workspace_bytes" else ctypes.c_int
+        fn.restype = {"d3d_pool_workspace_bytes": ctypes.c_size_t, "d3d_ffh_create": ctypes.c_void_p, "d3d_ffh_destroy": None}.get(name, ctypes.c_int)
 
 
 def lib():

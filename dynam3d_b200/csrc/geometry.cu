@@ -498,3 +498,49 @@ extern "C" int d3d_env_export(const float* pos, const float* fts, const int* ids
   D3D_CHECK_LAUNCH();
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// a7: FastSAM masks -> 24x24 dense segment labels (FF:411-422).  One block per image.
+//   paint masks in order (later mask wins; pixels in no mask keep label 0), nearest-resize to gh x gw, relabel the labels
+//   that occur to 0..G-1 in ascending order.
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct SegIdx { int r[32]; int c[32]; };
+
+__global__ void __launch_bounds__(1024) segm_relabel_kernel(const uint8_t* __restrict__ masks, int M, int H, int W, SegIdx si, int gh, int gw,
+                                                            long long* __restrict__ out, int* __restrict__ n_seg) {
+  extern __shared__ int present[];  // [M+1] occurrence flags, then exclusive ranks
+  const int img = blockIdx.x;
+  const uint8_t* mk = masks + (size_t)img * M * H * W;
+  const int r = threadIdx.y, c = threadIdx.x;
+  const int tid = r * blockDim.x + c;
+  for (int i = tid; i <= M; i += blockDim.x * blockDim.y) present[i] = 0;
+  __syncthreads();
+  int label = 0;
+  if (r < gh && c < gw) {
+    const size_t pix = (size_t)si.r[r] * W + si.c[c];
+    for (int g = M - 1; g >= 0; --g)
+      if (mk[(size_t)g * H * W + pix]) { label = g; break; }
+    present[label] = 1;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int i = 0; i < M; ++i) { const int p = present[i]; present[i] = run; run += p; }
+    n_seg[img] = run;
+  }
+  __syncthreads();
+  if (r < gh && c < gw) out[(size_t)img * gh * gw + r * gw + c] = (long long)present[label];
+}
+}  // namespace
+
+extern "C" int d3d_segm_relabel(const uint8_t* masks, int n_img, int M, int H, int W, int gh, int gw, const int* row_idx_h,
+                                const int* col_idx_h, int64_t* out, int* n_seg, void* stream) {
+  D3D_REQUIRE(masks && out && n_seg && row_idx_h && col_idx_h && n_img > 0 && M > 0, "args");
+  D3D_REQUIRE(gh <= 32 && gw <= 32 && M <= 8192, "grid up to 32x32, at most 8192 masks");
+  SegIdx si;
+  for (int i = 0; i < 32; ++i) { si.r[i] = i < gh ? row_idx_h[i] : 0; si.c[i] = i < gw ? col_idx_h[i] : 0; }
+  segm_relabel_kernel<<<n_img, dim3(32, 32), (M + 1) * sizeof(int), (cudaStream_t)stream>>>(masks, M, H, W, si, gh, gw, (long long*)out, n_seg);
+  D3D_CHECK_LAUNCH();
+  return 0;
+}

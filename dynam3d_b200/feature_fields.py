@@ -13,8 +13,9 @@ Design (B200-first, not a translation):
     2-layer post-norm encoder with a varlen attention kernel;
   * torch_kdtree (rebuilt after every view, FF:396,815) is replaced by an exact brute-force K-NN kernel over the
     instance slots -- no tree, nothing to rebuild;
-  * the discrete bookkeeping (ids, member lists, zone keys; FF:362-393, 623-756) stays on the host in numpy, fed by ONE
-    small device->host copy per view (centroids, K-NN indices, merge logits) instead of one `.cpu()` per segment/zone.
+  * the discrete bookkeeping (ids, member lists, zone keys; FF:362-393, 623-756) stays on the host -- in the library's C++ planner
+    (csrc/ff_host.cu) -- fed by ONE small device->host copy per view (centroids, K-NN indices, merge logits) instead of one
+    `.cpu()` per segment / zone.
     The reference's index quirks are reproduced literally.
 There is no CPU fallback: without the CUDA library / an sm_100 device construction fails.
 """
@@ -66,94 +67,19 @@ class _Pool:
 
 
 class _Episode:
+    """Device pools of one episode.  The integer state (ids, member lists, zone keys) lives in the C++ planner (ff_host.cu)."""
+
     def __init__(self, device):
         self.patch_pos = _Pool(3, torch.float32, device, 8192)
         self.patch_dir = _Pool(0, torch.float32, device, 8192)
         self.patch_scale = _Pool(0, torch.float32, device, 8192)
         self.patch_fts = _Pool(D, torch.float16, device, 8192)
-        self.n_patch = 0
-        self.patch_pos_h = np.zeros((8192, 3), F32)
-        self.p2i = np.full((8192,), -1, np.int64)  # patch id -> instance id (-1 = not a key), FF:168
-        self.n_p2i = 0
-        self.i2p = {}  # instance id -> member patch ids (insertion ordered like the reference dict), FF:172
-        self.inst_alive = np.zeros((1024,), bool)  # id in i2p
         self.inst_pos = _Pool(3, torch.float32, device, 1024)
         self.inst_fts = _Pool(D, torch.float32, device, 1024)
-        self.inst_pos_h = np.zeros((1024, 3), F32)
-        self.n_inst = 0
         self.zone_pos = _Pool(3, torch.float32, device, 256)
         self.zone_fts = _Pool(D, torch.float32, device, 256)
-        self.n_zone = 0
-        self.zone_code_to_id = {}  # voxel code (int) -> zone id; `zone_key_to_id` exposes the reference's float-tuple keys
-        self.z2i = {}
-        self.zone_alive = np.zeros((256,), bool)  # id in z2i
+        self.n_patch = self.n_inst = self.n_zone = 0
         self.tree = False
-        self.last = {}
-
-    @property
-    def zone_key_to_id(self):
-        return {_code_to_key(c): z for c, z in self.zone_code_to_id.items()}
-
-    def grow_host(self, n_patch=None, n_inst=None):
-        if n_patch is not None and n_patch > len(self.patch_pos_h):
-            cap = len(self.patch_pos_h)
-            while cap < n_patch:
-                cap *= 2
-            a = np.zeros((cap, 3), F32); a[: len(self.patch_pos_h)] = self.patch_pos_h; self.patch_pos_h = a
-            m = np.full((cap,), -1, np.int64); m[: len(self.p2i)] = self.p2i; self.p2i = m
-        if n_inst is not None and n_inst > len(self.inst_pos_h):
-            cap = len(self.inst_pos_h)
-            while cap < n_inst:
-                cap *= 2
-            a = np.zeros((cap, 3), F32); a[: len(self.inst_pos_h)] = self.inst_pos_h; self.inst_pos_h = a
-
-    @staticmethod
-    def _lowest_free(alive, n_keys, n):
-        """FF:433-475: the n lowest non-negative ints that are not dict keys (`alive` marks the keys)."""
-        need = n_keys + n
-        if need > len(alive):
-            return None
-        return np.flatnonzero(~alive[:need])[:n].astype(np.int64)
-
-    def free_instance_ids(self, n):
-        if len(self.i2p) + n > len(self.inst_alive):
-            a = np.zeros((max(2 * len(self.inst_alive), len(self.i2p) + n),), bool); a[: len(self.inst_alive)] = self.inst_alive; self.inst_alive = a
-        return self._lowest_free(self.inst_alive, len(self.i2p), n)
-
-    def free_zone_ids(self, n):
-        if len(self.z2i) + n > len(self.zone_alive):
-            a = np.zeros((max(2 * len(self.zone_alive), len(self.z2i) + n),), bool); a[: len(self.zone_alive)] = self.zone_alive; self.zone_alive = a
-        return self._lowest_free(self.zone_alive, len(self.z2i), n)
-
-
-_VOFF, _VM = 1 << 20, 1 << 21
-
-
-def _voxel_codes(pos, length=2.0):
-    """Integer code of the 2 m voxel of each position, monotone in the lexicographic (x, y, z) order of the reference's
-    float keys `(p // L) * L + L/2` (FF:694-695), so np.unique(codes) == torch.unique(keys, dim=0) order."""
-    with np.errstate(all="ignore"):
-        v = np.floor(np.asarray(pos, dtype=F32) / F32(length)).astype(np.int64) + _VOFF
-    return (v[:, 0] * _VM + v[:, 1]) * _VM + v[:, 2]
-
-
-def _code_to_key(c, length=2.0):
-    z = c % _VM; c //= _VM
-    y = c % _VM; x = c // _VM
-    return tuple(float(F32(F32(F32(v - _VOFF) * F32(length)) + F32(length / 2))) for v in (x, y, z))
-
-
-def _zone_keys(pos, length=2.0):
-    p = np.asarray(pos, dtype=F32)
-    with np.errstate(all="ignore"):
-        return ((np.floor(p / F32(length)).astype(F32) * F32(length)).astype(F32) + F32(length / 2)).astype(F32)
-
-
-def _mean64(x):
-    x = np.asarray(x, dtype=np.float64).reshape(-1, 3)
-    if len(x) == 0:
-        return np.full((3,), np.nan, F32)
-    return (x.sum(0) / len(x)).astype(F32)
 
 
 class Feature_Fields(nn.Module):
@@ -191,12 +117,17 @@ class Feature_Fields(nn.Module):
     def reset(self, batch_size=1):
         self.batch_size = batch_size
         self.eps = [_Episode(self.device) for _ in range(batch_size)]
+        if getattr(self, "_h", None):
+            L.check(L.lib().d3d_ffh_reset(self._h, batch_size))
+        else:
+            self._h = L.lib().d3d_ffh_create(batch_size, self.args.num_proposal_instances, self.args.zone_x_length)
         self.keep_target_waypoint = [None for _ in range(batch_size)]
         self.history_actions = [["none\n"] * 4] * batch_size  # Q10: the reference aliases one list across the batch
 
     def pop(self, index):
         self.batch_size -= 1
         self.eps.pop(index)
+        L.check(L.lib().d3d_ffh_pop(self._h, index))
         self.keep_target_waypoint.pop(index)
         self.history_actions.pop(index)
 
@@ -206,8 +137,18 @@ class Feature_Fields(nn.Module):
 
     def delete_feature_fields(self):
         self.eps = []
+        L.check(L.lib().d3d_ffh_reset(self._h, 0))
         self.keep_target_waypoint = []
         self.history_actions = []
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                L.lib().d3d_ffh_destroy(h)
+            except Exception:
+                pass
+            self._h = None
 
     def load_state_dict(self, state_dict, strict=True):
         # Q12: convert_ckpt.py keeps Pretrain-only keys (nerf_*, patch_to_nerf_*) that this module does not own
@@ -217,22 +158,64 @@ class Feature_Fields(nn.Module):
         self._W = None
         return out
 
-    # reference-style views of the state (read-only helpers for callers / tests)
+    # reference-style views of the state (read-only helpers for callers / tests), rebuilt from the C++ planner on demand
+    def _map(self, b, which):
+        sizes = np.zeros(2, np.int64)
+        lib = L.lib()
+        L.check(lib.d3d_ffh_get_map(self._h, b, which, None, None, None, sizes.ctypes.data))
+        ids = np.zeros(max(int(sizes[0]), 1), np.int64); lens = np.zeros_like(ids); cat = np.zeros(max(int(sizes[1]), 1), np.int64)
+        L.check(lib.d3d_ffh_get_map(self._h, b, which, ids.ctypes.data, lens.ctypes.data, cat.ctypes.data, sizes.ctypes.data))
+        out, off = {}, 0
+        for i in range(int(sizes[0])):
+            out[int(ids[i])] = cat[off:off + int(lens[i])].copy()
+            off += int(lens[i])
+        return out
+
+    def _p2i(self, b):
+        n = self.eps[b].n_patch
+        a = np.zeros(max(n, 1), np.int64)
+        L.check(L.lib().d3d_ffh_get_p2i(self._h, b, a.ctypes.data))
+        return a[:n]
+
+    def _zone_keys_dict(self, b):
+        n = np.zeros(1, np.int64)
+        L.check(L.lib().d3d_ffh_get_zone_keys(self._h, b, None, None, n.ctypes.data))
+        keys = np.zeros((max(int(n[0]), 1), 3), F32); ids = np.zeros(max(int(n[0]), 1), np.int64)
+        L.check(L.lib().d3d_ffh_get_zone_keys(self._h, b, keys.ctypes.data, ids.ctypes.data, n.ctypes.data))
+        return {tuple(float(x) for x in keys[i]): int(ids[i]) for i in range(int(n[0]))}
+
+    def _last(self, b):
+        cnt = np.zeros(8, np.int64)
+        L.check(L.lib().d3d_ffh_counts(self._h, b, cnt.ctypes.data))
+        K = int(cnt[7])
+        if K < 0:
+            return {}
+        n = np.zeros(2, np.int64)
+        L.check(L.lib().d3d_ffh_get_last(self._h, b, None, None, None, n.ctypes.data))
+        d2 = np.zeros(max(int(n[0]), 1), F32); idx = np.zeros(max(int(n[0]), 1), np.int32); mg = np.zeros(max(int(n[0]), 1), np.uint8)
+        L.check(L.lib().d3d_ffh_get_last(self._h, b, d2.ctypes.data, idx.ctypes.data, mg.ctypes.data, n.ctypes.data))
+        G = int(n[1])
+        return {"knn": (d2[:G * K].reshape(G, K), idx[:G * K].reshape(G, K)), "merge": mg[:G * K].reshape(G, K).astype(bool)}
+
     @property
     def global_instance_to_patch_dict(self):
-        return [ep.i2p for ep in self.eps]
+        return [self._map(b, 0) for b in range(self.batch_size)]
 
     @property
     def global_zone_to_instance_dict(self):
-        return [ep.z2i for ep in self.eps]
+        return [self._map(b, 1) for b in range(self.batch_size)]
 
     @property
     def global_zone_key_to_id(self):
-        return [ep.zone_key_to_id for ep in self.eps]
+        return [self._zone_keys_dict(b) for b in range(self.batch_size)]
 
     @property
     def global_patch_to_instance_dict(self):
-        return [{int(k): int(ep.p2i[k]) for k in np.flatnonzero(ep.p2i[: ep.n_patch] >= 0)} for ep in self.eps]
+        out = []
+        for b in range(self.batch_size):
+            a = self._p2i(b)
+            out.append({int(k): int(a[k]) for k in np.flatnonzero(a >= 0)})
+        return out
 
     @property
     def global_patch_position(self):
@@ -377,37 +360,22 @@ class Feature_Fields(nn.Module):
             out.append(t.view(a.shape) if a.ndim > 1 else t)
         return out
 
-    def _run_sequences(self, member_rows, xyz_ptrs, dir_ptrs, scale_ptrs, fts_ptrs, fts_is_f32, centre, mode, level):
-        """Generic packed pooling: sequence s gathers rows `member_rows[s]` (np int arrays) from its own base pointers.
-        centre: device fp32 [n_seq,3] or a numpy [n_seq,3] (uploaded with the index arrays).
-        Returns fp32 [n_seq,768] (token 0 of each encoded sequence)."""
+    def _pool_pass(self, tok_src, tok_seq, cu, ptrs, centre, n_seq, max_len, mode, level, fts_is_f32, extra=()):
+        """One packed pooling pass (FF:580-597 / 662-688 / 717-756).  tok_src / tok_seq / cu: numpy int32 token arrays; ptrs: numpy int64
+        [4, n_seq] (xyz, dir, scale, fts base address per sequence); centre: device fp32 [n_seq,3] or numpy (uploaded along).
+        `extra`: more numpy arrays to ride on the same upload.  Returns (fp32 [n_seq,768], centre_dev, uploaded extras)."""
         W = self._weights()
-        mlp, agg, enc = (W["p2i_mlp"], W["p2i_agg"], W["p2i_enc"]) if level == 0 else (W["i2z_mlp"], W["i2z_agg"], W["i2z_enc"])
-        n_seq = len(member_rows)
-        lens = np.fromiter((len(m) + 1 for m in member_rows), dtype=np.int64, count=n_seq)
-        cu = np.zeros(n_seq + 1, np.int32)
-        cu[1:] = np.cumsum(lens)
-        T = int(cu[-1])
-        tok_src = np.full(T, -1, np.int32)
-        tok_seq = np.repeat(np.arange(n_seq, dtype=np.int32), lens)
-        if T > n_seq:
-            body = np.ones(T, bool)
-            body[cu[:-1]] = False
-            tok_src[body] = np.concatenate(member_rows)
-        ptrs = np.stack([np.asarray(xyz_ptrs, np.int64), np.asarray(dir_ptrs if dir_ptrs is not None else xyz_ptrs, np.int64),
-                         np.asarray(scale_ptrs if scale_ptrs is not None else xyz_ptrs, np.int64), np.asarray(fts_ptrs, np.int64)])
-        arrs = [tok_src, tok_seq, cu, ptrs]
-        if isinstance(centre, np.ndarray):
-            arrs.append(np.ascontiguousarray(centre, dtype=F32))
+        T = len(tok_src)
+        arrs = [tok_src, tok_seq, cu, ptrs] + ([np.ascontiguousarray(centre, dtype=F32)] if isinstance(centre, np.ndarray) else []) + list(extra)
         up = self._upload(arrs)
-        tok_src_d, tok_seq_d, cu_d, ptrs_d = up[:4]
+        k = 5 if isinstance(centre, np.ndarray) else 4
         centre_dev = up[4] if isinstance(centre, np.ndarray) else centre
         out = torch.empty((n_seq, D), device=self.device, dtype=torch.float32)
         ws = self._workspace(int(L.lib().d3d_pool_workspace_bytes(T, D, D)))
         lv = W["c_levels"][level]
-        L.check(L.lib().d3d_pool_tokens(ctypes.addressof(lv), L.ptr(ptrs_d), L.ptr(centre_dev), L.ptr(tok_seq_d), L.ptr(tok_src_d), L.ptr(cu_d), T, n_seq,
-                                        int(lens.max()), mode, int(fts_is_f32), L.ptr(ws), ws.numel(), L.ptr(out), L.stream_ptr()))
-        return out, centre_dev
+        L.check(L.lib().d3d_pool_tokens(ctypes.addressof(lv), L.ptr(up[3]), L.ptr(centre_dev), L.ptr(up[1]), L.ptr(up[0]), L.ptr(up[2]), T, n_seq,
+                                        int(max_len), mode, int(fts_is_f32), L.ptr(ws), ws.numel(), L.ptr(out), L.stream_ptr()))
+        return out, centre_dev, up[k:]
 
     def _workspace(self, nbytes):
         if self._ws is None or self._ws.numel() < nbytes:
@@ -446,13 +414,16 @@ class Feature_Fields(nn.Module):
             raise NotImplementedError("posed-dataset branch (FF:343-344) is outside the hot path built here")
         depth = self._as_dev(batch_depth, torch.float32).contiguous()
         V = num_of_views
+        lib = L.lib()
         with L.stream_scope():
+            if not any(ep.n_patch for ep in self.eps):
+                L.check(lib.d3d_ffh_set_tree(self._h))
+                return
             cams = np.concatenate([ops.camera_rows(batch_position[b], [float(batch_heading[b]) + (ix * (-math.pi / 6) if self.q7_fix else 0.0)
                                                                       for ix in range(V)]) for b in range(self.batch_size)], 0)  # Q7
             cam_d = self._upload([cams])[0]
             masks = []
-            for b in range(self.batch_size):
-                ep = self.eps[b]
+            for b, ep in enumerate(self.eps):
                 if ep.n_patch == 0:
                     masks.append(None)
                     continue
@@ -460,71 +431,33 @@ class Feature_Fields(nn.Module):
                                         self.args.input_hfov, self.args.input_vfov, 0.0, self.args.deleted_frustum_distance, 0.1)
                 masks.append(m.to("cpu", non_blocking=True))
             torch.cuda.current_stream().synchronize()
-            rows_i, rows_z = [], []
-            for b in range(self.batch_size):
-                ep = self.eps[b]
-                if masks[b] is not None:
-                    di, dz = self._host_cull(ep, np.flatnonzero(masks[b].numpy()))
-                    rows_i += [(ep, i) for i in di]
-                    rows_z += [(ep, z) for z in dz]
+            pp_i, fp_i, pp_z, fp_z = [], [], [], []
+            nd = (ctypes.c_int * 2)()
+            for b, ep in enumerate(self.eps):
+                if masks[b] is None:
+                    continue
+                mk = masks[b].numpy()
+                di = np.zeros(max(ep.n_inst, 1), np.int64); dz = np.zeros(max(ep.n_zone, 1), np.int64)
+                L.check(lib.d3d_ffh_cull(self._h, b, mk.ctypes.data, ep.n_patch, di.ctypes.data, ctypes.addressof(nd), dz.ctypes.data,
+                                         ctypes.addressof(nd) + 4))
+                if nd[0]:
+                    pp_i.append(ep.inst_pos.t.data_ptr() + 12 * di[:nd[0]]); fp_i.append(ep.inst_fts.t.data_ptr() + 4 * D * di[:nd[0]])
+                if nd[1]:
+                    pp_z.append(ep.zone_pos.t.data_ptr() + 12 * dz[:nd[1]]); fp_z.append(ep.zone_fts.t.data_ptr() + 4 * D * dz[:nd[1]])
                 ep.tree = ep.n_inst > 0
             # tombstone dead instance / zone slots on the device (FF:378-379, 392-393): one batched scatter per tensor kind
-            if rows_i or rows_z:
+            rows_p, rows_f = pp_i + pp_z, fp_i + fp_z
+            if rows_p:
+                pp, fp = np.concatenate(rows_p), np.concatenate(rows_f)
                 const = self._tomb_rows()
-                for rows, pos_attr, fts_attr in ((rows_i, "inst_pos", "inst_fts"), (rows_z, "zone_pos", "zone_fts")):
-                    if not rows:
-                        continue
-                    pp = np.fromiter((getattr(e, pos_attr).t.data_ptr() + 12 * i for e, i in rows), np.int64, len(rows))
-                    fp = np.fromiter((getattr(e, fts_attr).t.data_ptr() + 4 * D * i for e, i in rows), np.int64, len(rows))
-                    zi = np.zeros(len(rows), np.int32)
-                    pp_d, fp_d, zi_d = self._upload([pp, fp, zi])
-                    L.check(L.lib().d3d_scatter_rows_ptr(L.ptr(const[0]), 3, L.ptr(zi_d), L.ptr(pp_d), len(rows), 3, L.stream_ptr()))
-                    L.check(L.lib().d3d_scatter_rows_ptr(L.ptr(const[1]), D, L.ptr(zi_d), L.ptr(fp_d), len(rows), D, L.stream_ptr()))
+                pp_d, fp_d, zi_d = self._upload([pp, fp, np.zeros(len(pp), np.int32)])
+                L.check(lib.d3d_scatter_rows_ptr(L.ptr(const[0]), 3, L.ptr(zi_d), L.ptr(pp_d), len(pp), 3, L.stream_ptr()))
+                L.check(lib.d3d_scatter_rows_ptr(L.ptr(const[1]), D, L.ptr(zi_d), L.ptr(fp_d), len(pp), D, L.stream_ptr()))
 
     def _tomb_rows(self):
         if self._tomb is None:
             self._tomb = (torch.full((1, 3), -10000.0, device=self.device), torch.zeros((1, D), device=self.device))
         return self._tomb
-
-    def _host_cull(self, ep, deleted):
-        """FF:362-393 for the culled array rows `deleted` (ascending): patch -> instance -> zone bookkeeping.
-        Returns (dead instance slots, dead zone slots).  The reference pops in ascending patch order; dict *removal* order does
-        not change the insertion order of the survivors, so grouping by instance yields the same state."""
-        if len(deleted) == 0:
-            return [], []
-        ep.patch_pos_h[deleted] = -10000.0
-        keyed = deleted[ep.p2i[deleted] >= 0]  # Q2: array index used as patch id
-        if len(keyed) == 0:
-            return [], []
-        owners = ep.p2i[keyed]
-        ep.p2i[keyed] = -1
-        ep.n_p2i -= len(keyed)
-        gone = np.zeros(ep.n_patch, bool)
-        gone[keyed] = True
-        dead_inst, dead_zone = [], []
-        for iid in np.unique(owners).tolist():
-            m = ep.i2p[iid]
-            keep = m[~gone[m]]
-            if len(keep):
-                ep.i2p[iid] = keep
-                continue
-            ep.i2p.pop(iid)
-            ep.inst_alive[iid] = False
-            code = int(_voxel_codes(ep.inst_pos_h[iid:iid + 1])[0])
-            ep.inst_pos_h[iid] = -10000.0
-            dead_inst.append(iid)
-            zid = ep.zone_code_to_id.get(code)
-            if zid is not None:
-                z = ep.z2i[zid]
-                z = z[z != iid]
-                if len(z):
-                    ep.z2i[zid] = z
-                else:
-                    ep.zone_code_to_id.pop(code)
-                    ep.z2i.pop(zid)
-                    ep.zone_alive[zid] = False
-                    dead_zone.append(zid)
-        return dead_inst, dead_zone
 
     # ------------------------------------------------------------------ FF:493-815
     def update_feature_fields(self, batch_depth, batch_grid_ft, batch_image=None, batch_position=None, batch_heading=None,
@@ -540,7 +473,8 @@ class Feature_Fields(nn.Module):
             if self.segmenter is None:
                 raise RuntimeError("no segmentation: pass batch_patch_segm or set .segmenter (FastSAM is not part of this engine)")
             batch_patch_segm = self.segmenter(batch_image)
-        segm = np.asarray(batch_patch_segm.cpu() if torch.is_tensor(batch_patch_segm) else batch_patch_segm).reshape(B, V, P).astype(np.int64)
+        segm = np.ascontiguousarray(np.asarray(batch_patch_segm.cpu() if torch.is_tensor(batch_patch_segm) else batch_patch_segm)
+                                    .reshape(B, V, P).transpose(1, 0, 2), dtype=np.int64)  # [V,B,P]
         with L.stream_scope():
             depth = self._as_dev(batch_depth, torch.float32).reshape(B * V, P).contiguous()
             grid = self._as_dev(batch_grid_ft, torch.float16).reshape(B * V * P, D).contiguous()
@@ -549,232 +483,139 @@ class Feature_Fields(nn.Module):
                                                           self.args.input_width, self.args.input_height)
             xyz_h = xyz.to("cpu", non_blocking=True)  # host mirror of the step's patch positions (one copy per step)
             torch.cuda.current_stream().synchronize()
-            xyz_h = xyz_h.numpy().reshape(B, V, P, 3)
+            xyz_h = np.ascontiguousarray(xyz_h.numpy().reshape(B, V, P, 3).transpose(1, 0, 2, 3))  # [V,B,P,3]
             stage = {"xyz": xyz.view(B * V * P, 3), "dir": direction.view(-1), "scale": scale.view(-1), "fts": grid}
             for ix in range(V):
-                self._update_view(ix, V, P, segm[:, ix], stage, xyz_h[:, ix])
+                self._update_view(ix, V, P, segm[ix], stage, xyz_h[ix])
 
     def _update_view(self, ix, V, P, segm, stage, xyz_h):
         """One panorama view for all episodes in lock step.  `stage` holds the step's unprojected patches / CLIP features for all
-        (episode, view) units, unit u = b*V+ix occupying rows [u*P, (u+1)*P)."""
+        (episode, view) units, unit u = b*V+ix occupying rows [u*P, (u+1)*P).  segm [B,P] int64, xyz_h [B,P,3] fp32 (host)."""
         B = self.batch_size
         dev = self.device
-        W = self._weights()
         lib = L.lib()
-        # 1. append the view's patches to the episode pools (FF:557-570): one batched block copy
-        base_rows, src, dst, nb = [], [], [], []
-        for b, ep in enumerate(self.eps):
-            n0 = ep.n_patch
+        eps = self.eps
+        # ---- plan the first half on the host (C++): packed sequences, one per (episode, segment) ----
+        cap = B * P
+        stage_off = (np.arange(B, dtype=np.int64) * V + ix) * P
+        base_rows = np.zeros(B, np.int64); n_seg = np.zeros(B, np.int32)
+        seq_owner = np.zeros(cap, np.int32); members = np.zeros(cap, np.int32); cu_m = np.zeros(cap + 1, np.int32)
+        tok_src = np.zeros(2 * cap, np.int32); tok_seq = np.zeros(2 * cap, np.int32); cu_tok = np.zeros(cap + 1, np.int32)
+        n_ref = np.zeros(cap, np.int32); info = np.zeros(2, np.int32)
+        L.check(lib.d3d_ffh_begin_view(self._h, xyz_h.ctypes.data, segm.ctypes.data, P, stage_off.ctypes.data, base_rows.ctypes.data,
+                                       n_seg.ctypes.data, seq_owner.ctypes.data, members.ctypes.data, cu_m.ctypes.data, tok_src.ctypes.data,
+                                       tok_seq.ctypes.data, cu_tok.ctypes.data, n_ref.ctypes.data, info.ctypes.data))
+        n_seq, max_len = int(info[0]), int(info[1])
+        T = cap + n_seq
+        owner = seq_owner[:n_seq]
+        # ---- 1. append the view's patches to the episode pools (FF:557-570): one batched block copy ----
+        src, dst, nb = [], [], []
+        for b, ep in enumerate(eps):
+            n0 = int(base_rows[b])
             for pool in (ep.patch_pos, ep.patch_dir, ep.patch_scale, ep.patch_fts):
                 pool.ensure(n0 + P)
-            ep.grow_host(n_patch=n0 + P)
             u = b * V + ix
             for key, pool, rb in (("xyz", ep.patch_pos, 12), ("dir", ep.patch_dir, 4), ("scale", ep.patch_scale, 4), ("fts", ep.patch_fts, 2 * D)):
                 src.append(stage[key].data_ptr() + u * P * rb)
                 dst.append(pool.t.data_ptr() + n0 * rb)
                 nb.append(P * rb)
-            ep.patch_pos_h[n0:n0 + P] = xyz_h[b]
-            base_rows.append(n0)
             ep.n_patch = n0 + P
-        # 2. packed sequences: one per (episode, segment); members keep patch order (boolean-mask semantics, FF:582)
-        member_rows, owner, splits_all = [], [], []
-        for b in range(B):
-            order = np.argsort(segm[b], kind="stable")
-            counts = np.bincount(segm[b])
-            if (counts == 0).any():
-                raise ValueError("patch_segm labels must be dense 0..G-1 (FF:411-422 relabels them)")
-            splits = np.split(order, np.cumsum(counts)[:-1])
-            splits_all.append(splits)
-            off = (b * V + ix) * P
-            member_rows += [(off + m).astype(np.int32) for m in splits]
-            owner += [b] * len(splits)
-        n_seq = len(member_rows)
-        owner = np.asarray(owner)
-        seq_start = np.searchsorted(owner, np.arange(B))
-        seq_end = np.searchsorted(owner, np.arange(B), side="right")
-        cu_m = np.zeros(n_seq + 1, np.int32)
-        cu_m[1:] = np.cumsum([len(m) for m in member_rows])
-        inst_ptr = np.fromiter((self.eps[b].inst_pos.t.data_ptr() for b in owner), np.int64, n_seq)
-        fts_ptr = np.fromiter((self.eps[b].inst_fts.t.data_ptr() for b in owner), np.int64, n_seq)
-        n_ref = np.fromiter((self.eps[b].n_inst if self.eps[b].tree else 0 for b in owner), np.int32, n_seq)
-        up = self._upload([np.asarray(src, np.int64), np.asarray(dst, np.int64), np.asarray(nb, np.int64), np.concatenate(member_rows), cu_m,
-                           inst_ptr, fts_ptr, n_ref])
-        L.check(lib.d3d_copy_blocks(L.ptr(up[0]), L.ptr(up[1]), L.ptr(up[2]), len(src), L.stream_ptr()))
-        centres = ops.seq_centroid(stage["xyz"], up[3], up[4], n_seq)  # fp64 accumulate, all episodes in one launch
-        sx, sd, ss, sf = (stage[k].data_ptr() for k in ("xyz", "dir", "scale", "fts"))
-        view_fts, _ = self._run_sequences(member_rows, [sx] * n_seq, [sd] * n_seq, [ss] * n_seq, [sf] * n_seq, False, centres, 0, 0)
-        # 3. K-NN proposals + merge discriminator (FF:604-621), all episodes in one launch each; K = 2 columns are always
-        #    computed, the host uses the first min(#live, 2) of them (further columns can only be tombstones or absent)
+        inst_pos_ptr = np.fromiter((e.inst_pos.t.data_ptr() for e in eps), np.int64, B)
+        inst_fts_ptr = np.fromiter((e.inst_fts.t.data_ptr() for e in eps), np.int64, B)
+        sp = np.array([stage[k].data_ptr() for k in ("xyz", "dir", "scale", "fts")], np.int64)
+        ptrs = np.repeat(sp[:, None], n_seq, axis=1)
+        extra = [np.asarray(src, np.int64), np.asarray(dst, np.int64), np.asarray(nb, np.int64), members, cu_m[:n_seq + 1],
+                 inst_pos_ptr[owner], inst_fts_ptr[owner], n_ref[:n_seq]]
+        # centroids need the member lists on the device first: upload everything in one go, then launch
+        up = self._upload([tok_src[:T], tok_seq[:T], cu_tok[:n_seq + 1], ptrs] + extra)
+        L.check(lib.d3d_copy_blocks(L.ptr(up[4]), L.ptr(up[5]), L.ptr(up[6]), len(src), L.stream_ptr()))
+        centres = ops.seq_centroid(stage["xyz"], up[7], up[8], n_seq)  # fp64 accumulate, all episodes in one launch
+        W = self._weights()
+        view_fts = torch.empty((n_seq, D), device=dev, dtype=torch.float32)
+        ws = self._workspace(int(lib.d3d_pool_workspace_bytes(T, D, D)))
+        L.check(lib.d3d_pool_tokens(ctypes.addressof(W["c_levels"][0]), L.ptr(up[3]), L.ptr(centres), L.ptr(up[1]), L.ptr(up[0]), L.ptr(up[2]), T,
+                                    n_seq, max_len, 0, 0, L.ptr(ws), ws.numel(), L.ptr(view_fts), L.stream_ptr()))
+        # ---- 3. K-NN proposals + merge discriminator (FF:604-621), all episodes in one launch each; 2 columns are always computed,
+        #         the planner uses the first min(#live, 2) of them (further columns can only be tombstones or absent) ----
         res = torch.empty((n_seq, 12), device=dev, dtype=torch.float32)  # [centre(3) | d2(2) | idx(2, int bits) | logits(4) | pad]
-        any_tree = bool(n_ref.max() > 0) if n_seq else False
-        d2_d = torch.empty((n_seq, 2), device=dev, dtype=torch.float32)
-        idx_d = torch.empty((n_seq, 2), device=dev, dtype=torch.int32)
-        if any_tree:
-            L.check(lib.d3d_knn2_batched(L.ptr(up[5]), L.ptr(up[7]), L.ptr(centres), n_seq, L.ptr(d2_d), L.ptr(idx_d), L.stream_ptr()))
+        if n_ref[:n_seq].max() > 0:
+            d2_d = torch.empty((n_seq, 2), device=dev, dtype=torch.float32)
+            idx_d = torch.empty((n_seq, 2), device=dev, dtype=torch.int32)
+            L.check(lib.d3d_knn2_batched(L.ptr(up[9]), L.ptr(up[11]), L.ptr(centres), n_seq, L.ptr(d2_d), L.ptr(idx_d), L.stream_ptr()))
             A = torch.empty((2 * n_seq, 1544), device=dev, dtype=self.compute_dtype)
-            L.check(lib.d3d_disc_input_batched(L.ptr(up[6]), L.ptr(up[5]), L.ptr(idx_d), L.ptr(view_fts), L.ptr(centres), n_seq, 2, D, 1544,
+            L.check(lib.d3d_disc_input_batched(L.ptr(up[10]), L.ptr(up[9]), L.ptr(idx_d), L.ptr(view_fts), L.ptr(centres), n_seq, 2, D, 1544,
                                                L.ptr(A), L.kind_of(A.dtype), L.stream_ptr()))
-            logits_d = self._disc_logits(A)  # [2*n_seq, 2]
-            res[:, 7:11] = logits_d.reshape(n_seq, 4)
+            res[:, 7:11] = self._disc_logits(A).reshape(n_seq, 4)
             res[:, 3:5] = d2_d
             res[:, 5:7] = idx_d.view(torch.float32)
         res[:, 0:3] = centres
-        # 4. ONE device->host copy per view
+        # ---- 4. ONE device->host copy per view, then the planner's second half (FF:623-756) ----
         res_h = res.to("cpu", non_blocking=True)
         torch.cuda.current_stream().synchronize()
         res_h = res_h.numpy()
-        centres_h = np.ascontiguousarray(res_h[:, 0:3])
-        d2_h = np.ascontiguousarray(res_h[:, 3:5])
-        idx_h = np.ascontiguousarray(res_h[:, 5:7]).view(np.int32)
-        logits_h = np.ascontiguousarray(res_h[:, 7:11]).reshape(n_seq, 2, 2)
-        # 5. host bookkeeping per episode (FF:623-756), collecting the device work it implies
-        new_src, new_fts_dst, new_pos_dst = [], [], []
-        merged, zones = [], []
-        for b, ep in enumerate(self.eps):
-            s0, s1 = seq_start[b], seq_end[b]
-            K = min(len(ep.i2p), self.args.num_proposal_instances) if ep.tree else 0
-            n_before = ep.n_inst
-            news = self._host_update(ep, b, splits_all[b], centres_h[s0:s1], idx_h[s0:s1, :K], d2_h[s0:s1, :K], logits_h[s0:s1, :K], merged, zones)
-            if news:
-                if ep.n_inst > n_before:
-                    ep.inst_pos.ensure(ep.n_inst)
-                    ep.inst_fts.ensure(ep.n_inst)
-                fp, pp = ep.inst_fts.t.data_ptr(), ep.inst_pos.t.data_ptr()
-                for g, iid in news:
-                    new_src.append(s0 + g)
-                    new_fts_dst.append(fp + 4 * D * iid)
-                    new_pos_dst.append(pp + 12 * iid)
-        # 6. device writes implied by the bookkeeping: batched scatters across episodes
-        if new_src:
-            a, bb, c = self._upload([np.asarray(new_src, np.int32), np.asarray(new_fts_dst, np.int64), np.asarray(new_pos_dst, np.int64)])
-            L.check(lib.d3d_scatter_rows_ptr(L.ptr(view_fts), D, L.ptr(a), L.ptr(bb), len(new_src), D, L.stream_ptr()))
-            L.check(lib.d3d_scatter_rows_ptr(L.ptr(centres), 3, L.ptr(a), L.ptr(c), len(new_src), 3, L.stream_ptr()))
-        if merged:
-            eps_ = [self.eps[m[0]] for m in merged]
-            pos_np = np.stack([m[3] for m in merged]).astype(F32)
-            fts, pos_d = self._run_sequences([m[2].astype(np.int32) for m in merged], [e.patch_pos.t.data_ptr() for e in eps_],
-                                             [e.patch_dir.t.data_ptr() for e in eps_], [e.patch_scale.t.data_ptr() for e in eps_],
-                                             [e.patch_fts.t.data_ptr() for e in eps_], False, pos_np, 0, 0)
-            fd = np.fromiter((e.inst_fts.t.data_ptr() + 4 * D * m[1] for e, m in zip(eps_, merged)), np.int64, len(merged))
-            pd = np.fromiter((e.inst_pos.t.data_ptr() + 12 * m[1] for e, m in zip(eps_, merged)), np.int64, len(merged))
-            fd_d, pd_d = self._upload([fd, pd])
-            L.check(lib.d3d_scatter_rows_ptr(L.ptr(fts), D, None, L.ptr(fd_d), len(merged), D, L.stream_ptr()))
-            L.check(lib.d3d_scatter_rows_ptr(L.ptr(pos_d), 3, None, L.ptr(pd_d), len(merged), 3, L.stream_ptr()))
-        if zones:
-            key_arrays = {}
-            xyz_ptrs, fts_ptrs = [], []
-            for (b, slot, members, use_keys, _) in zones:
-                ep = self.eps[b]
-                ep.zone_pos.ensure(slot + 1)
-                ep.zone_fts.ensure(slot + 1)
-                if use_keys:  # Q5: an updated zone is embedded from its members' voxel-centre keys
-                    if b not in key_arrays:
-                        key_arrays[b] = self._upload([_zone_keys(ep.inst_pos_h[: ep.n_inst])])[0]
-                    xyz_ptrs.append(key_arrays[b].data_ptr())
-                else:
-                    xyz_ptrs.append(ep.inst_pos.t.data_ptr())
-                fts_ptrs.append(ep.inst_fts.t.data_ptr())
-            zpos_np = np.stack([z[4] for z in zones]).astype(F32)
-            zf, zpos_d = self._run_sequences([z[2].astype(np.int32) for z in zones], xyz_ptrs, None, None, fts_ptrs, True, zpos_np, 1, 1)
-            fd = np.fromiter((self.eps[z[0]].zone_fts.t.data_ptr() + 4 * D * z[1] for z in zones), np.int64, len(zones))
-            pd = np.fromiter((self.eps[z[0]].zone_pos.t.data_ptr() + 12 * z[1] for z in zones), np.int64, len(zones))
-            fd_d, pd_d = self._upload([fd, pd])
-            L.check(lib.d3d_scatter_rows_ptr(L.ptr(zf), D, None, L.ptr(fd_d), len(zones), D, L.stream_ptr()))
-            L.check(lib.d3d_scatter_rows_ptr(L.ptr(zpos_d), 3, None, L.ptr(pd_d), len(zones), 3, L.stream_ptr()))
-        for ep in self.eps:
+        sizes = np.zeros(10, np.int32); after = np.zeros(B * 3, np.int64)
+        L.check(lib.d3d_ffh_finish_view(self._h, res_h.ctypes.data, sizes.ctypes.data, after.ctypes.data))
+        n_new, n_mg, t_mg, n_zn, t_zn, ml_mg, ml_zn = (int(x) for x in sizes[:7])
+        for b, ep in enumerate(eps):
+            ep.n_inst, ep.n_zone = int(after[b * 3]), int(after[b * 3 + 1])
+            ep.inst_pos.ensure(ep.n_inst); ep.inst_fts.ensure(ep.n_inst)
+            ep.zone_pos.ensure(ep.n_zone); ep.zone_fts.ensure(ep.n_zone)
             ep.tree = ep.n_inst > 0
+        i32, i64 = np.int32, np.int64
+        new_src = np.zeros(max(n_new, 1), i32); new_owner = np.zeros(max(n_new, 1), i32); new_iid = np.zeros(max(n_new, 1), i64)
+        mg_owner = np.zeros(max(n_mg, 1), i32); mg_iid = np.zeros(max(n_mg, 1), i64); mg_pos = np.zeros((max(n_mg, 1), 3), F32)
+        mg_src = np.zeros(t_mg + n_mg + 1, i32); mg_seq = np.zeros(t_mg + n_mg + 1, i32); mg_cu = np.zeros(n_mg + 1, i32)
+        zn_owner = np.zeros(max(n_zn, 1), i32); zn_slot = np.zeros(max(n_zn, 1), i64); zn_keys = np.zeros(max(n_zn, 1), i32)
+        zn_pos = np.zeros((max(n_zn, 1), 3), F32)
+        zn_src = np.zeros(t_zn + n_zn + 1, i32); zn_seq = np.zeros(t_zn + n_zn + 1, i32); zn_cu = np.zeros(n_zn + 1, i32)
+        L.check(lib.d3d_ffh_fetch_view(self._h, *(a.ctypes.data for a in (new_src, new_owner, new_iid, mg_owner, mg_iid, mg_pos, mg_src, mg_seq,
+                                                                           mg_cu, zn_owner, zn_slot, zn_keys, zn_pos, zn_src, zn_seq, zn_cu))))
+        # pool base addresses AFTER any growth
+        ip = np.fromiter((e.inst_pos.t.data_ptr() for e in eps), i64, B); ifp = np.fromiter((e.inst_fts.t.data_ptr() for e in eps), i64, B)
+        zp = np.fromiter((e.zone_pos.t.data_ptr() for e in eps), i64, B); zfp = np.fromiter((e.zone_fts.t.data_ptr() for e in eps), i64, B)
+        # ---- 6. device writes implied by the bookkeeping: batched scatters / pooling passes across episodes ----
+        if n_new:
+            o = new_owner[:n_new]
+            a, bb, c = self._upload([new_src[:n_new], ifp[o] + 4 * D * new_iid[:n_new], ip[o] + 12 * new_iid[:n_new]])
+            L.check(lib.d3d_scatter_rows_ptr(L.ptr(view_fts), D, L.ptr(a), L.ptr(bb), n_new, D, L.stream_ptr()))
+            L.check(lib.d3d_scatter_rows_ptr(L.ptr(centres), 3, L.ptr(a), L.ptr(c), n_new, 3, L.stream_ptr()))
+        if n_mg:
+            o = mg_owner[:n_mg]
+            pp = np.fromiter((e.patch_pos.t.data_ptr() for e in eps), i64, B); pd = np.fromiter((e.patch_dir.t.data_ptr() for e in eps), i64, B)
+            ps = np.fromiter((e.patch_scale.t.data_ptr() for e in eps), i64, B); pf = np.fromiter((e.patch_fts.t.data_ptr() for e in eps), i64, B)
+            ptrs = np.stack([pp[o], pd[o], ps[o], pf[o]])
+            fts, pos_d, (fd_d, pd_d) = self._pool_pass(mg_src[:t_mg + n_mg], mg_seq[:t_mg + n_mg], mg_cu, ptrs, mg_pos[:n_mg], n_mg, ml_mg, 0, 0, False,
+                                                       extra=[ifp[o] + 4 * D * mg_iid[:n_mg], ip[o] + 12 * mg_iid[:n_mg]])
+            L.check(lib.d3d_scatter_rows_ptr(L.ptr(fts), D, None, L.ptr(fd_d), n_mg, D, L.stream_ptr()))
+            L.check(lib.d3d_scatter_rows_ptr(L.ptr(pos_d), 3, None, L.ptr(pd_d), n_mg, 3, L.stream_ptr()))
+        if n_zn:
+            o = zn_owner[:n_zn]
+            xyz_ptr = ip[o].copy()
+            if zn_keys[:n_zn].any():  # Q5: an updated zone is embedded from its members' voxel-centre keys
+                key_arrays = []
+                need = np.flatnonzero(after.reshape(B, 3)[:, 2])
+                for b in need.tolist():
+                    ka = np.zeros((max(eps[b].n_inst, 1), 3), F32)
+                    L.check(lib.d3d_ffh_zone_key_array(self._h, b, ka.ctypes.data))
+                    key_arrays.append(ka)
+                key_dev = self._upload(key_arrays)
+                kp = np.zeros(B, i64)
+                kp[need] = [t.data_ptr() for t in key_dev]
+                use = zn_keys[:n_zn] != 0
+                xyz_ptr[use] = kp[o][use]
+            ptrs = np.stack([xyz_ptr, xyz_ptr, xyz_ptr, ifp[o]])
+            zf, zpos_d, (fd_d, pd_d) = self._pool_pass(zn_src[:t_zn + n_zn], zn_seq[:t_zn + n_zn], zn_cu, ptrs, zn_pos[:n_zn], n_zn, ml_zn, 1, 1, True,
+                                                       extra=[zfp[o] + 4 * D * zn_slot[:n_zn], zp[o] + 12 * zn_slot[:n_zn]])
+            L.check(lib.d3d_scatter_rows_ptr(L.ptr(zf), D, None, L.ptr(fd_d), n_zn, D, L.stream_ptr()))
+            L.check(lib.d3d_scatter_rows_ptr(L.ptr(zpos_d), 3, None, L.ptr(pd_d), n_zn, 3, L.stream_ptr()))
 
-    def _host_update(self, ep, b, splits, cen, idx, d2, logits, merged, zones):
-        """FF:623-756 / 759-812 for one episode and one view.  Returns [(segment, instance id)] of the NEW instances."""
-        G = len(cen)
-        P = sum(len(m) for m in splits)
-        news = []
-        patch_ids = np.flatnonzero(ep.p2i[: ep.n_p2i + P] < 0)[:P].astype(np.int64)  # FF:433-445 lowest free patch ids
-        if ep.tree:
-            K = idx.shape[1]
-            if K > 0 and float(d2.astype(np.float64).sum()) > 1e6:  # Q9: K-shrink heuristic (FF:607-610)
-                K = int((d2.astype(np.float64).sum(0) < 1e6).sum())
-                idx, d2, logits = idx[:, :K], d2[:, :K], logits[:, :K]
-            merge_target = logits[..., 1] > logits[..., 0]  # argmax of the 2-way softmax, first max wins
-            ep.last = {"knn": (d2.copy(), idx.copy()), "merge": merge_target.copy(), "logits": logits.copy()}
-            is_new = ~merge_target.any(-1) if K > 0 else np.ones(G, bool)
-            new_ids = ep.free_instance_ids(int(is_new.sum()))
-            first = merge_target.argmax(-1) if K > 0 else None  # nearest accepted proposal only (FF:653,691)
-            ni = 0
-            touched = {}
-            for g in range(G):
-                members = patch_ids[splits[g]]
-                if is_new[g]:
-                    iid = int(new_ids[ni]); ni += 1
-                    if iid >= ep.n_inst:
-                        ep.n_inst = iid + 1
-                        ep.grow_host(n_inst=ep.n_inst)
-                    ep.i2p[iid] = members
-                    ep.inst_alive[iid] = True
-                    ep.inst_pos_h[iid] = cen[g]
-                    news.append((g, iid))
-                else:
-                    iid = int(idx[g, first[g]])
-                    if iid not in ep.i2p:
-                        raise KeyError(f"merge target instance {iid} is not alive (the reference raises here too, FF:658)")
-                    ep.i2p[iid] = np.concatenate([ep.i2p[iid], members])
-                    touched[iid] = True
-                ep.p2i[members] = iid
-            ep.n_p2i += P
-            for iid in touched:  # only the state after the last merge survives (FF:663,688 overwrite)
-                ids = ep.i2p[iid]
-                pos = _mean64(ep.patch_pos_h[ids])  # Q2: ids index the patch arrays directly
-                ep.inst_pos_h[iid] = pos
-                merged.append((b, iid, ids, pos))
-            slot_pos = ep.inst_pos_h[: ep.n_inst]
-        else:
-            ep.last = {}
-            ids = ep.free_instance_ids(G)
-            ep.n_inst = G
-            ep.grow_host(n_inst=G)
-            ep.inst_pos_h[:G] = cen
-            for g in range(G):
-                members = patch_ids[splits[g]]
-                iid = int(ids[g])
-                ep.i2p[iid] = members
-                ep.inst_alive[iid] = True
-                ep.p2i[members] = iid
-                news.append((g, iid))
-            ep.n_p2i += P
-            slot_pos = cen
-        # zones (FF:693-756 / 777-812): group the instance slots by voxel once, then visit the view's voxels in key order
-        slot_code = _voxel_codes(slot_pos)
-        order = np.argsort(slot_code, kind="stable")
-        sorted_code = slot_code[order]
-        uniq = np.unique(_voxel_codes(cen))
-        lo = np.searchsorted(sorted_code, uniq, side="left")
-        hi = np.searchsorted(sorted_code, uniq, side="right")
-        zone_ids = ep.free_zone_ids(len(uniq))
-        # per-voxel member centroids in fp64 (exact for fp32 inputs, so any summation order gives the same fp32 result)
-        cnt = (hi - lo).astype(np.float64)
-        csum = np.concatenate([np.zeros((1, 3)), np.cumsum(slot_pos[order].astype(np.float64), axis=0)], 0) if len(order) else np.zeros((1, 3))
-        with np.errstate(all="ignore"):
-            mean_pos = ((csum[hi] - csum[lo]) / cnt[:, None]).astype(F32)  # empty voxel -> 0/0 = NaN (Q5)
-        v = uniq.copy()
-        vz = v % _VM; v //= _VM
-        vy = v % _VM; vx = v // _VM
-        keys = ((np.stack([vx, vy, vz], 1) - _VOFF).astype(F32) * F32(self.args.zone_x_length) + F32(self.args.zone_x_length / 2)).astype(F32)
-        zi = 0
-        for j, code in enumerate(uniq.tolist()):
-            members = order[lo[j]:hi[j]]  # ascending slot order (stable sort)
-            zid = ep.zone_code_to_id.get(code)
-            if zid is None:
-                zid = int(zone_ids[zi]); zi += 1
-                ep.zone_code_to_id[code] = zid
-                ep.z2i[zid] = members
-                ep.zone_alive[zid] = True
-                slot = ep.n_zone  # Q3: a new zone is always appended, whatever its id
-                ep.n_zone += 1
-                zones.append((b, slot, members, False, mean_pos[j]))
-            else:
-                ep.z2i[zid] = members
-                zones.append((b, zid, members, True, keys[j] if len(members) else np.full(3, np.nan, F32)))  # Q5: mean of identical keys
-        return news
+    def _live_ids(self, b, which):
+        """dict-order keys of the instance->patch (0) or zone->instance (1) map (FF:825, 844)."""
+        sizes = np.zeros(2, np.int64)
+        L.check(L.lib().d3d_ffh_get_map(self._h, b, which, None, None, None, sizes.ctypes.data))
+        ids = np.zeros(max(int(sizes[0]), 1), np.int64); lens = np.zeros_like(ids); cat = np.zeros(max(int(sizes[1]), 1), np.int64)
+        L.check(L.lib().d3d_ffh_get_map(self._h, b, which, ids.ctypes.data, lens.ctypes.data, cat.ctypes.data, sizes.ctypes.data))
+        return ids[: int(sizes[0])].tolist()
 
     # ------------------------------------------------------------------ FF:818-862
     def get_environment_features(self, agent_position, agent_heading_angle, instance_distance=5.0, zone_distance=100.0):
@@ -783,8 +624,8 @@ class Feature_Fields(nn.Module):
         for b, ep in enumerate(self.eps):
             agent = torch.from_numpy(ops.camera_rows(agent_position[b], [agent_heading_angle[b]])[0]).to(dev, non_blocking=True)
             pair = []
-            for ids, pos, fts, radius in ((list(ep.i2p.keys()), ep.inst_pos.t, ep.inst_fts.t, instance_distance),
-                                          (list(ep.z2i.keys()), ep.zone_pos.t, ep.zone_fts.t, zone_distance)):
+            for ids, pos, fts, radius in ((self._live_ids(b, 0), ep.inst_pos.t, ep.inst_fts.t, instance_distance),
+                                          (self._live_ids(b, 1), ep.zone_pos.t, ep.zone_fts.t, zone_distance)):
                 n = len(ids)
                 rel = torch.empty((max(n, 1), 3), device=dev, dtype=torch.float32)
                 out = torch.empty((max(n, 1), D), device=dev, dtype=torch.float32)
@@ -807,13 +648,17 @@ class Feature_Fields(nn.Module):
     # ------------------------------------------------------------------ discrete-state snapshot (parity tests)
     def snapshot(self, b=0):
         ep = self.eps[b]
+        i2p, z2i = self._map(b, 0), self._map(b, 1)
+        p2i = self._p2i(b)
+        pos = np.zeros((max(ep.n_patch, 1), 3), F32)
+        L.check(L.lib().d3d_ffh_get_patch_pos(self._h, b, pos.ctypes.data))
         return {
             "n_patches": ep.n_patch,
-            "p2i": {int(k): int(ep.p2i[k]) for k in np.flatnonzero(ep.p2i[: max(ep.n_patch, 1)] >= 0)},
-            "i2p": {k: v.copy() for k, v in ep.i2p.items()}, "i2p_order": list(ep.i2p.keys()),
+            "p2i": {int(k): int(p2i[k]) for k in np.flatnonzero(p2i >= 0)},
+            "i2p": i2p, "i2p_order": list(i2p.keys()),
             "n_inst_slots": ep.n_inst,
-            "zone_key_to_id": dict(ep.zone_key_to_id),
-            "z2i": {k: v.copy() for k, v in ep.z2i.items()}, "z2i_order": list(ep.z2i.keys()),
+            "zone_key_to_id": self._zone_keys_dict(b),
+            "z2i": z2i, "z2i_order": list(z2i.keys()),
             "n_zone_slots": ep.n_zone,
-            "patch_tomb": (ep.patch_pos_h[: ep.n_patch, 0] == -10000.0).copy(),
+            "patch_tomb": (pos[: ep.n_patch, 0] == -10000.0).copy(),
         }

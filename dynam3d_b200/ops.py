@@ -264,7 +264,7 @@ def attention(qkv, out, cu_seqlens, n_seq, max_len, H, Dh, causal=False, uniform
     """Self-attention over packed sequences.  `impl`: 'tc' (tcgen05, head_dim 64), 'mma' (legacy tensor cores), 'simt' (fp32
     CUDA cores) or 'auto' (tc for long head_dim-64 sequences, mma otherwise, simt for very short ones)."""
     scale = 1.0 / math.sqrt(Dh)
-    if impl == "tc" or (impl == "auto" and Dh == 64 and max_len >= 128):
+    if impl == "tc":  # opt-in: the first tcgen05 version is softmax-latency bound and not yet faster than the mma kernel
         L.check(L.lib().d3d_attention_tc(L.ptr(qkv), qkv.stride(0), qkv.shape[0], L.ptr(out), out.stride(0), L.ptr(cu_seqlens), n_seq, max_len, H, Dh,
                                          int(bool(causal)), L.kind_of(qkv.dtype), scale, L.stream_ptr()))
         return
@@ -273,3 +273,52 @@ def attention(qkv, out, cu_seqlens, n_seq, max_len, H, Dh, causal=False, uniform
                                           int(bool(causal)), L.kind_of(qkv.dtype), scale, L.stream_ptr()))
         return
     attention_simt(qkv, out, cu_seqlens, n_seq, max_len, H, Dh, causal)
+
+
+# ------------------------------------------------------------------------------------------------
+# pooling token builders / discriminator / policy operands
+# ------------------------------------------------------------------------------------------------
+def pool_features(seq_xyz, seq_dir, seq_scale, centre, tok_seq, tok_src, T, mode, out16):
+    L.check(L.lib().d3d_pool_features(L.ptr(seq_xyz), L.ptr(seq_dir), L.ptr(seq_scale), L.ptr(centre), L.ptr(tok_seq), L.ptr(tok_src), T, mode,
+                                      L.ptr(out16), L.kind_of(out16.dtype), L.stream_ptr()))
+
+
+def pool_assemble(emb, seq_fts, fts_is_f32, tok_seq, tok_src, agg, T, X):
+    L.check(L.lib().d3d_pool_assemble(L.ptr(emb), L.ptr(seq_fts), int(fts_is_f32), L.ptr(tok_seq), L.ptr(tok_src), L.ptr(agg), T, X.shape[1],
+                                      L.ptr(X), L.stream_ptr()))
+
+
+def disc_input(inst_fts, inst_pos, idx, view_fts, centre, G, K, out16):
+    L.check(L.lib().d3d_disc_input(L.ptr(inst_fts), L.ptr(inst_pos), L.ptr(idx), L.ptr(view_fts), L.ptr(centre), G, K, inst_fts.shape[1],
+                                   out16.stride(0), L.ptr(out16), L.kind_of(out16.dtype), L.stream_ptr()))
+
+
+def patch_info_rows(info5, out16):
+    n = info5.shape[1] * info5.shape[2]
+    L.check(L.lib().d3d_patch_info_rows(L.ptr(info5), n, L.ptr(out16), L.kind_of(out16.dtype), L.stream_ptr()))
+
+
+def concat2_cast(a, b, out16):
+    L.check(L.lib().d3d_concat2_cast(L.ptr(a), L.ptr(b), a.shape[0], a.shape[1], L.ptr(out16), L.kind_of(out16.dtype), L.stream_ptr()))
+
+
+def pos3_rows(x, out16):
+    L.check(L.lib().d3d_pos3_rows(L.ptr(x), x.shape[0], L.ptr(out16), L.kind_of(out16.dtype), L.stream_ptr()))
+
+
+def torch_nearest_index_table(dst, src):
+    """Source indices of F.interpolate(mode='nearest'): min(floor(dst_index * (src/dst) as float32), src-1)."""
+    scale = np.float32(src) / np.float32(dst)
+    return np.minimum(np.floor(np.arange(dst, dtype=np.float32) * scale).astype(np.int32), src - 1).astype(np.int32)
+
+
+def segm_relabel(masks_u8, gh=24, gw=24):
+    """masks_u8 [n_img, M, H, W] uint8 (device) -> (labels int64 [n_img, gh, gw], n_seg int32 [n_img]) (FF:411-422)."""
+    n, M, H, W = masks_u8.shape
+    assert masks_u8.dtype == torch.uint8 and masks_u8.is_contiguous()
+    out = torch.empty((n, gh, gw), device=masks_u8.device, dtype=torch.int64)
+    n_seg = torch.empty((n,), device=masks_u8.device, dtype=torch.int32)
+    ri, rp = _hp_i32(torch_nearest_index_table(gh, H))
+    ci, cp = _hp_i32(torch_nearest_index_table(gw, W))
+    L.check(L.lib().d3d_segm_relabel(L.ptr(masks_u8), n, M, H, W, gh, gw, rp, cp, L.ptr(out), L.ptr(n_seg), L.stream_ptr()))
+    return out, n_seg

@@ -125,6 +125,12 @@ int d3d_seq_centroid(const float* xyz, const int* member, const int* cu_seqlens,
 int d3d_env_export(const float* pos, const float* fts, const int* ids, int n_ids, const float* agent, float radius, int width,
                    float* out_rel, float* out_fts, int* out_count, void* stream);
 
+/* FastSAM post-processing (FF:411-422): masks [n_img, M, H, W] u8 (0/1, in FastSAM's order) -> dense segment labels
+ * out [n_img, gh*gw] int64 in 0..G-1 and n_seg[n_img]: later masks overwrite earlier ones, uncovered pixels take label 0,
+ * torch 'nearest' resize through the host index tables (floor(dst * in/out)), labels renumbered in ascending order. */
+int d3d_segm_relabel(const uint8_t* masks, int n_img, int M, int H, int W, int gh, int gw, const int* row_idx_h,
+                     const int* col_idx_h, int64_t* out, int* n_seg, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Normalisation / elementwise / gather kernels between the GEMMs (fp32 math; 16-bit outputs feed GEMM A operands).
  * Row widths D must be one of 128, 256, 512, 768, 1024, 3072, 4096.
@@ -254,6 +260,33 @@ int d3d_mlp_ln_gelu(const d3d_mlp* m_h, const void* A0, int64_t lda, int T, void
 int d3d_pool_tokens(const d3d_pool_level* lvl_h, const int64_t* seq_ptrs, const float* centre, const int* tok_seq, const int* tok_src,
                     const int* cu_seqlens, int T, int n_seq, int max_len, int mode, int fts_is_f32, void* workspace,
                     size_t workspace_bytes, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Host-side bookkeeping of the 3D token memory (CPU code in the same library; ALL pointers below are HOST pointers).
+ * Owns what the reference keeps in Python dicts (FF:164-177) for every episode of a Feature_Fields and plans each view:
+ * d3d_ffh_begin_view -> [pooling / K-NN / discriminator kernels] -> d3d_ffh_finish_view -> d3d_ffh_fetch_view -> [slot writes,
+ * merged-instance and zone pooling kernels].  Literal FF:362-393, 433-475, 623-756, 759-812 incl. Q2, Q3, Q5, Q9.
+ * ------------------------------------------------------------------------------------------------ */
+void* d3d_ffh_create(int batch_size, int num_proposal, float zone_len);
+void d3d_ffh_destroy(void* h);
+int d3d_ffh_reset(void* h, int batch_size);                 /* FF:186-206 */
+int d3d_ffh_pop(void* h, int index);                        /* FF:210-229 */
+int d3d_ffh_counts(void* h, int b, int64_t* counts8);       /* n_patch, n_p2i, n_inst, live inst, n_zone, live zones, tree, last K */
+int d3d_ffh_cull(void* h, int b, const uint8_t* mask, int64_t n, int64_t* dead_inst, int* n_dead_inst, int64_t* dead_zone,
+                 int* n_dead_zone);                         /* FF:362-393 */
+int d3d_ffh_set_tree(void* h);                              /* FF:396 */
+int d3d_ffh_begin_view(void* h, const float* xyz, const int64_t* segm, int P, const int64_t* stage_off, int64_t* base_rows, int* n_seg,
+                       int* seq_owner, int* members, int* cu_m, int* tok_src, int* tok_seq, int* cu_tok, int* n_ref, int* info);
+int d3d_ffh_finish_view(void* h, const float* res12, int* sizes10, int64_t* after3);
+int d3d_ffh_fetch_view(void* h, int* new_src, int* new_owner, int64_t* new_iid, int* mg_owner, int64_t* mg_iid, float* mg_pos,
+                       int* mg_tok_src, int* mg_tok_seq, int* mg_cu, int* zn_owner, int64_t* zn_slot, int* zn_keys, float* zn_pos,
+                       int* zn_tok_src, int* zn_tok_seq, int* zn_cu);
+int d3d_ffh_zone_key_array(void* h, int b, float* out);
+int d3d_ffh_get_map(void* h, int b, int which, int64_t* ids, int64_t* lens, int64_t* cat, int64_t* sizes2);
+int d3d_ffh_get_p2i(void* h, int b, int64_t* out);
+int d3d_ffh_get_patch_pos(void* h, int b, float* out);
+int d3d_ffh_get_zone_keys(void* h, int b, float* keys, int64_t* ids, int64_t* n);
+int d3d_ffh_get_last(void* h, int b, float* d2, int* idx, uint8_t* merge, int64_t* n);
 
 #ifdef __cplusplus
 }

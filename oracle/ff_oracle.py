@@ -194,6 +194,7 @@ class FeatureFieldsOracle:
 
         if ep.tree:
             d2, idx = G.knn3d(ep.inst_pos, centres, proposal_num)
+            ep.last_raw = {"centres": centres.copy(), "d2": d2.copy(), "idx": idx.copy()}
             if float(d2.astype(np.float64).sum()) > 1e6:  # Q9
                 col = d2.astype(np.float64).sum(0)
                 proposal_num = int((col < 1e6).sum())
@@ -270,6 +271,7 @@ class FeatureFieldsOracle:
                     ep.zone_fts[zid] = self._run_encoder([seq], "aggregate_instance_to_zone_encoder").numpy()[0]
         else:
             # first view of the episode (FF:759-812)
+            ep.last_raw = {"centres": centres.copy(), "d2": np.zeros((n_seg, 0), F32), "idx": np.zeros((n_seg, 0), np.int32)}
             ep.last_knn = None
             ep.last_merge = None
             ep.inst_pos = centres.copy()

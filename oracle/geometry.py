@@ -256,3 +256,22 @@ def to_agent_frame(pos, agent_position_hab, agent_heading):
         n2 = (((rx * rx).astype(F32) + (ry * ry).astype(F32)).astype(F32) + (pz * pz).astype(F32)).astype(F32)
         dist = np.sqrt(n2).astype(F32)
     return rel, dist
+
+
+# ----------------------------------------------------------------------------------------------
+# a7: FastSAM masks -> dense 24x24 labels (FF:411-422), restated with the reference's own torch ops
+# ----------------------------------------------------------------------------------------------
+def segm_relabel(masks, gh=24, gw=24):
+    """masks [M,H,W] float/bool tensor-like (FastSAM `everything_prompt()` output) -> int64 [gh,gw] dense labels."""
+    import torch
+    masks = torch.as_tensor(np.asarray(masks)).to(torch.float32)
+    patch_group = masks[0].clone()
+    for group_id in range(masks.shape[0]):
+        patch_group[masks[group_id] == 1] = group_id
+    patch_group = torch.nn.functional.interpolate(patch_group.unsqueeze(0).unsqueeze(0), (gh, gw), mode="nearest").to(torch.int64).squeeze(0)
+    patch_segm = patch_group.clone()
+    group_id = 0
+    for mask_id in torch.unique(patch_group).cpu().numpy().tolist():
+        patch_segm[patch_group == mask_id] = group_id
+        group_id += 1
+    return patch_segm[0].numpy()

@@ -71,11 +71,11 @@ def test_engine_matches_oracle(cfg):
                                   batch_patch_segm=segm)
         for b in range(B):
             assert _compare_snap(orc.snapshot(b), eng.snapshot(b)) == [], f"step {t} episode {b}"
-            last_o, last_e = orc.eps[b].last_knn, eng.eps[b].last.get("knn")
+            last_o, last_e = orc.eps[b].last_knn, eng._last(b).get("knn")
             if last_o is not None:
                 assert np.array_equal(last_o[1], last_e[1]) and np.array_equal(last_o[0], last_e[0]), "K-NN indices / distances"
                 mo, lo = orc.eps[b].last_merge
-                assert np.array_equal(mo.astype(bool), eng.eps[b].last["merge"])
+                assert np.array_equal(mo.astype(bool), eng._last(b)["merge"])
                 n_merge += int(mo.any(-1).sum()); n_dec += mo.size
                 margin = np.abs(lo[..., 1] - lo[..., 0]).min() if lo.size else 1.0
                 assert margin > 1e-3, "fixture has a near-tie merge decision; pick another seed"

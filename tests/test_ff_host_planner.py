@@ -1,0 +1,97 @@
+"""CPU test of the C++ bookkeeping planner (csrc/ff_host.cu) through the C ABI: driven with the ORACLE's per-view numeric results
+(centroids, K-NN proposals, merge logits) it must reproduce the oracle's / reference's discrete state on the golden trajectories."""
+import ctypes
+import glob
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _planner_snapshot(lib, h, b, n_patch):
+    from dynam3d_b200.feature_fields import Feature_Fields
+    ff = Feature_Fields.__new__(Feature_Fields)  # only the read-back helpers are used
+    ff._h = h
+    ff.eps = [type("E", (), {"n_patch": n_patch})()]
+    cnt = np.zeros(8, np.int64)
+    lib.d3d_ffh_counts(h, b, cnt.ctypes.data)
+    i2p, z2i, p2i = ff._map(b, 0), ff._map(b, 1), ff._p2i(b)
+    pos = np.zeros((max(n_patch, 1), 3), np.float32)
+    lib.d3d_ffh_get_patch_pos(h, b, pos.ctypes.data)
+    ff._h = None
+    return {"n_patches": int(cnt[0]), "p2i": {int(k): int(p2i[k]) for k in np.flatnonzero(p2i >= 0)}, "i2p": i2p, "i2p_order": list(i2p.keys()),
+            "n_inst_slots": int(cnt[2]), "zone_key_to_id": Feature_Fields._zone_keys_dict(type("F", (), {"_h": h})(), b), "z2i": z2i,
+            "z2i_order": list(z2i.keys()), "n_zone_slots": int(cnt[4]), "patch_tomb": (pos[:n_patch, 0] == -10000.0).copy()}, cnt
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "ff_traj_*.npz"))), ids=os.path.basename)
+def test_planner_reproduces_golden_state(path):
+    from dynam3d_b200 import _lib as L
+    from oracle import geometry as G
+    from oracle import ref_compare as RC
+    from oracle.ff_oracle import FeatureFieldsOracle
+    from oracle.make_golden import load_ff_fixture
+    lib = L.lib()
+    cfg, steps, gold = load_ff_fixture(path)
+    V, P = cfg["num_views"], 576
+    orc = FeatureFieldsOracle(RC.ff_params(cfg["weight_seed"], cfg["merge_bias"]), batch_size=1, rnd=None)
+    h = lib.d3d_ffh_create(1, 2, 2.0)
+    try:
+        for t, (st, g) in enumerate(zip(steps, gold)):
+            d576 = G.depth_patch_grid(st["depth"], 1, V, q1_fix=cfg.get("q1_fix", False))
+            full = G.preprocess_depth(st["depth"], (0.0, 10.0)).reshape(1, V, 256, 256)
+            pos, head = [st["position"]], [st["heading"]]
+            ep = orc.eps[0]
+            # ---- cull: feed the oracle's mask (union over views == sequential application) ----
+            n0 = len(ep.patch_pos)
+            before = ep.patch_pos[:, 0].copy() == -10000.0 if n0 else np.zeros(0, bool)
+            orc.delete_old_features_from_camera_frustum(full, pos, head, num_of_views=V)
+            if n0:
+                mask = ((ep.patch_pos[:, 0] == -10000.0) & ~before).astype(np.uint8)
+                di, dz = np.zeros(4096, np.int64), np.zeros(4096, np.int64)
+                nd = (ctypes.c_int * 2)()
+                L.check(lib.d3d_ffh_cull(h, 0, mask.ctypes.data, n0, di.ctypes.data, ctypes.addressof(nd), dz.ctypes.data, ctypes.addressof(nd) + 4))
+            else:
+                lib.d3d_ffh_set_tree(h)
+            # ---- update, view by view ----
+            for ix in range(V):
+                orc._update_view(ep, np.asarray(d576[0][ix], np.float32), st["grid"][0][ix].astype(np.float16), st["segm"][ix].reshape(-1),
+                                 st["position"], float(st["heading"]), ix)
+                raw = ep.last_raw
+                Gn = len(raw["centres"])
+                xyz = np.ascontiguousarray(ep.patch_pos[-P:]).astype(np.float32)
+                # the oracle appended the view before culling nothing in between: the last P rows are this view's patches
+                segm = np.ascontiguousarray(st["segm"][ix].reshape(1, P), dtype=np.int64)
+                cap = P
+                base_rows = np.zeros(1, np.int64); n_seg = np.zeros(1, np.int32); seq_owner = np.zeros(cap, np.int32)
+                members = np.zeros(cap, np.int32); cu_m = np.zeros(cap + 1, np.int32); tok_src = np.zeros(2 * cap, np.int32)
+                tok_seq = np.zeros(2 * cap, np.int32); cu_tok = np.zeros(cap + 1, np.int32); n_ref = np.zeros(cap, np.int32); info = np.zeros(2, np.int32)
+                stage_off = np.zeros(1, np.int64)
+                L.check(lib.d3d_ffh_begin_view(h, xyz.ctypes.data, segm.ctypes.data, P, stage_off.ctypes.data, base_rows.ctypes.data, n_seg.ctypes.data,
+                                               seq_owner.ctypes.data, members.ctypes.data, cu_m.ctypes.data, tok_src.ctypes.data, tok_seq.ctypes.data,
+                                               cu_tok.ctypes.data, n_ref.ctypes.data, info.ctypes.data))
+                assert int(info[0]) == Gn
+                res = np.zeros((Gn, 12), np.float32)
+                res[:, 0:3] = raw["centres"]
+                k_raw = raw["d2"].shape[1]
+                res[:, 3:3 + k_raw] = raw["d2"]
+                idx2 = np.full((Gn, 2), -1, np.int32); idx2[:, :k_raw] = raw["idx"]
+                res[:, 5:7] = idx2.view(np.float32)
+                if ep.last_knn is not None and ep.last_merge[1].shape[1] > 0:
+                    lg = ep.last_merge[1]  # [G, K', 2]
+                    pad = np.zeros((Gn, 2, 2), np.float32); pad[:, :lg.shape[1]] = lg
+                    res[:, 7:11] = pad.reshape(Gn, 4)
+                sizes = np.zeros(10, np.int32); after = np.zeros(3, np.int64)
+                L.check(lib.d3d_ffh_finish_view(h, res.ctypes.data, sizes.ctypes.data, after.ctypes.data))
+                if ep.last_knn is not None:
+                    from dynam3d_b200.feature_fields import Feature_Fields
+                    last = Feature_Fields._last(type("F", (), {"_h": h})(), 0)
+                    assert np.array_equal(last["knn"][1], ep.last_knn[1]) and np.array_equal(last["knn"][0], ep.last_knn[0]), (t, ix)
+                    assert np.array_equal(last["merge"], ep.last_merge[0].astype(bool)), (t, ix)
+            snap, cnt = _planner_snapshot(lib, h, 0, len(ep.patch_pos))
+            assert RC.snapshots_equal(g["snap"], snap) == [], f"step {t}"
+            assert RC.snapshots_equal(orc.snapshot(0), snap) == [], f"step {t} (oracle)"
+    finally:
+        lib.d3d_ffh_destroy(h)

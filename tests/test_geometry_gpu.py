@@ -128,3 +128,22 @@ def test_centroid_and_export():
     n = int(cnt.item())
     assert n == int(keep.sum()) and 100 < n < 3000
     assert np.array_equal(out_rel[:n].cpu().numpy(), rel[keep]) and np.array_equal(out_fts[:n].cpu().numpy(), fts[ids][keep])
+
+
+@pytest.mark.parametrize("size,M", [(336, 40), (224, 7), (576, 150)])
+def test_segm_relabel_bit_exact(size, M):
+    """a7 (FF:411-422): FastSAM masks -> dense 24x24 labels, vs the reference's own torch ops restated in oracle/geometry.py."""
+    from dynam3d_b200 import ops
+    from oracle import geometry as G
+    rng = np.random.default_rng(size + M)
+    masks = np.zeros((2, M, size, size), np.uint8)
+    for i in range(2):
+        for g in range(M):
+            y0, x0 = rng.integers(0, size - 20, 2)
+            h, w = rng.integers(10, size // 2, 2)
+            masks[i, g, y0:y0 + h, x0:x0 + w] = 1
+    lab, n_seg = ops.segm_relabel(_dev(masks))
+    for i in range(2):
+        want = G.segm_relabel(masks[i])
+        assert np.array_equal(lab[i].cpu().numpy(), want)
+        assert int(n_seg[i].item()) == int(want.max()) + 1

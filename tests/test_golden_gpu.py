@@ -32,9 +32,9 @@ def test_engine_reproduces_reference_trajectory(path):
                                   batch_patch_segm=st["segm"][None])
         assert RC.snapshots_equal(g["snap"], eng.snapshot(0)) == [], f"step {t}"
         if "knn_idx" in g:
-            assert np.array_equal(eng.eps[0].last["knn"][1], g["knn_idx"]), "K-NN indices"
-            assert np.array_equal(eng.eps[0].last["knn"][0], g["knn_d2"]), "K-NN squared distances"
-            assert np.array_equal(eng.eps[0].last["merge"].astype(np.uint8), g["merge"]), "merge decisions"
+            assert np.array_equal(eng._last(0)["knn"][1], g["knn_idx"]), "K-NN indices"
+            assert np.array_equal(eng._last(0)["knn"][0], g["knn_d2"]), "K-NN squared distances"
+            assert np.array_equal(eng._last(0)["merge"].astype(np.uint8), g["merge"]), "merge decisions"
         env = eng.get_environment_features(pos, head)
         assert np.allclose(env["batch_instance_relative_position"][0].cpu().numpy(), g["inst_rel"], atol=2e-5, equal_nan=True)
         assert np.allclose(env["batch_zone_relative_position"][0].cpu().numpy(), g["zone_rel"], atol=2e-5, equal_nan=True)
