@@ -97,6 +97,8 @@ SIGNATURES = {
     "d3d_ffh_finish_view": [_P, _P, _P, _P], "d3d_ffh_fetch_view": [_P] * 17, "d3d_ffh_zone_key_array": [_P, _I, _P],
     "d3d_ffh_get_map": [_P, _I, _I, _P, _P, _P, _P], "d3d_ffh_get_p2i": [_P, _I, _P], "d3d_ffh_get_patch_pos": [_P, _I, _P],
     "d3d_ffh_get_zone_keys": [_P, _I, _P, _P, _P], "d3d_ffh_get_last": [_P, _I, _P, _P, _P, _P],
+    "d3d_split16": [_P, _L, _P, _L, _I, _I, _I, _P],
+    "d3d_attention_f32": [_P, _L, _P, _L, _P, _I, _I, _I, _I, _I, _F, _P],
 }
 OPTIONAL = set()
 
@@ -158,8 +160,7 @@ class stream_scope:
         global _STREAM
         import torch
         self.prev = _STREAM
-        if _STREAM is None:
-            _STREAM = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _STREAM = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)  # re-query: scopes may nest inside torch.cuda.stream(...)
         return self
 
     def __exit__(self, *a):

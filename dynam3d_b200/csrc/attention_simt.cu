@@ -137,3 +137,103 @@ extern "C" int d3d_attention_simt(const void* qkv, int64_t ld, void* out, int64_
   D3D_CHECK_LAUNCH();
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// fp32-in / fp32-out variant for the "precise" pipeline (no 16-bit rounding of q, k, v or the output)
+// ------------------------------------------------------------------------------------------------
+namespace {
+constexpr int KC32 = 32;
+
+template <int D>
+__global__ void __launch_bounds__(NWARP * 32) attn_simt_f32_kernel(const float* __restrict__ qkv, long long ld, float* __restrict__ out,
+                                                                   long long ldo, const int* __restrict__ cu, int H, int causal, float scale) {
+  constexpr int DPL = D / 32;
+  __shared__ float sK[KC32][D + 1];
+  __shared__ float sV[KC32][D];
+  __shared__ float sQ[QT][D];
+  __shared__ float sP[NWARP][KC32];
+  const int seq = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * QT;
+  const int b = cu[seq], len = cu[seq + 1] - b;
+  if (q0 >= len) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t qoff = (size_t)h * D, koff = (size_t)(H + h) * D, voff = (size_t)(2 * H + h) * D;
+  for (int i = threadIdx.x; i < QT * D; i += blockDim.x) {
+    const int qi = i / D, d = i % D;
+    sQ[qi][d] = (q0 + qi < len) ? qkv[(size_t)(b + q0 + qi) * ld + qoff + d] * scale : 0.f;
+  }
+  float m[QPW], l[QPW], o[QPW][DPL];
+#pragma unroll
+  for (int i = 0; i < QPW; ++i) {
+    m[i] = -INFINITY; l[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < DPL; ++j) o[i][j] = 0.f;
+  }
+  const int kmax = causal ? min(len, q0 + QT) : len;
+  for (int c0 = 0; c0 < kmax; c0 += KC32) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < KC32 * D; i += blockDim.x) {
+      const int r = i / D, d = i % D;
+      const bool ok = c0 + r < len;
+      const size_t row = (size_t)(b + c0 + r) * ld;
+      sK[r][d] = ok ? qkv[row + koff + d] : 0.f;
+      sV[r][d] = ok ? qkv[row + voff + d] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int qi = 0; qi < QPW; ++qi) {
+      const int ql = warp * QPW + qi;
+      const int q = q0 + ql;
+      if (q >= len) continue;
+      if (causal && c0 > q) continue;
+      float s0 = 0.f;
+#pragma unroll 8
+      for (int d = 0; d < D; ++d) s0 = fmaf(sQ[ql][d], sK[lane][d], s0);
+      const int j0 = c0 + lane;
+      const bool ok0 = j0 < len && (!causal || j0 <= q);
+      if (!ok0) s0 = -INFINITY;
+      const float mx = warp_max(s0);
+      const float m_new = fmaxf(m[qi], mx);
+      const float p0 = ok0 ? expf(s0 - m_new) : 0.f;
+      const float corr = (m[qi] == -INFINITY) ? 0.f : expf(m[qi] - m_new);
+      l[qi] = l[qi] * corr + warp_sum(p0);
+      m[qi] = m_new;
+      sP[warp][lane] = p0;
+      __syncwarp();
+      float acc[DPL];
+#pragma unroll
+      for (int j = 0; j < DPL; ++j) acc[j] = o[qi][j] * corr;
+      const int jn = min(KC32, kmax - c0);
+      for (int j = 0; j < jn; ++j) {
+        const float p = sP[warp][j];
+#pragma unroll
+        for (int t = 0; t < DPL; ++t) acc[t] = fmaf(p, sV[j][lane + 32 * t], acc[t]);
+      }
+#pragma unroll
+      for (int j = 0; j < DPL; ++j) o[qi][j] = acc[j];
+      __syncwarp();
+    }
+  }
+#pragma unroll
+  for (int qi = 0; qi < QPW; ++qi) {
+    const int q = q0 + warp * QPW + qi;
+    if (q >= len) continue;
+    const float inv = 1.0f / l[qi];
+#pragma unroll
+    for (int t = 0; t < DPL; ++t) out[(size_t)(b + q) * ldo + (size_t)h * D + lane + 32 * t] = o[qi][t] * inv;
+  }
+}
+}  // namespace
+
+extern "C" int d3d_attention_f32(const float* qkv, int64_t ld, float* out, int64_t ldo, const int* cu_seqlens, int n_seq, int max_len, int H,
+                                 int Dh, int causal, float scale, void* stream) {
+  if (n_seq == 0 || max_len == 0) return 0;
+  D3D_REQUIRE(qkv && out && cu_seqlens, "args");
+  D3D_REQUIRE(Dh == 64 || Dh == 96, "head_dim 64 or 96");
+  D3D_REQUIRE(n_seq <= 65535 && H <= 65535, "grid limits");
+  dim3 grid(d3d_cdiv(max_len, QT), H, n_seq);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (Dh == 64) attn_simt_f32_kernel<64><<<grid, NWARP * 32, 0, st>>>(qkv, ld, out, ldo, cu_seqlens, H, causal, scale);
+  else attn_simt_f32_kernel<96><<<grid, NWARP * 32, 0, st>>>(qkv, ld, out, ldo, cu_seqlens, H, causal, scale);
+  D3D_CHECK_LAUNCH();
+  return 0;
+}

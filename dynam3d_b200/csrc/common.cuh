@@ -67,12 +67,15 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 __device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 
-// 16-bit storage type selected at run time: 0 = fp16, 1 = bf16 (matches D3D_F16 / D3D_BF16)
+// storage type selected at run time: 0 = fp16, 1 = bf16, 2 = fp32 (matches D3D_F16 / D3D_BF16 / D3D_OUT_F32);
+// the fp32 kind is what the "precise" (split fp16x2 operand) pipeline stores between kernels
 __device__ __forceinline__ float ld16(const void* p, size_t i, int kind) {
+  if (kind == D3D_OUT_F32) return ((const float*)p)[i];
   return kind == D3D_BF16 ? __bfloat162float(((const __nv_bfloat16*)p)[i]) : __half2float(((const __half*)p)[i]);
 }
 __device__ __forceinline__ void st16(void* p, size_t i, float v, int kind) {
-  if (kind == D3D_BF16) ((__nv_bfloat16*)p)[i] = __float2bfloat16_rn(v);
+  if (kind == D3D_OUT_F32) ((float*)p)[i] = v;
+  else if (kind == D3D_BF16) ((__nv_bfloat16*)p)[i] = __float2bfloat16_rn(v);
   else ((__half*)p)[i] = __float2half_rn(v);
 }
 __device__ __forceinline__ uint32_t pack16x2(float a, float b, int kind) {

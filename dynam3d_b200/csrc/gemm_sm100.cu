@@ -1,6 +1,6 @@
 // tcgen05 / TMEM / TMA persistent GEMM for sm_100a:  C[M,N] = epi(A[M,K] @ W[N,K]^T), fp32 accumulate.
 //
-// Structure (one CTA per SM, 256 threads, static persistent tile schedule):
+// Structure (one CTA per SM, 384 threads, static persistent tile schedule):
 //   warp 0      : TMA producer  -- cp.async.bulk.tensor.2d of a 128x64 A tile and a BNx64 W tile per stage
 //                                  (SWIZZLE_128B, K-major), mbarrier complete_tx
 //   warp 1      : MMA issuer    -- one elected lane issues 4 x tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16)
@@ -8,8 +8,8 @@
 //                                  last K block, publishes the accumulator
 //   warp 2      : TMEM allocator (2*BN columns: double-buffered accumulator so the epilogue of tile i overlaps
 //                                  the main loop of tile i+1)
-//   warps 4..7  : epilogue      -- tcgen05.ld 32x32b (one accumulator row per thread), bias / activation / residual,
-//                                  vectorised global stores
+//   warps 4..11 : epilogue      -- tcgen05.ld 32x32b (one accumulator row per thread, two warps per TMEM lane quadrant split the
+//                                  columns), bias / activation / residual in registers, vectorised global stores
 // Replaces the cuBLAS calls behind every nn.Linear on the reference path (see include/dynam3d_b200.h).
 #include "common.cuh"
 
@@ -18,7 +18,8 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 x 16-bit = 128 B = one SWIZZLE_128B atom row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;  // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4-11: epilogue (2 per TMEM lane quadrant)
+constexpr int NUM_EPI_WARPS = 8;
 
 template <int BN>
 struct Cfg {
@@ -163,7 +164,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
+      mbar_init(tempty_bar(a), NUM_EPI_WARPS);  // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -226,8 +227,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue (warps 4..7 <-> TMEM lane quadrants 0..3) =====================
+    // ===================== epilogue: warps 4..11; warp w drains TMEM lane quadrant w%4, column half (w-4)/4 =====================
     const int q = warp & 3;
+    const int chalf = (warp - 4) >> 2;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -239,8 +241,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < M;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+#pragma unroll 2
+      for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 32) {
         uint32_t r[32];
         tmem_ld32(taddr + (uint32_t)c, r);
         tmem_ld_wait();
@@ -249,10 +251,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          const bool full = col0 + 32 <= N;
           if (ep.bias) {
+            if (full) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (col0 + i < N) v[i] += __ldg(ep.bias + col0 + i);
+              for (int i = 0; i < 8; ++i) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(ep.bias + col0) + i);
+                v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (col0 + i < N) v[i] += __ldg(ep.bias + col0 + i);
+            }
           }
           if (ep.act == D3D_ACT_SWIGLU) {
             // row-interleaved gate/up: acc cols (2j, 2j+1) -> out col j
@@ -291,7 +302,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = __fdividef(v[i], 1.0f + __expf(-v[i]));
             }
-            const bool full = col0 + 32 <= N;
             if (ep.residual) {
               const float* res = ep.residual + (long long)row * ep.ldres + col0;
               if (full) {
@@ -436,6 +446,7 @@ int validate(const d3d_gemm_args& a) {
   const int esz = a.out_kind == D3D_OUT_F32 ? 4 : 2;
   D3D_REQUIRE(((uintptr_t)a.C % 16) == 0 && ((a.ldc * esz) % 16) == 0, "C rows must be 16-byte aligned");
   D3D_REQUIRE(!a.residual || (((uintptr_t)a.residual % 16) == 0 && (a.ldres % 4) == 0), "residual rows must be 16-byte aligned");
+  D3D_REQUIRE(!a.bias || ((uintptr_t)a.bias % 16) == 0, "bias must be 16-byte aligned");
   return 0;
 }
 

@@ -197,11 +197,26 @@ __global__ void preprocess_im2col_kernel(const uint8_t* __restrict__ img, int N,
 }
 
 // zero the K padding columns [k, kpad) of an im2col matrix
-__global__ void zero_pad_cols_kernel(uint16_t* out, long long rows, int k, int kpad) {
+__global__ void zero_pad_cols_kernel(void* out, long long rows, int k, int kpad, int kind) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int w = kpad - k;
   if (idx >= rows * w) return;
-  out[(idx / w) * kpad + k + (idx % w)] = 0;
+  st16(out, (size_t)((idx / w) * kpad + k + (idx % w)), 0.f, kind);
+}
+
+// precise-mode operand split: out[r, c] = hi = fp16(x), out[r, K + c] = lo = fp16(x - hi), and with terms == 3 also
+// out[r, 2K + c] = hi (for weights that are not fp16-representable: A.[W_hi|W_hi|W_lo] = A_hi W_hi + A_lo W_hi + A_hi W_lo)
+__global__ void split16_kernel(const float* __restrict__ in, long long ldi, __half* __restrict__ out, long long ldo, int T, int K, int terms) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)T * K) return;
+  const long long r = i / K, c = i % K;
+  const float x = in[r * ldi + c];
+  const __half hi = __float2half_rn(x);
+  const __half lo = __float2half_rn(x - __half2float(hi));
+  __half* o = out + r * ldo;
+  o[c] = hi;
+  o[K + c] = lo;
+  if (terms == 3) o[2 * (long long)K + c] = hi;
 }
 
 // ViT token assembly + ln_pre (CLIPM:223-225): X[n, 0] = cls + pos[0]; X[n, 1+i] = conv[n*g2+i] + pos[1+i]; X = ln_pre(X)
@@ -330,7 +345,7 @@ extern "C" int d3d_preprocess_im2col(const uint8_t* img, int N, int Hin, int Win
   const long long rows = (long long)N * g * g;
   const int k = 3 * patch * patch;
   if (kpad > k) {
-    zero_pad_cols_kernel<<<d3d_cdiv(rows * (kpad - k), 256), 256, 0, st>>>((uint16_t*)out, rows, k, kpad);
+    zero_pad_cols_kernel<<<d3d_cdiv(rows * (kpad - k), 256), 256, 0, st>>>(out, rows, k, kpad, kind);
     D3D_CHECK_LAUNCH();
   }
   const long long total = (long long)N * R * R;
@@ -373,6 +388,14 @@ extern "C" int d3d_add_inplace(float* a, const float* b, int64_t n_rows, int D, 
 extern "C" int d3d_cast16(const float* in, int64_t ldi, void* out, int64_t ldo, int T, int D, int kind, void* stream) {
   if (T == 0) return 0;
   cast_rows_kernel<<<d3d_cdiv((long long)T * D, 256), 256, 0, (cudaStream_t)stream>>>(in, ldi, out, ldo, T, D, kind);
+  D3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int d3d_split16(const float* in, int64_t ldi, void* out16, int64_t ldo, int T, int K, int terms, void* stream) {
+  if (T == 0) return 0;
+  D3D_REQUIRE(in && out16 && (terms == 2 || terms == 3) && ldo >= (int64_t)terms * K, "args");
+  split16_kernel<<<d3d_cdiv((long long)T * K, 256), 256, 0, (cudaStream_t)stream>>>(in, ldi, (__half*)out16, ldo, T, K, terms);
   D3D_CHECK_LAUNCH();
   return 0;
 }

@@ -32,6 +32,11 @@ __global__ void pool_features_kernel(const long long* __restrict__ seq_xyz, cons
       f[6] = reinterpret_cast<const float*>(seq_scale[s])[src];
     }
   }
+  if (kind == D3D_OUT_F32) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ((float*)out)[(size_t)t * 8 + i] = f[i];
+    return;
+  }
   uint4 p = make_uint4(pack16x2(f[0], f[1], kind), pack16x2(f[2], f[3], kind), pack16x2(f[4], f[5], kind), pack16x2(f[6], f[7], kind));
   reinterpret_cast<uint4*>(out)[t] = p;
 }
@@ -87,6 +92,12 @@ __global__ void patch_info_rows_kernel(const float* __restrict__ info5, long lon
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float d = info5[3 * plane + i];
+  if (kind == D3D_OUT_F32) {
+    float* o = (float*)out + i * 8;
+    o[0] = info5[i]; o[1] = info5[plane + i]; o[2] = info5[2 * plane + i]; o[3] = sinf(d); o[4] = cosf(d); o[5] = info5[4 * plane + i];
+    o[6] = 0.f; o[7] = 0.f;
+    return;
+  }
   uint4 p = make_uint4(pack16x2(info5[i], info5[plane + i], kind), pack16x2(info5[2 * plane + i], sinf(d), kind),
                        pack16x2(cosf(d), info5[4 * plane + i], kind), 0u);
   reinterpret_cast<uint4*>(out)[i] = p;
@@ -106,6 +117,12 @@ __global__ void concat2_cast_kernel(const float* __restrict__ a, const float* __
 __global__ void pos3_rows_kernel(const float* __restrict__ x, int n, void* __restrict__ out, int kind) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
+  if (kind == D3D_OUT_F32) {
+    float* o = (float*)out + (size_t)r * 8;
+    o[0] = x[(size_t)r * 3]; o[1] = x[(size_t)r * 3 + 1]; o[2] = x[(size_t)r * 3 + 2];
+    o[3] = o[4] = o[5] = o[6] = o[7] = 0.f;
+    return;
+  }
   uint4 p = make_uint4(pack16x2(x[(size_t)r * 3], x[(size_t)r * 3 + 1], kind), pack16x2(x[(size_t)r * 3 + 2], 0.f, kind), 0u, 0u);
   reinterpret_cast<uint4*>(out)[r] = p;
 }

@@ -83,7 +83,7 @@ class _Episode:
 
 
 class Feature_Fields(nn.Module):
-    def __init__(self, batch_size=1, device="cuda", dtype=torch.float16, q7_fix=False):
+    def __init__(self, batch_size=1, device="cuda", dtype=torch.float16, q7_fix=False, precise=False):
         super().__init__()
         if torch.cuda.is_available():
             L.require_device()  # compute entry points raise D3DLibraryError otherwise (no CPU fallback)
@@ -91,6 +91,7 @@ class Feature_Fields(nn.Module):
         self.args = _Args()
         self.compute_dtype = dtype
         self.q7_fix = q7_fix
+        self.precise = precise  # split-operand fp32-activation mode (dynam3d_b200/precise.py): parity evidence, not production
         width = D
         scale = width ** -0.5
         enc_layer = nn.TransformerEncoderLayer(d_model=width, nhead=width // 64, dim_feedforward=4 * width, dropout=0.1,
@@ -279,6 +280,25 @@ class Feature_Fields(nn.Module):
             "i2z_enc": enc(self.aggregate_instance_to_zone_encoder),
             "disc": mlp(self.instance_merge_discriminator, 1544),
         }
+        def mlp32(seq, kpad):
+            w0 = seq[0].weight.detach().to(torch.float32).cpu()
+            if w0.shape[1] < kpad:
+                w0 = torch.cat([w0, torch.zeros(w0.shape[0], kpad - w0.shape[1])], 1)
+            return {"w0": w0.to(dev).contiguous(), "b0": f32(seq[0].bias), "g": f32(seq[1].weight), "b": f32(seq[1].bias),
+                    "w3": f32(seq[3].weight), "b3": f32(seq[3].bias)}
+
+        def enc32(e):
+            return {"layers": [{"w_in": f32(l.self_attn.in_proj_weight), "b_in": f32(l.self_attn.in_proj_bias),
+                                "w_out": f32(l.self_attn.out_proj.weight), "b_out": f32(l.self_attn.out_proj.bias),
+                                "n1": (f32(l.norm1.weight), f32(l.norm1.bias)), "w1": f32(l.linear1.weight), "b1": f32(l.linear1.bias),
+                                "w2": f32(l.linear2.weight), "b2": f32(l.linear2.bias), "n2": (f32(l.norm2.weight), f32(l.norm2.bias))}
+                               for l in e.layers], "norm": (f32(e.norm.weight), f32(e.norm.bias)), "eps": float(e.norm.eps)}
+        if self.precise:
+            self._W["m32"] = ({"mlp": mlp32(self.patch_to_instance_position_embedding, 8), "agg": self._W["p2i_agg"],
+                               "enc": enc32(self.aggregate_patch_to_instance_encoder)},
+                              {"mlp": mlp32(self.instance_to_zone_position_embedding, 8), "agg": self._W["i2z_agg"],
+                               "enc": enc32(self.aggregate_instance_to_zone_encoder)})
+            self._W["disc32"] = mlp32(self.instance_merge_discriminator, 1544)
         kind = L.kind_of(dt)
 
         def c_mlp(m):
@@ -360,6 +380,24 @@ class Feature_Fields(nn.Module):
             out.append(t.view(a.shape) if a.ndim > 1 else t)
         return out
 
+    def _pool_tokens(self, level, ptrs_d, centre_dev, tok_seq_d, tok_src_d, cu_d, T, n_seq, max_len, mode, fts_is_f32):
+        """features -> MLP -> assemble -> encoder for one packed batch (device arrays); fp32 [n_seq, 768]."""
+        W = self._weights()
+        out = torch.empty((n_seq, D), device=self.device, dtype=torch.float32)
+        if not self.precise:
+            ws = self._workspace(int(L.lib().d3d_pool_workspace_bytes(T, D, D)))
+            L.check(L.lib().d3d_pool_tokens(ctypes.addressof(W["c_levels"][level]), L.ptr(ptrs_d), L.ptr(centre_dev), L.ptr(tok_seq_d), L.ptr(tok_src_d),
+                                            L.ptr(cu_d), T, n_seq, int(max_len), mode, int(fts_is_f32), L.ptr(ws), ws.numel(), L.ptr(out), L.stream_ptr()))
+            return out
+        from . import precise as PR
+        m = W["m32"][level]
+        A0 = torch.empty((T, 8), device=self.device, dtype=torch.float32)
+        ops.pool_features(ptrs_d[0], ptrs_d[1], ptrs_d[2], centre_dev, tok_seq_d, tok_src_d, T, mode, A0)
+        emb = PR.mlp_ln_gelu(A0, m["mlp"])
+        X = torch.empty((T, D), device=self.device, dtype=torch.float32)
+        ops.pool_assemble(emb, ptrs_d[3], fts_is_f32, tok_seq_d, tok_src_d, m["agg"], T, X)
+        return PR.encoder(X, cu_d, n_seq, int(max_len), m["enc"])
+
     def _pool_pass(self, tok_src, tok_seq, cu, ptrs, centre, n_seq, max_len, mode, level, fts_is_f32, extra=()):
         """One packed pooling pass (FF:580-597 / 662-688 / 717-756).  tok_src / tok_seq / cu: numpy int32 token arrays; ptrs: numpy int64
         [4, n_seq] (xyz, dir, scale, fts base address per sequence); centre: device fp32 [n_seq,3] or numpy (uploaded along).
@@ -370,11 +408,7 @@ class Feature_Fields(nn.Module):
         up = self._upload(arrs)
         k = 5 if isinstance(centre, np.ndarray) else 4
         centre_dev = up[4] if isinstance(centre, np.ndarray) else centre
-        out = torch.empty((n_seq, D), device=self.device, dtype=torch.float32)
-        ws = self._workspace(int(L.lib().d3d_pool_workspace_bytes(T, D, D)))
-        lv = W["c_levels"][level]
-        L.check(L.lib().d3d_pool_tokens(ctypes.addressof(lv), L.ptr(up[3]), L.ptr(centre_dev), L.ptr(up[1]), L.ptr(up[0]), L.ptr(up[2]), T, n_seq,
-                                        int(max_len), mode, int(fts_is_f32), L.ptr(ws), ws.numel(), L.ptr(out), L.stream_ptr()))
+        out = self._pool_tokens(level, up[3], centre_dev, up[1], up[0], up[2], T, n_seq, max_len, mode, fts_is_f32)
         return out, centre_dev, up[k:]
 
     def _workspace(self, nbytes):
@@ -530,11 +564,7 @@ class Feature_Fields(nn.Module):
         up = self._upload([tok_src[:T], tok_seq[:T], cu_tok[:n_seq + 1], ptrs] + extra)
         L.check(lib.d3d_copy_blocks(L.ptr(up[4]), L.ptr(up[5]), L.ptr(up[6]), len(src), L.stream_ptr()))
         centres = ops.seq_centroid(stage["xyz"], up[7], up[8], n_seq)  # fp64 accumulate, all episodes in one launch
-        W = self._weights()
-        view_fts = torch.empty((n_seq, D), device=dev, dtype=torch.float32)
-        ws = self._workspace(int(lib.d3d_pool_workspace_bytes(T, D, D)))
-        L.check(lib.d3d_pool_tokens(ctypes.addressof(W["c_levels"][0]), L.ptr(up[3]), L.ptr(centres), L.ptr(up[1]), L.ptr(up[0]), L.ptr(up[2]), T,
-                                    n_seq, max_len, 0, 0, L.ptr(ws), ws.numel(), L.ptr(view_fts), L.stream_ptr()))
+        view_fts = self._pool_tokens(0, up[3], centres, up[1], up[0], up[2], T, n_seq, max_len, 0, False)
         # ---- 3. K-NN proposals + merge discriminator (FF:604-621), all episodes in one launch each; 2 columns are always computed,
         #         the planner uses the first min(#live, 2) of them (further columns can only be tombstones or absent) ----
         res = torch.empty((n_seq, 12), device=dev, dtype=torch.float32)  # [centre(3) | d2(2) | idx(2, int bits) | logits(4) | pad]
@@ -542,10 +572,14 @@ class Feature_Fields(nn.Module):
             d2_d = torch.empty((n_seq, 2), device=dev, dtype=torch.float32)
             idx_d = torch.empty((n_seq, 2), device=dev, dtype=torch.int32)
             L.check(lib.d3d_knn2_batched(L.ptr(up[9]), L.ptr(up[11]), L.ptr(centres), n_seq, L.ptr(d2_d), L.ptr(idx_d), L.stream_ptr()))
-            A = torch.empty((2 * n_seq, 1544), device=dev, dtype=self.compute_dtype)
+            A = torch.empty((2 * n_seq, 1544), device=dev, dtype=torch.float32 if self.precise else self.compute_dtype)
             L.check(lib.d3d_disc_input_batched(L.ptr(up[10]), L.ptr(up[9]), L.ptr(idx_d), L.ptr(view_fts), L.ptr(centres), n_seq, 2, D, 1544,
                                                L.ptr(A), L.kind_of(A.dtype), L.stream_ptr()))
-            res[:, 7:11] = self._disc_logits(A).reshape(n_seq, 4)
+            if self.precise:
+                from . import precise as PR
+                res[:, 7:11] = PR.mlp_ln_gelu(A, self._weights()["disc32"]).reshape(n_seq, 4)
+            else:
+                res[:, 7:11] = self._disc_logits(A).reshape(n_seq, 4)
             res[:, 3:5] = d2_d
             res[:, 5:7] = idx_d.view(torch.float32)
         res[:, 0:3] = centres

@@ -33,9 +33,10 @@ def _mlp_container(d_in, d_hidden, d_out):
 class CLIPEncoder(nn.Module):
     """Drop-in for ENC:245-284: forward({'rgb': uint8 [N,H,W,3]}) -> (view_fts [N,768], grid_fts [N,576,768]) fp16."""
 
-    def __init__(self, model_name="ViT-L/14@336px", device="cuda", max_images=12):
+    def __init__(self, model_name="ViT-L/14@336px", device="cuda", max_images=12, precise=False):
         super().__init__()
         self.device = device
+        self.precise = precise
         self.engine = None
         self.max_images = max_images
         self.is_blind = False
@@ -49,16 +50,21 @@ class CLIPEncoder(nn.Module):
         rgb = observations["rgb"]
         if not rgb.is_cuda:
             rgb = rgb.to(self.device, non_blocking=True)
+        if self.precise:
+            from . import precise as PR
+            cls, grid = PR.vit_forward(self.engine, rgb.contiguous(), ln_post_on_patches=ln_post_on_patches)
+            return cls.to(torch.float16), grid.to(torch.float16)  # the reference stores grid features as fp16 (FF:500)
         return self.engine.forward(rgb.contiguous(), ln_post_on_patches=ln_post_on_patches)
 
 
 class _Llava:
     """Engine-side stand-in for LlavaForConditionalGeneration (POL:123-127): vision tower + projector + language model."""
 
-    def __init__(self):
+    def __init__(self, precise=False):
         self.tower = None
         self.lm = None
         self.proj = None
+        self.precise = precise
 
     def load_state_dict(self, sd, device="cuda", lm_dtype=torch.float16, max_images=1, max_tokens=2048):
         """Accepts HF llava keys: [model.]vision_tower.vision_model.*, [model.]multi_modal_projector.linear_{1,2}.*,
@@ -81,6 +87,12 @@ class _Llava:
 
     def image_features(self, rgb_u8):
         """get_image_features (POL:448-452): hidden_states[-2] of the tower without CLS -> linear_1 -> GELU -> linear_2; fp32 [N*576, 3072]."""
+        if self.precise:
+            from . import precise as PR
+            hid = PR.vit_forward(self.tower, rgb_u8, n_layers_run=len(self.tower.w.layers) - 1, project=False)
+            x = hid[:, 1:].reshape(hid.shape[0] * 576, hid.shape[2]).contiguous()
+            h = PR.linear(x, self.proj["w1"], self.proj["b1"], act=L.ACT_GELU)
+            return PR.linear(h, self.proj["w2"], self.proj["b2"])
         hid = self.tower.forward(rgb_u8, n_layers_run=len(self.tower.w.layers) - 1, project=False)  # [N, 577, 1024] fp32
         N = hid.shape[0]
         a16 = torch.empty((N * 576, hid.shape[2]), device=hid.device, dtype=torch.float16)
@@ -92,11 +104,12 @@ class _Llava:
 class Dynam3D_VLN(nn.Module):
     IMAGE_TOKEN = "<image>"
 
-    def __init__(self, observation_space=None, model_config=None, num_actions=None, device="cuda", q1_fix=False, q7_fix=False):
+    def __init__(self, observation_space=None, model_config=None, num_actions=None, device="cuda", q1_fix=False, q7_fix=False, precise=False):
         super().__init__()
         self.device = torch.device(device)
         self.q1_fix = q1_fix
-        self.feature_fields = Feature_Fields(batch_size=1, device=self.device, q7_fix=q7_fix)
+        self.precise = precise  # split-operand fp32-activation mode (precise.py): parity evidence only
+        self.feature_fields = Feature_Fields(batch_size=1, device=self.device, q7_fix=q7_fix, precise=precise)
         width = 768
         self.patch_position_embedding = _mlp_container(6, width * 4, width * 4)
         self.instance_position_embedding = _mlp_container(3, width, width)
@@ -105,12 +118,13 @@ class Dynam3D_VLN(nn.Module):
         self.zone_projector = _mlp_container(width * 2, width * 4, width * 4)
         for p in self.parameters():
             p.requires_grad_(False)
-        self.rgb_encoder = CLIPEncoder("ViT-L/14@336px", self.device)
+        self.rgb_encoder = CLIPEncoder("ViT-L/14@336px", self.device, precise=precise)
         self.depth_encoder = None  # SURVEY.md 8(f) rank 3 (waypoint branch), not part of this step
-        self.llava = _Llava()
+        self.llava = _Llava(precise=precise)
         self.tokenize = None      # callable(str) -> list[int]; the real one is the llava-phi-3 tokenizer (POL:131)
         self.detokenize = None    # callable(list[int]) -> str
         self._PW = None
+        self._side = None
 
     # -- properties the habitat `Net` interface expects (POL:159-169)
     @property
@@ -148,6 +162,14 @@ class Dynam3D_VLN(nn.Module):
                     w0 = torch.cat([w0, torch.zeros(w0.shape[0], kpad - w0.shape[1])], 1)
                 return {"w0": w0.to(dev).half().contiguous(), "b0": f32(seq[0].bias), "g": f32(seq[1].weight), "b": f32(seq[1].bias),
                         "w3": seq[3].weight.detach().float().to(dev).half().contiguous(), "b3": f32(seq[3].bias)}
+            def mlp32(seq, kpad=None):
+                w0 = seq[0].weight.detach().float().cpu()
+                if kpad is not None and w0.shape[1] < kpad:
+                    w0 = torch.cat([w0, torch.zeros(w0.shape[0], kpad - w0.shape[1])], 1)
+                return {"w0": w0.to(dev).contiguous(), "b0": f32(seq[0].bias), "g": f32(seq[1].weight), "b": f32(seq[1].bias),
+                        "w3": f32(seq[3].weight), "b3": f32(seq[3].bias)}
+            if self.precise:
+                mlp = mlp32
             self._PW = {"patch_pos": mlp(self.patch_position_embedding, 8), "inst_pos": mlp(self.instance_position_embedding, 8),
                         "zone_pos": mlp(self.zone_position_embedding, 8), "inst_proj": mlp(self.instance_projector),
                         "zone_proj": mlp(self.zone_projector)}
@@ -215,6 +237,9 @@ class Dynam3D_VLN(nn.Module):
 
     # ------------------------------------------------------------------ building blocks of forward
     def _mlp(self, A0, m):
+        if self.precise:
+            from . import precise as PR
+            return PR.mlp_ln_gelu(A0, m)
         h = ops.gemm(A0, m["w0"], bias=m["b0"], out_dtype=torch.float32)
         a16 = torch.empty(h.shape, device=h.device, dtype=torch.float16)
         ops.layernorm(h, m["g"], m["b"], 1e-5, out16=a16, act=L.ACT_GELU)
@@ -225,10 +250,11 @@ class Dynam3D_VLN(nn.Module):
         n = fts.shape[0]
         if n == 0:
             return torch.zeros((0, 3072), device=self.device, dtype=torch.float32)
-        a = torch.empty((n, 8), device=self.device, dtype=torch.float16)
+        op_dt = torch.float32 if self.precise else torch.float16
+        a = torch.empty((n, 8), device=self.device, dtype=op_dt)
         ops.pos3_rows(rel.contiguous(), a)
         pe = self._mlp(a, pos_mlp)
-        cat = torch.empty((n, 1536), device=self.device, dtype=torch.float16)
+        cat = torch.empty((n, 1536), device=self.device, dtype=op_dt)
         ops.concat2_cast(fts.contiguous(), pe, cat)
         return self._mlp(cat, proj_mlp)
 
@@ -253,18 +279,27 @@ class Dynam3D_VLN(nn.Module):
             full = ops.depth_preprocess(depth, depth_scale[0], depth_scale[1]).view(B, V, H, W)  # POL:350
             ff.delete_old_features_from_camera_frustum(full, agent_positions, agent_heading_angles, num_of_views=V)
         segm = observations.get("patch_segm") if hasattr(observations, "get") else None
+        # The LLaVA tower + projector of the view the LLM sees (Q13: view 0 of every episode) does not depend on the 3D memory:
+        # run it on a side stream so it fills the GPU idle gaps of the (host-synchronised) memory update below.
+        sel = torch.arange(B, device=dev) * V
+        info5 = ops.patch_3d_info(d576, ff.args.input_hfov, ff.args.input_vfov, ff.args.input_width, ff.args.input_height)
+        PW = self._policy_weights()
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side), L.stream_scope():
+            rows = torch.empty((B * P, 8), device=dev, dtype=torch.float32 if self.precise else torch.float16)
+            ops.patch_info_rows(info5[:, sel].contiguous(), rows)
+            patch_pos = self._mlp(rows, PW["patch_pos"])  # POL:432-433
+            patch = self.llava.image_features(rgb[sel].contiguous())  # POL:448-452
+            ops.add_inplace(patch, patch_pos)  # POL:453
         ff.update_feature_fields(d576.view(B, V, P), grid.reshape(B, V, P, 768), batch_image=rgb, batch_position=agent_positions,
                                  batch_heading=agent_heading_angles, num_of_views=V, batch_patch_segm=segm)
         env = ff.get_environment_features(agent_positions, agent_heading_angles)
-        info5 = ops.patch_3d_info(d576, ff.args.input_hfov, ff.args.input_vfov, ff.args.input_width, ff.args.input_height)
-        PW = self._policy_weights()
-        # patch tokens of the view the LLM sees (Q13: view 0 of every episode)
-        sel = torch.arange(B, device=dev) * V
-        rows = torch.empty((B * P, 8), device=dev, dtype=torch.float16)
-        ops.patch_info_rows(info5[:, sel].contiguous(), rows)
-        patch_pos = self._mlp(rows, PW["patch_pos"])  # POL:432-433
-        patch = self.llava.image_features(rgb[sel].contiguous())  # POL:448-452
-        ops.add_inplace(patch, patch_pos)  # POL:453
+        main.wait_stream(self._side)
+        for t in (rows, patch_pos, patch):
+            t.record_stream(main)
         inst = [self._project_tokens(env["batch_instance_fts"][b], env["batch_instance_relative_position"][b], PW["inst_pos"], PW["inst_proj"])
                 for b in range(B)]
         zone = [self._project_tokens(env["batch_zone_fts"][b], env["batch_zone_relative_position"][b], PW["zone_pos"], PW["zone_proj"])
@@ -306,6 +341,9 @@ class Dynam3D_VLN(nn.Module):
         pos = torch.cat([torch.arange(n, dtype=torch.int32) for n in lens]).to(self.device)
         last = (cu[1:] - 1).to(torch.int32).contiguous()
         self.last_seq_lens = lens
+        if self.precise:
+            from . import precise as PR
+            return PR.lm_prefill(lm, X, cu, pos, B, max(lens), last)
         return lm.prefill(X, cu, pos, B, max(lens), last)
 
     def forward(self, observations, instructions, agent_positions, agent_heading_angles, depth_scale=(0.0, 10.0), gt_text=None,

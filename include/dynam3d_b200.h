@@ -288,6 +288,17 @@ int d3d_ffh_get_patch_pos(void* h, int b, float* out);
 int d3d_ffh_get_zone_keys(void* h, int b, float* keys, int64_t* ids, int64_t* n);
 int d3d_ffh_get_last(void* h, int b, float* d2, int* idx, uint8_t* merge, int64_t* n);
 
+/* ------------------------------------------------------------------------------------------------
+ * "Precise" pipeline (parity evidence against the reference's fp32 CPU path; not the production mode): activations stay
+ * fp32 between kernels (every producer above accepts kind = D3D_OUT_F32) and each tensor-core GEMM runs on split operands:
+ * d3d_split16 writes [hi | lo (| hi)] along K (hi = fp16(x), lo = fp16(x - hi)), the weight is stored as [W_hi | W_hi (| W_lo)],
+ * so the unchanged tcgen05 GEMM computes A_hi W_hi + A_lo W_hi (+ A_hi W_lo) with fp32 accumulation (~2^-22 operand precision).
+ * ------------------------------------------------------------------------------------------------ */
+int d3d_split16(const float* in, int64_t ldi, void* out16, int64_t ldo, int T, int K, int terms, void* stream);
+/* fp32-in / fp32-out variant of d3d_attention_simt (no 16-bit rounding of q, k, v or the output). */
+int d3d_attention_f32(const float* qkv, int64_t ld, float* out, int64_t ldo, const int* cu_seqlens, int n_seq, int max_len, int H,
+                      int Dh, int causal, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

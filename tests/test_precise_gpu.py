@@ -1,0 +1,80 @@
+"""The "precise" pipeline (split fp16x2 tensor-core operands, fp32 activations; dynam3d_b200/precise.py) against the oracle's
+PURE fp32 path (rnd=None) -- the arithmetic of the reference on CPU.  This is the north star's logit tolerance: 1e-3."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_vit_l14_precise_vs_fp32_oracle():
+    from dynam3d_b200 import precise as PR, synth
+    from dynam3d_b200.clip_vit import ViTEngine, ViTWeights
+    from oracle import nn_ops as NN
+    layers = 6
+    sd = synth.vit_state_dict(4, layers=layers)
+    img = np.random.default_rng(4).integers(0, 256, size=(1, 224, 224, 3), dtype=np.uint8)
+    eng = ViTEngine(ViTWeights.from_openai_state_dict(sd), n_head=16, resolution=336, max_images=1)
+    cls, patch = PR.vit_forward(eng, torch.from_numpy(img).cuda())
+    want_cls, want_patch = NN.vit_forward(NN.clip_preprocess(img, 336), sd, layers, 16, rnd=None)
+    e = (patch.cpu() - want_patch).abs().max().item()
+    print(f"precise ViT ({layers} layers): max abs err vs fp32 oracle {e:.2e} (|x| max {want_patch.abs().max().item():.2f})")
+    # the bicubic resize rounds to uint8 like torchvision: a pixel on a .5 boundary may flip by 1/255 -> allow 1e-3
+    assert e <= 1e-3 and (cls.cpu() - want_cls).abs().max().item() <= 1e-3
+
+
+def test_lm_phi3_width_precise_vs_fp32_oracle():
+    from dynam3d_b200 import precise as PR, synth
+    from dynam3d_b200.phi3 import LMEngine, LMWeights
+    from oracle import nn_ops as NN
+    hidden, layers, heads, ffn, vocab, lens = 3072, 4, 32, 8192, 32064, [600]
+    sd = synth.lm_state_dict(5, hidden, layers, ffn, vocab, round_to=torch.float16)
+    emb = synth.hash_uniform((sum(lens), hidden), 105, 1.0)
+    eng = LMEngine(LMWeights.from_state_dict(sd, dtype=torch.float16), n_heads=heads, max_tokens=sum(lens))
+    cu = torch.tensor([0, 600], dtype=torch.int32, device="cuda")
+    pos = torch.arange(600, dtype=torch.int32, device="cuda")
+    logits = PR.lm_prefill(eng, emb.cuda().clone(), cu, pos, 1, 600, torch.tensor([599], dtype=torch.int32, device="cuda")).cpu()
+    want = NN.lm_prefill(emb, lens, sd, layers, heads, rnd=None)
+    e = (logits - want).abs().max().item()
+    print(f"precise LM (4 layers, Phi-3 widths): max abs logit err vs fp32 oracle {e:.2e} (|logit| max {want.abs().max().item():.2f})")
+    assert e <= 1e-3
+
+
+def test_full_step_precise_logits_within_1e_3():
+    """North-star config 3 shape (reduced depth so the CPU oracle stays in seconds): one full navigation step, logits <= 1e-3."""
+    from dynam3d_b200 import precise as PR, synth
+    from dynam3d_b200.policy import Dynam3D_VLN
+    from oracle.policy_oracle import PolicyOracle
+    from oracle.ref_compare import snapshots_equal
+    seed, V, B = 2, 2, 1
+    pol_sd = synth.policy_state_dict(seed)
+    clip_sd = synth.vit_state_dict(seed, layers=2)
+    llava_sd = synth.llava_state_dict(seed, clip_layers=2, lm_layers=2, lm_round_to=torch.float16)
+    net = Dynam3D_VLN(q1_fix=True, precise=True)
+    net.load_policy_state_dict(pol_sd)
+    net.rgb_encoder.load_openai_state_dict(clip_sd)
+    net.llava.load_state_dict(llava_sd, max_images=B)
+    net.feature_fields.reset(B)
+    orc = PolicyOracle(pol_sd, clip_sd, llava_sd, clip_layers=2, lm_layers=2, batch_size=B, rnd=None, q1_fix=True)
+    tok = synth.ToyTokenizer()
+    ep = synth.make_episode(seed * 10, n_steps=2, num_views=V, rgb_size=224, n_seg=16, seg_kind="voronoi")
+    for t in range(2):
+        obs = {"rgb": ep[t]["rgb"], "depth": ep[t]["depth"], "patch_segm": ep[t]["segm"][None]}
+        t_obs = {"rgb": torch.from_numpy(obs["rgb"]), "depth": torch.from_numpy(obs["depth"]), "patch_segm": obs["patch_segm"]}
+        pos, head = [ep[t]["position"]], [ep[t]["heading"]]
+        patch, inst, zone = net.encode_step(t_obs, pos, head, num_of_views=V)
+        n_img = 576 + inst[0].shape[0] + zone[0].shape[0]
+        ids = [tok(net.build_prompt(n_img, synth.make_instruction(seed), ["none\n"] * 4))]
+        want = orc.step_logits(obs, pos, head, ids, num_of_views=V)
+        assert snapshots_equal(orc.ff.snapshot(0), net.feature_fields.snapshot(0)) == []
+        lm = net.llava.lm
+        idt = torch.tensor(ids[0], dtype=torch.int32, device="cuda")
+        eh = torch.empty((2, 3072), device="cuda"); et = torch.empty((len(ids[0]) - n_img - 2, 3072), device="cuda")
+        lm.embed(idt[:2].contiguous(), eh); lm.embed(idt[n_img + 2:].contiguous(), et)
+        X = torch.cat([eh, patch[0], inst[0], zone[0], et], 0)
+        S = X.shape[0]
+        got = PR.lm_prefill(lm, X, torch.tensor([0, S], dtype=torch.int32, device="cuda"), torch.arange(S, dtype=torch.int32, device="cuda"), 1, S,
+                            torch.tensor([S - 1], dtype=torch.int32, device="cuda")).cpu()
+        e = (got - want).abs().max().item()
+        print(f"precise full step {t}: S={S} max abs logit err vs fp32 oracle {e:.2e}")
+        assert e <= 1e-3 and torch.equal(got.argmax(-1), want.argmax(-1))
