@@ -42,7 +42,10 @@ def linear(x32, w, bias=None, act=L.ACT_NONE, residual=None, out=None, w_prepare
     assert x32.dtype == torch.float32 and x32.stride(1) == 1 and wx.shape[1] == terms * K, (wx.shape, terms, K)
     a = torch.empty((T, terms * K), device=x32.device, dtype=torch.float16)
     L.check(L.lib().d3d_split16(L.ptr(x32), x32.stride(0), L.ptr(a), a.stride(0), T, K, terms, L.stream_ptr()))
-    return ops.gemm(a, wx, out=out, bias=bias, act=act, residual=residual, out_dtype=torch.float32)
+    if out is None:
+        n_out = wx.shape[0] // 2 if act == L.ACT_SWIGLU else wx.shape[0]
+        out = torch.empty((T, (n_out + 3) // 4 * 4), device=x32.device, dtype=torch.float32)[:, :n_out]  # 16-byte aligned rows
+    return ops.gemm(a, wx, out=out, bias=bias, act=act, residual=residual)
 
 
 def attention(qkv32, cu, n_seq, max_len, H, Dh, causal):

@@ -7,19 +7,21 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def test_vit_l14_precise_vs_fp32_oracle():
+def test_vit_l14_precise_vs_fp32_oracle(size=336):
+    """336^2 inputs (the simulator's native RGB sensor, r2r_vlnce.yaml:13-21): the bicubic resize of other sizes rounds to uint8 and a
+    pixel within ~1e-5 of a .5 boundary may land on the other side than torch's kernel (measured: 2.3e-3 on the features from a handful
+    of 1/255 flips); the resize itself is covered by tests/test_nn_kernels_gpu.py::test_preprocess_im2col."""
     from dynam3d_b200 import precise as PR, synth
     from dynam3d_b200.clip_vit import ViTEngine, ViTWeights
     from oracle import nn_ops as NN
     layers = 6
     sd = synth.vit_state_dict(4, layers=layers)
-    img = np.random.default_rng(4).integers(0, 256, size=(1, 224, 224, 3), dtype=np.uint8)
+    img = np.random.default_rng(4).integers(0, 256, size=(1, size, size, 3), dtype=np.uint8)
     eng = ViTEngine(ViTWeights.from_openai_state_dict(sd), n_head=16, resolution=336, max_images=1)
     cls, patch = PR.vit_forward(eng, torch.from_numpy(img).cuda())
     want_cls, want_patch = NN.vit_forward(NN.clip_preprocess(img, 336), sd, layers, 16, rnd=None)
     e = (patch.cpu() - want_patch).abs().max().item()
-    print(f"precise ViT ({layers} layers): max abs err vs fp32 oracle {e:.2e} (|x| max {want_patch.abs().max().item():.2f})")
-    # the bicubic resize rounds to uint8 like torchvision: a pixel on a .5 boundary may flip by 1/255 -> allow 1e-3
+    print(f"precise ViT ({layers} layers, input {size}): max abs err vs fp32 oracle {e:.2e} (|x| max {want_patch.abs().max().item():.2f})")
     assert e <= 1e-3 and (cls.cpu() - want_cls).abs().max().item() <= 1e-3
 
 
@@ -57,7 +59,7 @@ def test_full_step_precise_logits_within_1e_3():
     net.feature_fields.reset(B)
     orc = PolicyOracle(pol_sd, clip_sd, llava_sd, clip_layers=2, lm_layers=2, batch_size=B, rnd=None, q1_fix=True)
     tok = synth.ToyTokenizer()
-    ep = synth.make_episode(seed * 10, n_steps=2, num_views=V, rgb_size=224, n_seg=16, seg_kind="voronoi")
+    ep = synth.make_episode(seed * 10, n_steps=2, num_views=V, rgb_size=336, n_seg=16, seg_kind="voronoi")
     for t in range(2):
         obs = {"rgb": ep[t]["rgb"], "depth": ep[t]["depth"], "patch_segm": ep[t]["segm"][None]}
         t_obs = {"rgb": torch.from_numpy(obs["rgb"]), "depth": torch.from_numpy(obs["depth"]), "patch_segm": obs["patch_segm"]}
