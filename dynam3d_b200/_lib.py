@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdynam3d_b200.so")
 
 D3D_F16, D3D_BF16, D3D_OUT_F32 = 0, 1, 2
-ACT_NONE, ACT_QUICK_GELU, ACT_GELU, ACT_SILU, ACT_SWIGLU = 0, 1, 2, 3, 4
+ACT_NONE, ACT_QUICK_GELU, ACT_GELU, ACT_SILU, ACT_SWIGLU, ACT_LEAKY_RELU = 0, 1, 2, 3, 4, 5
 
 
 class D3DLibraryError(RuntimeError):
@@ -99,6 +99,12 @@ SIGNATURES = {
     "d3d_ffh_get_zone_keys": [_P, _I, _P, _P, _P], "d3d_ffh_get_last": [_P, _I, _P, _P, _P, _P],
     "d3d_split16": [_P, _L, _P, _L, _I, _I, _I, _P],
     "d3d_attention_f32": [_P, _L, _P, _L, _P, _I, _I, _I, _I, _I, _F, _P],
+    "d3d_ray_points_habitat": [_P, _P, _P, _I, _I] + [ctypes.c_double] * 5 + [_P, _P],
+    "d3d_ray_topk": [_P, _P, _I, _I, _I, _F, _I, _P, _P],
+    "d3d_gather_samples": [_P, _P, _I, _I, _I, _P, _P],
+    "d3d_nerf_gather": [_P] * 8 + [_I, _I, _I, _I, _F, _F, _F, _F, _F, _P, _I, _P, _P],
+    "d3d_add_half": [_P, _P, _P, _L, _P],
+    "d3d_volume_render": [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P],
 }
 OPTIONAL = set()
 

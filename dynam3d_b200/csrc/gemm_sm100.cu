@@ -127,6 +127,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     case D3D_ACT_QUICK_GELU: return quick_gelu(v);
     case D3D_ACT_GELU: return gelu_erf(v);
     case D3D_ACT_SILU: return silu(v);
+    case D3D_ACT_LEAKY_RELU: return v > 0.f ? v : 0.01f * v;
     default: return v;
   }
 }
@@ -301,6 +302,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             } else if (ep.act == D3D_ACT_SILU) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = __fdividef(v[i], 1.0f + __expf(-v[i]));
+            } else if (ep.act == D3D_ACT_LEAKY_RELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : 0.01f * v[i];
             }
             if (ep.residual) {
               const float* res = ep.residual + (long long)row * ep.ldres + col0;

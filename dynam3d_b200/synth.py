@@ -292,3 +292,24 @@ def make_instruction(seed, n_chars=64):
     while len(s) < n_chars:
         s += words[int(rng.integers(len(words)))] + " "
     return s[:n_chars]
+
+
+def nerf_state_dict(seed, width=768, K=4, layers=4):
+    """Reference-named parameters of the Pretrain renderer (PFF:221-254): two Linear+LayerNorm blocks and the flat tinycudann vectors."""
+    import torch
+    s = seed * 3000
+    pad = lambda n: (n + 15) // 16 * 16
+    n_enc = width * width * (layers // 2) + pad(width + 1) * width
+    n_dec = width * width * (layers - layers // 2) + pad(width) * width
+    return {
+        "patch_to_nerf_position_embedding.0.weight": hash_uniform((width, 6), s + 1, 6 ** -0.5),
+        "patch_to_nerf_position_embedding.0.bias": hash_uniform((width,), s + 2, 0.05),
+        "patch_to_nerf_position_embedding.1.weight": 1.0 + hash_uniform((width,), s + 3, 0.05),
+        "patch_to_nerf_position_embedding.1.bias": hash_uniform((width,), s + 4, 0.05),
+        "aggregate_patch_to_nerf_encoder.0.weight": hash_uniform((width, width * K), s + 5, (width * K) ** -0.5),
+        "aggregate_patch_to_nerf_encoder.0.bias": hash_uniform((width,), s + 6, 0.05),
+        "aggregate_patch_to_nerf_encoder.1.weight": 1.0 + hash_uniform((width,), s + 7, 0.05),
+        "aggregate_patch_to_nerf_encoder.1.bias": hash_uniform((width,), s + 8, 0.05),
+        "nerf_encoder.params": hash_uniform((n_enc,), s + 9, (3.0 / width) ** 0.5).to(torch.float16).to(torch.float32),
+        "nerf_decoder.params": hash_uniform((n_dec,), s + 10, (3.0 / width) ** 0.5).to(torch.float16).to(torch.float32),
+    }

@@ -42,6 +42,7 @@ extern "C" {
 #define D3D_ACT_GELU 2       /* exact erf GELU, nn.GELU() */
 #define D3D_ACT_SILU 3
 #define D3D_ACT_SWIGLU 4     /* out[:, j] = silu(acc[:, 2j]) * acc[:, 2j+1] on row-interleaved gate/up weights */
+#define D3D_ACT_LEAKY_RELU 5 /* slope 0.01: tinycudann CutlassMLP "LeakyReLU" (PFF:221-243) */
 
 const char* d3d_last_error(void);
 int d3d_version(void);
@@ -298,6 +299,29 @@ int d3d_split16(const float* in, int64_t ldi, void* out16, int64_t ldo, int T, i
 /* fp32-in / fp32-out variant of d3d_attention_simt (no 16-bit rounding of q, k, v or the output). */
 int d3d_attention_f32(const float* qkv, int64_t ld, float* out, int64_t ldo, const int* cu_seqlens, int n_seq, int max_len, int H,
                       int Dh, int causal, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Pretrain novel-view patch renderer, render_view_3d_patch (PFF:494-625), habitat mode.  The two torch_kdtree queries are
+ * d3d_knn3d (K = 4); the tinycudann CutlassMLPs run on d3d_gemm (bias-free, D3D_ACT_LEAKY_RELU).
+ * ------------------------------------------------------------------------------------------------ */
+/* ray sample points (PFF:408-422, 523-528), evaluated in fp64 like the numpy code and rounded once: rel_y [n_samples] fp64,
+ * tan_x / tan_z [n_rays] fp32 per-ray tangents -> out_xyz [n_rays*n_samples, 3] fp32. */
+int d3d_ray_points_habitat(const double* rel_y, const float* tan_x, const float* tan_z, int n_rays, int n_samples, double cos_h,
+                           double sin_h, double cam_x, double cam_y, double cam_z, float* out_xyz, void* stream);
+/* PFF:542-552: sqrt, radius cut-off (idx <- -1 in place), density proxy 1/sum(dist), top-n_top samples per ray (ties: lowest index). */
+int d3d_ray_topk(const float* d2, int* idx, int n_rays, int n_samples, int K, float radius, int n_top, int* topk, void* stream);
+int d3d_gather_samples(const float* ray_xyz, const int* topk, int n_rays, int n_samples, int n_top, float* out, void* stream);
+/* PFF:586-615: neighbour gather of the selected samples into GEMM operands: pos_rows [n_points*K, 8] (kind pos_kind) and
+ * feat_rows16 [n_points*K, D] fp16; idx is updated in place with the radius cut-off. */
+int d3d_nerf_gather(const float* d2, int* idx, const float* sample_xyz, const float* patch_xyz, const float* patch_dir,
+                    const float* patch_scale, const void* patch_fts16, const float* ray_dir, int n_points, int n_top, int K, int D,
+                    float radius, float far_, float cam_dir, float cos_neg, float sin_neg, void* pos_rows, int pos_kind,
+                    void* feat_rows16, void* stream);
+/* out16 = fp16(fp16(a32) + b16) (PFF:478-482). */
+int d3d_add_half(const float* a32, const void* b16, void* out16, int64_t n, void* stream);
+/* raw2feature (PFF:446-474): feat [n_rays*n_top, D] fp32, density [n_rays*n_top] -> feature_map [n_rays, D] (L2-normalised), depth_map [n_rays]. */
+int d3d_volume_render(const float* feat, const float* density, const int* topk, const float* rel_dist, int n_rays, int n_samples,
+                      int n_top, int D, float* feature_map, float* depth_map, void* stream);
 
 #ifdef __cplusplus
 }
