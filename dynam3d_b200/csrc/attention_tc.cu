@@ -2,12 +2,15 @@
 //
 //   S = Q K^T      : tcgen05.mma kind::f16, M=128 (queries) x N=128 (keys) x K=64, Q and K tiles TMA-loaded (SWIZZLE_128B,
 //                    K-major) straight out of the packed [T, 3*H*64] QKV matrix, accumulator in TMEM (128 columns)
-//   softmax        : 4 warps, one query row per thread (TMEM lane == row): tcgen05.ld of S, running max / sum in registers,
-//                    P written to shared memory in the UMMA K-major SWIZZLE_128B layout
+//   softmax        : 8 warps, two threads per query row (TMEM lane == row; each owns 64 of the tile's 128 keys): tcgen05.ld of S,
+//                    running max / sum in registers (row max exchanged through smem), ex2.approx, P written to shared memory in
+//                    the UMMA K-major SWIZZLE_128B layout
 //   O_j = P V      : tcgen05.mma M=128 x N=64 x K=128 with V as an MN-major B operand (V rows are keys, d contiguous),
 //                    accumulator in TMEM (64 columns); the softmax warps fold O_j into their fp32 row with the running rescale
 // One CTA = 128 queries of one (sequence, head); K/V double-buffered; 2 CTAs per SM (112 KB smem, 256 TMEM columns each) so one
 // CTA's softmax overlaps the other's MMAs.  Replaces nn.MultiheadAttention's attention in CLIPM:181-183 and the LLaVA tower.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace {
@@ -15,14 +18,17 @@ namespace {
 constexpr int D = 64;
 constexpr int BQ = 128;
 constexpr int BKV = 128;
-constexpr int NTHREADS = 256;
+constexpr int NTHREADS = 320;  // warp 0: TMEM alloc + TMA; warp 1: MMA issue; warps 2-9: softmax (2 per TMEM lane quadrant); 96 regs at 2 CTAs/SM
+constexpr int NSOFT = 8;
 constexpr int TILE_BYTES = 128 * 64 * 2;                 // one [128 x 64] 16-bit tile = 16 KB
 constexpr int SMEM_Q = 0;
 constexpr int SMEM_K = TILE_BYTES;                       // 2 stages
 constexpr int SMEM_V = 3 * TILE_BYTES;                   // 2 stages
 constexpr int SMEM_P = 5 * TILE_BYTES;                   // [128 x 128] = 2 atoms of [128 x 64]
 constexpr int SMEM_BAR = 7 * TILE_BYTES;
-constexpr int SMEM_BYTES = SMEM_BAR + 128;               // + barriers; 2 CTAs/SM: 2 x (114816 + 1024 reserved) <= 228 KB
+constexpr int SMEM_XMAX = SMEM_BAR + 128;                // [2][128] bf16 row-max exchange between the two column halves
+constexpr int SMEM_BYTES = SMEM_XMAX + 512;              // 115328; 2 CTAs/SM: 2 x (115328 + 1024 reserved) <= 233472 (228 KB)
+static_assert(2 * (SMEM_BYTES + 1024) <= 233472, "two CTAs per SM");
 constexpr int TMEM_COLS = 256;                           // S: [0,128)  O: [128,192)
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
@@ -41,6 +47,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "DONE:\n\t"
       "}" ::"r"(bar),
       "r"(parity)
+      : "memory");
+}
+// same wait with a suspend-time hint: the polling warps (8 softmax warps per CTA) give their issue slots to the other CTA
+__device__ __forceinline__ void mbar_wait_sleepy(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP_S:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+      "@P1 bra DONE_S;\n\t"
+      "bra WAIT_LOOP_S;\n\t"
+      "DONE_S:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity), "r"(0x989680)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -75,6 +95,51 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+#ifdef D3D_ATTN_STAMPS
+// debug build only (make EXTRA=-DD3D_ATTN_STAMPS): per-phase clock64 stamps of one CTA, read back by tools/attn_stamps.py
+__device__ long long g_stamps[256];
+#define STAMP(cond, slot) do { if (cond) g_stamps[(slot)] = clock64(); } while (0)
+#else
+#define STAMP(cond, slot) do { } while (0)
+#endif
+
+// packed fp32x2 arithmetic (sm_100 FFMA2 / FADD2): halves the issue slots of the softmax inner loops
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15};" ::"r"(r[0]),
+      "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]),
+      "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major SWIZZLE_128B operand descriptor (8-row groups 1024 B apart) -- same as the GEMM's
@@ -99,7 +164,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, uint16_t* __restrict_
   const uint32_t sbase = smem_u32(smem_raw);
   if (sbase & 1023u) __trap();  // SWIZZLE_128B tiles need 1024-byte alignment
   const uint32_t bar0 = sbase + SMEM_BAR;
-  // barriers: 0 q_full | 1,2 kv_full | 3,4 kv_empty | 5 s_full | 6 s_free | 7 p_ready | 8 o_full | 9 o_free ; tmem ptr at +96
+  // barriers: 0 q_full | 1,2 kv_full | 3,4 kv_empty | 5 s_full | 6 s_free | 7 p_ready (and O rescaled) | 8 o_full ; tmem ptr at +96
   auto bar = [&](int i) { return bar0 + 8u * i; };
   const uint32_t tmem_ptr_addr = bar0 + 96;
 
@@ -112,19 +177,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, uint16_t* __restrict_
   const int kmax = causal ? min(len, q0 + BQ) : len;
   const int n_tiles = (kmax + BKV - 1) / BKV;
 
-  if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_qkv) : "memory");
   if (warp == 1 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_qkv) : "memory");
     mbar_init(bar(0), 1);
     mbar_init(bar(1), 1); mbar_init(bar(2), 1);
     mbar_init(bar(3), 1); mbar_init(bar(4), 1);
     mbar_init(bar(5), 1);
-    mbar_init(bar(6), 4);
-    mbar_init(bar(7), 4);
+    mbar_init(bar(6), NSOFT);
+    mbar_init(bar(7), NSOFT);
     mbar_init(bar(8), 1);
-    mbar_init(bar(9), 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) {
+  if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "n"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -151,6 +215,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, uint16_t* __restrict_
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
+#ifdef D3D_ATTN_STAMPS
+      const bool mst_on = blockIdx.x == 1 && blockIdx.y == 5 && blockIdx.z == 40;
+#endif
       const uint32_t idesc_s = make_idesc(kind, BQ, BKV, 0);
       const uint32_t idesc_o = make_idesc(kind, BQ, D, 1);
       const uint64_t dq = desc_kmajor(sbase + SMEM_Q);
@@ -168,133 +235,189 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, uint16_t* __restrict_
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j & 1;
         if (j + 1 < n_tiles) {
-          mbar_wait(bar(6), (uint32_t)j & 1u);  // softmax has pulled S_j out of TMEM
+          mbar_wait(bar(6), (uint32_t)j & 1u);  // the softmax warps hold S_j in registers
           tc_fence_after();
+          STAMP(mst_on && j < 8, 64 + j * 8 + 0);
           issue_s(j + 1);
+          STAMP(mst_on && j < 8, 64 + j * 8 + 1);
         }
-        mbar_wait(bar(7), (uint32_t)j & 1u);      // P_j is in shared memory
-        if (j > 0) mbar_wait(bar(9), (uint32_t)(j - 1) & 1u);  // O_{j-1} has been folded into registers
+        mbar_wait(bar(7), (uint32_t)j & 1u);  // P_j is in shared memory and O has been rescaled where the running max moved
+        STAMP(mst_on && j < 8, 64 + j * 8 + 2);
         tc_fence_after();
         const uint64_t dp = desc_kmajor(sbase + SMEM_P);
         const uint64_t dv = desc_mnmajor(sbase + SMEM_V + st * TILE_BYTES);
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k) {
-          // A = P: 16 keys = 32 B inside a 64-key atom (+2), next atom +16 KB; B = V: 16 key rows = 2048 B (+128)
+          // A = P: 16 keys = 32 B inside a 64-key atom (+2), next atom +16 KB; B = V: 16 key rows = 2048 B (+128).
+          // O accumulates in TMEM over all key tiles (the tensor pipe executes the products in issue order).
           const uint64_t a = dp + (uint64_t)((k & 3) * 2 + (k >> 2) * (TILE_BYTES >> 4));
-          umma_f16(tmem_o, a, dv + (uint64_t)(k * 128), idesc_o, k ? 1u : 0u);
+          umma_f16(tmem_o, a, dv + (uint64_t)(k * 128), idesc_o, (j | k) ? 1u : 0u);
         }
         umma_commit(bar(3 + st));  // K_j / V_j stage free
-        umma_commit(bar(8));       // O_j ready
+        umma_commit(bar(8));       // O += P_j V_j done: P buffer free, O readable
+        STAMP(mst_on && j < 8, 64 + j * 8 + 3);
       }
     }
-  } else if (warp >= 4) {
-    // ===================== softmax / correction / epilogue: one query row per thread =====================
+  } else {
+    // ===================== softmax / correction / epilogue =====================
+    // 8 warps: warp w owns TMEM lane quadrant w&3 (rows) and column half (w-2)>>2: 64 of the 128 keys of a tile and 32 of the
+    // 64 output channels.  A thread holds its 64 scores in registers (one TMEM read per tile); O stays in TMEM and is only
+    // rescaled when a row's running max moves by more than 2^8 (any consistent base <= max + 8 keeps P within 16-bit range).
     const int qd = warp & 3;
+    const int hf = (warp - 2) >> 2;
     const int r = qd * 32 + lane;        // row inside the tile == TMEM lane
     const int row = q0 + r;
     const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
-    float o[D];
-#pragma unroll
-    for (int i = 0; i < D; ++i) o[i] = 0.f;
+    constexpr int DH = D / 2;
     float m = -INFINITY, l = 0.f;
-    const uint32_t p_row = sbase + SMEM_P + (uint32_t)r * 128u;
+    const uint32_t p_row = sbase + SMEM_P + (uint32_t)hf * (uint32_t)TILE_BYTES + (uint32_t)r * 128u;  // this half's 64-key atom
     const uint32_t sw = (uint32_t)(r & 7);
-    for (int j = 0; j < n_tiles; ++j) {
-      const int c0 = j * BKV;
-      mbar_wait(bar(5), (uint32_t)j & 1u);
-      tc_fence_after();
-      // pass 1: row max
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < BKV; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_s + lane_off + (uint32_t)c, v);
-        tmem_ld_wait();
+    const uint32_t xmax_mine = sbase + SMEM_XMAX + (uint32_t)(hf * 128 + r) * 2u;
+    const uint32_t xmax_other = sbase + SMEM_XMAX + (uint32_t)((hf ^ 1) * 128 + r) * 2u;
+    // the row sums are exchanged (fp32) through the P buffer once the last P.V product has completed
+    const uint32_t xsum_mine = sbase + SMEM_P + (uint32_t)(hf * 128 + r) * 4u;
+    const uint32_t xsum_other = sbase + SMEM_P + (uint32_t)((hf ^ 1) * 128 + r) * 4u;
+#ifdef D3D_ATTN_STAMPS
+    const bool st_on = blockIdx.x == 1 && blockIdx.y == 5 && blockIdx.z == 40 && warp == 2 && lane == 0;
+#endif
+    const int lim_row = causal ? min(len, row + 1) : len;  // keys >= lim_row are masked for this row
+    // one key tile; EDGE tiles (crossing the sequence end or the causal diagonal) pay for the per-element compare
+    auto tile = [&](int j, auto edge_tag) {
+      constexpr bool EDGE = decltype(edge_tag)::value;
+      const int nv = lim_row - (j * BKV + hf * 64);  // this thread's keys [0, 64) of the tile half are valid below nv
+      uint32_t v[64];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int key = c0 + c + i;
-          const bool ok = key < len && (!causal || key <= row);
-          mx = fmaxf(mx, ok ? __uint_as_float(v[i]) : -INFINITY);
-        }
-      }
-      const float m_new = fmaxf(m, mx * scale_log2);
-      const float base = (m_new == -INFINITY) ? 0.f : m_new;
-      const float corr = exp2f(m - base);
-      m = m_new;
-      // pass 2: P = exp2(S*scale - m) -> 16-bit -> swizzled shared memory; row sum
-      float rs = 0.f;
-      // (the P buffer is free: this thread already waited for O_{j-1}, i.e. PV_{j-1} has retired)
-#pragma unroll 1
-      for (int c = 0; c < BKV; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_s + lane_off + (uint32_t)c, v);
-        tmem_ld_wait();
-        if (c == BKV - 32) {  // S_j fully read: the MMA warp may overwrite it with S_{j+1}
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar(6));
-        }
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const int key = c0 + c + i;
-          const bool ok0 = key < len && (!causal || key <= row);
-          const bool ok1 = key + 1 < len && (!causal || key + 1 <= row);
-          const float p0 = ok0 ? exp2f(__uint_as_float(v[i]) * scale_log2 - base) : 0.f;
-          const float p1 = ok1 ? exp2f(__uint_as_float(v[i + 1]) * scale_log2 - base) : 0.f;
-          rs += p0 + p1;
-          pk[i >> 1] = pack16x2(p0, p1, kind);
-        }
-        // 32 keys = 4 chunks of 16 B; key c -> atom c/64, chunk (c%64)/8 XOR (row%8)
-        const uint32_t atom = p_row + (uint32_t)(c >> 6) * (uint32_t)TILE_BYTES;
-        const uint32_t ch0 = (uint32_t)((c & 63) >> 3);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t addr = atom + (((ch0 + q) ^ sw) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * q]), "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]),
-                       "r"(pk[4 * q + 3])
-                       : "memory");
-        }
-      }
-      l = l * corr + rs;
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor-core (async) proxy
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(7));
-      // fold the previous tile's O into the running row while the tensor core works on PV_j:  o = o*corr_prev ... (done below)
-      // wait for O_j and accumulate
-      mbar_wait(bar(8), (uint32_t)j & 1u);
-      tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < D; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_o + lane_off + (uint32_t)c, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[c + i] = o[c + i] * corr + __uint_as_float(v[i]);
-      }
+      for (int c = 0; c < 64; c += 16) tmem_ld16(tmem_s + lane_off + (uint32_t)(hf * 64 + c), v + c);
+      tmem_ld_wait();
+      // S_j is in registers: the MMA warp may overwrite it with S_{j+1} once all 8 warps arrive
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar(9));
+      if (lane == 0) mbar_arrive(bar(6));
+      STAMP(st_on && j < 8, j * 8 + 2);
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) mx = fmaxf(mx, (!EDGE || i < nv) ? __uint_as_float(v[i]) : -INFINITY);
+      // the softmax base only has to be the SAME on both halves of a row and close to the true max: both threads use
+      // max(bf16(own), bf16(other)), so the 2-byte exchange loses nothing (2 CTAs/SM leaves 512 B for it)
+      {
+        const uint16_t mine = __bfloat16_as_ushort(__float2bfloat16_rn(mx));
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(xmax_mine), "h"(mine) : "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        uint16_t other;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(other) : "r"(xmax_other) : "memory");
+        mx = fmaxf(__bfloat162float(__ushort_as_bfloat16(mine)), __bfloat162float(__ushort_as_bfloat16(other)));
+      }
+      STAMP(st_on && j < 8, j * 8 + 3);
+      // lazy rescale: keep the old base while the row max grew by <= 8 (P <= 2^8); both threads of a row decide alike
+      const float m_cand = fmaxf(m, mx * scale_log2);
+      const bool move = (m_cand > m + 8.0f) || (m == -INFINITY && m_cand != -INFINITY);
+      float resc = 1.f;
+      if (move) {
+        resc = ex2_approx(m - m_cand);  // 0 on the first valid tile (m = -inf)
+        m = m_cand;
+      }
+      bool o_done = false;
+      if (j > 0 && __any_sync(0xffffffffu, move)) {
+        // O (TMEM) *= resc for the rows whose base moved; needs O += P_{j-1} V_{j-1} to have completed
+        mbar_wait_sleepy(bar(8), (uint32_t)(j - 1) & 1u);
+        tc_fence_after();
+        o_done = true;
+#pragma unroll
+        for (int c = 0; c < DH; c += 16) {
+          uint32_t ov[16];
+          tmem_ld16(tmem_o + lane_off + (uint32_t)(hf * DH + c), ov);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * resc);
+          tmem_st16(tmem_o + lane_off + (uint32_t)(hf * DH + c), ov);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      }
+      l *= resc;
+      const float nbase = (m == -INFINITY) ? 0.f : -m;
+      // P = 2^(S*scale - m) -> 16 bit (in place over the score registers); partial row sum
+      float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 64; i += 2) {
+        float t0, t1;
+        ffma2(t0, t1, __uint_as_float(v[i]), __uint_as_float(v[i + 1]), scale_log2, scale_log2, nbase, nbase);
+        float p0 = ex2_approx(t0), p1 = ex2_approx(t1);
+        if (EDGE) {
+          p0 = (i < nv) ? p0 : 0.f;
+          p1 = (i + 1 < nv) ? p1 : 0.f;
+        }
+        fadd2(rs0, rs1, rs0, rs1, p0, p1);
+        v[i >> 1] = pack16x2(p0, p1, kind);
+      }
+      l += rs0 + rs1;
+      STAMP(st_on && j < 8, j * 8 + 4);
+      // the P buffer is free once O += P_{j-1} V_{j-1} has completed
+      if (j > 0 && !o_done) {
+        mbar_wait_sleepy(bar(8), (uint32_t)(j - 1) & 1u);
+        tc_fence_after();
+      }
+      STAMP(st_on && j < 8, j * 8 + 5);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {  // 8 x 16 B = this thread's 64 keys, K-major SWIZZLE_128B atom of this half
+        const uint32_t addr = p_row + ((((uint32_t)q) ^ sw) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[4 * q]), "r"(v[4 * q + 1]), "r"(v[4 * q + 2]),
+                     "r"(v[4 * q + 3])
+                     : "memory");
+      }
+    };
+    for (int j = 0; j < n_tiles; ++j) {
+      const bool edge = __any_sync(0xffffffffu, j * BKV + BKV > lim_row);  // warp-uniform
+      STAMP(st_on && j < 8, j * 8 + 0);
+      mbar_wait_sleepy(bar(5), (uint32_t)j & 1u);
+      tc_fence_after();
+      STAMP(st_on && j < 8, j * 8 + 1);
+      if (edge) tile(j, std::true_type{});
+      else tile(j, std::false_type{});
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor-core (async) proxy
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(7));
+      STAMP(st_on && j < 8, j * 8 + 6);
     }
+    // epilogue: O / l
+    mbar_wait_sleepy(bar(8), (uint32_t)(n_tiles - 1) & 1u);
+    tc_fence_after();
+    // total row sum = sum of the two halves (same base on both sides)
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(xsum_mine), "f"(l) : "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    float l_other;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(l_other) : "r"(xsum_other) : "memory");
+    l += l_other;
+    uint32_t o[DH];
+    tmem_ld32(tmem_o + lane_off + (uint32_t)(hf * DH), o);
+    tmem_ld_wait();
     if (row < len) {
       const float inv = l > 0.f ? 1.0f / l : 0.f;
-      uint4* dst = reinterpret_cast<uint4*>(out + (size_t)(b + row) * ldo + (size_t)h * D);
+      uint4* dst = reinterpret_cast<uint4*>(out + (size_t)(b + row) * ldo + (size_t)h * D + hf * DH);
 #pragma unroll
-      for (int i = 0; i < D / 8; ++i) {
-        dst[i] = make_uint4(pack16x2(o[8 * i] * inv, o[8 * i + 1] * inv, kind), pack16x2(o[8 * i + 2] * inv, o[8 * i + 3] * inv, kind),
-                            pack16x2(o[8 * i + 4] * inv, o[8 * i + 5] * inv, kind), pack16x2(o[8 * i + 6] * inv, o[8 * i + 7] * inv, kind));
+      for (int i = 0; i < DH / 8; ++i) {
+        auto f = [&](int k) { return __uint_as_float(o[8 * i + k]) * inv; };
+        dst[i] = make_uint4(pack16x2(f(0), f(1), kind), pack16x2(f(2), f(3), kind), pack16x2(f(4), f(5), kind), pack16x2(f(6), f(7), kind));
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 }  // namespace
+
+#ifdef D3D_ATTN_STAMPS
+extern "C" int d3d_debug_attn_stamps(long long* host_out) {
+  D3D_CHECK_CUDA(cudaDeviceSynchronize());
+  D3D_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_stamps, sizeof(long long) * 256));
+  return 0;
+}
+#endif
 
 extern "C" int d3d_attention_tc(const void* qkv, int64_t ld, int64_t n_rows, void* out, int64_t ldo, const int* cu_seqlens, int n_seq,
                                 int max_len, int H, int Dh, int causal, int kind, float scale, void* stream) {

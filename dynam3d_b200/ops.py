@@ -264,7 +264,7 @@ def attention(qkv, out, cu_seqlens, n_seq, max_len, H, Dh, causal=False, uniform
     """Self-attention over packed sequences.  `impl`: 'tc' (tcgen05, head_dim 64), 'mma' (legacy tensor cores), 'simt' (fp32
     CUDA cores) or 'auto' (tc for long head_dim-64 sequences, mma otherwise, simt for very short ones)."""
     scale = 1.0 / math.sqrt(Dh)
-    if impl == "tc":  # opt-in: the first tcgen05 version is softmax-latency bound and not yet faster than the mma kernel
+    if impl == "tc" or (impl == "auto" and Dh == 64 and max_len >= 256):
         L.check(L.lib().d3d_attention_tc(L.ptr(qkv), qkv.stride(0), qkv.shape[0], L.ptr(out), out.stride(0), L.ptr(cu_seqlens), n_seq, max_len, H, Dh,
                                          int(bool(causal)), L.kind_of(qkv.dtype), scale, L.stream_ptr()))
         return
