@@ -56,7 +56,7 @@ _IP, _FP = ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_float)
 # argument types of every exported entry (mirrors include/dynam3d_b200.h); tests/test_abi.py checks the symbol list
 SIGNATURES = {
     "d3d_version": [], "d3d_sm_count": [], "d3d_check_device": [_I],
-    "d3d_gemm": [_P, _P], "d3d_gemm_simt": [_P, _P],
+    "d3d_gemm": [_P, _P], "d3d_gemm_simt": [_P, _P], "d3d_gemm_set_pair_mode": [_I],
     "d3d_depth_preprocess": [_P, _P, _I, _I, _I, _F, _F, _P],
     "d3d_depth_patch_grid": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _IP, _IP, _F, _F, _P],
     "d3d_unproject_habitat": [_P, _P, _I, _I, _I, _FP, _FP, _FP, _F, _P, _P, _P, _P],

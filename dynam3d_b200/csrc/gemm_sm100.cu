@@ -10,7 +10,14 @@
 //                                  the main loop of tile i+1)
 //   warps 4..11 : epilogue      -- tcgen05.ld 32x32b (one accumulator row per thread, two warps per TMEM lane quadrant split the
 //                                  columns), bias / activation / residual in registers, vectorised global stores
+// CTAS == 2 (large problems): the two CTAs of a cluster (one TPC) work as a pair on a 256 x BN tile with
+//   tcgen05.mma.cta_group::2 (UMMA_M = 256): each CTA stages its own 128 rows of A and HALF of the W tile (BN/2 rows), so the
+//   shared-memory traffic per MMA halves; TMA loads of both CTAs complete on the leader's full barrier, the leader's MMA warp
+//   issues for the pair and multicasts its commits to both CTAs' empty / tmem-full barriers; every CTA drains its own 128 TMEM
+//   lanes, and the peer's epilogue warps release the accumulator with a remote mbarrier arrive on the leader.
 // Replaces the cuBLAS calls behind every nn.Linear on the reference path (see include/dynam3d_b200.h).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -21,11 +28,12 @@ constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 384;  // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4-11: epilogue (2 per TMEM lane quadrant)
 constexpr int NUM_EPI_WARPS = 8;
 
-template <int BN>
+template <int BN, int CTAS>
 struct Cfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int STAGES = (BN == 256 && CTAS == 1) ? 4 : 6;
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_ROWS = BN / CTAS;  // rows of the W tile this CTA stages
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;  // 256 or 512: power of two >= 32
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
@@ -85,6 +93,48 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// ---- cta_group::2 (CTA pair) variants ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same smem offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load issued by either CTA of a pair; the transaction bytes complete on `bar_cluster` (the LEADER's full barrier)
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// commit of the pair's MMAs: arrives once on the barrier at this smem offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -112,13 +162,13 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 }
 // UMMA instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1<<4), a/b format (0=f16,1=bf16) at 7/10,
 // K-major A and B (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).
-__device__ __forceinline__ uint32_t make_idesc(int kind, int n) {
+__device__ __forceinline__ uint32_t make_idesc(int kind, int n, int m = BM) {
   uint32_t d = 0;
   d |= 1u << 4;
   d |= (uint32_t)kind << 7;
   d |= (uint32_t)kind << 10;
   d |= (uint32_t)(n >> 3) << 17;
-  d |= (uint32_t)(BM >> 4) << 24;
+  d |= (uint32_t)(m >> 4) << 24;
   return d;
 }
 
@@ -132,11 +182,10 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   }
 }
 
-template <int BN>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Epilogue ep, int M, int N,
-                    int K, int in_kind) {
-  using C = Cfg<BN>;
+template <int BN, int CTAS>
+__device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const Epilogue& ep, int M, int N, int K, int in_kind) {
+  using C = Cfg<BN, CTAS>;
+  constexpr int TM = BM * CTAS;  // rows of the tile a CTA (pair) owns
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
@@ -149,10 +198,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int tiles_m = (M + BM - 1) / BM;
+  const int tiles_m = (M + TM - 1) / TM;
   const int tiles_n = (N + BN - 1) / BN;
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = (K + BK - 1) / BK;
+  const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0u;
+  const int first_tile = CTAS == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = CTAS == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -165,16 +217,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), NUM_EPI_WARPS);  // one arrive per epilogue warp
+      mbar_init(tempty_bar(a), NUM_EPI_WARPS * CTAS);  // one arrive per epilogue warp (of both CTAs of a pair, on the leader)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "n"(C::TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CTAS == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "n"(C::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "n"(C::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync(); else __syncthreads();  // the peer's barriers must be initialised before any remote arrive / complete_tx
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
@@ -184,27 +241,35 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / tiles_n) * BM;
-        const int n0 = (tile % tiles_n) * BN;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+        const int m0 = (tile / tiles_n) * TM + (int)cta_rank * BM;
+        const int n0 = (tile % tiles_n) * BN + (int)cta_rank * C::B_ROWS;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
-          mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
-          tma_load_2d(sa, &tmA, full_bar(stage), kb * BK, m0);
-          tma_load_2d(sa + C::A_BYTES, &tmB, full_bar(stage), kb * BK, n0);
+          if (CTAS == 2) {
+            // both CTAs' loads complete on the LEADER's full barrier, which expects the bytes of the pair
+            if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
+            const uint32_t lead_full = mapa(full_bar(stage), 0);
+            tma_load_2d_2sm(sa, &tmA, lead_full, kb * BK, m0);
+            tma_load_2d_2sm(sa + C::A_BYTES, &tmB, lead_full, kb * BK, n0);
+          } else {
+            mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+            tma_load_2d(sa, &tmA, full_bar(stage), kb * BK, m0);
+            tma_load_2d(sa + C::A_BYTES, &tmB, full_bar(stage), kb * BK, n0);
+          }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(in_kind, BN);
+    if (lane == 0 && cta_rank == 0) {  // in a pair only the leader issues
+      const uint32_t idesc = make_idesc(in_kind, BN, TM);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
@@ -219,10 +284,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance 16 elements (32 B) along K inside the 128 B swizzle atom: +2 in the (addr >> 4) field
-            umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+            if (CTAS == 2) umma_f16_2sm(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+            else umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
           }
-          umma_commit(empty_bar(stage));  // frees this smem stage when the MMAs above retire
-          if (kb == num_kb - 1) umma_commit(tfull_bar(acc));
+          if (CTAS == 2) {
+            umma_commit_2sm(empty_bar(stage));  // frees this smem stage in BOTH CTAs when the MMAs above retire
+            if (kb == num_kb - 1) umma_commit_2sm(tfull_bar(acc));
+          } else {
+            umma_commit(empty_bar(stage));  // frees this smem stage when the MMAs above retire
+            if (kb == num_kb - 1) umma_commit(tfull_bar(acc));
+          }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -232,10 +303,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int q = warp & 3;
     const int chalf = (warp - 4) >> 2;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-      const int m0 = (tile / tiles_n) * BM;
+      const int m0 = (tile / tiles_n) * TM + (int)cta_rank * BM;
       const int n0 = (tile % tiles_n) * BN;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
@@ -348,15 +419,34 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if (CTAS == 2) mbar_arrive_cluster(mapa(tempty_bar(acc), 0));  // the leader's MMA warp waits for both CTAs' epilogues
+        else mbar_arrive(tempty_bar(acc));
+      }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync(); else __syncthreads();  // the leader's MMAs read the peer's smem: nobody leaves early
   if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
+    if (CTAS == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
   }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Epilogue ep, int M, int N,
+                    int K, int in_kind) {
+  gemm_body<BN, 1>(tmA, tmB, ep, M, N, K, in_kind);
+}
+
+// CTA-pair variant: cluster of 2 (same TPC), 256 x BN tile per pair
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Epilogue ep, int M, int N,
+                         int K, int in_kind) {
+  gemm_body<BN, 2>(tmA, tmB, ep, M, N, K, in_kind);
 }
 
 // ---------------- host side ----------------
@@ -398,7 +488,7 @@ int make_tmap(CUtensorMap* map, const void* base, int kind, long long rows, long
 
 template <int BN>
 int launch(const d3d_gemm_args& a, cudaStream_t st) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, 1>;
   static bool attr_set = false;
   if (!attr_set) {
     D3D_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -456,6 +546,32 @@ int validate(const d3d_gemm_args& a) {
 
 }  // namespace
 
+template <int BN>
+int launch_pair(const d3d_gemm_args& a, cudaStream_t st) {
+  using C = Cfg<BN, 2>;
+  static int max_clusters = -1;
+  if (max_clusters < 0) {
+    D3D_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(d3d_num_sms() & ~1)); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_tcgen05_pair_kernel<BN>, &cfg) != cudaSuccess || n <= 0) { (void)cudaGetLastError(); n = d3d_num_sms() / 2; }
+    max_clusters = n < d3d_num_sms() / 2 ? n : d3d_num_sms() / 2;
+  }
+  CUtensorMap tmA, tmB;
+  D3D_TRY(make_tmap(&tmA, a.A, a.in_kind, a.M, a.K, a.lda, BM));
+  D3D_TRY(make_tmap(&tmB, a.W, a.in_kind, a.N, a.K, a.ldw, C::B_ROWS));
+  Epilogue ep{a.C, a.ldc, a.bias, a.residual, a.ldres, a.act, a.out_kind};
+  const int tiles = d3d_cdiv(a.M, 2 * BM) * d3d_cdiv(a.N, BN);
+  const int clusters = tiles < max_clusters ? tiles : max_clusters;
+  gemm_tcgen05_pair_kernel<BN><<<2 * clusters, NUM_THREADS, C::SMEM_BYTES, st>>>(tmA, tmB, ep, a.M, a.N, a.K, a.in_kind);
+  D3D_CHECK_LAUNCH();
+  return 0;
+}
+
+static int g_gemm_pair_mode = -1;  // -1: read D3D_GEMM_PAIR from the environment (default on), 0 off, 1 on
+extern "C" int d3d_gemm_set_pair_mode(int mode) { g_gemm_pair_mode = mode; return 0; }
+
 extern "C" int d3d_gemm(const d3d_gemm_args* args_h, void* stream) {
   D3D_REQUIRE(args_h != nullptr, "args");
   const d3d_gemm_args& a = *args_h;
@@ -463,6 +579,12 @@ extern "C" int d3d_gemm(const d3d_gemm_args* args_h, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   // wide tiles once there is enough work to fill the machine with them; 128-wide otherwise
   const long long tiles256 = (long long)d3d_cdiv(a.M, BM) * d3d_cdiv(a.N, 256);
+  if (g_gemm_pair_mode < 0) {
+    const char* e = getenv("D3D_GEMM_PAIR");
+    g_gemm_pair_mode = (e && e[0] == '0') ? 0 : 1;
+  }
+  // CTA pairs (cta_group::2, 256 x 256 tiles) once every pair has at least ~2 tiles
+  if (g_gemm_pair_mode == 1 && a.N >= 256 && (long long)d3d_cdiv(a.M, 2 * BM) * d3d_cdiv(a.N, 256) >= (long long)d3d_num_sms()) return launch_pair<256>(a, st);
   if (a.N >= 256 && tiles256 >= 2LL * d3d_num_sms()) return launch<256>(a, st);
   return launch<128>(a, st);
 }

@@ -71,6 +71,9 @@ typedef struct {
   int64_t ldres;
 } d3d_gemm_args;
 int d3d_gemm(const d3d_gemm_args* args_h, void* stream);
+/* Large problems run on CTA pairs (tcgen05.mma.cta_group::2, 256x256 tiles per 2-CTA cluster).  mode: 1 = on (default),
+ * 0 = single-CTA kernels only (A/B comparisons in tools/gemm_bench.py), -1 = re-read D3D_GEMM_PAIR from the environment. */
+int d3d_gemm_set_pair_mode(int mode);
 
 /* Plain CUDA-core reference GEMM with the same contract (debug / self-check only, slow). */
 int d3d_gemm_simt(const d3d_gemm_args* args_h, void* stream);

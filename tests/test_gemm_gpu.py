@@ -37,6 +37,12 @@ CASES = [
     (6912, 1024, 592, torch.float16, False, 0, False, torch.float32),
     (1, 768, 768, torch.float16, True, 3, False, torch.float32),
     (4800, 8192, 3072, torch.bfloat16, False, 0, True, torch.float32),
+    # CTA-pair (cta_group::2) shapes: >= 148 pair tiles of 256x256; ragged M (not a multiple of 256 / 128) and N = 768
+    (20000, 4096, 1024, torch.float16, True, 1, False, torch.float16),
+    (19999, 1024, 4096, torch.float16, True, 0, True, torch.float32),
+    (13849, 768, 1024, torch.float16, False, 0, False, torch.float16),
+    (6001, 16384, 3072, torch.float16, False, 4, False, torch.float16),
+    (6100, 9216, 3072, torch.bfloat16, False, 0, False, torch.bfloat16),
 ]
 
 
@@ -74,3 +80,20 @@ def test_gemm_simt_agrees():
     y2 = ops.gemm(a, w, bias=b, act=2, out_dtype=torch.float32, simt=True)
     torch.cuda.synchronize()
     assert (y1 - y2).abs().max().item() < 2e-3
+
+
+def test_gemm_pair_and_single_cta_agree_bitwise():
+    """The CTA-pair kernel accumulates every output element over K in the same order as the single-CTA kernel."""
+    from dynam3d_b200 import ops, _lib
+    a = (torch.randn(16000, 1024, device="cuda") * 0.5).half()
+    w = (torch.randn(4096, 1024, device="cuda") / 32).half()
+    b = torch.randn(4096, device="cuda")
+    try:
+        _lib.lib().d3d_gemm_set_pair_mode(0)
+        y0 = ops.gemm(a, w, bias=b, act=1)
+        _lib.lib().d3d_gemm_set_pair_mode(1)
+        y1 = ops.gemm(a, w, bias=b, act=1)
+    finally:
+        _lib.lib().d3d_gemm_set_pair_mode(-1)
+    torch.cuda.synchronize()
+    assert torch.equal(y0, y1)
