@@ -36,7 +36,8 @@ struct Cfg {
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;  // 256 or 512: power of two >= 32
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int EPI_STAGING = NUM_EPI_WARPS * 32 * 32 * 4;  // one 32x32 fp32 transposition tile per epilogue warp
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGING + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 struct Epilogue {
@@ -148,6 +149,24 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait that also names the destination registers of the outstanding tcgen05.ld, so no use of them can be scheduled above it
+__device__ __forceinline__ void tmem_ld_wait32(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                 "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),
+                 "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),
+                 "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+// x * sigmoid(a x) = 0.5 x (1 + tanh(0.5 a x)): ONE MUFU op (tanh.approx, rel. error 2^-11) instead of ex2 + rcp.  Used where the
+// result is stored as a 16-bit value anyway (same 2^-11 rounding); fp32 outputs (precise mode) take the exact path.
+__device__ __forceinline__ float x_sigmoid_fast(float x, float half_a) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x * half_a));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
+}
 
 // UMMA shared-memory descriptor, K-major operand, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor):
 // [0,14) start>>4 | [16,30) LBO>>4 (=1, ignored for swizzled K-major) | [32,46) SBO>>4 (=64) | [46,48) version=1 | [61,64) layout=2
@@ -182,13 +201,142 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   }
 }
 
+// Epilogue of one 32-row x (BN/2)-column slab of an accumulator tile, executed by ONE warp (TMEM lane quadrant = rows row0..row0+31).
+// Per 32-column chunk: tcgen05.ld (one accumulator row per thread; the next chunk's load is in flight while this one is processed),
+// bias + activation in registers, then the 32x32 fp32 chunk (SWIGLU: 32x16) is transposed through the warp's XOR-swizzled smem tile so
+// that every lane owns 8 consecutive output columns of a row: residual loads and stores are row-contiguous (32 B .. 128 B per row
+// and instruction instead of 32 rows x 16 B).  All addressing that does not depend on the chunk is hoisted out of the chunk loop.
+template <int BN, bool SWIGLU>
+__device__ __forceinline__ void epilogue_tile(const Epilogue& ep, uint32_t taddr, uint32_t stg, int lane, int chalf, int row0, int n0, int M, int N) {
+  constexpr int PASSES = SWIGLU ? 2 : 4;   // read-back passes per chunk
+  constexpr int CW = SWIGLU ? 16 : 32;     // output columns per chunk
+  const int n_out = SWIGLU ? (N >> 1) : N;
+  const int rr0 = SWIGLU ? (lane & 15) : (lane >> 2);   // row of this lane in pass 0 (pass p: + p * 32 / PASSES)
+  const int g0 = SWIGLU ? ((lane >> 4) * 2) : ((lane & 3) * 2);  // first of the lane's two 16-byte groups
+  const int esz = ep.out_kind == D3D_OUT_F32 ? 4 : 2;
+  const bool fast = ep.out_kind != D3D_OUT_F32;
+  const uint32_t st_row = stg + (uint32_t)lane * 128u;
+  const uint32_t sw = (uint32_t)(lane & 7);
+  // read-back smem addresses and global row pointers (chunk-independent)
+  uint32_t ld_a[PASSES], ld_b[PASSES];
+  char* cptr[PASSES];
+  const float* rptr[PASSES];
+  bool ok[PASSES];
+#pragma unroll
+  for (int p = 0; p < PASSES; ++p) {
+    const int rr = rr0 + p * (32 / PASSES);
+    const uint32_t rsw = (uint32_t)(rr & 7);
+    ld_a[p] = stg + (uint32_t)rr * 128u + (((uint32_t)g0 ^ rsw) << 4);
+    ld_b[p] = stg + (uint32_t)rr * 128u + (((uint32_t)(g0 + 1) ^ rsw) << 4);
+    const long long grow = row0 + rr;
+    ok[p] = grow < M;
+    const int oc = (SWIGLU ? (n0 >> 1) : n0) + g0 * 4;
+    cptr[p] = (char*)ep.C + (grow * ep.ldc + oc) * esz;
+    rptr[p] = ep.residual ? ep.residual + grow * ep.ldres + oc : nullptr;
+  }
+  const int c_begin = chalf * (BN / 2), c_end = (chalf + 1) * (BN / 2);
+  uint32_t r[32];
+  tmem_ld32(taddr + (uint32_t)c_begin, r);
+#pragma unroll 1
+  for (int c = c_begin; c < c_end; c += 32) {
+    tmem_ld_wait32(r);
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+    if (c + 32 < c_end) tmem_ld32(taddr + (uint32_t)(c + 32), r);
+    const int col0 = n0 + c;
+    if (col0 >= N) continue;  // warp-uniform
+    const bool full = col0 + 32 <= N;
+    if (ep.bias) {
+      if (full) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(ep.bias + col0) + i);
+          v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (col0 + i < N) v[i] += __ldg(ep.bias + col0 + i);
+      }
+    }
+    if (SWIGLU) {  // row-interleaved gate/up: acc cols (2j, 2j+1) -> out col j
+      if (fast) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = x_sigmoid_fast(v[2 * i], 0.5f) * v[2 * i + 1];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __fdividef(v[2 * i], 1.0f + __expf(-v[2 * i])) * v[2 * i + 1];
+      }
+    } else if (ep.act == D3D_ACT_QUICK_GELU) {
+      if (fast) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = x_sigmoid_fast(v[i], 0.851f);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __fdividef(v[i], 1.0f + __expf(-1.702f * v[i]));
+      }
+    } else if (ep.act == D3D_ACT_GELU) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+    } else if (ep.act == D3D_ACT_SILU) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __fdividef(v[i], 1.0f + __expf(-v[i]));
+    } else if (ep.act == D3D_ACT_LEAKY_RELU) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : 0.01f * v[i];
+    }
+#pragma unroll
+    for (int j = 0; j < CW / 4; ++j)
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st_row + (((uint32_t)j ^ sw) << 4)), "f"(v[4 * j]), "f"(v[4 * j + 1]),
+                   "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
+                   : "memory");
+    __syncwarp();
+    const int oc_chunk = SWIGLU ? (c >> 1) : c;                 // output-column offset of this chunk inside the tile
+    const int ocol = (SWIGLU ? (n0 >> 1) : n0) + g0 * 4 + oc_chunk;  // first of this lane's 8 output columns
+    const bool vec = (SWIGLU ? ((col0 >> 1) + CW) : (col0 + CW)) <= n_out;  // warp-uniform: the whole chunk is inside the matrix
+#pragma unroll
+    for (int p = 0; p < PASSES; ++p) {
+      float f[8];
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]) : "r"(ld_a[p]));
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7]) : "r"(ld_b[p]));
+      if (!ok[p]) continue;
+      if (vec) {
+        if (rptr[p]) {
+          const float4* res = reinterpret_cast<const float4*>(rptr[p] + oc_chunk);
+          const float4 t0 = res[0], t1 = res[1];
+          f[0] += t0.x; f[1] += t0.y; f[2] += t0.z; f[3] += t0.w; f[4] += t1.x; f[5] += t1.y; f[6] += t1.z; f[7] += t1.w;
+        }
+        if (ep.out_kind == D3D_OUT_F32) {
+          float4* dst = reinterpret_cast<float4*>(cptr[p] + oc_chunk * 4);
+          dst[0] = make_float4(f[0], f[1], f[2], f[3]);
+          dst[1] = make_float4(f[4], f[5], f[6], f[7]);
+        } else {
+          *reinterpret_cast<uint4*>(cptr[p] + oc_chunk * 2) =
+              make_uint4(pack16x2(f[0], f[1], ep.out_kind), pack16x2(f[2], f[3], ep.out_kind), pack16x2(f[4], f[5], ep.out_kind),
+                         pack16x2(f[6], f[7], ep.out_kind));
+        }
+      } else {
+        for (int i = 0; i < 8 && ocol + i < n_out; ++i) {
+          float x = f[i];
+          if (rptr[p]) x += rptr[p][oc_chunk + i];
+          if (ep.out_kind == D3D_OUT_F32) reinterpret_cast<float*>(cptr[p])[oc_chunk + i] = x;
+          else st16(cptr[p], (size_t)(oc_chunk + i), x, ep.out_kind);
+        }
+      }
+    }
+    __syncwarp();  // the smem tile is rewritten by the next chunk
+  }
+}
+
 template <int BN, int CTAS>
 __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const Epilogue& ep, int M, int N, int K, int in_kind) {
   using C = Cfg<BN, CTAS>;
   constexpr int TM = BM * CTAS;  // rows of the tile a CTA (pair) owns
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
+  const uint32_t epi_base = smem_base + C::STAGES * C::STAGE_BYTES;
+  const uint32_t bar_base = epi_base + C::EPI_STAGING;
   // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem ptr (4 B)
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
@@ -302,6 +450,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
     // ===================== epilogue: warps 4..11; warp w drains TMEM lane quadrant w%4, column half (w-4)/4 =====================
     const int q = warp & 3;
     const int chalf = (warp - 4) >> 2;
+    const uint32_t stg = epi_base + (uint32_t)(warp - 4) * 4096u;
     int it = 0;
     for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
       const int acc = it & 1;
@@ -310,113 +459,9 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
       const int n0 = (tile % tiles_n) * BN;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int row = m0 + q * 32 + lane;
-      const bool row_ok = row < M;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 2
-      for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 32) {
-        uint32_t r[32];
-        tmem_ld32(taddr + (uint32_t)c, r);
-        tmem_ld_wait();
-        const int col0 = n0 + c;
-        if (row_ok && col0 < N) {
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-          const bool full = col0 + 32 <= N;
-          if (ep.bias) {
-            if (full) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float4 t = __ldg(reinterpret_cast<const float4*>(ep.bias + col0) + i);
-                v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (col0 + i < N) v[i] += __ldg(ep.bias + col0 + i);
-            }
-          }
-          if (ep.act == D3D_ACT_SWIGLU) {
-            // row-interleaved gate/up: acc cols (2j, 2j+1) -> out col j
-            const long long ocol0 = col0 >> 1;
-            const int nout = N >> 1;
-            float o[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = __fdividef(v[2 * i], 1.0f + __expf(-v[2 * i])) * v[2 * i + 1];
-            if (ep.out_kind == D3D_OUT_F32) {
-              float* dst = (float*)ep.C + (long long)row * ep.ldc + ocol0;
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (ocol0 + i < nout) dst[i] = o[i];
-            } else {
-              uint32_t* dst = (uint32_t*)((uint16_t*)ep.C + (long long)row * ep.ldc + ocol0);
-              if (ocol0 + 16 <= nout) {
-                uint4 p0 = make_uint4(pack16x2(o[0], o[1], ep.out_kind), pack16x2(o[2], o[3], ep.out_kind),
-                                      pack16x2(o[4], o[5], ep.out_kind), pack16x2(o[6], o[7], ep.out_kind));
-                uint4 p1 = make_uint4(pack16x2(o[8], o[9], ep.out_kind), pack16x2(o[10], o[11], ep.out_kind),
-                                      pack16x2(o[12], o[13], ep.out_kind), pack16x2(o[14], o[15], ep.out_kind));
-                reinterpret_cast<uint4*>(dst)[0] = p0;
-                reinterpret_cast<uint4*>(dst)[1] = p1;
-              } else {
-                for (int i = 0; i < 16; ++i)
-                  if (ocol0 + i < nout) st16(ep.C, (size_t)((long long)row * ep.ldc + ocol0 + i), o[i], ep.out_kind);
-              }
-            }
-          } else {
-            if (ep.act == D3D_ACT_QUICK_GELU) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = __fdividef(v[i], 1.0f + __expf(-1.702f * v[i]));
-            } else if (ep.act == D3D_ACT_GELU) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
-            } else if (ep.act == D3D_ACT_SILU) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = __fdividef(v[i], 1.0f + __expf(-v[i]));
-            } else if (ep.act == D3D_ACT_LEAKY_RELU) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : 0.01f * v[i];
-            }
-            if (ep.residual) {
-              const float* res = ep.residual + (long long)row * ep.ldres + col0;
-              if (full) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  float4 t = reinterpret_cast<const float4*>(res)[i];
-                  v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
-                }
-              } else {
-                for (int i = 0; i < 32; ++i)
-                  if (col0 + i < N) v[i] += res[i];
-              }
-            }
-            if (ep.out_kind == D3D_OUT_F32) {
-              float* dst = (float*)ep.C + (long long)row * ep.ldc + col0;
-              if (full) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                  reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-              } else {
-                for (int i = 0; i < 32; ++i)
-                  if (col0 + i < N) dst[i] = v[i];
-              }
-            } else {
-              uint16_t* dst = (uint16_t*)ep.C + (long long)row * ep.ldc + col0;
-              if (full) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  uint4 p = make_uint4(pack16x2(v[8 * i], v[8 * i + 1], ep.out_kind), pack16x2(v[8 * i + 2], v[8 * i + 3], ep.out_kind),
-                                       pack16x2(v[8 * i + 4], v[8 * i + 5], ep.out_kind), pack16x2(v[8 * i + 6], v[8 * i + 7], ep.out_kind));
-                  reinterpret_cast<uint4*>(dst)[i] = p;
-                }
-              } else {
-                for (int i = 0; i < 32; ++i)
-                  if (col0 + i < N) st16(ep.C, (size_t)((long long)row * ep.ldc + col0 + i), v[i], ep.out_kind);
-              }
-            }
-          }
-        }
-      }
+      if (ep.act == D3D_ACT_SWIGLU) epilogue_tile<BN, true>(ep, taddr, stg, lane, chalf, m0 + q * 32, n0, M, N);
+      else epilogue_tile<BN, false>(ep, taddr, stg, lane, chalf, m0 + q * 32, n0, M, N);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {

@@ -9,7 +9,7 @@ from dynam3d_b200 import ops, _lib  # noqa: E402
 
 SHAPES = [  # (M, N, K, dtype, act)
     (6924, 3072, 1024, torch.float16, 0), (6924, 1024, 1024, torch.float16, 0), (6924, 4096, 1024, torch.float16, 1),
-    (6924, 1024, 4096, torch.float16, 0), (55392, 4096, 1024, torch.float16, 1), (55392, 1024, 4096, torch.float16, 0),
+    (6924, 1024, 4096, torch.float16, 0), (55392, 3072, 1024, torch.float16, 0), (55392, 1024, 1024, torch.float16, 0), (55392, 4096, 1024, torch.float16, 1), (55392, 1024, 4096, torch.float16, 0),
     (600, 9216, 3072, torch.bfloat16, 0), (600, 16384, 3072, torch.bfloat16, 4), (600, 3072, 8192, torch.bfloat16, 0),
     (6000, 9216, 3072, torch.float16, 0), (6000, 16384, 3072, torch.float16, 4), (6000, 3072, 8192, torch.float16, 0), (6000, 3072, 3072, torch.float16, 0),
     (4800, 9216, 3072, torch.bfloat16, 0), (4800, 16384, 3072, torch.bfloat16, 4), (4800, 3072, 8192, torch.bfloat16, 0),
