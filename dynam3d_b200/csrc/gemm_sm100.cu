@@ -202,131 +202,196 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 }
 
 // Epilogue of one 32-row x (BN/2)-column slab of an accumulator tile, executed by ONE warp (TMEM lane quadrant = rows row0..row0+31).
-// Per 32-column chunk: tcgen05.ld (one accumulator row per thread; the next chunk's load is in flight while this one is processed),
-// bias + activation in registers, then the 32x32 fp32 chunk (SWIGLU: 32x16) is transposed through the warp's XOR-swizzled smem tile so
-// that every lane owns 8 consecutive output columns of a row: residual loads and stores are row-contiguous (32 B .. 128 B per row
-// and instruction instead of 32 rows x 16 B).  All addressing that does not depend on the chunk is hoisted out of the chunk loop.
+// Per 32-column chunk: tcgen05.ld (one accumulator row per thread) -> the raw 32x32 fp32 chunk is transposed through the warp's
+// XOR-swizzled smem tile (the next chunk's TMEM load is issued right behind it) -> every lane then owns 8 consecutive columns of one row
+// per pass (4 passes): + bias (8 registers, loaded before the TMEM wait so the L2 latency is hidden), activation, + fp32 residual and
+// a row-contiguous vector store (32 B .. 128 B per row and instruction instead of 32 rows x 16 B).  All addressing that does not
+// depend on the chunk is hoisted out of the chunk loop.
 template <int BN, bool SWIGLU>
 __device__ __forceinline__ void epilogue_tile(const Epilogue& ep, uint32_t taddr, uint32_t stg, int lane, int chalf, int row0, int n0, int M, int N) {
-  constexpr int PASSES = SWIGLU ? 2 : 4;   // read-back passes per chunk
-  constexpr int CW = SWIGLU ? 16 : 32;     // output columns per chunk
+  constexpr int PASSES = 4;
+  constexpr int OW = SWIGLU ? 4 : 8;  // output columns per lane and pass (SWIGLU: acc cols (2j, 2j+1) -> out col j)
   const int n_out = SWIGLU ? (N >> 1) : N;
-  const int rr0 = SWIGLU ? (lane & 15) : (lane >> 2);   // row of this lane in pass 0 (pass p: + p * 32 / PASSES)
-  const int g0 = SWIGLU ? ((lane >> 4) * 2) : ((lane & 3) * 2);  // first of the lane's two 16-byte groups
+  const int rr0 = lane >> 2;        // row of this lane in pass 0 (pass p: + 8p)
+  const int g0 = (lane & 3) * 2;    // first of the lane's two 16-byte groups = accumulator columns g0*4 .. g0*4+7 of the chunk
   const int esz = ep.out_kind == D3D_OUT_F32 ? 4 : 2;
   const bool fast = ep.out_kind != D3D_OUT_F32;
   const uint32_t st_row = stg + (uint32_t)lane * 128u;
   const uint32_t sw = (uint32_t)(lane & 7);
-  // read-back smem addresses and global row pointers (chunk-independent)
   uint32_t ld_a[PASSES], ld_b[PASSES];
   char* cptr[PASSES];
   const float* rptr[PASSES];
   bool ok[PASSES];
+  const int oc_lane = SWIGLU ? ((n0 + g0 * 4) >> 1) : (n0 + g0 * 4);  // output column of the lane's first element in chunk 0 of the tile
 #pragma unroll
   for (int p = 0; p < PASSES; ++p) {
-    const int rr = rr0 + p * (32 / PASSES);
+    const int rr = rr0 + p * 8;
     const uint32_t rsw = (uint32_t)(rr & 7);
     ld_a[p] = stg + (uint32_t)rr * 128u + (((uint32_t)g0 ^ rsw) << 4);
     ld_b[p] = stg + (uint32_t)rr * 128u + (((uint32_t)(g0 + 1) ^ rsw) << 4);
     const long long grow = row0 + rr;
     ok[p] = grow < M;
-    const int oc = (SWIGLU ? (n0 >> 1) : n0) + g0 * 4;
-    cptr[p] = (char*)ep.C + (grow * ep.ldc + oc) * esz;
-    rptr[p] = ep.residual ? ep.residual + grow * ep.ldres + oc : nullptr;
+    cptr[p] = (char*)ep.C + (grow * ep.ldc + oc_lane) * esz;
+    rptr[p] = ep.residual ? ep.residual + grow * ep.ldres + oc_lane : nullptr;
   }
   const int c_begin = chalf * (BN / 2), c_end = (chalf + 1) * (BN / 2);
   uint32_t r[32];
   tmem_ld32(taddr + (uint32_t)c_begin, r);
 #pragma unroll 1
   for (int c = c_begin; c < c_end; c += 32) {
-    tmem_ld_wait32(r);
-    float v[32];
+    const int col0 = n0 + c;                 // first accumulator column of the chunk
+    const int acol = col0 + g0 * 4;          // first accumulator column of this lane
+    const bool vec = col0 + 32 <= N;         // warp-uniform: the whole chunk is inside the matrix
+    float b8[8];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-    if (c + 32 < c_end) tmem_ld32(taddr + (uint32_t)(c + 32), r);
-    const int col0 = n0 + c;
-    if (col0 >= N) continue;  // warp-uniform
-    const bool full = col0 + 32 <= N;
-    if (ep.bias) {
-      if (full) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 t = __ldg(reinterpret_cast<const float4*>(ep.bias + col0) + i);
-          v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (col0 + i < N) v[i] += __ldg(ep.bias + col0 + i);
-      }
-    }
-    if (SWIGLU) {  // row-interleaved gate/up: acc cols (2j, 2j+1) -> out col j
-      if (fast) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = x_sigmoid_fast(v[2 * i], 0.5f) * v[2 * i + 1];
-      } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __fdividef(v[2 * i], 1.0f + __expf(-v[2 * i])) * v[2 * i + 1];
-      }
-    } else if (ep.act == D3D_ACT_QUICK_GELU) {
-      if (fast) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = x_sigmoid_fast(v[i], 0.851f);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __fdividef(v[i], 1.0f + __expf(-1.702f * v[i]));
-      }
-    } else if (ep.act == D3D_ACT_GELU) {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
-    } else if (ep.act == D3D_ACT_SILU) {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = __fdividef(v[i], 1.0f + __expf(-v[i]));
-    } else if (ep.act == D3D_ACT_LEAKY_RELU) {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : 0.01f * v[i];
-    }
-#pragma unroll
-    for (int j = 0; j < CW / 4; ++j)
-      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st_row + (((uint32_t)j ^ sw) << 4)), "f"(v[4 * j]), "f"(v[4 * j + 1]),
-                   "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
-                   : "memory");
-    __syncwarp();
-    const int oc_chunk = SWIGLU ? (c >> 1) : c;                 // output-column offset of this chunk inside the tile
-    const int ocol = (SWIGLU ? (n0 >> 1) : n0) + g0 * 4 + oc_chunk;  // first of this lane's 8 output columns
-    const bool vec = (SWIGLU ? ((col0 >> 1) + CW) : (col0 + CW)) <= n_out;  // warp-uniform: the whole chunk is inside the matrix
-#pragma unroll
-    for (int p = 0; p < PASSES; ++p) {
-      float f[8];
-      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]) : "r"(ld_a[p]));
-      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7]) : "r"(ld_b[p]));
-      if (!ok[p]) continue;
+    for (int i = 0; i < 8; ++i) b8[i] = 0.f;
+    if (ep.bias && col0 < N) {
       if (vec) {
-        if (rptr[p]) {
-          const float4* res = reinterpret_cast<const float4*>(rptr[p] + oc_chunk);
-          const float4 t0 = res[0], t1 = res[1];
-          f[0] += t0.x; f[1] += t0.y; f[2] += t0.z; f[3] += t0.w; f[4] += t1.x; f[5] += t1.y; f[6] += t1.z; f[7] += t1.w;
+        const float4 t0 = __ldg(reinterpret_cast<const float4*>(ep.bias + acol)), t1 = __ldg(reinterpret_cast<const float4*>(ep.bias + acol) + 1);
+        b8[0] = t0.x; b8[1] = t0.y; b8[2] = t0.z; b8[3] = t0.w; b8[4] = t1.x; b8[5] = t1.y; b8[6] = t1.z; b8[7] = t1.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (acol + i < N) b8[i] = __ldg(ep.bias + acol + i);
+      }
+    }
+    tmem_ld_wait32(r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_row + (((uint32_t)j ^ sw) << 4)), "r"(r[4 * j]), "r"(r[4 * j + 1]),
+                   "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
+                   : "memory");
+    if (c + 32 < c_end) tmem_ld32(taddr + (uint32_t)(c + 32), r);  // lands while this chunk is processed
+    __syncwarp();
+    if (col0 < N) {  // warp-uniform
+      const int oc_chunk = SWIGLU ? (c >> 1) : c;  // output-column offset of this chunk inside the tile
+      // straight-line over the lane's 4 x 8 values: all smem loads first, then the arithmetic with 32-way ILP, then the memory operations
+      float f[PASSES][8];
+#pragma unroll
+      for (int p = 0; p < PASSES; ++p) {
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f[p][0]), "=f"(f[p][1]), "=f"(f[p][2]), "=f"(f[p][3]) : "r"(ld_a[p]));
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f[p][4]), "=f"(f[p][5]), "=f"(f[p][6]), "=f"(f[p][7]) : "r"(ld_b[p]));
+      }
+      if (ep.bias) {
+#pragma unroll
+        for (int p = 0; p < PASSES; ++p)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[p][i] += b8[i];
+      }
+      if (SWIGLU) {
+        if (fast) {
+#pragma unroll
+          for (int p = 0; p < PASSES; ++p)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) f[p][i] = x_sigmoid_fast(f[p][2 * i], 0.5f) * f[p][2 * i + 1];
+        } else {
+#pragma unroll
+          for (int p = 0; p < PASSES; ++p)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) f[p][i] = __fdividef(f[p][2 * i], 1.0f + __expf(-f[p][2 * i])) * f[p][2 * i + 1];
+        }
+      } else if (ep.act == D3D_ACT_QUICK_GELU) {
+        if (fast) {
+#pragma unroll
+          for (int p = 0; p < PASSES; ++p)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[p][i] = x_sigmoid_fast(f[p][i], 0.851f);
+        } else {
+#pragma unroll
+          for (int p = 0; p < PASSES; ++p)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[p][i] = __fdividef(f[p][i], 1.0f + __expf(-1.702f * f[p][i]));
+        }
+      } else if (ep.act == D3D_ACT_GELU) {
+#pragma unroll
+        for (int p = 0; p < PASSES; ++p)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[p][i] = gelu_erf(f[p][i]);
+      } else if (ep.act == D3D_ACT_SILU) {
+#pragma unroll
+        for (int p = 0; p < PASSES; ++p)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[p][i] = __fdividef(f[p][i], 1.0f + __expf(-f[p][i]));
+      } else if (ep.act == D3D_ACT_LEAKY_RELU) {
+#pragma unroll
+        for (int p = 0; p < PASSES; ++p)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[p][i] = f[p][i] > 0.f ? f[p][i] : 0.01f * f[p][i];
+      }
+      if (vec) {
+        if (ep.residual) {
+          float4 t[PASSES][2];
+#pragma unroll
+          for (int p = 0; p < PASSES; ++p) {
+            t[p][0] = t[p][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok[p]) {
+              const float4* res = reinterpret_cast<const float4*>(rptr[p] + oc_chunk);
+              t[p][0] = res[0];
+              if (!SWIGLU) t[p][1] = res[1];
+            }
+          }
+#pragma unroll
+          for (int p = 0; p < PASSES; ++p) {
+            f[p][0] += t[p][0].x; f[p][1] += t[p][0].y; f[p][2] += t[p][0].z; f[p][3] += t[p][0].w;
+            f[p][4] += t[p][1].x; f[p][5] += t[p][1].y; f[p][6] += t[p][1].z; f[p][7] += t[p][1].w;
+          }
         }
         if (ep.out_kind == D3D_OUT_F32) {
-          float4* dst = reinterpret_cast<float4*>(cptr[p] + oc_chunk * 4);
-          dst[0] = make_float4(f[0], f[1], f[2], f[3]);
-          dst[1] = make_float4(f[4], f[5], f[6], f[7]);
+#pragma unroll
+          for (int p = 0; p < PASSES; ++p)
+            if (ok[p]) {
+              float4* dst = reinterpret_cast<float4*>(cptr[p] + oc_chunk * 4);
+              dst[0] = make_float4(f[p][0], f[p][1], f[p][2], f[p][3]);
+              if (!SWIGLU) dst[1] = make_float4(f[p][4], f[p][5], f[p][6], f[p][7]);
+            }
+        } else if (ep.out_kind == D3D_BF16) {
+#pragma unroll
+          for (int p = 0; p < PASSES; ++p)
+            if (ok[p]) {
+              if (SWIGLU) *reinterpret_cast<uint2*>(cptr[p] + oc_chunk * 2) = make_uint2(pack16x2(f[p][0], f[p][1], D3D_BF16), pack16x2(f[p][2], f[p][3], D3D_BF16));
+              else *reinterpret_cast<uint4*>(cptr[p] + oc_chunk * 2) = make_uint4(pack16x2(f[p][0], f[p][1], D3D_BF16), pack16x2(f[p][2], f[p][3], D3D_BF16),
+                                                                                 pack16x2(f[p][4], f[p][5], D3D_BF16), pack16x2(f[p][6], f[p][7], D3D_BF16));
+            }
         } else {
-          *reinterpret_cast<uint4*>(cptr[p] + oc_chunk * 2) =
-              make_uint4(pack16x2(f[0], f[1], ep.out_kind), pack16x2(f[2], f[3], ep.out_kind), pack16x2(f[4], f[5], ep.out_kind),
-                         pack16x2(f[6], f[7], ep.out_kind));
+#pragma unroll
+          for (int p = 0; p < PASSES; ++p)
+            if (ok[p]) {
+              if (SWIGLU) *reinterpret_cast<uint2*>(cptr[p] + oc_chunk * 2) = make_uint2(pack16x2(f[p][0], f[p][1], D3D_F16), pack16x2(f[p][2], f[p][3], D3D_F16));
+              else *reinterpret_cast<uint4*>(cptr[p] + oc_chunk * 2) = make_uint4(pack16x2(f[p][0], f[p][1], D3D_F16), pack16x2(f[p][2], f[p][3], D3D_F16),
+                                                                                 pack16x2(f[p][4], f[p][5], D3D_F16), pack16x2(f[p][6], f[p][7], D3D_F16));
+            }
         }
-      } else {
-        for (int i = 0; i < 8 && ocol + i < n_out; ++i) {
-          float x = f[i];
-          if (rptr[p]) x += rptr[p][oc_chunk + i];
-          if (ep.out_kind == D3D_OUT_F32) reinterpret_cast<float*>(cptr[p])[oc_chunk + i] = x;
-          else st16(cptr[p], (size_t)(oc_chunk + i), x, ep.out_kind);
+      } else {  // ragged last columns: scalar
+        const int ocol = oc_lane + oc_chunk;
+#pragma unroll
+        for (int p = 0; p < PASSES; ++p) {
+#pragma unroll
+          for (int i = 0; i < OW; ++i) {
+            if (ok[p] && ocol + i < n_out) {
+              float x = f[p][i];
+              if (rptr[p]) x += rptr[p][oc_chunk + i];
+              if (ep.out_kind == D3D_OUT_F32) reinterpret_cast<float*>(cptr[p])[oc_chunk + i] = x;
+              else st16(cptr[p], (size_t)(oc_chunk + i), x, ep.out_kind);
+            }
+          }
         }
       }
     }
     __syncwarp();  // the smem tile is rewritten by the next chunk
   }
+}
+
+// Tile order: column groups of RASTER_GW n-tiles are swept over all m-tiles before the next group starts, so the CTAs running at the
+// same time touch ~GW W-tiles and ~#CTAs/GW A-tiles (instead of one A tile and every W tile): the W slice of a group stays in L2
+// while it is reused by every m-tile (Phi-3 gate/up: 100 MB of weights no longer stream through L2 once per m-tile).
+constexpr int RASTER_GW = 8;
+__device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int& tm, int& tn) {
+  const int group_tiles = RASTER_GW * tiles_m;
+  const int grp = tile / group_tiles, rem = tile - grp * group_tiles;
+  const int left = tiles_n - grp * RASTER_GW;
+  const int gw = left < RASTER_GW ? left : RASTER_GW;
+  tm = rem / gw;
+  tn = grp * RASTER_GW + (rem - tm * gw);
 }
 
 template <int BN, int CTAS>
@@ -390,8 +455,10 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
-        const int m0 = (tile / tiles_n) * TM + (int)cta_rank * BM;
-        const int n0 = (tile % tiles_n) * BN + (int)cta_rank * C::B_ROWS;
+        int tm, tn;
+        tile_coords(tile, tiles_m, tiles_n, tm, tn);
+        const int m0 = tm * TM + (int)cta_rank * BM;
+        const int n0 = tn * BN + (int)cta_rank * C::B_ROWS;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
@@ -455,8 +522,10 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
     for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-      const int m0 = (tile / tiles_n) * TM + (int)cta_rank * BM;
-      const int n0 = (tile % tiles_n) * BN;
+      int tm, tn;
+      tile_coords(tile, tiles_m, tiles_n, tm, tn);
+      const int m0 = tm * TM + (int)cta_rank * BM;
+      const int n0 = tn * BN;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
