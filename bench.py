@@ -172,7 +172,7 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # this engine
 # ------------------------------------------------------------------------------------------------
-def build_engine(episodes):
+def build_engine(episodes, n_steps=16):
     from dynam3d_b200.policy import Dynam3D_VLN
     net = Dynam3D_VLN(q1_fix=True, q7_fix=True)  # 12-view panorama: per-view depth / heading (the literal Q1/Q7 paths only make sense at V=1)
     net.load_policy_state_dict(synth.policy_state_dict(WEIGHT_SEED, merge_bias=0.3))
@@ -181,6 +181,7 @@ def build_engine(episodes):
     net.llava.load_state_dict(synth.llava_state_dict(WEIGHT_SEED, clip_layers=24, lm_layers=32, device="cuda", lm_round_to=torch.float16),
                               max_images=episodes, max_tokens=episodes * 1100)
     net.feature_fields.reset(episodes)
+    net.feature_fields.reserve(patches=n_steps * VIEWS * 576, instances=4096)  # the rollout horizon is known: no pool growth inside the timed region
     net.tokenize = synth.ToyTokenizer()
     return net
 
@@ -196,9 +197,9 @@ def run_engine(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     E = args.episodes
-    net = build_engine(E)
-    instr = [synth.make_instruction(rank * 100 + b, INSTR_CHARS) for b in range(E)]
     n_total = args.warmup + 2 * args.steps
+    net = build_engine(E, n_total)
+    instr = [synth.make_instruction(rank * 100 + b, INSTR_CHARS) for b in range(E)]
     steps = make_inputs(rank, n_total, E)
     dev = torch.device("cuda", local)
     # device-resident copies for the kernel-side number, pinned host copies for the end-to-end number

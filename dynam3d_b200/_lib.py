@@ -62,6 +62,8 @@ SIGNATURES = {
     "d3d_unproject_habitat": [_P, _P, _I, _I, _I, _FP, _FP, _FP, _F, _P, _P, _P, _P],
     "d3d_patch_3d_info": [_P, _I, _I, _I, _FP, _FP, _FP, _F, _P, _P],
     "d3d_frustum_cull": [_P, _P, _P, _P, _I, _I, _P, _I, _I, _I, _P, _F, _F, _F, _F, _F, _F, _F, _P, _P, _P],
+    "d3d_frustum_cull_matrix": [_P, _P, _P, _P, _I, _I, _P, _I, _I, _I, _P, _F, _F, _F, _P, _P, _P],
+    "d3d_unproject_pinhole": [_P, _I, _I, _I, _P, _I, _I, _IP, _IP, _F, _F, _F, _P, _P, _P, _P, _P],
     "d3d_knn3d": [_P, _I, _P, _I, _I, _P, _P, _P],
     "d3d_seq_centroid": [_P, _P, _P, _I, _P, _P],
     "d3d_env_export": [_P, _P, _P, _I, _P, _F, _I, _P, _P, _P, _P],
@@ -69,6 +71,7 @@ SIGNATURES = {
     "d3d_layernorm": [_P, _L, _P, _P, _P, _F, _I, _I, _I, _P, _L, _P, _L, _I, _P],
     "d3d_rmsnorm": [_P, _L, _P, _P, _F, _I, _I, _P, _L, _P, _L, _I, _P],
     "d3d_rope": [_P, _L, _P, _P, _I, _I, _I, _I, _P],
+    "d3d_rope_table": [_P, _P, _I, _I, _P, _P], "d3d_rope_apply": [_P, _L, _P, _I, _I, _I, _I, _P],
     "d3d_embed_gather": [_P, _I, _P, _I, _I, _P, _L, _P],
     "d3d_preprocess_im2col": [_P, _I, _I, _I, _I, _I, _FP, _FP, _P, _I, _I, _P],
     "d3d_vit_embed_ln": [_P, _P, _P, _P, _P, _F, _I, _I, _I, _P, _P],
@@ -94,6 +97,7 @@ SIGNATURES = {
     "d3d_ffh_create": [_I, _I, _F], "d3d_ffh_destroy": [_P], "d3d_ffh_reset": [_P, _I], "d3d_ffh_pop": [_P, _I],
     "d3d_ffh_counts": [_P, _I, _P], "d3d_ffh_cull": [_P, _I, _P, _L, _P, _P, _P, _P], "d3d_ffh_set_tree": [_P],
     "d3d_ffh_begin_view": [_P] * 3 + [_I] + [_P] * 11,
+    "d3d_ffh_begin_step": [_P] * 3 + [_I, _I] + [_P] * 9, "d3d_ffh_begin_view_refs": [_P, _I, _P],
     "d3d_ffh_finish_view": [_P, _P, _P, _P], "d3d_ffh_fetch_view": [_P] * 17, "d3d_ffh_zone_key_array": [_P, _I, _P],
     "d3d_ffh_get_map": [_P, _I, _I, _P, _P, _P, _P], "d3d_ffh_get_p2i": [_P, _I, _P], "d3d_ffh_get_patch_pos": [_P, _I, _P],
     "d3d_ffh_get_zone_keys": [_P, _I, _P, _P, _P], "d3d_ffh_get_last": [_P, _I, _P, _P, _P, _P],

@@ -91,6 +91,10 @@ struct FFH {
   int P = 0;
   std::vector<std::vector<std::vector<int>>> splits;  // [b][g] -> view-local patch indices (ascending)
   std::vector<int> seq_start;                          // [B+1]
+  int res_base = 0;                                    // sequence index of the first row of the `res` array handed to finish_view
+  // whole-step plan (begin_step): splits / sequence starts of every view, sequences numbered globally in (view, episode, segment) order
+  std::vector<std::vector<std::vector<std::vector<int>>>> step_splits;  // [V][b][g]
+  std::vector<std::vector<int>> step_seq_start;                        // [V][B+1]
   ViewPlan plan;
 };
 
@@ -402,7 +406,88 @@ extern "C" int d3d_ffh_begin_view(void* h, const float* xyz, const int64_t* segm
     }
   }
   H.seq_start[(size_t)B] = n_seq;
+  H.res_base = 0;
   info[0] = n_seq; info[1] = max_len;
+  return 0;
+}
+
+// Whole-step variant of begin_view: the patch -> instance pooling of a view does not depend on the memory state, so ALL views of a step
+// are planned (and pooled on the device) in one packed batch; only the K-NN / merge / zone part stays per view (begin_view_refs).
+//   xyz [V,B,P,3], segm [V,B,P]; stage row of (episode b, view ix, patch p) = (b*V + ix)*P + p.
+// Outputs: base_rows[B] (first pool row of the step's patches; view ix starts at base + ix*P), view_seq_start[V+1], seq_owner[n_seq],
+//   members[V*B*P], cu_m[n_seq+1], tok_src / tok_seq [V*B*P + n_seq], cu_tok[n_seq+1]; info[0] = n_seq, info[1] = max sequence length.
+extern "C" int d3d_ffh_begin_step(void* h, const float* xyz, const int64_t* segm, int P, int V, int64_t* base_rows, int* view_seq_start,
+                                  int* seq_owner, int* members, int* cu_m, int* tok_src, int* tok_seq, int* cu_tok, int* info) {
+  FFH& H = HH(h);
+  const int B = (int)H.eps.size();
+  H.P = P;
+  H.step_splits.assign((size_t)V, {});
+  H.step_seq_start.assign((size_t)V, std::vector<int>((size_t)B + 1, 0));
+  for (int b = 0; b < B; ++b) {
+    Episode& ep = H.eps[(size_t)b];
+    base_rows[b] = ep.n_patch;
+    for (int ix = 0; ix < V; ++ix) {
+      const float* src = xyz + ((size_t)ix * B + b) * P * 3;
+      ep.patch_pos.insert(ep.patch_pos.end(), src, src + (size_t)P * 3);
+    }
+    ep.n_patch += (i64)P * V;
+    if (ep.p2i.size() < (size_t)ep.n_patch) ep.p2i.resize((size_t)ep.n_patch, -1);
+  }
+  int n_seq = 0, max_len = 0;
+  size_t mpos = 0, tpos = 0;
+  cu_m[0] = 0; cu_tok[0] = 0;
+  for (int ix = 0; ix < V; ++ix) {
+    view_seq_start[ix] = n_seq;
+    auto& vs = H.step_splits[(size_t)ix];
+    vs.assign((size_t)B, {});
+    for (int b = 0; b < B; ++b) {
+      const int64_t* sg = segm + ((size_t)ix * B + b) * P;
+      int G = 0;
+      for (int p = 0; p < P; ++p) {
+        D3D_REQUIRE(sg[p] >= 0 && sg[p] < P, "segment label out of range");
+        G = std::max(G, (int)sg[p] + 1);
+      }
+      auto& sp = vs[(size_t)b];
+      sp.assign((size_t)G, {});
+      for (int p = 0; p < P; ++p) sp[(size_t)sg[p]].push_back(p);
+      H.step_seq_start[(size_t)ix][(size_t)b] = n_seq;
+      const long long stage0 = ((long long)b * V + ix) * P;
+      for (int g = 0; g < G; ++g) {
+        D3D_REQUIRE(!sp[(size_t)g].empty(), "patch_segm labels must be dense 0..G-1 (FF:411-422 relabels them)");
+        seq_owner[n_seq] = b;
+        tok_src[tpos] = -1; tok_seq[tpos] = n_seq; ++tpos;
+        for (int p : sp[(size_t)g]) {
+          const int row = (int)(stage0 + p);
+          members[mpos++] = row;
+          tok_src[tpos] = row; tok_seq[tpos] = n_seq; ++tpos;
+        }
+        max_len = std::max(max_len, (int)sp[(size_t)g].size() + 1);
+        ++n_seq;
+        cu_m[n_seq] = (int)mpos;
+        cu_tok[n_seq] = (int)tpos;
+      }
+    }
+    H.step_seq_start[(size_t)ix][(size_t)B] = n_seq;
+  }
+  view_seq_start[V] = n_seq;
+  info[0] = n_seq; info[1] = max_len;
+  return 0;
+}
+
+// Makes view `ix` of the step planned by begin_step the view in flight: n_ref[s] (instance slots the K-NN of sequence s searches, 0 = no
+// tree yet) for the view's sequences, in order.  finish_view then expects `res` rows of exactly these sequences.
+extern "C" int d3d_ffh_begin_view_refs(void* h, int ix, int* n_ref) {
+  FFH& H = HH(h);
+  D3D_REQUIRE(ix >= 0 && ix < (int)H.step_splits.size(), "view index");
+  const int B = (int)H.eps.size();
+  H.splits = H.step_splits[(size_t)ix];
+  H.seq_start = H.step_seq_start[(size_t)ix];
+  H.res_base = H.seq_start[0];
+  for (int b = 0; b < B; ++b) {
+    const Episode& ep = H.eps[(size_t)b];
+    const int nref = ep.tree ? (int)ep.n_inst : 0;
+    for (int s = H.seq_start[(size_t)b]; s < H.seq_start[(size_t)b + 1]; ++s) n_ref[s - H.res_base] = nref;
+  }
   return 0;
 }
 
@@ -419,7 +504,7 @@ extern "C" int d3d_ffh_finish_view(void* h, const float* res, int* sizes, int64_
     std::vector<float> cen((size_t)G * 3), d2((size_t)G * 2), lg((size_t)G * 4);
     std::vector<int> idx((size_t)G * 2);
     for (int g = 0; g < G; ++g) {
-      const float* r = res + (size_t)(s0 + g) * 12;
+      const float* r = res + (size_t)(s0 - H.res_base + g) * 12;
       memcpy(&cen[(size_t)g * 3], r, 12);
       memcpy(&d2[(size_t)g * 2], r + 3, 8);
       memcpy(&idx[(size_t)g * 2], r + 5, 8);

@@ -180,6 +180,88 @@ __global__ void frustum_cull_kernel(float* __restrict__ xyz, float* __restrict__
   if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(n_deleted, __popc(ballot));
 }
 
+// Posed-dataset form of the cull (get_frustum_mask FF:64-84 + z-test FF:349-353): cam row = [view matrix 4x4 row-major (world -> camera) |
+// intrinsics 3x3 row-major] fp32.  The two einsums are left-to-right fp32 sums of separately rounded products (oracle/geometry.py).
+__global__ void frustum_cull_matrix_kernel(float* __restrict__ xyz, float* __restrict__ dir, float* __restrict__ scale,
+                                           const float* __restrict__ depth, const float* __restrict__ cam, CullParams p, int n,
+                                           uint8_t* __restrict__ mask, int* __restrict__ n_deleted) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool del = false;
+  if (i < n) {
+    const float x = xyz[(size_t)i * 3], y = xyz[(size_t)i * 3 + 1], z = xyz[(size_t)i * 3 + 2];
+    for (int v = 0; v < p.n_views && !del; ++v) {
+      const float* M = cam + v * 25;
+      const float* K = M + 16;
+      float vw[3];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+        vw[r] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(M[r * 4], x), __fmul_rn(M[r * 4 + 1], y)), __fmul_rn(M[r * 4 + 2], z)), M[r * 4 + 3]);
+      float uv[3];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+        uv[r] = __fadd_rn(__fadd_rn(__fmul_rn(K[r * 3], vw[0]), __fmul_rn(K[r * 3 + 1], vw[1])), __fmul_rn(K[r * 3 + 2], vw[2]));
+      const float uf = __fdiv_rn(uv[0], uv[2]), vf = __fdiv_rn(uv[1], uv[2]);
+      if (!(isfinite(uf) && isfinite(vf))) continue;
+      const float ut = truncf(uf), vt = truncf(vf);
+      const float vz = vw[2];
+      if (!(vz >= p.near_ && vz <= p.far_)) continue;
+      if (!(ut >= 0.0f && ut <= (float)(p.W - 1) && vt >= 0.0f && vt <= (float)(p.H - 1))) continue;
+      const int ui = (int)ut, vi = (int)vt;
+      const float cd = depth[((size_t)v * p.H + vi) * p.W + ui];
+      if (vz < __fadd_rn(cd, p.eps)) del = true;
+    }
+    mask[i] = del ? 1 : 0;
+    if (del) {
+      xyz[(size_t)i * 3] = -10000.0f;
+      xyz[(size_t)i * 3 + 1] = -10000.0f;
+      xyz[(size_t)i * 3 + 2] = -10000.0f;
+      dir[i] = 0.0f;
+      scale[i] = 0.0f;
+    }
+  }
+  const unsigned ballot = __ballot_sync(0xffffffffu, del);
+  if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(n_deleted, __popc(ballot));
+}
+
+// ------------------------------------------------------------------------------------------------
+// a4': posed-dataset unprojection (project_depth_to_3d FF:50-60 = open3d create_from_depth_image + nearest resize; rigid transform,
+// heading and scale FF:536-546).  One thread per (view, grid patch).  vp [n,16] double = fx, fy, cx, cy, R (9, row-major), T (3).
+// open3d arithmetic: z = float(u16)/float(depth_scale) (>= depth_trunc -> 0), x = (u-cx)*z/fx, y = (v-cy)*z/fy in double; the points are
+// rounded to fp32 (FF:538) before R @ p + T in double; direction = -asin(dx/|xy|) (-pi if dy < 0), all rounded to fp32 at the end.
+// ------------------------------------------------------------------------------------------------
+__global__ void unproject_pinhole_kernel(const uint16_t* __restrict__ depth, int n, int H, int W, const double* __restrict__ vp, GridIdx gi,
+                                         int gh, int gw, float depth_scale, float depth_trunc, float tan_abs, float* __restrict__ xyz,
+                                         float* __restrict__ dir, float* __restrict__ scale, int* __restrict__ n_invalid) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * gh * gw) return;
+  const int view = idx / (gh * gw), pp = idx - view * gh * gw;
+  const int r = gi.r[pp / gw], c = gi.c[pp % gw];
+  unsigned d = depth[((size_t)view * H + r) * W + c];
+  if (d == 0) d = 1;  // FF:51
+  float z32 = __fdiv_rn((float)d, depth_scale);
+  if (z32 >= depth_trunc) z32 = 0.f;
+  if (!(z32 > 0.f)) atomicAdd(n_invalid, 1);  // open3d drops the pixel; the reference's view(H,W,3) then raises
+  const double* q = vp + (size_t)view * 16;
+  const double z = (double)z32;
+  const double x = __ddiv_rn(__dmul_rn((double)c - q[2], z), q[0]);
+  const double y = __ddiv_rn(__dmul_rn((double)r - q[3], z), q[1]);
+  const float px = (float)x, py = (float)y, pz = z32;
+  scale[idx] = __fdiv_rn(__fmul_rn(__fmul_rn(pz, tan_abs), 2.0f), (float)gw);
+  const double X = (double)px, Y = (double)py, Z = (double)pz;
+  double w[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    w[k] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(q[4 + 3 * k], X), __dmul_rn(q[5 + 3 * k], Y)), __dmul_rn(q[6 + 3 * k], Z)), q[13 + k]);
+  xyz[(size_t)idx * 3] = (float)w[0];
+  xyz[(size_t)idx * 3 + 1] = (float)w[1];
+  xyz[(size_t)idx * 3 + 2] = (float)w[2];
+  double xy = sqrt(__dadd_rn(__dmul_rn(w[0], w[0]), __dmul_rn(w[1], w[1])));
+  if (xy < 1e-4) xy = 1e-4;
+  double h = -asin(w[0] / xy);
+  if (w[1] < 0.0) h = h - 3.14159265358979323846;
+  dir[idx] = (float)h;
+}
+
 // zero the fp16 feature rows of culled patches (FF:358); one warp per row
 __global__ void zero_rows_kernel(uint16_t* __restrict__ fts, const uint8_t* __restrict__ mask, int n, int row_halves) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -461,6 +543,40 @@ extern "C" int d3d_frustum_cull(float* xyz, float* dir, float* scale, void* fts1
     zero_rows_kernel<<<d3d_cdiv((long long)n_patches * 32, 256), 256, 0, st>>>((uint16_t*)fts16, mask, n_patches, fts_dim);
     D3D_CHECK_LAUNCH();
   }
+  return 0;
+}
+
+extern "C" int d3d_frustum_cull_matrix(float* xyz, float* dir, float* scale, void* fts16, int n_patches, int fts_dim, const float* depth,
+                                       int n_views, int H, int W, const float* cam25, float near_, float far_, float eps, uint8_t* mask,
+                                       int* n_deleted, void* stream) {
+  D3D_REQUIRE(xyz && dir && scale && depth && cam25 && mask && n_deleted, "args");
+  D3D_REQUIRE(fts16 == nullptr || fts_dim % 8 == 0, "feature rows must be multiples of 16 B");
+  cudaStream_t st = (cudaStream_t)stream;
+  D3D_CHECK_CUDA(cudaMemsetAsync(n_deleted, 0, sizeof(int), st));
+  if (n_patches == 0) return 0;
+  CullParams p{0.f, 0.f, 0.f, 0.f, near_, far_, eps, H, W, n_views};
+  frustum_cull_matrix_kernel<<<d3d_cdiv(n_patches, 256), 256, 0, st>>>(xyz, dir, scale, depth, cam25, p, n_patches, mask, n_deleted);
+  D3D_CHECK_LAUNCH();
+  if (fts16) {
+    zero_rows_kernel<<<d3d_cdiv((long long)n_patches * 32, 256), 256, 0, st>>>((uint16_t*)fts16, mask, n_patches, fts_dim);
+    D3D_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+extern "C" int d3d_unproject_pinhole(const uint16_t* depth, int n_views, int H, int W, const double* view_params, int gh, int gw,
+                                     const int* row_idx_h, const int* col_idx_h, float depth_scale, float depth_trunc, float tan_abs,
+                                     float* xyz, float* dir, float* scale, int* n_invalid, void* stream) {
+  D3D_REQUIRE(depth && view_params && row_idx_h && col_idx_h && xyz && dir && scale && n_invalid, "args");
+  D3D_REQUIRE(gh <= 32 && gw <= 32 && gh > 0 && gw > 0, "grid up to 32x32");
+  cudaStream_t st = (cudaStream_t)stream;
+  D3D_CHECK_CUDA(cudaMemsetAsync(n_invalid, 0, sizeof(int), st));
+  if (n_views == 0) return 0;
+  GridIdx gi;
+  for (int i = 0; i < 32; ++i) { gi.r[i] = i < gh ? row_idx_h[i] : 0; gi.c[i] = i < gw ? col_idx_h[i] : 0; }
+  unproject_pinhole_kernel<<<d3d_cdiv((long long)n_views * gh * gw, 256), 256, 0, st>>>(depth, n_views, H, W, view_params, gi, gh, gw, depth_scale,
+                                                                                        depth_trunc, tan_abs, xyz, dir, scale, n_invalid);
+  D3D_CHECK_LAUNCH();
   return 0;
 }
 

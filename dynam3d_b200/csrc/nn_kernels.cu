@@ -119,8 +119,46 @@ __global__ void rope_kernel(void* __restrict__ qkv, long long ld, const int* __r
   sincosf(ang, &sn, &cs);
   const size_t base = (size_t)t * ld + (size_t)h * Dh;
   const float a = ld16(qkv, base + i, kind), b = ld16(qkv, base + i + half, kind);
-  st16(qkv, base + i, a * cs - b * sn, kind);
-  st16(qkv, base + i + half, b * cs + a * sn, kind);
+  // products rounded separately (no FMA contraction), as in x*cos + rotate_half(x)*sin evaluated by PyTorch
+  st16(qkv, base + i, __fsub_rn(__fmul_rn(a, cs), __fmul_rn(b, sn)), kind);
+  st16(qkv, base + i + half, __fadd_rn(__fmul_rn(b, cs), __fmul_rn(a, sn)), kind);
+}
+
+// The same rotation from a per-token cos/sin table (built once per prefill, reused by all 32 layers), 8 elements per thread:
+// tab [T, Dh] fp32 = [cos(pos*inv_freq[0..half)) | sin(...)]; 16-bit QKV only.  Same sincosf on the same angle as rope_kernel.
+__global__ void rope_table_kernel(const int* __restrict__ pos, const float* __restrict__ inv_freq, int T, int half, float* __restrict__ tab) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= T * half) return;
+  const int t = idx / half, i = idx - t * half;
+  float sn, cs;
+  sincosf((float)pos[t] * inv_freq[i], &sn, &cs);
+  tab[(size_t)t * 2 * half + i] = cs;
+  tab[(size_t)t * 2 * half + half + i] = sn;
+}
+
+__global__ void rope_apply_kernel(uint16_t* __restrict__ qkv, long long ld, const float* __restrict__ tab, int T, int H, int Dh, int kind) {
+  const int half = Dh / 2, groups = half / 8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)T * 2 * H * groups) return;
+  const int g = (int)(idx % groups);
+  const int h = (int)((idx / groups) % (2 * H));  // q heads then k heads
+  const int t = (int)(idx / ((long long)groups * 2 * H));
+  uint16_t* base = qkv + (size_t)t * ld + (size_t)h * Dh + g * 8;
+  const float4* cs = reinterpret_cast<const float4*>(tab + (size_t)t * Dh + g * 8);
+  const float4* sn = reinterpret_cast<const float4*>(tab + (size_t)t * Dh + half + g * 8);
+  const float4 c0 = cs[0], c1 = cs[1], s0 = sn[0], s1 = sn[1];
+  const float c[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w}, s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+  const uint4 av = *reinterpret_cast<const uint4*>(base), bv = *reinterpret_cast<const uint4*>(base + half);
+  const uint32_t aw[4] = {av.x, av.y, av.z, av.w}, bw[4] = {bv.x, bv.y, bv.z, bv.w};
+  uint32_t ao[4], bo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 a = unpack16x2(aw[j], kind), b = unpack16x2(bw[j], kind);
+    ao[j] = pack16x2(__fsub_rn(__fmul_rn(a.x, c[2 * j]), __fmul_rn(b.x, s[2 * j])), __fsub_rn(__fmul_rn(a.y, c[2 * j + 1]), __fmul_rn(b.y, s[2 * j + 1])), kind);
+    bo[j] = pack16x2(__fadd_rn(__fmul_rn(b.x, c[2 * j]), __fmul_rn(a.x, s[2 * j])), __fadd_rn(__fmul_rn(b.y, c[2 * j + 1]), __fmul_rn(a.y, s[2 * j + 1])), kind);
+  }
+  *reinterpret_cast<uint4*>(base) = make_uint4(ao[0], ao[1], ao[2], ao[3]);
+  *reinterpret_cast<uint4*>(base + half) = make_uint4(bo[0], bo[1], bo[2], bo[3]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -322,6 +360,25 @@ extern "C" int d3d_rope(void* qkv, int64_t ld, const int* pos, const float* inv_
   D3D_REQUIRE(qkv && pos && inv_freq && Dh % 2 == 0, "args");
   const long long total = (long long)T * 2 * H * (Dh / 2);
   rope_kernel<<<d3d_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(qkv, ld, pos, inv_freq, T, H, Dh, kind);
+  D3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int d3d_rope_table(const int* pos, const float* inv_freq, int T, int Dh, float* tab, void* stream) {
+  if (T == 0) return 0;
+  D3D_REQUIRE(pos && inv_freq && tab && Dh % 2 == 0, "args");
+  rope_table_kernel<<<d3d_cdiv((long long)T * (Dh / 2), 256), 256, 0, (cudaStream_t)stream>>>(pos, inv_freq, T, Dh / 2, tab);
+  D3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int d3d_rope_apply(void* qkv, int64_t ld, const float* tab, int T, int H, int Dh, int kind, void* stream) {
+  if (T == 0) return 0;
+  D3D_REQUIRE(qkv && tab, "args");
+  D3D_REQUIRE(kind == D3D_F16 || kind == D3D_BF16, "16-bit QKV only (fp32 buffers use d3d_rope)");
+  D3D_REQUIRE(Dh % 16 == 0 && ld % 8 == 0 && ((uintptr_t)qkv % 16) == 0 && ((uintptr_t)tab % 16) == 0, "16-byte vectors");
+  const long long total = (long long)T * 2 * H * (Dh / 16);
+  rope_apply_kernel<<<d3d_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((uint16_t*)qkv, ld, tab, T, H, Dh, kind);
   D3D_CHECK_LAUNCH();
   return 0;
 }

@@ -69,15 +69,17 @@ class _Pool:
 class _Episode:
     """Device pools of one episode.  The integer state (ids, member lists, zone keys) lives in the C++ planner (ff_host.cu)."""
 
-    def __init__(self, device):
-        self.patch_pos = _Pool(3, torch.float32, device, 8192)
-        self.patch_dir = _Pool(0, torch.float32, device, 8192)
-        self.patch_scale = _Pool(0, torch.float32, device, 8192)
-        self.patch_fts = _Pool(D, torch.float16, device, 8192)
-        self.inst_pos = _Pool(3, torch.float32, device, 1024)
-        self.inst_fts = _Pool(D, torch.float32, device, 1024)
-        self.zone_pos = _Pool(3, torch.float32, device, 256)
-        self.zone_fts = _Pool(D, torch.float32, device, 256)
+    def __init__(self, device, patch_cap=65536, inst_cap=4096, zone_cap=512):
+        # sized for HBM3e: 65 536 patches (113 steps of one view, 9 twelve-view steps) = 101 MB of fp16 features per episode; growth past
+        # the capacity reallocates (cudaMalloc + copy, tens of ms), so callers that know the horizon pass it to Feature_Fields.reserve()
+        self.patch_pos = _Pool(3, torch.float32, device, patch_cap)
+        self.patch_dir = _Pool(0, torch.float32, device, patch_cap)
+        self.patch_scale = _Pool(0, torch.float32, device, patch_cap)
+        self.patch_fts = _Pool(D, torch.float16, device, patch_cap)
+        self.inst_pos = _Pool(3, torch.float32, device, inst_cap)
+        self.inst_fts = _Pool(D, torch.float32, device, inst_cap)
+        self.zone_pos = _Pool(3, torch.float32, device, zone_cap)
+        self.zone_fts = _Pool(D, torch.float32, device, zone_cap)
         self.n_patch = self.n_inst = self.n_zone = 0
         self.tree = False
 
@@ -124,6 +126,14 @@ class Feature_Fields(nn.Module):
             self._h = L.lib().d3d_ffh_create(batch_size, self.args.num_proposal_instances, self.args.zone_x_length)
         self.keep_target_waypoint = [None for _ in range(batch_size)]
         self.history_actions = [["none\n"] * 4] * batch_size  # Q10: the reference aliases one list across the batch
+
+    def reserve(self, patches=0, instances=0, zones=0):
+        """Grow every episode's pools up front (e.g. steps x views x 576 patches) so no reallocation happens inside a rollout."""
+        for ep in self.eps:
+            for pool in (ep.patch_pos, ep.patch_dir, ep.patch_scale, ep.patch_fts):
+                pool.ensure(patches)
+            ep.inst_pos.ensure(instances); ep.inst_fts.ensure(instances)
+            ep.zone_pos.ensure(zones); ep.zone_fts.ensure(zones)
 
     def pop(self, index):
         self.batch_size -= 1
@@ -443,27 +453,46 @@ class Feature_Fields(nn.Module):
     # ------------------------------------------------------------------ FF:329-396
     def delete_old_features_from_camera_frustum(self, batch_depth, batch_position=None, batch_heading=None, batch_camera_intrinsic=None,
                                                 batch_extrinsic=None, num_of_views=1):
-        """batch_depth [B,V,H,W] metres (device tensor preferred).  Habitat branch only (batch_position given)."""
-        if batch_extrinsic is not None or batch_position is None:
-            raise NotImplementedError("posed-dataset branch (FF:343-344) is outside the hot path built here")
-        depth = self._as_dev(batch_depth, torch.float32).contiguous()
+        """Habitat branch (batch_position / batch_heading given): batch_depth [B,V,H,W] metres (device tensor preferred).
+        Posed-dataset branch (batch_camera_intrinsic / batch_extrinsic given, FF:343-344): batch_depth[b] [V,H,W] fp32 in the unit of the
+        stored points, batch_camera_intrinsic[b][ix] [>=3,>=3], batch_extrinsic[b][ix] [4,4] world->camera; the far plane is
+        get_frustum_mask's default 2.0 (the VLN call site does not pass `far`)."""
+        posed = batch_extrinsic is not None
+        if not posed and batch_position is None:
+            raise ValueError("either batch_position/batch_heading (habitat) or batch_camera_intrinsic/batch_extrinsic (posed datasets) is required")
         V = num_of_views
         lib = L.lib()
         with L.stream_scope():
             if not any(ep.n_patch for ep in self.eps):
                 L.check(lib.d3d_ffh_set_tree(self._h))
                 return
-            cams = np.concatenate([ops.camera_rows(batch_position[b], [float(batch_heading[b]) + (ix * (-math.pi / 6) if self.q7_fix else 0.0)
-                                                                      for ix in range(V)]) for b in range(self.batch_size)], 0)  # Q7
-            cam_d = self._upload([cams])[0]
             masks = []
-            for b, ep in enumerate(self.eps):
-                if ep.n_patch == 0:
-                    masks.append(None)
-                    continue
-                m, _ = ops.frustum_cull(ep.patch_pos.t, ep.patch_dir.t, ep.patch_scale.t, ep.patch_fts.t, ep.n_patch, depth[b], cam_d[b * V:(b + 1) * V],
-                                        self.args.input_hfov, self.args.input_vfov, 0.0, self.args.deleted_frustum_distance, 0.1)
-                masks.append(m.to("cpu", non_blocking=True))
+            if posed:
+                for b, ep in enumerate(self.eps):
+                    if ep.n_patch == 0:
+                        masks.append(None)
+                        continue
+                    depth_b = self._as_dev(batch_depth[b], torch.float32).contiguous()
+                    Vb = depth_b.shape[0]
+                    cam25 = np.zeros((Vb, 25), F32)
+                    for ix in range(Vb):
+                        cam25[ix, :16] = np.asarray(torch.as_tensor(batch_extrinsic[b][ix]).cpu(), F32).reshape(16)
+                        cam25[ix, 16:] = np.asarray(torch.as_tensor(batch_camera_intrinsic[b][ix]).cpu(), F32)[:3, :3].reshape(9)
+                    m, _ = ops.frustum_cull_matrix(ep.patch_pos.t, ep.patch_dir.t, ep.patch_scale.t, ep.patch_fts.t, ep.n_patch, depth_b,
+                                                   self._upload([cam25])[0], 0.0, 2.0, 0.1)
+                    masks.append(m.to("cpu", non_blocking=True))
+            else:
+                depth = self._as_dev(batch_depth, torch.float32).contiguous()
+                cams = np.concatenate([ops.camera_rows(batch_position[b], [float(batch_heading[b]) + (ix * (-math.pi / 6) if self.q7_fix else 0.0)
+                                                                          for ix in range(V)]) for b in range(self.batch_size)], 0)  # Q7
+                cam_d = self._upload([cams])[0]
+                for b, ep in enumerate(self.eps):
+                    if ep.n_patch == 0:
+                        masks.append(None)
+                        continue
+                    m, _ = ops.frustum_cull(ep.patch_pos.t, ep.patch_dir.t, ep.patch_scale.t, ep.patch_fts.t, ep.n_patch, depth[b], cam_d[b * V:(b + 1) * V],
+                                            self.args.input_hfov, self.args.input_vfov, 0.0, self.args.deleted_frustum_distance, 0.1)
+                    masks.append(m.to("cpu", non_blocking=True))
             torch.cuda.current_stream().synchronize()
             pp_i, fp_i, pp_z, fp_z = [], [], [], []
             nd = (ctypes.c_int * 2)()
@@ -497,83 +526,130 @@ class Feature_Fields(nn.Module):
     def update_feature_fields(self, batch_depth, batch_grid_ft, batch_image=None, batch_position=None, batch_heading=None,
                               batch_camera_intrinsic=None, batch_rot=None, batch_trans=None, depth_scale=1000.0, depth_trunc=1000.0,
                               num_of_views=1, batch_patch_segm=None):
-        """batch_depth [B,V,576] metres; batch_grid_ft [B,V,576,768] (device fp16 preferred); batch_patch_segm [B,V,24,24]
-        dense int labels (or `self.segmenter(batch_image)` is called, standing in for FastSAM, FF:509)."""
-        if batch_camera_intrinsic is not None or batch_position is None:
-            raise NotImplementedError("posed-dataset branch (FF:501-546) is outside the hot path built here")
-        B, V = self.batch_size, num_of_views
+        """Habitat branch: batch_depth [B,V,576] metres; batch_grid_ft [B,V,576,768] (device fp16 preferred); batch_patch_segm [B,V,24,24]
+        dense int labels (or `self.segmenter(batch_image)` is called, standing in for FastSAM, FF:509).
+        Posed-dataset branch (batch_camera_intrinsic given, FF:501-546): batch_depth[b] [V,H,W] uint16-valued raw depth, batch_camera_intrinsic[b][ix]
+        [>=3,>=3], batch_rot[b][ix] [3,3], batch_trans[b][ix] [3,1] (camera -> world, used in float64), depth_scale / depth_trunc as open3d."""
+        posed = batch_camera_intrinsic is not None
+        if not posed and batch_position is None:
+            raise ValueError("either batch_position/batch_heading (habitat) or batch_camera_intrinsic/batch_rot/batch_trans (posed datasets) is required")
+        B = self.batch_size
+        V = len(batch_depth[0]) if posed else num_of_views  # FF:520
         P = self.args.input_height * self.args.input_width
         if batch_patch_segm is None:
             if self.segmenter is None:
                 raise RuntimeError("no segmentation: pass batch_patch_segm or set .segmenter (FastSAM is not part of this engine)")
-            batch_patch_segm = self.segmenter(batch_image)
+            if posed:  # FF:504-506: one FastSAM call per episode
+                batch_patch_segm = np.stack([np.asarray(torch.as_tensor(self.segmenter(batch_image[b])).cpu()) for b in range(B)], 0)
+            else:
+                batch_patch_segm = self.segmenter(batch_image)
         segm = np.ascontiguousarray(np.asarray(batch_patch_segm.cpu() if torch.is_tensor(batch_patch_segm) else batch_patch_segm)
                                     .reshape(B, V, P).transpose(1, 0, 2), dtype=np.int64)  # [V,B,P]
         with L.stream_scope():
-            depth = self._as_dev(batch_depth, torch.float32).reshape(B * V, P).contiguous()
+            if posed:
+                xyz, direction, scale = self._unproject_posed(batch_depth, batch_camera_intrinsic, batch_rot, batch_trans, depth_scale, depth_trunc, V)
+                if not torch.is_tensor(batch_grid_ft):
+                    batch_grid_ft = np.stack([np.asarray(g) for g in batch_grid_ft], 0)
+            else:
+                depth = self._as_dev(batch_depth, torch.float32).reshape(B * V, P).contiguous()
+                pose = self._upload([ops.pose_rows(batch_position, batch_heading, V)])[0]
+                xyz, direction, scale = ops.unproject_habitat(depth, pose, self.args.input_hfov, self.args.input_vfov,
+                                                              self.args.input_width, self.args.input_height)
             grid = self._as_dev(batch_grid_ft, torch.float16).reshape(B * V * P, D).contiguous()
-            pose = self._upload([ops.pose_rows(batch_position, batch_heading, V)])[0]
-            xyz, direction, scale = ops.unproject_habitat(depth, pose, self.args.input_hfov, self.args.input_vfov,
-                                                          self.args.input_width, self.args.input_height)
             xyz_h = xyz.to("cpu", non_blocking=True)  # host mirror of the step's patch positions (one copy per step)
             torch.cuda.current_stream().synchronize()
             xyz_h = np.ascontiguousarray(xyz_h.numpy().reshape(B, V, P, 3).transpose(1, 0, 2, 3))  # [V,B,P,3]
             stage = {"xyz": xyz.view(B * V * P, 3), "dir": direction.view(-1), "scale": scale.view(-1), "fts": grid}
+            plan = self._begin_step(V, P, segm, stage, xyz_h)
             for ix in range(V):
-                self._update_view(ix, V, P, segm[ix], stage, xyz_h[ix])
+                self._update_view(ix, plan)
 
-    def _update_view(self, ix, V, P, segm, stage, xyz_h):
-        """One panorama view for all episodes in lock step.  `stage` holds the step's unprojected patches / CLIP features for all
-        (episode, view) units, unit u = b*V+ix occupying rows [u*P, (u+1)*P).  segm [B,P] int64, xyz_h [B,P,3] fp32 (host)."""
+    def _unproject_posed(self, batch_depth, batch_K, batch_rot, batch_trans, depth_scale, depth_trunc, V):
+        """a4' (FF:50-60, 518, 533-546): all (episode, view) images of the step in one kernel instead of 8 joblib threads of open3d."""
         B = self.batch_size
-        dev = self.device
+        gh, gw = self.args.input_height, self.args.input_width
+        imgs, vp = [], np.zeros((B * V, 16), np.float64)
+        for b in range(B):
+            if len(batch_depth[b]) != V:
+                raise ValueError("the engine steps all episodes in lock step: every episode must bring the same number of views")
+            for ix in range(V):
+                imgs.append(np.asarray(torch.as_tensor(batch_depth[b][ix]).cpu()).astype(np.uint16))
+                K = np.asarray(torch.as_tensor(batch_K[b][ix]).cpu(), np.float64)
+                vp[b * V + ix, :4] = (K[0][0], K[1][1], K[0][2], K[1][2])
+                vp[b * V + ix, 4:13] = np.asarray(torch.as_tensor(batch_rot[b][ix]).cpu(), np.float64).reshape(9)
+                vp[b * V + ix, 13:16] = np.asarray(torch.as_tensor(batch_trans[b][ix]).cpu(), np.float64).reshape(3)
+        fx0 = float(np.asarray(torch.as_tensor(batch_K[0][0]).cpu(), np.float64)[0][0])  # get_rays(batch_camera_intrinsic[0][0]), FF:503
+        tan_abs = abs(math.tan(ops.ray_direction0(fx0, gw, self.args.deleted_frustum_distance)))
+        depth = torch.from_numpy(np.stack(imgs, 0).view(np.int16)).to(self.device)
+        xyz, direction, scale, n_invalid = ops.unproject_pinhole(depth, torch.from_numpy(vp).to(self.device), depth_scale, depth_trunc, tan_abs, gh, gw)
+        bad = int(n_invalid.item())
+        if bad:  # open3d drops these pixels and the reference's .view(H, W, 3) raises (FF:55)
+            raise ValueError(f"{bad} depth pixels are >= depth_trunc after scaling: open3d would drop them (feature_fields.py:55)")
+        return xyz, direction, scale
+
+    def _begin_step(self, V, P, segm, stage, xyz_h):
+        """Everything of a step that does not depend on the memory state, for ALL views at once: append the step's patches to the episode
+        pools (FF:557-570) and pool every (view, episode, segment) sequence into its view-instance token (FF:580-601) as ONE packed batch.
+        `stage` holds the step's unprojected patches / CLIP features, unit u = b*V+ix occupying rows [u*P, (u+1)*P).
+        segm [V,B,P] int64, xyz_h [V,B,P,3] fp32 (host)."""
+        B = self.batch_size
         lib = L.lib()
         eps = self.eps
-        # ---- plan the first half on the host (C++): packed sequences, one per (episode, segment) ----
-        cap = B * P
-        stage_off = (np.arange(B, dtype=np.int64) * V + ix) * P
-        base_rows = np.zeros(B, np.int64); n_seg = np.zeros(B, np.int32)
+        cap = V * B * P
+        base_rows = np.zeros(B, np.int64); view_start = np.zeros(V + 1, np.int32)
         seq_owner = np.zeros(cap, np.int32); members = np.zeros(cap, np.int32); cu_m = np.zeros(cap + 1, np.int32)
         tok_src = np.zeros(2 * cap, np.int32); tok_seq = np.zeros(2 * cap, np.int32); cu_tok = np.zeros(cap + 1, np.int32)
-        n_ref = np.zeros(cap, np.int32); info = np.zeros(2, np.int32)
-        L.check(lib.d3d_ffh_begin_view(self._h, xyz_h.ctypes.data, segm.ctypes.data, P, stage_off.ctypes.data, base_rows.ctypes.data,
-                                       n_seg.ctypes.data, seq_owner.ctypes.data, members.ctypes.data, cu_m.ctypes.data, tok_src.ctypes.data,
-                                       tok_seq.ctypes.data, cu_tok.ctypes.data, n_ref.ctypes.data, info.ctypes.data))
+        info = np.zeros(2, np.int32)
+        L.check(lib.d3d_ffh_begin_step(self._h, xyz_h.ctypes.data, segm.ctypes.data, P, V, base_rows.ctypes.data, view_start.ctypes.data,
+                                       seq_owner.ctypes.data, members.ctypes.data, cu_m.ctypes.data, tok_src.ctypes.data, tok_seq.ctypes.data,
+                                       cu_tok.ctypes.data, info.ctypes.data))
         n_seq, max_len = int(info[0]), int(info[1])
         T = cap + n_seq
-        owner = seq_owner[:n_seq]
-        # ---- 1. append the view's patches to the episode pools (FF:557-570): one batched block copy ----
+        # ---- append the step's patches to the episode pools: one batched block copy (4 pools x B episodes, V*P rows each) ----
         src, dst, nb = [], [], []
         for b, ep in enumerate(eps):
             n0 = int(base_rows[b])
             for pool in (ep.patch_pos, ep.patch_dir, ep.patch_scale, ep.patch_fts):
-                pool.ensure(n0 + P)
-            u = b * V + ix
+                pool.ensure(n0 + V * P)
             for key, pool, rb in (("xyz", ep.patch_pos, 12), ("dir", ep.patch_dir, 4), ("scale", ep.patch_scale, 4), ("fts", ep.patch_fts, 2 * D)):
-                src.append(stage[key].data_ptr() + u * P * rb)
+                src.append(stage[key].data_ptr() + b * V * P * rb)
                 dst.append(pool.t.data_ptr() + n0 * rb)
-                nb.append(P * rb)
-            ep.n_patch = n0 + P
-        inst_pos_ptr = np.fromiter((e.inst_pos.t.data_ptr() for e in eps), np.int64, B)
-        inst_fts_ptr = np.fromiter((e.inst_fts.t.data_ptr() for e in eps), np.int64, B)
+                nb.append(V * P * rb)
+            ep.n_patch = n0 + V * P
         sp = np.array([stage[k].data_ptr() for k in ("xyz", "dir", "scale", "fts")], np.int64)
         ptrs = np.repeat(sp[:, None], n_seq, axis=1)
-        extra = [np.asarray(src, np.int64), np.asarray(dst, np.int64), np.asarray(nb, np.int64), members, cu_m[:n_seq + 1],
-                 inst_pos_ptr[owner], inst_fts_ptr[owner], n_ref[:n_seq]]
-        # centroids need the member lists on the device first: upload everything in one go, then launch
-        up = self._upload([tok_src[:T], tok_seq[:T], cu_tok[:n_seq + 1], ptrs] + extra)
+        up = self._upload([tok_src[:T], tok_seq[:T], cu_tok[:n_seq + 1], ptrs, np.asarray(src, np.int64), np.asarray(dst, np.int64),
+                           np.asarray(nb, np.int64), members, cu_m[:n_seq + 1]])
         L.check(lib.d3d_copy_blocks(L.ptr(up[4]), L.ptr(up[5]), L.ptr(up[6]), len(src), L.stream_ptr()))
-        centres = ops.seq_centroid(stage["xyz"], up[7], up[8], n_seq)  # fp64 accumulate, all episodes in one launch
+        centres = ops.seq_centroid(stage["xyz"], up[7], up[8], n_seq)  # fp64 accumulate, every sequence of the step in one launch
         view_fts = self._pool_tokens(0, up[3], centres, up[1], up[0], up[2], T, n_seq, max_len, 0, False)
+        return {"view_start": view_start, "seq_owner": seq_owner[:n_seq], "centres": centres, "view_fts": view_fts}
+
+    def _update_view(self, ix, plan):
+        """The state-dependent part of one panorama view for all episodes in lock step: K-NN proposals, merge discriminator, then the
+        planner's bookkeeping and the device writes it implies (FF:604-756)."""
+        B = self.batch_size
+        dev = self.device
+        lib = L.lib()
+        eps = self.eps
+        s_lo, s_hi = int(plan["view_start"][ix]), int(plan["view_start"][ix + 1])
+        n_seq = s_hi - s_lo
+        owner = plan["seq_owner"][s_lo:s_hi]
+        centres, view_fts = plan["centres"][s_lo:s_hi], plan["view_fts"][s_lo:s_hi]
+        n_ref = np.zeros(max(n_seq, 1), np.int32)
+        L.check(lib.d3d_ffh_begin_view_refs(self._h, ix, n_ref.ctypes.data))
         # ---- 3. K-NN proposals + merge discriminator (FF:604-621), all episodes in one launch each; 2 columns are always computed,
         #         the planner uses the first min(#live, 2) of them (further columns can only be tombstones or absent) ----
         res = torch.empty((n_seq, 12), device=dev, dtype=torch.float32)  # [centre(3) | d2(2) | idx(2, int bits) | logits(4) | pad]
         if n_ref[:n_seq].max() > 0:
+            inst_pos_ptr = np.fromiter((e.inst_pos.t.data_ptr() for e in eps), np.int64, B)
+            inst_fts_ptr = np.fromiter((e.inst_fts.t.data_ptr() for e in eps), np.int64, B)
+            pos_d, fts_d, nref_d = self._upload([inst_pos_ptr[owner], inst_fts_ptr[owner], n_ref[:n_seq]])
             d2_d = torch.empty((n_seq, 2), device=dev, dtype=torch.float32)
             idx_d = torch.empty((n_seq, 2), device=dev, dtype=torch.int32)
-            L.check(lib.d3d_knn2_batched(L.ptr(up[9]), L.ptr(up[11]), L.ptr(centres), n_seq, L.ptr(d2_d), L.ptr(idx_d), L.stream_ptr()))
+            L.check(lib.d3d_knn2_batched(L.ptr(pos_d), L.ptr(nref_d), L.ptr(centres), n_seq, L.ptr(d2_d), L.ptr(idx_d), L.stream_ptr()))
             A = torch.empty((2 * n_seq, 1544), device=dev, dtype=torch.float32 if self.precise else self.compute_dtype)
-            L.check(lib.d3d_disc_input_batched(L.ptr(up[10]), L.ptr(up[9]), L.ptr(idx_d), L.ptr(view_fts), L.ptr(centres), n_seq, 2, D, 1544,
+            L.check(lib.d3d_disc_input_batched(L.ptr(fts_d), L.ptr(pos_d), L.ptr(idx_d), L.ptr(view_fts), L.ptr(centres), n_seq, 2, D, 1544,
                                                L.ptr(A), L.kind_of(A.dtype), L.stream_ptr()))
             if self.precise:
                 from . import precise as PR
@@ -611,8 +687,9 @@ class Feature_Fields(nn.Module):
         if n_new:
             o = new_owner[:n_new]
             a, bb, c = self._upload([new_src[:n_new], ifp[o] + 4 * D * new_iid[:n_new], ip[o] + 12 * new_iid[:n_new]])
-            L.check(lib.d3d_scatter_rows_ptr(L.ptr(view_fts), D, L.ptr(a), L.ptr(bb), n_new, D, L.stream_ptr()))
-            L.check(lib.d3d_scatter_rows_ptr(L.ptr(centres), 3, L.ptr(a), L.ptr(c), n_new, 3, L.stream_ptr()))
+            # new_src are step-global sequence indices
+            L.check(lib.d3d_scatter_rows_ptr(L.ptr(plan["view_fts"]), D, L.ptr(a), L.ptr(bb), n_new, D, L.stream_ptr()))
+            L.check(lib.d3d_scatter_rows_ptr(L.ptr(plan["centres"]), 3, L.ptr(a), L.ptr(c), n_new, 3, L.stream_ptr()))
         if n_mg:
             o = mg_owner[:n_mg]
             pp = np.fromiter((e.patch_pos.t.data_ptr() for e in eps), i64, B); pd = np.fromiter((e.patch_dir.t.data_ptr() for e in eps), i64, B)

@@ -164,6 +164,45 @@ def frustum_cull(xyz, direction, scale, fts16, n_patches, depth, cam, hfov=90.0,
     return mask[:n_patches], n_deleted
 
 
+def frustum_cull_matrix(xyz, direction, scale, fts16, n_patches, depth, cam25, near=0.0, far=2.0, eps=0.1):
+    """Posed-dataset cull (FF:64-84, 343-353): depth [V,H,W] fp32 (device), cam25 [V,25] fp32 (device) = view matrix | intrinsics."""
+    V, H, W = depth.shape
+    mask = torch.empty((max(n_patches, 1),), device=xyz.device, dtype=torch.uint8)
+    n_deleted = torch.zeros((1,), device=xyz.device, dtype=torch.int32)
+    f = ctypes.c_float
+    L.check(L.lib().d3d_frustum_cull_matrix(L.ptr(xyz), L.ptr(direction), L.ptr(scale), L.ptr(fts16), n_patches,
+                                            fts16.shape[1] if fts16 is not None else 0, L.ptr(depth), V, H, W, L.ptr(cam25), f(near), f(far), f(eps),
+                                            L.ptr(mask), L.ptr(n_deleted), L.stream_ptr()))
+    return mask[:n_patches], n_deleted
+
+
+def ray_direction0(fx, gw=24, distance=3.0, depth_trunc=1000.0):
+    """rel_direction[0][-1] of get_rays (PFF:390-405; FF:262-273 is the same expression but cannot run)."""
+    z32 = np.float32(distance) / np.float32(1.0)
+    if z32 >= np.float32(depth_trunc):
+        raise ValueError("get_rays: constant depth >= depth_trunc, open3d returns no points (FF:267)")
+    z = float(z32)
+    x = (0.0 - gw / 2) * z / float(fx)
+    return -math.atan(x / z)
+
+
+def unproject_pinhole(depth_u16, view_params, depth_scale, depth_trunc, tan_abs, gh=24, gw=24):
+    """depth_u16 [n,H,W] int16/uint16 bit pattern (device), view_params [n,16] float64 (device) -> xyz [n,gh*gw,3], dir, scale, n_invalid."""
+    n, H, W = depth_u16.shape
+    assert depth_u16.element_size() == 2 and depth_u16.is_contiguous() and view_params.dtype == torch.float64 and view_params.is_contiguous()
+    dev = depth_u16.device
+    xyz = torch.empty((n, gh * gw, 3), device=dev, dtype=torch.float32)
+    d = torch.empty((n, gh * gw), device=dev, dtype=torch.float32)
+    s = torch.empty((n, gh * gw), device=dev, dtype=torch.float32)
+    n_invalid = torch.zeros((1,), device=dev, dtype=torch.int32)
+    ri, rp = _hp_i32(torch_nearest_index_table(gh, H))
+    ci, cp = _hp_i32(torch_nearest_index_table(gw, W))
+    f = ctypes.c_float
+    L.check(L.lib().d3d_unproject_pinhole(L.ptr(depth_u16), n, H, W, L.ptr(view_params), gh, gw, rp, cp, f(depth_scale), f(depth_trunc),
+                                          f(float(np.float32(tan_abs))), L.ptr(xyz), L.ptr(d), L.ptr(s), L.ptr(n_invalid), L.stream_ptr()))
+    return xyz, d, s, n_invalid
+
+
 def knn3d(refs, queries, k):
     """Exact K-NN (squared L2, ascending, lowest index on ties): -> (d2 [Q,k] fp32, idx [Q,k] int32)."""
     assert refs.dtype == torch.float32 and queries.dtype == torch.float32 and refs.is_contiguous() and queries.is_contiguous()
@@ -210,6 +249,16 @@ def rmsnorm(x, w, eps, out32=None, out16=None, row_index=None, n_rows=None):
 
 def rope(qkv, pos, inv_freq, H, Dh):
     L.check(L.lib().d3d_rope(L.ptr(qkv), qkv.stride(0), L.ptr(pos), L.ptr(inv_freq), qkv.shape[0], H, Dh, L.kind_of(qkv.dtype), L.stream_ptr()))
+
+
+def rope_table(pos, inv_freq, Dh):
+    tab = torch.empty((pos.numel(), Dh), device=pos.device, dtype=torch.float32)
+    L.check(L.lib().d3d_rope_table(L.ptr(pos), L.ptr(inv_freq), pos.numel(), Dh, L.ptr(tab), L.stream_ptr()))
+    return tab
+
+
+def rope_apply(qkv, tab, H, Dh):
+    L.check(L.lib().d3d_rope_apply(L.ptr(qkv), qkv.stride(0), L.ptr(tab), qkv.shape[0], H, Dh, L.kind_of(qkv.dtype), L.stream_ptr()))
 
 
 def embed_gather(table, ids, out):

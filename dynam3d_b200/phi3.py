@@ -76,10 +76,11 @@ class LMEngine:
         if T > self.max_tokens:
             self._alloc(T)
         A16, qkv, att, h = self.A16[:T], self.qkv[:T], self.att[:T], self.h[:T]
+        tab = ops.rope_table(positions, self.inv_freq, self.Dh)  # cos/sin per token, shared by all layers
         for p in w.layers:
             ops.rmsnorm(X, p["rms1"], self.eps, out16=A16)
             ops.gemm(A16, p["w_qkv"], out=qkv)
-            ops.rope(qkv, positions, self.inv_freq, self.H, self.Dh)
+            ops.rope_apply(qkv, tab, self.H, self.Dh)
             ops.attention(qkv, att, cu_seqlens, n_seq, max_len, self.H, self.Dh, causal=True, impl=self.attention)
             ops.gemm(att, p["w_o"], out=X, residual=X)
             ops.rmsnorm(X, p["rms2"], self.eps, out16=A16)

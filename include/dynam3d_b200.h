@@ -114,6 +114,21 @@ int d3d_frustum_cull(float* xyz, float* dir, float* scale, void* fts16, int n_pa
                      int n_views, int H, int W, const float* cam, float fx, float fy, float cx, float cy, float near_,
                      float far_, float eps, uint8_t* mask, int* n_deleted, void* stream);
 
+/* Posed-dataset form of the cull (get_frustum_mask FF:64-84, call site FF:343-344; z-test FF:349-353): cam25 [n_views,25] fp32 =
+ * world->camera view matrix (4x4 row-major) followed by the intrinsics (3x3 row-major).  Same tombstoning / outputs as above. */
+int d3d_frustum_cull_matrix(float* xyz, float* dir, float* scale, void* fts16, int n_patches, int fts_dim, const float* depth,
+                            int n_views, int H, int W, const float* cam25, float near_, float far_, float eps, uint8_t* mask,
+                            int* n_deleted, void* stream);
+
+/* Posed-dataset unprojection (a4'): project_depth_to_3d (FF:50-60: open3d create_from_depth_image on the uint16 depth + nearest resize to
+ * the gh x gw grid, replacing the 8 joblib/open3d CPU threads of FF:130,518), R @ p + T, get_heading_angle and the patch scale (FF:250-259,
+ * 536-546).  depth [n_views,H,W] uint16; view_params [n_views,16] double (device) = fx, fy, cx, cy, R[9] row-major, T[3];
+ * row_idx_h / col_idx_h: host tables of F.interpolate(mode='nearest') source indices; tan_abs = |tan(rel_direction[0][-1])| of get_rays.
+ * *n_invalid counts pixels open3d would drop (z >= depth_trunc): the reference raises there, the caller should too. */
+int d3d_unproject_pinhole(const uint16_t* depth, int n_views, int H, int W, const double* view_params, int gh, int gw,
+                          const int* row_idx_h, const int* col_idx_h, float depth_scale, float depth_trunc, float tan_abs, float* xyz,
+                          float* dir, float* scale, int* n_invalid, void* stream);
+
 /* Exact K-NN in 3-D, replaces torch_kdtree build_kd_tree + query (FF:246,606,610; PFF:364,540,584):
  * squared L2 ((dx*dx+dy*dy)+dz*dz in fp32), ascending, lowest index on ties.  k <= 8, n_ref >= k.
  * refs [n_ref,3], queries [n_q,3] -> out_d2 [n_q,k] fp32, out_idx [n_q,k] int32. */
@@ -152,6 +167,10 @@ int d3d_rmsnorm(const float* x, int64_t ldx, const int* row_index, const float* 
 /* HF apply_rotary_pos_emb (rotate_half form) in place on q and k of a packed [T, 3*H*Dh] 16-bit QKV buffer;
  * pos [T] int32 token positions, inv_freq [Dh/2] fp32. */
 int d3d_rope(void* qkv, int64_t ld, const int* pos, const float* inv_freq, int T, int H, int Dh, int kind, void* stream);
+/* The same rotation split in two: the per-token table tab [T, Dh] fp32 = [cos | sin] of pos*inv_freq is built once per prefill and
+ * applied by every layer with 16-byte vector accesses (16-bit QKV; identical results to d3d_rope). */
+int d3d_rope_table(const int* pos, const float* inv_freq, int T, int Dh, float* tab, void* stream);
+int d3d_rope_apply(void* qkv, int64_t ld, const float* tab, int T, int H, int Dh, int kind, void* stream);
 
 /* embed_tokens (POL:439): out[t, :D] = table16[ids[t], :D] as fp32. */
 int d3d_embed_gather(const void* table, int kind, const int* ids, int T, int D, float* out, int64_t ldo, void* stream);
@@ -281,6 +300,11 @@ int d3d_ffh_cull(void* h, int b, const uint8_t* mask, int64_t n, int64_t* dead_i
 int d3d_ffh_set_tree(void* h);                              /* FF:396 */
 int d3d_ffh_begin_view(void* h, const float* xyz, const int64_t* segm, int P, const int64_t* stage_off, int64_t* base_rows, int* n_seg,
                        int* seq_owner, int* members, int* cu_m, int* tok_src, int* tok_seq, int* cu_tok, int* n_ref, int* info);
+/* Whole-step planning: the patch -> instance pooling of a view is independent of the memory state, so all V views are planned (and pooled
+ * on the device) as ONE packed batch; begin_view_refs then makes view ix the view in flight for finish_view / fetch_view. */
+int d3d_ffh_begin_step(void* h, const float* xyz /*[V,B,P,3]*/, const int64_t* segm /*[V,B,P]*/, int P, int V, int64_t* base_rows,
+                       int* view_seq_start, int* seq_owner, int* members, int* cu_m, int* tok_src, int* tok_seq, int* cu_tok, int* info);
+int d3d_ffh_begin_view_refs(void* h, int ix, int* n_ref);
 int d3d_ffh_finish_view(void* h, const float* res12, int* sizes10, int64_t* after3);
 int d3d_ffh_fetch_view(void* h, int* new_src, int* new_owner, int64_t* new_iid, int* mg_owner, int64_t* mg_iid, float* mg_pos,
                        int* mg_tok_src, int* mg_tok_seq, int* mg_cu, int* zn_owner, int64_t* zn_slot, int* zn_keys, float* zn_pos,

@@ -177,9 +177,35 @@ class FeatureFieldsOracle:
                 self._update_view(ep, np.asarray(batch_depth[b][ix], F32), np.asarray(batch_grid_ft[b][ix]).astype(np.float16),
                                   np.asarray(batch_patch_segm[b][ix]).reshape(-1), batch_position[b], float(batch_heading[b]), ix)
 
-    def _update_view(self, ep, depth576, grid_ft16, segm, position, heading, ix):
+    # ---- posed-dataset branch (FF:343-344, 501-546): same state machine, geometry from intrinsics / poses ----
+    def delete_old_features_posed(self, batch_depth, batch_intrinsic, batch_extrinsic):
+        """batch_depth[b] [V,H,W] fp32; batch_intrinsic[b][ix] [>=3,>=3]; batch_extrinsic[b][ix] [4,4] world->camera (far = 2.0, FF:64)."""
+        for b in range(self.batch_size):
+            ep = self.eps[b]
+            for ix in range(len(batch_depth[b])):
+                if len(ep.patch_pos) == 0:
+                    continue
+                mask = G.frustum_mask_matrix(ep.patch_pos, np.asarray(batch_depth[b][ix], F32), batch_intrinsic[b][ix], batch_extrinsic[b][ix])
+                self._apply_cull(ep, mask)
+            ep.tree = len(ep.inst_pos) > 0
+
+    def update_feature_fields_posed(self, batch_depth, batch_grid_ft, batch_patch_segm, batch_intrinsic, batch_rot, batch_trans,
+                                    depth_scale=1000.0, depth_trunc=1000.0, ray_distance=3.0):
+        fx0 = float(np.asarray(batch_intrinsic[0][0])[0][0])  # get_rays(batch_camera_intrinsic[0][0]) (FF:503)
+        for b in range(self.batch_size):
+            ep = self.eps[b]
+            for ix in range(len(batch_depth[b])):
+                xyz, direction, scale = G.unproject_posed_view(batch_depth[b][ix], batch_intrinsic[b][ix], batch_rot[b][ix], batch_trans[b][ix],
+                                                               depth_scale, depth_trunc, ray_distance=ray_distance, ray_fx=fx0)
+                self._update_view(ep, None, np.asarray(batch_grid_ft[b][ix]).astype(np.float16), np.asarray(batch_patch_segm[b][ix]).reshape(-1),
+                                  None, None, ix, geom=(xyz, direction, scale))
+
+    def _update_view(self, ep, depth576, grid_ft16, segm, position, heading, ix, geom=None):
         proposal_num = min(len(ep.i2p), self.num_proposal)
-        xyz, direction, scale = G.unproject_view_world(depth576, position, heading, ix, self.hfov, self.vfov)
+        if geom is not None:
+            xyz, direction, scale = geom
+        else:
+            xyz, direction, scale = G.unproject_view_world(depth576, position, heading, ix, self.hfov, self.vfov)
         ep.patch_pos = np.concatenate([ep.patch_pos, xyz], 0)
         ep.patch_dir = np.concatenate([ep.patch_dir, direction], 0)
         ep.patch_scale = np.concatenate([ep.patch_scale, scale], 0)

@@ -188,6 +188,119 @@ def frustum_mask_habitat(points, depth_img, cam_pos_internal, heading, hfov=90.0
 
 
 # ----------------------------------------------------------------------------------------------
+# a4': posed-dataset branch (FF:50-60, 250-273, 536-546, 64-84 + 343-344); PFF = Dynam3D_Pretrain/src_3dff/models/feature_fields.py
+#
+# open3d (pinned open3d==0.19.0, environment.yml) is NOT in the reference tree and not installable here: its
+# PointCloud.create_from_depth_image / Image.ConvertDepthToFloatImage are restated from the published algorithm
+# (cpp/open3d/geometry/PointCloudFactory.cpp, ImageFactory.cpp): z32 = float(u16) / float(depth_scale); z32 >= depth_trunc -> 0;
+# for z > 0: x = (u - cx) * z / fx, y = (v - cy) * z / fy evaluated in double from the float z.  PARITY UNPINNED for this
+# third-party step (no reference test holds its outputs); everything around it is pinned against the reference's own functions
+# (tests/test_oracle_vs_reference.py::test_posed_*).
+# ----------------------------------------------------------------------------------------------
+def torch_nearest_index(dst, src):
+    """Source index table of F.interpolate(mode='nearest'): min(floor(i * (src/dst) as fp32), src-1)."""
+    scale = F32(src) / F32(dst)
+    return np.minimum(np.floor(np.arange(dst, dtype=F32) * scale).astype(np.int64), src - 1)
+
+
+def open3d_depth_to_points(depth_u16, fx, fy, cx, cy, depth_scale, depth_trunc):
+    """create_from_depth_image on a uint16 image: [H,W,3] float64 camera-frame points and the validity mask (z > 0)."""
+    d = np.asarray(depth_u16).astype(np.uint16)
+    z32 = (d.astype(F32) / F32(depth_scale)).astype(F32)
+    z32 = np.where(z32 >= F32(depth_trunc), F32(0), z32).astype(F32)
+    H, W = z32.shape
+    z = z32.astype(np.float64)
+    u = np.arange(W, dtype=np.float64)[None, :]
+    v = np.arange(H, dtype=np.float64)[:, None]
+    x = (u - float(cx)) * z / float(fx)
+    y = (v - float(cy)) * z / float(fy)
+    return np.stack([x, y, z], -1), z32 > 0
+
+
+def project_depth_to_3d(depth, intrinsic, depth_scale, depth_trunc, gh=24, gw=24):
+    """FF:50-60: depth (uint16-valued [H,W]) -> (points [gh*gw,3] float64 camera frame, mask z > 0.002).
+    Zero depth is replaced by 1 raw unit (FF:51); open3d drops invalid pixels, which makes the reference's .view(H,W,3) raise --
+    restated as ValueError."""
+    d = np.array(depth).astype(np.int64)
+    d[d == 0] = 1
+    K = np.asarray(intrinsic, dtype=np.float64)
+    pts, valid = open3d_depth_to_points(d, K[0][0], K[1][1], K[0][2], K[1][2], depth_scale, depth_trunc)
+    if not valid.all():
+        raise ValueError("open3d dropped %d pixels (depth >= depth_trunc): the reference's view(H,W,3) fails here (FF:55)" % int((~valid).sum()))
+    ri, ci = torch_nearest_index(gh, pts.shape[0]), torch_nearest_index(gw, pts.shape[1])
+    pts = pts[ri][:, ci].reshape(-1, 3)
+    return pts, pts[:, 2] > 0.002
+
+
+def ray_direction0(fx, gw=24, distance=3.0, depth_trunc=1000.0):
+    """rel_direction[0][-1] of get_rays (PFF:390-405 / FF:262-273): -arctan(x/z) of grid pixel (0,0) on a constant-depth image with
+    principal point (gw/2, gh/2).  Q14: the VLN copy passes depth_trunc=1. with a 3 m image (FF:267), so open3d would drop every
+    point and the reshape at FF:270 raises; the Pretrain copy (depth_trunc=1000., PFF:397) is the working form restated here."""
+    z32 = F32(distance) / F32(1.0)
+    if z32 >= F32(depth_trunc):
+        raise ValueError("get_rays: constant depth >= depth_trunc, open3d returns no points (FF:267, quirk Q14)")
+    z = float(z32)
+    x = (0.0 - gw / 2) * z / float(fx)
+    return -math.atan(x / z)
+
+
+def heading_angle_of_points(points):
+    """FF:250-259 (float64 in, float64 out)."""
+    p = np.asarray(points, dtype=np.float64)
+    dx, dy = p[:, 0], p[:, 1]
+    xy = np.sqrt(np.square(dx) + np.square(dy))
+    xy[xy < 1e-4] = 1e-4
+    h = -np.arcsin(dx / xy)
+    h[dy < 0] = h[dy < 0] - np.pi
+    return h
+
+
+def unproject_posed_view(depth, intrinsic, R, T, depth_scale=1000.0, depth_trunc=1000.0, gh=24, gw=24, ray_distance=3.0, ray_fx=None):
+    """FF:533-546: world-frame patch xyz [gh*gw,3] fp32, direction, scale for one posed image (R [3,3], T [3,1] float64).
+    `ray_fx`: focal length get_rays was built with -- the reference uses the FIRST image of the batch for every view (FF:503)."""
+    pts, _ = project_depth_to_3d(depth, intrinsic, depth_scale, depth_trunc, gh, gw)
+    pts32 = pts.astype(F32)
+    t = abs(math.tan(ray_direction0(np.asarray(intrinsic)[0][0] if ray_fx is None else ray_fx, gw, ray_distance)))
+    scale = (((pts32[:, 2] * F32(t)).astype(F32) * F32(2.0)).astype(F32) / F32(gw)).astype(F32)
+    R = np.asarray(R, dtype=np.float64).reshape(3, 3)
+    T = np.asarray(T, dtype=np.float64).reshape(3, 1)
+    world = (R @ pts32.astype(np.float64).T + T).T
+    return world.astype(F32), heading_angle_of_points(world).astype(F32), scale
+
+
+def frustum_mask_matrix(points, depth_img, intrinsic, view_matrix, near=0.0, far=2.0, eps=0.1):
+    """FF:64-84 + the z-test FF:349-353 for ONE posed view: points [N,3] fp32, depth_img [H,W] fp32, intrinsic [>=3,>=3], view_matrix
+    [4,4] (world -> camera), all fp32.  The two einsums are evaluated as left-to-right fp32 sums of separately rounded products."""
+    p = np.asarray(points, dtype=F32)
+    K = np.asarray(intrinsic, dtype=F32)[:3, :3]
+    M = np.asarray(view_matrix, dtype=F32)
+    H, W = depth_img.shape
+
+    def row4(r):
+        a = ((M[r, 0] * p[:, 0]).astype(F32) + (M[r, 1] * p[:, 1]).astype(F32)).astype(F32)
+        a = (a + (M[r, 2] * p[:, 2]).astype(F32)).astype(F32)
+        return (a + M[r, 3]).astype(F32)  # homogeneous 1 * m3
+
+    vx, vy, vz = row4(0), row4(1), row4(2)
+
+    def row3(r):
+        a = ((K[r, 0] * vx).astype(F32) + (K[r, 1] * vy).astype(F32)).astype(F32)
+        return (a + (K[r, 2] * vz).astype(F32)).astype(F32)
+
+    with np.errstate(all="ignore"):
+        uh, vh, zh = row3(0), row3(1), row3(2)
+        uf = (uh / zh).astype(F32)
+        vf = (vh / zh).astype(F32)
+    finite = np.isfinite(uf) & np.isfinite(vf)
+    u = np.where(finite, np.trunc(np.where(finite, uf, 0)), -1).astype(np.int64)
+    v = np.where(finite, np.trunc(np.where(finite, vf, 0)), -1).astype(np.int64)
+    mask = (vz >= F32(near)) & (vz <= F32(far)) & (u >= 0) & (u <= W - 1) & (v >= 0) & (v <= H - 1) & finite
+    cam_depth = np.asarray(depth_img, dtype=F32)[np.mod(v, H), np.mod(u, W)]
+    mask &= vz < (cam_depth + F32(eps)).astype(F32)
+    return mask
+
+
+# ----------------------------------------------------------------------------------------------
 # a9: exact K-NN (torch_kdtree semantics pinned by us: FF:606-612)
 # ----------------------------------------------------------------------------------------------
 def knn3d(refs, queries, k, chunk=2048):

@@ -15,8 +15,9 @@ are replaced by minimal stand-ins injected into `sys.modules`:
 
 * `torch_kdtree.build_kd_tree` (feature_fields.py:7,246,606) -> exact
   brute-force K-NN, squared L2 in fp32, ascending, lowest index on ties.
-* `open3d` (feature_fields.py:8) -> empty module (the habitat branch never
-  touches it).
+* `open3d` (feature_fields.py:8) -> the three entry points of the posed-dataset branch (Image,
+  PinholeCameraIntrinsic, PointCloud.create_from_depth_image) restated from open3d 0.19's published
+  algorithm; the habitat branch never touches them.
 * `configargparse` (feature_fields.py:24) -> argparse.
 * `vlnce_baselines.models.fastsam` (feature_fields.py:17) -> stub classes; the
   segmentation (FastSAM output) is an INPUT of the hot path, so
@@ -72,13 +73,53 @@ class _BruteForceTree:
         return torch.from_numpy(dist), torch.from_numpy(order.astype(np.int64))
 
 
+def _open3d_stand_in():
+    """The three open3d entry points the posed-dataset branch uses (feature_fields.py:50-60, 262-273), following open3d 0.19's
+    published algorithm (ImageFactory.cpp ConvertDepthToFloatImage, PointCloudFactory.cpp CreatePointCloudFromFloatDepthImage):
+    float z = depth / depth_scale, z >= depth_trunc -> 0, pixels with z <= 0 are DROPPED, x = (u - cx) z / fx in double."""
+    o3d = types.ModuleType("open3d")
+    geometry, camera = types.ModuleType("open3d.geometry"), types.ModuleType("open3d.camera")
+
+    class Image:
+        def __init__(self, array):
+            self.array = np.asarray(array)
+
+    class PinholeCameraIntrinsic:
+        def __init__(self, width, height, fx, fy, cx, cy):
+            self.width, self.height, self.fx, self.fy, self.cx, self.cy = int(width), int(height), float(fx), float(fy), float(cx), float(cy)
+
+    class PointCloud:
+        def __init__(self):
+            self.points = np.zeros((0, 3), np.float64)
+
+        def __iadd__(self, other):
+            self.points = np.concatenate([self.points, other.points], 0)
+            return self
+
+        @staticmethod
+        def create_from_depth_image(depth, intrinsic, depth_scale=1000.0, depth_trunc=1000.0, stride=1):
+            z = depth.array.astype(np.float32)  # uint16 -> float (CreateFloatImage) or already float
+            z = (z / np.float32(depth_scale)).astype(np.float32)
+            z = np.where(z >= np.float32(depth_trunc), np.float32(0), z)
+            H, W = z.shape
+            v, u = np.nonzero(z > 0)  # row-major scan order, invalid pixels dropped
+            zz = z[v, u].astype(np.float64)
+            pc = PointCloud()
+            pc.points = np.stack([(u - intrinsic.cx) * zz / intrinsic.fx, (v - intrinsic.cy) * zz / intrinsic.fy, zz], -1)
+            return pc
+
+    geometry.Image, geometry.PointCloud, camera.PinholeCameraIntrinsic = Image, PointCloud, PinholeCameraIntrinsic
+    o3d.geometry, o3d.camera = geometry, camera
+    return o3d
+
+
 def _install_stubs():
     if "torch_kdtree" not in sys.modules:
         m = types.ModuleType("torch_kdtree")
         m.build_kd_tree = lambda pts: _BruteForceTree(pts)
         sys.modules["torch_kdtree"] = m
     if "open3d" not in sys.modules:
-        sys.modules["open3d"] = types.ModuleType("open3d")
+        sys.modules["open3d"] = _open3d_stand_in()
     if "configargparse" not in sys.modules:
         m = types.ModuleType("configargparse")
         m.ArgumentParser = argparse.ArgumentParser

@@ -27,6 +27,84 @@ def _planner_snapshot(lib, h, b, n_patch):
 
 
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "ff_traj_*.npz"))), ids=os.path.basename)
+def test_step_planner_reproduces_golden_state(path):
+    """Same check through the whole-step entry points the engine uses (d3d_ffh_begin_step + d3d_ffh_begin_view_refs): all views of a step
+    are planned up front, the per-view results are then fed in order."""
+    import copy
+    from dynam3d_b200 import _lib as L
+    from dynam3d_b200.feature_fields import Feature_Fields
+    from oracle import geometry as G
+    from oracle import ref_compare as RC
+    from oracle.ff_oracle import FeatureFieldsOracle
+    from oracle.make_golden import load_ff_fixture
+    lib = L.lib()
+    cfg, steps, gold = load_ff_fixture(path)
+    V, P = cfg["num_views"], 576
+    orc = FeatureFieldsOracle(RC.ff_params(cfg["weight_seed"], cfg["merge_bias"]), batch_size=1, rnd=None)
+    h = lib.d3d_ffh_create(1, 2, 2.0)
+    try:
+        for t, (st, g) in enumerate(zip(steps, gold)):
+            d576 = G.depth_patch_grid(st["depth"], 1, V, q1_fix=cfg.get("q1_fix", False))
+            full = G.preprocess_depth(st["depth"], (0.0, 10.0)).reshape(1, V, 256, 256)
+            pos, head = [st["position"]], [st["heading"]]
+            ep = orc.eps[0]
+            n0 = len(ep.patch_pos)
+            before = ep.patch_pos[:, 0].copy() == -10000.0 if n0 else np.zeros(0, bool)
+            orc.delete_old_features_from_camera_frustum(full, pos, head, num_of_views=V)
+            if n0:
+                mask = ((ep.patch_pos[:, 0] == -10000.0) & ~before).astype(np.uint8)
+                di, dz = np.zeros(4096, np.int64), np.zeros(4096, np.int64)
+                nd = (ctypes.c_int * 2)()
+                L.check(lib.d3d_ffh_cull(h, 0, mask.ctypes.data, n0, di.ctypes.data, ctypes.addressof(nd), dz.ctypes.data, ctypes.addressof(nd) + 4))
+            else:
+                lib.d3d_ffh_set_tree(h)
+            per_view = []
+            for ix in range(V):  # the oracle runs the whole step first; its per-view results are replayed into the planner below
+                orc._update_view(ep, np.asarray(d576[0][ix], np.float32), st["grid"][0][ix].astype(np.float16), st["segm"][ix].reshape(-1),
+                                 st["position"], float(st["heading"]), ix)
+                per_view.append((copy.deepcopy(ep.last_raw), copy.deepcopy(ep.last_knn), copy.deepcopy(ep.last_merge)))
+            xyz = np.ascontiguousarray(ep.patch_pos[-V * P:].reshape(V, 1, P, 3)).astype(np.float32)
+            segm = np.ascontiguousarray(np.asarray(st["segm"]).reshape(V, 1, P), dtype=np.int64)
+            cap = V * P
+            base_rows = np.zeros(1, np.int64); view_start = np.zeros(V + 1, np.int32); seq_owner = np.zeros(cap, np.int32)
+            members = np.zeros(cap, np.int32); cu_m = np.zeros(cap + 1, np.int32); tok_src = np.zeros(2 * cap, np.int32)
+            tok_seq = np.zeros(2 * cap, np.int32); cu_tok = np.zeros(cap + 1, np.int32); info = np.zeros(2, np.int32)
+            L.check(lib.d3d_ffh_begin_step(h, xyz.ctypes.data, segm.ctypes.data, P, V, base_rows.ctypes.data, view_start.ctypes.data,
+                                           seq_owner.ctypes.data, members.ctypes.data, cu_m.ctypes.data, tok_src.ctypes.data, tok_seq.ctypes.data,
+                                           cu_tok.ctypes.data, info.ctypes.data))
+            assert int(info[0]) == sum(len(r[0]["centres"]) for r in per_view) and int(base_rows[0]) == n0
+            # stage rows of view ix are [ix*P, (ix+1)*P) for a single episode: every member list must stay inside its view's block
+            for ix in range(V):
+                m = members[cu_m[view_start[ix]]:cu_m[view_start[ix + 1]]]
+                assert m.min() >= ix * P and m.max() < (ix + 1) * P and len(m) == P
+            for ix in range(V):
+                raw, last_knn, last_merge = per_view[ix]
+                Gn = len(raw["centres"])
+                assert int(view_start[ix + 1] - view_start[ix]) == Gn
+                n_ref = np.zeros(Gn, np.int32)
+                L.check(lib.d3d_ffh_begin_view_refs(h, ix, n_ref.ctypes.data))
+                res = np.zeros((Gn, 12), np.float32)
+                res[:, 0:3] = raw["centres"]
+                k_raw = raw["d2"].shape[1]
+                res[:, 3:3 + k_raw] = raw["d2"]
+                idx2 = np.full((Gn, 2), -1, np.int32); idx2[:, :k_raw] = raw["idx"]
+                res[:, 5:7] = idx2.view(np.float32)
+                if last_knn is not None and last_merge[1].shape[1] > 0:
+                    lg = last_merge[1]
+                    pad = np.zeros((Gn, 2, 2), np.float32); pad[:, :lg.shape[1]] = lg
+                    res[:, 7:11] = pad.reshape(Gn, 4)
+                sizes = np.zeros(10, np.int32); after = np.zeros(3, np.int64)
+                L.check(lib.d3d_ffh_finish_view(h, res.ctypes.data, sizes.ctypes.data, after.ctypes.data))
+                if last_knn is not None:
+                    last = Feature_Fields._last(type("F", (), {"_h": h})(), 0)
+                    assert np.array_equal(last["knn"][1], last_knn[1]) and np.array_equal(last["merge"], last_merge[0].astype(bool)), (t, ix)
+            snap, cnt = _planner_snapshot(lib, h, 0, len(ep.patch_pos))
+            assert RC.snapshots_equal(g["snap"], snap) == [], f"step {t}"
+    finally:
+        lib.d3d_ffh_destroy(h)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "ff_traj_*.npz"))), ids=os.path.basename)
 def test_planner_reproduces_golden_state(path):
     from dynam3d_b200 import _lib as L
     from oracle import geometry as G

@@ -40,6 +40,7 @@ def test_rope_matches_hf_formula(dtype):
     pos = torch.arange(T, device="cuda", dtype=torch.int32) % 50
     inv_freq = (1.0 / (10000.0 ** (torch.arange(0, Dh, 2).float() / Dh))).cuda()
     ref = qkv.float().clone()
+    ref_in = qkv.clone()
     freqs = pos.float()[:, None] * inv_freq[None]
     emb = torch.cat([freqs, freqs], -1)
     cos, sin = emb.cos()[:, None, :], emb.sin()[:, None, :]
@@ -51,6 +52,10 @@ def test_rope_matches_hf_formula(dtype):
     tol = 4e-3 if dtype == torch.float16 else 3e-2  # one 16-bit rounding of values up to ~4
     assert (qkv.float() - ref).abs().max().item() < tol
     assert torch.equal(qkv[:, 2 * H * Dh:].float(), ref[:, 2 * H * Dh:])  # v untouched
+    # the table-based vectorised form used by the LM engine is bit-identical
+    qkv2 = ref_in.clone()
+    ops.rope_apply(qkv2, ops.rope_table(pos, inv_freq, Dh), H, Dh)
+    assert torch.equal(qkv2, qkv)
 
 
 @pytest.mark.parametrize("impl", ["simt", "mma", "tc"])

@@ -93,3 +93,67 @@ def test_vit_restatement_matches_reference_module(pretrain):
         ref_cls, ref_patch = vit(x)
     cls, patch = NN.vit_forward(x, sd, layers, heads, rnd=None, ln_post_on_patches=not pretrain)
     assert (ref_cls - cls).abs().max().item() < 2e-5 and (ref_patch - patch).abs().max().item() < 2e-5
+
+
+def _posed_inputs(seed, H=240, W=320):
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:H, 0:W]
+    depth = (1500 + 900 * np.sin(xx / 37.0 + seed) + 600 * np.cos(yy / 23.0) + rng.integers(0, 40, (H, W))).astype(np.uint16)
+    depth[rng.integers(0, H, 30), rng.integers(0, W, 30)] = 0  # missing returns -> 1 raw unit (FF:51)
+    K = np.array([[285.0 + seed, 0, W / 2 - 3.5], [0, 291.0, H / 2 + 2.25], [0, 0, 1]], np.float64)
+    a = 0.3 * seed + 0.2
+    R = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1.0]]) @ np.array([[1, 0, 0], [0, 0, 1], [0, -1, 0.0]])
+    T = rng.uniform(-2, 2, (3, 1))
+    return depth, K, R, T
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_posed_unprojection_matches_reference_functions(seed):
+    """a4': FF:50-60 (through the open3d stand-in), FF:250-259 and the glue of FF:533-546 against oracle/geometry.py."""
+    from oracle import geometry as G
+    mod = ref_shim.load_reference_feature_fields_module()
+    ff = ref_shim.make_reference_feature_fields()
+    depth, K, R, T = _posed_inputs(seed)
+    pts_ref, mask_ref = mod.project_depth_to_3d(torch.from_numpy(depth.astype(np.int32)), K, 1000.0, 1000.0, 24, 24)
+    pts, mask = G.project_depth_to_3d(depth, K, 1000.0, 1000.0, 24, 24)
+    assert pts_ref.dtype == np.float64 and np.array_equal(pts_ref, pts) and np.array_equal(mask_ref, mask)
+    # the reference's glue, literally (FF:536-546), with the working get_rays direction (Q14)
+    points = pts_ref.astype(np.float32)
+    t = abs(np.tan(G.ray_direction0(K[0][0], 24, 3.0)))
+    scale_ref = points[:, -1] * float(t) * 2. / 24
+    world = (R @ points.T + T).T
+    xyz, direction, scale = G.unproject_posed_view(depth, K, R, T)
+    assert scale_ref.dtype == np.float32 and np.array_equal(scale_ref, scale)
+    assert np.array_equal(world.astype(np.float32), xyz)
+    assert np.array_equal(ff.get_heading_angle(world).astype(np.float32), direction)
+
+
+def test_posed_get_rays_quirk_q14():
+    """The VLN copy of get_rays asks open3d for a 3 m image with depth_trunc=1 (FF:267): every point is dropped and FF:270 raises."""
+    ff = ref_shim.make_reference_feature_fields()
+    with pytest.raises(ValueError):
+        ff.get_rays(np.array([[300.0, 0, 12], [0, 300.0, 12], [0, 0, 1]]))
+
+
+@pytest.mark.parametrize("seed", [0, 3])
+def test_posed_frustum_mask_matches_reference_function(seed):
+    """a6 (dataset form): get_frustum_mask FF:64-84 + z-test FF:349-353 against oracle/geometry.frustum_mask_matrix."""
+    from oracle import geometry as G
+    mod = ref_shim.load_reference_feature_fields_module()
+    rng = np.random.default_rng(seed)
+    depth_u16, K, R, T = _posed_inputs(seed)
+    H, W = depth_u16.shape
+    depth_m = (depth_u16.astype(np.float32) / 1000.0).astype(np.float32)
+    pts = rng.uniform(-3, 3, (40000, 3)).astype(np.float32)
+    # world -> camera matrix of the pose (R, T) (camera -> world)
+    M = np.eye(4)
+    M[:3, :3] = R.T
+    M[:3, 3:] = -R.T @ T
+    M32, K32 = M.astype(np.float32), np.eye(4, dtype=np.float32)
+    K32[:3, :3] = K.astype(np.float32)
+    mask_ref, d_ref, u, v = mod.get_frustum_mask(torch.from_numpy(pts), H, W, torch.from_numpy(K32), torch.from_numpy(M32))
+    cam_depth = torch.from_numpy(depth_m)[v % H, u % W]
+    mask_ref = (mask_ref & (d_ref < cam_depth + 0.1)).numpy()
+    mask = G.frustum_mask_matrix(pts, depth_m, K32, M32)
+    # CPU einsum may contract / reorder the 4-term sums: identical except for points within one ulp of a pixel or depth boundary
+    assert (mask_ref != mask).sum() <= 2 and mask.sum() > 100
