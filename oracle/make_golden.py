@@ -131,6 +131,43 @@ def make_geometry():
     print("wrote geometry")
 
 
+def make_posed():
+    """a4': outputs of the reference's own posed-dataset functions (project_depth_to_3d FF:50-60 through the open3d stand-in of
+    ref_shim, the literal glue FF:536-546, get_heading_angle FF:250-259, get_frustum_mask FF:64-84 + z-test) on seeded inputs."""
+    mod = ref_shim.load_reference_feature_fields_module()
+    ff = ref_shim.make_reference_feature_fields()
+    from oracle import geometry as G
+    out = {}
+    rng = np.random.default_rng(5)
+    H, W = 120, 160
+    yy, xx = np.mgrid[0:H, 0:W]
+    for i in range(3):
+        depth = (1500 + 900 * np.sin(xx / 19.0 + i) + 600 * np.cos(yy / 11.0) + rng.integers(0, 40, (H, W))).astype(np.uint16)
+        depth[rng.integers(0, H, 20), rng.integers(0, W, 20)] = 0
+        K = np.array([[140.0 + i, 0, W / 2 - 1.5], [0, 145.0, H / 2 + 0.75], [0, 0, 1]], np.float64)
+        a = 0.4 * i + 0.1
+        R = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1.0]]) @ np.array([[1, 0, 0], [0, 0, 1], [0, -1, 0.0]])
+        T = rng.uniform(-1, 1, (3, 1))
+        pts, _ = mod.project_depth_to_3d(torch.from_numpy(depth.astype(np.int32)), K, 1000.0, 1000.0, 24, 24)
+        points = pts.astype(np.float32)
+        t = abs(np.tan(G.ray_direction0(140.0, 24, 3.0)))  # get_rays of the first image (Q14: the VLN get_rays itself cannot run)
+        scale = points[:, -1] * float(t) * 2. / 24
+        world = (R @ points.T + T).T
+        out.update({f"depth{i}": depth, f"K{i}": K, f"R{i}": R, f"T{i}": T, f"xyz{i}": world.astype(np.float32),
+                    f"dir{i}": ff.get_heading_angle(world).astype(np.float32), f"scale{i}": scale.astype(np.float32)})
+    cloud = rng.uniform(-3, 3, (30000, 3)).astype(np.float32)
+    M = np.eye(4)
+    M[:3, :3], M[:3, 3:] = out["R1"].T, -out["R1"].T @ out["T1"]
+    K4 = np.eye(4, dtype=np.float32)
+    K4[:3, :3] = out["K1"].astype(np.float32)
+    depth_m = (out["depth1"].astype(np.float32) / 1000.0).astype(np.float32)
+    m, dep, u, v = mod.get_frustum_mask(torch.from_numpy(cloud), H, W, torch.from_numpy(K4), torch.from_numpy(M.astype(np.float32)))
+    m = m & (dep < torch.from_numpy(depth_m)[v % H, u % W] + 0.1)
+    out.update(cull_pts=cloud, cull_M=M.astype(np.float32), cull_mask=np.packbits(m.numpy()))
+    np.savez_compressed(os.path.join(OUT, "posed.npz"), **out)
+    print("wrote posed", int(m.sum()))
+
+
 def make_vit():
     out = {}
     width, layers, heads, res, od = 256, 3, 4, 112, 128
@@ -151,5 +188,6 @@ def make_vit():
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     make_geometry()
+    make_posed()
     make_vit()
     make_ff()

@@ -23,6 +23,19 @@ def test_geometry_vs_reference_vectors():
     assert np.array_equal(got, want) and 100 < want.sum() < n
 
 
+def test_posed_geometry_vs_reference_vectors():
+    """a4': oracle/geometry.py posed-dataset functions against the vectors the reference's own functions produced (posed.npz)."""
+    from oracle import geometry as G
+    z = np.load(os.path.join(GOLD, "posed.npz"))
+    for i in range(3):
+        xyz, d, s = G.unproject_posed_view(z[f"depth{i}"], z[f"K{i}"], z[f"R{i}"], z[f"T{i}"], 1000.0, 1000.0, ray_fx=140.0)
+        assert np.array_equal(xyz, z[f"xyz{i}"]) and np.array_equal(d, z[f"dir{i}"]) and np.array_equal(s, z[f"scale{i}"])
+    n = len(z["cull_pts"])
+    want = np.unpackbits(z["cull_mask"])[:n].astype(bool)
+    got = G.frustum_mask_matrix(z["cull_pts"], (z["depth1"].astype(np.float32) / 1000.0).astype(np.float32), z["K1"].astype(np.float32), z["cull_M"])
+    assert (got != want).sum() <= 1 and want.sum() > 100  # torch's CPU einsum may contract the 4-term sums (one-ulp boundary cases)
+
+
 def test_vit_restatement_vs_reference_vectors():
     from dynam3d_b200 import synth
     from oracle import nn_ops as NN

@@ -60,3 +60,27 @@ def test_geometry_kernels_vs_reference_vectors():
     mask, _ = ops.frustum_cull(dev(z["cull_pts"].copy()), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda"), None, n,
                                dev(z["cull_depth"].astype(np.float32)[None]), cam)
     assert np.array_equal(mask.cpu().numpy().astype(bool), want)
+
+
+def test_posed_kernels_vs_reference_vectors():
+    """a4': d3d_unproject_pinhole / d3d_frustum_cull_matrix against the vectors the reference's own functions produced (posed.npz)."""
+    from dynam3d_b200 import ops
+    z = np.load(os.path.join(GOLD, "posed.npz"))
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    vp = np.zeros((3, 16))
+    for i in range(3):
+        K = z[f"K{i}"]
+        vp[i] = [K[0][0], K[1][1], K[0][2], K[1][2], *z[f"R{i}"].reshape(9), *z[f"T{i}"].reshape(3)]
+    depth = np.stack([z[f"depth{i}"] for i in range(3)])
+    t = abs(np.tan(ops.ray_direction0(140.0, 24, 3.0)))
+    xyz, d, s, bad = ops.unproject_pinhole(dev(depth.view(np.int16)), dev(vp), 1000.0, 1000.0, t)
+    assert int(bad.item()) == 0
+    for i in range(3):
+        assert np.array_equal(xyz[i].cpu().numpy(), z[f"xyz{i}"]) and np.array_equal(d[i].cpu().numpy(), z[f"dir{i}"])
+        assert np.array_equal(s[i].cpu().numpy(), z[f"scale{i}"])
+    n = len(z["cull_pts"])
+    want = np.unpackbits(z["cull_mask"])[:n].astype(bool)
+    cam25 = np.concatenate([z["cull_M"].reshape(16), z["K1"].astype(np.float32)[:3, :3].reshape(9)]).astype(np.float32)[None]
+    mask, _ = ops.frustum_cull_matrix(dev(z["cull_pts"].copy()), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda"), None, n,
+                                      dev((depth[1].astype(np.float32) / 1000.0).astype(np.float32)[None]), dev(cam25))
+    assert (mask.cpu().numpy().astype(bool) != want).sum() <= 1  # torch's CPU einsum may contract the 4-term sums
