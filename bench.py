@@ -253,6 +253,27 @@ def run_engine(args):
     e3.record()
     barrier()
     ms_e2e = e2.elapsed_time(e3)
+    # ---- per-stage rooflines: ONE extra step (outside both timed regions) with CUDA events around every C-ABI call ----
+    stages = []
+    if rank == 0:
+        ops.STAGE_PROFILE = []
+        one_step(args.warmup, dev_in)
+        torch.cuda.synchronize()
+        prof_s, ops.STAGE_PROFILE = ops.STAGE_PROFILE, None
+        peak_tf_, peak_hbm_, _ = peaks()
+        agg = {}
+        for name, bound, work, a, b in prof_s:
+            d = agg.setdefault(name, {"bound": bound, "work": 0.0, "ms": 0.0, "launches": 0})
+            d["work"] += work; d["ms"] += a.elapsed_time(b); d["launches"] += 1
+        for name, d in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
+            if d["ms"] <= 0:
+                continue
+            if d["bound"] == "tensor":
+                ach, peak, unit = d["work"] / (d["ms"] * 1e-3) / 1e12, peak_tf_, "TFLOP/s"
+            else:
+                ach, peak, unit = d["work"] / (d["ms"] * 1e-3) / 1e9, peak_hbm_, "GB/s"
+            stages.append({"stage": name, "bound": d["bound"], "launches": d["launches"], "ms": round(d["ms"], 3), "achieved": round(ach, 1),
+                           "unit": unit, "frac": round(ach / peak, 3)})
     sampler.stop_flag = True
     sampler.join(timeout=2)
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
@@ -277,6 +298,7 @@ def run_engine(args):
                        "precision": "fp16 GEMM operands (reference: fp16 autocast, TR:385), fp32 accumulate / residual / norm statistics"},
             "e2e": {"value": e2e, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(E * 32064 * 4)},
             "gpu_launches": int(launches),
+            "stages": stages,  # one extra profiled step: per-stage algorithmic FLOPs or bytes / CUDA-event time vs the measured peaks
             "clocks": sampler.summary(),
             "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all tcgen05 GEMM launches of the timed region)", "achieved": achieved,
                          "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None, "peak_source": which,

@@ -86,8 +86,9 @@ class ViTWeights:
 class ViTEngine:
     """Runs the tower for up to `max_images` images per call; all scratch is preallocated (CUDA-graph friendly)."""
 
-    def __init__(self, weights, n_head=16, resolution=336, max_images=12, attention="auto"):
+    def __init__(self, weights, n_head=16, resolution=336, max_images=12, attention="auto", tag="vit"):
         L.require_device()
+        self.tag = tag  # stage name in ops.STAGE_PROFILE
         self.w = weights
         self.H = n_head
         self.R = resolution
@@ -113,6 +114,7 @@ class ViTEngine:
         """img_u8 [N,H,W,3] uint8 on device.  Returns (cls [N,out], patch [N,g2,out]) 16-bit views into `self.out`
         (valid until the next call), or with project=False the fp32 hidden state [N,tokens,width] after `n_layers_run` blocks."""
         w = self.w
+        ops.STAGE_TAG = self.tag
         N = img_u8.shape[0]
         if N > self.max_images:
             self._alloc(N)

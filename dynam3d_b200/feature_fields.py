@@ -396,8 +396,10 @@ class Feature_Fields(nn.Module):
         out = torch.empty((n_seq, D), device=self.device, dtype=torch.float32)
         if not self.precise:
             ws = self._workspace(int(L.lib().d3d_pool_workspace_bytes(T, D, D)))
-            L.check(L.lib().d3d_pool_tokens(ctypes.addressof(W["c_levels"][level]), L.ptr(ptrs_d), L.ptr(centre_dev), L.ptr(tok_seq_d), L.ptr(tok_src_d),
-                                            L.ptr(cu_d), T, n_seq, int(max_len), mode, int(fts_is_f32), L.ptr(ws), ws.numel(), L.ptr(out), L.stream_ptr()))
+            # position MLP + 2 post-norm encoder layers: 2*(8*768 + 768^2) + 2 * 2*(768*2304 + 768^2 + 2*768*3072) = 29.5 MFLOP per token (+ attention)
+            with ops._Rec("pool_tokens", "tensor", T * 29.5e6):
+                L.check(L.lib().d3d_pool_tokens(ctypes.addressof(W["c_levels"][level]), L.ptr(ptrs_d), L.ptr(centre_dev), L.ptr(tok_seq_d), L.ptr(tok_src_d),
+                                                L.ptr(cu_d), T, n_seq, int(max_len), mode, int(fts_is_f32), L.ptr(ws), ws.numel(), L.ptr(out), L.stream_ptr()))
             return out
         from . import precise as PR
         m = W["m32"][level]
@@ -457,6 +459,7 @@ class Feature_Fields(nn.Module):
         Posed-dataset branch (batch_camera_intrinsic / batch_extrinsic given, FF:343-344): batch_depth[b] [V,H,W] fp32 in the unit of the
         stored points, batch_camera_intrinsic[b][ix] [>=3,>=3], batch_extrinsic[b][ix] [4,4] world->camera; the far plane is
         get_frustum_mask's default 2.0 (the VLN call site does not pass `far`)."""
+        ops.STAGE_TAG = "ff"
         posed = batch_extrinsic is not None
         if not posed and batch_position is None:
             raise ValueError("either batch_position/batch_heading (habitat) or batch_camera_intrinsic/batch_extrinsic (posed datasets) is required")
@@ -530,6 +533,7 @@ class Feature_Fields(nn.Module):
         dense int labels (or `self.segmenter(batch_image)` is called, standing in for FastSAM, FF:509).
         Posed-dataset branch (batch_camera_intrinsic given, FF:501-546): batch_depth[b] [V,H,W] uint16-valued raw depth, batch_camera_intrinsic[b][ix]
         [>=3,>=3], batch_rot[b][ix] [3,3], batch_trans[b][ix] [3,1] (camera -> world, used in float64), depth_scale / depth_trunc as open3d."""
+        ops.STAGE_TAG = "ff"
         posed = batch_camera_intrinsic is not None
         if not posed and batch_position is None:
             raise ValueError("either batch_position/batch_heading (habitat) or batch_camera_intrinsic/batch_rot/batch_trans (posed datasets) is required")

@@ -10,6 +10,29 @@ from . import _lib as L
 
 
 GEMM_PROFILE = None  # set to a list to record (flops, start_event, end_event) per tensor-core GEMM launch (bench.py roofline)
+# Per-stage roofline profile (bench.py `stages`): set STAGE_PROFILE to a list and every wrapped op appends
+# (stage, bound, work, start_event, end_event) with work = algorithmic FLOPs ("tensor") or bytes ("hbm") of the launch.  STAGE_TAG names the
+# caller (vit / tower / lm / ff / proj) and is set by the engines.
+STAGE_PROFILE = None
+STAGE_TAG = "misc"
+
+
+class _Rec:
+    """Context manager: CUDA events around one C-ABI call on the current stream (no-op unless STAGE_PROFILE is a list)."""
+
+    def __init__(self, name, bound, work):
+        self.args = (name, bound, work)
+
+    def __enter__(self):
+        if STAGE_PROFILE is not None:
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if STAGE_PROFILE is not None:
+            self.e1.record()
+            STAGE_PROFILE.append((STAGE_TAG + "." + self.args[0], self.args[1], float(self.args[2]), self.e0, self.e1))
+        return False
 
 
 def gemm(a, w, out=None, bias=None, act=L.ACT_NONE, residual=None, out_dtype=None, simt=False):
@@ -32,6 +55,10 @@ def gemm(a, w, out=None, bias=None, act=L.ACT_NONE, residual=None, out_dtype=Non
         L.kind_of(a.dtype), L.kind_of(out.dtype), L.ptr(bias), int(act),
         L.ptr(residual), residual.stride(0) if residual is not None else 0)
     fn = L.lib().d3d_gemm_simt if simt else L.lib().d3d_gemm
+    if STAGE_PROFILE is not None:
+        with _Rec("gemm", "tensor", 2.0 * M * N * K):
+            L.check(fn(ctypes.cast(ctypes.byref(args), ctypes.c_void_p), L.stream_ptr()))
+        return out
     if GEMM_PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -132,8 +159,9 @@ def unproject_habitat(depth, pose, hfov=90.0, vfov=90.0, W=24, H=24):
     d = torch.empty((n, W * H), device=depth.device, dtype=torch.float32)
     s = torch.empty((n, W * H), device=depth.device, dtype=torch.float32)
     tx, txp = _hp_f32(tx); tz, tzp = _hp_f32(tz); na, nap = _hp_f32(na)
-    L.check(L.lib().d3d_unproject_habitat(L.ptr(depth), L.ptr(pose), n, W, H, txp, tzp, nap, ctypes.c_float(th),
-                                          L.ptr(xyz), L.ptr(d), L.ptr(s), L.stream_ptr()))
+    with _Rec("unproject", "hbm", n * (W * H * (4 + 12 + 4 + 4) + 24)):  # 13.8 KB / view
+        L.check(L.lib().d3d_unproject_habitat(L.ptr(depth), L.ptr(pose), n, W, H, txp, tzp, nap, ctypes.c_float(th),
+                                              L.ptr(xyz), L.ptr(d), L.ptr(s), L.stream_ptr()))
     return xyz, d, s
 
 
@@ -157,10 +185,11 @@ def frustum_cull(xyz, direction, scale, fts16, n_patches, depth, cam, hfov=90.0,
     if n_deleted is None:
         n_deleted = torch.zeros((1,), device=xyz.device, dtype=torch.int32)
     f = ctypes.c_float
-    L.check(L.lib().d3d_frustum_cull(L.ptr(xyz), L.ptr(direction), L.ptr(scale), L.ptr(fts16), n_patches,
-                                     fts16.shape[1] if fts16 is not None else 0, L.ptr(depth), V, H, W, L.ptr(cam),
-                                     f(fx), f(fy), f(W / 2.0), f(H / 2.0), f(near), f(far), f(eps), L.ptr(mask), L.ptr(n_deleted),
-                                     L.stream_ptr()))
+    with _Rec("frustum_cull", "hbm", n_patches * 13 + V * H * W * 4):  # 12 B xyz + 1 B mask per stored patch + the depth maps
+        L.check(L.lib().d3d_frustum_cull(L.ptr(xyz), L.ptr(direction), L.ptr(scale), L.ptr(fts16), n_patches,
+                                         fts16.shape[1] if fts16 is not None else 0, L.ptr(depth), V, H, W, L.ptr(cam),
+                                         f(fx), f(fy), f(W / 2.0), f(H / 2.0), f(near), f(far), f(eps), L.ptr(mask), L.ptr(n_deleted),
+                                         L.stream_ptr()))
     return mask[:n_patches], n_deleted
 
 
@@ -231,20 +260,22 @@ def layernorm(x, gamma, beta, eps, out32=None, out16=None, act=L.ACT_NONE, row_i
     T = n_rows if n_rows is not None else (row_index.numel() if row_index is not None else x.shape[0])
     D = x.shape[1]
     assert x.dtype == torch.float32 and x.stride(1) == 1
-    L.check(L.lib().d3d_layernorm(L.ptr(x), x.stride(0), L.ptr(row_index), L.ptr(gamma), L.ptr(beta), ctypes.c_float(eps), T, D, int(act),
-                                  L.ptr(out32), out32.stride(0) if out32 is not None else 0,
-                                  L.ptr(out16), out16.stride(0) if out16 is not None else 0,
-                                  L.kind_of(out16.dtype) if out16 is not None else 0, L.stream_ptr()))
+    with _Rec("layernorm", "hbm", T * D * (4 + (4 if out32 is not None else 0) + (2 if out16 is not None else 0))):
+        L.check(L.lib().d3d_layernorm(L.ptr(x), x.stride(0), L.ptr(row_index), L.ptr(gamma), L.ptr(beta), ctypes.c_float(eps), T, D, int(act),
+                                      L.ptr(out32), out32.stride(0) if out32 is not None else 0,
+                                      L.ptr(out16), out16.stride(0) if out16 is not None else 0,
+                                      L.kind_of(out16.dtype) if out16 is not None else 0, L.stream_ptr()))
 
 
 def rmsnorm(x, w, eps, out32=None, out16=None, row_index=None, n_rows=None):
     T = n_rows if n_rows is not None else (row_index.numel() if row_index is not None else x.shape[0])
     D = x.shape[1]
     assert x.dtype == torch.float32 and x.stride(1) == 1
-    L.check(L.lib().d3d_rmsnorm(L.ptr(x), x.stride(0), L.ptr(row_index), L.ptr(w), ctypes.c_float(eps), T, D,
-                                L.ptr(out32), out32.stride(0) if out32 is not None else 0,
-                                L.ptr(out16), out16.stride(0) if out16 is not None else 0,
-                                L.kind_of(out16.dtype) if out16 is not None else 0, L.stream_ptr()))
+    with _Rec("rmsnorm", "hbm", T * D * (4 + (4 if out32 is not None else 0) + (2 if out16 is not None else 0))):
+        L.check(L.lib().d3d_rmsnorm(L.ptr(x), x.stride(0), L.ptr(row_index), L.ptr(w), ctypes.c_float(eps), T, D,
+                                    L.ptr(out32), out32.stride(0) if out32 is not None else 0,
+                                    L.ptr(out16), out16.stride(0) if out16 is not None else 0,
+                                    L.kind_of(out16.dtype) if out16 is not None else 0, L.stream_ptr()))
 
 
 def rope(qkv, pos, inv_freq, H, Dh):
@@ -258,7 +289,8 @@ def rope_table(pos, inv_freq, Dh):
 
 
 def rope_apply(qkv, tab, H, Dh):
-    L.check(L.lib().d3d_rope_apply(L.ptr(qkv), qkv.stride(0), L.ptr(tab), qkv.shape[0], H, Dh, L.kind_of(qkv.dtype), L.stream_ptr()))
+    with _Rec("rope", "hbm", qkv.shape[0] * (2 * H * Dh * 2 * 2 + Dh * 4)):  # q and k read + written (16 bit), cos/sin row read
+        L.check(L.lib().d3d_rope_apply(L.ptr(qkv), qkv.stride(0), L.ptr(tab), qkv.shape[0], H, Dh, L.kind_of(qkv.dtype), L.stream_ptr()))
 
 
 def embed_gather(table, ids, out):
@@ -280,7 +312,8 @@ def preprocess_im2col(img_u8, R=336, patch=14, out_dtype=torch.float16, mean=CLI
     out = torch.empty((N * g * g, kpad), device=img_u8.device, dtype=out_dtype)
     m, mp = _hp_f32(mean)
     s, sp = _hp_f32(std)
-    L.check(L.lib().d3d_preprocess_im2col(L.ptr(img_u8), N, Hin, Win, R, patch, mp, sp, L.ptr(out), kpad, L.kind_of(out_dtype), L.stream_ptr()))
+    with _Rec("preprocess_im2col", "hbm", N * (Hin * Win * 3 + g * g * kpad * 2)):
+        L.check(L.lib().d3d_preprocess_im2col(L.ptr(img_u8), N, Hin, Win, R, patch, mp, sp, L.ptr(out), kpad, L.kind_of(out_dtype), L.stream_ptr()))
     return out
 
 
@@ -313,15 +346,17 @@ def attention(qkv, out, cu_seqlens, n_seq, max_len, H, Dh, causal=False, uniform
     """Self-attention over packed sequences.  `impl`: 'tc' (tcgen05, head_dim 64), 'mma' (legacy tensor cores), 'simt' (fp32
     CUDA cores) or 'auto' (tc for long head_dim-64 sequences, mma otherwise, simt for very short ones)."""
     scale = 1.0 / math.sqrt(Dh)
-    if impl == "tc" or (impl == "auto" and Dh == 64 and max_len >= 256):
-        L.check(L.lib().d3d_attention_tc(L.ptr(qkv), qkv.stride(0), qkv.shape[0], L.ptr(out), out.stride(0), L.ptr(cu_seqlens), n_seq, max_len, H, Dh,
-                                         int(bool(causal)), L.kind_of(qkv.dtype), scale, L.stream_ptr()))
-        return
-    if impl == "mma" or (impl == "auto" and Dh in (64, 96) and max_len >= 64):
-        L.check(L.lib().d3d_attention_mma(L.ptr(qkv), qkv.stride(0), L.ptr(out), out.stride(0), L.ptr(cu_seqlens), n_seq, max_len, H, Dh,
-                                          int(bool(causal)), L.kind_of(qkv.dtype), scale, L.stream_ptr()))
-        return
-    attention_simt(qkv, out, cu_seqlens, n_seq, max_len, H, Dh, causal)
+    # algorithmic FLOPs of the launch (QK^T + PV), assuming equal-length sequences (exact for the ViT, ~2 % high for the packed LM batch)
+    work = 4.0 * (qkv.shape[0] ** 2 / max(n_seq, 1)) * Dh * H * (0.5 if causal else 1.0)
+    with _Rec("attention", "tensor", work):
+        if impl == "tc" or (impl == "auto" and Dh == 64 and max_len >= 256):
+            L.check(L.lib().d3d_attention_tc(L.ptr(qkv), qkv.stride(0), qkv.shape[0], L.ptr(out), out.stride(0), L.ptr(cu_seqlens), n_seq, max_len, H, Dh,
+                                             int(bool(causal)), L.kind_of(qkv.dtype), scale, L.stream_ptr()))
+        elif impl == "mma" or (impl == "auto" and Dh in (64, 96) and max_len >= 64):
+            L.check(L.lib().d3d_attention_mma(L.ptr(qkv), qkv.stride(0), L.ptr(out), out.stride(0), L.ptr(cu_seqlens), n_seq, max_len, H, Dh,
+                                              int(bool(causal)), L.kind_of(qkv.dtype), scale, L.stream_ptr()))
+        else:
+            attention_simt(qkv, out, cu_seqlens, n_seq, max_len, H, Dh, causal)
 
 
 # ------------------------------------------------------------------------------------------------

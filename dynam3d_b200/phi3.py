@@ -72,6 +72,7 @@ class LMEngine:
         """X fp32 [T, hidden] (overwritten: it is the residual stream); cu_seqlens int32 [n_seq+1]; positions int32 [T];
         last_rows int32 [n_seq] (row of each sequence's last token).  Returns logits fp32 [n_seq, vocab]."""
         w = self.w
+        ops.STAGE_TAG = "lm"
         T = X.shape[0]
         if T > self.max_tokens:
             self._alloc(T)

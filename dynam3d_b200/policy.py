@@ -75,7 +75,7 @@ class _Llava:
                     return k[: -len(suffix)]
             raise KeyError(suffix)
         vt = find("vision_model.embeddings.class_embedding")
-        self.tower = ViTEngine(ViTWeights.from_hf_clip_state_dict(sd, device, torch.float16, vt + "vision_model."), 16, 336, max_images)
+        self.tower = ViTEngine(ViTWeights.from_hf_clip_state_dict(sd, device, torch.float16, vt + "vision_model."), 16, 336, max_images, tag="tower")
         pj = find("multi_modal_projector.linear_1.weight")
         c16 = lambda t: t.detach().to(device=device, dtype=torch.float32).to(torch.float16).contiguous()
         f32 = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()
@@ -95,6 +95,7 @@ class _Llava:
             return PR.linear(h, self.proj["w2"], self.proj["b2"])
         hid = self.tower.forward(rgb_u8, n_layers_run=len(self.tower.w.layers) - 1, project=False)  # [N, 577, 1024] fp32
         N = hid.shape[0]
+        ops.STAGE_TAG = "proj"
         a16 = torch.empty((N * 576, hid.shape[2]), device=hid.device, dtype=torch.float16)
         ops.cast16(hid[:, 1:].reshape(N * 576, hid.shape[2]), a16)
         h = ops.gemm(a16, self.proj["w1"], bias=self.proj["b1"], act=L.ACT_GELU)
@@ -248,6 +249,7 @@ class Dynam3D_VLN(nn.Module):
     def _project_tokens(self, fts, rel, pos_mlp, proj_mlp):
         """POL:434-435: projector(cat[fts, position_embedding(rel)]) -> fp32 [n, 3072]."""
         n = fts.shape[0]
+        ops.STAGE_TAG = "proj"
         if n == 0:
             return torch.zeros((0, 3072), device=self.device, dtype=torch.float32)
         op_dt = torch.float32 if self.precise else torch.float16
@@ -300,10 +302,13 @@ class Dynam3D_VLN(nn.Module):
         main.wait_stream(self._side)
         for t in (rows, patch_pos, patch):
             t.record_stream(main)
-        inst = [self._project_tokens(env["batch_instance_fts"][b], env["batch_instance_relative_position"][b], PW["inst_pos"], PW["inst_proj"])
-                for b in range(B)]
-        zone = [self._project_tokens(env["batch_zone_fts"][b], env["batch_zone_relative_position"][b], PW["zone_pos"], PW["zone_proj"])
-                for b in range(B)]
+        # POL:434-435 for all episodes of the rank in one packed batch per token kind (row-wise MLPs: batching does not change any value)
+        def project_all(fts, rel, pos_mlp, proj_mlp):
+            counts = [int(f.shape[0]) for f in fts]
+            out = self._project_tokens(torch.cat(fts, 0), torch.cat(rel, 0), pos_mlp, proj_mlp)
+            return list(torch.split(out, counts, 0))
+        inst = project_all(env["batch_instance_fts"], env["batch_instance_relative_position"], PW["inst_pos"], PW["inst_proj"])
+        zone = project_all(env["batch_zone_fts"], env["batch_zone_relative_position"], PW["zone_pos"], PW["zone_proj"])
         return patch.view(B, P, 3072), inst, zone
 
     def forward_logits(self, observations, instructions, agent_positions, agent_heading_angles, depth_scale=(0.0, 10.0),
