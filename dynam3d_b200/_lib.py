@@ -36,6 +36,16 @@ class PoolLevel(ctypes.Structure):
                 ("norm_eps", ctypes.c_float), ("n_layers", ctypes.c_int), ("d_model", ctypes.c_int), ("n_head", ctypes.c_int)]
 
 
+class LMLayer(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ("rms1", "w_qkv", "w_o", "rms2", "w_gu", "w_down")]
+
+
+class LMModel(ctypes.Structure):
+    _fields_ = [("n_layers", ctypes.c_int), ("hidden", ctypes.c_int), ("n_heads", ctypes.c_int), ("head_dim", ctypes.c_int), ("ffn", ctypes.c_int),
+                ("vocab", ctypes.c_int), ("kind", ctypes.c_int), ("eps", ctypes.c_float), ("layers", ctypes.POINTER(LMLayer)),
+                ("norm", ctypes.c_void_p), ("lm_head", ctypes.c_void_p), ("embed", ctypes.c_void_p)]
+
+
 class GemmArgs(ctypes.Structure):
     _fields_ = [
         ("A", ctypes.c_void_p), ("lda", ctypes.c_int64),
@@ -71,6 +81,9 @@ SIGNATURES = {
     "d3d_layernorm": [_P, _L, _P, _P, _P, _F, _I, _I, _I, _P, _L, _P, _L, _I, _P],
     "d3d_rmsnorm": [_P, _L, _P, _P, _F, _I, _I, _P, _L, _P, _L, _I, _P],
     "d3d_rope": [_P, _L, _P, _P, _I, _I, _I, _I, _P],
+    "d3d_gemm_skinny": [_P, _P], "d3d_argmax_rows": [_P, _L, _I, _I, _P, _P],
+    "d3d_decode_attention": [_P, _L, _P, _I, _I, _I, _I, _I, _I, _F, _P, _L, _P],
+    "d3d_lm_decode_step": [_P, _P, _L, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "d3d_rope_table": [_P, _P, _I, _I, _P, _P], "d3d_rope_apply": [_P, _L, _P, _I, _I, _I, _I, _P],
     "d3d_embed_gather": [_P, _I, _P, _I, _I, _P, _L, _P],
     "d3d_preprocess_im2col": [_P, _I, _I, _I, _I, _I, _FP, _FP, _P, _I, _I, _P],

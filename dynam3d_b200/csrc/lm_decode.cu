@@ -1,0 +1,312 @@
+// Greedy decode with a KV cache for the llava-phi-3-mini language model (POL:463: llava.generate(max_new_tokens=20, do_sample=False);
+// SURVEY.md 8(f) rank 1).  A decode step multiplies 8..16 activation rows with every weight matrix once, so it is HBM-bound on the
+// weights (7.6 GB per token): the kernels here are written for the memory roofline, not for the tensor pipe.
+//
+//   skinny_gemm_kernel  : out[M<=16, N] = epi(A[M,K] @ W[N,K]^T).  One CTA per 16 weight rows, 8 warps split K; every thread streams
+//                         16-byte pieces of its weight row straight from HBM (L1 no-allocate) and feeds mma.sync.m16n8k16 with a
+//                         K-permuted fragment layout (the SAME permutation on A and W, so no shuffles or smem staging are needed);
+//                         fp32 partials of the 8 warps are summed in a fixed order in smem (deterministic), then +bias / SwiGLU /
+//                         +fp32 residual and the store.
+//   decode_attn_kernel  : one CTA per (sequence, head); keys / values = the sequence's prefill rows plus its rows of the earlier
+//                         decode steps in the per-layer QKV cache; one warp per key, online softmax, 8-way merge in smem.
+//   argmax_kernel       : first maximum of every logit row (torch.argmax / HF greedy tie-break).
+//   d3d_lm_decode_step  : the whole step (32 layers) behind ONE C call, so the host issues ~260 launches without interpreter overhead.
+#include "common.cuh"
+
+extern "C" int d3d_rmsnorm(const float* x, int64_t ldx, const int* row_index, const float* w, float eps, int T, int D, float* out32,
+                           int64_t ld32, void* out16, int64_t ld16, int kind16, void* stream);
+extern "C" int d3d_rope_table(const int* pos, const float* inv_freq, int T, int Dh, float* tab, void* stream);
+extern "C" int d3d_rope_apply(void* qkv, int64_t ld, const float* tab, int T, int H, int Dh, int kind, void* stream);
+
+namespace {
+
+constexpr int SK_WARPS = 8;
+constexpr int SK_NT = 2;  // n-tiles (8 weight rows each) per CTA
+
+__device__ __forceinline__ uint4 ldg_stream16(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1, int kind) {
+  if (kind == D3D_BF16)
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  else
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+struct SkinnyEpi {
+  void* C; long long ldc;
+  const float* bias; const float* residual; long long ldres;
+  int act, out_kind;
+};
+
+// Fragment trick: thread (g = lane/4, kq = lane%4) loads 16 contiguous bytes (8 K-elements at k0 = 32*ks + 8*kq) of A row g / g+8 and of
+// W row n0+g.  MMA 1 uses elements {0,1} as K-slots (2kq, 2kq+1) and {2,3} as slots (2kq+8, 2kq+9); MMA 2 uses {4,5} and {6,7} the same
+// way.  A and W use the same slot -> k map, so the products pair up correctly and the 32 k of the step are each used exactly once.
+__global__ void __launch_bounds__(SK_WARPS * 32) skinny_gemm_kernel(const uint16_t* __restrict__ A, long long lda, const uint16_t* __restrict__ W,
+                                                                    long long ldw, int M, int N, int K, int kind, SkinnyEpi ep) {
+  __shared__ float red[SK_WARPS][SK_NT][16][8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, kq = lane & 3;
+  const int n_base = blockIdx.x * (8 * SK_NT);
+  float acc[SK_NT][4];
+#pragma unroll
+  for (int t = 0; t < SK_NT; ++t)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[t][i] = 0.f;
+  const bool lo_ok = g < M, hi_ok = g + 8 < M;
+  const uint16_t* a_lo_p = A + (long long)g * lda + kq * 8;
+  const uint16_t* a_hi_p = A + (long long)(g + 8) * lda + kq * 8;
+  const uint16_t* w_p[SK_NT];
+  bool w_ok[SK_NT];
+#pragma unroll
+  for (int t = 0; t < SK_NT; ++t) {
+    const int n = n_base + t * 8 + g;
+    w_ok[t] = n < N;
+    w_p[t] = W + (long long)(w_ok[t] ? n : 0) * ldw + kq * 8;
+  }
+  const int steps = K >> 5;
+#pragma unroll 4
+  for (int ks = warp; ks < steps; ks += SK_WARPS) {
+    const int off = ks << 5;
+    uint4 wv[SK_NT];
+#pragma unroll
+    for (int t = 0; t < SK_NT; ++t) wv[t] = w_ok[t] ? ldg_stream16(w_p[t] + off) : make_uint4(0, 0, 0, 0);
+    const uint4 al = lo_ok ? __ldg(reinterpret_cast<const uint4*>(a_lo_p + off)) : make_uint4(0, 0, 0, 0);
+    const uint4 ah = hi_ok ? __ldg(reinterpret_cast<const uint4*>(a_hi_p + off)) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int t = 0; t < SK_NT; ++t) {
+      mma16816(acc[t], al.x, ah.x, al.y, ah.y, wv[t].x, wv[t].y, kind);
+      mma16816(acc[t], al.z, ah.z, al.w, ah.w, wv[t].z, wv[t].w, kind);
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < SK_NT; ++t) {
+    red[warp][t][g][kq * 2] = acc[t][0];
+    red[warp][t][g][kq * 2 + 1] = acc[t][1];
+    red[warp][t][g + 8][kq * 2] = acc[t][2];
+    red[warp][t][g + 8][kq * 2 + 1] = acc[t][3];
+  }
+  __syncthreads();
+  // one thread per (tile, row, column pair): fixed-order sum over the 8 K-slices, then the epilogue
+  const int e = threadIdx.x;
+  if (e < SK_NT * 16 * 4) {
+    const int t = e / 64, r = (e / 4) % 16, cp = e % 4;
+    const int n = n_base + t * 8 + cp * 2;
+    if (r < M && n < N) {
+      float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+      for (int w = 0; w < SK_WARPS; ++w) {
+        v0 += red[w][t][r][cp * 2];
+        v1 += red[w][t][r][cp * 2 + 1];
+      }
+      const bool has1 = n + 1 < N;
+      if (ep.bias) {
+        v0 += ep.bias[n];
+        if (has1) v1 += ep.bias[n + 1];
+      }
+      if (ep.act == D3D_ACT_SWIGLU) {  // row-interleaved gate/up: columns (2j, 2j+1) -> output column j
+        const float o = __fdividef(v0, 1.0f + __expf(-v0)) * v1;
+        const long long oc = n >> 1;
+        if (ep.out_kind == D3D_OUT_F32) ((float*)ep.C)[(long long)r * ep.ldc + oc] = o;
+        else st16(ep.C, (size_t)((long long)r * ep.ldc + oc), o, ep.out_kind);
+      } else {
+        if (ep.act == D3D_ACT_QUICK_GELU) { v0 = quick_gelu(v0); v1 = quick_gelu(v1); }
+        else if (ep.act == D3D_ACT_GELU) { v0 = gelu_erf(v0); v1 = gelu_erf(v1); }
+        else if (ep.act == D3D_ACT_SILU) { v0 = silu(v0); v1 = silu(v1); }
+        else if (ep.act == D3D_ACT_LEAKY_RELU) { v0 = v0 > 0.f ? v0 : 0.01f * v0; v1 = v1 > 0.f ? v1 : 0.01f * v1; }
+        if (ep.residual) {
+          v0 += ep.residual[(long long)r * ep.ldres + n];
+          if (has1) v1 += ep.residual[(long long)r * ep.ldres + n + 1];
+        }
+        if (ep.out_kind == D3D_OUT_F32) {
+          ((float*)ep.C)[(long long)r * ep.ldc + n] = v0;
+          if (has1) ((float*)ep.C)[(long long)r * ep.ldc + n + 1] = v1;
+        } else {
+          st16(ep.C, (size_t)((long long)r * ep.ldc + n), v0, ep.out_kind);
+          if (has1) st16(ep.C, (size_t)((long long)r * ep.ldc + n + 1), v1, ep.out_kind);
+        }
+      }
+    }
+  }
+}
+
+// ---- decode attention over the per-layer QKV cache ----
+// cache row layout: [q (H*Dh) | k (H*Dh) | v (H*Dh)] 16-bit; sequence b owns the prefill rows [cu[b], cu[b+1]) and the decode rows
+// t_prefill + s*n_seq + b for s = 0..step (the last one is the query's own row).  Dh % 32 == 0 (96 or 64), Dh <= 128.
+constexpr int DA_WARPS = 8;
+template <int DH>
+__global__ void __launch_bounds__(DA_WARPS * 32) decode_attn_kernel(const uint16_t* __restrict__ qkv, long long ld, const int* __restrict__ cu,
+                                                                   int n_seq, int t_prefill, int step, int H, int kind, float scale,
+                                                                   uint16_t* __restrict__ out, long long ldo) {
+  constexpr int VPL = DH / 32;  // elements per lane (3 for head_dim 96)
+  __shared__ float s_m[DA_WARPS], s_l[DA_WARPS], s_acc[DA_WARPS][DH];
+  const int b = blockIdx.x, h = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p0 = cu[b], n_pre = cu[b + 1] - p0;
+  const int n_keys = n_pre + step + 1;
+  const long long q_row = (long long)t_prefill + (long long)step * n_seq + b;
+  float q[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) q[i] = ld16(qkv, (size_t)(q_row * ld + (long long)h * DH + lane * VPL + i), kind) * scale;
+  float m = -INFINITY, l = 0.f, acc[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) acc[i] = 0.f;
+  const long long k_off = (long long)(H + h) * DH + lane * VPL, v_off = (long long)(2 * H + h) * DH + lane * VPL;
+  for (int j = warp; j < n_keys; j += DA_WARPS) {
+    const long long row = j < n_pre ? (long long)(p0 + j) : (long long)t_prefill + (long long)(j - n_pre) * n_seq + b;
+    float kv[VPL], vv[VPL], s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      kv[i] = ld16(qkv, (size_t)(row * ld + k_off + i), kind);
+      vv[i] = ld16(qkv, (size_t)(row * ld + v_off + i), kind);
+      s += q[i] * kv[i];
+    }
+    s = warp_sum(s);
+    const float m_new = fmaxf(m, s);
+    const float c = __expf(m - m_new), p = __expf(s - m_new);  // exp(-inf) = 0 on the first key
+    l = l * c + p;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) acc[i] = acc[i] * c + p * vv[i];
+    m = m_new;
+  }
+  if (lane == 0) { s_m[warp] = m; s_l[warp] = l; }
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) s_acc[warp][lane * VPL + i] = acc[i];
+  __syncthreads();
+  if (threadIdx.x < DH) {
+    float gm = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < DA_WARPS; ++w) gm = fmaxf(gm, s_m[w]);
+    float num = 0.f, den = 0.f;
+#pragma unroll
+    for (int w = 0; w < DA_WARPS; ++w) {
+      const float c = s_m[w] == -INFINITY ? 0.f : __expf(s_m[w] - gm);
+      num += c * s_acc[w][threadIdx.x];
+      den += c * s_l[w];
+    }
+    st16(out, (size_t)((long long)b * ldo + (long long)h * DH + threadIdx.x), num / den, kind);
+  }
+}
+
+__global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ x, long long ld, int n, int* __restrict__ out) {
+  __shared__ float sv[32];
+  __shared__ int si[32];
+  const float* r = x + (long long)blockIdx.x * ld;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = r[i];
+    if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    best = threadIdx.x < (blockDim.x >> 5) ? sv[threadIdx.x] : -INFINITY;
+    bi = threadIdx.x < (blockDim.x >> 5) ? si[threadIdx.x] : 0x7fffffff;
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = bi == 0x7fffffff ? 0 : bi;
+  }
+}
+
+// embed the fed tokens (fp32 residual rows) and set their positions: pos[b] = prefill length of b + step
+__global__ void decode_prep_kernel(const void* __restrict__ table, int kind, const int* __restrict__ ids, const int* __restrict__ cu, int step, int D,
+                                   float* __restrict__ x, int* __restrict__ pos) {
+  const int b = blockIdx.x;
+  if (threadIdx.x == 0) pos[b] = cu[b + 1] - cu[b] + step;
+  const size_t src = (size_t)ids[b] * D;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) x[(long long)b * D + c] = ld16(table, src + c, kind);
+}
+
+int skinny(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N, int K, int kind, int out_kind,
+           const float* bias, int act, const float* residual, long long ldres, cudaStream_t st) {
+  D3D_REQUIRE(M >= 1 && M <= 16, "skinny GEMM handles 1..16 activation rows");
+  D3D_REQUIRE(K % 32 == 0 && lda % 8 == 0 && ldw % 8 == 0, "K must be a multiple of 32, rows 16-byte aligned");
+  D3D_REQUIRE(((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0, "A/W must be 16-byte aligned");
+  D3D_REQUIRE(kind == D3D_F16 || kind == D3D_BF16, "16-bit operands");
+  D3D_REQUIRE(act != D3D_ACT_SWIGLU || ((N % 2) == 0 && residual == nullptr), "swiglu needs even N, no residual");
+  SkinnyEpi ep{C, ldc, bias, residual, ldres, act, out_kind};
+  skinny_gemm_kernel<<<d3d_cdiv(N, 8 * SK_NT), SK_WARPS * 32, 0, st>>>((const uint16_t*)A, lda, (const uint16_t*)W, ldw, M, N, K, kind, ep);
+  D3D_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int d3d_gemm_skinny(const d3d_gemm_args* a, void* stream) {
+  D3D_REQUIRE(a != nullptr && a->A && a->W && a->C, "args");
+  return skinny(a->A, a->lda, a->W, a->ldw, a->C, a->ldc, a->M, a->N, a->K, a->in_kind, a->out_kind, a->bias, a->act, a->residual, a->ldres,
+                (cudaStream_t)stream);
+}
+
+extern "C" int d3d_argmax_rows(const float* x, int64_t ld, int rows, int n, int* out, void* stream) {
+  if (rows == 0) return 0;
+  D3D_REQUIRE(x && out && n > 0, "args");
+  argmax_kernel<<<rows, 1024, 0, (cudaStream_t)stream>>>(x, ld, n, out);
+  D3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int d3d_decode_attention(const void* qkv, int64_t ld, const int* cu_seqlens, int n_seq, int t_prefill, int step, int H, int Dh,
+                                    int kind, float scale, void* out, int64_t ldo, void* stream) {
+  if (n_seq == 0) return 0;
+  D3D_REQUIRE(qkv && cu_seqlens && out && step >= 0, "args");
+  D3D_REQUIRE(kind == D3D_F16 || kind == D3D_BF16, "16-bit cache");
+  dim3 grid(n_seq, H);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (Dh == 96) decode_attn_kernel<96><<<grid, DA_WARPS * 32, 0, st>>>((const uint16_t*)qkv, ld, cu_seqlens, n_seq, t_prefill, step, H, kind, scale, (uint16_t*)out, ldo);
+  else if (Dh == 64) decode_attn_kernel<64><<<grid, DA_WARPS * 32, 0, st>>>((const uint16_t*)qkv, ld, cu_seqlens, n_seq, t_prefill, step, H, kind, scale, (uint16_t*)out, ldo);
+  else if (Dh == 128) decode_attn_kernel<128><<<grid, DA_WARPS * 32, 0, st>>>((const uint16_t*)qkv, ld, cu_seqlens, n_seq, t_prefill, step, H, kind, scale, (uint16_t*)out, ldo);
+  else { d3d_set_error("decode attention: head_dim %d not built (64, 96, 128)", Dh); return D3D_EINVAL; }
+  D3D_CHECK_LAUNCH();
+  return 0;
+}
+
+// One greedy decode step for all sequences of the rank.  Feeds tokens_in (the previous step's arg-max), appends their q/k/v rows to the
+// per-layer caches at row t_prefill + step*n_seq + b, and writes the next-token logits and their arg-max.
+extern "C" int d3d_lm_decode_step(const d3d_lm_model* m, void* const* qkv_layers_h, int64_t ld_qkv, const int* cu_seqlens, int n_seq,
+                                  int t_prefill, int step, const int* tokens_in, const float* inv_freq, float* x32, void* a16, void* att16,
+                                  void* h16, float* rope_tab, int* pos, float* logits, int* next_tokens, void* stream) {
+  D3D_REQUIRE(m && qkv_layers_h && cu_seqlens && tokens_in && inv_freq && x32 && a16 && att16 && h16 && rope_tab && pos && logits && next_tokens,
+              "args");
+  D3D_REQUIRE(n_seq >= 1 && n_seq <= 16, "1..16 sequences per decode step");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Dm = m->hidden, H = m->n_heads, Dh = m->head_dim, kind = m->kind;
+  D3D_REQUIRE(H * Dh == Dm, "hidden = heads * head_dim");
+  decode_prep_kernel<<<n_seq, 256, 0, st>>>(m->embed, kind, tokens_in, cu_seqlens, step, Dm, x32, pos);
+  D3D_CHECK_LAUNCH();
+  D3D_TRY(d3d_rope_table(pos, inv_freq, n_seq, Dh, rope_tab, stream));
+  const long long row0 = (long long)t_prefill + (long long)step * n_seq;
+  const float scale = 1.0f / sqrtf((float)Dh);
+  for (int l = 0; l < m->n_layers; ++l) {
+    const d3d_lm_layer& L = m->layers[l];
+    uint16_t* rows = (uint16_t*)qkv_layers_h[l] + row0 * ld_qkv;
+    D3D_TRY(d3d_rmsnorm(x32, Dm, nullptr, L.rms1, m->eps, n_seq, Dm, nullptr, 0, a16, Dm, kind, stream));
+    D3D_TRY(skinny(a16, Dm, L.w_qkv, Dm, rows, ld_qkv, n_seq, 3 * Dm, Dm, kind, kind, nullptr, D3D_ACT_NONE, nullptr, 0, st));
+    D3D_TRY(d3d_rope_apply(rows, ld_qkv, rope_tab, n_seq, H, Dh, kind, stream));
+    D3D_TRY(d3d_decode_attention(qkv_layers_h[l], ld_qkv, cu_seqlens, n_seq, t_prefill, step, H, Dh, kind, scale, att16, Dm, stream));
+    D3D_TRY(skinny(att16, Dm, L.w_o, Dm, x32, Dm, n_seq, Dm, Dm, kind, D3D_OUT_F32, nullptr, D3D_ACT_NONE, x32, Dm, st));
+    D3D_TRY(d3d_rmsnorm(x32, Dm, nullptr, L.rms2, m->eps, n_seq, Dm, nullptr, 0, a16, Dm, kind, stream));
+    D3D_TRY(skinny(a16, Dm, L.w_gu, Dm, h16, m->ffn, n_seq, 2 * m->ffn, Dm, kind, kind, nullptr, D3D_ACT_SWIGLU, nullptr, 0, st));
+    D3D_TRY(skinny(h16, m->ffn, L.w_down, m->ffn, x32, Dm, n_seq, Dm, m->ffn, kind, D3D_OUT_F32, nullptr, D3D_ACT_NONE, x32, Dm, st));
+  }
+  D3D_TRY(d3d_rmsnorm(x32, Dm, nullptr, m->norm, m->eps, n_seq, Dm, nullptr, 0, a16, Dm, kind, stream));
+  D3D_TRY(skinny(a16, Dm, m->lm_head, Dm, logits, m->vocab, n_seq, m->vocab, Dm, kind, D3D_OUT_F32, nullptr, D3D_ACT_NONE, nullptr, 0, st));
+  argmax_kernel<<<n_seq, 1024, 0, st>>>(logits, m->vocab, m->vocab, next_tokens);
+  D3D_CHECK_LAUNCH();
+  return 0;
+}

@@ -31,6 +31,7 @@ from . import ops
 
 F32 = np.float32
 D = 768
+TRACE = None  # set to a list: _update_view appends (launch_ms, sync_wait_ms, plan_ms, post_ms) host wall times per view (profiling aid)
 _TORCH_DT = {np.int32: torch.int32, np.int64: torch.int64, np.float32: torch.float32, np.uint8: torch.uint8, np.float16: torch.float16}
 
 
@@ -636,6 +637,9 @@ class Feature_Fields(nn.Module):
         dev = self.device
         lib = L.lib()
         eps = self.eps
+        if TRACE is not None:
+            import time
+            t0 = time.perf_counter()
         s_lo, s_hi = int(plan["view_start"][ix]), int(plan["view_start"][ix + 1])
         n_seq = s_hi - s_lo
         owner = plan["seq_owner"][s_lo:s_hi]
@@ -665,7 +669,11 @@ class Feature_Fields(nn.Module):
         res[:, 0:3] = centres
         # ---- 4. ONE device->host copy per view, then the planner's second half (FF:623-756) ----
         res_h = res.to("cpu", non_blocking=True)
+        if TRACE is not None:
+            t1 = time.perf_counter()
         torch.cuda.current_stream().synchronize()
+        if TRACE is not None:
+            t2 = time.perf_counter()
         res_h = res_h.numpy()
         sizes = np.zeros(10, np.int32); after = np.zeros(B * 3, np.int64)
         L.check(lib.d3d_ffh_finish_view(self._h, res_h.ctypes.data, sizes.ctypes.data, after.ctypes.data))
@@ -687,6 +695,8 @@ class Feature_Fields(nn.Module):
         # pool base addresses AFTER any growth
         ip = np.fromiter((e.inst_pos.t.data_ptr() for e in eps), i64, B); ifp = np.fromiter((e.inst_fts.t.data_ptr() for e in eps), i64, B)
         zp = np.fromiter((e.zone_pos.t.data_ptr() for e in eps), i64, B); zfp = np.fromiter((e.zone_fts.t.data_ptr() for e in eps), i64, B)
+        if TRACE is not None:
+            t3 = time.perf_counter()
         # ---- 6. device writes implied by the bookkeeping: batched scatters / pooling passes across episodes ----
         if n_new:
             o = new_owner[:n_new]
@@ -723,6 +733,9 @@ class Feature_Fields(nn.Module):
                                                        extra=[zfp[o] + 4 * D * zn_slot[:n_zn], zp[o] + 12 * zn_slot[:n_zn]])
             L.check(lib.d3d_scatter_rows_ptr(L.ptr(zf), D, None, L.ptr(fd_d), n_zn, D, L.stream_ptr()))
             L.check(lib.d3d_scatter_rows_ptr(L.ptr(zpos_d), 3, None, L.ptr(pd_d), n_zn, 3, L.stream_ptr()))
+        if TRACE is not None:
+            t4 = time.perf_counter()
+            TRACE.append(((t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3, (t4 - t3) * 1e3, n_new, n_mg, t_mg, n_zn, t_zn))
 
     def _live_ids(self, b, which):
         """dict-order keys of the instance->patch (0) or zone->instance (1) map (FF:825, 844)."""

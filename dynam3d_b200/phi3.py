@@ -68,17 +68,24 @@ class LMEngine:
         """embed_tokens (POL:439): ids int32 [T] -> out fp32 [T, hidden]."""
         ops.embed_gather(self.w.embed, ids, out)
 
-    def prefill(self, X, cu_seqlens, positions, n_seq, max_len, last_rows):
+    def prefill(self, X, cu_seqlens, positions, n_seq, max_len, last_rows, kv_rows=0):
         """X fp32 [T, hidden] (overwritten: it is the residual stream); cu_seqlens int32 [n_seq+1]; positions int32 [T];
-        last_rows int32 [n_seq] (row of each sequence's last token).  Returns logits fp32 [n_seq, vocab]."""
+        last_rows int32 [n_seq] (row of each sequence's last token).  Returns logits fp32 [n_seq, vocab].
+        kv_rows > 0 keeps every layer's packed QKV matrix (K rotated) in `self.kv` [layers, T + kv_rows, 3*hidden]: the KV cache of `generate`."""
         w = self.w
         ops.STAGE_TAG = "lm"
         T = X.shape[0]
         if T > self.max_tokens:
             self._alloc(T)
         A16, qkv, att, h = self.A16[:T], self.qkv[:T], self.att[:T], self.h[:T]
+        if kv_rows:
+            kv = getattr(self, "kv", None)
+            if kv is None or kv.shape[1] < T + kv_rows:
+                self.kv = kv = torch.empty((len(w.layers), T + kv_rows, 3 * w.hidden), device=X.device, dtype=w.dtype)
         tab = ops.rope_table(positions, self.inv_freq, self.Dh)  # cos/sin per token, shared by all layers
-        for p in w.layers:
+        for li, p in enumerate(w.layers):
+            if kv_rows:
+                qkv = self.kv[li, :T]
             ops.rmsnorm(X, p["rms1"], self.eps, out16=A16)
             ops.gemm(A16, p["w_qkv"], out=qkv)
             ops.rope_apply(qkv, tab, self.H, self.Dh)
@@ -92,3 +99,73 @@ class LMEngine:
         logits = torch.empty((n_seq, w.vocab), device=X.device, dtype=torch.float32)
         ops.gemm(last16, w.lm_head, out=logits)
         return logits
+
+    # ------------------------------------------------------------------ greedy decode with the KV cache (POL:463-469)
+    def _c_model(self):
+        if getattr(self, "_cm", None) is None:
+            w = self.w
+            arr = (L.LMLayer * len(w.layers))()
+            for i, p in enumerate(w.layers):
+                arr[i] = L.LMLayer(p["rms1"].data_ptr(), p["w_qkv"].data_ptr(), p["w_o"].data_ptr(), p["rms2"].data_ptr(), p["w_gu"].data_ptr(),
+                                   p["w_down"].data_ptr())
+            m = L.LMModel(len(w.layers), w.hidden, self.H, self.Dh, w.ffn, w.vocab, L.kind_of(w.dtype), self.eps, arr, w.norm.data_ptr(),
+                          w.lm_head.data_ptr(), w.embed.data_ptr())
+            self._cm = (m, arr)
+        return self._cm[0]
+
+    def generate(self, X, cu_seqlens, positions, n_seq, max_len, last_rows, max_new_tokens=20, eos_ids=(), step_logits=None):
+        """Prefill + greedy decode (HF `generate(do_sample=False)` semantics: a sequence stops at its first EOS id; at most
+        `max_new_tokens` tokens).  Returns (prefill logits [n_seq, vocab], list of n_seq python lists of generated ids, ending with the EOS id if one was produced).
+        `step_logits` (a list) collects the logits of every decode step for tests."""
+        import ctypes
+        w = self.w
+        dev = X.device
+        T = X.shape[0]
+        logits0 = self.prefill(X, cu_seqlens, positions, n_seq, max_len, last_rows, kv_rows=n_seq * max_new_tokens)
+        m = self._c_model()
+        ptrs = (ctypes.c_void_p * len(w.layers))(*[self.kv[l].data_ptr() for l in range(len(w.layers))])
+        tok = torch.empty((max_new_tokens, n_seq), device=dev, dtype=torch.int32)  # tok[s] = ids produced at step s (tok[0] from the prefill)
+        L.check(L.lib().d3d_argmax_rows(L.ptr(logits0), logits0.stride(0), n_seq, w.vocab, L.ptr(tok[0]), L.stream_ptr()))
+        x32 = torch.empty((n_seq, w.hidden), device=dev, dtype=torch.float32)
+        a16 = torch.empty((n_seq, w.hidden), device=dev, dtype=w.dtype)
+        att16 = torch.empty((n_seq, w.hidden), device=dev, dtype=w.dtype)
+        h16 = torch.empty((n_seq, w.ffn), device=dev, dtype=w.dtype)
+        tab = torch.empty((n_seq, self.Dh), device=dev, dtype=torch.float32)
+        pos = torch.empty((n_seq,), device=dev, dtype=torch.int32)
+        logits = torch.empty((n_seq, w.vocab), device=dev, dtype=torch.float32)
+        host = torch.empty((max_new_tokens, n_seq), dtype=torch.int32).pin_memory()
+        events = []
+        eos = set(int(e) for e in eos_ids)
+        stream = torch.cuda.current_stream()
+
+        def finished_upto(s):  # every sequence has produced an EOS among tok[0..s] (host copy already complete)
+            h = host[: s + 1].numpy()
+            return bool(eos) and all(any(int(t) in eos for t in h[:, b]) for b in range(n_seq))
+
+        n_steps = 1
+        host[0].copy_(tok[0], non_blocking=True)
+        ev = torch.cuda.Event(); ev.record(stream); events.append(ev)
+        for s in range(max_new_tokens - 1):
+            # stop as soon as a COMPLETED earlier step shows that all sequences ended (no blocking: the GPU keeps a step or two of lead)
+            done = [i for i, e in enumerate(events) if e.query()]
+            if done and finished_upto(max(done)):
+                break
+            L.check(L.lib().d3d_lm_decode_step(ctypes.addressof(m), ctypes.cast(ptrs, ctypes.c_void_p), self.kv.stride(1), L.ptr(cu_seqlens), n_seq, T, s,
+                                               L.ptr(tok[s]), L.ptr(self.inv_freq), L.ptr(x32), L.ptr(a16), L.ptr(att16), L.ptr(h16), L.ptr(tab),
+                                               L.ptr(pos), L.ptr(logits), L.ptr(tok[s + 1]), L.stream_ptr()))
+            if step_logits is not None:  # tests: logits that chose tok[s + 1]
+                step_logits.append(logits.clone())
+            host[s + 1].copy_(tok[s + 1], non_blocking=True)
+            ev = torch.cuda.Event(); ev.record(stream); events.append(ev)
+            n_steps += 1
+        stream.synchronize()
+        out = []
+        hn = host[:n_steps].numpy()
+        for b in range(n_seq):
+            ids = []
+            for t in hn[:, b].tolist():
+                ids.append(int(t))  # like HF generate, the EOS id itself is part of the output
+                if t in eos:
+                    break
+            out.append(ids)
+        return logits0, out

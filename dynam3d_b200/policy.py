@@ -124,6 +124,8 @@ class Dynam3D_VLN(nn.Module):
         self.llava = _Llava(precise=precise)
         self.tokenize = None      # callable(str) -> list[int]; the real one is the llava-phi-3 tokenizer (POL:131)
         self.detokenize = None    # callable(list[int]) -> str
+        self.eos_token_ids = (32000, 32007)  # <|endoftext|>, <|end|> of the llava-phi-3-mini tokenizer (generation stops there, POL:463)
+        self.max_new_tokens = 20             # POL:463
         self._PW = None
         self._side = None
 
@@ -318,8 +320,16 @@ class Dynam3D_VLN(nn.Module):
             return self._forward_logits(observations, instructions, agent_positions, agent_heading_angles, depth_scale, delete_old_features,
                                         num_of_views, input_ids)
 
+    def generate_ids(self, observations, instructions, agent_positions, agent_heading_angles, depth_scale=(0.0, 10.0),
+                     delete_old_features=True, num_of_views=1, input_ids=None):
+        """The whole of POL:430-463: the step above followed by the greedy decode (KV cache, <= max_new_tokens ids per episode, EOS cut).
+        Returns (next-action logits [B, vocab], list of B id lists)."""
+        with L.stream_scope():
+            return self._forward_logits(observations, instructions, agent_positions, agent_heading_angles, depth_scale, delete_old_features,
+                                        num_of_views, input_ids, generate=True)
+
     def _forward_logits(self, observations, instructions, agent_positions, agent_heading_angles, depth_scale, delete_old_features,
-                        num_of_views, input_ids):
+                        num_of_views, input_ids, generate=False):
         ff = self.feature_fields
         B = ff.batch_size
         patch, inst, zone = self.encode_step(observations, agent_positions, agent_heading_angles, depth_scale, delete_old_features, num_of_views)
@@ -346,6 +356,10 @@ class Dynam3D_VLN(nn.Module):
         pos = torch.cat([torch.arange(n, dtype=torch.int32) for n in lens]).to(self.device)
         last = (cu[1:] - 1).to(torch.int32).contiguous()
         self.last_seq_lens = lens
+        if generate:
+            if self.precise:
+                raise NotImplementedError("the precise (split-operand) mode covers the prefill only")
+            return lm.generate(X, cu, pos, B, max(lens), last, max_new_tokens=self.max_new_tokens, eos_ids=self.eos_token_ids)
         if self.precise:
             from . import precise as PR
             return PR.lm_prefill(lm, X, cu, pos, B, max(lens), last)
@@ -355,11 +369,20 @@ class Dynam3D_VLN(nn.Module):
                 delete_old_features=True, num_of_views=1, is_train=False, input_ids=None, return_logits=False):
         if is_train:
             raise NotImplementedError("training branch (POL:366-427) is a SURVEY.md 8(f) 'next' row")
-        logits = self.forward_logits(observations, instructions, agent_positions, agent_heading_angles, depth_scale, delete_old_features,
-                                     num_of_views, input_ids)
         if return_logits or self.detokenize is None:
-            return logits
-        raise NotImplementedError("greedy decode with KV cache (POL:463-469) is the next SURVEY.md 8(f) row; use return_logits=True")
+            return self.forward_logits(observations, instructions, agent_positions, agent_heading_angles, depth_scale, delete_old_features,
+                                       num_of_views, input_ids)
+        # eval branch (POL:463-469): generate, decode the text, cut at "<|end|>", remember the action
+        _, ids = self.generate_ids(observations, instructions, agent_positions, agent_heading_angles, depth_scale, delete_old_features,
+                                   num_of_views, input_ids)
+        texts = []
+        for b, seq in enumerate(ids):
+            txt = self.detokenize(seq)
+            txt = txt[:txt.find("<|end|>")]  # POL:465, literally (no "<|end|>" -> find() = -1 drops the last character)
+            texts.append(txt)
+            self.feature_fields.history_actions[b].pop(0)                # POL:466-468 (Q10: the reference's lists alias each other)
+            self.feature_fields.history_actions[b].append(txt + "\n")
+        return texts
 
 
 class Policy_Dynam3D_VLN(nn.Module):

@@ -172,6 +172,37 @@ int d3d_rope(void* qkv, int64_t ld, const int* pos, const float* inv_freq, int T
 int d3d_rope_table(const int* pos, const float* inv_freq, int T, int Dh, float* tab, void* stream);
 int d3d_rope_apply(void* qkv, int64_t ld, const float* tab, int T, int H, int Dh, int kind, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Greedy decode with a KV cache (POL:463 `llava.generate(max_new_tokens=20, do_sample=False)`).
+ * The prefill keeps every layer's packed QKV matrix [rows_cap, 3*hidden] (K already rotated): that IS the cache.  Decode step s
+ * appends the new tokens' rows at t_prefill + s*n_seq + b.  HBM-bound on the weights: d3d_gemm_skinny streams each weight matrix once.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+  const float* rms1; const void* w_qkv; const void* w_o; const float* rms2;
+  const void* w_gu;   /* row-interleaved gate/up [2*ffn, hidden] */
+  const void* w_down;
+} d3d_lm_layer;
+typedef struct {
+  int n_layers, hidden, n_heads, head_dim, ffn, vocab;
+  int kind;                    /* D3D_F16 | D3D_BF16: weights, activations and cache */
+  float eps;
+  const d3d_lm_layer* layers;  /* HOST array [n_layers] of device pointers */
+  const float* norm; const void* lm_head; const void* embed;
+} d3d_lm_model;
+/* C = epi(A @ W^T) for 1..16 activation rows (same argument struct and epilogue contract as d3d_gemm; K % 32 == 0). */
+int d3d_gemm_skinny(const d3d_gemm_args* args_h, void* stream);
+/* out[r] = index of the FIRST maximum of x[r, :n] (torch.argmax / HF greedy search). */
+int d3d_argmax_rows(const float* x, int64_t ld, int rows, int n, int* out, void* stream);
+/* Attention of the step's n_seq new query rows over their sequences' cached keys / values (prefill rows [cu[b], cu[b+1]) + decode rows). */
+int d3d_decode_attention(const void* qkv, int64_t ld, const int* cu_seqlens, int n_seq, int t_prefill, int step, int H, int Dh, int kind,
+                         float scale, void* out, int64_t ldo, void* stream);
+/* One decode step for all sequences: embeds tokens_in [n_seq], runs the layers (qkv_layers_h: HOST array of the per-layer cache base
+ * pointers), writes logits [n_seq, vocab] fp32 and next_tokens [n_seq].  Scratch: x32 [n_seq,hidden] f32, a16 [n_seq,hidden], att16
+ * [n_seq,hidden], h16 [n_seq,ffn] 16-bit, rope_tab [n_seq,head_dim] f32, pos [n_seq] int32. */
+int d3d_lm_decode_step(const d3d_lm_model* m_h, void* const* qkv_layers_h, int64_t ld_qkv, const int* cu_seqlens, int n_seq, int t_prefill,
+                       int step, const int* tokens_in, const float* inv_freq, float* x32, void* a16, void* att16, void* h16, float* rope_tab,
+                       int* pos, float* logits, int* next_tokens, void* stream);
+
 /* embed_tokens (POL:439): out[t, :D] = table16[ids[t], :D] as fp32. */
 int d3d_embed_gather(const void* table, int kind, const int* ids, int T, int D, float* out, int64_t ldo, void* stream);
 

@@ -209,3 +209,43 @@ def lm_prefill(embeds, seq_lens, P, n_layers, n_heads, eps=1e-5, theta=10000.0, 
     last = torch.tensor([sum(seq_lens[:i + 1]) - 1 for i in range(len(seq_lens))])
     h = rms_norm(x[last], P[prefix + "norm.weight"], eps)
     return linear(h, P["lm_head.weight"], None, rnd)
+
+
+def lm_teacher_forced_logits(embeds, seq_lens, tokens, P, n_layers, n_heads, rnd=None, prefix="model.", **kw):
+    """Next-token logits after feeding `tokens[b][:s]` for every s (no cache: each step re-runs the full prefill over
+    [prompt || generated], the arithmetic HF `generate` performs with use_cache=False; POL:463).  tokens: list of B id lists (same length n).
+    Returns [n + 1, B, vocab]: entry s = logits that choose token s."""
+    r = rnd or _id
+    table = P[prefix + "embed_tokens.weight"].to(torch.float32)
+    parts, s0 = [], 0
+    for n in seq_lens:
+        parts.append(embeds[s0:s0 + n].to(torch.float32))
+        s0 += n
+    n_new = len(tokens[0])
+    out = []
+    for s in range(n_new + 1):
+        cur = [torch.cat([parts[b], r(table[torch.tensor(tokens[b][:s], dtype=torch.long)])], 0) if s else parts[b] for b in range(len(seq_lens))]
+        out.append(lm_prefill(torch.cat(cur, 0), [c.shape[0] for c in cur], P, n_layers, n_heads, rnd=rnd, prefix=prefix, **kw))
+    return torch.stack(out, 0)
+
+
+def lm_greedy_decode(embeds, seq_lens, P, n_layers, n_heads, max_new_tokens=20, eos_ids=(), rnd=None, prefix="model.", **kw):
+    """HF greedy search restated without a cache; returns B id lists (ending with the EOS id when one was produced).  Only meaningful where the arg-max margins exceed the
+    arithmetic noise of the implementation under test (tests use lm_teacher_forced_logits for the numeric comparison)."""
+    B = len(seq_lens)
+    outs, done = [[] for _ in range(B)], [False] * B
+    for _ in range(max_new_tokens):
+        n = max(len(o) for o in outs)
+        padded = [o + [0] * (n - len(o)) for o in outs]  # finished sequences keep a dummy continuation (their logits are ignored)
+        lg = lm_teacher_forced_logits(embeds, seq_lens, padded, P, n_layers, n_heads, rnd=rnd, prefix=prefix, **kw)[-1] if n else \
+            lm_prefill(embeds, seq_lens, P, n_layers, n_heads, rnd=rnd, prefix=prefix, **kw)
+        for b in range(B):
+            if done[b]:
+                continue
+            t = int(lg[b].argmax())
+            outs[b].append(t)  # HF keeps the EOS id as the last token
+            if t in eos_ids:
+                done[b] = True
+        if all(done):
+            break
+    return outs
