@@ -8,7 +8,8 @@
 //                         fp32 partials of the 8 warps are summed in a fixed order in smem (deterministic), then +bias / SwiGLU /
 //                         +fp32 residual and the store.
 //   decode_attn_kernel  : one CTA per (sequence, head); keys / values = the sequence's prefill rows plus its rows of the earlier
-//                         decode steps in the per-layer QKV cache; one warp per key, online softmax, 8-way merge in smem.
+//                         decode steps in the per-layer QKV cache; 16 warps, each loads 8 keys' K and V rows back to back (8-byte
+//                         loads), batched online softmax, 16-way merge in smem.
 //   argmax_kernel       : first maximum of every logit row (torch.argmax / HF greedy tie-break).
 //   d3d_lm_decode_step  : the whole step (32 layers) behind ONE C call, so the host issues ~260 launches without interpreter overhead.
 #include "common.cuh"
@@ -22,6 +23,7 @@ namespace {
 
 constexpr int SK_WARPS = 8;
 constexpr int SK_NT = 2;  // n-tiles (8 weight rows each) per CTA
+constexpr int SK_U = 2;   // K super-steps (128 elements each) whose loads a warp issues before it starts multiplying
 
 __device__ __forceinline__ uint4 ldg_stream16(const void* p) {
   uint4 v;
@@ -45,9 +47,12 @@ struct SkinnyEpi {
   int act, out_kind;
 };
 
-// Fragment trick: thread (g = lane/4, kq = lane%4) loads 16 contiguous bytes (8 K-elements at k0 = 32*ks + 8*kq) of A row g / g+8 and of
-// W row n0+g.  MMA 1 uses elements {0,1} as K-slots (2kq, 2kq+1) and {2,3} as slots (2kq+8, 2kq+9); MMA 2 uses {4,5} and {6,7} the same
-// way.  A and W use the same slot -> k map, so the products pair up correctly and the 32 k of the step are each used exactly once.
+// Fragment trick: a K "super-step" is 128 elements.  Thread (g = lane/4, kq = lane%4) loads the 64 contiguous bytes (32 K-elements at
+// k0 = 128*ss + 32*kq) of A row g / g+8 and of W row n0+g, so a warp instruction group reads 256 contiguous bytes of each of its 8 weight
+// rows (DRAM-friendly).  Every 16-byte piece feeds two MMAs: elements {0,1} are K-slots (2kq, 2kq+1), {2,3} slots (2kq+8, 2kq+9) of the
+// first, {4,5} / {6,7} of the second.  A and W use the same slot -> k map, so the products pair up and each k is used exactly once.
+// HI: rows 8..15 of A exist (M > 8); otherwise their fragment registers are zero and never loaded.
+template <bool HI>
 __global__ void __launch_bounds__(SK_WARPS * 32) skinny_gemm_kernel(const uint16_t* __restrict__ A, long long lda, const uint16_t* __restrict__ W,
                                                                     long long ldw, int M, int N, int K, int kind, SkinnyEpi ep) {
   __shared__ float red[SK_WARPS][SK_NT][16][8];
@@ -59,31 +64,46 @@ __global__ void __launch_bounds__(SK_WARPS * 32) skinny_gemm_kernel(const uint16
   for (int t = 0; t < SK_NT; ++t)
 #pragma unroll
     for (int i = 0; i < 4; ++i) acc[t][i] = 0.f;
-  const bool lo_ok = g < M, hi_ok = g + 8 < M;
-  const uint16_t* a_lo_p = A + (long long)g * lda + kq * 8;
-  const uint16_t* a_hi_p = A + (long long)(g + 8) * lda + kq * 8;
+  const bool lo_ok = g < M, hi_ok = HI && g + 8 < M;
+  const uint16_t* a_lo_p = A + (long long)(lo_ok ? g : 0) * lda + kq * 32;
+  const uint16_t* a_hi_p = A + (long long)(hi_ok ? g + 8 : 0) * lda + kq * 32;
   const uint16_t* w_p[SK_NT];
   bool w_ok[SK_NT];
 #pragma unroll
   for (int t = 0; t < SK_NT; ++t) {
     const int n = n_base + t * 8 + g;
     w_ok[t] = n < N;
-    w_p[t] = W + (long long)(w_ok[t] ? n : 0) * ldw + kq * 8;
+    w_p[t] = W + (long long)(w_ok[t] ? n : 0) * ldw + kq * 32;
   }
-  const int steps = K >> 5;
-#pragma unroll 4
-  for (int ks = warp; ks < steps; ks += SK_WARPS) {
-    const int off = ks << 5;
-    uint4 wv[SK_NT];
+  // the warp owns super-steps warp, warp+8, ...; it issues the loads of SK_U super-steps back to back, then multiplies.
+  // K % 128 != 0: the 32-element pieces beyond K are skipped (K % 32 == 0 is required)
+  const int ssteps = (K + 127) >> 7;
+  for (int ss0 = warp; ss0 < ssteps; ss0 += SK_WARPS * SK_U) {
+    uint4 wv[SK_U][SK_NT][4], al[SK_U][4], ah[SK_U][4];
 #pragma unroll
-    for (int t = 0; t < SK_NT; ++t) wv[t] = w_ok[t] ? ldg_stream16(w_p[t] + off) : make_uint4(0, 0, 0, 0);
-    const uint4 al = lo_ok ? __ldg(reinterpret_cast<const uint4*>(a_lo_p + off)) : make_uint4(0, 0, 0, 0);
-    const uint4 ah = hi_ok ? __ldg(reinterpret_cast<const uint4*>(a_hi_p + off)) : make_uint4(0, 0, 0, 0);
+    for (int u = 0; u < SK_U; ++u) {
+      const int off = (ss0 + u * SK_WARPS) << 7;
+      const bool in = off + kq * 32 < K;
 #pragma unroll
-    for (int t = 0; t < SK_NT; ++t) {
-      mma16816(acc[t], al.x, ah.x, al.y, ah.y, wv[t].x, wv[t].y, kind);
-      mma16816(acc[t], al.z, ah.z, al.w, ah.w, wv[t].z, wv[t].w, kind);
+      for (int t = 0; t < SK_NT; ++t)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) wv[u][t][c] = (in && w_ok[t]) ? ldg_stream16(w_p[t] + off + c * 8) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        al[u][c] = (in && lo_ok) ? __ldg(reinterpret_cast<const uint4*>(a_lo_p + off + c * 8)) : make_uint4(0, 0, 0, 0);
+        if (HI) ah[u][c] = (in && hi_ok) ? __ldg(reinterpret_cast<const uint4*>(a_hi_p + off + c * 8)) : make_uint4(0, 0, 0, 0);
+        else ah[u][c] = make_uint4(0, 0, 0, 0);
+      }
     }
+#pragma unroll
+    for (int u = 0; u < SK_U; ++u)
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int t = 0; t < SK_NT; ++t) {
+          mma16816(acc[t], al[u][c].x, ah[u][c].x, al[u][c].y, ah[u][c].y, wv[u][t][c].x, wv[u][t][c].y, kind);
+          mma16816(acc[t], al[u][c].z, ah[u][c].z, al[u][c].w, ah[u][c].w, wv[u][t][c].z, wv[u][t][c].w, kind);
+        }
   }
 #pragma unroll
   for (int t = 0; t < SK_NT; ++t) {
@@ -139,45 +159,70 @@ __global__ void __launch_bounds__(SK_WARPS * 32) skinny_gemm_kernel(const uint16
 // ---- decode attention over the per-layer QKV cache ----
 // cache row layout: [q (H*Dh) | k (H*Dh) | v (H*Dh)] 16-bit; sequence b owns the prefill rows [cu[b], cu[b+1]) and the decode rows
 // t_prefill + s*n_seq + b for s = 0..step (the last one is the query's own row).  Dh % 32 == 0 (96 or 64), Dh <= 128.
-constexpr int DA_WARPS = 8;
+constexpr int DA_WARPS = 16;
+constexpr int DA_U = 8;  // keys whose K and V rows a warp loads back to back (bytes in flight: the kernel is HBM-bound)
 template <int DH>
-__global__ void __launch_bounds__(DA_WARPS * 32) decode_attn_kernel(const uint16_t* __restrict__ qkv, long long ld, const int* __restrict__ cu,
+__global__ void __launch_bounds__(DA_WARPS * 32, 1) decode_attn_kernel(const uint16_t* __restrict__ qkv, long long ld, const int* __restrict__ cu,
                                                                    int n_seq, int t_prefill, int step, int H, int kind, float scale,
                                                                    uint16_t* __restrict__ out, long long ldo) {
-  constexpr int VPL = DH / 32;  // elements per lane (3 for head_dim 96)
+  constexpr int ACTIVE = DH / 4;  // lanes that hold 4 consecutive channels (8-byte loads); the other lanes idle (head_dim 96: 24 of 32)
   __shared__ float s_m[DA_WARPS], s_l[DA_WARPS], s_acc[DA_WARPS][DH];
   const int b = blockIdx.x, h = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool on = lane < ACTIVE;
   const int p0 = cu[b], n_pre = cu[b + 1] - p0;
   const int n_keys = n_pre + step + 1;
   const long long q_row = (long long)t_prefill + (long long)step * n_seq + b;
-  float q[VPL];
+  auto load4 = [&](long long row, long long col, float (&f)[4]) {
+    const uint2 v = on ? *reinterpret_cast<const uint2*>(qkv + row * ld + col + lane * 4) : make_uint2(0, 0);
+    const float2 a = unpack16x2(v.x, kind), c = unpack16x2(v.y, kind);
+    f[0] = a.x; f[1] = a.y; f[2] = c.x; f[3] = c.y;
+  };
+  float q[4];
+  load4(q_row, (long long)h * DH, q);
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) q[i] = ld16(qkv, (size_t)(q_row * ld + (long long)h * DH + lane * VPL + i), kind) * scale;
-  float m = -INFINITY, l = 0.f, acc[VPL];
+  for (int i = 0; i < 4; ++i) q[i] *= scale;
+  float m = -INFINITY, l = 0.f, acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const long long k_col = (long long)(H + h) * DH, v_col = (long long)(2 * H + h) * DH;
+  for (int j0 = warp * DA_U; j0 < n_keys; j0 += DA_WARPS * DA_U) {
+    float kf[DA_U][4], vf[DA_U][4], s[DA_U];
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) acc[i] = 0.f;
-  const long long k_off = (long long)(H + h) * DH + lane * VPL, v_off = (long long)(2 * H + h) * DH + lane * VPL;
-  for (int j = warp; j < n_keys; j += DA_WARPS) {
-    const long long row = j < n_pre ? (long long)(p0 + j) : (long long)t_prefill + (long long)(j - n_pre) * n_seq + b;
-    float kv[VPL], vv[VPL], s = 0.f;
-#pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      kv[i] = ld16(qkv, (size_t)(row * ld + k_off + i), kind);
-      vv[i] = ld16(qkv, (size_t)(row * ld + v_off + i), kind);
-      s += q[i] * kv[i];
+    for (int u = 0; u < DA_U; ++u) {
+      const int j = min(j0 + u, n_keys - 1);  // clamped: the duplicate is masked below
+      const long long row = j < n_pre ? (long long)(p0 + j) : (long long)t_prefill + (long long)(j - n_pre) * n_seq + b;
+      load4(row, k_col, kf[u]);
+      load4(row, v_col, vf[u]);
     }
-    s = warp_sum(s);
-    const float m_new = fmaxf(m, s);
-    const float c = __expf(m - m_new), p = __expf(s - m_new);  // exp(-inf) = 0 on the first key
-    l = l * c + p;
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) acc[i] = acc[i] * c + p * vv[i];
-    m = m_new;
+    for (int u = 0; u < DA_U; ++u) s[u] = (q[0] * kf[u][0] + q[1] * kf[u][1]) + (q[2] * kf[u][2] + q[3] * kf[u][3]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < DA_U; ++u) s[u] += __shfl_xor_sync(0xffffffffu, s[u], o);
+    float mx = m;
+#pragma unroll
+    for (int u = 0; u < DA_U; ++u) {
+      if (j0 + u >= n_keys) s[u] = -INFINITY;
+      mx = fmaxf(mx, s[u]);
+    }
+    const float c = __expf(m - mx);  // 0 on the first batch (m = -inf)
+    l *= c;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] *= c;
+#pragma unroll
+    for (int u = 0; u < DA_U; ++u) {
+      const float p = __expf(s[u] - mx);
+      l += p;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] += p * vf[u][i];
+    }
+    m = mx;
   }
   if (lane == 0) { s_m[warp] = m; s_l[warp] = l; }
+  if (on) {
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) s_acc[warp][lane * VPL + i] = acc[i];
+    for (int i = 0; i < 4; ++i) s_acc[warp][lane * 4 + i] = acc[i];
+  }
   __syncthreads();
   if (threadIdx.x < DH) {
     float gm = -INFINITY;
@@ -240,7 +285,8 @@ int skinny(const void* A, long long lda, const void* W, long long ldw, void* C, 
   D3D_REQUIRE(kind == D3D_F16 || kind == D3D_BF16, "16-bit operands");
   D3D_REQUIRE(act != D3D_ACT_SWIGLU || ((N % 2) == 0 && residual == nullptr), "swiglu needs even N, no residual");
   SkinnyEpi ep{C, ldc, bias, residual, ldres, act, out_kind};
-  skinny_gemm_kernel<<<d3d_cdiv(N, 8 * SK_NT), SK_WARPS * 32, 0, st>>>((const uint16_t*)A, lda, (const uint16_t*)W, ldw, M, N, K, kind, ep);
+  if (M > 8) skinny_gemm_kernel<true><<<d3d_cdiv(N, 8 * SK_NT), SK_WARPS * 32, 0, st>>>((const uint16_t*)A, lda, (const uint16_t*)W, ldw, M, N, K, kind, ep);
+  else skinny_gemm_kernel<false><<<d3d_cdiv(N, 8 * SK_NT), SK_WARPS * 32, 0, st>>>((const uint16_t*)A, lda, (const uint16_t*)W, ldw, M, N, K, kind, ep);
   D3D_CHECK_LAUNCH();
   return 0;
 }
