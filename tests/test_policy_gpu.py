@@ -68,3 +68,38 @@ def test_full_step_matches_oracle(cfg):
         print(f"step {t}: S={lens} |logit|max={want.abs().max().item():.2f} err={err:.2e}")
         assert err <= 8e-3
         assert torch.equal(got.argmax(-1), want.argmax(-1))
+
+
+def test_forward_eval_branch_returns_text_and_updates_history():
+    """POL:463-469 through the public `forward`: tokenizer in, greedy decode with the KV cache, text cut at "<|end|>", history rotated."""
+    from dynam3d_b200 import synth
+    B, V = 2, 1
+    net, _ = _build(6, 2, 2, B, q1_fix=True)
+    net.tokenize = synth.ToyTokenizer()
+    vocab = {32007: "<|end|>"}
+    net.detokenize = lambda ids: "".join(vocab.get(i, chr(97 + i % 26)) for i in ids)
+    net.max_new_tokens = 6
+    # two independent history lists (the reference aliases them, Q10; the test wants to see both episodes)
+    net.feature_fields.history_actions = [["none\n"] * 4 for _ in range(B)]
+    eps = [synth.make_episode(60 + b, n_steps=1, num_views=V, rgb_size=224, n_seg=16, seg_kind="voronoi") for b in range(B)]
+    obs = {"rgb": torch.from_numpy(np.concatenate([eps[b][0]["rgb"] for b in range(B)], 0)),
+           "depth": torch.from_numpy(np.concatenate([eps[b][0]["depth"] for b in range(B)], 0)),
+           "patch_segm": np.stack([eps[b][0]["segm"] for b in range(B)], 0)}
+    pos, head = [eps[b][0]["position"] for b in range(B)], [eps[b][0]["heading"] for b in range(B)]
+    instr = [synth.make_instruction(b) for b in range(B)]
+    # reference run of the same step for the ids (fresh memory), then the text path
+    logits, ids = net.generate_ids(obs, instr, pos, head, num_of_views=V)
+    assert logits.shape == (B, 32064) and all(1 <= len(s) <= 6 for s in ids)
+    assert [s[0] for s in ids] == logits.argmax(-1).cpu().tolist()  # the first generated id is the prefill's arg-max
+    net.feature_fields.reset(B)
+    net.feature_fields.history_actions = [["none\n"] * 4 for _ in range(B)]
+    net.eos_token_ids = (ids[0][2],)  # make the third token of episode 0 the end token
+    vocab[ids[0][2]] = "<|end|>"
+    texts = net(obs, instr, pos, head, num_of_views=V)
+    assert isinstance(texts, list) and len(texts) == B and all(isinstance(t, str) for t in texts)
+    k = ids[0].index(ids[0][2])  # greedy decoding of random weights may repeat ids: the text ends at the FIRST occurrence
+    assert len(texts[0]) == k and "<|end|>" not in texts[0]
+    for b in range(B):
+        h = net.feature_fields.history_actions[b]
+        assert len(h) == 4 and h[-1] == texts[b] + "\n" and h[0] == "none\n"
+    assert net.convert_text_to_action(["stop"]) == [-100]
