@@ -207,9 +207,9 @@ def run_engine(args):
     host_in = [{"rgb": torch.from_numpy(s["rgb"]).pin_memory(), "depth": torch.from_numpy(s["depth"]).pin_memory(), "patch_segm": s["segm"]} for s in steps]
     from dynam3d_b200.sharding import allgather_last_logits
 
-    def one_step(i, inputs):
+    def one_step(i, inputs, gather=True):
         lg = net.forward_logits(inputs[i], instr, steps[i]["pos"], steps[i]["head"], num_of_views=VIEWS)
-        if world > 1:
+        if world > 1 and gather:
             lg = allgather_last_logits(lg)
         return lg
 
@@ -257,7 +257,7 @@ def run_engine(args):
     stages = []
     if rank == 0:
         ops.STAGE_PROFILE = []
-        one_step(args.warmup, dev_in)
+        one_step(args.warmup, dev_in, gather=False)  # rank 0 only: no collective in this extra step
         torch.cuda.synchronize()
         prof_s, ops.STAGE_PROFILE = ops.STAGE_PROFILE, None
         peak_tf_, peak_hbm_, _ = peaks()
