@@ -300,8 +300,8 @@ def run_engine(args):
             "gpu_launches": int(launches),
             "stages": stages,  # one extra profiled step: per-stage algorithmic FLOPs or bytes / CUDA-event time vs the measured peaks
             "clocks": sampler.summary(),
-            "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all tcgen05 GEMM launches of the timed region)", "achieved": achieved,
-                         "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None, "peak_source": which,
+            "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_pair_kernel<256> / gemm_tcgen05_kernel<128|256> (all tcgen05 GEMM launches of the timed region)", "achieved": achieved,
+                         "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None, "traffic_note": "per-launch DRAM bytes of the four dominant shapes (ncu --set full) = 1.0-1.4x their algorithmic bytes: profiles/ncu_full_gemm_r01_final_summary.json", "peak_source": which,
                          "gemm_share_of_step": gemm_ms / ms, "gemm_launches": len(prof)},
         }
         if world == 1 and not args.no_cpu_baseline:

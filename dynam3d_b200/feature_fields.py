@@ -154,13 +154,13 @@ class Feature_Fields(nn.Module):
         self.history_actions = []
 
     def __del__(self):
-        h = getattr(self, "_h", None)
-        if h:
-            try:
+        try:  # may run during interpreter shutdown, when torch's module machinery is already gone
+            h = self.__dict__.get("_h")
+            if h:
+                self.__dict__["_h"] = None
                 L.lib().d3d_ffh_destroy(h)
-            except Exception:
-                pass
-            self._h = None
+        except Exception:
+            pass
 
     def load_state_dict(self, state_dict, strict=True):
         # Q12: convert_ckpt.py keeps Pretrain-only keys (nerf_*, patch_to_nerf_*) that this module does not own
@@ -568,6 +568,12 @@ class Feature_Fields(nn.Module):
             plan = self._begin_step(V, P, segm, stage, xyz_h)
             for ix in range(V):
                 self._update_view(ix, plan)
+            self._run_deferred()
+
+    def _run_deferred(self):
+        fn, self._deferred = getattr(self, "_deferred", None), None
+        if fn is not None:
+            fn()
 
     def _unproject_posed(self, batch_depth, batch_K, batch_rot, batch_trans, depth_scale, depth_trunc, V):
         """a4' (FF:50-60, 518, 533-546): all (episode, view) images of the step in one kernel instead of 8 joblib threads of open3d."""
@@ -669,9 +675,12 @@ class Feature_Fields(nn.Module):
         res[:, 0:3] = centres
         # ---- 4. ONE device->host copy per view, then the planner's second half (FF:623-756) ----
         res_h = res.to("cpu", non_blocking=True)
+        copied = torch.cuda.Event()
+        copied.record()
+        self._run_deferred()  # the previous view's zone pass: executes while the host waits for / plans this view
         if TRACE is not None:
             t1 = time.perf_counter()
-        torch.cuda.current_stream().synchronize()
+        copied.synchronize()
         if TRACE is not None:
             t2 = time.perf_counter()
         res_h = res_h.numpy()
@@ -716,6 +725,7 @@ class Feature_Fields(nn.Module):
         if n_zn:
             o = zn_owner[:n_zn]
             xyz_ptr = ip[o].copy()
+            key_dev = None
             if zn_keys[:n_zn].any():  # Q5: an updated zone is embedded from its members' voxel-centre keys
                 key_arrays = []
                 need = np.flatnonzero(after.reshape(B, 3)[:, 2])
@@ -729,10 +739,16 @@ class Feature_Fields(nn.Module):
                 use = zn_keys[:n_zn] != 0
                 xyz_ptr[use] = kp[o][use]
             ptrs = np.stack([xyz_ptr, xyz_ptr, xyz_ptr, ifp[o]])
-            zf, zpos_d, (fd_d, pd_d) = self._pool_pass(zn_src[:t_zn + n_zn], zn_seq[:t_zn + n_zn], zn_cu, ptrs, zn_pos[:n_zn], n_zn, ml_zn, 1, 1, True,
-                                                       extra=[zfp[o] + 4 * D * zn_slot[:n_zn], zp[o] + 12 * zn_slot[:n_zn]])
-            L.check(lib.d3d_scatter_rows_ptr(L.ptr(zf), D, None, L.ptr(fd_d), n_zn, D, L.stream_ptr()))
-            L.check(lib.d3d_scatter_rows_ptr(L.ptr(zpos_d), 3, None, L.ptr(pd_d), n_zn, 3, L.stream_ptr()))
+
+            def zone_pass(_keep_alive=key_dev):  # the uploaded key arrays are referenced by address only: they must outlive the launch
+                zf, zpos_d, (fd_d, pd_d) = self._pool_pass(zn_src[:t_zn + n_zn], zn_seq[:t_zn + n_zn], zn_cu, ptrs, zn_pos[:n_zn], n_zn, ml_zn, 1, 1,
+                                                           True, extra=[zfp[o] + 4 * D * zn_slot[:n_zn], zp[o] + 12 * zn_slot[:n_zn]])
+                L.check(lib.d3d_scatter_rows_ptr(L.ptr(zf), D, None, L.ptr(fd_d), n_zn, D, L.stream_ptr()))
+                L.check(lib.d3d_scatter_rows_ptr(L.ptr(zpos_d), 3, None, L.ptr(pd_d), n_zn, 3, L.stream_ptr()))
+            # Zone tokens are only read by the export: nothing in the next view's proposal phase depends on them.  The pass is issued
+            # right after the next view's result copy (see above), so the device runs it while the host plans that view; stream order keeps
+            # it before the next view's slot writes, i.e. it still sees exactly the instance features of THIS view.
+            self._deferred = zone_pass
         if TRACE is not None:
             t4 = time.perf_counter()
             TRACE.append(((t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3, (t4 - t3) * 1e3, n_new, n_mg, t_mg, n_zn, t_zn))
