@@ -3,10 +3,11 @@
 //   S = Q K^T      : tcgen05.mma kind::f16, M=128 (queries) x N=128 (keys) x K=64, Q and K tiles TMA-loaded (SWIZZLE_128B,
 //                    K-major) straight out of the packed [T, 3*H*64] QKV matrix, accumulator in TMEM (128 columns)
 //   softmax        : 8 warps, two threads per query row (TMEM lane == row; each owns 64 of the tile's 128 keys): tcgen05.ld of S,
-//                    running max / sum in registers (row max exchanged through smem), ex2.approx, P written to shared memory in
-//                    the UMMA K-major SWIZZLE_128B layout
-//   O_j = P V      : tcgen05.mma M=128 x N=64 x K=128 with V as an MN-major B operand (V rows are keys, d contiguous),
-//                    accumulator in TMEM (64 columns); the softmax warps fold O_j into their fp32 row with the running rescale
+//                    running max / sum in registers, ex2.approx, P written to shared memory in the UMMA K-major SWIZZLE_128B layout.
+//                    The two key halves of a row are INDEPENDENT online softmaxes (own base, own sum, own O accumulator), merged
+//                    once in the epilogue -- no per-tile exchange or block barrier between the halves.
+//   O_j = P V      : per key half, tcgen05.mma M=128 x N=64 x K=64 with V as an MN-major B operand (V rows are keys, d contiguous),
+//                    two accumulators in TMEM (2 x 64 columns) that stay there over all key tiles (lazy rescale)
 // One CTA = 128 queries of one (sequence, head); K/V double-buffered; 2 CTAs per SM (112 KB smem, 256 TMEM columns each) so one
 // CTA's softmax overlaps the other's MMAs.  Replaces nn.MultiheadAttention's attention in CLIPM:181-183 and the LLaVA tower.
 #include <type_traits>
@@ -29,7 +30,7 @@ constexpr int SMEM_BAR = 7 * TILE_BYTES;
 constexpr int SMEM_XMAX = SMEM_BAR + 128;                // [2][128] bf16 row-max exchange between the two column halves
 constexpr int SMEM_BYTES = SMEM_XMAX + 512;              // 115328; 2 CTAs/SM: 2 x (115328 + 1024 reserved) <= 233472 (228 KB)
 static_assert(2 * (SMEM_BYTES + 1024) <= 233472, "two CTAs per SM");
-constexpr int TMEM_COLS = 256;                           // S: [0,128)  O: [128,192)
+constexpr int TMEM_COLS = 256;                           // S: [0,128)  O of key half 0: [128,192)  O of key half 1: [192,256)
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -251,7 +252,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, uint16_t* __restrict_
           // A = P: 16 keys = 32 B inside a 64-key atom (+2), next atom +16 KB; B = V: 16 key rows = 2048 B (+128).
           // O accumulates in TMEM over all key tiles (the tensor pipe executes the products in issue order).
           const uint64_t a = dp + (uint64_t)((k & 3) * 2 + (k >> 2) * (TILE_BYTES >> 4));
-          umma_f16(tmem_o, a, dv + (uint64_t)(k * 128), idesc_o, (j | k) ? 1u : 0u);
+          // keys 0..63 of the tile (k < 4) accumulate into O half 0, keys 64..127 into O half 1 (independent softmax bases)
+          umma_f16(tmem_o + (uint32_t)((k >> 2) * D), a, dv + (uint64_t)(k * 128), idesc_o, (j | (k & 3)) ? 1u : 0u);
         }
         umma_commit(bar(3 + st));  // K_j / V_j stage free
         umma_commit(bar(8));       // O += P_j V_j done: P buffer free, O readable
@@ -272,11 +274,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, uint16_t* __restrict_
     float m = -INFINITY, l = 0.f;
     const uint32_t p_row = sbase + SMEM_P + (uint32_t)hf * (uint32_t)TILE_BYTES + (uint32_t)r * 128u;  // this half's 64-key atom
     const uint32_t sw = (uint32_t)(r & 7);
-    const uint32_t xmax_mine = sbase + SMEM_XMAX + (uint32_t)(hf * 128 + r) * 2u;
-    const uint32_t xmax_other = sbase + SMEM_XMAX + (uint32_t)((hf ^ 1) * 128 + r) * 2u;
-    // the row sums are exchanged (fp32) through the P buffer once the last P.V product has completed
-    const uint32_t xsum_mine = sbase + SMEM_P + (uint32_t)(hf * 128 + r) * 4u;
-    const uint32_t xsum_other = sbase + SMEM_P + (uint32_t)((hf ^ 1) * 128 + r) * 4u;
+    // (base, sum) of the two key halves are exchanged (fp32) through the P buffer once the last P.V product has completed
+    const uint32_t xsum_mine = sbase + SMEM_P + (uint32_t)(hf * 128 + r) * 8u;
+    const uint32_t xsum_other = sbase + SMEM_P + (uint32_t)((hf ^ 1) * 128 + r) * 8u;
 #ifdef D3D_ATTN_STAMPS
     const bool st_on = blockIdx.x == 1 && blockIdx.y == 5 && blockIdx.z == 40 && warp == 2 && lane == 0;
 #endif
@@ -297,18 +297,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, uint16_t* __restrict_
       float mx = -INFINITY;
 #pragma unroll
       for (int i = 0; i < 64; ++i) mx = fmaxf(mx, (!EDGE || i < nv) ? __uint_as_float(v[i]) : -INFINITY);
-      // the softmax base only has to be the SAME on both halves of a row and close to the true max: both threads use
-      // max(bf16(own), bf16(other)), so the 2-byte exchange loses nothing (2 CTAs/SM leaves 512 B for it)
-      {
-        const uint16_t mine = __bfloat16_as_ushort(__float2bfloat16_rn(mx));
-        asm volatile("st.shared.u16 [%0], %1;" ::"r"(xmax_mine), "h"(mine) : "memory");
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        uint16_t other;
-        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(other) : "r"(xmax_other) : "memory");
-        mx = fmaxf(__bfloat162float(__ushort_as_bfloat16(mine)), __bfloat162float(__ushort_as_bfloat16(other)));
-      }
       STAMP(st_on && j < 8, j * 8 + 3);
-      // lazy rescale: keep the old base while the row max grew by <= 8 (P <= 2^8); both threads of a row decide alike
+      // lazy rescale: keep the old base while this half's row max grew by <= 8 (P <= 2^8)
       const float m_cand = fmaxf(m, mx * scale_log2);
       const bool move = (m_cand > m + 8.0f) || (m == -INFINITY && m_cand != -INFINITY);
       float resc = 1.f;
@@ -323,13 +313,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, uint16_t* __restrict_
         tc_fence_after();
         o_done = true;
 #pragma unroll
-        for (int c = 0; c < DH; c += 16) {
+        for (int c = 0; c < D; c += 16) {  // this key half's own accumulator: all 64 channels of the row
           uint32_t ov[16];
-          tmem_ld16(tmem_o + lane_off + (uint32_t)(hf * DH + c), ov);
+          tmem_ld16(tmem_o + lane_off + (uint32_t)(hf * D + c), ov);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * resc);
-          tmem_st16(tmem_o + lane_off + (uint32_t)(hf * DH + c), ov);
+          tmem_st16(tmem_o + lane_off + (uint32_t)(hf * D + c), ov);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       }
@@ -382,22 +372,31 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, uint16_t* __restrict_
     // epilogue: O / l
     mbar_wait_sleepy(bar(8), (uint32_t)(n_tiles - 1) & 1u);
     tc_fence_after();
-    // total row sum = sum of the two halves (same base on both sides)
-    asm volatile("st.shared.f32 [%0], %1;" ::"r"(xsum_mine), "f"(l) : "memory");
+    // merge the two key halves of the row: exchange (base, sum) through the (now free) P buffer, then
+    // out = (O_mine * 2^(m_mine - M) + O_other * 2^(m_other - M)) / (l_mine * 2^(m_mine - M) + l_other * 2^(m_other - M))
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(xsum_mine), "f"(m), "f"(l) : "memory");
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    float l_other;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(l_other) : "r"(xsum_other) : "memory");
-    l += l_other;
-    uint32_t o[DH];
-    tmem_ld32(tmem_o + lane_off + (uint32_t)(hf * DH), o);
-    tmem_ld_wait();
-    if (row < len) {
-      const float inv = l > 0.f ? 1.0f / l : 0.f;
-      uint4* dst = reinterpret_cast<uint4*>(out + (size_t)(b + row) * ldo + (size_t)h * D + hf * DH);
+    float m_other, l_other;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(m_other), "=f"(l_other) : "r"(xsum_other) : "memory");
+    const float mm = fmaxf(m, m_other);
+    const float a_mine = (m == -INFINITY) ? 0.f : ex2_approx(m - mm);
+    const float a_other = (m_other == -INFINITY) ? 0.f : ex2_approx(m_other - mm);
+    const float lt = l * a_mine + l_other * a_other;
+    const float inv = lt > 0.f ? 1.0f / lt : 0.f;
+    const float w1 = a_mine * inv, w2 = a_other * inv;
+    uint4* dst = reinterpret_cast<uint4*>(out + (size_t)(b + row) * ldo + (size_t)h * D + hf * DH);
 #pragma unroll
-      for (int i = 0; i < DH / 8; ++i) {
-        auto f = [&](int k) { return __uint_as_float(o[8 * i + k]) * inv; };
-        dst[i] = make_uint4(pack16x2(f(0), f(1), kind), pack16x2(f(2), f(3), kind), pack16x2(f(4), f(5), kind), pack16x2(f(6), f(7), kind));
+    for (int c = 0; c < DH; c += 16) {  // 16 channels at a time (register budget of 2 CTAs / SM)
+      uint32_t o[16], o2[16];
+      tmem_ld16(tmem_o + lane_off + (uint32_t)(hf * D + hf * DH + c), o);           // my key half's accumulator, my output channels
+      tmem_ld16(tmem_o + lane_off + (uint32_t)((hf ^ 1) * D + hf * DH + c), o2);    // the other key half's accumulator, same channels
+      tmem_ld_wait();
+      if (row < len) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          auto f = [&](int k) { return __uint_as_float(o[8 * i + k]) * w1 + __uint_as_float(o2[8 * i + k]) * w2; };
+          dst[c / 8 + i] = make_uint4(pack16x2(f(0), f(1), kind), pack16x2(f(2), f(3), kind), pack16x2(f(4), f(5), kind), pack16x2(f(6), f(7), kind));
+        }
       }
     }
   }

@@ -425,8 +425,11 @@ class Feature_Fields(nn.Module):
         return out, centre_dev, up[k:]
 
     def _workspace(self, nbytes):
+        # grown with 25 % headroom: the packed token count varies a little from step to step, and re-allocating a GB-sized buffer
+        # (cudaFree + cudaMalloc synchronise the device) inside a rollout costs tens of milliseconds
         if self._ws is None or self._ws.numel() < nbytes:
-            self._ws = torch.empty(max(nbytes, 64 << 20), device=self.device, dtype=torch.uint8)
+            self._ws = None
+            self._ws = torch.empty(max(int(nbytes * 1.25), 64 << 20), device=self.device, dtype=torch.uint8)
         return self._ws
 
     def _disc_logits(self, A):
