@@ -36,6 +36,19 @@ class PoolLevel(ctypes.Structure):
                 ("norm_eps", ctypes.c_float), ("n_layers", ctypes.c_int), ("d_model", ctypes.c_int), ("n_head", ctypes.c_int)]
 
 
+class FFPools(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int64) for n in ("patch_pos", "patch_dir", "patch_scale", "patch_fts", "inst_pos", "inst_fts", "zone_pos", "zone_fts")]
+
+
+class FFRuntime(ctypes.Structure):
+    _fields_ = [("level_inst", ctypes.c_void_p), ("level_zone", ctypes.c_void_p), ("disc", ctypes.c_void_p),
+                ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
+                ("stage_dev", ctypes.c_void_p), ("stage_host", ctypes.c_void_p), ("stage_bytes", ctypes.c_size_t),
+                ("res_dev", ctypes.c_void_p), ("res_host", ctypes.c_void_p), ("d2", ctypes.c_void_p), ("idx", ctypes.c_void_p),
+                ("disc_in", ctypes.c_void_p), ("disc_h32", ctypes.c_void_p), ("disc_h16", ctypes.c_void_p), ("disc_out", ctypes.c_void_p),
+                ("out_merge", ctypes.c_void_p), ("out_zone", ctypes.c_void_p), ("event", ctypes.c_void_p), ("max_seq", ctypes.c_int)]
+
+
 class LMLayer(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in ("rms1", "w_qkv", "w_o", "rms2", "w_gu", "w_down")]
 
@@ -111,6 +124,8 @@ SIGNATURES = {
     "d3d_ffh_counts": [_P, _I, _P], "d3d_ffh_cull": [_P, _I, _P, _L, _P, _P, _P, _P], "d3d_ffh_set_tree": [_P],
     "d3d_ffh_begin_view": [_P] * 3 + [_I] + [_P] * 11,
     "d3d_ffh_begin_step": [_P] * 3 + [_I, _I] + [_P] * 9, "d3d_ffh_begin_view_refs": [_P, _I, _P],
+    "d3d_ff_view_pre": [_P, _I, _P, _P, _P, _P, _P, _P, _P], "d3d_ff_view_post": [_P, _P, _P, _P, _P, _P], "d3d_ff_run_deferred": [_P, _P, _P],
+    "d3d_event_create": [], "d3d_event_destroy": [_P],
     "d3d_ffh_finish_view": [_P, _P, _P, _P], "d3d_ffh_fetch_view": [_P] * 17, "d3d_ffh_zone_key_array": [_P, _I, _P],
     "d3d_ffh_get_map": [_P, _I, _I, _P, _P, _P, _P], "d3d_ffh_get_p2i": [_P, _I, _P], "d3d_ffh_get_patch_pos": [_P, _I, _P],
     "d3d_ffh_get_zone_keys": [_P, _I, _P, _P, _P], "d3d_ffh_get_last": [_P, _I, _P, _P, _P, _P],
@@ -134,7 +149,8 @@ def _declare(lib_):
                 continue
             raise D3DLibraryError(f"{LIB_PATH} does not export {name}: stale build?")
         fn.argtypes = argtypes
-        fn.restype = {"d3d_pool_workspace_bytes": ctypes.c_size_t, "d3d_ffh_create": ctypes.c_void_p, "d3d_ffh_destroy": None}.get(name, ctypes.c_int)
+        fn.restype = {"d3d_pool_workspace_bytes": ctypes.c_size_t, "d3d_ffh_create": ctypes.c_void_p, "d3d_ffh_destroy": None,
+                      "d3d_event_create": ctypes.c_void_p, "d3d_event_destroy": None}.get(name, ctypes.c_int)
 
 
 def lib():

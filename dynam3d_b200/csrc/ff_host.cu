@@ -95,6 +95,13 @@ struct FFH {
   // whole-step plan (begin_step): splits / sequence starts of every view, sequences numbered globally in (view, episode, segment) order
   std::vector<std::vector<std::vector<std::vector<int>>>> step_splits;  // [V][b][g]
   std::vector<std::vector<int>> step_seq_start;                        // [V][B+1]
+  // per-view runtime (d3d_ff_view_pre / _post): upload ring cursor and the zone pooling pass waiting to be issued
+  size_t stage_cursor = 0;
+  struct Deferred {
+    bool pending = false;
+    const int64_t* ptrs; const float* centre; const int* tok_seq; const int* tok_src; const int* cu; const int64_t* fts_dst; const int64_t* pos_dst;
+    float* out; int T, n_seq, max_len;
+  } zone;
   ViewPlan plan;
 };
 
@@ -606,6 +613,232 @@ extern "C" int d3d_ffh_get_last(void* h, int b, float* d2, int* idx, uint8_t* me
   if (d2 && !ep.last_d2.empty()) {
     memcpy(d2, ep.last_d2.data(), ep.last_d2.size() * 4); memcpy(idx, ep.last_idx.data(), ep.last_idx.size() * 4);
     memcpy(merge, ep.last_merge.data(), ep.last_merge.size());
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-view runtime: the state-dependent part of a panorama view (FF:604-756) behind TWO host calls, so the interpreter is not on the
+// critical path of the host-synchronised loop:  d3d_ff_view_pre  = K-NN proposals + merge discriminator + result copy + (previous view's
+// deferred zone pass) + wait + planner;   [caller grows the episode pools if the plan needs more slots]   d3d_ff_view_post = slot
+// writes, merged-instance pooling pass, upload of the zone pass (issued by the NEXT pre call or d3d_ff_run_deferred).
+// ------------------------------------------------------------------------------------------------
+extern "C" int d3d_knn2_batched(const int64_t* ref_ptr, const int* n_ref, const float* queries, int n_q, float* out_d2, int* out_idx, void* stream);
+extern "C" int d3d_disc_input_batched(const int64_t* fts_ptr, const int64_t* pos_ptr, const int* idx, const float* view_fts, const float* centre,
+                                      int Q, int K, int D, int ldo, void* out16, int kind, void* stream);
+extern "C" int d3d_scatter_rows_ptr(const float* src, int64_t lds, const int* src_idx, const int64_t* dst_row_ptr, int n, int D, void* stream);
+
+namespace {
+
+__global__ void pack_view_result_kernel(const float* __restrict__ centre, const float* __restrict__ d2, const int* __restrict__ idx,
+                                        const float* __restrict__ logits4, int n, int has_refs, float* __restrict__ res) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float* r = res + (size_t)i * 12;
+  r[0] = centre[i * 3]; r[1] = centre[i * 3 + 1]; r[2] = centre[i * 3 + 2];
+  if (has_refs) {
+    r[3] = d2[i * 2]; r[4] = d2[i * 2 + 1];
+    r[5] = __int_as_float(idx[i * 2]); r[6] = __int_as_float(idx[i * 2 + 1]);
+    // logits4 rows are [2*n, 4] (ld 4): proposal j of segment i = row 2i+j, columns 0..1
+    r[7] = logits4[(2 * i) * 4]; r[8] = logits4[(2 * i) * 4 + 1]; r[9] = logits4[(2 * i + 1) * 4]; r[10] = logits4[(2 * i + 1) * 4 + 1];
+  } else {
+    for (int k = 3; k < 11; ++k) r[k] = 0.f;
+  }
+  r[11] = 0.f;
+}
+
+// bump allocator over the upload ring: returns the offset of `bytes` (16-byte aligned) in both the pinned host and the device mirror
+struct Stage {
+  FFH& H; const d3d_ff_runtime& rt; size_t begin, end;
+  Stage(FFH& h, const d3d_ff_runtime& r) : H(h), rt(r) {
+    // a view's uploads are < 1/4 of the ring and every view ends with a host wait on the device, so a region is never
+    // rewritten while an earlier copy or a kernel that reads it (the deferred zone pass: issued one view later) is in flight
+    if (H.stage_cursor + rt.stage_bytes / 4 > rt.stage_bytes) H.stage_cursor = 0;
+    begin = end = H.stage_cursor;
+  }
+  template <typename T>
+  size_t put(const T* src, size_t n) {
+    const size_t off = end;
+    if (n) memcpy((char*)rt.stage_host + off, src, n * sizeof(T));
+    end += (n * sizeof(T) + 15) / 16 * 16;
+    return off;
+  }
+  bool fits() const { return end <= rt.stage_bytes && end - begin <= rt.stage_bytes / 4; }
+  int flush(cudaStream_t st) {
+    if (end > begin) D3D_CHECK_CUDA(cudaMemcpyAsync((char*)rt.stage_dev + begin, (char*)rt.stage_host + begin, end - begin, cudaMemcpyHostToDevice, st));
+    H.stage_cursor = end;
+    return 0;
+  }
+  template <typename T>
+  T* dev(size_t off) const { return (T*)((char*)rt.stage_dev + off); }
+};
+
+int run_deferred(FFH& H, const d3d_ff_runtime& rt, void* stream) {
+  if (!H.zone.pending) return 0;
+  const FFH::Deferred& z = H.zone;
+  D3D_TRY(d3d_pool_tokens(rt.level_zone, z.ptrs, z.centre, z.tok_seq, z.tok_src, z.cu, z.T, z.n_seq, z.max_len, 1, 1, rt.workspace, rt.workspace_bytes,
+                          z.out, stream));
+  D3D_TRY(d3d_scatter_rows_ptr(z.out, rt.level_zone->d_model, nullptr, z.fts_dst, z.n_seq, rt.level_zone->d_model, stream));
+  D3D_TRY(d3d_scatter_rows_ptr(z.centre, 3, nullptr, z.pos_dst, z.n_seq, 3, stream));
+  H.zone.pending = false;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int d3d_ff_run_deferred(void* h, const d3d_ff_runtime* rt, void* stream) { return run_deferred(HH(h), *rt, stream); }
+extern "C" void* d3d_event_create(void) {
+  cudaEvent_t e = nullptr;
+  if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { d3d_set_error("cudaEventCreate failed"); return nullptr; }
+  return (void*)e;
+}
+extern "C" void d3d_event_destroy(void* e) { if (e) cudaEventDestroy((cudaEvent_t)e); }
+
+extern "C" int d3d_ff_view_pre(void* h, int ix, const d3d_ff_runtime* rt_p, const d3d_ff_pools* pools, const float* centres_step,
+                               const float* view_fts_step, int* sizes10, int64_t* after3, void* stream) {
+  FFH& H = HH(h);
+  const d3d_ff_runtime& rt = *rt_p;
+  D3D_REQUIRE(ix >= 0 && ix < (int)H.step_splits.size(), "view index");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = (int)H.eps.size();
+  H.splits = H.step_splits[(size_t)ix];
+  H.seq_start = H.step_seq_start[(size_t)ix];
+  H.res_base = H.seq_start[0];
+  const int s_lo = H.seq_start[0], n_seq = H.seq_start[(size_t)B] - s_lo;
+  D3D_REQUIRE(n_seq <= rt.max_seq, "more sequences in a view than the runtime buffers hold");
+  const int Dm = rt.level_inst->d_model;
+  std::vector<int64_t> pos_ptr((size_t)n_seq), fts_ptr((size_t)n_seq);
+  std::vector<int> nref((size_t)n_seq);
+  bool any = false;
+  for (int b = 0; b < B; ++b) {
+    const Episode& ep = H.eps[(size_t)b];
+    const int nr = ep.tree ? (int)ep.n_inst : 0;
+    any |= nr > 0;
+    for (int s = H.seq_start[(size_t)b]; s < H.seq_start[(size_t)b + 1]; ++s) {
+      nref[(size_t)(s - s_lo)] = nr;
+      pos_ptr[(size_t)(s - s_lo)] = pools[b].inst_pos;
+      fts_ptr[(size_t)(s - s_lo)] = pools[b].inst_fts;
+    }
+  }
+  const float* centres = centres_step + (size_t)s_lo * 3;
+  const float* view_fts = view_fts_step + (size_t)s_lo * Dm;
+  if (any) {
+    Stage sg(H, rt);
+    const size_t o_pos = sg.put(pos_ptr.data(), (size_t)n_seq), o_fts = sg.put(fts_ptr.data(), (size_t)n_seq), o_nr = sg.put(nref.data(), (size_t)n_seq);
+    D3D_REQUIRE(sg.fits(), "upload ring too small");
+    D3D_TRY(sg.flush(st));
+    D3D_TRY(d3d_knn2_batched(sg.dev<int64_t>(o_pos), sg.dev<int>(o_nr), centres, n_seq, rt.d2, rt.idx, stream));
+    D3D_TRY(d3d_disc_input_batched(sg.dev<int64_t>(o_fts), sg.dev<int64_t>(o_pos), rt.idx, view_fts, centres, n_seq, 2, Dm, rt.disc->k_pad, rt.disc_in,
+                                   rt.disc->kind, stream));
+    D3D_TRY(d3d_mlp_ln_gelu(rt.disc, rt.disc_in, rt.disc->k_pad, 2 * n_seq, rt.disc_h32, rt.disc_h16, rt.disc_out, 4, stream));
+  }
+  pack_view_result_kernel<<<d3d_cdiv(n_seq, 128), 128, 0, st>>>(centres, rt.d2, rt.idx, rt.disc_out, n_seq, any ? 1 : 0, rt.res_dev);
+  D3D_CHECK_LAUNCH();
+  D3D_CHECK_CUDA(cudaMemcpyAsync(rt.res_host, rt.res_dev, (size_t)n_seq * 12 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  D3D_CHECK_CUDA(cudaEventRecord((cudaEvent_t)rt.event, st));
+  D3D_TRY(run_deferred(H, rt, stream));  // the previous view's zone pass executes while the host waits for / plans this view
+  D3D_CHECK_CUDA(cudaEventSynchronize((cudaEvent_t)rt.event));
+  return d3d_ffh_finish_view(h, rt.res_host, sizes10, after3);
+}
+
+extern "C" int d3d_ff_view_post(void* h, const d3d_ff_runtime* rt_p, const d3d_ff_pools* pools, float* centres_step, float* view_fts_step,
+                                void* stream) {
+  FFH& H = HH(h);
+  const d3d_ff_runtime& rt = *rt_p;
+  cudaStream_t st = (cudaStream_t)stream;
+  const ViewPlan& pl = H.plan;
+  const int Dm = rt.level_inst->d_model;
+  const int n_new = (int)pl.new_src.size(), n_mg = (int)pl.mg_owner.size(), n_zn = (int)pl.zn_owner.size();
+  D3D_REQUIRE(n_mg <= rt.max_seq && n_zn <= rt.max_seq, "more merged instances / zones than the runtime buffers hold");
+  auto toks = [](const std::vector<int>& len, const std::vector<int>& mem, std::vector<int>& src, std::vector<int>& seq, std::vector<int>& cu,
+                 int& max_len) {
+    src.clear(); seq.clear(); cu.assign(1, 0);
+    max_len = 0;
+    size_t m = 0;
+    for (size_t s = 0; s < len.size(); ++s) {
+      src.push_back(-1); seq.push_back((int)s);
+      for (int i = 0; i < len[s]; ++i) { src.push_back(mem[m++]); seq.push_back((int)s); }
+      cu.push_back((int)src.size());
+      max_len = std::max(max_len, len[s] + 1);
+    }
+  };
+  Stage sg(H, rt);
+  // ---- new instances: view token / centroid -> their slots (FF:643-648) ----
+  size_t o_ns = 0, o_nf = 0, o_np = 0;
+  if (n_new) {
+    std::vector<int64_t> fd((size_t)n_new), pd((size_t)n_new);
+    for (int i = 0; i < n_new; ++i) {
+      const d3d_ff_pools& p = pools[pl.new_owner[(size_t)i]];
+      fd[(size_t)i] = p.inst_fts + 4LL * Dm * pl.new_iid[(size_t)i];
+      pd[(size_t)i] = p.inst_pos + 12LL * pl.new_iid[(size_t)i];
+    }
+    o_ns = sg.put(pl.new_src.data(), (size_t)n_new); o_nf = sg.put(fd.data(), (size_t)n_new); o_np = sg.put(pd.data(), (size_t)n_new);
+  }
+  // ---- merged instances: re-encode ALL member patches (FF:658-688) ----
+  size_t o_ms = 0, o_mq = 0, o_mc = 0, o_mp = 0, o_mx = 0, o_mf = 0, o_md = 0;
+  int t_mg = 0, ml_mg = 0;
+  if (n_mg) {
+    std::vector<int> src, seq, cu;
+    toks(pl.mg_len, pl.mg_members, src, seq, cu, ml_mg);
+    t_mg = (int)src.size();
+    std::vector<int64_t> ptrs((size_t)4 * n_mg), fd((size_t)n_mg), pd((size_t)n_mg);
+    for (int i = 0; i < n_mg; ++i) {
+      const d3d_ff_pools& p = pools[pl.mg_owner[(size_t)i]];
+      ptrs[(size_t)i] = p.patch_pos; ptrs[(size_t)n_mg + i] = p.patch_dir; ptrs[(size_t)2 * n_mg + i] = p.patch_scale; ptrs[(size_t)3 * n_mg + i] = p.patch_fts;
+      fd[(size_t)i] = p.inst_fts + 4LL * Dm * pl.mg_iid[(size_t)i];
+      pd[(size_t)i] = p.inst_pos + 12LL * pl.mg_iid[(size_t)i];
+    }
+    o_ms = sg.put(src.data(), src.size()); o_mq = sg.put(seq.data(), seq.size()); o_mc = sg.put(cu.data(), cu.size());
+    o_mp = sg.put(ptrs.data(), ptrs.size()); o_mx = sg.put(pl.mg_pos.data(), pl.mg_pos.size());
+    o_mf = sg.put(fd.data(), fd.size()); o_md = sg.put(pd.data(), pd.size());
+  }
+  // ---- zones (FF:693-756): uploaded now, issued behind the next view's result copy ----
+  size_t o_zs = 0, o_zq = 0, o_zc = 0, o_zp = 0, o_zx = 0, o_zf = 0, o_zd = 0;
+  int t_zn = 0, ml_zn = 0;
+  if (n_zn) {
+    std::vector<int> src, seq, cu;
+    toks(pl.zn_len, pl.zn_members, src, seq, cu, ml_zn);
+    t_zn = (int)src.size();
+    // Q5: an updated zone is embedded from its members' voxel-centre keys: one key array per episode that needs it
+    std::vector<size_t> key_off((size_t)H.eps.size(), (size_t)-1);
+    for (int i = 0; i < n_zn; ++i) {
+      const int b = pl.zn_owner[(size_t)i];
+      if (!pl.zn_keys[(size_t)i] || key_off[(size_t)b] != (size_t)-1) continue;
+      const Episode& ep = H.eps[(size_t)b];
+      std::vector<float> ka((size_t)std::max<i64>(ep.n_inst, 1) * 3);
+      D3D_TRY(d3d_ffh_zone_key_array(h, b, ka.data()));
+      key_off[(size_t)b] = sg.put(ka.data(), ka.size());
+    }
+    std::vector<int64_t> ptrs((size_t)4 * n_zn), fd((size_t)n_zn), pd((size_t)n_zn);
+    for (int i = 0; i < n_zn; ++i) {
+      const int b = pl.zn_owner[(size_t)i];
+      const d3d_ff_pools& p = pools[b];
+      const int64_t xyz = pl.zn_keys[(size_t)i] ? (int64_t)(uintptr_t)sg.dev<float>(key_off[(size_t)b]) : p.inst_pos;
+      ptrs[(size_t)i] = xyz; ptrs[(size_t)n_zn + i] = xyz; ptrs[(size_t)2 * n_zn + i] = xyz; ptrs[(size_t)3 * n_zn + i] = p.inst_fts;
+      fd[(size_t)i] = p.zone_fts + 4LL * Dm * pl.zn_slot[(size_t)i];
+      pd[(size_t)i] = p.zone_pos + 12LL * pl.zn_slot[(size_t)i];
+    }
+    o_zs = sg.put(src.data(), src.size()); o_zq = sg.put(seq.data(), seq.size()); o_zc = sg.put(cu.data(), cu.size());
+    o_zp = sg.put(ptrs.data(), ptrs.size()); o_zx = sg.put(pl.zn_pos.data(), pl.zn_pos.size());
+    o_zf = sg.put(fd.data(), fd.size()); o_zd = sg.put(pd.data(), pd.size());
+  }
+  D3D_REQUIRE(sg.fits(), "upload ring too small for this view's plan");
+  D3D_TRY(sg.flush(st));
+  if (n_new) {
+    D3D_TRY(d3d_scatter_rows_ptr(view_fts_step, Dm, sg.dev<int>(o_ns), sg.dev<int64_t>(o_nf), n_new, Dm, stream));
+    D3D_TRY(d3d_scatter_rows_ptr(centres_step, 3, sg.dev<int>(o_ns), sg.dev<int64_t>(o_np), n_new, 3, stream));
+  }
+  if (n_mg) {
+    D3D_TRY(d3d_pool_tokens(rt.level_inst, sg.dev<int64_t>(o_mp), sg.dev<float>(o_mx), sg.dev<int>(o_mq), sg.dev<int>(o_ms), sg.dev<int>(o_mc), t_mg, n_mg,
+                            ml_mg, 0, 0, rt.workspace, rt.workspace_bytes, rt.out_merge, stream));
+    D3D_TRY(d3d_scatter_rows_ptr(rt.out_merge, Dm, nullptr, sg.dev<int64_t>(o_mf), n_mg, Dm, stream));
+    D3D_TRY(d3d_scatter_rows_ptr(sg.dev<float>(o_mx), 3, nullptr, sg.dev<int64_t>(o_md), n_mg, 3, stream));
+  }
+  if (n_zn) {
+    FFH::Deferred& z = H.zone;
+    z.pending = true;
+    z.ptrs = sg.dev<int64_t>(o_zp); z.centre = sg.dev<float>(o_zx); z.tok_seq = sg.dev<int>(o_zq); z.tok_src = sg.dev<int>(o_zs); z.cu = sg.dev<int>(o_zc);
+    z.fts_dst = sg.dev<int64_t>(o_zf); z.pos_dst = sg.dev<int64_t>(o_zd); z.out = rt.out_zone; z.T = t_zn; z.n_seq = n_zn; z.max_len = ml_zn;
   }
   return 0;
 }

@@ -21,6 +21,7 @@ There is no CPU fallback: without the CUDA library / an sm_100 device constructi
 """
 import ctypes
 import math
+import os
 
 import numpy as np
 import torch
@@ -51,6 +52,7 @@ class _Args:
 
 class _Pool:
     """Growable [cap, width] device tensor (capacity doubling keeps appends amortised O(1))."""
+    version = 0
 
     def __init__(self, width, dtype, device, cap=2048):
         self.width, self.dtype, self.device = width, dtype, device
@@ -65,6 +67,7 @@ class _Pool:
         t = torch.zeros((cap,) + tuple(self.t.shape[1:]), device=self.device, dtype=self.dtype)
         t[: self.t.shape[0]].copy_(self.t)
         self.t = t
+        _Pool.version += 1  # base addresses changed: pointer tables handed to the C runtime must be rebuilt
 
 
 class _Episode:
@@ -159,6 +162,10 @@ class Feature_Fields(nn.Module):
             if h:
                 self.__dict__["_h"] = None
                 L.lib().d3d_ffh_destroy(h)
+            rt = self.__dict__.get("_rt")
+            if rt and rt.get("event"):
+                L.lib().d3d_event_destroy(rt["event"])
+                rt["event"] = None
         except Exception:
             pass
 
@@ -569,9 +576,83 @@ class Feature_Fields(nn.Module):
             xyz_h = np.ascontiguousarray(xyz_h.numpy().reshape(B, V, P, 3).transpose(1, 0, 2, 3))  # [V,B,P,3]
             stage = {"xyz": xyz.view(B * V * P, 3), "dir": direction.view(-1), "scale": scale.view(-1), "fts": grid}
             plan = self._begin_step(V, P, segm, stage, xyz_h)
-            for ix in range(V):
-                self._update_view(ix, plan)
-            self._run_deferred()
+            if self.precise or os.environ.get("D3D_FF_PYTHON_VIEWS") == "1":
+                for ix in range(V):
+                    self._update_view(ix, plan)
+                self._run_deferred()
+            else:
+                self._update_views_native(V, plan)
+
+    # ------------------------------------------------------------------ the view loop in the library (csrc/ff_host.cu: d3d_ff_view_pre/_post)
+    def _ff_runtime(self, max_seq):
+        """Scratch / upload ring / weights table of the C view runtime (allocated once, regrown when a view has more sequences)."""
+        rt = getattr(self, "_rt", None)
+        if rt is not None and rt["max_seq"] >= max_seq and rt["W"] is self._weights():
+            return rt
+        W = self._weights()
+        dev, dt = self.device, self.compute_dtype
+        max_seq = max(256, 1 << (max_seq - 1).bit_length())
+        hidden = W["disc"]["w0"].shape[0]
+        bufs = {
+            "stage_dev": torch.empty(8 << 20, device=dev, dtype=torch.uint8), "stage_host": torch.empty(8 << 20, dtype=torch.uint8).pin_memory(),
+            "res_dev": torch.empty((max_seq, 12), device=dev, dtype=torch.float32), "res_host": torch.empty((max_seq, 12), dtype=torch.float32).pin_memory(),
+            "d2": torch.zeros((max_seq, 2), device=dev, dtype=torch.float32), "idx": torch.zeros((max_seq, 2), device=dev, dtype=torch.int32),
+            "disc_in": torch.empty((2 * max_seq, 1544), device=dev, dtype=dt), "disc_h32": torch.empty((2 * max_seq, hidden), device=dev, dtype=torch.float32),
+            "disc_h16": torch.empty((2 * max_seq, hidden), device=dev, dtype=dt), "disc_out": torch.zeros((2 * max_seq, 4), device=dev, dtype=torch.float32),
+            "out_merge": torch.empty((max_seq, D), device=dev, dtype=torch.float32), "out_zone": torch.empty((max_seq, D), device=dev, dtype=torch.float32)}
+        if rt is None or not rt.get("event"):
+            event = L.lib().d3d_event_create()
+            if not event:
+                raise L.D3DError("cudaEventCreate failed")
+        else:
+            event = rt["event"]
+        c = L.FFRuntime()
+        c.level_inst, c.level_zone = ctypes.addressof(W["c_levels"][0]), ctypes.addressof(W["c_levels"][1])
+        c.disc = ctypes.addressof(W["c_disc"])
+        for k, t in bufs.items():
+            setattr(c, k, t.data_ptr())
+        c.stage_bytes = bufs["stage_dev"].numel()
+        c.event, c.max_seq = event, max_seq
+        self._rt = {"c": c, "bufs": bufs, "max_seq": max_seq, "W": W, "event": event, "pools": None, "pools_version": -1}
+        return self._rt
+
+    def _pool_table(self, rt):
+        """Device base addresses of every episode's pools for the C runtime (rebuilt only after a pool was re-allocated or episodes changed)."""
+        if rt["pools"] is None or rt["pools_version"] != _Pool.version or len(rt["pools"]) != self.batch_size or rt.get("eps_id") != id(self.eps):
+            arr = (L.FFPools * max(self.batch_size, 1))()
+            for b, ep in enumerate(self.eps):
+                arr[b] = L.FFPools(ep.patch_pos.t.data_ptr(), ep.patch_dir.t.data_ptr(), ep.patch_scale.t.data_ptr(), ep.patch_fts.t.data_ptr(),
+                                   ep.inst_pos.t.data_ptr(), ep.inst_fts.t.data_ptr(), ep.zone_pos.t.data_ptr(), ep.zone_fts.t.data_ptr())
+            rt["pools"], rt["pools_version"], rt["eps_id"] = arr, _Pool.version, id(self.eps)
+        return rt["pools"]
+
+    def _update_views_native(self, V, plan):
+        """All views of the step through the library's view runtime: two C calls per view, pool growth in between."""
+        lib = L.lib()
+        B = self.batch_size
+        vs = plan["view_start"]
+        rt = self._ff_runtime(int(np.max(vs[1:] - vs[:-1])))
+        c = rt["c"]
+        sizes = (ctypes.c_int * 10)()
+        after = (ctypes.c_int64 * (3 * max(B, 1)))()
+        cen, vf = L.ptr(plan["centres"]), L.ptr(plan["view_fts"])
+        for ix in range(V):
+            ws = self._workspace(int(lib.d3d_pool_workspace_bytes(8192, D, D)))  # merged / zone passes; the step pass already sized it
+            c.workspace, c.workspace_bytes = ws.data_ptr(), ws.numel()
+            L.check(lib.d3d_ff_view_pre(self._h, ix, ctypes.addressof(c), ctypes.cast(self._pool_table(rt), ctypes.c_void_p), cen, vf,
+                                        ctypes.cast(sizes, ctypes.c_void_p), ctypes.cast(after, ctypes.c_void_p), L.stream_ptr()))
+            t_mg, t_zn = int(sizes[2]) + int(sizes[1]), int(sizes[4]) + int(sizes[3])
+            need = int(lib.d3d_pool_workspace_bytes(max(t_mg, t_zn, 1), D, D))
+            if need > c.workspace_bytes:  # a pending (deferred) zone pass only reads its own uploaded arrays: re-allocating the workspace is safe
+                ws = self._workspace(need)
+                c.workspace, c.workspace_bytes = ws.data_ptr(), ws.numel()
+            for b, ep in enumerate(self.eps):
+                ep.n_inst, ep.n_zone = int(after[3 * b]), int(after[3 * b + 1])
+                ep.inst_pos.ensure(ep.n_inst); ep.inst_fts.ensure(ep.n_inst)
+                ep.zone_pos.ensure(ep.n_zone); ep.zone_fts.ensure(ep.n_zone)
+                ep.tree = ep.n_inst > 0
+            L.check(lib.d3d_ff_view_post(self._h, ctypes.addressof(c), ctypes.cast(self._pool_table(rt), ctypes.c_void_p), cen, vf, L.stream_ptr()))
+        L.check(lib.d3d_ff_run_deferred(self._h, ctypes.addressof(c), L.stream_ptr()))
 
     def _run_deferred(self):
         fn, self._deferred = getattr(self, "_deferred", None), None

@@ -337,6 +337,30 @@ int d3d_ffh_begin_step(void* h, const float* xyz /*[V,B,P,3]*/, const int64_t* s
                        int* view_seq_start, int* seq_owner, int* members, int* cu_m, int* tok_src, int* tok_seq, int* cu_tok, int* info);
 int d3d_ffh_begin_view_refs(void* h, int ix, int* n_ref);
 int d3d_ffh_finish_view(void* h, const float* res12, int* sizes10, int64_t* after3);
+/* Per-view runtime (the interpreter-free form of the view loop): see csrc/ff_host.cu.  d3d_ff_pools: device base addresses of one
+ * episode's pools; d3d_ff_runtime: weights, workspace, the pinned/device upload ring and scratch owned by the caller.
+ *   d3d_ff_view_pre : K-NN proposals + merge discriminator for view ix, result copy, previous view's deferred zone pass, wait, planner
+ *                     (same sizes10 / after3 as d3d_ffh_finish_view);  the caller then grows pools if after3 asks for more slots;
+ *   d3d_ff_view_post: slot writes + merged-instance pooling pass, upload of the zone pass (issued by the next pre / d3d_ff_run_deferred). */
+typedef struct { int64_t patch_pos, patch_dir, patch_scale, patch_fts, inst_pos, inst_fts, zone_pos, zone_fts; } d3d_ff_pools;
+typedef struct {
+  const d3d_pool_level* level_inst; const d3d_pool_level* level_zone; const d3d_mlp* disc;
+  void* workspace; size_t workspace_bytes;                 /* d3d_pool_tokens workspace */
+  void* stage_dev; void* stage_host; size_t stage_bytes;   /* upload ring: device buffer + pinned host mirror (>= 4 views of uploads) */
+  float* res_dev; float* res_host;                         /* [max_seq, 12] */
+  float* d2; int* idx;                                     /* [max_seq, 2] */
+  void* disc_in; float* disc_h32; void* disc_h16; float* disc_out;  /* [2*max_seq, k_pad] 16-bit, [2*max_seq, hidden] f32 / 16-bit, [2*max_seq, 4] f32 */
+  float* out_merge; float* out_zone;                       /* [max_seq, d_model] f32 */
+  void* event;                                             /* cudaEvent_t */
+  int max_seq;
+} d3d_ff_runtime;
+int d3d_ff_view_pre(void* h, int ix, const d3d_ff_runtime* rt, const d3d_ff_pools* pools_h, const float* centres_step, const float* view_fts_step,
+                    int* sizes10, int64_t* after3, void* stream);
+int d3d_ff_view_post(void* h, const d3d_ff_runtime* rt, const d3d_ff_pools* pools_h, float* centres_step, float* view_fts_step, void* stream);
+int d3d_ff_run_deferred(void* h, const d3d_ff_runtime* rt, void* stream);
+void* d3d_event_create(void);   /* cudaEvent_t without timing, for d3d_ff_runtime.event */
+void d3d_event_destroy(void* e);
+
 int d3d_ffh_fetch_view(void* h, int* new_src, int* new_owner, int64_t* new_iid, int* mg_owner, int64_t* mg_iid, float* mg_pos,
                        int* mg_tok_src, int* mg_tok_seq, int* mg_cu, int* zn_owner, int64_t* zn_slot, int* zn_keys, float* zn_pos,
                        int* zn_tok_src, int* zn_tok_seq, int* zn_cu);
