@@ -334,7 +334,8 @@ class Dynam3D_VLN(nn.Module):
         B = ff.batch_size
         patch, inst, zone = self.encode_step(observations, agent_positions, agent_heading_angles, depth_scale, delete_old_features, num_of_views)
         lm = self.llava.lm
-        seqs, lens = [], []
+        # text tokens of all episodes: ONE id upload and ONE embedding gather (POL:439), then the literal splice of POL:456
+        heads, tails, n_imgs = [], [], []
         for b in range(B):
             n_img = patch.shape[1] + inst[b].shape[0] + zone[b].shape[0]
             if input_ids is not None:
@@ -343,14 +344,16 @@ class Dynam3D_VLN(nn.Module):
                 if self.tokenize is None:
                     raise RuntimeError("no tokenizer: set .tokenize or pass input_ids (prompt ids with n_img image slots after 2 tokens)")
                 ids = self.tokenize(self.build_prompt(n_img, instructions[b], ff.history_actions[b]))
-            ids = torch.tensor(ids, dtype=torch.int32)
-            head, tail = ids[:2], ids[n_img + 2:]  # POL:456 literal splice
-            eh = torch.empty((len(head), lm.w.hidden), device=self.device, dtype=torch.float32)
-            et = torch.empty((len(tail), lm.w.hidden), device=self.device, dtype=torch.float32)
-            lm.embed(head.to(self.device), eh)
-            lm.embed(tail.to(self.device), et)
-            seqs += [eh, patch[b], inst[b], zone[b], et]
-            lens.append(len(head) + n_img + len(tail))
+            heads.append(ids[:2]); tails.append(ids[n_img + 2:]); n_imgs.append(n_img)
+        flat = [t for b in range(B) for t in (heads[b] + tails[b])]
+        E = torch.empty((len(flat), lm.w.hidden), device=self.device, dtype=torch.float32)
+        lm.embed(torch.tensor(flat, dtype=torch.int32).to(self.device, non_blocking=True), E)
+        seqs, lens, off = [], [], 0
+        for b in range(B):
+            nh, nt = len(heads[b]), len(tails[b])
+            seqs += [E[off:off + nh], patch[b], inst[b], zone[b], E[off + nh:off + nh + nt]]
+            off += nh + nt
+            lens.append(nh + n_imgs[b] + nt)
         X = torch.cat(seqs, 0)
         cu = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int32, device=self.device)
         pos = torch.cat([torch.arange(n, dtype=torch.int32) for n in lens]).to(self.device)

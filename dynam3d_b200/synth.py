@@ -271,17 +271,22 @@ class ToyTokenizer:
     per character.  Only the SHAPE of the prompt matters for the hot path (ids index a random embedding table)."""
     SPECIAL = {"<|user|>": 32010, "<|end|>": 32007, "<|assistant|>": 32001, "<image>": 32038}
 
+    _SPLIT = None
+
     def __call__(self, text):
-        ids, i = [1], 0  # BOS like LlamaTokenizer
-        while i < len(text):
-            for tok, tid in self.SPECIAL.items():
-                if text.startswith(tok, i):
-                    ids.append(tid)
-                    i += len(tok)
-                    break
+        import re
+        if ToyTokenizer._SPLIT is None:  # runs of "<image>" are one match: the prompt carries hundreds of them (POL:436)
+            ToyTokenizer._SPLIT = re.compile("((?:<image>)+|" + "|".join(re.escape(t) for t in self.SPECIAL if t != "<image>") + ")")
+        ids = [1]  # BOS like LlamaTokenizer
+        for part in ToyTokenizer._SPLIT.split(text):  # leftmost special token wins at every position, as a character scan would find it
+            if not part:
+                continue
+            if part in self.SPECIAL:
+                ids.append(self.SPECIAL[part])
+            elif part.startswith("<image>"):
+                ids.extend([self.SPECIAL["<image>"]] * (len(part) // 7))
             else:
-                ids.append(3 + (ord(text[i]) * 131) % 31990)
-                i += 1
+                ids.extend([3 + (ord(c) * 131) % 31990 for c in part])
         return ids
 
 
