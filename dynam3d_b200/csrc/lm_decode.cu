@@ -22,12 +22,14 @@ extern "C" int d3d_rope_apply(void* qkv, int64_t ld, const float* tab, int T, in
 namespace {
 
 constexpr int SK_WARPS = 8;
-constexpr int SK_NT = 2;  // n-tiles (8 weight rows each) per CTA
-constexpr int SK_U = 2;   // K super-steps (128 elements each) whose loads a warp issues before it starts multiplying
+// tuning knobs (template parameters of the kernel, chosen per problem in skinny()):
+//   SK_NT  n-tiles (8 weight rows each) per CTA;  SK_U  K super-steps (128 elements each) whose loads a warp issues before it multiplies
 
+template <bool NOALLOC>
 __device__ __forceinline__ uint4 ldg_stream16(const void* p) {
   uint4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  if (NOALLOC) asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  else asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
 }
 __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1, int kind) {
@@ -52,7 +54,7 @@ struct SkinnyEpi {
 // rows (DRAM-friendly).  Every 16-byte piece feeds two MMAs: elements {0,1} are K-slots (2kq, 2kq+1), {2,3} slots (2kq+8, 2kq+9) of the
 // first, {4,5} / {6,7} of the second.  A and W use the same slot -> k map, so the products pair up and each k is used exactly once.
 // HI: rows 8..15 of A exist (M > 8); otherwise their fragment registers are zero and never loaded.
-template <bool HI>
+template <bool HI, int SK_NT, int SK_U, bool NOALLOC>
 __global__ void __launch_bounds__(SK_WARPS * 32) skinny_gemm_kernel(const uint16_t* __restrict__ A, long long lda, const uint16_t* __restrict__ W,
                                                                     long long ldw, int M, int N, int K, int kind, SkinnyEpi ep) {
   __shared__ float red[SK_WARPS][SK_NT][16][8];
@@ -87,7 +89,7 @@ __global__ void __launch_bounds__(SK_WARPS * 32) skinny_gemm_kernel(const uint16
 #pragma unroll
       for (int t = 0; t < SK_NT; ++t)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) wv[u][t][c] = (in && w_ok[t]) ? ldg_stream16(w_p[t] + off + c * 8) : make_uint4(0, 0, 0, 0);
+        for (int c = 0; c < 4; ++c) wv[u][t][c] = (in && w_ok[t]) ? ldg_stream16<NOALLOC>(w_p[t] + off + c * 8) : make_uint4(0, 0, 0, 0);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         al[u][c] = (in && lo_ok) ? __ldg(reinterpret_cast<const uint4*>(a_lo_p + off + c * 8)) : make_uint4(0, 0, 0, 0);
@@ -277,6 +279,8 @@ __global__ void decode_prep_kernel(const void* __restrict__ table, int kind, con
   for (int c = threadIdx.x; c < D; c += blockDim.x) x[(long long)b * D + c] = ld16(table, src + c, kind);
 }
 
+int g_skinny_cfg = 0;
+
 int skinny(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N, int K, int kind, int out_kind,
            const float* bias, int act, const float* residual, long long ldres, cudaStream_t st) {
   D3D_REQUIRE(M >= 1 && M <= 16, "skinny GEMM handles 1..16 activation rows");
@@ -285,13 +289,36 @@ int skinny(const void* A, long long lda, const void* W, long long ldw, void* C, 
   D3D_REQUIRE(kind == D3D_F16 || kind == D3D_BF16, "16-bit operands");
   D3D_REQUIRE(act != D3D_ACT_SWIGLU || ((N % 2) == 0 && residual == nullptr), "swiglu needs even N, no residual");
   SkinnyEpi ep{C, ldc, bias, residual, ldres, act, out_kind};
-  if (M > 8) skinny_gemm_kernel<true><<<d3d_cdiv(N, 8 * SK_NT), SK_WARPS * 32, 0, st>>>((const uint16_t*)A, lda, (const uint16_t*)W, ldw, M, N, K, kind, ep);
-  else skinny_gemm_kernel<false><<<d3d_cdiv(N, 8 * SK_NT), SK_WARPS * 32, 0, st>>>((const uint16_t*)A, lda, (const uint16_t*)W, ldw, M, N, K, kind, ep);
+  const uint16_t* a = (const uint16_t*)A;
+  const uint16_t* w = (const uint16_t*)W;
+#define SK_LAUNCH(NT, U, NA)                                                                                                              \
+  do {                                                                                                                                    \
+    if (M > 8) skinny_gemm_kernel<true, NT, U, NA><<<d3d_cdiv(N, 8 * NT), SK_WARPS * 32, 0, st>>>(a, lda, w, ldw, M, N, K, kind, ep);      \
+    else skinny_gemm_kernel<false, NT, U, NA><<<d3d_cdiv(N, 8 * NT), SK_WARPS * 32, 0, st>>>(a, lda, w, ldw, M, N, K, kind, ep);           \
+  } while (0)
+  switch (g_skinny_cfg) {  // 0 = default heuristic; 1.. = tuning variants (tools/skinny_bench.py)
+    case 1: SK_LAUNCH(1, 2, true); break;
+    case 2: SK_LAUNCH(2, 2, true); break;
+    case 3: SK_LAUNCH(2, 4, true); break;
+    case 4: SK_LAUNCH(4, 2, true); break;
+    case 5: SK_LAUNCH(1, 4, true); break;
+    case 6: SK_LAUNCH(1, 2, false); break;
+    case 7: SK_LAUNCH(2, 2, false); break;
+    case 8: SK_LAUNCH(4, 1, true); break;
+    case 9: SK_LAUNCH(2, 1, true); break;
+    default:  // tools/skinny_bench.py: wide problems stream best with 32 weight rows per CTA, narrow ones (N = 3072) need every CTA they can get
+      if (N >= 8192) SK_LAUNCH(4, 1, true);
+      else SK_LAUNCH(1, 2, true);
+      break;
+  }
+#undef SK_LAUNCH
   D3D_CHECK_LAUNCH();
   return 0;
 }
 
 }  // namespace
+
+extern "C" int d3d_gemm_skinny_set_config(int cfg) { g_skinny_cfg = cfg; return 0; }
 
 extern "C" int d3d_gemm_skinny(const d3d_gemm_args* a, void* stream) {
   D3D_REQUIRE(a != nullptr && a->A && a->W && a->C, "args");

@@ -191,6 +191,7 @@ typedef struct {
 } d3d_lm_model;
 /* C = epi(A @ W^T) for 1..16 activation rows (same argument struct and epilogue contract as d3d_gemm; K % 32 == 0). */
 int d3d_gemm_skinny(const d3d_gemm_args* args_h, void* stream);
+int d3d_gemm_skinny_set_config(int cfg);  /* 0 = default heuristic, 1..9 = tuning variants (tools/skinny_bench.py) */
 /* out[r] = index of the FIRST maximum of x[r, :n] (torch.argmax / HF greedy search). */
 int d3d_argmax_rows(const float* x, int64_t ld, int rows, int n, int* out, void* stream);
 /* Attention of the step's n_seq new query rows over their sequences' cached keys / values (prefill rows [cu[b], cu[b+1]) + decode rows). */
