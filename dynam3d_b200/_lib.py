@@ -127,7 +127,7 @@ SIGNATURES = {
     "d3d_ff_view_pre": [_P, _I, _P, _P, _P, _P, _P, _P, _P], "d3d_ff_view_post": [_P, _P, _P, _P, _P, _P], "d3d_ff_run_deferred": [_P, _P, _P],
     "d3d_event_create": [], "d3d_event_destroy": [_P],
     "d3d_ffh_finish_view": [_P, _P, _P, _P], "d3d_ffh_fetch_view": [_P] * 17, "d3d_ffh_zone_key_array": [_P, _I, _P],
-    "d3d_ffh_get_map": [_P, _I, _I, _P, _P, _P, _P], "d3d_ffh_get_p2i": [_P, _I, _P], "d3d_ffh_get_patch_pos": [_P, _I, _P],
+    "d3d_ffh_get_map": [_P, _I, _I, _P, _P, _P, _P], "d3d_ffh_get_p2i": [_P, _I, _P], "d3d_ffh_live_ids": [_P, _I, _I, _P, _P], "d3d_ffh_get_patch_pos": [_P, _I, _P],
     "d3d_ffh_get_zone_keys": [_P, _I, _P, _P, _P], "d3d_ffh_get_last": [_P, _I, _P, _P, _P, _P],
     "d3d_split16": [_P, _L, _P, _L, _I, _I, _I, _P],
     "d3d_attention_f32": [_P, _L, _P, _L, _P, _I, _I, _I, _I, _I, _F, _P],

@@ -584,6 +584,20 @@ extern "C" int d3d_ffh_get_map(void* h, int b, int which, int64_t* ids, int64_t*
   if (sizes) { sizes[0] = (int64_t)n; sizes[1] = (int64_t)tot; }
   return 0;
 }
+// dict-order keys only (get_environment_features FF:825,844): ids may be NULL to query the count
+extern "C" int d3d_ffh_live_ids(void* h, int b, int which, int64_t* ids, int64_t* n_out) {
+  FFH& H = HH(h);
+  D3D_REQUIRE(b >= 0 && b < (int)H.eps.size(), "episode index");
+  const OMap& m = which == 0 ? H.eps[(size_t)b].i2p : H.eps[(size_t)b].z2i;
+  size_t n = 0;
+  for (size_t r = 0; r < m.ids.size(); ++r) {
+    if (!m.live[r]) continue;
+    if (ids) ids[n] = m.ids[r];
+    ++n;
+  }
+  *n_out = (int64_t)n;
+  return 0;
+}
 extern "C" int d3d_ffh_get_p2i(void* h, int b, int64_t* out) {
   const Episode& ep = HH(h).eps[(size_t)b];
   if (ep.n_patch) memcpy(out, ep.p2i.data(), (size_t)ep.n_patch * sizeof(i64));

@@ -839,11 +839,11 @@ class Feature_Fields(nn.Module):
 
     def _live_ids(self, b, which):
         """dict-order keys of the instance->patch (0) or zone->instance (1) map (FF:825, 844)."""
-        sizes = np.zeros(2, np.int64)
-        L.check(L.lib().d3d_ffh_get_map(self._h, b, which, None, None, None, sizes.ctypes.data))
-        ids = np.zeros(max(int(sizes[0]), 1), np.int64); lens = np.zeros_like(ids); cat = np.zeros(max(int(sizes[1]), 1), np.int64)
-        L.check(L.lib().d3d_ffh_get_map(self._h, b, which, ids.ctypes.data, lens.ctypes.data, cat.ctypes.data, sizes.ctypes.data))
-        return ids[: int(sizes[0])].tolist()
+        ep = self.eps[b]
+        ids = np.zeros(max(ep.n_inst if which == 0 else ep.n_zone, 1), np.int64)  # live keys <= slots
+        n = np.zeros(1, np.int64)
+        L.check(L.lib().d3d_ffh_live_ids(self._h, b, which, ids.ctypes.data, n.ctypes.data))
+        return ids[: int(n[0])].tolist()
 
     # ------------------------------------------------------------------ FF:818-862
     def get_environment_features(self, agent_position, agent_heading_angle, instance_distance=5.0, zone_distance=100.0):

@@ -367,6 +367,7 @@ int d3d_ffh_fetch_view(void* h, int* new_src, int* new_owner, int64_t* new_iid, 
                        int* zn_tok_src, int* zn_tok_seq, int* zn_cu);
 int d3d_ffh_zone_key_array(void* h, int b, float* out);
 int d3d_ffh_get_map(void* h, int b, int which, int64_t* ids, int64_t* lens, int64_t* cat, int64_t* sizes2);
+int d3d_ffh_live_ids(void* h, int b, int which, int64_t* ids, int64_t* n_out);  /* dict-order keys of map `which` (ids may be NULL) */
 int d3d_ffh_get_p2i(void* h, int b, int64_t* out);
 int d3d_ffh_get_patch_pos(void* h, int b, float* out);
 int d3d_ffh_get_zone_keys(void* h, int b, float* keys, int64_t* ids, int64_t* n);

@@ -20,6 +20,10 @@ def _planner_snapshot(lib, h, b, n_patch):
     i2p, z2i, p2i = ff._map(b, 0), ff._map(b, 1), ff._p2i(b)
     pos = np.zeros((max(n_patch, 1), 3), np.float32)
     lib.d3d_ffh_get_patch_pos(h, b, pos.ctypes.data)
+    for which, m in ((0, i2p), (1, z2i)):  # the light accessor used by the export returns the same dict-order keys
+        ids = np.zeros(max(int(cnt[2 if which == 0 else 4]), 1), np.int64); n = np.zeros(1, np.int64)
+        assert lib.d3d_ffh_live_ids(h, b, which, ids.ctypes.data, n.ctypes.data) == 0
+        assert ids[: int(n[0])].tolist() == list(m.keys())
     ff._h = None
     return {"n_patches": int(cnt[0]), "p2i": {int(k): int(p2i[k]) for k in np.flatnonzero(p2i >= 0)}, "i2p": i2p, "i2p_order": list(i2p.keys()),
             "n_inst_slots": int(cnt[2]), "zone_key_to_id": Feature_Fields._zone_keys_dict(type("F", (), {"_h": h})(), b), "z2i": z2i,
