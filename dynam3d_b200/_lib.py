@@ -90,6 +90,7 @@ SIGNATURES = {
     "d3d_knn3d": [_P, _I, _P, _I, _I, _P, _P, _P],
     "d3d_seq_centroid": [_P, _P, _P, _I, _P, _P],
     "d3d_env_export": [_P, _P, _P, _I, _P, _F, _I, _P, _P, _P, _P],
+    "d3d_env_export_batched": [_P, _P, _I, _I, _P, _P],
     "d3d_segm_relabel": [_P, _I, _I, _I, _I, _I, _I, _IP, _IP, _P, _P, _P],
     "d3d_layernorm": [_P, _L, _P, _P, _P, _F, _I, _I, _I, _P, _L, _P, _L, _I, _P],
     "d3d_rmsnorm": [_P, _L, _P, _P, _F, _I, _I, _P, _L, _P, _L, _I, _P],

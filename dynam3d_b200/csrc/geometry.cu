@@ -406,9 +406,9 @@ __global__ void seq_centroid_kernel(const float* __restrict__ xyz, const int* __
 // a13: agent-frame export (FF:818-862): gather ids, rotate/translate, keep dist <= radius, order-preserving compaction
 // ------------------------------------------------------------------------------------------------
 // agent row: [cx, cy, cz (internal), cos(-heading), sin(-heading)]
-__global__ void __launch_bounds__(1024) export_kernel(const float* __restrict__ pos, const float* __restrict__ fts, const int* __restrict__ ids,
-                                                      int n_ids, const float* __restrict__ agent, float radius, int width,
-                                                      float* __restrict__ out_rel, float* __restrict__ out_fts, int* __restrict__ out_count) {
+__device__ __forceinline__ void export_body(const float* __restrict__ pos, const float* __restrict__ fts, const int* __restrict__ ids,
+                                            int n_ids, const float* __restrict__ agent, float radius, int width,
+                                            float* __restrict__ out_rel, float* __restrict__ out_fts, int* __restrict__ out_count) {
   // single block; chunks of 1024 ids with a running base keep the dict order
   __shared__ int warp_tot[32];
   __shared__ int base_s;
@@ -460,6 +460,26 @@ __global__ void __launch_bounds__(1024) export_kernel(const float* __restrict__ 
     __syncthreads();
   }
   if (tid == 0) *out_count = base_s;
+}
+
+__global__ void __launch_bounds__(1024) export_kernel(const float* __restrict__ pos, const float* __restrict__ fts, const int* __restrict__ ids,
+                                                      int n_ids, const float* __restrict__ agent, float radius, int width,
+                                                      float* __restrict__ out_rel, float* __restrict__ out_fts, int* __restrict__ out_count) {
+  export_body(pos, fts, ids, n_ids, agent, radius, width, out_rel, out_fts, out_count);
+}
+
+// all (episode, token kind) exports of a step in one launch: one block per job
+struct ExportJob {
+  const float* pos; const float* fts; long long ids_off; float* out_rel; float* out_fts;  // ids_off: first id of the job in `ids_all`
+  float agent[5]; float radius; int n_ids; int pad;
+};
+__global__ void __launch_bounds__(1024) export_batched_kernel(const ExportJob* __restrict__ jobs, const int* __restrict__ ids_all, int width,
+                                                              int* __restrict__ out_count) {
+  const ExportJob j = jobs[blockIdx.x];
+  __shared__ float ag[5];
+  if (threadIdx.x < 5) ag[threadIdx.x] = j.agent[threadIdx.x];
+  __syncthreads();
+  export_body(j.pos, j.fts, ids_all + j.ids_off, j.n_ids, ag, j.radius, width, j.out_rel, j.out_fts, out_count + blockIdx.x);
 }
 
 }  // namespace
@@ -602,6 +622,16 @@ extern "C" int d3d_seq_centroid(const float* xyz, const int* member, const int* 
   if (n_seq == 0) return 0;
   D3D_REQUIRE(xyz && member && cu_seqlens && out, "args");
   seq_centroid_kernel<<<d3d_cdiv((long long)n_seq * 32, 128), 128, 0, (cudaStream_t)stream>>>(xyz, member, cu_seqlens, n_seq, out);
+  D3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int d3d_env_export_batched(const void* jobs, const int* ids_all, int n_jobs, int width, int* out_count, void* stream) {
+  if (n_jobs == 0) return 0;
+  D3D_REQUIRE(jobs && ids_all && out_count, "args");
+  D3D_REQUIRE(width % 4 == 0, "feature width must be a multiple of 4");
+  static_assert(sizeof(ExportJob) == 72, "job layout is part of the C ABI (see include/dynam3d_b200.h)");
+  export_batched_kernel<<<n_jobs, 1024, 0, (cudaStream_t)stream>>>((const ExportJob*)jobs, ids_all, width, out_count);
   D3D_CHECK_LAUNCH();
   return 0;
 }

@@ -32,6 +32,10 @@ from . import ops
 
 F32 = np.float32
 D = 768
+# record layout of d3d_env_export_batched (include/dynam3d_b200.h)
+_EXPORT_JOB = np.dtype([("pos", "<u8"), ("fts", "<u8"), ("ids_off", "<i8"), ("out_rel", "<u8"), ("out_fts", "<u8"), ("agent", "<f4", (5,)),
+                        ("radius", "<f4"), ("n_ids", "<i4"), ("pad", "<i4")])
+assert _EXPORT_JOB.itemsize == 72
 TRACE = None  # set to a list: _update_view appends (launch_ms, sync_wait_ms, plan_ms, post_ms) host wall times per view (profiling aid)
 _TORCH_DT = {np.int32: torch.int32, np.int64: torch.int64, np.float32: torch.float32, np.uint8: torch.uint8, np.float16: torch.float16}
 
@@ -847,31 +851,42 @@ class Feature_Fields(nn.Module):
 
     # ------------------------------------------------------------------ FF:818-862
     def get_environment_features(self, agent_position, agent_heading_angle, instance_distance=5.0, zone_distance=100.0):
+        """Agent-frame instance (<= 5 m) and zone (<= 100 m) tokens of every episode in dict order: one upload, ONE kernel launch and one
+        count read-back for the whole batch."""
         dev = self.device
-        res = []
+        B = self.batch_size
+        jobs = np.zeros(2 * B, _EXPORT_JOB)
+        ids_all, offs, n_rows = [], [], 0
         for b, ep in enumerate(self.eps):
-            agent = torch.from_numpy(ops.camera_rows(agent_position[b], [agent_heading_angle[b]])[0]).to(dev, non_blocking=True)
-            pair = []
-            for ids, pos, fts, radius in ((self._live_ids(b, 0), ep.inst_pos.t, ep.inst_fts.t, instance_distance),
-                                          (self._live_ids(b, 1), ep.zone_pos.t, ep.zone_fts.t, zone_distance)):
-                n = len(ids)
-                rel = torch.empty((max(n, 1), 3), device=dev, dtype=torch.float32)
-                out = torch.empty((max(n, 1), D), device=dev, dtype=torch.float32)
-                cnt = torch.zeros((1,), device=dev, dtype=torch.int32)
-                ids_d = torch.tensor(ids, device=dev, dtype=torch.int32) if n else torch.zeros((1,), device=dev, dtype=torch.int32)
-                L.check(L.lib().d3d_env_export(L.ptr(pos), L.ptr(fts), L.ptr(ids_d), n, L.ptr(agent), float(radius), D, L.ptr(rel), L.ptr(out),
-                                               L.ptr(cnt), L.stream_ptr()))
-                pair.append((rel, out, cnt.to("cpu", non_blocking=True)))
-            res.append(pair)
-        torch.cuda.current_stream().synchronize()
-        out = {"batch_instance_fts": [], "batch_instance_relative_position": [], "batch_zone_fts": [], "batch_zone_relative_position": []}
-        for (ri, fi, ci), (rz, fz, cz) in res:
-            ni, nz = int(ci.item()), int(cz.item())
-            out["batch_instance_fts"].append(fi[:ni])
-            out["batch_instance_relative_position"].append(ri[:ni])
-            out["batch_zone_fts"].append(fz[:nz])
-            out["batch_zone_relative_position"].append(rz[:nz])
-        return out
+            agent = ops.camera_rows(agent_position[b], [agent_heading_angle[b]])[0]
+            for k, (which, pos, fts, radius) in enumerate(((0, ep.inst_pos.t, ep.inst_fts.t, instance_distance),
+                                                           (1, ep.zone_pos.t, ep.zone_fts.t, zone_distance))):
+                ids = self._live_ids(b, which)
+                j = jobs[2 * b + k]
+                j["pos"], j["fts"], j["ids_off"], j["n_ids"] = pos.data_ptr(), fts.data_ptr(), len(ids_all), len(ids)
+                j["agent"], j["radius"] = agent, radius
+                offs.append(n_rows)
+                n_rows += max(len(ids), 1)
+                ids_all.extend(ids)
+        rel = torch.empty((n_rows, 3), device=dev, dtype=torch.float32)
+        out = torch.empty((n_rows, D), device=dev, dtype=torch.float32)
+        for i, o in enumerate(offs):
+            jobs[i]["out_rel"], jobs[i]["out_fts"] = rel.data_ptr() + 12 * o, out.data_ptr() + 4 * D * o
+        cnt = torch.zeros((2 * B,), device=dev, dtype=torch.int32)
+        with L.stream_scope():
+            jobs_d, ids_d = self._upload([jobs.view(np.uint8).reshape(-1), np.asarray(ids_all if ids_all else [0], np.int32)])
+            L.check(L.lib().d3d_env_export_batched(L.ptr(jobs_d), L.ptr(ids_d), 2 * B, D, L.ptr(cnt), L.stream_ptr()))
+            cnt_h = cnt.to("cpu", non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        res = {"batch_instance_fts": [], "batch_instance_relative_position": [], "batch_zone_fts": [], "batch_zone_relative_position": []}
+        c = cnt_h.tolist()
+        for b in range(B):
+            oi, oz = offs[2 * b], offs[2 * b + 1]
+            res["batch_instance_fts"].append(out[oi:oi + c[2 * b]])
+            res["batch_instance_relative_position"].append(rel[oi:oi + c[2 * b]])
+            res["batch_zone_fts"].append(out[oz:oz + c[2 * b + 1]])
+            res["batch_zone_relative_position"].append(rel[oz:oz + c[2 * b + 1]])
+        return res
 
     # ------------------------------------------------------------------ discrete-state snapshot (parity tests)
     def snapshot(self, b=0):

@@ -143,6 +143,10 @@ int d3d_seq_centroid(const float* xyz, const int* member, const int* cu_seqlens,
  * agent [5] = (x, y, z internal, cos(-heading), sin(-heading)).  out_rel [n_ids,3], out_fts [n_ids,width], *out_count. */
 int d3d_env_export(const float* pos, const float* fts, const int* ids, int n_ids, const float* agent, float radius, int width,
                    float* out_rel, float* out_fts, int* out_count, void* stream);
+/* All (episode, token kind) exports of a step in ONE launch (one block per job).  jobs: device array of 72-byte records
+ * { const float* pos; const float* fts; int64 ids_off; float* out_rel; float* out_fts; float agent[5]; float radius; int n_ids; int pad; };
+ * ids_all: the jobs' id lists back to back (job i reads ids_all[ids_off .. ids_off + n_ids)); out_count [n_jobs]. */
+int d3d_env_export_batched(const void* jobs, const int* ids_all, int n_jobs, int width, int* out_count, void* stream);
 
 /* FastSAM post-processing (FF:411-422): masks [n_img, M, H, W] u8 (0/1, in FastSAM's order) -> dense segment labels
  * out [n_img, gh*gw] int64 in 0..G-1 and n_seg[n_img]: later masks overwrite earlier ones, uncovered pixels take label 0,
