@@ -294,9 +294,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, uint16_t* __restrict_
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(6));
       STAMP(st_on && j < 8, j * 8 + 2);
+      // rows past the end of the sequence (last query tile) and keys past it (last key tile) take no part in the arithmetic below:
+      // their exponentials are skipped (the kernel is MUFU-bound), their P entries are zero
+      const int nvv = EDGE ? (row < len ? nv : 0) : 64;
       float mx = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < 64; ++i) mx = fmaxf(mx, (!EDGE || i < nv) ? __uint_as_float(v[i]) : -INFINITY);
+      for (int i = 0; i < 64; ++i) mx = fmaxf(mx, (!EDGE || i < nvv) ? __uint_as_float(v[i]) : -INFINITY);
       STAMP(st_on && j < 8, j * 8 + 3);
       // lazy rescale: keep the old base while this half's row max grew by <= 8 (P <= 2^8)
       const float m_cand = fmaxf(m, mx * scale_log2);
@@ -329,13 +332,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, uint16_t* __restrict_
       float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
       for (int i = 0; i < 64; i += 2) {
+        if (EDGE && i >= nvv) {  // both keys masked: no exponentials
+          v[i >> 1] = 0u;
+          continue;
+        }
         float t0, t1;
         ffma2(t0, t1, __uint_as_float(v[i]), __uint_as_float(v[i + 1]), scale_log2, scale_log2, nbase, nbase);
         float p0 = ex2_approx(t0), p1 = ex2_approx(t1);
-        if (EDGE) {
-          p0 = (i < nv) ? p0 : 0.f;
-          p1 = (i + 1 < nv) ? p1 : 0.f;
-        }
+        if (EDGE) p1 = (i + 1 < nvv) ? p1 : 0.f;
         fadd2(rs0, rs1, rs0, rs1, p0, p1);
         v[i >> 1] = pack16x2(p0, p1, kind);
       }
@@ -356,7 +360,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, uint16_t* __restrict_
       }
     };
     for (int j = 0; j < n_tiles; ++j) {
-      const bool edge = __any_sync(0xffffffffu, j * BKV + BKV > lim_row);  // warp-uniform
+      const bool edge = __any_sync(0xffffffffu, j * BKV + BKV > lim_row || row >= len);  // warp-uniform
       STAMP(st_on && j < 8, j * 8 + 0);
       mbar_wait_sleepy(bar(5), (uint32_t)j & 1u);
       tc_fence_after();
