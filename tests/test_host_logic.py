@@ -101,3 +101,35 @@ def test_sharding_and_allgather_over_gloo_world2():
     for r in res:
         assert r[2] == [[0.0] * 5, [0.0] * 5, [1.0] * 5, [1.0] * 5]
         assert tuple(r[3]) == (4, 6, 4) and r[4] == [3, 1, 4, 1] and r[5] == 1.0
+
+
+def test_toy_tokenizer_matches_character_scan():
+    """The regex form of the stand-in tokenizer (runs of "<image>" in one match) equals the plain left-to-right character scan."""
+    from dynam3d_b200 import synth
+    special = synth.ToyTokenizer.SPECIAL
+
+    def scan(text):
+        ids, i = [1], 0
+        while i < len(text):
+            for tok, tid in special.items():
+                if text.startswith(tok, i):
+                    ids.append(tid)
+                    i += len(tok)
+                    break
+            else:
+                ids.append(3 + (ord(text[i]) * 131) % 31990)
+                i += 1
+        return ids
+    tok = synth.ToyTokenizer()
+    cases = ["<|user|>\n" + "<image>" * 700 + "\nInstruction:\nwalk <ima ge> <|end<|end|>|>\nHistory actions:\n" + "none\n" * 4 + "<|end|>\n<|assistant|>\nNext action:\n",
+             "", "<image", "<<image>>", "a<|user|><|user|>b", "<image><image>x<image>", "<|assistant|><image>"]
+    for c in cases:
+        assert tok(c) == scan(c)
+
+
+def test_export_job_record_layout_matches_header():
+    """The numpy record the engine uploads for d3d_env_export_batched is the 72-byte struct documented in include/dynam3d_b200.h."""
+    from dynam3d_b200.feature_fields import _EXPORT_JOB
+    assert _EXPORT_JOB.itemsize == 72
+    offs = {n: _EXPORT_JOB.fields[n][1] for n in _EXPORT_JOB.names}
+    assert offs == {"pos": 0, "fts": 8, "ids_off": 16, "out_rel": 24, "out_fts": 32, "agent": 40, "radius": 60, "n_ids": 64, "pad": 68}
