@@ -49,6 +49,51 @@ struct SkinnyEpi {
   int act, out_kind;
 };
 
+// one thread per (tile, row, column pair): fixed-order sum over the 8 K-slices (deterministic), then bias / activation / residual / store
+template <int NT>
+__device__ __forceinline__ void skinny_epilogue(const float (*red)[NT][16][8], int n_base, int M, int N, const SkinnyEpi& ep) {
+  const int e = threadIdx.x;
+  if (e < NT * 16 * 4) {
+    const int t = e / 64, r = (e / 4) % 16, cp = e % 4;
+    const int n = n_base + t * 8 + cp * 2;
+    if (r < M && n < N) {
+      float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+      for (int w = 0; w < SK_WARPS; ++w) {
+        v0 += red[w][t][r][cp * 2];
+        v1 += red[w][t][r][cp * 2 + 1];
+      }
+      const bool has1 = n + 1 < N;
+      if (ep.bias) {
+        v0 += ep.bias[n];
+        if (has1) v1 += ep.bias[n + 1];
+      }
+      if (ep.act == D3D_ACT_SWIGLU) {  // row-interleaved gate/up: columns (2j, 2j+1) -> output column j
+        const float o = __fdividef(v0, 1.0f + __expf(-v0)) * v1;
+        const long long oc = n >> 1;
+        if (ep.out_kind == D3D_OUT_F32) ((float*)ep.C)[(long long)r * ep.ldc + oc] = o;
+        else st16(ep.C, (size_t)((long long)r * ep.ldc + oc), o, ep.out_kind);
+      } else {
+        if (ep.act == D3D_ACT_QUICK_GELU) { v0 = quick_gelu(v0); v1 = quick_gelu(v1); }
+        else if (ep.act == D3D_ACT_GELU) { v0 = gelu_erf(v0); v1 = gelu_erf(v1); }
+        else if (ep.act == D3D_ACT_SILU) { v0 = silu(v0); v1 = silu(v1); }
+        else if (ep.act == D3D_ACT_LEAKY_RELU) { v0 = v0 > 0.f ? v0 : 0.01f * v0; v1 = v1 > 0.f ? v1 : 0.01f * v1; }
+        if (ep.residual) {
+          v0 += ep.residual[(long long)r * ep.ldres + n];
+          if (has1) v1 += ep.residual[(long long)r * ep.ldres + n + 1];
+        }
+        if (ep.out_kind == D3D_OUT_F32) {
+          ((float*)ep.C)[(long long)r * ep.ldc + n] = v0;
+          if (has1) ((float*)ep.C)[(long long)r * ep.ldc + n + 1] = v1;
+        } else {
+          st16(ep.C, (size_t)((long long)r * ep.ldc + n), v0, ep.out_kind);
+          if (has1) st16(ep.C, (size_t)((long long)r * ep.ldc + n + 1), v1, ep.out_kind);
+        }
+      }
+    }
+  }
+}
+
 // Fragment trick: a K "super-step" is 128 elements.  Thread (g = lane/4, kq = lane%4) loads the 64 contiguous bytes (32 K-elements at
 // k0 = 128*ss + 32*kq) of A row g / g+8 and of W row n0+g, so a warp instruction group reads 256 contiguous bytes of each of its 8 weight
 // rows (DRAM-friendly).  Every 16-byte piece feeds two MMAs: elements {0,1} are K-slots (2kq, 2kq+1), {2,3} slots (2kq+8, 2kq+9) of the
@@ -115,45 +160,132 @@ __global__ void __launch_bounds__(SK_WARPS * 32) skinny_gemm_kernel(const uint16
     red[warp][t][g + 8][kq * 2 + 1] = acc[t][3];
   }
   __syncthreads();
-  // one thread per (tile, row, column pair): fixed-order sum over the 8 K-slices, then the epilogue
-  const int e = threadIdx.x;
-  if (e < SK_NT * 16 * 4) {
-    const int t = e / 64, r = (e / 4) % 16, cp = e % 4;
-    const int n = n_base + t * 8 + cp * 2;
-    if (r < M && n < N) {
-      float v0 = 0.f, v1 = 0.f;
+  skinny_epilogue<SK_NT>(red, n_base, M, N, ep);
+}
+
+// ---- bulk-copy variant of the skinny GEMM -------------------------------------------------------------------------------------
+// The register-staged kernel above keeps the LSU busy (eight 64-byte row pieces per warp load) and tops out near 3.6 TB/s.  Here a
+// producer warp streams the CTA's 16 weight rows with cp.async.bulk (1 KB per row and stage, mbarrier complete_tx) into a 6-stage
+// shared-memory ring -- no LSU wavefronts, no register staging, ~96 KB in flight per CTA -- and 8 consumer warps read their fragments
+// with conflict-free 16-byte LDS (row pitch 1088 B) using the same K-permuted fragment trick.
+constexpr int BK_ROWS = 16;                 // weight rows per CTA (2 n-tiles)
+constexpr int BK_KC = 512;                  // K elements per stage (1 KB per row)
+constexpr int BK_PITCH = BK_KC * 2 + 64;    // 1088 B: consecutive rows start 16 banks apart -> 2 rows x 64 B per LDS wavefront, no conflicts
+constexpr int BK_STAGES = 6;
+constexpr int BK_STAGE_BYTES = BK_ROWS * BK_PITCH;
+constexpr int BK_SMEM = BK_STAGES * BK_STAGE_BYTES + 128;
+
+__device__ __forceinline__ void bk_mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void bk_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bk_mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void bk_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "BK_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra BK_DONE;\n\t"
+      "bra BK_WAIT;\n\t"
+      "BK_DONE:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+template <bool HI>
+__global__ void __launch_bounds__(288) skinny_bulk_kernel(const uint16_t* __restrict__ A, long long lda, const uint16_t* __restrict__ W, long long ldw,
+                                                          int M, int N, int K, int kind, SkinnyEpi ep) {
+  extern __shared__ __align__(128) uint8_t bk_smem[];
+  __shared__ float red[SK_WARPS][2][16][8];
+  const uint32_t sbase = smem_u32(bk_smem);
+  const uint32_t bar0 = sbase + BK_STAGES * BK_STAGE_BYTES;  // full[s] at +8s, empty[s] at +8(STAGES+s)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = (N + BK_ROWS - 1) / BK_ROWS;
+  const int n_stages = (K + BK_KC - 1) / BK_KC;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < BK_STAGES; ++s) { bk_mbar_init(bar0 + 8 * s, 1); bk_mbar_init(bar0 + 8 * (BK_STAGES + s), SK_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // persistent: the CTA walks row tiles blockIdx.x, +gridDim.x, ...; the ring position runs on across tiles, so the producer keeps
+  // ~96 KB of weight rows in flight while the consumers reduce and store the previous tile
+  if (warp == SK_WARPS) {
+    // ===== producer: one row copy per lane =====
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int n_base = tile * BK_ROWS;
+      const int rows = min(BK_ROWS, N - n_base);
+      for (int ks = 0; ks < n_stages; ++ks, ++it) {
+        const int s = it % BK_STAGES;
+        const uint32_t ph = (uint32_t)(it / BK_STAGES) & 1u;
+        bk_mbar_wait(bar0 + 8 * (BK_STAGES + s), ph ^ 1u);
+        const int k0 = ks * BK_KC;
+        const uint32_t bytes = (uint32_t)min(BK_KC, K - k0) * 2u;
+        if (lane == 0) bk_mbar_expect_tx(bar0 + 8 * s, bytes * (uint32_t)rows);
+        __syncwarp();
+        if (lane < rows) bulk_g2s(sbase + s * BK_STAGE_BYTES + lane * BK_PITCH, W + (long long)(n_base + lane) * ldw + k0, bytes, bar0 + 8 * s);
+      }
+    }
+  } else {
+    // ===== consumers: warp w owns K elements [64w, 64w + 64) of every stage =====
+    const int g = lane >> 2, kq = lane & 3;
+    const bool lo_ok = g < M, hi_ok = HI && g + 8 < M;
+    const uint16_t* a_lo_p = A + (long long)(lo_ok ? g : 0) * lda + warp * 64 + kq * 8;
+    const uint16_t* a_hi_p = A + (long long)(hi_ok ? g + 8 : 0) * lda + warp * 64 + kq * 8;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int n_base = tile * BK_ROWS;
+      const int rows = min(BK_ROWS, N - n_base);
+      const bool ok0 = g < rows, ok1 = g + 8 < rows;
+      float acc[2][4];
 #pragma unroll
-      for (int w = 0; w < SK_WARPS; ++w) {
-        v0 += red[w][t][r][cp * 2];
-        v1 += red[w][t][r][cp * 2 + 1];
-      }
-      const bool has1 = n + 1 < N;
-      if (ep.bias) {
-        v0 += ep.bias[n];
-        if (has1) v1 += ep.bias[n + 1];
-      }
-      if (ep.act == D3D_ACT_SWIGLU) {  // row-interleaved gate/up: columns (2j, 2j+1) -> output column j
-        const float o = __fdividef(v0, 1.0f + __expf(-v0)) * v1;
-        const long long oc = n >> 1;
-        if (ep.out_kind == D3D_OUT_F32) ((float*)ep.C)[(long long)r * ep.ldc + oc] = o;
-        else st16(ep.C, (size_t)((long long)r * ep.ldc + oc), o, ep.out_kind);
-      } else {
-        if (ep.act == D3D_ACT_QUICK_GELU) { v0 = quick_gelu(v0); v1 = quick_gelu(v1); }
-        else if (ep.act == D3D_ACT_GELU) { v0 = gelu_erf(v0); v1 = gelu_erf(v1); }
-        else if (ep.act == D3D_ACT_SILU) { v0 = silu(v0); v1 = silu(v1); }
-        else if (ep.act == D3D_ACT_LEAKY_RELU) { v0 = v0 > 0.f ? v0 : 0.01f * v0; v1 = v1 > 0.f ? v1 : 0.01f * v1; }
-        if (ep.residual) {
-          v0 += ep.residual[(long long)r * ep.ldres + n];
-          if (has1) v1 += ep.residual[(long long)r * ep.ldres + n + 1];
+      for (int t = 0; t < 2; ++t)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[t][i] = 0.f;
+      for (int ks = 0; ks < n_stages; ++ks, ++it) {
+        const int s = it % BK_STAGES;
+        const uint32_t ph = (uint32_t)(it / BK_STAGES) & 1u;
+        const int k0 = ks * BK_KC + warp * 64;
+        // A fragments of the two 32-element K-steps of this warp (L1 / L2 resident), issued before the wait
+        uint4 al[2], ah[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const bool in = k0 + u * 32 + kq * 8 < K;
+          al[u] = (in && lo_ok) ? __ldg(reinterpret_cast<const uint4*>(a_lo_p + ks * BK_KC + u * 32)) : make_uint4(0, 0, 0, 0);
+          ah[u] = (HI && in && hi_ok) ? __ldg(reinterpret_cast<const uint4*>(a_hi_p + ks * BK_KC + u * 32)) : make_uint4(0, 0, 0, 0);
         }
-        if (ep.out_kind == D3D_OUT_F32) {
-          ((float*)ep.C)[(long long)r * ep.ldc + n] = v0;
-          if (has1) ((float*)ep.C)[(long long)r * ep.ldc + n + 1] = v1;
-        } else {
-          st16(ep.C, (size_t)((long long)r * ep.ldc + n), v0, ep.out_kind);
-          if (has1) st16(ep.C, (size_t)((long long)r * ep.ldc + n + 1), v1, ep.out_kind);
+        bk_mbar_wait(bar0 + 8 * s, ph);
+        const uint32_t st = sbase + s * BK_STAGE_BYTES + (uint32_t)(warp * 128 + kq * 16);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const bool in = k0 + u * 32 + kq * 8 < K;
+          uint4 w0 = make_uint4(0, 0, 0, 0), w1 = make_uint4(0, 0, 0, 0);
+          if (in && ok0) asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w0.x), "=r"(w0.y), "=r"(w0.z), "=r"(w0.w) : "r"(st + g * BK_PITCH + u * 64));
+          if (in && ok1) asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w1.x), "=r"(w1.y), "=r"(w1.z), "=r"(w1.w) : "r"(st + (g + 8) * BK_PITCH + u * 64));
+          mma16816(acc[0], al[u].x, ah[u].x, al[u].y, ah[u].y, w0.x, w0.y, kind);
+          mma16816(acc[0], al[u].z, ah[u].z, al[u].w, ah[u].w, w0.z, w0.w, kind);
+          mma16816(acc[1], al[u].x, ah[u].x, al[u].y, ah[u].y, w1.x, w1.y, kind);
+          mma16816(acc[1], al[u].z, ah[u].z, al[u].w, ah[u].w, w1.z, w1.w, kind);
         }
+        __syncwarp();
+        if (lane == 0) bk_mbar_arrive(bar0 + 8 * (BK_STAGES + s));
       }
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        red[warp][t][g][kq * 2] = acc[t][0];
+        red[warp][t][g][kq * 2 + 1] = acc[t][1];
+        red[warp][t][g + 8][kq * 2] = acc[t][2];
+        red[warp][t][g + 8][kq * 2 + 1] = acc[t][3];
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 consumer warps only: the producer keeps streaming the next tile
+      skinny_epilogue<2>(red, n_base, M, N, ep);
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // `red` is rewritten by the next tile
     }
   }
 }
@@ -306,10 +438,20 @@ int skinny(const void* A, long long lda, const void* W, long long ldw, void* C, 
     case 7: SK_LAUNCH(2, 2, false); break;
     case 8: SK_LAUNCH(4, 1, true); break;
     case 9: SK_LAUNCH(2, 1, true); break;
-    default:  // tools/skinny_bench.py: wide problems stream best with 32 weight rows per CTA, narrow ones (N = 3072) need every CTA they can get
-      if (N >= 8192) SK_LAUNCH(4, 1, true);
-      else SK_LAUNCH(1, 2, true);
+    case 10:
+    bulk: {  // bulk-copy (cp.async.bulk + mbarrier ring) variant
+      static bool attr = false;
+      if (!attr) {
+        D3D_CHECK_CUDA(cudaFuncSetAttribute(skinny_bulk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM));
+        D3D_CHECK_CUDA(cudaFuncSetAttribute(skinny_bulk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM));
+        attr = true;
+      }
+      const int tiles = d3d_cdiv(N, BK_ROWS), grid = tiles < 2 * d3d_num_sms() ? tiles : 2 * d3d_num_sms();  // two resident CTAs per SM
+      if (M > 8) skinny_bulk_kernel<true><<<grid, 288, BK_SMEM, st>>>(a, lda, w, ldw, M, N, K, kind, ep);
+      else skinny_bulk_kernel<false><<<grid, 288, BK_SMEM, st>>>(a, lda, w, ldw, M, N, K, kind, ep);
       break;
+    }
+    default: goto bulk;  // tools/skinny_bench.py: the persistent cp.async.bulk kernel streams fastest on every Phi-3 shape
   }
 #undef SK_LAUNCH
   D3D_CHECK_LAUNCH();

@@ -26,7 +26,8 @@ def _ref(a, w, bias, act, residual):
     (1, 23, 96, torch.bfloat16, True, 0, True, torch.float32),
     (11, 40, 3072, torch.float16, False, 4, False, torch.float32),
 ])
-def test_skinny_gemm_matches_torch(M, N, K, dtype, use_bias, act, use_res, out_dtype):
+@pytest.mark.parametrize("variant", [0, 10])  # 0 = register-staged kernels (heuristic), 10 = cp.async.bulk ring
+def test_skinny_gemm_matches_torch(M, N, K, dtype, use_bias, act, use_res, out_dtype, variant):
     """HBM-bound decode GEMM (1..16 rows) vs a plain PyTorch fp32 reference; only the summation order differs (tolerances as test_gemm_gpu)."""
     import ctypes
     from dynam3d_b200 import _lib as L
@@ -40,8 +41,12 @@ def test_skinny_gemm_matches_torch(M, N, K, dtype, use_bias, act, use_res, out_d
     out = torch.zeros((M, ldc), device="cuda", dtype=out_dtype)
     args = L.GemmArgs(L.ptr(a), a.stride(0), L.ptr(w), w.stride(0), L.ptr(out), ldc, M, N, K, L.kind_of(dtype), L.kind_of(out_dtype), L.ptr(bias),
                       act, L.ptr(res), ldc if use_res else 0)
-    L.check(L.lib().d3d_gemm_skinny(ctypes.cast(ctypes.byref(args), ctypes.c_void_p), L.stream_ptr()))
-    torch.cuda.synchronize()
+    try:
+        L.lib().d3d_gemm_skinny_set_config(variant)
+        L.check(L.lib().d3d_gemm_skinny(ctypes.cast(ctypes.byref(args), ctypes.c_void_p), L.stream_ptr()))
+        torch.cuda.synchronize()
+    finally:
+        L.lib().d3d_gemm_skinny_set_config(0)
     ref = _ref(a, w, bias, act, res[:, :n_out] if use_res else None)
     tol = 2e-3 if out_dtype == torch.float32 else 8e-3
     err = (out[:, :n_out].float() - ref).abs().max().item()

@@ -12,7 +12,7 @@ for name, N, K, act in SHAPES:
     ws = [(torch.randn(N, K, device="cuda") * K ** -0.5).half() for _ in range(n_w)]
     a = (torch.randn(M, K, device="cuda") * 0.5).half()
     out = torch.empty(M, N // 2 if act == 4 else N, device="cuda", dtype=torch.float16)
-    for cfg in range(0, 10):
+    for cfg in range(0, 11):
         L.lib().d3d_gemm_skinny_set_config(cfg)
         ts = []
         for it in range(3 + 3 * n_w):
