@@ -78,7 +78,7 @@ _IP, _FP = ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_float)
 
 # argument types of every exported entry (mirrors include/dynam3d_b200.h); tests/test_abi.py checks the symbol list
 SIGNATURES = {
-    "d3d_version": [], "d3d_sm_count": [], "d3d_check_device": [_I],
+    "d3d_version": [], "d3d_sm_count": [], "d3d_check_device": [_I], "d3d_launch_count": [],
     "d3d_gemm": [_P, _P], "d3d_gemm_simt": [_P, _P], "d3d_gemm_set_pair_mode": [_I],
     "d3d_depth_preprocess": [_P, _P, _I, _I, _I, _F, _F, _P],
     "d3d_depth_patch_grid": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _IP, _IP, _F, _F, _P],
@@ -151,7 +151,7 @@ def _declare(lib_):
             raise D3DLibraryError(f"{LIB_PATH} does not export {name}: stale build?")
         fn.argtypes = argtypes
         fn.restype = {"d3d_pool_workspace_bytes": ctypes.c_size_t, "d3d_ffh_create": ctypes.c_void_p, "d3d_ffh_destroy": None,
-                      "d3d_event_create": ctypes.c_void_p, "d3d_event_destroy": None}.get(name, ctypes.c_int)
+                      "d3d_event_create": ctypes.c_void_p, "d3d_event_destroy": None, "d3d_launch_count": ctypes.c_longlong}.get(name, ctypes.c_int)
 
 
 def lib():

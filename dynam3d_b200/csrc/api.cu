@@ -23,6 +23,8 @@ int d3d_num_sms() {
   return n;
 }
 
+unsigned long long g_d3d_launches = 0;
+extern "C" long long d3d_launch_count(void) { return (long long)g_d3d_launches; }
 extern "C" const char* d3d_last_error(void) { return g_err; }
 extern "C" int d3d_version(void) { return 100; }
 extern "C" int d3d_sm_count(void) { return d3d_num_sms(); }

@@ -31,7 +31,13 @@ void d3d_set_error(const char* fmt, ...);
     }                                                                                             \
   } while (0)
 
-#define D3D_CHECK_LAUNCH() D3D_CHECK_CUDA(cudaGetLastError())
+// every kernel launch site is followed by this macro: it also counts the launch (d3d_launch_count(), bench.py `gpu_launches`)
+extern unsigned long long g_d3d_launches;
+#define D3D_CHECK_LAUNCH()                  \
+  do {                                      \
+    ++g_d3d_launches;                       \
+    D3D_CHECK_CUDA(cudaGetLastError());     \
+  } while (0)
 
 #define D3D_TRY(expr)                                                                             \
   do {                                                                                            \

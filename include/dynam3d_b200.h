@@ -49,6 +49,8 @@ int d3d_version(void);
 /* 0 when device `dev` is an sm_100 part, D3D_EARCH otherwise */
 int d3d_check_device(int dev);
 int d3d_sm_count(void);
+/* number of kernels this library has launched in the calling process (bench.py reports the difference over the timed region) */
+long long d3d_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Tensor-core GEMM (tcgen05.mma + TMEM accumulators, TMA-fed, persistent):  C = epi(A @ W^T)
