@@ -30,24 +30,22 @@ def _planner_snapshot(lib, h, b, n_patch):
             "z2i_order": list(z2i.keys()), "n_zone_slots": int(cnt[4]), "patch_tomb": (pos[:n_patch, 0] == -10000.0).copy()}, cnt
 
 
-@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "ff_traj_*.npz"))), ids=os.path.basename)
-def test_step_planner_reproduces_golden_state(path):
-    """Same check through the whole-step entry points the engine uses (d3d_ffh_begin_step + d3d_ffh_begin_view_refs): all views of a step
-    are planned up front, the per-view results are then fed in order."""
+def _drive_step_planner(cfg, steps, gold):
+    """Runs the oracle over `steps` and replays its per-view numeric results into the whole-step planner entry points
+    (d3d_ffh_begin_step + d3d_ffh_begin_view_refs + d3d_ffh_finish_view); the planner's discrete state must equal the oracle's (and the
+    golden reference state when given) after every step."""
     import copy
     from dynam3d_b200 import _lib as L
     from dynam3d_b200.feature_fields import Feature_Fields
     from oracle import geometry as G
     from oracle import ref_compare as RC
     from oracle.ff_oracle import FeatureFieldsOracle
-    from oracle.make_golden import load_ff_fixture
     lib = L.lib()
-    cfg, steps, gold = load_ff_fixture(path)
     V, P = cfg["num_views"], 576
     orc = FeatureFieldsOracle(RC.ff_params(cfg["weight_seed"], cfg["merge_bias"]), batch_size=1, rnd=None)
     h = lib.d3d_ffh_create(1, 2, 2.0)
     try:
-        for t, (st, g) in enumerate(zip(steps, gold)):
+        for t, (st, g) in enumerate(zip(steps, gold if gold is not None else [None] * len(steps))):
             d576 = G.depth_patch_grid(st["depth"], 1, V, q1_fix=cfg.get("q1_fix", False))
             full = G.preprocess_depth(st["depth"], (0.0, 10.0)).reshape(1, V, 256, 256)
             pos, head = [st["position"]], [st["heading"]]
@@ -103,9 +101,33 @@ def test_step_planner_reproduces_golden_state(path):
                     last = Feature_Fields._last(type("F", (), {"_h": h})(), 0)
                     assert np.array_equal(last["knn"][1], last_knn[1]) and np.array_equal(last["merge"], last_merge[0].astype(bool)), (t, ix)
             snap, cnt = _planner_snapshot(lib, h, 0, len(ep.patch_pos))
-            assert RC.snapshots_equal(g["snap"], snap) == [], f"step {t}"
+            if g is not None:
+                assert RC.snapshots_equal(g["snap"], snap) == [], f"step {t}"
+            assert RC.snapshots_equal(orc.snapshot(0), snap) == [], f"step {t} (oracle)"
     finally:
         lib.d3d_ffh_destroy(h)
+
+
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "ff_traj_*.npz"))), ids=os.path.basename)
+def test_step_planner_reproduces_golden_state(path):
+    """The whole-step entry points the engine uses, on the golden trajectories produced by the reference."""
+    from oracle.make_golden import load_ff_fixture
+    cfg, steps, gold = load_ff_fixture(path)
+    _drive_step_planner(cfg, steps, gold)
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(seed=21, n_steps=5, num_views=2, n_seg=48, seg_kind="voronoi", merge_bias=2.0, weight_seed=3),   # merge-heavy: slot reuse after culls
+    dict(seed=22, n_steps=4, num_views=3, n_seg=16, seg_kind="voronoi", merge_bias=0.3, weight_seed=1, q1_fix=True),
+    dict(seed=23, n_steps=6, num_views=1, n_seg=36, seg_kind="blocks", merge_bias=-2.0, weight_seed=2),   # never merges: instance slots only grow / die
+], ids=lambda c: f"seed{c['seed']}")
+def test_step_planner_matches_oracle_on_fresh_trajectories(cfg):
+    """Beyond the three golden fixtures: seeded trajectories with other view counts, segmentations and merge rates (oracle vs planner)."""
+    from oracle import ref_compare as RC
+    steps = RC.make_inputs(cfg["seed"], cfg["n_steps"], cfg["num_views"], cfg["n_seg"], cfg["seg_kind"])
+    _drive_step_planner(cfg, steps, None)
 
 
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "ff_traj_*.npz"))), ids=os.path.basename)
