@@ -16,21 +16,30 @@
 
 namespace {
 
-constexpr int D = 64;
 constexpr int BQ = 128;
 constexpr int BKV = 128;
 constexpr int NTHREADS = 320;  // warp 0: TMEM alloc + TMA; warp 1: MMA issue; warps 2-9: softmax (2 per TMEM lane quadrant); 96 regs at 2 CTAs/SM
 constexpr int NSOFT = 8;
-constexpr int TILE_BYTES = 128 * 64 * 2;                 // one [128 x 64] 16-bit tile = 16 KB
-constexpr int SMEM_Q = 0;
-constexpr int SMEM_K = TILE_BYTES;                       // 2 stages
-constexpr int SMEM_V = 3 * TILE_BYTES;                   // 2 stages
-constexpr int SMEM_P = 5 * TILE_BYTES;                   // [128 x 128] = 2 atoms of [128 x 64]
-constexpr int SMEM_BAR = 7 * TILE_BYTES;
-constexpr int SMEM_XMAX = SMEM_BAR + 128;                // [2][128] bf16 row-max exchange between the two column halves
-constexpr int SMEM_BYTES = SMEM_XMAX + 512;              // 115328; 2 CTAs/SM: 2 x (115328 + 1024 reserved) <= 233472 (228 KB)
-static_assert(2 * (SMEM_BYTES + 1024) <= 233472, "two CTAs per SM");
-constexpr int TMEM_COLS = 256;                           // S: [0,128)  O of key half 0: [128,192)  O of key half 1: [192,256)
+constexpr int ATOM64 = 128 * 64 * 2;                     // [128 rows x 64 columns] 16-bit, SWIZZLE_128B: 16 KB
+constexpr int ATOM32 = 128 * 32 * 2;                     // [128 rows x 32 columns] 16-bit, SWIZZLE_64B: 8 KB (head_dim 96 = 64 + 32)
+// Per head dim.  D = 64: one atom per tile, 2 CTAs per SM (112 KB smem, 256 TMEM columns each).  D = 96 (Phi-3): every Q/K/V tile is a
+// 64-column atom followed by a 32-column atom, the O accumulators take 2 x 96 columns (512-column allocation), one CTA per SM.
+template <int D>
+struct AC {
+  static_assert(D == 64 || D == 96, "head_dim 64 or 96");
+  static constexpr bool HAS32 = D == 96;
+  static constexpr int TILE_BYTES = ATOM64 + (HAS32 ? ATOM32 : 0);
+  static constexpr int SMEM_Q = 0;
+  static constexpr int SMEM_K = TILE_BYTES;              // 2 stages
+  static constexpr int SMEM_V = 3 * TILE_BYTES;          // 2 stages
+  static constexpr int SMEM_P = 5 * TILE_BYTES;          // [128 x 128] = 2 atoms of [128 x 64]
+  static constexpr int SMEM_BAR = SMEM_P + 2 * ATOM64;
+  static constexpr int SMEM_BYTES = SMEM_BAR + 640;
+  static constexpr int TMEM_COLS = HAS32 ? 512 : 256;    // S: [0,128)  O of key half 0: [128,128+D)  O of key half 1: [128+D,128+2D)
+  static constexpr int CTAS_PER_SM = HAS32 ? 1 : 2;
+};
+static_assert(2 * (AC<64>::SMEM_BYTES + 1024) <= 233472, "two CTAs per SM at head_dim 64");
+static_assert(AC<96>::SMEM_BYTES + 1024 <= 233472, "head_dim 96 fits one CTA");
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -150,17 +159,29 @@ __device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) {
 // MN-major SWIZZLE_128B operand descriptor for a [K rows x 64 (MN, contiguous)] tile with 128-byte rows:
 // SBO = 1024 B between 8-row K groups; LBO = byte distance between 64-element MN atoms (only one atom here)
 __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(TILE_BYTES >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(ATOM64 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
          ((uint64_t)2 << 61);
+}
+// the same two descriptors for the 32-column atom (64-byte rows, SWIZZLE_64B = layout type 4, 8-row groups 512 B apart)
+__device__ __forceinline__ uint64_t desc_kmajor_sw64(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
+}
+__device__ __forceinline__ uint64_t desc_mnmajor_sw64(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(ATOM32 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)4 << 61);
 }
 __device__ __forceinline__ uint32_t make_idesc(int kind, int m, int n, int b_mn_major) {
   return (1u << 4) | ((uint32_t)kind << 7) | ((uint32_t)kind << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) |
          ((uint32_t)(m >> 4) << 24);
 }
 
-__global__ void __launch_bounds__(NTHREADS, 2)
-attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, uint16_t* __restrict__ out, long long ldo, const int* __restrict__ cu, int H,
-               int causal, int kind, float scale_log2) {
+template <int D>
+__global__ void __launch_bounds__(NTHREADS, AC<D>::CTAS_PER_SM)
+attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_qkv32, uint16_t* __restrict__ out, long long ldo,
+               const int* __restrict__ cu, int H, int causal, int kind, float scale_log2) {
+  using C = AC<D>;
+  constexpr int TILE_BYTES = C::TILE_BYTES, SMEM_Q = C::SMEM_Q, SMEM_K = C::SMEM_K, SMEM_V = C::SMEM_V, SMEM_P = C::SMEM_P, SMEM_BAR = C::SMEM_BAR;
+  constexpr int TMEM_COLS = C::TMEM_COLS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t sbase = smem_u32(smem_raw);
   if (sbase & 1023u) __trap();  // SWIZZLE_128B tiles need 1024-byte alignment
@@ -205,12 +226,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, uint16_t* __restrict_
     if (lane == 0) {
       mbar_expect_tx(bar(0), TILE_BYTES);
       tma_load_2d(sbase + SMEM_Q, &tm_qkv, bar(0), h * D, b + q0);
+      if (C::HAS32) tma_load_2d(sbase + SMEM_Q + ATOM64, &tm_qkv32, bar(0), h * D + 64, b + q0);
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j & 1;
         mbar_wait(bar(3 + st), (((uint32_t)j >> 1) & 1u) ^ 1u);
         mbar_expect_tx(bar(1 + st), 2 * TILE_BYTES);
         tma_load_2d(sbase + SMEM_K + st * TILE_BYTES, &tm_qkv, bar(1 + st), (H + h) * D, b + j * BKV);
         tma_load_2d(sbase + SMEM_V + st * TILE_BYTES, &tm_qkv, bar(1 + st), (2 * H + h) * D, b + j * BKV);
+        if (C::HAS32) {
+          tma_load_2d(sbase + SMEM_K + st * TILE_BYTES + ATOM64, &tm_qkv32, bar(1 + st), (H + h) * D + 64, b + j * BKV);
+          tma_load_2d(sbase + SMEM_V + st * TILE_BYTES + ATOM64, &tm_qkv32, bar(1 + st), (2 * H + h) * D + 64, b + j * BKV);
+        }
       }
     }
   } else if (warp == 1) {
@@ -220,15 +246,22 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, uint16_t* __restrict_
       const bool mst_on = blockIdx.x == 1 && blockIdx.y == 5 && blockIdx.z == 40;
 #endif
       const uint32_t idesc_s = make_idesc(kind, BQ, BKV, 0);
-      const uint32_t idesc_o = make_idesc(kind, BQ, D, 1);
+      const uint32_t idesc_o = make_idesc(kind, BQ, 64, 1);
+      const uint32_t idesc_o32 = make_idesc(kind, BQ, 32, 1);
       const uint64_t dq = desc_kmajor(sbase + SMEM_Q);
+      const uint64_t dq32 = desc_kmajor_sw64(sbase + SMEM_Q + ATOM64);
       auto issue_s = [&](int j) {
         const int st = j & 1;
         mbar_wait(bar(1 + st), ((uint32_t)j >> 1) & 1u);  // K_j, V_j landed
         tc_fence_after();
         const uint64_t dk = desc_kmajor(sbase + SMEM_K + st * TILE_BYTES);
 #pragma unroll
-        for (int k = 0; k < D / 16; ++k) umma_f16(tmem_s, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, k ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) umma_f16(tmem_s, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, k ? 1u : 0u);
+        if (C::HAS32) {  // head dims 64..95: the 32-column atom (two more K-steps)
+          const uint64_t dk32 = desc_kmajor_sw64(sbase + SMEM_K + st * TILE_BYTES + ATOM64);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) umma_f16(tmem_s, dq32 + (uint64_t)(2 * k), dk32 + (uint64_t)(2 * k), idesc_s, 1u);
+        }
         umma_commit(bar(5));
       };
       mbar_wait(bar(0), 0);
@@ -247,13 +280,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, uint16_t* __restrict_
         tc_fence_after();
         const uint64_t dp = desc_kmajor(sbase + SMEM_P);
         const uint64_t dv = desc_mnmajor(sbase + SMEM_V + st * TILE_BYTES);
+        const uint64_t dv32 = desc_mnmajor_sw64(sbase + SMEM_V + st * TILE_BYTES + ATOM64);
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k) {
           // A = P: 16 keys = 32 B inside a 64-key atom (+2), next atom +16 KB; B = V: 16 key rows = 2048 B (+128).
           // O accumulates in TMEM over all key tiles (the tensor pipe executes the products in issue order).
-          const uint64_t a = dp + (uint64_t)((k & 3) * 2 + (k >> 2) * (TILE_BYTES >> 4));
+          const uint64_t a = dp + (uint64_t)((k & 3) * 2 + (k >> 2) * (ATOM64 >> 4));
           // keys 0..63 of the tile (k < 4) accumulate into O half 0, keys 64..127 into O half 1 (independent softmax bases)
           umma_f16(tmem_o + (uint32_t)((k >> 2) * D), a, dv + (uint64_t)(k * 128), idesc_o, (j | (k & 3)) ? 1u : 0u);
+          // channels 64..95: 16 key rows of the 32-column atom = 1024 B (+64)
+          if (C::HAS32) umma_f16(tmem_o + (uint32_t)((k >> 2) * D + 64), a, dv32 + (uint64_t)(k * 64), idesc_o32, (j | (k & 3)) ? 1u : 0u);
         }
         umma_commit(bar(3 + st));  // K_j / V_j stage free
         umma_commit(bar(8));       // O += P_j V_j done: P buffer free, O readable
@@ -272,7 +308,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, uint16_t* __restrict_
     const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
     constexpr int DH = D / 2;
     float m = -INFINITY, l = 0.f;
-    const uint32_t p_row = sbase + SMEM_P + (uint32_t)hf * (uint32_t)TILE_BYTES + (uint32_t)r * 128u;  // this half's 64-key atom
+    const uint32_t p_row = sbase + SMEM_P + (uint32_t)hf * (uint32_t)ATOM64 + (uint32_t)r * 128u;  // this half's 64-key atom
     const uint32_t sw = (uint32_t)(r & 7);
     // (base, sum) of the two key halves are exchanged (fp32) through the P buffer once the last P.V product has completed
     const uint32_t xsum_mine = sbase + SMEM_P + (uint32_t)(hf * 128 + r) * 8u;
@@ -422,11 +458,27 @@ extern "C" int d3d_debug_attn_stamps(long long* host_out) {
 }
 #endif
 
+namespace {
+template <int D>
+int launch_attn_tc(const CUtensorMap& tm, const CUtensorMap& tm32, void* out, int64_t ldo, const int* cu_seqlens, int n_seq, int max_len, int H,
+                   int causal, int kind, float scale, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    D3D_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, AC<D>::SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid(d3d_cdiv(max_len, BQ), H, n_seq);
+  attn_tc_kernel<D><<<grid, NTHREADS, AC<D>::SMEM_BYTES, st>>>(tm, tm32, (uint16_t*)out, ldo, cu_seqlens, H, causal, kind, scale * 1.4426950408889634f);
+  D3D_CHECK_LAUNCH();
+  return 0;
+}
+}  // namespace
+
 extern "C" int d3d_attention_tc(const void* qkv, int64_t ld, int64_t n_rows, void* out, int64_t ldo, const int* cu_seqlens, int n_seq,
                                 int max_len, int H, int Dh, int causal, int kind, float scale, void* stream) {
   if (n_seq == 0 || max_len == 0) return 0;
   D3D_REQUIRE(qkv && out && cu_seqlens, "args");
-  D3D_REQUIRE(Dh == D, "tcgen05 attention is built for head_dim 64");
+  D3D_REQUIRE(Dh == 64 || Dh == 96, "tcgen05 attention is built for head_dim 64 and 96");
   D3D_REQUIRE(ld % 8 == 0 && ldo % 8 == 0 && ((uintptr_t)qkv % 16) == 0 && ((uintptr_t)out % 16) == 0, "16-byte aligned rows");
   D3D_REQUIRE(n_seq <= 65535 && H <= 65535, "grid limits");
   static EncodeTiledFn fn = nullptr;
@@ -439,25 +491,23 @@ extern "C" int d3d_attention_tc(const void* qkv, int64_t ld, int64_t n_rows, voi
     }
     fn = (EncodeTiledFn)p;
   }
-  CUtensorMap tm;
-  cuuint64_t dims[2] = {(cuuint64_t)(3 * H * D), (cuuint64_t)n_rows};
+  CUtensorMap tm, tm32;
+  cuuint64_t dims[2] = {(cuuint64_t)(3 * H * Dh), (cuuint64_t)n_rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {64, 128};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(&tm, kind == D3D_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)qkv, dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUtensorMapDataType dt = kind == D3D_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  cuuint32_t box[2] = {64, 128};
+  CUresult r = fn(&tm, dt, 2, (void*)qkv, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_SUCCESS) {  // the 32-column atom of head_dim 96 (unused at 64, but the kernel signature is shared)
+    cuuint32_t box32[2] = {32, 128};
+    r = fn(&tm32, dt, 2, (void*)qkv, dims, strides, box32, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
   if (r != CUDA_SUCCESS) {
     d3d_set_error("cuTensorMapEncodeTiled(qkv) failed (%d)", (int)r);
     return D3D_ECUDA;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    D3D_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
-  }
-  dim3 grid(d3d_cdiv(max_len, BQ), H, n_seq);
-  attn_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tm, (uint16_t*)out, ldo, cu_seqlens, H, causal, kind,
-                                                                      scale * 1.4426950408889634f);
-  D3D_CHECK_LAUNCH();
-  return 0;
+  if (Dh == 96) return launch_attn_tc<96>(tm, tm32, out, ldo, cu_seqlens, n_seq, max_len, H, causal, kind, scale, (cudaStream_t)stream);
+  return launch_attn_tc<64>(tm, tm32, out, ldo, cu_seqlens, n_seq, max_len, H, causal, kind, scale, (cudaStream_t)stream);
 }

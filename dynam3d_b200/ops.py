@@ -343,13 +343,13 @@ def attention_simt(qkv, out, cu_seqlens, n_seq, max_len, H, Dh, causal=False, sc
 
 
 def attention(qkv, out, cu_seqlens, n_seq, max_len, H, Dh, causal=False, uniform_len=None, impl="auto"):
-    """Self-attention over packed sequences.  `impl`: 'tc' (tcgen05, head_dim 64), 'mma' (legacy tensor cores), 'simt' (fp32
-    CUDA cores) or 'auto' (tc for long head_dim-64 sequences, mma otherwise, simt for very short ones)."""
+    """Self-attention over packed sequences.  `impl`: 'tc' (tcgen05, head_dim 64 / 96), 'mma' (legacy tensor cores), 'simt' (fp32
+    CUDA cores) or 'auto' (tc for long head_dim-64 / 96 sequences, mma otherwise, simt for very short ones)."""
     scale = 1.0 / math.sqrt(Dh)
     # algorithmic FLOPs of the launch (QK^T + PV), assuming equal-length sequences (exact for the ViT, ~2 % high for the packed LM batch)
     work = 4.0 * (qkv.shape[0] ** 2 / max(n_seq, 1)) * Dh * H * (0.5 if causal else 1.0)
     with _Rec("attention", "tensor", work):
-        if impl == "tc" or (impl == "auto" and Dh == 64 and max_len >= 256):
+        if impl == "tc" or (impl == "auto" and Dh in (64, 96) and max_len >= 256):
             L.check(L.lib().d3d_attention_tc(L.ptr(qkv), qkv.stride(0), qkv.shape[0], L.ptr(out), out.stride(0), L.ptr(cu_seqlens), n_seq, max_len, H, Dh,
                                              int(bool(causal)), L.kind_of(qkv.dtype), scale, L.stream_ptr()))
         elif impl == "mma" or (impl == "auto" and Dh in (64, 96) and max_len >= 64):

@@ -66,11 +66,13 @@ def test_rope_matches_hf_formula(dtype):
     ([700, 130, 128, 5], 3, 64, True, torch.float16),
     ([577] * 6, 16, 64, False, torch.bfloat16),
     ([128], 2, 96, True, torch.float16),
+    ([735, 745, 300, 129], 8, 96, True, torch.float16),   # Phi-3 prefill shape (head_dim 96, causal, ragged)
+    ([200, 65], 2, 96, False, torch.bfloat16),
 ])
 def test_attention_matches_torch(lens, H, Dh, causal, dtype, impl):
     from dynam3d_b200 import ops
-    if impl == "tc" and Dh != 64:
-        pytest.skip("tcgen05 attention is built for head_dim 64")
+    if impl == "tc" and Dh not in (64, 96):
+        pytest.skip("tcgen05 attention is built for head_dim 64 and 96")
     T = sum(lens)
     qkv = (torch.randn(T, 3 * H * Dh, device="cuda") * 0.7).to(dtype)
     out = torch.zeros(T, H * Dh, device="cuda", dtype=dtype)

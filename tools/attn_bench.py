@@ -15,7 +15,7 @@ for name, lens, H, Dh, causal, dt in CASES:
     cu = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), device="cuda", dtype=torch.int32)
     flops = sum(4.0 * n * n * Dh * H * (0.5 if causal else 1.0) for n in lens)
     for impl in ("tc", "mma", "simt"):
-        if impl == "tc" and Dh != 64:
+        if impl == "tc" and Dh not in (64, 96):
             continue
         if impl == "simt" and T > 20000:
             continue
