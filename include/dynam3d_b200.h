@@ -243,8 +243,9 @@ int d3d_attention_simt(const void* qkv, int64_t ld, void* out, int64_t ldo, cons
 int d3d_attention_mma(const void* qkv, int64_t ld, void* out, int64_t ldo, const int* cu_seqlens, int n_seq, int max_len, int H,
                       int Dh, int causal, int kind, float scale, void* stream);
 
-/* tcgen05 flash attention (S = QK^T and O = PV on the 5th-gen tensor cores, accumulators in TMEM, Q/K/V tiles by TMA), head_dim 64,
- * same packed-QKV contract as d3d_attention_simt; n_rows = total rows T of the qkv matrix (for the TMA descriptor). */
+/* tcgen05 flash attention (S = QK^T and O = PV on the 5th-gen tensor cores, accumulators in TMEM, Q/K/V tiles by TMA), head_dim 64
+ * (CLIP ViT / LLaVA tower) or 96 (Phi-3: 64 + 32 column swizzle atoms), non-causal or causal; same packed-QKV contract as
+ * d3d_attention_simt; n_rows = total rows T of the qkv matrix (for the TMA descriptors). */
 int d3d_attention_tc(const void* qkv, int64_t ld, int64_t n_rows, void* out, int64_t ldo, const int* cu_seqlens, int n_seq,
                      int max_len, int H, int Dh, int causal, int kind, float scale, void* stream);
 
