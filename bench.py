@@ -192,6 +192,8 @@ def run_engine(args):
     from dynam3d_b200 import ops
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # one process per GPU shares the host: keep PyTorch's intra-op pool from oversubscribing the cores (the reference pins 4, run.py:90)
+    torch.set_num_threads(max(1, min(4, (os.cpu_count() or 4) // max(world, 1))))
     torch.cuda.set_device(local)
     L.require_device(local)
     if world > 1:
