@@ -4,13 +4,15 @@
 
     python bench.py --gpus N --steps K --warmup W            # this engine (one process per GPU under torchrun for N > 1)
     python bench.py --impl reference --steps K --warmup W    # the reference's CPU/PyTorch path (oracle port) on the host cores
+    python bench.py --precise                                # the <= 1e-3 logit-parity mode (split fp16x2 operands, fp32 activations)
+    python bench.py --generate                               # the whole POL:463 step: prefill + 20-token greedy decode
+    python bench.py --workload long_horizon                  # BASELINE configs[4]: 256 one-view steps, memory -> 4 k instance slots
 
 One "step" = one navigation step for every episode of the rank's shard (EPISODES_PER_GPU episodes, independent -> weak
 scaling); `value` = episodes * steps / time summed over ranks.  Prints ONE JSON line (see the task contract).
 """
 import argparse
 import json
-import math
 import os
 import subprocess
 import sys
@@ -33,6 +35,7 @@ N_SEG = 16
 INSTR_CHARS = 64
 WEIGHT_SEED = 7
 METRIC = "navigation steps/sec (12x224^2 RGB-D->3D tokens->Phi-3) @1/2/4/8 B200"
+GEMM_TRAFFIC = os.path.join(ROOT, "profiles", "gemm_traffic_r02.json")
 
 
 def peaks():
@@ -76,8 +79,8 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons)}
 
 
-def make_inputs(rank, n_steps, episodes):
-    eps = [synth.make_episode(1000 * 4 + rank * 100 + b, n_steps=n_steps, num_views=VIEWS, rgb_size=RGB, depth_size=DEPTH, n_seg=N_SEG,
+def make_inputs(rank, n_steps, episodes, views=VIEWS, rgb=RGB, depth=DEPTH, n_seg=N_SEG, seed0=4000):
+    eps = [synth.make_episode(seed0 + rank * 100 + b, n_steps=n_steps, num_views=views, rgb_size=rgb, depth_size=depth, n_seg=n_seg,
                               seg_kind="voronoi") for b in range(episodes)]
     steps = []
     for t in range(n_steps):
@@ -90,80 +93,63 @@ def make_inputs(rank, n_steps, episodes):
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm / cpu_baseline: the reference's own CPU PyTorch path (oracle port), bounded sample, extrapolated
+# reference arm: the reference's own CPU PyTorch path (oracle port, fp32) timed on WHOLE episode-steps of the bench workload
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_sample(threads, budget_s=20.0):
-    """Times the reference CPU path (fp32 PyTorch, oracle port) on a bounded sample of ONE episode-step of the bench workload and
-    extrapolates to the full step: ViT on 1 of 12 views, 2 of 32 LM layers, 3 of 23 LLaVA-tower layers, the 3D memory on 2 views.
-    Returns (steps_per_sec, detail dict)."""
-    from oracle import nn_ops as NN
-    from oracle.ff_oracle import FeatureFieldsOracle
-    from oracle import geometry as G
+def reference_oracle(threads):
+    """PolicyOracle (pure fp32 = the reference's arithmetic on CPU) at full depth with the bench's weights.  The weights are synthesised with
+    torch (on the GPU when one is there -- set-up only, bit-identical to the CPU generator) and live on the host."""
+    from oracle.policy_oracle import PolicyOracle
     torch.set_num_threads(threads)
-    ep = synth.make_episode(4242, n_steps=2, num_views=2, rgb_size=RGB, depth_size=DEPTH, n_seg=N_SEG, seg_kind="voronoi")
-    t0 = time.perf_counter()
-    clip_sd = synth.vit_state_dict(WEIGHT_SEED, layers=24)
-    x = NN.clip_preprocess(ep[0]["rgb"][:1], 336)
-    t = time.perf_counter()
-    with torch.no_grad():
-        _, grid = NN.vit_forward(x, clip_sd, 24, 16)
-    t_vit_view = time.perf_counter() - t
-    with torch.no_grad():
-        t = time.perf_counter()
-        NN.vit_forward(x, clip_sd, 24, 16, n_layers_run=3, return_hidden=True)
-        t_tower = (time.perf_counter() - t) / 3 * 23
-    del clip_sd
-    pol = synth.policy_state_dict(WEIGHT_SEED)
-    ff_sd = {k[len("feature_fields."):]: v for k, v in pol.items() if k.startswith("feature_fields.")}
-    ff = FeatureFieldsOracle(ff_sd, batch_size=1)
-    rng = np.random.default_rng(0)
-    t_ff = 0.0
-    with torch.no_grad():
-        for s in range(2):
-            d576 = G.depth_patch_grid(ep[s]["depth"], 1, 2, q1_fix=True)
-            full = G.preprocess_depth(ep[s]["depth"], (0.0, 10.0)).reshape(1, 2, DEPTH, DEPTH)
-            g = (rng.standard_normal((1, 2, 576, 768)) * 0.5).astype(np.float16)
-            t = time.perf_counter()
-            ff.delete_old_features_from_camera_frustum(full, [ep[s]["position"]], [ep[s]["heading"]], num_of_views=2)
-            ff.update_feature_fields(d576, g, ep[s]["segm"][None], [ep[s]["position"]], [ep[s]["heading"]], num_of_views=2)
-            ff.get_environment_features([ep[s]["position"]], [ep[s]["heading"]])
-            if s == 1:
-                t_ff = (time.perf_counter() - t) / 2 * VIEWS
-    S = 900
-    lm_sd = synth.lm_state_dict(WEIGHT_SEED, layers=2)
-    emb = synth.hash_uniform((S, 3072), 5, 1.0)
-    with torch.no_grad():
-        t = time.perf_counter()
-        NN.lm_prefill(emb, [S], lm_sd, 2, 32)
-        t_lm = (time.perf_counter() - t)
-    # the 2-layer call also includes the lm_head (1 row) -- negligible; per-layer time ~ t_lm / 2
-    t_lm_full = t_lm / 2 * 32
-    step = t_vit_view * VIEWS + t_tower + t_ff + t_lm_full
-    detail = {"vit_s_per_view": round(t_vit_view, 3), "llava_tower_s": round(t_tower, 3), "ff_s_per_step": round(t_ff, 3),
-              "lm_prefill_s_S900": round(t_lm_full, 3), "sample_wall_s": round(time.perf_counter() - t0, 1)}
-    return 1.0 / step, detail
+    gen = "cuda" if torch.cuda.is_available() else "cpu"
+    pol_sd = synth.policy_state_dict(WEIGHT_SEED, merge_bias=0.3)
+    clip_sd = {k: v.cpu() for k, v in synth.vit_state_dict(WEIGHT_SEED, layers=24, device=gen).items()}
+    llava_sd = {k: v.cpu() for k, v in synth.llava_state_dict(WEIGHT_SEED, clip_layers=24, lm_layers=32, device=gen, lm_round_to=torch.float16).items()}
+    if gen == "cuda":
+        torch.cuda.empty_cache()
+    return PolicyOracle(pol_sd, clip_sd, llava_sd, clip_layers=24, lm_layers=32, batch_size=1, rnd=None, q1_fix=True, q7_fix=True)
 
 
 def run_reference(args):
+    """Times real, whole episode-steps (a1-a16: CLIP ViT-L/14@336 on 12 views, the full 3D-memory update, LLaVA tower, 32-layer Phi-3 prefill
+    at the sequence length the memory produces) of ONE episode of the bench workload, consecutive steps of the same rollout.  A step takes
+    ~8-11 s on 16 cores, so the number of timed steps is bounded by a wall budget; `steps` in the line is what was actually timed."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    vals, detail = [], None
-    for i in range(args.warmup + args.steps):
-        v, detail = cpu_reference_sample(cores)
-        if i >= args.warmup:
-            vals.append(v)
-        if i == 0 and detail["sample_wall_s"] * (args.warmup + args.steps) > 240:  # keep the whole arm within a few minutes
-            vals = vals or [v]
+    t_setup = time.perf_counter()
+    orc = reference_oracle(cores)
+    tok = synth.ToyTokenizer()
+    from dynam3d_b200.prompt import build_prompt as build  # pure string formatting (POL:436); no engine code runs in this arm
+    n_total = max(1, min(args.warmup, 1)) + args.steps
+    ep = synth.make_episode(4000, n_steps=n_total, num_views=VIEWS, rgb_size=RGB, depth_size=DEPTH, n_seg=N_SEG, seg_kind="voronoi")
+    instr = [synth.make_instruction(0, INSTR_CHARS)]
+    setup_s = time.perf_counter() - t_setup
+    budget_s = args.reference_budget
+    times, lens = [], []
+    t_begin = time.perf_counter()
+    for t in range(n_total):
+        obs = {"rgb": ep[t]["rgb"], "depth": ep[t]["depth"], "patch_segm": ep[t]["segm"][None]}
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            orc.step_logits(obs, [ep[t]["position"]], [ep[t]["heading"]],
+                            lambda b, n_img: tok(build(n_img, instr[b], ["none\n"] * 4)), num_of_views=VIEWS)
+        dt = time.perf_counter() - t0
+        if t >= n_total - args.steps:
+            times.append(dt)
+            lens.append(orc.last_lens[0])
+        if time.perf_counter() - t_begin + dt > budget_s and len(times) >= 1:
             break
-    value = float(np.mean(vals))
-    sample = ("one episode-step extrapolated from: CLIP ViT-L/14@336 on 1 of 12 views, 3 of 23 LLaVA-tower layers, 3D memory on 2 of 12 views, "
-              "2 of 32 Phi-3 layers at S=900; fp32 PyTorch, all host threads")
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
+    value = len(times) / sum(times)
+    sample = (f"{len(times)} whole episode-steps of one bench episode (12 x {RGB}^2 views -> ViT-L/14@336 24L -> 3D memory update -> LLaVA tower 23L -> "
+              f"Phi-3 32L prefill at S={lens}), consecutive steps after {n_total - args.steps} warm-up step(s); fp32 PyTorch oracle port, {cores} host threads")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": args.gpus, "steps": len(times), "warmup": n_total - args.steps,
             "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{VIEWS}x{RGB}^2 RGB-D views/episode-step, ViT-L/14@336 + 3D token memory + Phi-3-mini prefill (reference CPU path)",
-                       "detail": detail},
+            "config": {"workload": f"full navigation step of ONE episode: {VIEWS} views of {RGB}^2 RGB + {DEPTH}^2 depth -> CLIP ViT-L/14@336 (24L) -> "
+                                   f"patch/instance/zone 3D token memory ({N_SEG} segments/view) -> LLaVA tower (23L, 1 view) + projector -> Phi-3-mini (32L) "
+                                   f"prefill -> next-action logits (reference CPU path; the engine arm steps {EPISODES_PER_GPU} such episodes per GPU)",
+                       "prefill_tokens": lens, "step_seconds": [round(x, 2) for x in times], "setup_s": round(setup_s, 1),
+                       "requested_steps": args.steps, "wall_budget_s": budget_s},
             "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -172,50 +158,130 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # this engine
 # ------------------------------------------------------------------------------------------------
-def build_engine(episodes, n_steps=16):
+def build_engine(episodes, n_steps=16, precise_parts=(), views=VIEWS):
     from dynam3d_b200.policy import Dynam3D_VLN
     net = Dynam3D_VLN(q1_fix=True, q7_fix=True)  # 12-view panorama: per-view depth / heading (the literal Q1/Q7 paths only make sense at V=1)
+    net.set_precise_parts(precise_parts)
     net.load_policy_state_dict(synth.policy_state_dict(WEIGHT_SEED, merge_bias=0.3))
-    net.rgb_encoder.max_images = episodes * VIEWS
-    net.rgb_encoder.load_openai_state_dict(synth.vit_state_dict(WEIGHT_SEED, layers=24, device="cuda"))
-    net.llava.load_state_dict(synth.llava_state_dict(WEIGHT_SEED, clip_layers=24, lm_layers=32, device="cuda", lm_round_to=torch.float16),
+    net.rgb_encoder.max_images = episodes * views
+    # the checkpoint tensors stay resident as module state (state_dict round trip, TR:75-84): hand them over in 16 bit
+    h = lambda sd: {k: (v.half() if v.dim() >= 2 else v) for k, v in sd.items()}
+    net.rgb_encoder.load_openai_state_dict(h(synth.vit_state_dict(WEIGHT_SEED, layers=24, device="cuda")))
+    net.llava.load_state_dict(h(synth.llava_state_dict(WEIGHT_SEED, clip_layers=24, lm_layers=32, device="cuda", lm_round_to=torch.float16)),
                               max_images=episodes, max_tokens=episodes * 1100)
+    net.llava.lm  # build the engine-layout weights now
+    net.rgb_encoder.engine
+    torch.cuda.empty_cache()
     net.feature_fields.reset(episodes)
-    net.feature_fields.reserve(patches=n_steps * VIEWS * 576, instances=4096)  # the rollout horizon is known: no pool growth inside the timed region
+    net.feature_fields.reserve(patches=n_steps * views * 576, instances=4096)  # the rollout horizon is known: commit the pools up front
     net.tokenize = synth.ToyTokenizer()
     return net
+
+
+def stage_table(prof_s, ff_prof):
+    peak_tf_, peak_hbm_, _ = peaks()
+    agg = {}
+    for name, bound, work, a, b in prof_s:
+        d = agg.setdefault(name, {"bound": bound, "work": 0.0, "ms": 0.0, "launches": 0})
+        d["work"] += work; d["ms"] += a.elapsed_time(b); d["launches"] += 1
+    if ff_prof is not None:
+        ms, work, n = ff_prof
+        for i, (name, bound) in enumerate((("ff.knn", "hbm"), ("ff.disc", "tensor"), ("ff.new_slots", "hbm"), ("ff.merge_pool", "tensor"),
+                                           ("ff.zone_pool", "tensor"), ("ff.result_copy", "hbm"))):
+            if n[i]:
+                agg[name] = {"bound": bound, "work": float(work[i]), "ms": float(ms[i]), "launches": int(n[i])}
+    stages = []
+    for name, d in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
+        if d["ms"] <= 0:
+            continue
+        if d["bound"] == "tensor":
+            ach, peak, unit = d["work"] / (d["ms"] * 1e-3) / 1e12, peak_tf_, "TFLOP/s"
+        else:
+            ach, peak, unit = d["work"] / (d["ms"] * 1e-3) / 1e9, peak_hbm_, "GB/s"
+        stages.append({"stage": name, "bound": d["bound"], "launches": d["launches"], "ms": round(d["ms"], 3), "achieved": round(ach, 1),
+                       "unit": unit, "frac": round(ach / peak, 4)})
+    return stages
+
+
+def profiled_step(fn):
+    """Runs fn() once with CUDA events around every C-ABI call (ops.STAGE_PROFILE) and inside the view runtime (d3d_ff_profile_*)."""
+    import ctypes
+    from dynam3d_b200 import _lib as L
+    from dynam3d_b200 import ops
+    ops.STAGE_PROFILE = []
+    L.lib().d3d_ff_profile_begin()
+    fn()
+    ms, work, n = (ctypes.c_float * 6)(), (ctypes.c_double * 6)(), (ctypes.c_int * 6)()
+    L.check(L.lib().d3d_ff_profile_end(ctypes.cast(ms, ctypes.c_void_p), ctypes.cast(work, ctypes.c_void_p), ctypes.cast(n, ctypes.c_void_p)))
+    torch.cuda.synchronize()
+    prof_s, ops.STAGE_PROFILE = ops.STAGE_PROFILE, None
+    return stage_table(prof_s, (list(ms), list(work), list(n)))
+
+
+def gemm_traffic():
+    """Per-launch DRAM bytes of the dominant kernel family from the committed ncu --set full capture (launch-weighted over the shapes of a step)."""
+    if not os.path.isfile(GEMM_TRAFFIC):
+        return None, "no ncu traffic file"
+    d = json.load(open(GEMM_TRAFFIC))
+    n = sum(s["launches_per_step"] for s in d["shapes"])
+    tr = sum(s["launches_per_step"] * s["dram_MB"] for s in d["shapes"]) / n * 1e6
+    al = sum(s["launches_per_step"] * s["algorithmic_MB"] for s in d["shapes"]) / n * 1e6
+    return tr, (f"launch-weighted mean over the {len(d['shapes'])} dominant GEMM shapes of a step ({d['source']}): {tr / 1e6:.0f} MB DRAM traffic vs "
+                f"{al / 1e6:.0f} MB algorithmic per launch = {tr / al:.2f}x")
 
 
 def run_engine(args):
     import torch.distributed as dist
     from dynam3d_b200 import _lib as L
     from dynam3d_b200 import ops
+    from dynam3d_b200.policy import Dynam3D_VLN
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    # one process per GPU shares the host: keep PyTorch's intra-op pool from oversubscribing the cores (the reference pins 4, run.py:90)
-    torch.set_num_threads(max(1, min(4, (os.cpu_count() or 4) // max(world, 1))))
+    # one process per GPU shares the host: keep PyTorch's intra-op pool from oversubscribing the cores (the reference pins 4, run.py:90),
+    # and give every rank its own slice of the cores so the view-loop planners do not migrate onto each other
+    ncpu = os.cpu_count() or 4
+    torch.set_num_threads(max(1, min(4, ncpu // max(world, 1))))
+    if world > 1 and hasattr(os, "sched_setaffinity"):
+        per = max(1, ncpu // world)
+        try:
+            os.sched_setaffinity(0, set(range(local * per, min(ncpu, (local + 1) * per))))
+        except OSError:
+            pass
     torch.cuda.set_device(local)
     L.require_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     E = args.episodes
     n_total = args.warmup + 2 * args.steps
-    net = build_engine(E, n_total)
+    parts = Dynam3D_VLN.PRECISE_PARTS if args.precise else tuple(p for p in (args.precise_parts or "").split(",") if p)
+    mode = "production" if not parts else ("precise" if set(parts) == set(Dynam3D_VLN.PRECISE_PARTS) else "precise:" + "+".join(parts))
+    net = build_engine(E, n_total, parts)
     instr = [synth.make_instruction(rank * 100 + b, INSTR_CHARS) for b in range(E)]
     steps = make_inputs(rank, n_total, E)
     dev = torch.device("cuda", local)
     # device-resident copies for the kernel-side number, pinned host copies for the end-to-end number
     dev_in = [{"rgb": torch.from_numpy(s["rgb"]).to(dev), "depth": torch.from_numpy(s["depth"]).to(dev), "patch_segm": s["segm"]} for s in steps]
     host_in = [{"rgb": torch.from_numpy(s["rgb"]).pin_memory(), "depth": torch.from_numpy(s["depth"]).pin_memory(), "patch_segm": s["segm"]} for s in steps]
-    from dynam3d_b200.sharding import allgather_last_logits
+    pending = []   # in-flight all-gathers: episodes are independent (BASE:770), so the gather of step i overlaps step i+1
 
     def one_step(i, inputs, gather=True):
-        lg = net.forward_logits(inputs[i], instr, steps[i]["pos"], steps[i]["head"], num_of_views=VIEWS)
+        if args.generate:
+            lg, ids = net.generate_ids(inputs[i], instr, steps[i]["pos"], steps[i]["head"], num_of_views=VIEWS)
+        else:
+            lg = net.forward_logits(inputs[i], instr, steps[i]["pos"], steps[i]["head"], num_of_views=VIEWS)
         if world > 1 and gather:
-            lg = allgather_last_logits(lg)
+            out = torch.empty((world * E, lg.shape[1]), device=dev, dtype=lg.dtype)
+            pending.append((dist.all_gather_into_tensor(out, lg, async_op=True), out, lg))
+            while len(pending) > 2:  # at most two gathers in flight: bounds memory, never stalls the step that just finished
+                pending.pop(0)[0].wait()
         return lg
 
+    def drain():
+        while pending:
+            pending.pop(0)[0].wait()
+
     def barrier():
+        drain()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -226,14 +292,15 @@ def run_engine(args):
     sampler = ClockSampler(local)
     sampler.start()
     ops.GEMM_PROFILE = []
-    calls0 = L.lib().d3d_launch_count()
     barrier()
+    calls0 = L.lib().d3d_launch_count()
     if args.profile_range:
         torch.cuda.profiler.start()  # ncu --profile-from-start off: only the timed steps are captured
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.warmup, args.warmup + args.steps):
         one_step(i, dev_in)
+    drain()
     e1.record()
     barrier()
     if args.profile_range:
@@ -244,38 +311,23 @@ def run_engine(args):
     gemm_flops = sum(p[0] for p in prof)
     gemm_ms = sum(p[1].elapsed_time(p[2]) for p in prof)
     seq_lens = list(net.last_seq_lens)
-    # ---- timed region 2: end to end through the public API with HOST buffers (H2D of the step's inputs + D2H of the logits) ----
+    # ---- timed region 2: end to end through the public API with HOST buffers (H2D of the step's inputs + D2H of the rank's logits) ----
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    out_host = torch.empty((E * world if world > 1 else E, 32064), dtype=torch.float32).pin_memory()
+    out_host = torch.empty((E, 32064), dtype=torch.float32).pin_memory()
     e2.record()
     for i in range(args.warmup + args.steps, n_total):
         lg = one_step(i, host_in)
-        out_host.copy_(lg, non_blocking=True)
+        out_host.copy_(lg, non_blocking=True)  # the rank's own rows: E x 32064 fp32
+    drain()
     e3.record()
     barrier()
     ms_e2e = e2.elapsed_time(e3)
+    finite = bool(torch.isfinite(out_host).all())
     # ---- per-stage rooflines: ONE extra step (outside both timed regions) with CUDA events around every C-ABI call ----
     stages = []
     if rank == 0:
-        ops.STAGE_PROFILE = []
-        one_step(args.warmup, dev_in, gather=False)  # rank 0 only: no collective in this extra step
-        torch.cuda.synchronize()
-        prof_s, ops.STAGE_PROFILE = ops.STAGE_PROFILE, None
-        peak_tf_, peak_hbm_, _ = peaks()
-        agg = {}
-        for name, bound, work, a, b in prof_s:
-            d = agg.setdefault(name, {"bound": bound, "work": 0.0, "ms": 0.0, "launches": 0})
-            d["work"] += work; d["ms"] += a.elapsed_time(b); d["launches"] += 1
-        for name, d in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
-            if d["ms"] <= 0:
-                continue
-            if d["bound"] == "tensor":
-                ach, peak, unit = d["work"] / (d["ms"] * 1e-3) / 1e12, peak_tf_, "TFLOP/s"
-            else:
-                ach, peak, unit = d["work"] / (d["ms"] * 1e-3) / 1e9, peak_hbm_, "GB/s"
-            stages.append({"stage": name, "bound": d["bound"], "launches": d["launches"], "ms": round(d["ms"], 3), "achieved": round(ach, 1),
-                           "unit": unit, "frac": round(ach / peak, 3)})
+        stages = profiled_step(lambda: one_step(args.warmup, dev_in, gather=False))  # rank 0 only: no collective in this extra step
     sampler.stop_flag = True
     sampler.join(timeout=2)
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
@@ -288,32 +340,126 @@ def run_engine(args):
         e2e = world * E * args.steps / (ms_e2e / 1000.0)
         achieved = gemm_flops / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else 0.0
         h2d = int(steps[0]["rgb"].nbytes + steps[0]["depth"].nbytes)
+        traffic, traffic_note = gemm_traffic()
         line = {
             "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16",
             "data": "synthetic",
             "config": {"workload": f"full navigation step: {E} episodes/GPU x {VIEWS} views of {RGB}^2 RGB + {DEPTH}^2 depth -> CLIP ViT-L/14@336 (24L) -> "
                                    f"patch/instance/zone 3D token memory ({N_SEG} segments/view) -> LLaVA tower (23L, 1 view) + projector -> "
-                                   f"Phi-3-mini (32L) prefill, S~{int(np.mean(seq_lens))} -> next-action logits",
-                       "episodes_per_gpu": E, "views": VIEWS, "prefill_tokens": seq_lens, "weights": "random init at true sizes (no checkpoints offline)",
+                                   f"Phi-3-mini (32L) prefill, S~{int(np.mean(seq_lens))} -> next-action logits"
+                                   + (" -> greedy decode (<= 20 tokens, KV cache; POL:463)" if args.generate else ""),
+                       "mode": mode, "episodes_per_gpu": E, "views": VIEWS, "prefill_tokens": seq_lens, "weights": "random init at true sizes (no checkpoints offline)",
                        "l2": "weights 8.9 GB >> 126 MB L2 are streamed every step (no explicit flush needed)",
-                       "precision": "fp16 GEMM operands (reference: fp16 autocast, TR:385), fp32 accumulate / residual / norm statistics"},
-            "e2e": {"value": e2e, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(E * 32064 * 4)},
+                       "precision": ("fp16 GEMM operands (reference: fp16 autocast, TR:385), fp32 accumulate / residual / norm statistics" if not parts else
+                                     "split fp16x2 tensor-core operands (A_hi W + A_lo W), fp32 activations / attention in: " + "+".join(parts))},
+            "e2e": {"value": e2e, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(E * 32064 * 4), "logits_finite": finite},
             "gpu_launches": int(launches),
             "stages": stages,  # one extra profiled step: per-stage algorithmic FLOPs or bytes / CUDA-event time vs the measured peaks
             "clocks": sampler.summary(),
             "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_pair_kernel<256> / gemm_tcgen05_kernel<128|256> (all tcgen05 GEMM launches of the timed region)", "achieved": achieved,
-                         "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None, "traffic_note": "per-launch DRAM bytes of the four dominant shapes (ncu --set full) = 1.0-1.4x their algorithmic bytes: profiles/ncu_full_gemm_r01_final_summary.json", "peak_source": which,
+                         "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic, "traffic_note": traffic_note, "peak_source": which,
                          "gemm_share_of_step": gemm_ms / ms, "gemm_launches": len(prof)},
         }
-        if world == 1 and not args.no_cpu_baseline:
-            v, detail = cpu_reference_sample(os.cpu_count() or 1)
-            line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": os.cpu_count() or 1, "kind": "port",
-                                    "sample": "one episode-step extrapolated from: ViT on 1 of 12 views, 3 of 23 tower layers, 3D memory on 2 of 12 views, "
-                                              "2 of 32 Phi-3 layers at S=900 (fp32 PyTorch oracle port, all host threads)", "detail": detail}
+        if world == 1 and not args.no_parity:
+            # ONE episode of this exact workload at full depth vs the CPU oracle (checker only, outside the timed regions): production is compared
+            # with the oracle that rounds at the same points AND with the pure-fp32 oracle; a precise mode with the pure-fp32 oracle
+            del net, dev_in, host_in
+            torch.cuda.empty_cache()
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            from full_depth import full_depth_parity
+            r = full_depth_parity(steps=1, modes=(mode,), log=lambda *a: None)
+            m = r[mode]
+            line["parity"] = {"mode": mode, "max_abs_vs_matched": m["max_abs_vs_matched"], "max_abs_vs_fp32": m["max_abs_vs_fp32"],
+                              "argmax_equal": m["argmax_equal"], "discrete_state_equal": m["discrete_state_equal"], "config": r["config"],
+                              "seq_lens": r["seq_lens"], "logit_absmax": r["logit_absmax"], "tolerance_north_star": 1e-3}
+            if not args.no_cpu_baseline:
+                sec = r["oracle_s_per_step"]["fp32"][0]
+                line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "steps/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                        "sample": f"1 whole episode-step (step 0 of a bench episode: 12 views, 24L ViT, 23L tower, 32L Phi-3 at S={r['seq_lens'][0]}) "
+                                                  f"through the fp32 PyTorch oracle port on all host threads: {sec} s"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE configs[4]: long horizon -- 256 one-view steps, the token memory growing to ~4 k instance slots / 147 k patches
+# ------------------------------------------------------------------------------------------------
+def run_long_horizon(args):
+    """The memory path only (frustum cull over all stored patches, K-NN over all instance slots, pooling / merge re-encode, zones, export) on
+    hash-generated CLIP grid features: per-step device time as the memory grows, and the growing stages as roofline fractions."""
+    import ctypes
+    from dynam3d_b200 import _lib as L
+    from dynam3d_b200 import ops
+    from dynam3d_b200.feature_fields import Feature_Fields
+    torch.cuda.set_device(0)
+    L.require_device(0)
+    E, T = args.episodes, args.horizon
+    pol = synth.policy_state_dict(WEIGHT_SEED, merge_bias=args.merge_bias)
+    ff = Feature_Fields(batch_size=E, device="cuda", q7_fix=True)
+    ff.load_state_dict({k[len("feature_fields."):]: v for k, v in pol.items() if k.startswith("feature_fields.")})
+    ff.reset(E)  # no reserve(): the pools grow inside the rollout (VMM chunks, no copy / no stall)
+    steps = make_inputs(0, T, E, views=1, rgb=8, depth=256, n_seg=17, seed0=5000)
+    grids = [synth.hash_uniform((E, 1, 576, 768), 5000 * 1000 + t % 8, 0.9, device="cuda").half() for t in range(8)]
+    depth_dev = [torch.from_numpy(s["depth"]).cuda().reshape(E, 256, 256).contiguous() for s in steps]
+    checkpoints = sorted({1, 2, 4, 8, 16, 32, 64, 128, 192, T})
+    curve, ev = [], []
+    sampler = ClockSampler(0)
+    sampler.start()
+    torch.cuda.synchronize()
+    calls0 = L.lib().d3d_launch_count()
+    t_all0 = torch.cuda.Event(enable_timing=True); t_all1 = torch.cuda.Event(enable_timing=True)
+    t_all0.record()
+    stage_rows = {}
+    for t in range(T):
+        s = steps[t]
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        prof = (t + 1) in (128, T)
+        if prof:
+            torch.cuda.synchronize()
+            ops.STAGE_PROFILE = []
+            L.lib().d3d_ff_profile_begin()
+        a.record()
+        d576 = ops.depth_patch_grid(depth_dev[t], E, 1, 24, 24, literal_q1=False)
+        full = ops.depth_preprocess(depth_dev[t], 0.0, 10.0).view(E, 1, 256, 256)
+        ff.delete_old_features_from_camera_frustum(full, s["pos"], s["head"], num_of_views=1)
+        ff.update_feature_fields(d576.view(E, 1, 576), grids[t % 8], batch_position=s["pos"], batch_heading=s["head"], num_of_views=1,
+                                 batch_patch_segm=s["segm"])
+        env = ff.get_environment_features(s["pos"], s["head"])
+        b.record()
+        ev.append((a, b))
+        if prof:
+            ms_, work_, n_ = (ctypes.c_float * 6)(), (ctypes.c_double * 6)(), (ctypes.c_int * 6)()
+            L.check(L.lib().d3d_ff_profile_end(ctypes.cast(ms_, ctypes.c_void_p), ctypes.cast(work_, ctypes.c_void_p), ctypes.cast(n_, ctypes.c_void_p)))
+            ps, ops.STAGE_PROFILE = ops.STAGE_PROFILE, None
+            stage_rows[t + 1] = stage_table(ps, (list(ms_), list(work_), list(n_)))
+        if (t + 1) in checkpoints:
+            curve.append({"step": t + 1, "n_patches": int(ff.eps[0].n_patch), "n_inst_slots": int(ff.eps[0].n_inst), "n_zone_slots": int(ff.eps[0].n_zone),
+                          "env_instance_tokens": int(env["batch_instance_fts"][0].shape[0]), "i": t})
+    t_all1.record()
+    torch.cuda.synchronize()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    launches = L.lib().d3d_launch_count() - calls0
+    per_step = [a.elapsed_time(b) for a, b in ev]
+    for c in curve:
+        i = c.pop("i")
+        lo = max(0, i - 3)
+        c["ms_per_step"] = round(float(np.mean(per_step[lo:i + 1])), 3)
+    total_ms = t_all0.elapsed_time(t_all1)
+    peak_tf, peak_hbm, which = peaks()
+    cull = next((r for r in stage_rows.get(T, []) if r["stage"] == "ff.frustum_cull"), None)
+    line = {"metric": "memory-update steps/sec, long horizon (256 one-view steps, token memory -> 4k instance slots) @1 B200", "value": E * T / (total_ms / 1e3),
+            "unit": "steps/s", "n_gpus": 1, "steps": T, "warmup": 0, "ms_per_step": total_ms / T, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp16", "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[4]: {E} episodes x {T} one-view steps, 17 segments/view, merge bias {args.merge_bias}: frustum cull over all stored "
+                                   "patches + K-NN over all instance slots + patch->instance->zone pooling + export (memory path only, CLIP grid features synthetic)",
+                       "episodes_per_gpu": E, "pools": "VMM-backed, no reserve(): grown inside the rollout"},
+            "curve": curve, "stages_at_step": stage_rows, "gpu_launches": int(launches), "clocks": sampler.summary(),
+            "roofline": ({"bound": "hbm", "kernel": "frustum_cull_kernel (all stored patches of an episode, step %d)" % T, "achieved": cull["achieved"], "peak": peak_hbm,
+                          "unit": "GB/s", "frac": cull["frac"], "traffic": None, "peak_source": which} if cull else None)}
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -323,11 +469,21 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--episodes", type=int, default=EPISODES_PER_GPU)
+    ap.add_argument("--workload", default="step", choices=["step", "long_horizon"])
+    ap.add_argument("--precise", action="store_true", help="every stage in the split-operand fp32-activation mode (<= 1e-3 vs the fp32 oracle)")
+    ap.add_argument("--precise-parts", default=None, help="comma list out of vit,tower,ff,proj,lm (error-vs-cost curve)")
+    ap.add_argument("--generate", action="store_true", help="time the whole POL:463 step: prefill + greedy decode of 20 tokens")
+    ap.add_argument("--horizon", type=int, default=256)
+    ap.add_argument("--merge-bias", type=float, default=-10.0, help="long_horizon: discriminator bias (-10 = merges off -> 4k instance slots)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the full-depth parity check against the CPU oracle after the timed regions")
+    ap.add_argument("--reference-budget", type=float, default=170.0, help="--impl reference: wall budget in seconds for the timed whole steps")
     ap.add_argument("--profile-range", action="store_true", help="cudaProfilerStart/Stop around the timed region (for ncu)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "long_horizon":
+        run_long_horizon(args)
     else:
         run_engine(args)
 

@@ -126,7 +126,9 @@ SIGNATURES = {
     "d3d_ffh_begin_view": [_P] * 3 + [_I] + [_P] * 11,
     "d3d_ffh_begin_step": [_P] * 3 + [_I, _I] + [_P] * 9, "d3d_ffh_begin_view_refs": [_P, _I, _P],
     "d3d_ff_view_pre": [_P, _I, _P, _P, _P, _P, _P, _P, _P], "d3d_ff_view_post": [_P, _P, _P, _P, _P, _P], "d3d_ff_run_deferred": [_P, _P, _P],
-    "d3d_event_create": [], "d3d_event_destroy": [_P],
+    "d3d_vmm_create": [ctypes.c_size_t, ctypes.c_size_t, _I], "d3d_vmm_ensure": [_P, ctypes.c_size_t, _P], "d3d_vmm_base": [_P],
+    "d3d_vmm_mapped": [_P], "d3d_vmm_reserved": [_P], "d3d_vmm_destroy": [_P],
+    "d3d_event_create": [], "d3d_event_destroy": [_P], "d3d_ff_profile_begin": [], "d3d_ff_profile_end": [_P, _P, _P],
     "d3d_ffh_finish_view": [_P, _P, _P, _P], "d3d_ffh_fetch_view": [_P] * 17, "d3d_ffh_zone_key_array": [_P, _I, _P],
     "d3d_ffh_get_map": [_P, _I, _I, _P, _P, _P, _P], "d3d_ffh_get_p2i": [_P, _I, _P], "d3d_ffh_live_ids": [_P, _I, _I, _P, _P], "d3d_ffh_get_patch_pos": [_P, _I, _P],
     "d3d_ffh_get_zone_keys": [_P, _I, _P, _P, _P], "d3d_ffh_get_last": [_P, _I, _P, _P, _P, _P],
@@ -151,7 +153,9 @@ def _declare(lib_):
             raise D3DLibraryError(f"{LIB_PATH} does not export {name}: stale build?")
         fn.argtypes = argtypes
         fn.restype = {"d3d_pool_workspace_bytes": ctypes.c_size_t, "d3d_ffh_create": ctypes.c_void_p, "d3d_ffh_destroy": None,
-                      "d3d_event_create": ctypes.c_void_p, "d3d_event_destroy": None, "d3d_launch_count": ctypes.c_longlong}.get(name, ctypes.c_int)
+                      "d3d_event_create": ctypes.c_void_p, "d3d_event_destroy": None, "d3d_launch_count": ctypes.c_longlong,
+                      "d3d_vmm_create": ctypes.c_void_p, "d3d_vmm_base": ctypes.c_uint64, "d3d_vmm_mapped": ctypes.c_size_t,
+                      "d3d_vmm_reserved": ctypes.c_size_t}.get(name, ctypes.c_int)
 
 
 def lib():

@@ -44,7 +44,7 @@ class ViTWeights:
         w.pos = cls._f32(g("positional_embedding"), device)
         w.tokens = w.pos.shape[0]
         w.ln_pre = (cls._f32(g("ln_pre.weight"), device), cls._f32(g("ln_pre.bias"), device))
-        n_layers = len({k_.split(".")[2] for k_ in sd if k_.startswith(prefix + "transformer.resblocks.")})
+        n_layers = len({k_[len(prefix):].split(".")[2] for k_ in sd if k_.startswith(prefix + "transformer.resblocks.")})
         for l in range(n_layers):
             p = f"transformer.resblocks.{l}."
             w.layers.append({

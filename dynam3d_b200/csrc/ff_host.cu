@@ -285,15 +285,26 @@ extern "C" void* d3d_ffh_create(int batch_size, int num_proposal, float zone_len
   return h;
 }
 extern "C" void d3d_ffh_destroy(void* h) { delete reinterpret_cast<FFH*>(h); }
+// a step that raised between view_post and the next run_deferred leaves a pending zone pass / plan behind: a new rollout must not see them
+static void clear_runtime(FFH& H) {
+  H.zone.pending = false;
+  H.plan.clear();
+  H.splits.clear(); H.seq_start.clear();
+  H.step_splits.clear(); H.step_seq_start.clear();
+  H.stage_cursor = 0;
+  H.res_base = 0;
+}
 extern "C" int d3d_ffh_reset(void* h, int batch_size) {
   HH(h).eps.clear();
   HH(h).eps.resize((size_t)batch_size);
+  clear_runtime(HH(h));
   return 0;
 }
 extern "C" int d3d_ffh_pop(void* h, int index) {
   FFH& H = HH(h);
   D3D_REQUIRE(index >= 0 && index < (int)H.eps.size(), "episode index");
   H.eps.erase(H.eps.begin() + index);
+  clear_runtime(H);
   return 0;
 }
 
@@ -499,7 +510,7 @@ extern "C" int d3d_ffh_begin_view_refs(void* h, int ix, int* n_ref) {
 }
 
 // Second half: res [n_seq, 12] fp32 rows = [centre(3) | d2(2) | idx(2, int32 bits) | logits(2x2) | pad] copied back from the device.
-// sizes[10] = n_new, n_merged, merged members, n_zones, zone members, max merged len, max zone len, -, -, -
+// sizes[10] = n_new, n_merged, merged members, n_zones, zone members, max merged len, max zone len, upload KiB d3d_ff_view_post needs, -, -
 // after[B*3] = (n_inst, n_zone, needs_key_array) per episode.
 extern "C" int d3d_ffh_finish_view(void* h, const float* res, int* sizes, int64_t* after) {
   FFH& H = HH(h);
@@ -531,6 +542,18 @@ extern "C" int d3d_ffh_finish_view(void* h, const float* res, int* sizes, int64_
   }
   for (size_t i = 0; i < pl.zn_owner.size(); ++i)
     if (pl.zn_keys[i]) after[pl.zn_owner[i] * 3 + 2] = 1;
+  // bytes d3d_ff_view_post stages for this plan (every array rounded up to 16 B): the caller grows the upload ring BEFORE the device writes
+  // are issued, so an oversized plan cannot fail after the host state was already mutated
+  size_t up = 0;
+  auto add = [&up](size_t bytes) { up += (bytes + 15) / 16 * 16; };
+  const size_t n_new = pl.new_src.size(), n_mg = pl.mg_owner.size(), n_zn = pl.zn_owner.size();
+  add(n_new * 4); add(n_new * 8); add(n_new * 8);
+  const size_t t_mg = pl.mg_members.size() + n_mg, t_zn = pl.zn_members.size() + n_zn;
+  add(t_mg * 4); add(t_mg * 4); add((n_mg + 1) * 4); add(n_mg * 32); add(n_mg * 12); add(n_mg * 8); add(n_mg * 8);
+  add(t_zn * 4); add(t_zn * 4); add((n_zn + 1) * 4); add(n_zn * 32); add(n_zn * 12); add(n_zn * 8); add(n_zn * 8);
+  for (int b = 0; b < B; ++b)
+    if (after[b * 3 + 2]) add((size_t)std::max<i64>(H.eps[(size_t)b].n_inst, 1) * 12);
+  sizes[7] = (int)std::min<size_t>((up + 1023) / 1024, (size_t)INT32_MAX);
   return 0;
 }
 
@@ -661,6 +684,25 @@ __global__ void pack_view_result_kernel(const float* __restrict__ centre, const 
   r[11] = 0.f;
 }
 
+// ---- per-stage device timing of the view runtime (bench.py `stages`: ff.knn / ff.disc / ff.new_slots / ff.merge_pool / ff.zone_pool /
+// ff.result_copy): CUDA events on the launch stream around each phase, only while d3d_ff_profile_begin() ... _end() is active ----
+enum { PF_KNN = 0, PF_DISC, PF_NEW, PF_MERGE, PF_ZONE, PF_RESULT, PF_N };
+struct ProfRec { int stage; cudaEvent_t e0, e1; double work; };
+struct Prof { bool on = false; std::vector<ProfRec> recs; } g_prof;
+struct ProfScope {
+  bool on; int stage; double work; cudaStream_t st; cudaEvent_t e0 = nullptr;
+  ProfScope(int stage_, double work_, cudaStream_t st_) : on(g_prof.on), stage(stage_), work(work_), st(st_) {
+    if (on && cudaEventCreate(&e0) == cudaSuccess) cudaEventRecord(e0, st); else on = false;
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEvent_t e1 = nullptr;
+    if (cudaEventCreate(&e1) != cudaSuccess) { cudaEventDestroy(e0); return; }
+    cudaEventRecord(e1, st);
+    g_prof.recs.push_back({stage, e0, e1, work});
+  }
+};
+
 // bump allocator over the upload ring: returns the offset of `bytes` (16-byte aligned) in both the pinned host and the device mirror
 struct Stage {
   FFH& H; const d3d_ff_runtime& rt; size_t begin, end;
@@ -690,6 +732,7 @@ struct Stage {
 int run_deferred(FFH& H, const d3d_ff_runtime& rt, void* stream) {
   if (!H.zone.pending) return 0;
   const FFH::Deferred& z = H.zone;
+  ProfScope pf(PF_ZONE, (double)z.T * 29.5e6, (cudaStream_t)stream);  // 4->768 MLP + 2 encoder layers: ~29.5 MFLOP per token
   D3D_TRY(d3d_pool_tokens(rt.level_zone, z.ptrs, z.centre, z.tok_seq, z.tok_src, z.cu, z.T, z.n_seq, z.max_len, 1, 1, rt.workspace, rt.workspace_bytes,
                           z.out, stream));
   D3D_TRY(d3d_scatter_rows_ptr(z.out, rt.level_zone->d_model, nullptr, z.fts_dst, z.n_seq, rt.level_zone->d_model, stream));
@@ -701,6 +744,26 @@ int run_deferred(FFH& H, const d3d_ff_runtime& rt, void* stream) {
 }  // namespace
 
 extern "C" int d3d_ff_run_deferred(void* h, const d3d_ff_runtime* rt, void* stream) { return run_deferred(HH(h), *rt, stream); }
+
+extern "C" int d3d_ff_profile_begin(void) {
+  for (auto& r : g_prof.recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  g_prof.recs.clear();
+  g_prof.on = true;
+  return 0;
+}
+// ms / work / launches: [6] arrays indexed knn, disc, new_slots, merge_pool, zone_pool, result_copy.  Synchronises the device.
+extern "C" int d3d_ff_profile_end(float* ms, double* work, int* launches) {
+  g_prof.on = false;
+  D3D_CHECK_CUDA(cudaDeviceSynchronize());
+  for (int i = 0; i < PF_N; ++i) { ms[i] = 0.f; work[i] = 0.0; launches[i] = 0; }
+  for (auto& r : g_prof.recs) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) { ms[r.stage] += t; work[r.stage] += r.work; launches[r.stage] += 1; }
+    cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+  }
+  g_prof.recs.clear();
+  return 0;
+}
 extern "C" void* d3d_event_create(void) {
   cudaEvent_t e = nullptr;
   if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { d3d_set_error("cudaEventCreate failed"); return nullptr; }
@@ -741,14 +804,25 @@ extern "C" int d3d_ff_view_pre(void* h, int ix, const d3d_ff_runtime* rt_p, cons
     const size_t o_pos = sg.put(pos_ptr.data(), (size_t)n_seq), o_fts = sg.put(fts_ptr.data(), (size_t)n_seq), o_nr = sg.put(nref.data(), (size_t)n_seq);
     D3D_REQUIRE(sg.fits(), "upload ring too small");
     D3D_TRY(sg.flush(st));
-    D3D_TRY(d3d_knn2_batched(sg.dev<int64_t>(o_pos), sg.dev<int>(o_nr), centres, n_seq, rt.d2, rt.idx, stream));
-    D3D_TRY(d3d_disc_input_batched(sg.dev<int64_t>(o_fts), sg.dev<int64_t>(o_pos), rt.idx, view_fts, centres, n_seq, 2, Dm, rt.disc->k_pad, rt.disc_in,
-                                   rt.disc->kind, stream));
-    D3D_TRY(d3d_mlp_ln_gelu(rt.disc, rt.disc_in, rt.disc->k_pad, 2 * n_seq, rt.disc_h32, rt.disc_h16, rt.disc_out, 4, stream));
+    {
+      double knn_bytes = 0;  // 12 B per reference slot searched + query / result rows
+      for (int s = 0; s < n_seq; ++s) knn_bytes += 12.0 * nref[(size_t)s] + 12.0 + 16.0;
+      ProfScope pf(PF_KNN, knn_bytes, st);
+      D3D_TRY(d3d_knn2_batched(sg.dev<int64_t>(o_pos), sg.dev<int>(o_nr), centres, n_seq, rt.d2, rt.idx, stream));
+    }
+    {
+      ProfScope pf(PF_DISC, 2.0 * (2.0 * n_seq) * ((double)rt.disc->k_pad * rt.disc->d_hidden + (double)rt.disc->d_hidden * rt.disc->d_out), st);
+      D3D_TRY(d3d_disc_input_batched(sg.dev<int64_t>(o_fts), sg.dev<int64_t>(o_pos), rt.idx, view_fts, centres, n_seq, 2, Dm, rt.disc->k_pad, rt.disc_in,
+                                     rt.disc->kind, stream));
+      D3D_TRY(d3d_mlp_ln_gelu(rt.disc, rt.disc_in, rt.disc->k_pad, 2 * n_seq, rt.disc_h32, rt.disc_h16, rt.disc_out, 4, stream));
+    }
   }
-  pack_view_result_kernel<<<d3d_cdiv(n_seq, 128), 128, 0, st>>>(centres, rt.d2, rt.idx, rt.disc_out, n_seq, any ? 1 : 0, rt.res_dev);
-  D3D_CHECK_LAUNCH();
-  D3D_CHECK_CUDA(cudaMemcpyAsync(rt.res_host, rt.res_dev, (size_t)n_seq * 12 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  {
+    ProfScope pf(PF_RESULT, (double)n_seq * 12 * sizeof(float) * 2, st);
+    pack_view_result_kernel<<<d3d_cdiv(n_seq, 128), 128, 0, st>>>(centres, rt.d2, rt.idx, rt.disc_out, n_seq, any ? 1 : 0, rt.res_dev);
+    D3D_CHECK_LAUNCH();
+    D3D_CHECK_CUDA(cudaMemcpyAsync(rt.res_host, rt.res_dev, (size_t)n_seq * 12 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
   D3D_CHECK_CUDA(cudaEventRecord((cudaEvent_t)rt.event, st));
   D3D_TRY(run_deferred(H, rt, stream));  // the previous view's zone pass executes while the host waits for / plans this view
   D3D_CHECK_CUDA(cudaEventSynchronize((cudaEvent_t)rt.event));
@@ -839,10 +913,12 @@ extern "C" int d3d_ff_view_post(void* h, const d3d_ff_runtime* rt_p, const d3d_f
   D3D_REQUIRE(sg.fits(), "upload ring too small for this view's plan");
   D3D_TRY(sg.flush(st));
   if (n_new) {
+    ProfScope pf(PF_NEW, (double)n_new * (Dm * 4 + 12) * 2, st);
     D3D_TRY(d3d_scatter_rows_ptr(view_fts_step, Dm, sg.dev<int>(o_ns), sg.dev<int64_t>(o_nf), n_new, Dm, stream));
     D3D_TRY(d3d_scatter_rows_ptr(centres_step, 3, sg.dev<int>(o_ns), sg.dev<int64_t>(o_np), n_new, 3, stream));
   }
   if (n_mg) {
+    ProfScope pf(PF_MERGE, (double)t_mg * 29.5e6, st);  // re-encode of ALL member patches of every merged instance (FF:662-688)
     D3D_TRY(d3d_pool_tokens(rt.level_inst, sg.dev<int64_t>(o_mp), sg.dev<float>(o_mx), sg.dev<int>(o_mq), sg.dev<int>(o_ms), sg.dev<int>(o_mc), t_mg, n_mg,
                             ml_mg, 0, 0, rt.workspace, rt.workspace_bytes, rt.out_merge, stream));
     D3D_TRY(d3d_scatter_rows_ptr(rt.out_merge, Dm, nullptr, sg.dev<int64_t>(o_mf), n_mg, Dm, stream));

@@ -54,40 +54,86 @@ class _Args:
         self.num_proposal_instances = 2
 
 
-class _Pool:
-    """Growable [cap, width] device tensor (capacity doubling keeps appends amortised O(1))."""
-    version = 0
+class _Ext:
+    """`__cuda_array_interface__` holder: lets torch alias device memory owned by the library's VMM pools."""
 
-    def __init__(self, width, dtype, device, cap=2048):
-        self.width, self.dtype, self.device = width, dtype, device
-        self.t = torch.zeros((cap,) + ((width,) if width else ()), device=device, dtype=dtype)
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2, "strides": None}
+
+
+_TYPESTR = {torch.float32: "<f4", torch.float16: "<f2", torch.int32: "<i4", torch.uint8: "|u1"}
+
+
+class _Pool:
+    """Growable [cap, width] device array with a STABLE base address (csrc/vmm_pool.cu): a reserved virtual range of `max_rows` rows whose
+    physical chunks are committed on demand -- growth neither copies nor moves the data nor synchronises the device, so a rollout that
+    outgrows its initial capacity (or was never `reserve()`d) does not stall, and the pointer tables of the view runtime stay valid.
+    `t` is a torch view of the committed rows.  On a CPU device (state-dict tests only: there are no CPU kernels) a plain tensor is used."""
+    version = 0  # bumped when a base address changed (CPU pools only)
+
+    def __init__(self, width, dtype, device, cap=2048, max_rows=1 << 20, chunk_bytes=0):
+        self.width, self.dtype, self.device = width, dtype, torch.device(device)
+        self.row_bytes = max(width, 1) * torch.empty((), dtype=dtype).element_size()
+        self._h = None
+        if self.device.type != "cuda":
+            self.t = torch.zeros((cap,) + ((width,) if width else ()), device=device, dtype=dtype)
+            return
+        index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self._h = L.lib().d3d_vmm_create(int(max_rows) * self.row_bytes, int(chunk_bytes), int(index))
+        if not self._h:
+            raise L.D3DError("d3d_vmm_create: " + L.lib().d3d_last_error().decode())
+        self.max_rows = int(L.lib().d3d_vmm_reserved(self._h)) // self.row_bytes
+        self.t = None
+        self.ensure(cap)
 
     def ensure(self, n):
-        cap = self.t.shape[0]
-        if n <= cap:
+        if self._h is None:  # CPU
+            cap = self.t.shape[0]
+            if n <= cap:
+                return
+            while cap < n:
+                cap *= 2
+            t = torch.zeros((cap,) + tuple(self.t.shape[1:]), device=self.device, dtype=self.dtype)
+            t[: self.t.shape[0]].copy_(self.t)
+            self.t = t
+            _Pool.version += 1
             return
-        while cap < n:
-            cap *= 2
-        t = torch.zeros((cap,) + tuple(self.t.shape[1:]), device=self.device, dtype=self.dtype)
-        t[: self.t.shape[0]].copy_(self.t)
-        self.t = t
-        _Pool.version += 1  # base addresses changed: pointer tables handed to the C runtime must be rebuilt
+        if self.t is not None and n <= self.t.shape[0]:
+            return
+        if n > self.max_rows:
+            raise L.D3DError(f"episode pool needs {n} rows but reserved address space for {self.max_rows}")
+        L.check(L.lib().d3d_vmm_ensure(self._h, int(n) * self.row_bytes, L.stream_ptr()))
+        rows = int(L.lib().d3d_vmm_mapped(self._h)) // self.row_bytes
+        shape = (rows, self.width) if self.width else (rows,)
+        self.t = torch.as_tensor(_Ext(L.lib().d3d_vmm_base(self._h), shape, _TYPESTR[self.dtype]), device=self.device)
+
+    def __del__(self):
+        try:  # unmapping needs an idle device; may run at interpreter shutdown
+            h, self._h = self._h, None
+            if h:
+                self.t = None
+                torch.cuda.synchronize(self.device)
+                L.lib().d3d_vmm_destroy(h)
+        except Exception:
+            pass
 
 
 class _Episode:
     """Device pools of one episode.  The integer state (ids, member lists, zone keys) lives in the C++ planner (ff_host.cu)."""
 
-    def __init__(self, device, patch_cap=65536, inst_cap=4096, zone_cap=512):
-        # sized for HBM3e: 65 536 patches (113 steps of one view, 9 twelve-view steps) = 101 MB of fp16 features per episode; growth past
-        # the capacity reallocates (cudaMalloc + copy, tens of ms), so callers that know the horizon pass it to Feature_Fields.reserve()
-        self.patch_pos = _Pool(3, torch.float32, device, patch_cap)
-        self.patch_dir = _Pool(0, torch.float32, device, patch_cap)
-        self.patch_scale = _Pool(0, torch.float32, device, patch_cap)
-        self.patch_fts = _Pool(D, torch.float16, device, patch_cap)
-        self.inst_pos = _Pool(3, torch.float32, device, inst_cap)
-        self.inst_fts = _Pool(D, torch.float32, device, inst_cap)
-        self.zone_pos = _Pool(3, torch.float32, device, zone_cap)
-        self.zone_fts = _Pool(D, torch.float32, device, zone_cap)
+    def __init__(self, device, patch_cap=16384, inst_cap=2048, zone_cap=512, max_patches=4 << 20, max_instances=1 << 20, max_zones=1 << 18):
+        # laid out for 180 GB of HBM3e: every pool reserves address space for the longest rollout we admit (4 Mi patches = 7 300 one-view
+        # steps: 6 GiB of VA for the fp16 features, no physical cost) and commits 2..32 MiB chunks as the episode grows; the initial
+        # commitment is 16 384 patches (28 one-view steps, 25 MB).  Feature_Fields.reserve() commits a known horizon up front.
+        MB = 1 << 20
+        self.patch_pos = _Pool(3, torch.float32, device, patch_cap, max_patches, 2 * MB)
+        self.patch_dir = _Pool(0, torch.float32, device, patch_cap, max_patches, 2 * MB)
+        self.patch_scale = _Pool(0, torch.float32, device, patch_cap, max_patches, 2 * MB)
+        self.patch_fts = _Pool(D, torch.float16, device, patch_cap, max_patches, 32 * MB)
+        self.inst_pos = _Pool(3, torch.float32, device, inst_cap, max_instances, 2 * MB)
+        self.inst_fts = _Pool(D, torch.float32, device, inst_cap, max_instances, 8 * MB)
+        self.zone_pos = _Pool(3, torch.float32, device, zone_cap, max_zones, 2 * MB)
+        self.zone_fts = _Pool(D, torch.float32, device, zone_cap, max_zones, 2 * MB)
         self.n_patch = self.n_inst = self.n_zone = 0
         self.tree = False
 
@@ -120,6 +166,7 @@ class Feature_Fields(nn.Module):
         for p in self.parameters():
             p.requires_grad_(False)
         self._ring, self._ring_i, self._tomb, self._ws = None, 0, None, None
+        self._gen = 0  # bumped whenever the set of episode pools changes (reset / pop / delete): keys the C runtime's pool-address table
         self.segmenter = None  # callable(batch_image) -> int64 [N,24,24]; FastSAM (FF:400-430) is outside the hot path
         self._W = None
         self.reset(batch_size)
@@ -127,6 +174,7 @@ class Feature_Fields(nn.Module):
     # ------------------------------------------------------------------ state management (FF:186-240)
     def reset(self, batch_size=1):
         self.batch_size = batch_size
+        self._gen += 1
         self.eps = [_Episode(self.device) for _ in range(batch_size)]
         if getattr(self, "_h", None):
             L.check(L.lib().d3d_ffh_reset(self._h, batch_size))
@@ -145,6 +193,7 @@ class Feature_Fields(nn.Module):
 
     def pop(self, index):
         self.batch_size -= 1
+        self._gen += 1
         self.eps.pop(index)
         L.check(L.lib().d3d_ffh_pop(self._h, index))
         self.keep_target_waypoint.pop(index)
@@ -155,6 +204,7 @@ class Feature_Fields(nn.Module):
         self.args.input_vfov = vfov
 
     def delete_feature_fields(self):
+        self._gen += 1
         self.eps = []
         L.check(L.lib().d3d_ffh_reset(self._h, 0))
         self.keep_target_waypoint = []
@@ -180,6 +230,10 @@ class Feature_Fields(nn.Module):
         out = super().load_state_dict(sd, strict=strict)
         self._W = None
         return out
+
+    def _load_from_state_dict(self, state_dict, prefix, *args):
+        self._W = None  # a load through the parent module (policy.load_state_dict, TR:214) must rebuild the engine-layout weights too
+        return super()._load_from_state_dict(state_dict, prefix, *args)
 
     # reference-style views of the state (read-only helpers for callers / tests), rebuilt from the C++ planner on demand
     def _map(self, b, which):
@@ -620,14 +674,25 @@ class Feature_Fields(nn.Module):
         self._rt = {"c": c, "bufs": bufs, "max_seq": max_seq, "W": W, "event": event, "pools": None, "pools_version": -1}
         return self._rt
 
+    def _grow_stage(self, rt, nbytes):
+        """Regrow the view runtime's upload ring (large merged instances: ~8 B per member patch).  Called between view_pre and view_post: no
+        deferred pass is pending there, every earlier upload has completed (view_pre waited on the device) and kernels still reading the old
+        device ring are ordered before its reuse by the caching allocator (same stream); the old buffers are kept alive for one more growth."""
+        cap = 1 << (int(nbytes) - 1).bit_length()
+        c, bufs = rt["c"], rt["bufs"]
+        rt["old_stage"] = (bufs["stage_dev"], bufs["stage_host"])
+        bufs["stage_dev"] = torch.empty(cap, device=self.device, dtype=torch.uint8)
+        bufs["stage_host"] = torch.empty(cap, dtype=torch.uint8).pin_memory()
+        c.stage_dev, c.stage_host, c.stage_bytes = bufs["stage_dev"].data_ptr(), bufs["stage_host"].data_ptr(), cap
+
     def _pool_table(self, rt):
         """Device base addresses of every episode's pools for the C runtime (rebuilt only after a pool was re-allocated or episodes changed)."""
-        if rt["pools"] is None or rt["pools_version"] != _Pool.version or len(rt["pools"]) != self.batch_size or rt.get("eps_id") != id(self.eps):
+        if rt["pools"] is None or rt["pools_version"] != _Pool.version or len(rt["pools"]) != self.batch_size or rt.get("gen") != self._gen:
             arr = (L.FFPools * max(self.batch_size, 1))()
             for b, ep in enumerate(self.eps):
                 arr[b] = L.FFPools(ep.patch_pos.t.data_ptr(), ep.patch_dir.t.data_ptr(), ep.patch_scale.t.data_ptr(), ep.patch_fts.t.data_ptr(),
                                    ep.inst_pos.t.data_ptr(), ep.inst_fts.t.data_ptr(), ep.zone_pos.t.data_ptr(), ep.zone_fts.t.data_ptr())
-            rt["pools"], rt["pools_version"], rt["eps_id"] = arr, _Pool.version, id(self.eps)
+            rt["pools"], rt["pools_version"], rt["gen"] = arr, _Pool.version, self._gen
         return rt["pools"]
 
     def _update_views_native(self, V, plan):
@@ -650,6 +715,8 @@ class Feature_Fields(nn.Module):
             if need > c.workspace_bytes:  # a pending (deferred) zone pass only reads its own uploaded arrays: re-allocating the workspace is safe
                 ws = self._workspace(need)
                 c.workspace, c.workspace_bytes = ws.data_ptr(), ws.numel()
+            if (int(sizes[7]) + 64) * 1024 * 4 > c.stage_bytes:  # a view's uploads may use a quarter of the ring (csrc/ff_host.cu: Stage)
+                self._grow_stage(rt, (int(sizes[7]) + 64) * 1024 * 4)
             for b, ep in enumerate(self.eps):
                 ep.n_inst, ep.n_zone = int(after[3 * b]), int(after[3 * b + 1])
                 ep.inst_pos.ensure(ep.n_inst); ep.inst_fts.ensure(ep.n_inst)
@@ -875,7 +942,9 @@ class Feature_Fields(nn.Module):
         cnt = torch.zeros((2 * B,), device=dev, dtype=torch.int32)
         with L.stream_scope():
             jobs_d, ids_d = self._upload([jobs.view(np.uint8).reshape(-1), np.asarray(ids_all if ids_all else [0], np.int32)])
-            L.check(L.lib().d3d_env_export_batched(L.ptr(jobs_d), L.ptr(ids_d), 2 * B, D, L.ptr(cnt), L.stream_ptr()))
+            ops.STAGE_TAG = "ff"
+            with ops._Rec("export", "hbm", len(ids_all) * (2 * (4 * D + 12) + 4)):  # every live token: position + feature read, row written
+                L.check(L.lib().d3d_env_export_batched(L.ptr(jobs_d), L.ptr(ids_d), 2 * B, D, L.ptr(cnt), L.stream_ptr()))
             cnt_h = cnt.to("cpu", non_blocking=True)
             torch.cuda.current_stream().synchronize()
         res = {"batch_instance_fts": [], "batch_instance_relative_position": [], "batch_zone_fts": [], "batch_zone_relative_position": []}

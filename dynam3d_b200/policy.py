@@ -24,6 +24,8 @@ from . import ops
 from .clip_vit import ViTEngine, ViTWeights
 from .feature_fields import Feature_Fields
 from .phi3 import LMEngine, LMWeights
+from .prompt import IMAGE_TOKEN, build_prompt
+from .weight_store import WeightStore
 
 
 def _mlp_container(d_in, d_hidden, d_out):
@@ -31,85 +33,144 @@ def _mlp_container(d_in, d_hidden, d_out):
 
 
 class CLIPEncoder(nn.Module):
-    """Drop-in for ENC:245-284: forward({'rgb': uint8 [N,H,W,3]}) -> (view_fts [N,768], grid_fts [N,576,768]) fp16."""
+    """Drop-in for ENC:245-284: forward({'rgb': uint8 [N,H,W,3]}) -> (view_fts [N,768], grid_fts [N,576,768]) fp16.
+
+    `self.model` holds the OpenAI CLIP checkpoint tensors under the reference's key names (`rgb_encoder.model.visual.*`, and whatever else a
+    trainer checkpoint carries for the text tower -- ENC:262 keeps the whole CLIP model), so `policy.state_dict()` / `load_state_dict(strict=False)`
+    (TR:75-84, 214, 219) round-trip them; the ViT engine is (re)built lazily from `model.visual.*` whenever the store changed."""
 
     def __init__(self, model_name="ViT-L/14@336px", device="cuda", max_images=12, precise=False):
         super().__init__()
         self.device = device
         self.precise = precise
-        self.engine = None
+        self.model = WeightStore(device)
+        self._engine, self._engine_version = None, -1
         self.max_images = max_images
+        self.n_head, self.resolution = 16, 336
         self.is_blind = False
 
     def load_openai_state_dict(self, sd, prefix="", n_head=16, resolution=336):
-        self.engine = ViTEngine(ViTWeights.from_openai_state_dict(sd, self.device, torch.float16, prefix), n_head, resolution, self.max_images)
+        """`sd`: OpenAI visual-tower names (conv1.weight, transformer.resblocks.N.*, ln_post.*, proj) below `prefix` (e.g. 'visual.')."""
+        self.n_head, self.resolution = n_head, resolution
+        self.model.adopt({k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}, "visual.")
+
+    @property
+    def engine(self):
+        if self._engine is None or self._engine_version != self.model.version:
+            if self.model.get("visual.conv1.weight") is None:
+                raise L.D3DLibraryError("CLIPEncoder has no weights: load a checkpoint (rgb_encoder.model.visual.*) or call load_openai_state_dict first")
+            self._engine = ViTEngine(ViTWeights.from_openai_state_dict(self.model.tensors(), self.device, torch.float16, "visual."), self.n_head,
+                                     self.resolution, self.max_images)
+            self._engine_version = self.model.version
+        return self._engine
 
     def forward(self, observations, ln_post_on_patches=True):
-        if self.engine is None:
-            raise L.D3DLibraryError("CLIPEncoder has no weights: call load_openai_state_dict first")
+        eng = self.engine
         rgb = observations["rgb"]
         if not rgb.is_cuda:
             rgb = rgb.to(self.device, non_blocking=True)
         if self.precise:
             from . import precise as PR
-            cls, grid = PR.vit_forward(self.engine, rgb.contiguous(), ln_post_on_patches=ln_post_on_patches)
+            cls, grid = PR.vit_forward(eng, rgb.contiguous(), ln_post_on_patches=ln_post_on_patches)
             return cls.to(torch.float16), grid.to(torch.float16)  # the reference stores grid features as fp16 (FF:500)
-        return self.engine.forward(rgb.contiguous(), ln_post_on_patches=ln_post_on_patches)
+        return eng.forward(rgb.contiguous(), ln_post_on_patches=ln_post_on_patches)
 
 
-class _Llava:
-    """Engine-side stand-in for LlavaForConditionalGeneration (POL:123-127): vision tower + projector + language model."""
+class _Llava(WeightStore):
+    """Engine-side stand-in for LlavaForConditionalGeneration (POL:123-127): vision tower + projector + language model.
 
-    def __init__(self, precise=False):
-        self.tower = None
-        self.lm = None
-        self.proj = None
-        self.precise = precise
+    The module itself is the weight store: its state-dict keys are the HF llava names of the checkpoint (`llava.vision_tower.vision_model.*`,
+    `llava.multi_modal_projector.linear_{1,2}.*`, `llava.language_model.model.*`, `llava.language_model.lm_head.weight` in the transformers-4.46
+    layout the reference pins; the 5.x layout `model.vision_tower...` / `lm_head.weight` is accepted as well).  The trainer's unchanged
+    `policy.load_state_dict(ckpt, strict=False)` therefore loads the fine-tuned LM, and `policy.state_dict()` saves it again; the fused 16-bit
+    engine weights are rebuilt lazily when the store changed."""
 
-    def load_state_dict(self, sd, device="cuda", lm_dtype=torch.float16, max_images=1, max_tokens=2048):
-        """Accepts HF llava keys: [model.]vision_tower.vision_model.*, [model.]multi_modal_projector.linear_{1,2}.*,
-        [model.]language_model.[model.]*, lm_head.weight (transformers 4.46 and 5.x layouts)."""
+    def __init__(self, precise=False, device="cuda"):
+        super().__init__(device)
+        self.precise_tower = self.precise_lm = precise
+        self._built_version = -1
+        self._tower = self._lm = self._proj = None
+        self.lm_dtype, self.max_images, self.max_tokens = torch.float16, 1, 2048
+
+    def load_state_dict(self, sd, strict=True, device=None, lm_dtype=None, max_images=None, max_tokens=None, assign=False):
+        """Explicit loader (tests / bench): adopts an HF-llava state dict and sets the engine's capacity hints."""
+        if device is not None:
+            self._store_device = device
+        if lm_dtype is not None:
+            self.lm_dtype = lm_dtype
+        if max_images is not None:
+            self.max_images = max_images
+        if max_tokens is not None:
+            self.max_tokens = max_tokens
+        self.adopt(sd)
+
+    def _build(self):
+        if self._built_version == self.version and self._lm is not None:
+            return
+        sd = self.tensors()
+        if not sd:
+            raise L.D3DLibraryError("llava has no weights: load a checkpoint (net.llava.*) or call llava.load_state_dict first")
+        device = self._target_device()
+
         def find(suffix):
             for k in sd:
                 if k.endswith(suffix):
                     return k[: -len(suffix)]
             raise KeyError(suffix)
         vt = find("vision_model.embeddings.class_embedding")
-        self.tower = ViTEngine(ViTWeights.from_hf_clip_state_dict(sd, device, torch.float16, vt + "vision_model."), 16, 336, max_images, tag="tower")
+        self._tower = ViTEngine(ViTWeights.from_hf_clip_state_dict(sd, device, torch.float16, vt + "vision_model."), 16, 336, self.max_images, tag="tower")
         pj = find("multi_modal_projector.linear_1.weight")
         c16 = lambda t: t.detach().to(device=device, dtype=torch.float32).to(torch.float16).contiguous()
         f32 = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()
-        self.proj = {"w1": c16(sd[pj + "multi_modal_projector.linear_1.weight"]), "b1": f32(sd[pj + "multi_modal_projector.linear_1.bias"]),
-                     "w2": c16(sd[pj + "multi_modal_projector.linear_2.weight"]), "b2": f32(sd[pj + "multi_modal_projector.linear_2.bias"])}
+        self._proj = {"w1": c16(sd[pj + "multi_modal_projector.linear_1.weight"]), "b1": f32(sd[pj + "multi_modal_projector.linear_1.bias"]),
+                      "w2": c16(sd[pj + "multi_modal_projector.linear_2.weight"]), "b2": f32(sd[pj + "multi_modal_projector.linear_2.bias"])}
         lm_prefix = find("embed_tokens.weight")
         head = [k for k in sd if k.endswith("lm_head.weight")][0]
-        self.lm = LMEngine(LMWeights.from_state_dict(sd, device, lm_dtype, lm_prefix, head), n_heads=32, max_tokens=max_tokens)
+        self._lm = LMEngine(LMWeights.from_state_dict(sd, device, self.lm_dtype, lm_prefix, head), n_heads=32, max_tokens=self.max_tokens)
+        self._built_version = self.version
+
+    @property
+    def tower(self):
+        self._build()
+        return self._tower
+
+    @property
+    def lm(self):
+        self._build()
+        return self._lm
+
+    @property
+    def proj(self):
+        self._build()
+        return self._proj
 
     def image_features(self, rgb_u8):
         """get_image_features (POL:448-452): hidden_states[-2] of the tower without CLS -> linear_1 -> GELU -> linear_2; fp32 [N*576, 3072]."""
-        if self.precise:
+        tower, proj = self.tower, self.proj
+        if self.precise_tower:
             from . import precise as PR
-            hid = PR.vit_forward(self.tower, rgb_u8, n_layers_run=len(self.tower.w.layers) - 1, project=False)
+            hid = PR.vit_forward(tower, rgb_u8, n_layers_run=len(tower.w.layers) - 1, project=False)
             x = hid[:, 1:].reshape(hid.shape[0] * 576, hid.shape[2]).contiguous()
-            h = PR.linear(x, self.proj["w1"], self.proj["b1"], act=L.ACT_GELU)
-            return PR.linear(h, self.proj["w2"], self.proj["b2"])
-        hid = self.tower.forward(rgb_u8, n_layers_run=len(self.tower.w.layers) - 1, project=False)  # [N, 577, 1024] fp32
+            h = PR.linear(x, proj["w1"], proj["b1"], act=L.ACT_GELU)
+            return PR.linear(h, proj["w2"], proj["b2"])
+        hid = tower.forward(rgb_u8, n_layers_run=len(tower.w.layers) - 1, project=False)  # [N, 577, 1024] fp32
         N = hid.shape[0]
         ops.STAGE_TAG = "proj"
         a16 = torch.empty((N * 576, hid.shape[2]), device=hid.device, dtype=torch.float16)
         ops.cast16(hid[:, 1:].reshape(N * 576, hid.shape[2]), a16)
-        h = ops.gemm(a16, self.proj["w1"], bias=self.proj["b1"], act=L.ACT_GELU)
-        return ops.gemm(h, self.proj["w2"], bias=self.proj["b2"], out_dtype=torch.float32)
+        h = ops.gemm(a16, proj["w1"], bias=proj["b1"], act=L.ACT_GELU)
+        return ops.gemm(h, proj["w2"], bias=proj["b2"], out_dtype=torch.float32)
 
 
 class Dynam3D_VLN(nn.Module):
-    IMAGE_TOKEN = "<image>"
+    IMAGE_TOKEN = IMAGE_TOKEN
 
     def __init__(self, observation_space=None, model_config=None, num_actions=None, device="cuda", q1_fix=False, q7_fix=False, precise=False):
         super().__init__()
         self.device = torch.device(device)
         self.q1_fix = q1_fix
-        self.precise = precise  # split-operand fp32-activation mode (precise.py): parity evidence only
+        self.precise = precise  # split-operand fp32-activation mode (precise.py): the <= 1e-3 logit-parity mode
+        self._precise_proj = precise
         self.feature_fields = Feature_Fields(batch_size=1, device=self.device, q7_fix=q7_fix, precise=precise)
         width = 768
         self.patch_position_embedding = _mlp_container(6, width * 4, width * 4)
@@ -121,7 +182,7 @@ class Dynam3D_VLN(nn.Module):
             p.requires_grad_(False)
         self.rgb_encoder = CLIPEncoder("ViT-L/14@336px", self.device, precise=precise)
         self.depth_encoder = None  # SURVEY.md 8(f) rank 3 (waypoint branch), not part of this step
-        self.llava = _Llava(precise=precise)
+        self.llava = _Llava(precise=precise, device=self.device)
         self.tokenize = None      # callable(str) -> list[int]; the real one is the llava-phi-3 tokenizer (POL:131)
         self.detokenize = None    # callable(list[int]) -> str
         self.eos_token_ids = (32000, 32007)  # <|endoftext|>, <|end|> of the llava-phi-3-mini tokenizer (generation stops there, POL:463)
@@ -142,17 +203,66 @@ class Dynam3D_VLN(nn.Module):
     def num_recurrent_layers(self):
         return 1
 
+    PRECISE_PARTS = ("vit", "tower", "ff", "proj", "lm")
+
+    def set_precise_parts(self, parts):
+        """Choose which stages run in the split-operand fp32-activation mode (error-vs-cost curve of DESIGN.md section 4): any subset of
+        PRECISE_PARTS; () = production.  Weights already loaded stay valid (the precise kernels read the same tensors)."""
+        parts = frozenset(parts)
+        assert parts <= frozenset(self.PRECISE_PARTS), parts
+        self.precise = bool(parts)
+        self.rgb_encoder.precise = "vit" in parts
+        self.llava.precise_tower, self.llava.precise_lm = "tower" in parts, "lm" in parts
+        self._precise_proj = "proj" in parts
+        ff = self.feature_fields
+        if ff.precise != ("ff" in parts):
+            ff.precise, ff._W = "ff" in parts, None
+        self._PW = None
+
+    _OWN_MLPS = ("patch_position_embedding", "instance_position_embedding", "zone_position_embedding", "instance_projector", "zone_projector")
+
     def load_policy_state_dict(self, sd, strict=True):
-        """`net.*` keys of a trainer checkpoint that this module owns (feature_fields.*, *_embedding.*, *_projector.*)."""
-        own = {k: v for k, v in sd.items() if k.split(".")[0] in ("feature_fields", "patch_position_embedding", "instance_position_embedding",
-                                                                   "zone_position_embedding", "instance_projector", "zone_projector")}
-        ff = {k[len("feature_fields."):]: v for k, v in own.items() if k.startswith("feature_fields.")}
+        """Explicit loader for the `net.*` keys of a trainer checkpoint (a leading `module.` / `net.` / `net.module.` prefix is stripped):
+        feature_fields.*, the five projection MLPs, and -- when present -- `llava.*` and `rgb_encoder.model.*`.  Raises when nothing matched;
+        `strict` applies to feature_fields AND the projection MLPs.  (The trainer's own `policy.load_state_dict(ckpt, strict=False)` works too:
+        every sub-module holds its weights as nn.Module state under the reference's names.)"""
+        def strip(k):
+            for pre in ("module.", "net.", "module."):
+                if k.startswith(pre):
+                    k = k[len(pre):]
+            return k
+        sd = {strip(k): v for k, v in sd.items()}
+        ff = {k[len("feature_fields."):]: v for k, v in sd.items() if k.startswith("feature_fields.")}
+        rest = {k: v for k, v in sd.items() if k.split(".")[0] in self._OWN_MLPS}
+        llava = {k[len("llava."):]: v for k, v in sd.items() if k.startswith("llava.")}
+        clip = {k[len("rgb_encoder.model."):]: v for k, v in sd.items() if k.startswith("rgb_encoder.model.")}
+        if not (ff or rest or llava or clip):
+            raise KeyError("load_policy_state_dict: no key of this policy found (expected [module.][net.]feature_fields.* / *_embedding.* / *_projector.* / "
+                           "llava.* / rgb_encoder.model.*); first keys: " + ", ".join(list(sd)[:3]))
         if ff:
             self.feature_fields.load_state_dict(ff, strict=strict)
-        rest = {k: v for k, v in own.items() if not k.startswith("feature_fields.")}
-        missing = super().load_state_dict(rest, strict=False)
+        missing, unexpected = [], []
+        if rest or strict:
+            own = {n: m for n, m in self.named_children() if n in self._OWN_MLPS}
+            for n, m in own.items():
+                sub = {k[len(n) + 1:]: v for k, v in rest.items() if k.startswith(n + ".")}
+                if not sub and not strict:
+                    continue
+                r = m.load_state_dict(sub, strict=False)
+                missing += [n + "." + k for k in r.missing_keys]
+                unexpected += [n + "." + k for k in r.unexpected_keys]
+            if strict and (missing or unexpected):
+                raise RuntimeError(f"load_policy_state_dict(strict=True): missing keys {missing}, unexpected keys {unexpected}")
+        if llava:
+            self.llava.adopt(llava)
+        if clip:
+            self.rgb_encoder.model.adopt(clip)
         self._PW = None
-        return missing
+        return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)
+
+    def _load_from_state_dict(self, state_dict, prefix, *args):
+        self._PW = None  # the engine-layout copies of the projection MLPs are rebuilt after any load through nn.Module.load_state_dict
+        return super()._load_from_state_dict(state_dict, prefix, *args)
 
     def _policy_weights(self):
         if self._PW is None:
@@ -171,7 +281,7 @@ class Dynam3D_VLN(nn.Module):
                     w0 = torch.cat([w0, torch.zeros(w0.shape[0], kpad - w0.shape[1])], 1)
                 return {"w0": w0.to(dev).contiguous(), "b0": f32(seq[0].bias), "g": f32(seq[1].weight), "b": f32(seq[1].bias),
                         "w3": f32(seq[3].weight), "b3": f32(seq[3].bias)}
-            if self.precise:
+            if self._precise_proj:
                 mlp = mlp32
             self._PW = {"patch_pos": mlp(self.patch_position_embedding, 8), "inst_pos": mlp(self.instance_position_embedding, 8),
                         "zone_pos": mlp(self.zone_position_embedding, 8), "inst_proj": mlp(self.instance_projector),
@@ -240,7 +350,7 @@ class Dynam3D_VLN(nn.Module):
 
     # ------------------------------------------------------------------ building blocks of forward
     def _mlp(self, A0, m):
-        if self.precise:
+        if self._precise_proj:
             from . import precise as PR
             return PR.mlp_ln_gelu(A0, m)
         h = ops.gemm(A0, m["w0"], bias=m["b0"], out_dtype=torch.float32)
@@ -254,7 +364,7 @@ class Dynam3D_VLN(nn.Module):
         ops.STAGE_TAG = "proj"
         if n == 0:
             return torch.zeros((0, 3072), device=self.device, dtype=torch.float32)
-        op_dt = torch.float32 if self.precise else torch.float16
+        op_dt = torch.float32 if self._precise_proj else torch.float16
         a = torch.empty((n, 8), device=self.device, dtype=op_dt)
         ops.pos3_rows(rel.contiguous(), a)
         pe = self._mlp(a, pos_mlp)
@@ -262,9 +372,9 @@ class Dynam3D_VLN(nn.Module):
         ops.concat2_cast(fts.contiguous(), pe, cat)
         return self._mlp(cat, proj_mlp)
 
-    def build_prompt(self, n_image_tokens, instruction, history):
-        return ("<|user|>\n" + self.IMAGE_TOKEN * n_image_tokens + "\nInstruction:\n" + instruction + "\nHistory actions:\n" + "".join(history) +
-                "<|end|>\n<|assistant|>\nNext action:\n")
+    @staticmethod
+    def build_prompt(n_image_tokens, instruction, history):
+        return build_prompt(n_image_tokens, instruction, history)
 
     def encode_step(self, observations, agent_positions, agent_heading_angles, depth_scale=(0.0, 10.0), delete_old_features=True, num_of_views=1):
         """Stages a1-a14 (POL:336-363, 432-435): returns per-episode projected tokens (patch, instance, zone), all fp32 [*, 3072]."""
@@ -293,7 +403,7 @@ class Dynam3D_VLN(nn.Module):
             self._side = torch.cuda.Stream()
         self._side.wait_stream(main)
         with torch.cuda.stream(self._side), L.stream_scope():
-            rows = torch.empty((B * P, 8), device=dev, dtype=torch.float32 if self.precise else torch.float16)
+            rows = torch.empty((B * P, 8), device=dev, dtype=torch.float32 if self._precise_proj else torch.float16)
             ops.patch_info_rows(info5[:, sel].contiguous(), rows)
             patch_pos = self._mlp(rows, PW["patch_pos"])  # POL:432-433
             patch = self.llava.image_features(rgb[sel].contiguous())  # POL:448-452
@@ -335,7 +445,7 @@ class Dynam3D_VLN(nn.Module):
         patch, inst, zone = self.encode_step(observations, agent_positions, agent_heading_angles, depth_scale, delete_old_features, num_of_views)
         lm = self.llava.lm
         # text tokens of all episodes: ONE id upload and ONE embedding gather (POL:439), then the literal splice of POL:456
-        heads, tails, n_imgs = [], [], []
+        heads, tails, n_imgs, all_ids = [], [], [], []
         for b in range(B):
             n_img = patch.shape[1] + inst[b].shape[0] + zone[b].shape[0]
             if input_ids is not None:
@@ -345,6 +455,8 @@ class Dynam3D_VLN(nn.Module):
                     raise RuntimeError("no tokenizer: set .tokenize or pass input_ids (prompt ids with n_img image slots after 2 tokens)")
                 ids = self.tokenize(self.build_prompt(n_img, instructions[b], ff.history_actions[b]))
             heads.append(ids[:2]); tails.append(ids[n_img + 2:]); n_imgs.append(n_img)
+            all_ids.append(ids)
+        self.last_input_ids = all_ids  # prompt ids of the step (tests / parity checks feed the same ids to the oracle)
         flat = [t for b in range(B) for t in (heads[b] + tails[b])]
         E = torch.empty((len(flat), lm.w.hidden), device=self.device, dtype=torch.float32)
         lm.embed(torch.tensor(flat, dtype=torch.int32).to(self.device, non_blocking=True), E)
@@ -360,10 +472,10 @@ class Dynam3D_VLN(nn.Module):
         last = (cu[1:] - 1).to(torch.int32).contiguous()
         self.last_seq_lens = lens
         if generate:
-            if self.precise:
+            if self.llava.precise_lm:
                 raise NotImplementedError("the precise (split-operand) mode covers the prefill only")
             return lm.generate(X, cu, pos, B, max(lens), last, max_new_tokens=self.max_new_tokens, eos_ids=self.eos_token_ids)
-        if self.precise:
+        if self.llava.precise_lm:
             from . import precise as PR
             return PR.lm_prefill(lm, X, cu, pos, B, max(lens), last)
         return lm.prefill(X, cu, pos, B, max(lens), last)

@@ -366,6 +366,21 @@ int d3d_ff_view_pre(void* h, int ix, const d3d_ff_runtime* rt, const d3d_ff_pool
                     int* sizes10, int64_t* after3, void* stream);
 int d3d_ff_view_post(void* h, const d3d_ff_runtime* rt, const d3d_ff_pools* pools_h, float* centres_step, float* view_fts_step, void* stream);
 int d3d_ff_run_deferred(void* h, const d3d_ff_runtime* rt, void* stream);
+/* Growable device arrays with stable addresses for the episode pools (csrc/vmm_pool.cu): a reserved virtual range, physical chunks committed
+ * on demand (CUDA virtual memory management).  Replaces the reference's grow-by-concatenation (feature_fields.py:557-570, 643-648, 715-730).
+ * create: reserve va_bytes (chunk_bytes = commit granularity, 0 = 32 MiB); ensure: commit until >= bytes are mapped, zero-filling new chunks
+ * on `stream` (no copy, no pointer change, no device synchronisation); destroy: the caller synchronises first. */
+void* d3d_vmm_create(size_t va_bytes, size_t chunk_bytes, int device);
+int d3d_vmm_ensure(void* pool, size_t bytes, void* stream);
+uint64_t d3d_vmm_base(void* pool);
+size_t d3d_vmm_mapped(void* pool);
+size_t d3d_vmm_reserved(void* pool);
+int d3d_vmm_destroy(void* pool);
+/* Device timing of the view runtime's phases (CUDA events on the launch stream), for bench.py's per-stage roofline table.
+ * begin: start recording; end: synchronise and return, per phase [knn, disc, new_slots, merge_pool, zone_pool, result_copy]: milliseconds,
+ * algorithmic work (bytes for knn / new_slots / result_copy, FLOPs for the others) and the number of recorded scopes. */
+int d3d_ff_profile_begin(void);
+int d3d_ff_profile_end(float* ms6, double* work6, int* launches6);
 void* d3d_event_create(void);   /* cudaEvent_t without timing, for d3d_ff_runtime.event */
 void d3d_event_destroy(void* e);
 

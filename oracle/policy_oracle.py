@@ -57,7 +57,8 @@ class PolicyOracle:
         return NN.mlp_ln_gelu(torch.cat([torch.from_numpy(fts), pe], -1), self.P, proj_prefix, self.rnd)
 
     def step_logits(self, obs, agent_positions, agent_headings, input_ids, num_of_views=1, delete_old_features=True):
-        """obs: dict rgb u8 [B*V,H,W,3], depth f32 [B*V,Hd,Wd,1], patch_segm [B,V,24,24]; input_ids: per-episode prompt ids."""
+        """obs: dict rgb u8 [B*V,H,W,3], depth f32 [B*V,Hd,Wd,1], patch_segm [B,V,24,24]; input_ids: per-episode prompt ids, or a
+        callable (b, n_image_tokens) -> ids (the prompt needs the 3D-token counts, POL:436, which only exist after the memory update)."""
         B, V = self.ff.batch_size, num_of_views
         depth = np.asarray(obs["depth"], np.float32)
         d576 = G.depth_patch_grid(depth, B, V, q1_fix=self.q1_fix)
@@ -84,7 +85,7 @@ class PolicyOracle:
             inst = self._tokens(env["batch_instance_fts"][b], env["batch_instance_relative_position"][b], "instance_position_embedding", "instance_projector")
             zone = self._tokens(env["batch_zone_fts"][b], env["batch_zone_relative_position"][b], "zone_position_embedding", "zone_projector")
             n_img = 576 + len(inst) + len(zone)
-            ids = torch.tensor(list(input_ids[b]), dtype=torch.long)
+            ids = torch.tensor(list(input_ids(b, n_img) if callable(input_ids) else input_ids[b]), dtype=torch.long)
             e = emb_table[ids]
             seq = torch.cat([e[:2], patch, inst, zone, e[n_img + 2:]], 0)  # POL:456
             embeds.append(seq)

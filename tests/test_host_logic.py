@@ -67,7 +67,7 @@ def test_prompt_and_splice_shape():
     from dynam3d_b200 import synth
     from dynam3d_b200.policy import Dynam3D_VLN
     tok = synth.ToyTokenizer()
-    p = Dynam3D_VLN.build_prompt(Dynam3D_VLN, 5, "go", ["none\n"] * 4)
+    p = Dynam3D_VLN.build_prompt(5, "go", ["none\n"] * 4)
     ids = tok(p)
     assert ids.count(tok.SPECIAL["<image>"]) == 5 and ids[1] == tok.SPECIAL["<|user|>"]
     assert p.startswith("<|user|>\n<image>") and p.endswith("<|assistant|>\nNext action:\n")
