@@ -101,6 +101,7 @@ SIGNATURES = {
     "d3d_rope_table": [_P, _P, _I, _I, _P, _P], "d3d_rope_apply": [_P, _L, _P, _I, _I, _I, _I, _P],
     "d3d_embed_gather": [_P, _I, _P, _I, _I, _P, _L, _P],
     "d3d_preprocess_im2col": [_P, _I, _I, _I, _I, _I, _FP, _FP, _P, _I, _I, _P],
+    "d3d_pil_resample_pass": [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P],
     "d3d_vit_embed_ln": [_P, _P, _P, _P, _P, _F, _I, _I, _I, _P, _P],
     "d3d_scatter_rows": [_P, _L, _P, _P, _L, _P, _I, _I, _P],
     "d3d_add_inplace": [_P, _P, _L, _I, _P],

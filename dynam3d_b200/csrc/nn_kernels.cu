@@ -177,16 +177,24 @@ __global__ void embed_gather_kernel(const void* __restrict__ table, int kind, co
 //   u8 NHWC -> (bicubic resize to RxR, A=-0.75, align_corners=False, round+clamp to u8 as torchvision does) -> /255
 //   -> (x-mean)/std -> 16-bit -> patches [N*g*g, Kpad], column = c*p*p + ky*p + kx
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cubic_coeffs(float t, float* w) {
+// The expressions below are written exactly like PyTorch's CUDA bicubic kernel (ATen/native/cuda/UpSample.cuh: cubic_convolution1/2,
+// get_cubic_upsample_coefficients, cubic_interp1d; UpSampleBicubic2d.cu: x pass per row, then the y pass) so that nvcc contracts them into
+// the same FMA sequence: resized pixels are bit-identical to torch's CUDA `interpolate(mode="bicubic")` -- the kernel the reference's
+// torchvision Resize (ENC:268) runs for observations that live on the GPU (tests/test_nn_kernels_gpu.py).  PyTorch's CPU kernel evaluates
+// the same formula in a different order; after rounding to uint8 it differs on < 1e-4 of the pixels, from this kernel as from torch's own.
+__device__ __forceinline__ float cubic_convolution1(float x, float A) { return ((A + 2) * x - (A + 3)) * x * x + 1; }
+__device__ __forceinline__ float cubic_convolution2(float x, float A) { return ((A * x - 5 * A) * x + 8 * A) * x - 4 * A; }
+__device__ __forceinline__ void cubic_coeffs(float t, float* coeffs) {
   const float A = -0.75f;
-  float x = t + 1.0f;
-  w[0] = ((A * x - 5.0f * A) * x + 8.0f * A) * x - 4.0f * A;
-  x = t;
-  w[1] = ((A + 2.0f) * x - (A + 3.0f)) * x * x + 1.0f;
-  x = 1.0f - t;
-  w[2] = ((A + 2.0f) * x - (A + 3.0f)) * x * x + 1.0f;
-  x = 2.0f - t;
-  w[3] = ((A * x - 5.0f * A) * x + 8.0f * A) * x - 4.0f * A;
+  float x1 = t;
+  coeffs[0] = cubic_convolution2(x1 + 1.0f, A);
+  coeffs[1] = cubic_convolution1(x1, A);
+  float x2 = 1.0f - t;
+  coeffs[2] = cubic_convolution1(x2, A);
+  coeffs[3] = cubic_convolution2(x2 + 1.0f, A);
+}
+__device__ __forceinline__ float cubic_interp1d(float x0, float x1, float x2, float x3, const float* coeffs) {
+  return x0 * coeffs[0] + x1 * coeffs[1] + x2 * coeffs[2] + x3 * coeffs[3];
 }
 
 struct NormParams {
@@ -211,17 +219,17 @@ __global__ void preprocess_im2col_kernel(const uint8_t* __restrict__ img, int N,
     float wy[4], wx[4];
     cubic_coeffs(fy - (float)iy, wy);
     cubic_coeffs(fx - (float)ix, wx);
+    int xs[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) xs[j] = min(max(ix - 1 + j, 0), Win - 1);
     for (int c = 0; c < 3; ++c) {
-      float acc = 0.f;
+      float rows[4];
+#pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int yy = min(max(iy - 1 + i, 0), Hin - 1);
-        float rowv = 0.f;
-        for (int j = 0; j < 4; ++j) {
-          const int xx = min(max(ix - 1 + j, 0), Win - 1);
-          rowv += (float)src[((size_t)yy * Win + xx) * 3 + c] * wx[j];
-        }
-        acc += rowv * wy[i];
+        const uint8_t* r = src + (size_t)min(max(iy - 1 + i, 0), Hin - 1) * Win * 3 + c;
+        rows[i] = cubic_interp1d((float)r[xs[0] * 3], (float)r[xs[1] * 3], (float)r[xs[2] * 3], (float)r[xs[3] * 3], wx);
       }
+      const float acc = cubic_interp1d(rows[0], rows[1], rows[2], rows[3], wy);
       px[c] = fminf(fmaxf(rintf(acc), 0.0f), 255.0f);  // torchvision casts the resized float image back to uint8
     }
   }
@@ -232,6 +240,35 @@ __global__ void preprocess_im2col_kernel(const uint8_t* __restrict__ img, int N,
     const float v = (px[c] / 255.0f - np.mean[c]) / np.std[c];
     st16(out, (size_t)prow * kpad + c * p * p + ky * p + kx, v, kind);
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// a15 input path (POL:438): HF CLIPImageProcessor resizes with Pillow -- ImagingResample, 8 bits per channel: fixed-point taps (22 bits),
+// horizontal pass -> uint8 intermediate -> vertical pass, clip8((acc + 2^21) >> 22).  One pass along `axis`; taps / bounds are tables
+// built on the host (ops.pil_bicubic_tables, Pillow's precompute_coeffs + normalize_coeffs_8bpc).  Integer work: bit-exact.
+//   src [N, H, W, C] u8 -> dst [N, H, Wout, C] (axis = 1, along W) or [N, Hout, W, C] (axis = 0, along H)
+// ------------------------------------------------------------------------------------------------
+__global__ void pil_resample_pass_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int N, int H, int W, int C, int out_size,
+                                         int axis, const int* __restrict__ bounds, const int* __restrict__ kk, int ksize) {
+  const int Ho = axis == 0 ? out_size : H, Wo = axis == 1 ? out_size : W;
+  const long long total = (long long)N * Ho * Wo * C;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % C);
+  const int x = (int)((idx / C) % Wo), y = (int)((idx / ((long long)C * Wo)) % Ho), n = (int)(idx / ((long long)C * Wo * Ho));
+  const int o = axis == 1 ? x : y;
+  const int first = bounds[o * 2], cnt = bounds[o * 2 + 1];
+  const int* k = kk + (size_t)o * ksize;
+  const uint8_t* base = src + (size_t)n * H * W * C + c;
+  int acc = 1 << 21;
+  if (axis == 1) {
+    const uint8_t* r = base + (size_t)y * W * C;
+    for (int t = 0; t < cnt; ++t) acc += (int)r[(size_t)(first + t) * C] * k[t];
+  } else {
+    const uint8_t* r = base + (size_t)x * C;
+    for (int t = 0; t < cnt; ++t) acc += (int)r[(size_t)(first + t) * W * C] * k[t];
+  }
+  dst[idx] = (uint8_t)min(max(acc >> 22, 0), 255);
 }
 
 // zero the K padding columns [k, kpad) of an im2col matrix
@@ -407,6 +444,15 @@ extern "C" int d3d_preprocess_im2col(const uint8_t* img, int N, int Hin, int Win
   }
   const long long total = (long long)N * R * R;
   preprocess_im2col_kernel<<<d3d_cdiv(total, 256), 256, 0, st>>>(img, N, Hin, Win, R, patch, np, out, kpad, kind);
+  D3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int d3d_pil_resample_pass(const uint8_t* src, uint8_t* dst, int N, int H, int W, int C, int out_size, int axis, const int* bounds,
+                                     const int* kk, int ksize, void* stream) {
+  D3D_REQUIRE(src && dst && bounds && kk && N > 0 && (axis == 0 || axis == 1) && ksize > 0, "args");
+  const long long total = (long long)N * (axis == 0 ? out_size : H) * (axis == 1 ? out_size : W) * C;
+  pil_resample_pass_kernel<<<d3d_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, N, H, W, C, out_size, axis, bounds, kk, ksize);
   D3D_CHECK_LAUNCH();
   return 0;
 }

@@ -317,6 +317,64 @@ def preprocess_im2col(img_u8, R=336, patch=14, out_dtype=torch.float16, mean=CLI
     return out
 
 
+_PIL_TABLES = {}
+
+
+def pil_bicubic_tables(in_size, out_size):
+    """Pillow's `precompute_coeffs` + `normalize_coeffs_8bpc` for the BICUBIC filter (a = -0.5, support 2, widened when down-scaling):
+    (bounds int32 [out,2] = first source index / tap count, kk int32 [out,ksize] = 22-bit fixed-point taps).  Host, double arithmetic."""
+    def filt(x):
+        a = -0.5
+        x = abs(x)
+        if x < 1.0:
+            return ((a + 2.0) * x - (a + 3.0)) * x * x + 1
+        if x < 2.0:
+            return (((x - 5) * x + 8) * x - 4) * a
+        return 0.0
+    scale = float(np.float32(in_size)) / out_size
+    filterscale = max(scale, 1.0)
+    support = 2.0 * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    bounds = np.zeros((out_size, 2), np.int32)
+    kk = np.zeros((out_size, ksize), np.int32)
+    ss = 1.0 / filterscale
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        xmin = max(int(center - support + 0.5), 0)
+        n = min(int(center + support + 0.5), in_size) - xmin
+        k = [filt((x + xmin - center + 0.5) * ss) for x in range(n)]
+        ww = 0.0
+        for w in k:
+            ww += w
+        for x, w in enumerate(k):
+            if ww != 0.0:
+                w = w / ww
+            kk[xx, x] = int(-0.5 + w * (1 << 22)) if w < 0 else int(0.5 + w * (1 << 22))
+        bounds[xx] = (xmin, n)
+    return bounds, kk
+
+
+def pil_bicubic_resize(img_u8, out_h, out_w):
+    """PIL `Image.resize((out_w, out_h), BICUBIC)` of uint8 NHWC device images, bit for bit (HF CLIPImageProcessor, POL:438)."""
+    assert img_u8.dtype == torch.uint8 and img_u8.is_cuda and img_u8.is_contiguous()
+    N, H, W, C = img_u8.shape
+    x = img_u8
+    for axis, n_in, n_out in ((1, W, out_w), (0, H, out_h)):  # horizontal pass first, uint8 intermediate (ImagingResample)
+        if n_in == n_out:
+            continue
+        key = (n_in, n_out, str(x.device))
+        if key not in _PIL_TABLES:
+            b, k = pil_bicubic_tables(n_in, n_out)
+            _PIL_TABLES[key] = (torch.from_numpy(b).to(x.device), torch.from_numpy(k).to(x.device))
+        b, k = _PIL_TABLES[key]
+        h, w = x.shape[1], x.shape[2]
+        dst = torch.empty((N, n_out if axis == 0 else h, n_out if axis == 1 else w, C), device=x.device, dtype=torch.uint8)
+        with _Rec("pil_resize", "hbm", x.numel() + dst.numel()):
+            L.check(L.lib().d3d_pil_resample_pass(L.ptr(x), L.ptr(dst), N, h, w, C, n_out, axis, L.ptr(b), L.ptr(k), k.shape[1], L.stream_ptr()))
+        x = dst
+    return x
+
+
 def vit_embed_ln(conv, cls, pos, gamma, beta, eps, N, tokens, out):
     L.check(L.lib().d3d_vit_embed_ln(L.ptr(conv), L.ptr(cls), L.ptr(pos), L.ptr(gamma), L.ptr(beta), ctypes.c_float(eps), N, tokens,
                                      conv.shape[1], L.ptr(out), L.stream_ptr()))

@@ -147,9 +147,16 @@ class _Llava(WeightStore):
     def image_features(self, rgb_u8):
         """get_image_features (POL:448-452): hidden_states[-2] of the tower without CLS -> linear_1 -> GELU -> linear_2; fp32 [N*576, 3072]."""
         tower, proj = self.tower, self.proj
+        if rgb_u8.shape[1] != tower.R or rgb_u8.shape[2] != tower.R:
+            # POL:438 `llava_processor(images=rgb)`: HF CLIPImageProcessor resizes with Pillow (bicubic a = -0.5, fixed point, uint8), NOT with
+            # the torchvision transform of the CLIPEncoder path -- reproduced bit for bit (square observations: the centre crop is the identity)
+            if rgb_u8.shape[1] != rgb_u8.shape[2]:
+                raise ValueError("llava image path: square observations expected (shortest-edge resize + centre crop of non-square frames is not built)")
+            ops.STAGE_TAG = "tower"
+            rgb_u8 = ops.pil_bicubic_resize(rgb_u8.contiguous(), tower.R, tower.R)
         if self.precise_tower:
             from . import precise as PR
-            hid = PR.vit_forward(tower, rgb_u8, n_layers_run=len(tower.w.layers) - 1, project=False)
+            hid = PR.vit_forward(tower, rgb_u8, n_layers_run=len(tower.w.layers) - 1, project=False, fp16_pixels=True)
             x = hid[:, 1:].reshape(hid.shape[0] * 576, hid.shape[2]).contiguous()
             h = PR.linear(x, proj["w1"], proj["b1"], act=L.ACT_GELU)
             return PR.linear(h, proj["w2"], proj["b2"])

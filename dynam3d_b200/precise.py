@@ -78,19 +78,24 @@ def encoder(X, cu, n_seq, max_len, e):
     return out
 
 
-def vit_forward(eng, img_u8, n_layers_run=None, ln_post_on_patches=True, project=True):
-    """Precise counterpart of ViTEngine.forward (weights of the tower are exactly fp16, so 2-term splits)."""
+def vit_forward(eng, img_u8, n_layers_run=None, ln_post_on_patches=True, project=True, fp16_pixels=False):
+    """Precise counterpart of ViTEngine.forward (weights of the tower are exactly fp16, so 2-term splits).
+    fp16_pixels: the normalised pixels are rounded to fp16 first -- POL:438 casts the HF processor's pixel_values with `.to(device, torch.float16)`
+    whatever precision the model runs in."""
     w = eng.w
     N = img_u8.shape[0]
     T = N * w.tokens
     dev = img_u8.device
     k = 3 * w.patch * w.patch
     g = eng.R // w.patch
-    cols = torch.empty((N * g * g, w.kpad), device=dev, dtype=torch.float32)
-    m, mp = ops._hp_f32(ops.CLIP_MEAN)
-    s, sp = ops._hp_f32(ops.CLIP_STD)
-    L.check(L.lib().d3d_preprocess_im2col(L.ptr(img_u8), N, img_u8.shape[1], img_u8.shape[2], eng.R, w.patch, mp, sp, L.ptr(cols), w.kpad,
-                                          L.D3D_OUT_F32, L.stream_ptr()))
+    if fp16_pixels:
+        cols = ops.preprocess_im2col(img_u8, eng.R, w.patch, torch.float16).float()
+    else:
+        cols = torch.empty((N * g * g, w.kpad), device=dev, dtype=torch.float32)
+        m, mp = ops._hp_f32(ops.CLIP_MEAN)
+        s, sp = ops._hp_f32(ops.CLIP_STD)
+        L.check(L.lib().d3d_preprocess_im2col(L.ptr(img_u8), N, img_u8.shape[1], img_u8.shape[2], eng.R, w.patch, mp, sp, L.ptr(cols), w.kpad,
+                                              L.D3D_OUT_F32, L.stream_ptr()))
     conv = linear(cols, w.conv_w)
     X = torch.empty((T, w.width), device=dev, dtype=torch.float32)
     ops.vit_embed_ln(conv, w.cls, w.pos, w.ln_pre[0], w.ln_pre[1], 1e-5, N, w.tokens, X)

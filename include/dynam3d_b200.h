@@ -220,6 +220,11 @@ int d3d_embed_gather(const void* table, int kind, const int* ids, int T, int D, 
 int d3d_preprocess_im2col(const uint8_t* img, int N, int Hin, int Win, int R, int patch, const float* mean3_h,
                           const float* std3_h, void* out, int kpad, int kind, void* stream);
 
+/* One pass of Pillow's ImagingResample (8 bits per channel, fixed-point taps, clip8) along H (axis 0) or W (axis 1) of u8 NHWC images:
+ * the resize inside HF's CLIPImageProcessor, i.e. the LLaVA tower's input path `llava_processor(images=rgb)` (Policy_Dynam3D_VLN.py:438).
+ * bounds [out_size,2] (first source index, tap count) and kk [out_size,ksize] int32 are DEVICE tables (ops.pil_bicubic_tables). */
+int d3d_pil_resample_pass(const uint8_t* src, uint8_t* dst, int N, int H, int W, int C, int out_size, int axis, const int* bounds,
+                          const int* kk, int ksize, void* stream);
 /* ViT token assembly + ln_pre (CLIPM:223-225): out[n,0] = LN(cls+pos[0]); out[n,1+i] = LN(conv[n*(tokens-1)+i]+pos[1+i]). */
 int d3d_vit_embed_ln(const float* conv, const float* cls, const float* pos, const float* gamma, const float* beta, float eps,
                      int N, int tokens, int D, float* out, void* stream);

@@ -249,3 +249,89 @@ def lm_greedy_decode(embeds, seq_lens, P, n_layers, n_heads, max_new_tokens=20, 
         if all(done):
             break
     return outs
+
+
+# ------------------------------------------------------------------------------------------------
+# HF CLIPImageProcessor (transformers 4.46 "slow" / PIL path) -- the LLaVA tower's input path: POL:438 `llava_processor(images=rgb)`.
+# Third-party arithmetic (Pillow's ImagingResample, 8 bits per channel; transformers' rescale / normalize): restated from the published
+# algorithm and PINNED in tests/test_image_processor.py against PIL.Image.resize and transformers' own PIL-backed CLIPImageProcessorPil.
+# ------------------------------------------------------------------------------------------------
+def _pil_bicubic_filter(x):
+    a = -0.5
+    x = abs(x)
+    if x < 1.0:
+        return ((a + 2.0) * x - (a + 3.0)) * x * x + 1
+    if x < 2.0:
+        return (((x - 5) * x + 8) * x - 4) * a
+    return 0.0
+
+
+def pil_resample_tables(in_size, out_size, support=2.0, filt=_pil_bicubic_filter, precision_bits=22):
+    """Pillow `precompute_coeffs` + `normalize_coeffs_8bpc` (src/libImaging/Resample.c): per output index the first source index, the tap
+    count and the fixed-point taps.  Returns (bounds int32 [out,2], kk int32 [out,ksize])."""
+    import numpy as np
+    scale = float(np.float32(in_size) - np.float32(0.0)) / out_size  # box = (0, 0, w, h) as C floats
+    filterscale = max(scale, 1.0)
+    sup = support * filterscale
+    ksize = int(math.ceil(sup)) * 2 + 1
+    bounds = np.zeros((out_size, 2), np.int32)
+    kk = np.zeros((out_size, ksize), np.int32)
+    ss = 1.0 / filterscale
+    for xx in range(out_size):
+        center = 0.0 + (xx + 0.5) * scale
+        xmin = max(int(center - sup + 0.5), 0)   # C (int) cast: truncation
+        xmax = min(int(center + sup + 0.5), in_size) - xmin
+        k = [filt((x + xmin - center + 0.5) * ss) for x in range(xmax)]
+        ww = sum(k[i] for i in range(xmax)) if xmax else 0.0
+        ww = 0.0
+        for w in k:
+            ww += w
+        if ww != 0.0:
+            k = [w / ww for w in k]
+        for x, w in enumerate(k):
+            kk[xx, x] = int(-0.5 + w * (1 << precision_bits)) if w < 0 else int(0.5 + w * (1 << precision_bits))
+        bounds[xx] = (xmin, xmax)
+    return bounds, kk
+
+
+def pil_bicubic_resize_u8(img_u8, out_h, out_w):
+    """Image.resize((out_w, out_h), BICUBIC) of uint8 [N,H,W,C] images: horizontal pass, uint8 intermediate, vertical pass (ImagingResample)."""
+    import numpy as np
+    img = np.asarray(img_u8)
+    N, H, W, C = img.shape
+    PB = 22
+
+    def one_pass(src, axis, out_size):
+        bounds, kk = pil_resample_tables(src.shape[axis], out_size)
+        src = np.moveaxis(src, axis, 0).astype(np.int64)  # [in, ...]
+        out = np.empty((out_size,) + src.shape[1:], np.uint8)
+        for xx in range(out_size):
+            x0, n = int(bounds[xx, 0]), int(bounds[xx, 1])
+            acc = np.full(src.shape[1:], 1 << (PB - 1), np.int64)
+            for t in range(n):
+                acc += src[x0 + t] * int(kk[xx, t])
+            out[xx] = np.clip(acc >> PB, 0, 255).astype(np.uint8)
+        return np.moveaxis(out, 0, axis)
+    x = img
+    if W != out_w:
+        x = one_pass(x, 2, out_w)
+    if H != out_h:
+        x = one_pass(x, 1, out_h)
+    return x
+
+
+def hf_clip_image_process(img_u8, R=336, rnd=None):
+    """CLIPImageProcessor(size={'shortest_edge': R}, crop_size=R, resample=BICUBIC) on square uint8 NHWC images, followed by the cast of
+    POL:438 (`.to(device, torch.float16)`): PIL resize -> * (1/255) in float64 -> float32 -> (x - mean) / std in float32 -> fp16.
+    Returns normalised [N,3,R,R] fp32 (fp16-rounded when rnd is given)."""
+    import numpy as np
+    r = rnd or _id
+    img = np.asarray(img_u8)
+    assert img.shape[1] == img.shape[2], "square inputs (shortest-edge resize + centre crop is the identity crop then)"
+    if img.shape[1] != R:
+        img = pil_bicubic_resize_u8(img, R, R)
+    x = (img.astype(np.float64) * (1 / 255)).astype(np.float32)
+    mean = np.array([0.48145466, 0.4578275, 0.40821073], np.float32)
+    std = np.array([0.26862954, 0.26130258, 0.27577711], np.float32)
+    x = ((x - mean) / std).transpose(0, 3, 1, 2)
+    return r(torch.from_numpy(np.ascontiguousarray(x)))

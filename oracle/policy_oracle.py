@@ -9,6 +9,8 @@ Parity status: the 3D-memory part is PINNED against the reference run here; `Pol
 (needs habitat / gym / peft), so this file is a restatement of its forward anchored on the pinned sub-blocks: "parity unpinned"
 for the glue (prompt splice, projector wiring), pinned for every numerical sub-block.
 Q13: for num_of_views > 1 the LLM sees view 0's patch tokens.
+The LLaVA tower's input follows POL:438: HF CLIPImageProcessor (Pillow bicubic, nn_ops.hf_clip_image_process -- pinned against Pillow and
+transformers' own PIL-backed processor in tests/test_image_processor.py), NOT the torchvision transform of the CLIPEncoder path.
 """
 import numpy as np
 import torch
@@ -77,7 +79,9 @@ class PolicyOracle:
             v0 = b * V
             feat6 = torch.from_numpy(np.stack([info[0][v0], info[1][v0], info[2][v0], np.sin(info[3][v0]), np.cos(info[3][v0]), info[4][v0]], -1))
             patch_pos = NN.mlp_ln_gelu(feat6, self.P, "patch_position_embedding", self.rnd)
-            hid = NN.vit_forward(x[v0:v0 + 1], self.tower_sd, self.tower_layers, self.clip_heads, rnd=self.rnd,
+            # POL:438: the tower's pixel_values come from the HF processor (Pillow resize), cast to fp16 whatever the model precision
+            px = NN.hf_clip_image_process(np.asarray(obs["rgb"])[v0:v0 + 1], 336, rnd=NN.round_fp16)
+            hid = NN.vit_forward(px, self.tower_sd, self.tower_layers, self.clip_heads, rnd=self.rnd,
                                  n_layers_run=self.tower_layers - 1, return_hidden=True)[0, 1:]
             h = NN.gelu(NN.linear(hid, self.llava["multi_modal_projector.linear_1.weight"], self.llava["multi_modal_projector.linear_1.bias"], self.rnd))
             patch = NN.linear(h, self.llava["multi_modal_projector.linear_2.weight"], self.llava["multi_modal_projector.linear_2.bias"], self.rnd)

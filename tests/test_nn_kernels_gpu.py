@@ -106,3 +106,19 @@ def test_preprocess_im2col(size):
     bad = (diff > 2e-3).float().mean().item()
     assert bad <= (1e-4 if size != 336 else 0.0), bad
     assert diff.max().item() < 0.02
+
+
+def test_bicubic_resize_is_bit_identical_to_torch_cuda():
+    """a1 byte work: the resized uint8 pixels equal torch's own CUDA bicubic kernel (what torchvision's Resize, ENC:268, runs for observations on
+    the GPU) on EVERY pixel; torch's CPU kernel orders the same formula differently (<= 1e-4 of pixels flip across a .5 boundary, checked above)."""
+    from dynam3d_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    img = torch.randint(0, 256, (4, 224, 224, 3), generator=g, dtype=torch.uint8)
+    img[1] = (torch.arange(224 * 224 * 3) % 251).view(224, 224, 3).to(torch.uint8)  # smooth ramps: many exact .5 candidates
+    cols = ops.preprocess_im2col(img.cuda(), out_dtype=torch.float16).float()
+    x = F.interpolate(img.cuda().permute(0, 3, 1, 2).float(), size=(336, 336), mode="bicubic", align_corners=False).round().clamp(0, 255)
+    mean = torch.tensor(ops.CLIP_MEAN, device="cuda").view(1, 3, 1, 1); std = torch.tensor(ops.CLIP_STD, device="cuda").view(1, 3, 1, 1)
+    ref = F.unfold(((x / 255.0 - mean) / std).half().float(), 14, stride=14).transpose(1, 2).reshape(-1, 588)
+    # one uint8 step is 1/255/std ~ 0.015 in normalised units: any pixel flip would show as a difference >> the fp16 rounding of equal pixels
+    n_flip = int(((cols[:, :588] - ref).abs() > 5e-3).sum())
+    assert n_flip == 0, n_flip
