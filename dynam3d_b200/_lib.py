@@ -85,6 +85,7 @@ SIGNATURES = {
     "d3d_unproject_habitat": [_P, _P, _I, _I, _I, _FP, _FP, _FP, _F, _P, _P, _P, _P],
     "d3d_patch_3d_info": [_P, _I, _I, _I, _FP, _FP, _FP, _F, _P, _P],
     "d3d_frustum_cull": [_P, _P, _P, _P, _I, _I, _P, _I, _I, _I, _P, _F, _F, _F, _F, _F, _F, _F, _P, _P, _P],
+    "d3d_frustum_cull_batched": [_P, _I, _I, _I, _P, _I, _I, _I, _P, _F, _F, _F, _F, _F, _F, _F, _P, _I, _P, _P],
     "d3d_frustum_cull_matrix": [_P, _P, _P, _P, _I, _I, _P, _I, _I, _I, _P, _F, _F, _F, _P, _P, _P],
     "d3d_unproject_pinhole": [_P, _I, _I, _I, _P, _I, _I, _IP, _IP, _F, _F, _F, _P, _P, _P, _P, _P],
     "d3d_knn3d": [_P, _I, _P, _I, _I, _P, _P, _P],
@@ -123,7 +124,7 @@ SIGNATURES = {
     "d3d_mlp_ln_gelu": [_P, _P, _L, _I, _P, _P, _P, _L, _P],
     "d3d_pool_tokens": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, ctypes.c_size_t, _P, _P],
     "d3d_ffh_create": [_I, _I, _F], "d3d_ffh_destroy": [_P], "d3d_ffh_reset": [_P, _I], "d3d_ffh_pop": [_P, _I],
-    "d3d_ffh_counts": [_P, _I, _P], "d3d_ffh_cull": [_P, _I, _P, _L, _P, _P, _P, _P], "d3d_ffh_set_tree": [_P],
+    "d3d_ffh_counts": [_P, _I, _P], "d3d_ffh_cull": [_P, _I, _P, _L, _P, _P, _P, _P], "d3d_ffh_cull_list": [_P, _I, _P, _L, _P, _P, _P, _P], "d3d_ffh_set_tree": [_P],
     "d3d_ffh_begin_view": [_P] * 3 + [_I] + [_P] * 11,
     "d3d_ffh_begin_step": [_P] * 3 + [_I, _I] + [_P] * 9, "d3d_ffh_begin_view_refs": [_P, _I, _P],
     "d3d_ff_view_pre": [_P, _I, _P, _P, _P, _P, _P, _P, _P], "d3d_ff_view_post": [_P, _P, _P, _P, _P, _P], "d3d_ff_run_deferred": [_P, _P, _P],

@@ -57,6 +57,7 @@ struct Episode {
   std::vector<i64> p2i;          // patch id -> instance id, -1 = not a key
   i64 n_patch = 0, n_p2i = 0;
   OMap i2p;
+  std::vector<unsigned char> gone;  // scratch flags of the cull (all zero between calls)
   std::vector<unsigned char> inst_alive;
   std::vector<float> inst_pos;   // host mirror [n_inst*3]
   i64 n_inst = 0;
@@ -318,26 +319,32 @@ extern "C" int d3d_ffh_counts(void* h, int b, int64_t* counts) {
   return 0;
 }
 
-// FF:362-393.  mask [n_patch] (1 = culled now).  dead_inst / dead_zone must hold n_inst / n_zone entries.
-extern "C" int d3d_ffh_cull(void* h, int b, const uint8_t* mask, int64_t n, int64_t* dead_inst, int* n_dead_inst, int64_t* dead_zone,
-                            int* n_dead_zone) {
-  FFH& H = HH(h);
-  D3D_REQUIRE(b >= 0 && b < (int)H.eps.size(), "episode index");
+// FF:362-393 for the rows culled in this step (any order).  dead_inst / dead_zone must hold n_inst / n_zone entries.
+static int cull_rows(FFH& H, int b, const int32_t* rows, int64_t n_rows, const uint8_t* mask, int64_t n_mask, int64_t* dead_inst, int* n_dead_inst,
+                     int64_t* dead_zone, int* n_dead_zone) {
   Episode& ep = H.eps[(size_t)b];
-  D3D_REQUIRE(n == ep.n_patch, "mask length != number of stored patches");
   *n_dead_inst = 0; *n_dead_zone = 0;
   std::vector<i64> owners;
-  std::vector<unsigned char> gone;
-  for (i64 r = 0; r < n; ++r) {
-    if (!mask[r]) continue;
+  std::vector<i64> hit;  // rows that were keys of the patch -> instance map
+  auto visit = [&](i64 r) {
     ep.patch_pos[(size_t)r * 3] = ep.patch_pos[(size_t)r * 3 + 1] = ep.patch_pos[(size_t)r * 3 + 2] = -10000.0f;
     const i64 own = ep.p2i[(size_t)r];  // Q2: array index used as patch id
-    if (own < 0) continue;
-    if (gone.empty()) gone.assign((size_t)n, 0);
-    gone[(size_t)r] = 1;
+    if (own < 0) return;
+    if (ep.gone.size() < (size_t)ep.n_patch) ep.gone.resize((size_t)ep.n_patch, 0);
+    ep.gone[(size_t)r] = 1;
+    hit.push_back(r);
     ep.p2i[(size_t)r] = -1;
     --ep.n_p2i;
     owners.push_back(own);
+  };
+  if (rows) {
+    for (int64_t k = 0; k < n_rows; ++k) {
+      D3D_REQUIRE(rows[k] >= 0 && rows[k] < ep.n_patch, "culled row out of range");
+      visit(rows[k]);
+    }
+  } else {
+    for (i64 r = 0; r < n_mask; ++r)
+      if (mask[r]) visit(r);
   }
   if (!owners.empty()) {
     std::sort(owners.begin(), owners.end());
@@ -346,7 +353,7 @@ extern "C" int d3d_ffh_cull(void* h, int b, const uint8_t* mask, int64_t n, int6
       auto& m = ep.i2p.at(iid);
       size_t w = 0;
       for (size_t i = 0; i < m.size(); ++i)
-        if (!gone[(size_t)m[i]]) m[w++] = m[i];
+        if (!ep.gone[(size_t)m[i]]) m[w++] = m[i];
       m.resize(w);
       if (w) continue;
       ep.i2p.erase(iid);
@@ -365,9 +372,28 @@ extern "C" int d3d_ffh_cull(void* h, int b, const uint8_t* mask, int64_t n, int6
       ep.zone_alive[(size_t)zid] = 0;
       dead_zone[(*n_dead_zone)++] = zid;
     }
+    for (i64 r : hit) ep.gone[(size_t)r] = 0;  // the scratch flags stay all-zero between calls: no O(n_patch) clear per step
   }
   ep.tree = ep.n_inst > 0;
   return 0;
+}
+
+// mask [n_patch] (1 = culled now): the per-episode form (d3d_frustum_cull / d3d_frustum_cull_matrix)
+extern "C" int d3d_ffh_cull(void* h, int b, const uint8_t* mask, int64_t n, int64_t* dead_inst, int* n_dead_inst, int64_t* dead_zone,
+                            int* n_dead_zone) {
+  FFH& H = HH(h);
+  D3D_REQUIRE(b >= 0 && b < (int)H.eps.size(), "episode index");
+  D3D_REQUIRE(n == H.eps[(size_t)b].n_patch, "mask length != number of stored patches");
+  return cull_rows(H, b, nullptr, 0, mask, n, dead_inst, n_dead_inst, dead_zone, n_dead_zone);
+}
+// rows [n] = the compacted list of d3d_frustum_cull_batched
+extern "C" int d3d_ffh_cull_list(void* h, int b, const int32_t* rows, int64_t n, int64_t* dead_inst, int* n_dead_inst, int64_t* dead_zone,
+                                 int* n_dead_zone) {
+  FFH& H = HH(h);
+  D3D_REQUIRE(b >= 0 && b < (int)H.eps.size(), "episode index");
+  D3D_REQUIRE(rows || n == 0, "rows");
+  static const int32_t none = 0;
+  return cull_rows(H, b, rows ? rows : &none, n, nullptr, 0, dead_inst, n_dead_inst, dead_zone, n_dead_zone);
 }
 extern "C" int d3d_ffh_set_tree(void* h) {
   for (auto& ep : HH(h).eps) ep.tree = ep.n_inst > 0;

@@ -180,6 +180,67 @@ __global__ void frustum_cull_kernel(float* __restrict__ xyz, float* __restrict__
   if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(n_deleted, __popc(ballot));
 }
 
+// Batched habitat cull: ALL episodes of the rank in one launch (blockIdx.y = episode), and the host no longer scans a mask over every
+// stored patch: newly culled rows are compacted on the device into del_idx[job][0 .. n_del[job]) (warp-aggregated atomics; order is
+// irrelevant to the bookkeeping, FF:362-393 visits sets) and their fp16 feature rows are zeroed by the warp that found them.
+// Per-step host work of the cull therefore scales with the number of DELETED patches, not with the 147 k patches a long rollout stores.
+__global__ void frustum_cull_batched_kernel(const d3d_cull_job* __restrict__ jobs, const float* __restrict__ depth_all, const float* __restrict__ cam_all,
+                                            CullParams p, int fts_dim, int* __restrict__ del_idx, int del_cap, int* __restrict__ n_del) {
+  const d3d_cull_job jb = jobs[blockIdx.y];
+  const int n = jb.n_patches;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (blockIdx.x * blockDim.x >= n) return;
+  float* xyz = (float*)jb.xyz;
+  const float* depth = depth_all + (size_t)blockIdx.y * p.n_views * p.H * p.W;
+  const float* cam = cam_all + (size_t)blockIdx.y * p.n_views * 5;
+  bool del = false;
+  if (i < n) {
+    const float x = xyz[(size_t)i * 3], y = xyz[(size_t)i * 3 + 1], z = xyz[(size_t)i * 3 + 2];
+    for (int v = 0; v < p.n_views && !del; ++v) {
+      const float* cm = cam + v * 5;
+      const float px = __fsub_rn(x, cm[0]), py = __fsub_rn(y, cm[1]), pz = __fsub_rn(z, cm[2]);
+      const float relx = __fsub_rn(__fmul_rn(px, cm[3]), __fmul_rn(py, cm[4]));
+      const float rely = __fadd_rn(__fmul_rn(px, cm[4]), __fmul_rn(py, cm[3]));
+      const float vx = relx, vy = -pz, vz = rely;
+      const float uh = __fadd_rn(__fmul_rn(p.fx, vx), __fmul_rn(p.cx, vz));
+      const float vh = __fadd_rn(__fmul_rn(p.fy, vy), __fmul_rn(p.cy, vz));
+      const float uf = __fdiv_rn(uh, vz), vf = __fdiv_rn(vh, vz);
+      if (!(isfinite(uf) && isfinite(vf))) continue;
+      const float ut = truncf(uf), vt = truncf(vf);
+      if (!(vz >= p.near_ && vz <= p.far_)) continue;
+      if (!(ut >= 0.0f && ut <= (float)(p.W - 1) && vt >= 0.0f && vt <= (float)(p.H - 1))) continue;
+      const int ui = (int)ut, vi = (int)vt;
+      const float cd = depth[((size_t)v * p.H + vi) * p.W + ui];
+      if (vz < __fadd_rn(cd, p.eps)) del = true;
+    }
+    if (del) {
+      xyz[(size_t)i * 3] = -10000.0f;
+      xyz[(size_t)i * 3 + 1] = -10000.0f;
+      xyz[(size_t)i * 3 + 2] = -10000.0f;
+      ((float*)jb.dir)[i] = 0.0f;
+      ((float*)jb.scale)[i] = 0.0f;
+    }
+  }
+  const unsigned ballot = __ballot_sync(0xffffffffu, del);
+  if (!ballot) return;
+  const int lane = threadIdx.x & 31;
+  int base = 0;
+  if (lane == 0) base = atomicAdd(n_del + blockIdx.y, __popc(ballot));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (del) {
+    const int pos = base + __popc(ballot & ((1u << lane) - 1));
+    if (pos < del_cap) del_idx[(size_t)blockIdx.y * del_cap + pos] = i;
+  }
+  if (jb.fts16 && fts_dim) {  // the whole warp zeroes the feature row of each culled lane (FF:358)
+    const int first = i - lane;
+    for (unsigned m = ballot; m; m &= m - 1) {
+      const int l = __ffs(m) - 1;
+      uint4* dst = reinterpret_cast<uint4*>((uint16_t*)jb.fts16 + (size_t)(first + l) * fts_dim);
+      for (int k = lane; k < fts_dim / 8; k += 32) dst[k] = make_uint4(0, 0, 0, 0);
+    }
+  }
+}
+
 // Posed-dataset form of the cull (get_frustum_mask FF:64-84 + z-test FF:349-353): cam row = [view matrix 4x4 row-major (world -> camera) |
 // intrinsics 3x3 row-major] fp32.  The two einsums are left-to-right fp32 sums of separately rounded products (oracle/geometry.py).
 __global__ void frustum_cull_matrix_kernel(float* __restrict__ xyz, float* __restrict__ dir, float* __restrict__ scale,
@@ -563,6 +624,21 @@ extern "C" int d3d_frustum_cull(float* xyz, float* dir, float* scale, void* fts1
     zero_rows_kernel<<<d3d_cdiv((long long)n_patches * 32, 256), 256, 0, st>>>((uint16_t*)fts16, mask, n_patches, fts_dim);
     D3D_CHECK_LAUNCH();
   }
+  return 0;
+}
+
+extern "C" int d3d_frustum_cull_batched(const d3d_cull_job* jobs, int n_jobs, int max_patches, int fts_dim, const float* depth, int n_views, int H, int W,
+                                        const float* cam, float fx, float fy, float cx, float cy, float near_, float far_, float eps, int* del_idx,
+                                        int del_cap, int* n_del, void* stream) {
+  D3D_REQUIRE(jobs && depth && cam && del_idx && n_del && n_jobs > 0 && n_jobs <= 65535, "args");
+  D3D_REQUIRE(fts_dim % 8 == 0, "feature rows must be multiples of 16 B");
+  cudaStream_t st = (cudaStream_t)stream;
+  D3D_CHECK_CUDA(cudaMemsetAsync(n_del, 0, sizeof(int) * (size_t)n_jobs, st));
+  if (max_patches == 0) return 0;
+  CullParams p{fx, fy, cx, cy, near_, far_, eps, H, W, n_views};
+  dim3 grid(d3d_cdiv(max_patches, 256), n_jobs);
+  frustum_cull_batched_kernel<<<grid, 256, 0, st>>>(jobs, depth, cam, p, fts_dim, del_idx, del_cap, n_del);
+  D3D_CHECK_LAUNCH();
   return 0;
 }
 

@@ -539,6 +539,7 @@ class Feature_Fields(nn.Module):
                 L.check(lib.d3d_ffh_set_tree(self._h))
                 return
             masks = []
+            pp_i, fp_i, pp_z, fp_z = [], [], [], []
             if posed:
                 for b, ep in enumerate(self.eps):
                     if ep.n_patch == 0:
@@ -554,32 +555,18 @@ class Feature_Fields(nn.Module):
                                                    self._upload([cam25])[0], 0.0, 2.0, 0.1)
                     masks.append(m.to("cpu", non_blocking=True))
             else:
-                depth = self._as_dev(batch_depth, torch.float32).contiguous()
-                cams = np.concatenate([ops.camera_rows(batch_position[b], [float(batch_heading[b]) + (ix * (-math.pi / 6) if self.q7_fix else 0.0)
-                                                                          for ix in range(V)]) for b in range(self.batch_size)], 0)  # Q7
-                cam_d = self._upload([cams])[0]
+                self._cull_habitat(batch_depth, batch_position, batch_heading, V, pp_i, fp_i, pp_z, fp_z)
+            if posed:
+                torch.cuda.current_stream().synchronize()
+                nd = (ctypes.c_int * 2)()
                 for b, ep in enumerate(self.eps):
-                    if ep.n_patch == 0:
-                        masks.append(None)
+                    if masks[b] is None:
                         continue
-                    m, _ = ops.frustum_cull(ep.patch_pos.t, ep.patch_dir.t, ep.patch_scale.t, ep.patch_fts.t, ep.n_patch, depth[b], cam_d[b * V:(b + 1) * V],
-                                            self.args.input_hfov, self.args.input_vfov, 0.0, self.args.deleted_frustum_distance, 0.1)
-                    masks.append(m.to("cpu", non_blocking=True))
-            torch.cuda.current_stream().synchronize()
-            pp_i, fp_i, pp_z, fp_z = [], [], [], []
-            nd = (ctypes.c_int * 2)()
-            for b, ep in enumerate(self.eps):
-                if masks[b] is None:
-                    continue
-                mk = masks[b].numpy()
-                di = np.zeros(max(ep.n_inst, 1), np.int64); dz = np.zeros(max(ep.n_zone, 1), np.int64)
-                L.check(lib.d3d_ffh_cull(self._h, b, mk.ctypes.data, ep.n_patch, di.ctypes.data, ctypes.addressof(nd), dz.ctypes.data,
-                                         ctypes.addressof(nd) + 4))
-                if nd[0]:
-                    pp_i.append(ep.inst_pos.t.data_ptr() + 12 * di[:nd[0]]); fp_i.append(ep.inst_fts.t.data_ptr() + 4 * D * di[:nd[0]])
-                if nd[1]:
-                    pp_z.append(ep.zone_pos.t.data_ptr() + 12 * dz[:nd[1]]); fp_z.append(ep.zone_fts.t.data_ptr() + 4 * D * dz[:nd[1]])
-                ep.tree = ep.n_inst > 0
+                    mk = masks[b].numpy()
+                    di = np.zeros(max(ep.n_inst, 1), np.int64); dz = np.zeros(max(ep.n_zone, 1), np.int64)
+                    L.check(lib.d3d_ffh_cull(self._h, b, mk.ctypes.data, ep.n_patch, di.ctypes.data, ctypes.addressof(nd), dz.ctypes.data,
+                                             ctypes.addressof(nd) + 4))
+                    self._dead_rows(ep, di, dz, nd, pp_i, fp_i, pp_z, fp_z)
             # tombstone dead instance / zone slots on the device (FF:378-379, 392-393): one batched scatter per tensor kind
             rows_p, rows_f = pp_i + pp_z, fp_i + fp_z
             if rows_p:
@@ -588,6 +575,64 @@ class Feature_Fields(nn.Module):
                 pp_d, fp_d, zi_d = self._upload([pp, fp, np.zeros(len(pp), np.int32)])
                 L.check(lib.d3d_scatter_rows_ptr(L.ptr(const[0]), 3, L.ptr(zi_d), L.ptr(pp_d), len(pp), 3, L.stream_ptr()))
                 L.check(lib.d3d_scatter_rows_ptr(L.ptr(const[1]), D, L.ptr(zi_d), L.ptr(fp_d), len(pp), D, L.stream_ptr()))
+
+    @staticmethod
+    def _dead_rows(ep, di, dz, nd, pp_i, fp_i, pp_z, fp_z):
+        if nd[0]:
+            pp_i.append(ep.inst_pos.t.data_ptr() + 12 * di[:nd[0]]); fp_i.append(ep.inst_fts.t.data_ptr() + 4 * D * di[:nd[0]])
+        if nd[1]:
+            pp_z.append(ep.zone_pos.t.data_ptr() + 12 * dz[:nd[1]]); fp_z.append(ep.zone_fts.t.data_ptr() + 4 * D * dz[:nd[1]])
+        ep.tree = ep.n_inst > 0
+
+    _CULL_JOB = np.dtype([("xyz", "<u8"), ("dir", "<u8"), ("scale", "<u8"), ("fts", "<u8"), ("n", "<i4"), ("pad", "<i4")])
+    _CULL_HEAD = 2048  # culled rows per episode fetched with the counts in ONE copy (a step rarely culls more; a second copy handles the rest)
+
+    def _cull_habitat(self, batch_depth, batch_position, batch_heading, V, pp_i, fp_i, pp_z, fp_z):
+        """Habitat cull of all episodes: one kernel launch, device-side compaction of the culled rows, host bookkeeping over the culled rows
+        only (csrc/geometry.cu: frustum_cull_batched_kernel; csrc/ff_host.cu: d3d_ffh_cull_list)."""
+        lib = L.lib()
+        B = self.batch_size
+        depth = self._as_dev(batch_depth, torch.float32).contiguous()
+        H, W = depth.shape[-2], depth.shape[-1]
+        cams = np.concatenate([ops.camera_rows(batch_position[b], [float(batch_heading[b]) + (ix * (-math.pi / 6) if self.q7_fix else 0.0)
+                                                                  for ix in range(V)]) for b in range(B)], 0)  # Q7
+        jobs = np.zeros(B, self._CULL_JOB)
+        for b, ep in enumerate(self.eps):
+            jobs[b] = (ep.patch_pos.t.data_ptr(), ep.patch_dir.t.data_ptr(), ep.patch_scale.t.data_ptr(), ep.patch_fts.t.data_ptr(), ep.n_patch, 0)
+        max_n = max(ep.n_patch for ep in self.eps)
+        cb = getattr(self, "_cull_buf", None)
+        if cb is None or cb["idx"].shape[0] != B or cb["idx"].shape[1] < max_n:
+            cap = max(self._CULL_HEAD, 1 << (max_n - 1).bit_length())
+            cb = self._cull_buf = {"idx": torch.empty((B, cap), device=self.device, dtype=torch.int32),
+                                   "cnt": torch.zeros((B,), device=self.device, dtype=torch.int32),
+                                   "idx_h": torch.empty((B, self._CULL_HEAD), dtype=torch.int32).pin_memory(),
+                                   "cnt_h": torch.empty((B,), dtype=torch.int32).pin_memory()}
+        cap = cb["idx"].shape[1]
+        jobs_d, cam_d = self._upload([jobs.view(np.uint8).reshape(-1), cams])
+        fx = float(np.float32(W / np.tan(np.deg2rad(self.args.input_hfov) / 2.0) / 2.0))
+        fy = float(np.float32(H / np.tan(np.deg2rad(self.args.input_vfov) / 2.0) / 2.0))
+        f = ctypes.c_float
+        with ops._Rec("frustum_cull", "hbm", sum(ep.n_patch for ep in self.eps) * 12 + B * V * H * W * 4):  # 12 B xyz per stored patch + depth maps
+            L.check(lib.d3d_frustum_cull_batched(L.ptr(jobs_d), B, max_n, D, L.ptr(depth), V, H, W, L.ptr(cam_d), f(fx), f(fy), f(W / 2.0), f(H / 2.0),
+                                                 f(0.0), f(self.args.deleted_frustum_distance), f(0.1), L.ptr(cb["idx"]), cap, L.ptr(cb["cnt"]),
+                                                 L.stream_ptr()))
+        cb["cnt_h"].copy_(cb["cnt"], non_blocking=True)
+        cb["idx_h"].copy_(cb["idx"][:, : self._CULL_HEAD], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        cnt = cb["cnt_h"].numpy()
+        nd = (ctypes.c_int * 2)()
+        for b, ep in enumerate(self.eps):
+            n = int(cnt[b])
+            if n == 0:
+                ep.tree = ep.n_inst > 0
+                L.check(lib.d3d_ffh_cull_list(self._h, b, None, 0, None, ctypes.addressof(nd), None, ctypes.addressof(nd) + 4))
+                continue
+            rows = cb["idx_h"][b, :n].numpy() if n <= self._CULL_HEAD else cb["idx"][b, :n].cpu().numpy()
+            rows = np.ascontiguousarray(rows)
+            di = np.zeros(max(ep.n_inst, 1), np.int64); dz = np.zeros(max(ep.n_zone, 1), np.int64)
+            L.check(lib.d3d_ffh_cull_list(self._h, b, rows.ctypes.data, n, di.ctypes.data, ctypes.addressof(nd), dz.ctypes.data,
+                                          ctypes.addressof(nd) + 4))
+            self._dead_rows(ep, di, dz, nd, pp_i, fp_i, pp_z, fp_z)
 
     def _tomb_rows(self):
         if self._tomb is None:

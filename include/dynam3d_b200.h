@@ -116,6 +116,16 @@ int d3d_frustum_cull(float* xyz, float* dir, float* scale, void* fts16, int n_pa
                      int n_views, int H, int W, const float* cam, float fx, float fy, float cx, float cy, float near_,
                      float far_, float eps, uint8_t* mask, int* n_deleted, void* stream);
 
+/* The same cull for ALL episodes of a rank in one launch, with device-side compaction of the culled row indices so that the host
+ * bookkeeping (d3d_ffh_cull_list) touches only what was deleted -- the long-horizon form (147 k stored patches per episode, FF:329-396).
+ * jobs [n_jobs] (device): per-episode pool base addresses and stored-patch count; depth [n_jobs, n_views, H, W]; cam [n_jobs, n_views, 5];
+ * del_idx [n_jobs, del_cap] int32 receives the culled rows of each episode in no particular order, n_del [n_jobs] their count
+ * (entries beyond del_cap are dropped: size del_cap >= the largest n_patches to make that impossible). */
+typedef struct { uint64_t xyz, dir, scale, fts16; int32_t n_patches; int32_t pad; } d3d_cull_job;
+int d3d_frustum_cull_batched(const d3d_cull_job* jobs, int n_jobs, int max_patches, int fts_dim, const float* depth, int n_views, int H, int W,
+                             const float* cam, float fx, float fy, float cx, float cy, float near_, float far_, float eps, int* del_idx,
+                             int del_cap, int* n_del, void* stream);
+
 /* Posed-dataset form of the cull (get_frustum_mask FF:64-84, call site FF:343-344; z-test FF:349-353): cam25 [n_views,25] fp32 =
  * world->camera view matrix (4x4 row-major) followed by the intrinsics (3x3 row-major).  Same tombstoning / outputs as above. */
 int d3d_frustum_cull_matrix(float* xyz, float* dir, float* scale, void* fts16, int n_patches, int fts_dim, const float* depth,
@@ -340,7 +350,9 @@ int d3d_ffh_reset(void* h, int batch_size);                 /* FF:186-206 */
 int d3d_ffh_pop(void* h, int index);                        /* FF:210-229 */
 int d3d_ffh_counts(void* h, int b, int64_t* counts8);       /* n_patch, n_p2i, n_inst, live inst, n_zone, live zones, tree, last K */
 int d3d_ffh_cull(void* h, int b, const uint8_t* mask, int64_t n, int64_t* dead_inst, int* n_dead_inst, int64_t* dead_zone,
-                 int* n_dead_zone);                         /* FF:362-393 */
+                 int* n_dead_zone); /* Same bookkeeping from the compacted list of culled rows (d3d_frustum_cull_batched): rows [n] in any order. */
+int d3d_ffh_cull_list(void* h, int b, const int32_t* rows, int64_t n, int64_t* dead_inst, int* n_dead_inst, int64_t* dead_zone, int* n_dead_zone);
+                        /* FF:362-393 */
 int d3d_ffh_set_tree(void* h);                              /* FF:396 */
 int d3d_ffh_begin_view(void* h, const float* xyz, const int64_t* segm, int P, const int64_t* stage_off, int64_t* base_rows, int* n_seg,
                        int* seq_owner, int* members, int* cu_m, int* tok_src, int* tok_seq, int* cu_tok, int* n_ref, int* info);

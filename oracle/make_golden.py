@@ -185,8 +185,36 @@ def make_vit():
     print("wrote vit_small")
 
 
+def render_scene(seed=31):
+    """The seeded patch cloud of the renderer fixtures (4 views of a synthetic room, a few tombstones, hash features) -- inputs are
+    regenerated from seeds by the tests, only the reference's OUTPUTS are stored."""
+    ep = synth.make_episode(seed, n_steps=1, num_views=4, n_seg=16)[0]
+    d576 = G.depth_patch_grid(ep["depth"], 1, 4, q1_fix=True)[0]
+    xyz, dr, sc = [], [], []
+    for ix in range(4):
+        a, b, c = G.unproject_view_world(d576[ix], ep["position"], ep["heading"], ix)
+        xyz.append(a); dr.append(b); sc.append(c)
+    xyz, dr, sc = np.concatenate(xyz), np.concatenate(dr), np.concatenate(sc)
+    xyz[::97] = -10000.0
+    fts = synth.hash_uniform((len(xyz), 768), 5, 0.9).numpy().astype(np.float16)
+    return xyz, dr, sc, fts, ep["position"], ep["heading"] + 0.3, synth.nerf_state_dict(3)
+
+
+def make_render():
+    """a18: outputs of the reference's own `render_view_3d_patch` (PFF:494-625, habitat mode) run here through ref_shim (tinycudann replaced
+    by the documented stand-in, CPU fp16 autocast): unit-norm rendered features [144,768] (stored fp16: the reference returns fp16) and the
+    first important sample of every ray."""
+    xyz, dr, sc, fts, pos, head, P = render_scene()
+    ff = ref_shim.make_reference_pretrain_feature_fields()
+    ff.load_state_dict(P, strict=False)
+    f_ref, p_ref = ref_shim.reference_render_view(ff, xyz, dr, sc, fts, pos, head)
+    np.savez_compressed(os.path.join(OUT, "render.npz"), feature_map=f_ref.astype(np.float16), positions=p_ref.astype(np.float32))
+    print("wrote render", f_ref.shape, float(np.linalg.norm(f_ref, axis=-1).max()))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    make_render()
     make_geometry()
     make_posed()
     make_vit()

@@ -203,3 +203,104 @@ def load_reference_clip_model_module(pretrain=False):
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
+
+
+# ------------------------------------------------------------------------------------------------
+# Pretrain renderer (a18): Dynam3D_Pretrain/src_3dff/models/feature_fields.py with a tinycudann stand-in
+# ------------------------------------------------------------------------------------------------
+PFF_PATH = os.path.join(REF_ROOT, "Dynam3D_Pretrain/src_3dff/models/feature_fields.py")
+
+
+class _TcnnNetwork(torch.nn.Module):
+    """Stand-in for `tinycudann.Network` with otype CutlassMLP (PFF:221-243; tinycudann 2.0 is CUDA-only and absent): bias-free fully
+    connected layers, fp16 weights / activations with fp32 accumulation, LeakyReLU slope 0.01, output width padded to a multiple of 16,
+    ONE flat fp32 `params` vector holding the row-major [out, in] matrices in layer order (the published layout).  The arithmetic of
+    tinycudann itself therefore stays unpinned; everything AROUND it in render_view_3d_patch is the reference's own code."""
+
+    def __init__(self, n_input_dims, n_output_dims, network_config, seed=1337):
+        super().__init__()
+        assert network_config["otype"] == "CutlassMLP"
+        self.n_in, self.n_out = int(n_input_dims), int(n_output_dims)
+        self.width, self.n_hidden = int(network_config["n_neurons"]), int(network_config["n_hidden_layers"])
+        self.act, self.out_act = network_config["activation"], network_config["output_activation"]
+        pad = (self.n_out + 15) // 16 * 16
+        self.dims = [(self.width, self.n_in)] + [(self.width, self.width)] * (self.n_hidden - 1) + [(pad, self.width)]
+        n = sum(o * i for o, i in self.dims)
+        g = torch.Generator().manual_seed(seed)
+        self.params = torch.nn.Parameter((torch.rand(n, generator=g) * 2 - 1) * (3.0 / self.width) ** 0.5)
+
+    def forward(self, x):
+        h = x.to(torch.float16).to(torch.float32)
+        off = 0
+        for li, (o, i) in enumerate(self.dims):
+            w = self.params[off: off + o * i].view(o, i).to(torch.float16).to(torch.float32)
+            off += o * i
+            h = h @ w.t()
+            last = li == len(self.dims) - 1
+            act = self.out_act if last else self.act
+            if act == "LeakyReLU":
+                h = torch.nn.functional.leaky_relu(h, 0.01)
+            else:
+                assert act == "None", act
+            h = h.to(torch.float16).to(torch.float32)
+        return h[:, : self.n_out].to(torch.float16)
+
+
+_PFF_MODULE = None
+
+
+def load_reference_pretrain_ff_module():
+    """Exec the reference Pretrain feature_fields.py unmodified, with stand-ins for tinycudann / torch_kdtree / open3d / configargparse / FastSAM."""
+    global _PFF_MODULE
+    if _PFF_MODULE is not None:
+        return _PFF_MODULE
+    _install_stubs()
+    _patch_cuda_probe()
+    if "tinycudann" not in sys.modules:
+        m = types.ModuleType("tinycudann")
+        m.Network = _TcnnNetwork
+        sys.modules["tinycudann"] = m
+    for name in ("src_3dff", "src_3dff.models"):
+        if name not in sys.modules:
+            pkg = types.ModuleType(name)
+            pkg.__path__ = []
+            sys.modules[name] = pkg
+    if "src_3dff.models.fastsam" not in sys.modules:
+        sys.modules["src_3dff.models.fastsam"] = sys.modules["vlnce_baselines.models.fastsam"]
+    with open(PFF_PATH, "r") as f:
+        src = f.read()
+    mod = types.ModuleType("ref_pretrain_feature_fields")
+    mod.__file__ = PFF_PATH
+    exec(compile(src, PFF_PATH, "exec"), mod.__dict__)
+    _PFF_MODULE = mod
+    return mod
+
+
+def make_reference_pretrain_feature_fields(batch_size=1, seed=0):
+    mod = load_reference_pretrain_ff_module()
+    argv = sys.argv
+    sys.argv = [argv[0]]
+    try:
+        torch.manual_seed(seed)
+        ff = mod.Feature_Fields(batch_size=batch_size, device="cpu")
+    finally:
+        sys.argv = argv
+    ff.eval()
+    return ff
+
+
+def reference_render_view(ff, patch_pos, patch_dir, patch_scale, patch_fts16, position_hab, heading):
+    """Run the reference's `render_view_3d_patch` (PFF:494-625, habitat mode) on a given patch cloud of episode 0.  The reference executes
+    this under fp16 autocast on the GPU (`.to(torch.float16)` inputs into fp32 nn.Linear weights, PFF:479-483); on CPU the same autocast
+    region is opened for float16."""
+    ff.batch_size, ff.mode = 1, "habitat"
+    ff.gt_pcd_tree = None
+    ff.global_patch_fts = [np.asarray(patch_fts16, np.float16)]
+    ff.global_patch_directions = [np.asarray(patch_dir, np.float32)]
+    ff.global_patch_scales = [np.asarray(patch_scale, np.float32)]
+    ff.global_patch_position = [torch.from_numpy(np.asarray(patch_pos, np.float32))]
+    ff.patch_tree = [ff.get_patch_tree(0)]
+    ff.sampled_rays = ff.get_rays_habitat()
+    with torch.no_grad(), torch.autocast("cpu", dtype=torch.float16):
+        fts, pos, _ = ff.render_view_3d_patch(batch_position=[np.asarray(position_hab, np.float32).copy()], batch_heading=[float(heading)])
+    return fts[0].reshape(-1, fts.shape[-1]).float().numpy(), pos[0].reshape(-1, 3).float().numpy()

@@ -2,12 +2,16 @@
 (Dynam3D_Pretrain/src_3dff/models/feature_fields.py = PFF: get_rays_habitat 408-422, raw2feature 446-474,
 patch_to_nerf_encode 477-491, render_view_3d_patch 494-625).
 
-Parity status: UNPINNED.  The reference module imports `tinycudann` (pinned 2.0, installed from NVlabs/tiny-cuda-nn HEAD,
-environment.yml:290; absent here and CUDA-only), so it cannot be executed in this container; `tcnn.Network(CutlassMLP)` is restated
-from its published behaviour: bias-free fully-connected layers, fp16 weights / activations with fp32 accumulation,
+Parity status: PINNED against the reference's own `render_view_3d_patch`, executed here through oracle/ref_shim.py (unmodified source, CPU,
+fp16 autocast) -- tests/test_oracle_vs_reference.py::test_render_oracle_matches_reference_renderer and the stored outputs in
+tests/golden/render.npz: rendered unit-norm features agree to 8e-5, the selected sample positions are bit-equal on every ray that has a
+neighbour within the search radius.  The one piece that stays UNPINNED is `tinycudann` itself (pinned 2.0, installed from
+NVlabs/tiny-cuda-nn HEAD, environment.yml:290; CUDA-only and absent here): `tcnn.Network(CutlassMLP)` is restated -- in the shim and
+below -- from its published behaviour: bias-free fully-connected layers, fp16 weights / activations with fp32 accumulation,
 LeakyReLU slope 0.01, output width padded to a multiple of 16, one flat `params` vector holding the row-major [out, in]
 matrices in layer order.  Everything else follows the reference source line by line, including the in-place aliasing at
-PFF:598-599 (y' is computed from the already rotated x').  torch.topk's tie order is unspecified; we take the lowest index.
+PFF:598-599 (y' is computed from the already rotated x').  torch.topk's tie order is unspecified (rays without any neighbour tie over all
+501 samples; every input of such a ray is masked, so its feature does not depend on the choice); we take the lowest index.
 """
 import math
 

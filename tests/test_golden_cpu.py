@@ -63,3 +63,17 @@ def test_feature_fields_oracle_vs_reference_trajectory(path):
         assert np.allclose(e["batch_zone_fts"][0].sum(-1), g["zone_fts_sum"], atol=2e-3)
         if "knn_idx" in g:
             assert np.array_equal(r["knn"][1], g["knn_idx"]) and np.array_equal(r["merge"][0].astype(np.uint8), g["merge"])
+
+
+def test_render_oracle_vs_reference_renderer_output():
+    """a18: oracle/render_oracle.py vs the stored output of the reference's own render_view_3d_patch (tests/golden/render.npz)."""
+    from oracle import nn_ops as NN
+    from oracle import render_oracle as RO
+    from oracle.make_golden import render_scene
+    z = np.load(os.path.join(GOLD, "render.npz"))
+    xyz, dr, sc, fts, pos, head, P = render_scene()
+    want = RO.render_view_3d_patch(P, xyz, dr, sc, fts, pos, head, rnd=NN.round_fp16)
+    valid = (want["idx"] >= 0).any(-1).any(-1)
+    assert valid.sum() > 100
+    assert np.array_equal(z["positions"][valid], want["positions"][valid])
+    assert np.abs(z["feature_map"].astype(np.float32) - want["feature_map"]).max() < 1e-3  # stored as fp16 (the reference's output dtype)

@@ -84,3 +84,21 @@ def test_posed_kernels_vs_reference_vectors():
     mask, _ = ops.frustum_cull_matrix(dev(z["cull_pts"].copy()), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda"), None, n,
                                       dev((depth[1].astype(np.float32) / 1000.0).astype(np.float32)[None]), dev(cam25))
     assert (mask.cpu().numpy().astype(bool) != want).sum() <= 1  # torch's CPU einsum may contract the 4-term sums
+
+
+def test_renderer_vs_reference_renderer_output():
+    """a18 on the C ABI vs the stored output of the reference's own render_view_3d_patch (PFF:494-625; tests/golden/render.npz)."""
+    import os
+    from dynam3d_b200.pretrain_render import NerfRenderer
+    from oracle.make_golden import render_scene
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "render.npz"))
+    xyz, dr, sc, fts, pos, head, P = render_scene()
+    ren = NerfRenderer(P)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    fmap, p, depth, aux = ren.render(dev(xyz), dev(dr), dev(sc), dev(fts), pos, head)
+    valid = (aux["idx"].cpu().numpy() >= 0).any(-1).any(-1)
+    assert valid.sum() > 100
+    assert np.array_equal(p.cpu().numpy()[valid], z["positions"][valid])  # selected samples: bit-equal wherever the ray has a neighbour
+    e = np.abs(fmap.cpu().numpy() - z["feature_map"].astype(np.float32)).max()
+    print(f"renderer vs the reference's own output: unit-norm feature err {e:.2e}")
+    assert e <= 5e-3

@@ -157,3 +157,19 @@ def test_posed_frustum_mask_matches_reference_function(seed):
     mask = G.frustum_mask_matrix(pts, depth_m, K32, M32)
     # CPU einsum may contract / reorder the 4-term sums: identical except for points within one ulp of a pixel or depth boundary
     assert (mask_ref != mask).sum() <= 2 and mask.sum() > 100
+
+
+def test_render_oracle_matches_reference_renderer():
+    """a18: the unmodified Pretrain `render_view_3d_patch` (PFF:494-625) vs oracle/render_oracle.py on the fixture scene."""
+    from oracle import nn_ops as NN
+    from oracle import render_oracle as RO
+    from oracle.make_golden import render_scene
+    xyz, dr, sc, fts, pos, head, P = render_scene()
+    ff = ref_shim.make_reference_pretrain_feature_fields()
+    ff.load_state_dict(P, strict=False)
+    f_ref, p_ref = ref_shim.reference_render_view(ff, xyz, dr, sc, fts, pos, head)
+    want = RO.render_view_3d_patch(P, xyz, dr, sc, fts, pos, head, rnd=NN.round_fp16)
+    valid = (want["idx"] >= 0).any(-1).any(-1)
+    assert valid.sum() > 100
+    assert np.array_equal(p_ref[valid], want["positions"][valid])  # rays without neighbours tie over all samples: topk order unspecified
+    assert np.abs(f_ref - want["feature_map"]).max() < 5e-4
