@@ -49,6 +49,24 @@ class FFRuntime(ctypes.Structure):
                 ("out_merge", ctypes.c_void_p), ("out_zone", ctypes.c_void_p), ("event", ctypes.c_void_p), ("max_seq", ctypes.c_int)]
 
 
+class ViTLayer(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ("ln1_g", "ln1_b", "w_qkv", "b_qkv", "w_o", "b_o", "ln2_g", "ln2_b", "w_fc", "b_fc", "w_pr", "b_pr")]
+
+
+class ViTModel(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in ("n_layers", "width", "n_heads", "patch", "tokens", "kpad", "resolution", "out_dim", "kind")] + \
+               [("conv_w", ctypes.c_void_p), ("cls", ctypes.c_void_p), ("pos", ctypes.c_void_p), ("ln_pre_g", ctypes.c_void_p), ("ln_pre_b", ctypes.c_void_p),
+                ("layers", ctypes.POINTER(ViTLayer)), ("ln_post_g", ctypes.c_void_p), ("ln_post_b", ctypes.c_void_p), ("proj", ctypes.c_void_p)]
+
+
+class ViTScratch(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ("cols", "conv", "X", "A16", "qkv", "att", "h", "out", "cu")]
+
+
+class LMScratch(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ("A16", "qkv", "att", "h", "rope_tab", "last16", "att_last", "x_last")]
+
+
 class LMLayer(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in ("rms1", "w_qkv", "w_o", "rms2", "w_gu", "w_down")]
 
@@ -103,6 +121,10 @@ SIGNATURES = {
     "d3d_embed_gather": [_P, _I, _P, _I, _I, _P, _L, _P],
     "d3d_preprocess_im2col": [_P, _I, _I, _I, _I, _I, _FP, _FP, _P, _I, _I, _P],
     "d3d_pil_resample_pass": [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P],
+    "d3d_gather_rows16": [_P, _L, _P, _P, _L, _I, _I, _P],
+    "d3d_vit_forward": [_P, _P, _I, _I, _I, _I, _I, _P, _P],
+    "d3d_phi3_prefill": [_P, _P, _I, _P, _P, _I, _I, _P, _P, _P, _L, _P, _I, _P, _P],
+    "d3d_gemm_profile_begin": [], "d3d_gemm_profile_end": [_P, _P, _P],
     "d3d_vit_embed_ln": [_P, _P, _P, _P, _P, _F, _I, _I, _I, _P, _P],
     "d3d_scatter_rows": [_P, _L, _P, _P, _L, _P, _I, _I, _P],
     "d3d_add_inplace": [_P, _P, _L, _I, _P],

@@ -109,6 +109,26 @@ class ViTEngine:
         self.h = torch.empty((T, 4 * w.width), device=dev, dtype=dt)
         self.out = torch.empty((T, w.out_dim), device=dev, dtype=dt)
         self.cu = (torch.arange(n + 1, device=dev, dtype=torch.int32) * w.tokens).contiguous()
+        self.cols = torch.empty((n * self.g2, w.kpad), device=dev, dtype=dt)
+        self._c = None
+
+    def _c_model(self):
+        """(d3d_vit_model, d3d_vit_scratch) for the one-call forward (csrc/forward_host.cu); rebuilt when the scratch was re-allocated."""
+        if self._c is None:
+            w = self.w
+            arr = (L.ViTLayer * len(w.layers))()
+            for i, p in enumerate(w.layers):
+                arr[i] = L.ViTLayer(p["ln1"][0].data_ptr(), p["ln1"][1].data_ptr(), p["w_qkv"].data_ptr(), p["b_qkv"].data_ptr(), p["w_o"].data_ptr(),
+                                    p["b_o"].data_ptr(), p["ln2"][0].data_ptr(), p["ln2"][1].data_ptr(), p["w_fc"].data_ptr(), p["b_fc"].data_ptr(),
+                                    p["w_pr"].data_ptr(), p["b_pr"].data_ptr())
+            m = L.ViTModel(len(w.layers), w.width, self.H, w.patch, w.tokens, w.kpad, self.R, w.out_dim, L.kind_of(w.dtype), w.conv_w.data_ptr(),
+                           w.cls.data_ptr(), w.pos.data_ptr(), w.ln_pre[0].data_ptr(), w.ln_pre[1].data_ptr(), arr,
+                           w.ln_post[0].data_ptr() if w.ln_post is not None else None, w.ln_post[1].data_ptr() if w.ln_post is not None else None,
+                           w.proj.data_ptr() if w.proj is not None else None)
+            sc = L.ViTScratch(self.cols.data_ptr(), self.conv.data_ptr(), self.X.data_ptr(), self.A16.data_ptr(), self.qkv.data_ptr(),
+                              self.att.data_ptr(), self.h.data_ptr(), self.out.data_ptr(), self.cu.data_ptr())
+            self._c = (m, sc, arr)
+        return self._c[0], self._c[1]
 
     def forward(self, img_u8, n_layers_run=None, ln_post_on_patches=True, project=True):
         """img_u8 [N,H,W,3] uint8 on device.  Returns (cls [N,out], patch [N,g2,out]) 16-bit views into `self.out`
@@ -119,12 +139,23 @@ class ViTEngine:
         if N > self.max_images:
             self._alloc(N)
         T = N * w.tokens
+        run = len(w.layers) if n_layers_run is None else n_layers_run
+        if ops.STAGE_PROFILE is None and self.attention == "auto" and (ln_post_on_patches or not project):
+            # the whole forward behind ONE C call (d3d_vit_forward); the per-kernel loop below remains for the per-stage profile, explicit
+            # attention implementations and the Pretrain (ln_post-less, Q8) projection
+            import ctypes
+            m, sc = self._c_model()
+            L.check(L.lib().d3d_vit_forward(ctypes.addressof(m), L.ptr(img_u8), N, img_u8.shape[1], img_u8.shape[2], run, int(bool(project)),
+                                            ctypes.addressof(sc), L.stream_ptr()))
+            if not project:
+                return self.X[:T].view(N, w.tokens, w.width)
+            o = self.out[:T].view(N, w.tokens, w.out_dim)
+            return o[:, 0], o[:, 1:]
         X, A16, qkv, att, h = self.X[:T], self.A16[:T], self.qkv[:T], self.att[:T], self.h[:T]
         cols = ops.preprocess_im2col(img_u8, self.R, w.patch, w.dtype)
         ops.gemm(cols, w.conv_w, out=self.conv[:N * self.g2])
         ops.vit_embed_ln(self.conv, w.cls, w.pos, w.ln_pre[0], w.ln_pre[1], 1e-5, N, w.tokens, X)
         Dh = w.width // self.H
-        run = len(w.layers) if n_layers_run is None else n_layers_run
         for l in range(run):
             p = w.layers[l]
             ops.layernorm(X, p["ln1"][0], p["ln1"][1], 1e-5, out16=A16)

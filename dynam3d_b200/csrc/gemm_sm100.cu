@@ -18,6 +18,8 @@
 // Replaces the cuBLAS calls behind every nn.Linear on the reference path (see include/dynam3d_b200.h).
 #include <stdlib.h>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace {
@@ -686,11 +688,49 @@ int launch_pair(const d3d_gemm_args& a, cudaStream_t st) {
 static int g_gemm_pair_mode = -1;  // -1: read D3D_GEMM_PAIR from the environment (default on), 0 off, 1 on
 extern "C" int d3d_gemm_set_pair_mode(int mode) { g_gemm_pair_mode = mode; return 0; }
 
+namespace {
+struct GemmRec { cudaEvent_t e0, e1; double flops; };
+struct GemmProf { bool on = false; std::vector<GemmRec> recs; } g_gprof;
+int gemm_dispatch(const d3d_gemm_args& a, cudaStream_t st);
+}  // namespace
+
+extern "C" int d3d_gemm_profile_begin(void) {
+  for (auto& r : g_gprof.recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  g_gprof.recs.clear();
+  g_gprof.on = true;
+  return 0;
+}
+extern "C" int d3d_gemm_profile_end(double* flops, float* ms, int* launches) {
+  g_gprof.on = false;
+  D3D_CHECK_CUDA(cudaDeviceSynchronize());
+  *flops = 0.0; *ms = 0.f; *launches = 0;
+  for (auto& r : g_gprof.recs) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) { *ms += t; *flops += r.flops; ++*launches; }
+    cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+  }
+  g_gprof.recs.clear();
+  return 0;
+}
+
 extern "C" int d3d_gemm(const d3d_gemm_args* args_h, void* stream) {
   D3D_REQUIRE(args_h != nullptr, "args");
   const d3d_gemm_args& a = *args_h;
   D3D_TRY(validate(a));
   cudaStream_t st = (cudaStream_t)stream;
+  if (!g_gprof.on) return gemm_dispatch(a, st);
+  GemmRec r{nullptr, nullptr, 2.0 * a.M * a.N * a.K};
+  D3D_CHECK_CUDA(cudaEventCreate(&r.e0));
+  D3D_CHECK_CUDA(cudaEventCreate(&r.e1));
+  D3D_CHECK_CUDA(cudaEventRecord(r.e0, st));
+  const int rc = gemm_dispatch(a, st);
+  D3D_CHECK_CUDA(cudaEventRecord(r.e1, st));
+  g_gprof.recs.push_back(r);
+  return rc;
+}
+
+namespace {
+int gemm_dispatch(const d3d_gemm_args& a, cudaStream_t st) {
   // wide tiles once there is enough work to fill the machine with them; 128-wide otherwise
   const long long tiles256 = (long long)d3d_cdiv(a.M, BM) * d3d_cdiv(a.N, 256);
   if (g_gemm_pair_mode < 0) {
@@ -702,6 +742,7 @@ extern "C" int d3d_gemm(const d3d_gemm_args* args_h, void* stream) {
   if (a.N >= 256 && tiles256 >= 2LL * d3d_num_sms()) return launch<256>(a, st);
   return launch<128>(a, st);
 }
+}  // namespace
 
 extern "C" int d3d_gemm_simt(const d3d_gemm_args* args_h, void* stream) {
   D3D_REQUIRE(args_h != nullptr, "args");

@@ -481,6 +481,24 @@ extern "C" int d3d_scatter_rows(const float* src, int64_t lds, const int* src_id
   return 0;
 }
 
+namespace {
+__global__ void gather_rows16_kernel(const uint16_t* __restrict__ src, long long lds, const int* __restrict__ idx, uint16_t* __restrict__ dst,
+                                     long long ldd, int n, int D) {
+  const int r = blockIdx.x;
+  if (r >= n) return;
+  const uint16_t* s = src + (size_t)idx[r] * lds;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) dst[(size_t)r * ldd + c] = s[c];
+}
+}  // namespace
+
+extern "C" int d3d_gather_rows16(const void* src, int64_t lds, const int* idx, void* dst, int64_t ldd, int n, int D, void* stream) {
+  if (n == 0) return 0;
+  D3D_REQUIRE(src && idx && dst, "args");
+  gather_rows16_kernel<<<n, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)src, lds, idx, (uint16_t*)dst, ldd, n, D);
+  D3D_CHECK_LAUNCH();
+  return 0;
+}
+
 extern "C" int d3d_add_inplace(float* a, const float* b, int64_t n_rows, int D, void* stream) {
   if (n_rows == 0) return 0;
   add_rows_kernel<<<d3d_cdiv(n_rows * D, 256), 256, 0, (cudaStream_t)stream>>>(a, b, n_rows, D);

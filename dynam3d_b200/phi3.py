@@ -52,6 +52,7 @@ class LMEngine:
         self.Dh = weights.hidden // n_heads
         self.eps = eps
         self.attention = attention
+        self.trim_last_layer = True  # final layer: o_proj / MLP on the last-token rows only (d3d_phi3_prefill)
         dev = weights.embed.device
         self.inv_freq = (1.0 / (rope_theta ** (torch.arange(0, self.Dh, 2, dtype=torch.float32) / self.Dh))).to(dev).contiguous()
         self._alloc(max_tokens)
@@ -63,6 +64,10 @@ class LMEngine:
         self.qkv = torch.empty((T, 3 * w.hidden), device=dev, dtype=dt)
         self.att = torch.empty((T, w.hidden), device=dev, dtype=dt)
         self.h = torch.empty((T, w.ffn), device=dev, dtype=dt)
+        self.rope_tab = torch.empty((T, self.Dh), device=dev, dtype=torch.float32)
+        self.last16 = torch.empty((64, w.hidden), device=dev, dtype=dt)
+        self.att_last = torch.empty((64, w.hidden), device=dev, dtype=dt)
+        self.x_last = torch.empty((64, w.hidden), device=dev, dtype=torch.float32)
 
     def embed(self, ids, out):
         """embed_tokens (POL:439): ids int32 [T] -> out fp32 [T, hidden]."""
@@ -82,6 +87,20 @@ class LMEngine:
             kv = getattr(self, "kv", None)
             if kv is None or kv.shape[1] < T + kv_rows:
                 self.kv = kv = torch.empty((len(w.layers), T + kv_rows, 3 * w.hidden), device=X.device, dtype=w.dtype)
+        if ops.STAGE_PROFILE is None and self.attention == "auto" and n_seq <= 64 and X.is_contiguous():
+            # the whole prefill behind ONE C call (d3d_phi3_prefill, csrc/forward_host.cu); the per-kernel loop below remains for the per-stage
+            # profile.  The final layer's o_proj / MLP run on the last-token rows only (the logits are the only output).
+            import ctypes
+            m = self._c_model()
+            sc = L.LMScratch(self.A16.data_ptr(), self.qkv.data_ptr(), self.att.data_ptr(), self.h.data_ptr(), self.rope_tab.data_ptr(),
+                             self.last16.data_ptr(), self.att_last.data_ptr(), self.x_last.data_ptr())
+            ptrs = (ctypes.c_void_p * len(w.layers))(*[self.kv[l].data_ptr() for l in range(len(w.layers))]) if kv_rows else None
+            logits = torch.empty((n_seq, w.vocab), device=X.device, dtype=torch.float32)
+            L.check(L.lib().d3d_phi3_prefill(ctypes.addressof(m), L.ptr(X), T, L.ptr(cu_seqlens), L.ptr(positions), n_seq, int(max_len), L.ptr(last_rows),
+                                             L.ptr(self.inv_freq), ctypes.cast(ptrs, ctypes.c_void_p) if kv_rows else None,
+                                             self.kv.stride(1) if kv_rows else 0, ctypes.addressof(sc), int(self.trim_last_layer), L.ptr(logits),
+                                             L.stream_ptr()))
+            return logits
         tab = ops.rope_table(positions, self.inv_freq, self.Dh)  # cos/sin per token, shared by all layers
         for li, p in enumerate(w.layers):
             if kv_rows:

@@ -220,6 +220,56 @@ int d3d_lm_decode_step(const d3d_lm_model* m_h, void* const* qkv_layers_h, int64
                        int step, const int* tokens_in, const float* inv_freq, float* x32, void* a16, void* att16, void* h16, float* rope_tab,
                        int* pos, float* logits, int* next_tokens, void* stream);
 
+/* dst[r, :D] = src[idx[r], :D] for n 16-bit rows (last-token rows of the final Phi-3 layer). */
+int d3d_gather_rows16(const void* src, int64_t lds, const int* idx, void* dst, int64_t ldd, int n, int D, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Coarse entry points: one call per transformer stack (csrc/forward_host.cu).  Bit-identical to issuing the per-kernel entries.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+  const float* ln1_g; const float* ln1_b; const void* w_qkv; const float* b_qkv; const void* w_o; const float* b_o;
+  const float* ln2_g; const float* ln2_b; const void* w_fc; const float* b_fc; const void* w_pr; const float* b_pr;
+} d3d_vit_layer;
+typedef struct {
+  int n_layers, width, n_heads, patch, tokens, kpad, resolution, out_dim;
+  int kind;                      /* D3D_F16 | D3D_BF16 */
+  const void* conv_w;            /* [width, kpad] patch embedding (conv1 14x14/14 as a GEMM) */
+  const float* cls; const float* pos; const float* ln_pre_g; const float* ln_pre_b;
+  const d3d_vit_layer* layers;   /* HOST array [n_layers] of device pointers */
+  const float* ln_post_g; const float* ln_post_b; const void* proj; /* NULL for the HF vision tower (hidden states only) */
+} d3d_vit_model;
+typedef struct {                 /* device scratch, sized for N images: T = N * tokens */
+  void* cols;                    /* [N*(tokens-1), kpad] 16-bit */
+  float* conv;                   /* [N*(tokens-1), width] */
+  float* X;                      /* [T, width] residual stream; the hidden state when project = 0 */
+  void* A16; void* qkv; void* att; void* h; void* out;   /* [T, width | 3 width | width | 4 width | out_dim] 16-bit */
+  const int* cu;                 /* [N+1] = i * tokens */
+} d3d_vit_scratch;
+/* CLIPEncoder.forward + VisionTransformer.forward (ENC:273-284, CLIPM:219-238) for N u8 NHWC images: preprocessing, patch embedding,
+ * n_layers_run residual blocks, then (project != 0) ln_post + proj into s->out [N, tokens, out_dim] (row 0 of an image = CLS), or
+ * (project == 0) the fp32 hidden state in s->X -- the LLaVA tower's hidden_states[-2] with n_layers_run = n_layers - 1 (POL:441-452). */
+int d3d_vit_forward(const d3d_vit_model* m_h, const uint8_t* img, int N, int Hin, int Win, int n_layers_run, int project,
+                    const d3d_vit_scratch* s_h, void* stream);
+
+typedef struct {                 /* device scratch for T packed tokens of n_seq sequences */
+  void* A16; void* qkv; void* att; void* h;              /* [T, hidden | 3 hidden | hidden | ffn] 16-bit (qkv unused with a KV cache) */
+  float* rope_tab;               /* [T, head_dim] */
+  void* last16;                  /* [n_seq, hidden] 16-bit */
+  void* att_last; float* x_last; /* [n_seq, hidden] 16-bit / fp32: last-token rows of the final layer */
+} d3d_lm_scratch;
+/* Prefill of llava.generate over packed inputs_embeds (POL:456-463): X [T, hidden] fp32 (overwritten: the residual stream), cu_seqlens
+ * [n_seq+1], positions [T], last_rows [n_seq] -> logits [n_seq, vocab] fp32 of every sequence's last token.  qkv_layers_h != NULL: HOST array
+ * of per-layer [>= T, ld_qkv] 16-bit buffers that keep the packed QKV matrices (K rotated) = the KV cache of d3d_lm_decode_step.
+ * trim_last_layer != 0: the final layer's o_proj / MLP run on the last-token rows only (same logits, ~2 % fewer FLOPs). */
+int d3d_phi3_prefill(const d3d_lm_model* m_h, float* X, int T, const int* cu_seqlens, const int* positions, int n_seq, int max_len,
+                     const int* last_rows, const float* inv_freq, void* const* qkv_layers_h, int64_t ld_qkv, const d3d_lm_scratch* s_h,
+                     int trim_last_layer, float* logits, void* stream);
+
+/* Device timing of every d3d_gemm launch between begin and end (CUDA events on the launch stream): total algorithmic FLOPs (2 M N K),
+ * total milliseconds and the launch count -- bench.py's `roofline` of the dominant kernel family.  end synchronises the device. */
+int d3d_gemm_profile_begin(void);
+int d3d_gemm_profile_end(double* flops, float* ms, int* launches);
+
 /* embed_tokens (POL:439): out[t, :D] = table16[ids[t], :D] as fp32. */
 int d3d_embed_gather(const void* table, int kind, const int* ids, int T, int D, float* out, int64_t ldo, void* stream);
 
