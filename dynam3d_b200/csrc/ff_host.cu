@@ -231,20 +231,24 @@ int update_episode(FFH& H, int b, const float* cen, const int* idx, const float*
   // zones (FF:693-756 / 777-812): group the instance slots by voxel, then visit the view's voxels in key order
   const float L = H.zone_len;
   const size_t NI = (size_t)ep.n_inst;
-  std::vector<std::pair<i64, int>> sc(NI);
-  for (size_t i = 0; i < NI; ++i) sc[i] = {voxel_code(&ep.inst_pos[i * 3], L), (int)i};
-  std::sort(sc.begin(), sc.end());  // (code, slot): ascending slot inside a voxel
   std::vector<i64> uniq(G);
   for (int g = 0; g < G; ++g) uniq[(size_t)g] = voxel_code(cen + g * 3, L);
   std::sort(uniq.begin(), uniq.end());
   uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+  // members of the view's voxels: ONE ascending pass over the instance slots (no sort of all slots: the memory holds thousands of them in
+  // a long rollout while a view touches a handful of voxels); ascending slot order inside a voxel, as the reference's boolean mask gives
+  std::vector<std::vector<i64>> members_of(uniq.size());
+  for (size_t i = 0; i < NI; ++i) {
+    const i64 code = voxel_code(&ep.inst_pos[i * 3], L);
+    auto it = std::lower_bound(uniq.begin(), uniq.end(), code);
+    if (it != uniq.end() && *it == code) members_of[(size_t)(it - uniq.begin())].push_back((i64)i);
+  }
   std::vector<i64> zone_ids;
   lowest_free(ep.zone_alive, ep.z2i.n_live, uniq.size(), zone_ids);
   size_t zi = 0;
-  for (i64 code : uniq) {
-    auto lo = std::lower_bound(sc.begin(), sc.end(), std::make_pair(code, -1));
-    std::vector<i64> mem;
-    for (auto it = lo; it != sc.end() && it->first == code; ++it) mem.push_back(it->second);
+  for (size_t ui = 0; ui < uniq.size(); ++ui) {
+    const i64 code = uniq[ui];
+    std::vector<i64>& mem = members_of[ui];
     float pos[3];
     auto zit = ep.zone_code_to_id.find(code);
     i64 slot;
@@ -577,8 +581,6 @@ extern "C" int d3d_ffh_finish_view(void* h, const float* res, int* sizes, int64_
   const size_t t_mg = pl.mg_members.size() + n_mg, t_zn = pl.zn_members.size() + n_zn;
   add(t_mg * 4); add(t_mg * 4); add((n_mg + 1) * 4); add(n_mg * 32); add(n_mg * 12); add(n_mg * 8); add(n_mg * 8);
   add(t_zn * 4); add(t_zn * 4); add((n_zn + 1) * 4); add(n_zn * 32); add(n_zn * 12); add(n_zn * 8); add(n_zn * 8);
-  for (int b = 0; b < B; ++b)
-    if (after[b * 3 + 2]) add((size_t)std::max<i64>(H.eps[(size_t)b].n_inst, 1) * 12);
   sizes[7] = (int)std::min<size_t>((up + 1023) / 1024, (size_t)INT32_MAX);
   return 0;
 }
@@ -913,22 +915,16 @@ extern "C" int d3d_ff_view_post(void* h, const d3d_ff_runtime* rt_p, const d3d_f
     std::vector<int> src, seq, cu;
     toks(pl.zn_len, pl.zn_members, src, seq, cu, ml_zn);
     t_zn = (int)src.size();
-    // Q5: an updated zone is embedded from its members' voxel-centre keys: one key array per episode that needs it
-    std::vector<size_t> key_off((size_t)H.eps.size(), (size_t)-1);
-    for (int i = 0; i < n_zn; ++i) {
-      const int b = pl.zn_owner[(size_t)i];
-      if (!pl.zn_keys[(size_t)i] || key_off[(size_t)b] != (size_t)-1) continue;
-      const Episode& ep = H.eps[(size_t)b];
-      std::vector<float> ka((size_t)std::max<i64>(ep.n_inst, 1) * 3);
-      D3D_TRY(d3d_ffh_zone_key_array(h, b, ka.data()));
-      key_off[(size_t)b] = sg.put(ka.data(), ka.size());
-    }
+    // Q5: an updated zone is embedded from its members' voxel-centre keys, derived on the device from the instance positions
+    // (pool_features_kernel: row 1 of the pointer table = 1 selects it, row 2 carries the voxel length as float bits)
+    int64_t len_bits = 0;
+    { const float L = H.zone_len; int32_t bits; memcpy(&bits, &L, 4); len_bits = (int64_t)(uint32_t)bits; }
     std::vector<int64_t> ptrs((size_t)4 * n_zn), fd((size_t)n_zn), pd((size_t)n_zn);
     for (int i = 0; i < n_zn; ++i) {
       const int b = pl.zn_owner[(size_t)i];
       const d3d_ff_pools& p = pools[b];
-      const int64_t xyz = pl.zn_keys[(size_t)i] ? (int64_t)(uintptr_t)sg.dev<float>(key_off[(size_t)b]) : p.inst_pos;
-      ptrs[(size_t)i] = xyz; ptrs[(size_t)n_zn + i] = xyz; ptrs[(size_t)2 * n_zn + i] = xyz; ptrs[(size_t)3 * n_zn + i] = p.inst_fts;
+      ptrs[(size_t)i] = p.inst_pos; ptrs[(size_t)n_zn + i] = pl.zn_keys[(size_t)i] ? 1 : 0; ptrs[(size_t)2 * n_zn + i] = len_bits;
+      ptrs[(size_t)3 * n_zn + i] = p.inst_fts;
       fd[(size_t)i] = p.zone_fts + 4LL * Dm * pl.zn_slot[(size_t)i];
       pd[(size_t)i] = p.zone_pos + 12LL * pl.zn_slot[(size_t)i];
     }

@@ -7,7 +7,7 @@ namespace {
 
 // feature row (16-bit, 8 wide, K padded for the tensor-core GEMM):
 //   mode 0 (patch -> instance, FF:584-591): [xyz - centre (3), |xyz|, sin(dir), cos(dir), scale, 0]
-//   mode 1 (instance -> zone,  FF:719-723): [xyz - centre (3), |xyz|, 0, 0, 0, 0]
+//   mode 1 (instance -> zone,  FF:719-723): [xyz - centre (3), |xyz|, 0, 0, 0, 0]; seq_dir[s] == 1 selects the voxel-centre keys (Q5)
 // |xyz| is the norm of the ABSOLUTE position.  Aggregate-token rows (src < 0) are zero.
 __global__ void pool_features_kernel(const long long* __restrict__ seq_xyz, const long long* __restrict__ seq_dir,
                                      const long long* __restrict__ seq_scale, const float* __restrict__ centre,
@@ -20,7 +20,16 @@ __global__ void pool_features_kernel(const long long* __restrict__ seq_xyz, cons
   if (src >= 0) {
     const int s = tok_seq[t];
     const float* xyz = reinterpret_cast<const float*>(seq_xyz[s]) + (size_t)src * 3;
-    const float x = xyz[0], y = xyz[1], z = xyz[2];
+    float x = xyz[0], y = xyz[1], z = xyz[2];
+    if (mode == 1 && seq_dir[s] == 1) {
+      // Q5 (FF:739-741): an UPDATED zone is embedded from its members' voxel-centre keys floor(p / L) * L + L / 2, computed here from the
+      // instance positions (L = float bits in seq_scale[s]) -- same fp32 expression as the host planner, no key array to build and upload
+      const float L = __int_as_float((int)seq_scale[s]);
+      const float hl = __fdiv_rn(L, 2.0f);
+      x = __fadd_rn(__fmul_rn(floorf(__fdiv_rn(x, L)), L), hl);
+      y = __fadd_rn(__fmul_rn(floorf(__fdiv_rn(y, L)), L), hl);
+      z = __fadd_rn(__fmul_rn(floorf(__fdiv_rn(z, L)), L), hl);
+    }
     f[0] = x - centre[(size_t)s * 3];
     f[1] = y - centre[(size_t)s * 3 + 1];
     f[2] = z - centre[(size_t)s * 3 + 2];

@@ -924,23 +924,12 @@ class Feature_Fields(nn.Module):
             L.check(lib.d3d_scatter_rows_ptr(L.ptr(pos_d), 3, None, L.ptr(pd_d), n_mg, 3, L.stream_ptr()))
         if n_zn:
             o = zn_owner[:n_zn]
-            xyz_ptr = ip[o].copy()
-            key_dev = None
-            if zn_keys[:n_zn].any():  # Q5: an updated zone is embedded from its members' voxel-centre keys
-                key_arrays = []
-                need = np.flatnonzero(after.reshape(B, 3)[:, 2])
-                for b in need.tolist():
-                    ka = np.zeros((max(eps[b].n_inst, 1), 3), F32)
-                    L.check(lib.d3d_ffh_zone_key_array(self._h, b, ka.ctypes.data))
-                    key_arrays.append(ka)
-                key_dev = self._upload(key_arrays)
-                kp = np.zeros(B, i64)
-                kp[need] = [t.data_ptr() for t in key_dev]
-                use = zn_keys[:n_zn] != 0
-                xyz_ptr[use] = kp[o][use]
-            ptrs = np.stack([xyz_ptr, xyz_ptr, xyz_ptr, ifp[o]])
+            # Q5: an updated zone is embedded from its members' voxel-centre keys, derived on the device from the instance positions
+            # (pool_features_kernel: row 1 of the pointer table = 1 selects it, row 2 carries the voxel length as float bits)
+            len_bits = int(np.array([self.args.zone_x_length], F32).view(np.uint32)[0])
+            ptrs = np.stack([ip[o], (zn_keys[:n_zn] != 0).astype(i64), np.full(n_zn, len_bits, i64), ifp[o]])
 
-            def zone_pass(_keep_alive=key_dev):  # the uploaded key arrays are referenced by address only: they must outlive the launch
+            def zone_pass():
                 zf, zpos_d, (fd_d, pd_d) = self._pool_pass(zn_src[:t_zn + n_zn], zn_seq[:t_zn + n_zn], zn_cu, ptrs, zn_pos[:n_zn], n_zn, ml_zn, 1, 1,
                                                            True, extra=[zfp[o] + 4 * D * zn_slot[:n_zn], zp[o] + 12 * zn_slot[:n_zn]])
                 L.check(lib.d3d_scatter_rows_ptr(L.ptr(zf), D, None, L.ptr(fd_d), n_zn, D, L.stream_ptr()))
@@ -959,7 +948,7 @@ class Feature_Fields(nn.Module):
         ids = np.zeros(max(ep.n_inst if which == 0 else ep.n_zone, 1), np.int64)  # live keys <= slots
         n = np.zeros(1, np.int64)
         L.check(L.lib().d3d_ffh_live_ids(self._h, b, which, ids.ctypes.data, n.ctypes.data))
-        return ids[: int(n[0])].tolist()
+        return ids[: int(n[0])]
 
     # ------------------------------------------------------------------ FF:818-862
     def get_environment_features(self, agent_position, agent_heading_angle, instance_distance=5.0, zone_distance=100.0):
@@ -968,27 +957,29 @@ class Feature_Fields(nn.Module):
         dev = self.device
         B = self.batch_size
         jobs = np.zeros(2 * B, _EXPORT_JOB)
-        ids_all, offs, n_rows = [], [], 0
+        ids_all, offs, n_rows, n_ids = [], [], 0, 0
         for b, ep in enumerate(self.eps):
             agent = ops.camera_rows(agent_position[b], [agent_heading_angle[b]])[0]
             for k, (which, pos, fts, radius) in enumerate(((0, ep.inst_pos.t, ep.inst_fts.t, instance_distance),
                                                            (1, ep.zone_pos.t, ep.zone_fts.t, zone_distance))):
                 ids = self._live_ids(b, which)
                 j = jobs[2 * b + k]
-                j["pos"], j["fts"], j["ids_off"], j["n_ids"] = pos.data_ptr(), fts.data_ptr(), len(ids_all), len(ids)
+                j["pos"], j["fts"], j["ids_off"], j["n_ids"] = pos.data_ptr(), fts.data_ptr(), n_ids, len(ids)
                 j["agent"], j["radius"] = agent, radius
                 offs.append(n_rows)
                 n_rows += max(len(ids), 1)
-                ids_all.extend(ids)
+                n_ids += len(ids)
+                ids_all.append(ids)
         rel = torch.empty((n_rows, 3), device=dev, dtype=torch.float32)
         out = torch.empty((n_rows, D), device=dev, dtype=torch.float32)
         for i, o in enumerate(offs):
             jobs[i]["out_rel"], jobs[i]["out_fts"] = rel.data_ptr() + 12 * o, out.data_ptr() + 4 * D * o
         cnt = torch.zeros((2 * B,), device=dev, dtype=torch.int32)
         with L.stream_scope():
-            jobs_d, ids_d = self._upload([jobs.view(np.uint8).reshape(-1), np.asarray(ids_all if ids_all else [0], np.int32)])
+            ids_np = np.concatenate(ids_all).astype(np.int32) if n_ids else np.zeros(1, np.int32)
+            jobs_d, ids_d = self._upload([jobs.view(np.uint8).reshape(-1), ids_np])
             ops.STAGE_TAG = "ff"
-            with ops._Rec("export", "hbm", len(ids_all) * (2 * (4 * D + 12) + 4)):  # every live token: position + feature read, row written
+            with ops._Rec("export", "hbm", n_ids * (2 * (4 * D + 12) + 4)):  # every live token: position + feature read, row written
                 L.check(L.lib().d3d_env_export_batched(L.ptr(jobs_d), L.ptr(ids_d), 2 * B, D, L.ptr(cnt), L.stream_ptr()))
             cnt_h = cnt.to("cpu", non_blocking=True)
             torch.cuda.current_stream().synchronize()
