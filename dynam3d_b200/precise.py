@@ -48,10 +48,16 @@ def linear(x32, w, bias=None, act=L.ACT_NONE, residual=None, out=None, w_prepare
     return ops.gemm(a, wx, out=out, bias=bias, act=act, residual=residual)
 
 
+SPLIT_ATTENTION = True  # sequences of >= 64 tokens on the tensor cores with split fp16x2 operands (csrc/attention_split.cu); False = fp32 CUDA cores
+
+
 def attention(qkv32, cu, n_seq, max_len, H, Dh, causal):
     out = torch.empty((qkv32.shape[0], H * Dh), device=qkv32.device, dtype=torch.float32)
-    L.check(L.lib().d3d_attention_f32(L.ptr(qkv32), qkv32.stride(0), L.ptr(out), out.stride(0), L.ptr(cu), n_seq, max_len, H, Dh,
-                                      int(bool(causal)), 1.0 / math.sqrt(Dh), L.stream_ptr()))
+    fn = L.lib().d3d_attention_split if (SPLIT_ATTENTION and max_len >= 64) else L.lib().d3d_attention_f32
+    work = 4.0 * (qkv32.shape[0] ** 2 / max(n_seq, 1)) * Dh * H * (0.5 if causal else 1.0) * (3.0 if fn is L.lib().d3d_attention_split else 1.0)
+    with ops._Rec("attention_precise", "tensor", work):
+        L.check(fn(L.ptr(qkv32), qkv32.stride(0), L.ptr(out), out.stride(0), L.ptr(cu), n_seq, max_len, H, Dh, int(bool(causal)),
+                   1.0 / math.sqrt(Dh), L.stream_ptr()))
     return out
 
 
@@ -83,6 +89,7 @@ def vit_forward(eng, img_u8, n_layers_run=None, ln_post_on_patches=True, project
     fp16_pixels: the normalised pixels are rounded to fp16 first -- POL:438 casts the HF processor's pixel_values with `.to(device, torch.float16)`
     whatever precision the model runs in."""
     w = eng.w
+    ops.STAGE_TAG = eng.tag
     N = img_u8.shape[0]
     T = N * w.tokens
     dev = img_u8.device
@@ -129,6 +136,7 @@ def vit_forward(eng, img_u8, n_layers_run=None, ln_post_on_patches=True, project
 def lm_prefill(eng, X, cu, positions, n_seq, max_len, last_rows):
     """Precise counterpart of LMEngine.prefill (X fp32 [T, hidden] is overwritten)."""
     w = eng.w
+    ops.STAGE_TAG = "lm"
     T = X.shape[0]
     h = torch.empty_like(X)
     for p in w.layers:
