@@ -253,8 +253,9 @@ def run_engine(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     E = args.episodes
     n_total = args.warmup + 2 * args.steps
-    parts = Dynam3D_VLN.PRECISE_PARTS if args.precise else tuple(p for p in (args.precise_parts or "").split(",") if p)
-    mode = "production" if not parts else ("precise" if set(parts) == set(Dynam3D_VLN.PRECISE_PARTS) else "precise:" + "+".join(parts))
+    parts = Dynam3D_VLN.PRECISE_DEFAULT if args.precise else tuple(p for p in (args.precise_parts or "").split(",") if p)
+    mode = "production" if not parts else ("precise" if set(parts) == set(Dynam3D_VLN.PRECISE_DEFAULT) else
+                                           ("precise:all" if set(parts) == set(Dynam3D_VLN.PRECISE_PARTS) else "precise:" + "+".join(parts)))
     net = build_engine(E, n_total, parts)
     instr = [synth.make_instruction(rank * 100 + b, INSTR_CHARS) for b in range(E)]
     steps = make_inputs(rank, n_total, E)
@@ -363,17 +364,41 @@ def run_engine(args):
                          "gemm_share_of_step": gemm_ms / ms, "gemm_launches": gemm_n},
         }
         if world == 1 and not args.no_parity:
+            if mode == "production" and not args.generate:
+                # the <= 1e-3 mode on the same engine, same workload, device-timed (split fp16x2 operands / fp32 activations in every stage whose
+                # rounding reaches the logits): a fresh rollout of the same episodes, 2 warm-up + 3 timed steps
+                net.set_precise_parts(Dynam3D_VLN.PRECISE_DEFAULT)
+                net.feature_fields.reset(E)
+                net.feature_fields.reserve(patches=n_total * VIEWS * 576, instances=4096)
+                for i in range(2):
+                    one_step(i, dev_in, gather=False)
+                torch.cuda.synchronize()
+                p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                p0.record()
+                for i in range(2, 5):
+                    one_step(i, dev_in, gather=False)
+                p1.record()
+                torch.cuda.synchronize()
+                ms_p = p0.elapsed_time(p1) / 3
+                line["precise"] = {"parts": list(Dynam3D_VLN.PRECISE_DEFAULT), "value": E / (ms_p / 1e3), "unit": "steps/s", "ms_per_step": ms_p, "steps": 3,
+                                   "warmup": 2, "cost_vs_production": ms_p / (ms / args.steps),
+                                   "note": "same engine and workload in the <= 1e-3 logit-parity mode (see parity.precise); bench.py --precise times it alone"}
             # ONE episode of this exact workload at full depth vs the CPU oracle (checker only, outside the timed regions): production is compared
-            # with the oracle that rounds at the same points AND with the pure-fp32 oracle; a precise mode with the pure-fp32 oracle
+            # with the oracle that rounds at the same points AND with the pure-fp32 oracle; the precise mode with the pure-fp32 oracle
             del net, dev_in, host_in
             torch.cuda.empty_cache()
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             from full_depth import full_depth_parity
-            r = full_depth_parity(steps=1, modes=(mode,), log=lambda *a: None)
+            modes = ("production", "precise") if mode == "production" else (mode,)
+            r = full_depth_parity(steps=1, modes=modes, log=lambda *a: None)
             m = r[mode]
             line["parity"] = {"mode": mode, "max_abs_vs_matched": m["max_abs_vs_matched"], "max_abs_vs_fp32": m["max_abs_vs_fp32"],
                               "argmax_equal": m["argmax_equal"], "discrete_state_equal": m["discrete_state_equal"], "config": r["config"],
                               "seq_lens": r["seq_lens"], "logit_absmax": r["logit_absmax"], "tolerance_north_star": 1e-3}
+            if mode == "production":
+                q = r["precise"]
+                line["parity"]["precise"] = {"parts": list(Dynam3D_VLN.PRECISE_DEFAULT), "max_abs_vs_fp32": q["max_abs_vs_fp32"],
+                                             "argmax_equal": q["argmax_equal"], "discrete_state_equal": q["discrete_state_equal"]}
             if not args.no_cpu_baseline:
                 sec = r["oracle_s_per_step"]["fp32"][0]
                 line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "steps/s", "cores": os.cpu_count() or 1, "kind": "port",
@@ -471,7 +496,7 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--episodes", type=int, default=EPISODES_PER_GPU)
     ap.add_argument("--workload", default="step", choices=["step", "long_horizon"])
-    ap.add_argument("--precise", action="store_true", help="every stage in the split-operand fp32-activation mode (<= 1e-3 vs the fp32 oracle)")
+    ap.add_argument("--precise", action="store_true", help="the <= 1e-3 mode: split-operand fp32-activation arithmetic in tower, 3D memory, projections and LM")
     ap.add_argument("--precise-parts", default=None, help="comma list out of vit,tower,ff,proj,lm (error-vs-cost curve)")
     ap.add_argument("--generate", action="store_true", help="time the whole POL:463 step: prefill + greedy decode of 20 tokens")
     ap.add_argument("--horizon", type=int, default=256)

@@ -211,6 +211,9 @@ class Dynam3D_VLN(nn.Module):
         return 1
 
     PRECISE_PARTS = ("vit", "tower", "ff", "proj", "lm")
+    # The <= 1e-3 mode: every stage whose rounding reaches the logits.  The CLIP ViT is left in fp16 -- the reference itself stores its patch
+    # features as fp16 (FF:500), and measured at full depth its split-operand version changes nothing (3.5e-4 with or without).
+    PRECISE_DEFAULT = ("tower", "ff", "proj", "lm")
 
     def set_precise_parts(self, parts):
         """Choose which stages run in the split-operand fp32-activation mode (error-vs-cost curve of DESIGN.md section 4): any subset of

@@ -4,7 +4,9 @@ the CPU oracle run on the host cores (tools/full_depth.py).
 
   production (fp16 GEMM operands = the reference's fp16 autocast, TR:385) vs the oracle that rounds at the same points:  <= 1.2e-2, same arg-max,
       identical discrete 3D-memory state (16-bit rounding-flip noise floor at 24+32 layers: measured 6.7e-3..7.8e-3 on logits of magnitude 4.7)
-  precise (split fp16x2 operands, fp32 activations) vs the pure-fp32 oracle (= the reference on CPU):  <= 1e-3  -- the north star's tolerance
+  precise (split fp16x2 operands, fp32 activations in the LLaVA tower, the 3D memory, the projections and the LM -- Dynam3D_VLN.PRECISE_DEFAULT;
+      the CLIP ViT stays fp16 like the reference's own fp16 feature store, FF:500) vs the pure-fp32 oracle (= the reference on CPU):  <= 1e-3
+      -- the north star's tolerance (measured 3.3e-4..3.5e-4)
 """
 import os
 import sys

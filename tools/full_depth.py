@@ -27,8 +27,8 @@ VIEWS, RGB, DEPTH, N_SEG, INSTR_CHARS, WEIGHT_SEED = 12, 224, 224, 16, 64, 7  # 
 
 def full_depth_parity(steps=1, clip_layers=24, lm_layers=32, modes=("production", "precise"), views=VIEWS, rgb=RGB, episode_seed=4000, log=print):
     """Runs `steps` navigation steps of one bench episode through the oracles (matched rounding + pure fp32) and then through every engine
-    mode.  `modes`: "production", "precise" (every stage precise) or "precise:<parts>" with parts a '+'-joined subset of
-    Dynam3D_VLN.PRECISE_PARTS (e.g. "precise:lm+tower").  Returns a dict with, per mode, max_abs_vs_matched (production only) /
+    mode.  `modes`: "production", "precise" (Dynam3D_VLN.PRECISE_DEFAULT: every stage but the CLIP ViT), "precise:all", or "precise:<parts>" with
+    parts a '+'-joined subset of Dynam3D_VLN.PRECISE_PARTS (e.g. "precise:lm+tower").  Returns a dict with, per mode, max_abs_vs_matched (production only) /
     max_abs_vs_fp32 (worst over the steps), argmax_equal, discrete_state_equal, engine ms per step, plus the oracle wall times."""
     from dynam3d_b200 import synth
     from dynam3d_b200.policy import Dynam3D_VLN
@@ -76,7 +76,8 @@ def full_depth_parity(steps=1, clip_layers=24, lm_layers=32, modes=("production"
         out["seq_lens"].append(want["fp32"][-1][2][0])
         out["logit_absmax"] = max(out["logit_absmax"], float(want["fp32"][-1][0].abs().max()))
     for mode in modes:
-        parts = () if mode == "production" else (Dynam3D_VLN.PRECISE_PARTS if mode == "precise" else tuple(mode.split(":", 1)[1].split("+")))
+        parts = () if mode == "production" else (Dynam3D_VLN.PRECISE_DEFAULT if mode == "precise" else
+                                                 (Dynam3D_VLN.PRECISE_PARTS if mode == "precise:all" else tuple(mode.split(":", 1)[1].split("+"))))
         net.set_precise_parts(parts)
         net.feature_fields.reset(1)
         ref_name = "matched" if mode == "production" else "fp32"
