@@ -689,9 +689,9 @@ static int g_gemm_pair_mode = -1;  // -1: read D3D_GEMM_PAIR from the environmen
 extern "C" int d3d_gemm_set_pair_mode(int mode) { g_gemm_pair_mode = mode; return 0; }
 
 namespace {
-struct GemmRec { cudaEvent_t e0, e1; double flops; };
+struct GemmRec { cudaEvent_t e0, e1; double flops; int variant; };
 struct GemmProf { bool on = false; std::vector<GemmRec> recs; } g_gprof;
-int gemm_dispatch(const d3d_gemm_args& a, cudaStream_t st);
+int gemm_dispatch(const d3d_gemm_args& a, cudaStream_t st, int* variant);
 }  // namespace
 
 extern "C" int d3d_gemm_profile_begin(void) {
@@ -703,10 +703,10 @@ extern "C" int d3d_gemm_profile_begin(void) {
 extern "C" int d3d_gemm_profile_end(double* flops, float* ms, int* launches) {
   g_gprof.on = false;
   D3D_CHECK_CUDA(cudaDeviceSynchronize());
-  *flops = 0.0; *ms = 0.f; *launches = 0;
+  for (int v = 0; v < 3; ++v) { flops[v] = 0.0; ms[v] = 0.f; launches[v] = 0; }
   for (auto& r : g_gprof.recs) {
     float t = 0.f;
-    if (cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) { *ms += t; *flops += r.flops; ++*launches; }
+    if (cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) { ms[r.variant] += t; flops[r.variant] += r.flops; ++launches[r.variant]; }
     cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
   }
   g_gprof.recs.clear();
@@ -718,19 +718,20 @@ extern "C" int d3d_gemm(const d3d_gemm_args* args_h, void* stream) {
   const d3d_gemm_args& a = *args_h;
   D3D_TRY(validate(a));
   cudaStream_t st = (cudaStream_t)stream;
-  if (!g_gprof.on) return gemm_dispatch(a, st);
-  GemmRec r{nullptr, nullptr, 2.0 * a.M * a.N * a.K};
+  int variant = 0;
+  if (!g_gprof.on) return gemm_dispatch(a, st, &variant);
+  GemmRec r{nullptr, nullptr, 2.0 * a.M * a.N * a.K, 0};
   D3D_CHECK_CUDA(cudaEventCreate(&r.e0));
   D3D_CHECK_CUDA(cudaEventCreate(&r.e1));
   D3D_CHECK_CUDA(cudaEventRecord(r.e0, st));
-  const int rc = gemm_dispatch(a, st);
+  const int rc = gemm_dispatch(a, st, &r.variant);
   D3D_CHECK_CUDA(cudaEventRecord(r.e1, st));
   g_gprof.recs.push_back(r);
   return rc;
 }
 
 namespace {
-int gemm_dispatch(const d3d_gemm_args& a, cudaStream_t st) {
+int gemm_dispatch(const d3d_gemm_args& a, cudaStream_t st, int* variant) {
   // wide tiles once there is enough work to fill the machine with them; 128-wide otherwise
   const long long tiles256 = (long long)d3d_cdiv(a.M, BM) * d3d_cdiv(a.N, 256);
   if (g_gemm_pair_mode < 0) {
@@ -738,8 +739,12 @@ int gemm_dispatch(const d3d_gemm_args& a, cudaStream_t st) {
     g_gemm_pair_mode = (e && e[0] == '0') ? 0 : 1;
   }
   // CTA pairs (cta_group::2, 256 x 256 tiles) once every pair has at least ~2 tiles
-  if (g_gemm_pair_mode == 1 && a.N >= 256 && (long long)d3d_cdiv(a.M, 2 * BM) * d3d_cdiv(a.N, 256) >= (long long)d3d_num_sms()) return launch_pair<256>(a, st);
-  if (a.N >= 256 && tiles256 >= 2LL * d3d_num_sms()) return launch<256>(a, st);
+  if (g_gemm_pair_mode == 1 && a.N >= 256 && (long long)d3d_cdiv(a.M, 2 * BM) * d3d_cdiv(a.N, 256) >= (long long)d3d_num_sms()) {
+    *variant = 0;
+    return launch_pair<256>(a, st);
+  }
+  if (a.N >= 256 && tiles256 >= 2LL * d3d_num_sms()) { *variant = 1; return launch<256>(a, st); }
+  *variant = 2;
   return launch<128>(a, st);
 }
 }  // namespace

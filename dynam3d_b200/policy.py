@@ -470,25 +470,37 @@ class Dynam3D_VLN(nn.Module):
         flat = [t for b in range(B) for t in (heads[b] + tails[b])]
         E = torch.empty((len(flat), lm.w.hidden), device=self.device, dtype=torch.float32)
         lm.embed(torch.tensor(flat, dtype=torch.int32).to(self.device, non_blocking=True), E)
-        seqs, lens, off = [], [], 0
-        for b in range(B):
-            nh, nt = len(heads[b]), len(tails[b])
-            seqs += [E[off:off + nh], patch[b], inst[b], zone[b], E[off + nh:off + nh + nt]]
-            off += nh + nt
-            lens.append(nh + n_imgs[b] + nt)
-        X = torch.cat(seqs, 0)
-        cu = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int32, device=self.device)
-        pos = torch.cat([torch.arange(n, dtype=torch.int32) for n in lens]).to(self.device)
-        last = (cu[1:] - 1).to(torch.int32).contiguous()
-        self.last_seq_lens = lens
+        offs = np.concatenate([[0], np.cumsum([len(heads[b]) + len(tails[b]) for b in range(B)])])
+        self.last_seq_lens = [len(heads[b]) + n_imgs[b] + len(tails[b]) for b in range(B)]
+
+        def run(group):
+            """Prefill (+ greedy decode) of the episodes in `group` as one packed batch."""
+            seqs, lens = [], []
+            for b in group:
+                nh, o = len(heads[b]), int(offs[b])
+                seqs += [E[o:o + nh], patch[b], inst[b], zone[b], E[o + nh:int(offs[b + 1])]]
+                lens.append(self.last_seq_lens[b])
+            X = torch.cat(seqs, 0)
+            cu = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int32, device=self.device)
+            pos = torch.cat([torch.arange(n, dtype=torch.int32) for n in lens]).to(self.device)
+            last = (cu[1:] - 1).to(torch.int32).contiguous()
+            if generate:
+                return lm.generate(X, cu, pos, len(group), max(lens), last, max_new_tokens=self.max_new_tokens, eos_ids=self.eos_token_ids)
+            if self.llava.precise_lm:
+                from . import precise as PR
+                return PR.lm_prefill(lm, X, cu, pos, len(group), max(lens), last)
+            return lm.prefill(X, cu, pos, len(group), max(lens), last)
+
         if generate:
             if self.llava.precise_lm:
                 raise NotImplementedError("the precise (split-operand) mode covers the prefill only")
-            return lm.generate(X, cu, pos, B, max(lens), last, max_new_tokens=self.max_new_tokens, eos_ids=self.eos_token_ids)
-        if self.llava.precise_lm:
-            from . import precise as PR
-            return PR.lm_prefill(lm, X, cu, pos, B, max(lens), last)
-        return lm.prefill(X, cu, pos, B, max(lens), last)
+            # the decode step takes 1..16 sequences (d3d_lm_decode_step): larger batches run in groups, each with its own KV cache
+            logits, ids = [], []
+            for g0 in range(0, B, 16):
+                lg, out = run(list(range(g0, min(B, g0 + 16))))
+                logits.append(lg); ids += out
+            return (logits[0] if len(logits) == 1 else torch.cat(logits, 0)), ids
+        return run(list(range(B)))
 
     def forward(self, observations, instructions, agent_positions, agent_heading_angles, depth_scale=(0.0, 10.0), gt_text=None,
                 delete_old_features=True, num_of_views=1, is_train=False, input_ids=None, return_logits=False):

@@ -265,10 +265,11 @@ int d3d_phi3_prefill(const d3d_lm_model* m_h, float* X, int T, const int* cu_seq
                      const int* last_rows, const float* inv_freq, void* const* qkv_layers_h, int64_t ld_qkv, const d3d_lm_scratch* s_h,
                      int trim_last_layer, float* logits, void* stream);
 
-/* Device timing of every d3d_gemm launch between begin and end (CUDA events on the launch stream): total algorithmic FLOPs (2 M N K),
- * total milliseconds and the launch count -- bench.py's `roofline` of the dominant kernel family.  end synchronises the device. */
+/* Device timing of every d3d_gemm launch between begin and end (CUDA events on the launch stream), per kernel variant
+ * [0] gemm_tcgen05_pair_kernel<256> (CTA pairs), [1] gemm_tcgen05_kernel<256>, [2] gemm_tcgen05_kernel<128>: algorithmic FLOPs (2 M N K),
+ * milliseconds and launch counts -- bench.py's `roofline` of the dominant kernel.  end synchronises the device. */
 int d3d_gemm_profile_begin(void);
-int d3d_gemm_profile_end(double* flops, float* ms, int* launches);
+int d3d_gemm_profile_end(double* flops3, float* ms3, int* launches3);
 
 /* embed_tokens (POL:439): out[t, :D] = table16[ids[t], :D] as fp32. */
 int d3d_embed_gather(const void* table, int kind, const int* ids, int T, int D, float* out, int64_t ldo, void* stream);
