@@ -139,7 +139,7 @@ class _Episode:
 
 
 class Feature_Fields(nn.Module):
-    def __init__(self, batch_size=1, device="cuda", dtype=torch.float16, q7_fix=False, precise=False):
+    def __init__(self, batch_size=1, device="cuda", dtype=torch.float16, q7_fix=False, precise=False, q10_fix=False):
         super().__init__()
         if torch.cuda.is_available():
             L.require_device()  # compute entry points raise D3DLibraryError otherwise (no CPU fallback)
@@ -147,6 +147,7 @@ class Feature_Fields(nn.Module):
         self.args = _Args()
         self.compute_dtype = dtype
         self.q7_fix = q7_fix
+        self.q10_fix = q10_fix  # False = literal: ONE history list aliased across the batch (FF:183,206); True = one list per episode
         self.precise = precise  # split-operand fp32-activation mode (dynam3d_b200/precise.py): parity evidence, not production
         width = D
         scale = width ** -0.5
@@ -181,7 +182,8 @@ class Feature_Fields(nn.Module):
         else:
             self._h = L.lib().d3d_ffh_create(batch_size, self.args.num_proposal_instances, self.args.zone_x_length)
         self.keep_target_waypoint = [None for _ in range(batch_size)]
-        self.history_actions = [["none\n"] * 4] * batch_size  # Q10: the reference aliases one list across the batch
+        # Q10: the reference aliases one list across the batch ([[...]] * B); the eval branch then rotates that shared list B times per step
+        self.history_actions = [["none\n"] * 4 for _ in range(batch_size)] if self.q10_fix else [["none\n"] * 4] * batch_size
 
     def reserve(self, patches=0, instances=0, zones=0):
         """Grow every episode's pools up front (e.g. steps x views x 576 patches) so no reallocation happens inside a rollout."""

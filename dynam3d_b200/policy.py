@@ -172,13 +172,14 @@ class _Llava(WeightStore):
 class Dynam3D_VLN(nn.Module):
     IMAGE_TOKEN = IMAGE_TOKEN
 
-    def __init__(self, observation_space=None, model_config=None, num_actions=None, device="cuda", q1_fix=False, q7_fix=False, precise=False):
+    def __init__(self, observation_space=None, model_config=None, num_actions=None, device="cuda", q1_fix=False, q7_fix=False, precise=False,
+                 q10_fix=False):
         super().__init__()
         self.device = torch.device(device)
         self.q1_fix = q1_fix
         self.precise = precise  # split-operand fp32-activation mode (precise.py): the <= 1e-3 logit-parity mode
         self._precise_proj = precise
-        self.feature_fields = Feature_Fields(batch_size=1, device=self.device, q7_fix=q7_fix, precise=precise)
+        self.feature_fields = Feature_Fields(batch_size=1, device=self.device, q7_fix=q7_fix, precise=precise, q10_fix=q10_fix)
         width = 768
         self.patch_position_embedding = _mlp_container(6, width * 4, width * 4)
         self.instance_position_embedding = _mlp_container(3, width, width)

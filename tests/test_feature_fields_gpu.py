@@ -35,6 +35,8 @@ def _compare_snap(a, b):
     dict(seed=3, n_steps=4, V=1, n_seg=16, kind="voronoi", B=1),
     dict(seed=5, n_steps=6, V=1, n_seg=48, kind="blocks", B=2),
     dict(seed=6, n_steps=2, V=12, n_seg=16, kind="voronoi", B=1),
+    dict(seed=3, n_steps=5, V=1, n_seg=16, kind="voronoi", B=1, merge_bias=0.3),   # the discriminator accepts proposals: merge path, re-encode
+    dict(seed=6, n_steps=2, V=12, n_seg=16, kind="voronoi", B=2, merge_bias=0.3),
 ])
 def test_engine_matches_oracle(cfg):
     from dynam3d_b200 import ops, synth
@@ -43,7 +45,7 @@ def test_engine_matches_oracle(cfg):
     from oracle import nn_ops as NN
     from oracle.ff_oracle import FeatureFieldsOracle
     B, V = cfg["B"], cfg["V"]
-    sd = _params(cfg["seed"], merge_bias=0.0)
+    sd = _params(cfg["seed"], merge_bias=cfg.get("merge_bias", 0.0))
     eng = Feature_Fields(batch_size=B)
     eng.load_state_dict(sd, strict=True)
     orc = FeatureFieldsOracle(sd, batch_size=B, rnd=NN.round_fp16)
@@ -78,7 +80,8 @@ def test_engine_matches_oracle(cfg):
                 assert np.array_equal(mo.astype(bool), eng._last(b)["merge"])
                 n_merge += int(mo.any(-1).sum()); n_dec += mo.size
                 margin = np.abs(lo[..., 1] - lo[..., 0]).min() if lo.size else 1.0
-                assert margin > 1e-3, "fixture has a near-tie merge decision; pick another seed"
+                if cfg.get("merge_bias", 0.0) == 0:
+                    assert margin > 1e-3, "fixture has a near-tie merge decision; pick another seed"
         env_o = orc.get_environment_features(pos, head)
         env_e = eng.get_environment_features(pos, head)
         for k in env_o:
@@ -91,3 +94,5 @@ def test_engine_matches_oracle(cfg):
                     # fp16-operand GEMMs, fp32 accumulate / LayerNorm: matched rounding points, different summation order
                     assert np.allclose(a, e, atol=3e-3, rtol=0), (t, k, np.abs(a - e).max())
     print(f"cfg {cfg}: merge decisions {n_merge}/{n_dec}")
+    if cfg.get("merge_bias", 0.0) > 0:
+        assert n_merge > 0, "a merge-biased fixture must exercise the merge path"
