@@ -257,6 +257,8 @@ def run_engine(args):
     mode = "production" if not parts else ("precise" if set(parts) == set(Dynam3D_VLN.PRECISE_DEFAULT) else
                                            ("precise:all" if set(parts) == set(Dynam3D_VLN.PRECISE_PARTS) else "precise:" + "+".join(parts)))
     net = build_engine(E, n_total, parts)
+    if args.chunked_prefill:
+        net.chunked_prefill, net.overlap_sms = True, tuple(int(x) for x in args.chunked_prefill.split(","))
     instr = [synth.make_instruction(rank * 100 + b, INSTR_CHARS) for b in range(E)]
     steps = make_inputs(rank, n_total, E)
     dev = torch.device("cuda", local)
@@ -502,6 +504,7 @@ def main():
     ap.add_argument("--precise", action="store_true", help="the <= 1e-3 mode: split-operand fp32-activation arithmetic in tower, 3D memory, projections and LM")
     ap.add_argument("--precise-parts", default=None, help="comma list out of vit,tower,ff,proj,lm (error-vs-cost curve)")
     ap.add_argument("--generate", action="store_true", help="time the whole POL:463 step: prefill + greedy decode of 20 tokens")
+    ap.add_argument("--chunked-prefill", default=None, help="SIDE,MAIN SM caps: prefill the prompt prefix on the side stream during the memory update (experiment)")
     ap.add_argument("--horizon", type=int, default=256)
     ap.add_argument("--merge-bias", type=float, default=-10.0, help="long_horizon: discriminator bias (-10 = merges off -> 4k instance slots)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -67,6 +67,11 @@ class LMScratch(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in ("A16", "qkv", "att", "h", "rope_tab", "last16", "att_last", "x_last")]
 
 
+class LMChunk(ctypes.Structure):
+    _fields_ = [("seq_start", ctypes.c_void_p), ("seq_len", ctypes.c_void_p), ("rows", ctypes.c_void_p), ("positions", ctypes.c_void_p),
+                ("q_tile_begin", ctypes.c_int), ("q_tile_end", ctypes.c_int)]
+
+
 class LMLayer(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in ("rms1", "w_qkv", "w_o", "rms2", "w_gu", "w_down")]
 
@@ -124,6 +129,10 @@ SIGNATURES = {
     "d3d_gather_rows16": [_P, _L, _P, _P, _L, _I, _I, _P],
     "d3d_vit_forward": [_P, _P, _I, _I, _I, _I, _I, _P, _P],
     "d3d_phi3_prefill": [_P, _P, _I, _P, _P, _I, _I, _P, _P, _P, _L, _P, _I, _P, _P],
+    "d3d_scatter_rows16": [_P, _L, _P, _L, _P, _I, _I, _P],
+    "d3d_attention_tc_ex": [_P, _L, _L, _P, _L, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P],
+    "d3d_phi3_prefill_chunk": [_P, _P, _I, _I, _I, _P, _P, _L, _L, _P, _P, _P, _P, _I, _P, _P],
+    "d3d_gemm_set_sm_limit": [_I],
     "d3d_gemm_profile_begin": [], "d3d_gemm_profile_end": [_P, _P, _P],
     "d3d_vit_embed_ln": [_P, _P, _P, _P, _P, _F, _I, _I, _I, _P, _P],
     "d3d_scatter_rows": [_P, _L, _P, _P, _L, _P, _I, _I, _P],

@@ -178,7 +178,7 @@ __device__ __forceinline__ uint32_t make_idesc(int kind, int m, int n, int b_mn_
 template <int D>
 __global__ void __launch_bounds__(NTHREADS, AC<D>::CTAS_PER_SM)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_qkv32, uint16_t* __restrict__ out, long long ldo,
-               const int* __restrict__ cu, int H, int causal, int kind, float scale_log2) {
+               const int* __restrict__ cu, const int* __restrict__ lens, int q_tile_begin, int H, int causal, int kind, float scale_log2) {
   using C = AC<D>;
   constexpr int TILE_BYTES = C::TILE_BYTES, SMEM_Q = C::SMEM_Q, SMEM_K = C::SMEM_K, SMEM_V = C::SMEM_V, SMEM_P = C::SMEM_P, SMEM_BAR = C::SMEM_BAR;
   constexpr int TMEM_COLS = C::TMEM_COLS;
@@ -191,8 +191,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant
   const uint32_t tmem_ptr_addr = bar0 + 96;
 
   const int seq = blockIdx.z, h = blockIdx.y;
-  const int b = cu[seq], len = cu[seq + 1] - b;
-  const int qt = causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+  // sequences are [cu[seq], cu[seq] + len): packed back to back (lens == NULL: len = cu[seq+1] - cu[seq]) or at arbitrary starts with explicit
+  // lengths (the strided KV cache of the chunked prefill); this launch computes query tiles q_tile_begin + [0, gridDim.x) of every sequence
+  const int b = cu[seq], len = lens ? lens[seq] : cu[seq + 1] - b;
+  const int qt = (causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x) + q_tile_begin;
   const int q0 = qt * BQ;
   if (q0 >= len) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -460,15 +462,18 @@ extern "C" int d3d_debug_attn_stamps(long long* host_out) {
 
 namespace {
 template <int D>
-int launch_attn_tc(const CUtensorMap& tm, const CUtensorMap& tm32, void* out, int64_t ldo, const int* cu_seqlens, int n_seq, int max_len, int H,
-                   int causal, int kind, float scale, cudaStream_t st) {
+int launch_attn_tc(const CUtensorMap& tm, const CUtensorMap& tm32, void* out, int64_t ldo, const int* cu_seqlens, const int* lens, int n_seq,
+                   int max_len, int q_tile_begin, int q_tile_end, int H, int causal, int kind, float scale, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     D3D_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, AC<D>::SMEM_BYTES));
     attr_set = true;
   }
-  dim3 grid(d3d_cdiv(max_len, BQ), H, n_seq);
-  attn_tc_kernel<D><<<grid, NTHREADS, AC<D>::SMEM_BYTES, st>>>(tm, tm32, (uint16_t*)out, ldo, cu_seqlens, H, causal, kind, scale * 1.4426950408889634f);
+  const int q_end = q_tile_end < d3d_cdiv(max_len, BQ) ? q_tile_end : d3d_cdiv(max_len, BQ);
+  if (q_end <= q_tile_begin) return 0;
+  dim3 grid(q_end - q_tile_begin, H, n_seq);
+  attn_tc_kernel<D><<<grid, NTHREADS, AC<D>::SMEM_BYTES, st>>>(tm, tm32, (uint16_t*)out, ldo, cu_seqlens, lens, q_tile_begin, H, causal, kind,
+                                                               scale * 1.4426950408889634f);
   D3D_CHECK_LAUNCH();
   return 0;
 }
@@ -476,7 +481,15 @@ int launch_attn_tc(const CUtensorMap& tm, const CUtensorMap& tm32, void* out, in
 
 extern "C" int d3d_attention_tc(const void* qkv, int64_t ld, int64_t n_rows, void* out, int64_t ldo, const int* cu_seqlens, int n_seq,
                                 int max_len, int H, int Dh, int causal, int kind, float scale, void* stream) {
+  return d3d_attention_tc_ex(qkv, ld, n_rows, out, ldo, cu_seqlens, nullptr, n_seq, max_len, 0, 1 << 30, H, Dh, causal, kind, scale, stream);
+}
+
+extern "C" int d3d_attention_tc_ex(const void* qkv, int64_t ld, int64_t n_rows, void* out, int64_t ldo, const int* seq_start, const int* seq_len,
+                                   int n_seq, int max_len, int q_tile_begin, int q_tile_end, int H, int Dh, int causal, int kind, float scale,
+                                   void* stream) {
+  const int* cu_seqlens = seq_start;
   if (n_seq == 0 || max_len == 0) return 0;
+  D3D_REQUIRE(q_tile_begin >= 0 && q_tile_end >= q_tile_begin, "query tile range");
   D3D_REQUIRE(qkv && out && cu_seqlens, "args");
   D3D_REQUIRE(Dh == 64 || Dh == 96, "tcgen05 attention is built for head_dim 64 and 96");
   D3D_REQUIRE(ld % 8 == 0 && ldo % 8 == 0 && ((uintptr_t)qkv % 16) == 0 && ((uintptr_t)out % 16) == 0, "16-byte aligned rows");
@@ -508,6 +521,7 @@ extern "C" int d3d_attention_tc(const void* qkv, int64_t ld, int64_t n_rows, voi
     d3d_set_error("cuTensorMapEncodeTiled(qkv) failed (%d)", (int)r);
     return D3D_ECUDA;
   }
-  if (Dh == 96) return launch_attn_tc<96>(tm, tm32, out, ldo, cu_seqlens, n_seq, max_len, H, causal, kind, scale, (cudaStream_t)stream);
-  return launch_attn_tc<64>(tm, tm32, out, ldo, cu_seqlens, n_seq, max_len, H, causal, kind, scale, (cudaStream_t)stream);
+  if (Dh == 96)
+    return launch_attn_tc<96>(tm, tm32, out, ldo, cu_seqlens, seq_len, n_seq, max_len, q_tile_begin, q_tile_end, H, causal, kind, scale, (cudaStream_t)stream);
+  return launch_attn_tc<64>(tm, tm32, out, ldo, cu_seqlens, seq_len, n_seq, max_len, q_tile_begin, q_tile_end, H, causal, kind, scale, (cudaStream_t)stream);
 }

@@ -90,3 +90,52 @@ extern "C" int d3d_phi3_prefill(const d3d_lm_model* m, float* X, int T, const in
   D3D_TRY(d3d_rmsnorm(X, Hd, last_rows, m->norm, m->eps, n_seq, Hd, nullptr, 0, s->last16, Hd, kind, stream));
   return gemm(s->last16, Hd, m->lm_head, Hd, logits, m->vocab, n_seq, m->vocab, Hd, kind, D3D_OUT_F32, nullptr, D3D_ACT_NONE, nullptr, 0, stream);
 }
+
+// Shared tail of a layer for compact rows: o_proj (+residual) -> rmsnorm -> gate/up + SwiGLU -> down (+residual)
+static int lm_layer_tail(const d3d_lm_model* m, const d3d_lm_layer& p, float* X, int T, const d3d_lm_scratch* s, void* stream) {
+  const int Hd = m->hidden, F = m->ffn, kind = m->kind;
+  D3D_TRY(gemm(s->att, Hd, p.w_o, Hd, X, Hd, T, Hd, Hd, kind, D3D_OUT_F32, nullptr, D3D_ACT_NONE, X, Hd, stream));
+  D3D_TRY(d3d_rmsnorm(X, Hd, nullptr, p.rms2, m->eps, T, Hd, nullptr, 0, s->A16, Hd, kind, stream));
+  D3D_TRY(gemm(s->A16, Hd, p.w_gu, Hd, s->h, F, T, 2 * F, Hd, kind, kind, nullptr, D3D_ACT_SWIGLU, nullptr, 0, stream));
+  return gemm(s->h, F, p.w_down, F, X, Hd, T, Hd, F, kind, D3D_OUT_F32, nullptr, D3D_ACT_NONE, X, Hd, stream);
+}
+
+extern "C" int d3d_phi3_prefill_chunk(const d3d_lm_model* m, float* X, int T, int n_seq, int max_len, const d3d_lm_chunk* c, void* const* cache_layers_h,
+                                      int64_t ld_cache, int64_t cache_rows, void* att_cache, const float* inv_freq, const d3d_lm_scratch* s,
+                                      const int* last_rows, int trim_last_layer, float* logits, void* stream) {
+  D3D_REQUIRE(m && X && c && cache_layers_h && att_cache && inv_freq && s && T > 0 && n_seq > 0, "args");
+  D3D_REQUIRE(c->seq_start && c->seq_len && c->rows && c->positions, "chunk tables");
+  D3D_REQUIRE(!last_rows || logits, "logits buffer");
+  const int Hd = m->hidden, F = m->ffn, kind = m->kind, H = m->n_heads, Dh = m->head_dim;
+  D3D_REQUIRE(Dh == 64 || Dh == 96, "the chunked prefill runs on the tcgen05 attention (head_dim 64 / 96)");
+  const float scale = (float)(1.0 / sqrt((double)Dh));
+  D3D_TRY(d3d_rope_table(c->positions, inv_freq, T, Dh, s->rope_tab, stream));
+  const bool trim = last_rows && trim_last_layer && n_seq <= 16 && m->n_layers > 0;
+  for (int l = 0; l < m->n_layers; ++l) {
+    const d3d_lm_layer& p = m->layers[l];
+    void* cache = cache_layers_h[l];
+    D3D_TRY(d3d_rmsnorm(X, Hd, nullptr, p.rms1, m->eps, T, Hd, nullptr, 0, s->A16, Hd, kind, stream));
+    D3D_TRY(gemm(s->A16, Hd, p.w_qkv, Hd, s->qkv, 3 * Hd, T, 3 * Hd, Hd, kind, kind, nullptr, D3D_ACT_NONE, nullptr, 0, stream));
+    D3D_TRY(d3d_rope_apply(s->qkv, 3 * Hd, s->rope_tab, T, H, Dh, kind, stream));
+    D3D_TRY(d3d_scatter_rows16(s->qkv, 3 * Hd, cache, ld_cache, c->rows, T, 3 * Hd, stream));
+    D3D_TRY(d3d_attention_tc_ex(cache, ld_cache, cache_rows, att_cache, Hd, c->seq_start, c->seq_len, n_seq, max_len, c->q_tile_begin, c->q_tile_end, H,
+                                Dh, 1, kind, scale, stream));
+    if (trim && l == m->n_layers - 1) {
+      // last-token rows only: att_last[i] = att_cache[rows[last_rows[i]]] needs a two-level index; gather the chunk's rows first
+      D3D_TRY(d3d_gather_rows16(att_cache, Hd, c->rows, s->att, Hd, T, Hd, stream));
+      D3D_TRY(d3d_gather_rows16(s->att, Hd, last_rows, s->att_last, Hd, n_seq, Hd, stream));
+      D3D_TRY(d3d_scatter_rows(X, Hd, last_rows, s->x_last, Hd, nullptr, n_seq, Hd, stream));
+      D3D_TRY(gemm(s->att_last, Hd, p.w_o, Hd, s->x_last, Hd, n_seq, Hd, Hd, kind, D3D_OUT_F32, nullptr, D3D_ACT_NONE, s->x_last, Hd, stream, true));
+      D3D_TRY(d3d_rmsnorm(s->x_last, Hd, nullptr, p.rms2, m->eps, n_seq, Hd, nullptr, 0, s->last16, Hd, kind, stream));
+      D3D_TRY(gemm(s->last16, Hd, p.w_gu, Hd, s->h, F, n_seq, 2 * F, Hd, kind, kind, nullptr, D3D_ACT_SWIGLU, nullptr, 0, stream, true));
+      D3D_TRY(gemm(s->h, F, p.w_down, F, s->x_last, Hd, n_seq, Hd, F, kind, D3D_OUT_F32, nullptr, D3D_ACT_NONE, s->x_last, Hd, stream, true));
+      D3D_TRY(d3d_rmsnorm(s->x_last, Hd, nullptr, m->norm, m->eps, n_seq, Hd, nullptr, 0, s->last16, Hd, kind, stream));
+      return gemm(s->last16, Hd, m->lm_head, Hd, logits, m->vocab, n_seq, m->vocab, Hd, kind, D3D_OUT_F32, nullptr, D3D_ACT_NONE, nullptr, 0, stream);
+    }
+    D3D_TRY(d3d_gather_rows16(att_cache, Hd, c->rows, s->att, Hd, T, Hd, stream));
+    D3D_TRY(lm_layer_tail(m, p, X, T, s, stream));
+  }
+  if (!last_rows) return 0;
+  D3D_TRY(d3d_rmsnorm(X, Hd, last_rows, m->norm, m->eps, n_seq, Hd, nullptr, 0, s->last16, Hd, kind, stream));
+  return gemm(s->last16, Hd, m->lm_head, Hd, logits, m->vocab, n_seq, m->vocab, Hd, kind, D3D_OUT_F32, nullptr, D3D_ACT_NONE, nullptr, 0, stream);
+}

@@ -602,6 +602,9 @@ int make_tmap(CUtensorMap* map, const void* base, int kind, long long rows, long
   return 0;
 }
 
+int g_gemm_sm_limit = 0;  // 0 = all SMs; otherwise persistent grids are capped (d3d_gemm_set_sm_limit)
+inline int usable_sms() { return (g_gemm_sm_limit > 0 && g_gemm_sm_limit < d3d_num_sms()) ? g_gemm_sm_limit : d3d_num_sms(); }
+
 template <int BN>
 int launch(const d3d_gemm_args& a, cudaStream_t st) {
   using C = Cfg<BN, 1>;
@@ -615,7 +618,7 @@ int launch(const d3d_gemm_args& a, cudaStream_t st) {
   D3D_TRY(make_tmap(&tmB, a.W, a.in_kind, a.N, a.K, a.ldw, BN));
   Epilogue ep{a.C, a.ldc, a.bias, a.residual, a.ldres, a.act, a.out_kind};
   const int tiles = d3d_cdiv(a.M, BM) * d3d_cdiv(a.N, BN);
-  const int grid = tiles < d3d_num_sms() ? tiles : d3d_num_sms();
+  const int grid = tiles < usable_sms() ? tiles : usable_sms();
   gemm_tcgen05_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tmA, tmB, ep, a.M, a.N, a.K, a.in_kind);
   D3D_CHECK_LAUNCH();
   return 0;
@@ -679,7 +682,8 @@ int launch_pair(const d3d_gemm_args& a, cudaStream_t st) {
   D3D_TRY(make_tmap(&tmB, a.W, a.in_kind, a.N, a.K, a.ldw, C::B_ROWS));
   Epilogue ep{a.C, a.ldc, a.bias, a.residual, a.ldres, a.act, a.out_kind};
   const int tiles = d3d_cdiv(a.M, 2 * BM) * d3d_cdiv(a.N, BN);
-  const int clusters = tiles < max_clusters ? tiles : max_clusters;
+  const int cap = max_clusters < usable_sms() / 2 ? max_clusters : usable_sms() / 2;
+  const int clusters = tiles < cap ? tiles : cap;
   gemm_tcgen05_pair_kernel<BN><<<2 * clusters, NUM_THREADS, C::SMEM_BYTES, st>>>(tmA, tmB, ep, a.M, a.N, a.K, a.in_kind);
   D3D_CHECK_LAUNCH();
   return 0;
@@ -687,6 +691,7 @@ int launch_pair(const d3d_gemm_args& a, cudaStream_t st) {
 
 static int g_gemm_pair_mode = -1;  // -1: read D3D_GEMM_PAIR from the environment (default on), 0 off, 1 on
 extern "C" int d3d_gemm_set_pair_mode(int mode) { g_gemm_pair_mode = mode; return 0; }
+extern "C" int d3d_gemm_set_sm_limit(int n) { g_gemm_sm_limit = n < 0 ? 0 : n; return 0; }
 
 namespace {
 struct GemmRec { cudaEvent_t e0, e1; double flops; int variant; };

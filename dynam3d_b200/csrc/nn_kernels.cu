@@ -482,19 +482,31 @@ extern "C" int d3d_scatter_rows(const float* src, int64_t lds, const int* src_id
 }
 
 namespace {
-__global__ void gather_rows16_kernel(const uint16_t* __restrict__ src, long long lds, const int* __restrict__ idx, uint16_t* __restrict__ dst,
-                                     long long ldd, int n, int D) {
+// dst[dst_idx ? dst_idx[r] : r] = src[src_idx ? src_idx[r] : r] for 16-bit rows of D elements (D % 8 == 0: 16-byte vectors)
+__global__ void copy_rows16_kernel(const uint4* __restrict__ src, long long lds8, const int* __restrict__ src_idx, uint4* __restrict__ dst,
+                                   long long ldd8, const int* __restrict__ dst_idx, int n, int D8) {
   const int r = blockIdx.x;
   if (r >= n) return;
-  const uint16_t* s = src + (size_t)idx[r] * lds;
-  for (int c = threadIdx.x; c < D; c += blockDim.x) dst[(size_t)r * ldd + c] = s[c];
+  const uint4* s = src + (size_t)(src_idx ? src_idx[r] : r) * lds8;
+  uint4* d = dst + (size_t)(dst_idx ? dst_idx[r] : r) * ldd8;
+  for (int c = threadIdx.x; c < D8; c += blockDim.x) d[c] = s[c];
 }
 }  // namespace
 
 extern "C" int d3d_gather_rows16(const void* src, int64_t lds, const int* idx, void* dst, int64_t ldd, int n, int D, void* stream) {
   if (n == 0) return 0;
   D3D_REQUIRE(src && idx && dst, "args");
-  gather_rows16_kernel<<<n, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)src, lds, idx, (uint16_t*)dst, ldd, n, D);
+  D3D_REQUIRE(D % 8 == 0 && lds % 8 == 0 && ldd % 8 == 0 && ((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 16) == 0, "16-byte aligned rows");
+  copy_rows16_kernel<<<n, 256, 0, (cudaStream_t)stream>>>((const uint4*)src, lds / 8, idx, (uint4*)dst, ldd / 8, nullptr, n, D / 8);
+  D3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int d3d_scatter_rows16(const void* src, int64_t lds, void* dst, int64_t ldd, const int* dst_idx, int n, int D, void* stream) {
+  if (n == 0) return 0;
+  D3D_REQUIRE(src && dst_idx && dst, "args");
+  D3D_REQUIRE(D % 8 == 0 && lds % 8 == 0 && ldd % 8 == 0 && ((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 16) == 0, "16-byte aligned rows");
+  copy_rows16_kernel<<<n, 256, 0, (cudaStream_t)stream>>>((const uint4*)src, lds / 8, nullptr, (uint4*)dst, ldd / 8, dst_idx, n, D / 8);
   D3D_CHECK_LAUNCH();
   return 0;
 }

@@ -119,6 +119,42 @@ class LMEngine:
         ops.gemm(last16, w.lm_head, out=logits)
         return logits
 
+    # ------------------------------------------------------------------ chunked prefill over a strided KV cache (d3d_phi3_prefill_chunk)
+    def chunk_cache(self, n_seq, stride):
+        """Per-layer packed-QKV cache [layers, n_seq * stride, 3*hidden] (sequence s at rows s*stride + position) and the attention scratch.
+        Zero-initialised ONCE: rows past a sequence's end are read (masked) by the attention tiles, so they must stay finite."""
+        w = self.w
+        kc = getattr(self, "kvc", None)
+        if kc is None or kc.shape[1] < n_seq * stride or getattr(self, "kvc_stride", 0) != stride:
+            dev = w.embed.device
+            self.kvc = torch.zeros((len(w.layers), n_seq * stride, 3 * w.hidden), device=dev, dtype=w.dtype)
+            self.attc = torch.zeros((n_seq * stride, w.hidden), device=dev, dtype=w.dtype)
+            self.kvc_stride = stride
+            self._kvc_ptrs = None
+        return self.kvc
+
+    def prefill_chunk(self, X, seq_start, seq_len, rows, positions, n_seq, max_len, q_tile_begin, q_tile_end, last_rows=None):
+        """One chunk of a prefill (see include/dynam3d_b200.h: d3d_phi3_prefill_chunk).  X fp32 [T, hidden] compact rows (overwritten);
+        seq_start / seq_len int32 [n_seq], rows / positions int32 [T] (device).  Returns logits [n_seq, vocab] when last_rows is given."""
+        import ctypes
+        w = self.w
+        T = X.shape[0]
+        if T > self.max_tokens:
+            self._alloc(T)
+        assert X.is_contiguous() and self.kvc is not None
+        if getattr(self, "_kvc_ptrs", None) is None:
+            self._kvc_ptrs = (ctypes.c_void_p * len(w.layers))(*[self.kvc[l].data_ptr() for l in range(len(w.layers))])
+        m = self._c_model()
+        sc = L.LMScratch(self.A16.data_ptr(), self.qkv.data_ptr(), self.att.data_ptr(), self.h.data_ptr(), self.rope_tab.data_ptr(),
+                         self.last16.data_ptr(), self.att_last.data_ptr(), self.x_last.data_ptr())
+        ch = L.LMChunk(seq_start.data_ptr(), seq_len.data_ptr(), rows.data_ptr(), positions.data_ptr(), int(q_tile_begin), int(q_tile_end))
+        logits = torch.empty((n_seq, w.vocab), device=X.device, dtype=torch.float32) if last_rows is not None else None
+        L.check(L.lib().d3d_phi3_prefill_chunk(ctypes.addressof(m), L.ptr(X), T, n_seq, int(max_len), ctypes.addressof(ch),
+                                               ctypes.cast(self._kvc_ptrs, ctypes.c_void_p), self.kvc.stride(1), self.kvc.shape[1], L.ptr(self.attc),
+                                               L.ptr(self.inv_freq), ctypes.addressof(sc), L.ptr(last_rows), int(self.trim_last_layer), L.ptr(logits),
+                                               L.stream_ptr()))
+        return logits
+
     # ------------------------------------------------------------------ greedy decode with the KV cache (POL:463-469)
     def _c_model(self):
         if getattr(self, "_cm", None) is None:

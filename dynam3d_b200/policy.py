@@ -197,6 +197,12 @@ class Dynam3D_VLN(nn.Module):
         self.max_new_tokens = 20             # POL:463
         self._PW = None
         self._side = None
+        self._chunk_tab, self._prefix_keep = {}, None
+        # Prefill of the memory-independent prompt prefix on the side stream during the 3D-memory update (bit-identical logits).  OFF by default:
+        # measured the memory-update window is not idle enough -- its GEMMs + the tower already fill most of it -- so
+        # partitioning the SMs between the two streams gives back what the overlap gains.
+        self.chunked_prefill = False
+        self.overlap_sms = (132, 0)  # persistent GEMM grid caps while overlapping: (side stream: tower + prefix, main stream: memory update; 0 = all)
 
     # -- properties the habitat `Net` interface expects (POL:159-169)
     @property
@@ -387,8 +393,11 @@ class Dynam3D_VLN(nn.Module):
     def build_prompt(n_image_tokens, instruction, history):
         return build_prompt(n_image_tokens, instruction, history)
 
-    def encode_step(self, observations, agent_positions, agent_heading_angles, depth_scale=(0.0, 10.0), delete_old_features=True, num_of_views=1):
-        """Stages a1-a14 (POL:336-363, 432-435): returns per-episode projected tokens (patch, instance, zone), all fp32 [*, 3072]."""
+    def encode_step(self, observations, agent_positions, agent_heading_angles, depth_scale=(0.0, 10.0), delete_old_features=True, num_of_views=1,
+                    lm_head_ids=None):
+        """Stages a1-a14 (POL:336-363, 432-435): returns per-episode projected tokens (patch, instance, zone), all fp32 [*, 3072].
+        lm_head_ids (B lists of the prompt's first two ids): also prefill the first PREFIX_TOKENS positions of every prompt -- [2 text tokens |
+        patch tokens], which do not depend on the 3D memory -- behind the LLaVA tower on the side stream, while the memory update runs."""
         ff = self.feature_fields
         B, V = ff.batch_size, num_of_views
         P = ff.args.input_height * ff.args.input_width
@@ -417,10 +426,23 @@ class Dynam3D_VLN(nn.Module):
             rows = torch.empty((B * P, 8), device=dev, dtype=torch.float32 if self._precise_proj else torch.float16)
             ops.patch_info_rows(info5[:, sel].contiguous(), rows)
             patch_pos = self._mlp(rows, PW["patch_pos"])  # POL:432-433
-            patch = self.llava.image_features(rgb[sel].contiguous())  # POL:448-452
-            ops.add_inplace(patch, patch_pos)  # POL:453
-        ff.update_feature_fields(d576.view(B, V, P), grid.reshape(B, V, P, 768), batch_image=rgb, batch_position=agent_positions,
-                                 batch_heading=agent_heading_angles, num_of_views=V, batch_patch_segm=segm)
+            if lm_head_ids is not None:
+                L.lib().d3d_gemm_set_sm_limit(self.overlap_sms[0])  # leave SMs free for the latency-bound view loop on the main stream
+            try:
+                patch = self.llava.image_features(rgb[sel].contiguous())  # POL:448-452
+                ops.add_inplace(patch, patch_pos)  # POL:453
+                if lm_head_ids is not None:
+                    self._prefill_prefix(patch, lm_head_ids, B, P)
+            finally:
+                if lm_head_ids is not None:
+                    L.lib().d3d_gemm_set_sm_limit(0)
+        if lm_head_ids is not None:
+            L.lib().d3d_gemm_set_sm_limit(self.overlap_sms[1])
+        try:
+            ff.update_feature_fields(d576.view(B, V, P), grid.reshape(B, V, P, 768), batch_image=rgb, batch_position=agent_positions,
+                                     batch_heading=agent_heading_angles, num_of_views=V, batch_patch_segm=segm)
+        finally:
+            L.lib().d3d_gemm_set_sm_limit(0)
         env = ff.get_environment_features(agent_positions, agent_heading_angles)
         main.wait_stream(self._side)
         for t in (rows, patch_pos, patch):
@@ -433,6 +455,37 @@ class Dynam3D_VLN(nn.Module):
         inst = project_all(env["batch_instance_fts"], env["batch_instance_relative_position"], PW["inst_pos"], PW["inst_proj"])
         zone = project_all(env["batch_zone_fts"], env["batch_zone_relative_position"], PW["zone_pos"], PW["zone_proj"])
         return patch.view(B, P, 3072), inst, zone
+
+    # ------------------------------------------------------------------ chunked prefill (prefix overlapped with the memory update)
+    PREFIX_TOKENS = 512      # 4 query tiles of 128: positions [0, 512) = 2 text tokens + the first 510 patch tokens of the view the LLM sees
+    MAX_PROMPT_TOKENS = 2048  # row stride of a sequence in the strided KV cache; longer prompts fall back to the one-pass prefill
+
+    def _chunk_tables(self, B):
+        t = self._chunk_tab.get(B)
+        if t is None:
+            Pn, S = self.PREFIX_TOKENS, self.MAX_PROMPT_TOKENS
+            i32 = lambda a: torch.tensor(np.asarray(a), dtype=torch.int32, device=self.device)
+            t = self._chunk_tab[B] = {"starts": i32(np.arange(B) * S), "len1": i32(np.full(B, Pn)), "pos1": i32(np.tile(np.arange(Pn), B)),
+                                      "rows1": i32(np.concatenate([b * S + np.arange(Pn) for b in range(B)]))}
+        return t
+
+    def _prefill_prefix(self, patch, head_ids, B, P):
+        """Pass 1 of the chunked prefill (side stream): positions [0, PREFIX_TOKENS) of every prompt = emb(ids[:2]) || patch tokens (POL:456)."""
+        lm = self.llava.lm
+        Pn, hid = self.PREFIX_TOKENS, lm.w.hidden
+        lm.chunk_cache(B, self.MAX_PROMPT_TOKENS)
+        t = self._chunk_tables(B)
+        Eh = torch.empty((2 * B, hid), device=self.device, dtype=torch.float32)
+        lm.embed(torch.tensor([i for ids in head_ids for i in ids[:2]], dtype=torch.int32).to(self.device, non_blocking=True), Eh)
+        Xp = torch.empty((B, Pn, hid), device=self.device, dtype=torch.float32)
+        Xp[:, :2].copy_(Eh.view(B, 2, hid))
+        Xp[:, 2:].copy_(patch.view(B, P, hid)[:, : Pn - 2])
+        lm.prefill_chunk(Xp.view(B * Pn, hid), t["starts"], t["len1"], t["rows1"], t["pos1"], B, Pn, 0, Pn // 128)
+        self._prefix_keep = (Eh, Xp)  # freed after the join (allocated on the side stream)
+
+    def _chunk_ok(self, generate, B):
+        return (self.chunked_prefill and not generate and not self.llava.precise_lm and ops.STAGE_PROFILE is None and B <= 16
+                and self.feature_fields.args.input_height * self.feature_fields.args.input_width + 2 >= self.PREFIX_TOKENS)
 
     def forward_logits(self, observations, instructions, agent_positions, agent_heading_angles, depth_scale=(0.0, 10.0),
                        delete_old_features=True, num_of_views=1, input_ids=None):
@@ -453,7 +506,14 @@ class Dynam3D_VLN(nn.Module):
                         num_of_views, input_ids, generate=False):
         ff = self.feature_fields
         B = ff.batch_size
-        patch, inst, zone = self.encode_step(observations, agent_positions, agent_heading_angles, depth_scale, delete_old_features, num_of_views)
+        head_ids = None
+        if self._chunk_ok(generate, B):
+            # the first two prompt ids do not depend on the number of image slots (POL:436: "<|user|>\n" + "<image>" * n ...)
+            head_ids = [list(input_ids[b][:2]) if input_ids is not None else
+                        self.tokenize(self.build_prompt(1, instructions[b], ff.history_actions[b]))[:2] for b in range(B)]
+        patch, inst, zone = self.encode_step(observations, agent_positions, agent_heading_angles, depth_scale, delete_old_features, num_of_views,
+                                             lm_head_ids=head_ids)
+        self._prefix_keep = None
         lm = self.llava.lm
         # text tokens of all episodes: ONE id upload and ONE embedding gather (POL:439), then the literal splice of POL:456
         heads, tails, n_imgs, all_ids = [], [], [], []
@@ -473,6 +533,21 @@ class Dynam3D_VLN(nn.Module):
         lm.embed(torch.tensor(flat, dtype=torch.int32).to(self.device, non_blocking=True), E)
         offs = np.concatenate([[0], np.cumsum([len(heads[b]) + len(tails[b]) for b in range(B)])])
         self.last_seq_lens = [len(heads[b]) + n_imgs[b] + len(tails[b]) for b in range(B)]
+        if head_ids is not None and max(self.last_seq_lens) <= self.MAX_PROMPT_TOKENS and all(heads[b] == head_ids[b] for b in range(B)):
+            # pass 2 of the chunked prefill: positions [PREFIX_TOKENS, S) = remaining patch tokens || instance || zone || text, attending to the
+            # prefix cached by pass 1 (which ran on the side stream during the memory update)
+            Pn, Sm, Pp = self.PREFIX_TOKENS, self.MAX_PROMPT_TOKENS, patch.shape[1]
+            seqs, n_suf = [], []
+            for b in range(B):
+                nh, o = len(heads[b]), int(offs[b])
+                seqs += [patch[b][Pn - 2:], inst[b], zone[b], E[o + nh:int(offs[b + 1])]]
+                n_suf.append(self.last_seq_lens[b] - Pn)
+            Xs = torch.cat(seqs, 0)
+            i32 = lambda a: torch.tensor(np.asarray(a), dtype=torch.int32).to(self.device, non_blocking=True)
+            rows2 = i32(np.concatenate([b * Sm + np.arange(Pn, self.last_seq_lens[b]) for b in range(B)]))
+            pos2 = i32(np.concatenate([np.arange(Pn, self.last_seq_lens[b]) for b in range(B)]))
+            return lm.prefill_chunk(Xs, self._chunk_tables(B)["starts"], i32(self.last_seq_lens), rows2, pos2, B, max(self.last_seq_lens), Pn // 128,
+                                    1 << 20, last_rows=i32(np.cumsum(n_suf) - 1))
 
         def run(group):
             """Prefill (+ greedy decode) of the episodes in `group` as one packed batch."""

@@ -222,6 +222,8 @@ int d3d_lm_decode_step(const d3d_lm_model* m_h, void* const* qkv_layers_h, int64
 
 /* dst[r, :D] = src[idx[r], :D] for n 16-bit rows (last-token rows of the final Phi-3 layer). */
 int d3d_gather_rows16(const void* src, int64_t lds, const int* idx, void* dst, int64_t ldd, int n, int D, void* stream);
+/* dst[dst_idx[r], :D] = src[r, :D] for n 16-bit rows (compact QKV rows of a prefill chunk -> their rows of the strided KV cache). */
+int d3d_scatter_rows16(const void* src, int64_t lds, void* dst, int64_t ldd, const int* dst_idx, int n, int D, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Coarse entry points: one call per transformer stack (csrc/forward_host.cu).  Bit-identical to issuing the per-kernel entries.
@@ -264,6 +266,26 @@ typedef struct {                 /* device scratch for T packed tokens of n_seq 
 int d3d_phi3_prefill(const d3d_lm_model* m_h, float* X, int T, const int* cu_seqlens, const int* positions, int n_seq, int max_len,
                      const int* last_rows, const float* inv_freq, void* const* qkv_layers_h, int64_t ld_qkv, const d3d_lm_scratch* s_h,
                      int trim_last_layer, float* logits, void* stream);
+
+/* Chunked prefill over a strided KV cache: the prompt of a navigation step is [2 text tokens | 576 patch tokens | instance | zone | text]
+ * (POL:456) and, attention being causal, the first tokens do not depend on the 3D memory -- their prefill can run while the (host-
+ * synchronised) memory update is in flight.  One call processes T compact rows X [T, hidden] (fp32 residual stream, overwritten) of n_seq
+ * sequences: rows[t] = row of the KV cache that compact row t occupies (sequence s lives at cache rows seq_start[s] + position),
+ * positions[t] its token position, seq_len[s] the number of keys visible to this pass; the pass computes the query tiles (128 positions)
+ * [q_tile_begin, q_tile_end) of every sequence, i.e. its compact rows must be exactly the positions of those tiles (< seq_len).
+ * cache_layers_h: HOST array of per-layer [cache_rows, ld_cache] 16-bit packed QKV buffers (zero-initialised once); att_cache
+ * [cache_rows, hidden] 16-bit scratch.  last_rows (compact rows of the sequences' last tokens) != NULL: also final norm + lm_head ->
+ * logits [n_seq, vocab].  Results are bit-identical to d3d_phi3_prefill (same kernels per row / tile; trim_last_layer as there). */
+typedef struct {
+  const int* seq_start; const int* seq_len; const int* rows; const int* positions;
+  int q_tile_begin, q_tile_end;
+} d3d_lm_chunk;
+int d3d_phi3_prefill_chunk(const d3d_lm_model* m_h, float* X, int T, int n_seq, int max_len, const d3d_lm_chunk* c_h, void* const* cache_layers_h,
+                           int64_t ld_cache, int64_t cache_rows, void* att_cache, const float* inv_freq, const d3d_lm_scratch* s_h,
+                           const int* last_rows, int trim_last_layer, float* logits, void* stream);
+/* Persistent GEMM kernels launch on at most `n` SMs (0 = all): leaves SMs free for a concurrent latency-bound stream (the view loop of the
+ * 3D-memory update) while a throughput-bound stream runs transformer layers. */
+int d3d_gemm_set_sm_limit(int n);
 
 /* Device timing of every d3d_gemm launch between begin and end (CUDA events on the launch stream), per kernel variant
  * [0] gemm_tcgen05_pair_kernel<256> (CTA pairs), [1] gemm_tcgen05_kernel<256>, [2] gemm_tcgen05_kernel<128>: algorithmic FLOPs (2 M N K),
@@ -314,6 +336,11 @@ int d3d_attention_mma(const void* qkv, int64_t ld, void* out, int64_t ldo, const
  * d3d_attention_simt; n_rows = total rows T of the qkv matrix (for the TMA descriptors). */
 int d3d_attention_tc(const void* qkv, int64_t ld, int64_t n_rows, void* out, int64_t ldo, const int* cu_seqlens, int n_seq,
                      int max_len, int H, int Dh, int causal, int kind, float scale, void* stream);
+/* The same kernel over sequences that start at arbitrary rows seq_start[s] with explicit lengths seq_len[s] (NULL: packed, len = start[s+1] -
+ * start[s]) and for the query tiles (128 rows) [q_tile_begin, q_tile_end) of every sequence only -- the chunked prefill over a strided KV
+ * cache (d3d_phi3_prefill_chunk): keys [0, len) of the sequence, queries of the selected tiles. */
+int d3d_attention_tc_ex(const void* qkv, int64_t ld, int64_t n_rows, void* out, int64_t ldo, const int* seq_start, const int* seq_len,
+                        int n_seq, int max_len, int q_tile_begin, int q_tile_end, int H, int Dh, int causal, int kind, float scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Token builders for the layer-wise pooling (patch -> instance -> zone) and the merge discriminator.

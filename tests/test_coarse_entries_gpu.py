@@ -58,3 +58,37 @@ def test_phi3_prefill_entry_equals_layer_loop():
     kv_loop = eng.kv[:, : sum(lens)].clone()
     got_kv = eng.prefill(emb.clone(), cu, pos, len(lens), max(lens), last, kv_rows=8)
     assert torch.equal(eng.kv[:, : sum(lens)], kv_loop) and (got_kv - want_kv).abs().max().item() < 2e-3
+
+
+def test_chunked_prefill_equals_one_pass():
+    """d3d_phi3_prefill_chunk: the first 512 tokens of every sequence in one pass, the rest (attending to the cached prefix) in a second pass over a
+    strided KV cache -> bit-identical logits to the one-pass prefill (same kernels per row / tile)."""
+    from dynam3d_b200 import synth
+    from dynam3d_b200.phi3 import LMEngine, LMWeights
+    hidden, layers, heads, ffn, vocab, lens = 3072, 2, 32, 8192, 32064, [745, 612, 701]
+    B, P, stride = len(lens), 512, 1024
+    sd = synth.lm_state_dict(9, hidden, layers, ffn, vocab, device="cuda", round_to=torch.float16)
+    eng = LMEngine(LMWeights.from_state_dict(sd, dtype=torch.float16), n_heads=heads, max_tokens=sum(lens))
+    emb = synth.hash_uniform((sum(lens), hidden), 109, 1.0, device="cuda")
+    cu_h = np.concatenate([[0], np.cumsum(lens)])
+    cu = torch.tensor(cu_h, dtype=torch.int32, device="cuda")
+    pos = torch.cat([torch.arange(n, dtype=torch.int32) for n in lens]).cuda()
+    last = (cu[1:] - 1).to(torch.int32).contiguous()
+    for trim in (False, True):
+        eng.trim_last_layer = trim
+        want = eng.prefill(emb.clone(), cu, pos, B, max(lens), last)
+        eng.chunk_cache(B, stride)
+        i32 = lambda a: torch.tensor(np.asarray(a), dtype=torch.int32, device="cuda")
+        starts = i32([b * stride for b in range(B)])
+        # pass 1: positions [0, 512) of every sequence
+        Xp = torch.cat([emb[cu_h[b]:cu_h[b] + P] for b in range(B)], 0).contiguous()
+        rows1 = i32(np.concatenate([b * stride + np.arange(P) for b in range(B)]))
+        pos1 = i32(np.tile(np.arange(P), B))
+        assert eng.prefill_chunk(Xp, starts, i32([P] * B), rows1, pos1, B, P, 0, P // 128) is None
+        # pass 2: positions [512, len)
+        Xs = torch.cat([emb[cu_h[b] + P:cu_h[b + 1]] for b in range(B)], 0).contiguous()
+        rows2 = i32(np.concatenate([b * stride + np.arange(P, lens[b]) for b in range(B)]))
+        pos2 = i32(np.concatenate([np.arange(P, lens[b]) for b in range(B)]))
+        last2 = i32(np.cumsum([n - P for n in lens]) - 1)
+        got = eng.prefill_chunk(Xs, starts, i32(lens), rows2, pos2, B, max(lens), P // 128, 1 << 20, last_rows=last2)
+        assert torch.equal(got, want), (trim, (got - want).abs().max().item())

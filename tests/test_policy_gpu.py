@@ -103,3 +103,24 @@ def test_forward_eval_branch_returns_text_and_updates_history():
         h = net.feature_fields.history_actions[b]
         assert len(h) == 4 and h[-1] == texts[b] + "\n" and h[0] == "none\n"
     assert net.convert_text_to_action(["stop"]) == [-100]
+
+
+def test_chunked_prefill_overlap_gives_identical_logits():
+    """`chunked_prefill`: the prompt prefix (2 text + 510 patch tokens) is prefilled on the side stream while the 3D memory updates, the rest
+    afterwards over the strided KV cache -> the same logits bit for bit as the one-pass prefill."""
+    from dynam3d_b200 import synth
+    B, V = 2, 2
+    outs = []
+    for chunked in (False, True):
+        net, _ = _build(8, 2, 2, B, q1_fix=True)
+        net.tokenize = synth.ToyTokenizer()
+        net.chunked_prefill, net.overlap_sms = chunked, (132, 16)
+        eps = [synth.make_episode(80 + b, n_steps=2, num_views=V, rgb_size=224, n_seg=16, seg_kind="voronoi") for b in range(B)]
+        instr = [synth.make_instruction(b) for b in range(B)]
+        for t in range(2):
+            obs = {"rgb": torch.from_numpy(np.concatenate([eps[b][t]["rgb"] for b in range(B)], 0)),
+                   "depth": torch.from_numpy(np.concatenate([eps[b][t]["depth"] for b in range(B)], 0)),
+                   "patch_segm": np.stack([eps[b][t]["segm"] for b in range(B)], 0)}
+            lg = net.forward_logits(obs, instr, [eps[b][t]["position"] for b in range(B)], [eps[b][t]["heading"] for b in range(B)], num_of_views=V)
+            outs.append(lg.cpu())
+    assert torch.equal(outs[0], outs[2]) and torch.equal(outs[1], outs[3])
