@@ -167,7 +167,7 @@ SIGNATURES = {
     "d3d_ffh_get_zone_keys": [_P, _I, _P, _P, _P], "d3d_ffh_get_last": [_P, _I, _P, _P, _P, _P],
     "d3d_split16": [_P, _L, _P, _L, _I, _I, _I, _P],
     "d3d_attention_f32": [_P, _L, _P, _L, _P, _I, _I, _I, _I, _I, _F, _P],
-    "d3d_attention_split": [_P, _L, _P, _L, _P, _I, _I, _I, _I, _I, _F, _P],
+    "d3d_attention_split": [_P, _L, _L, _P, _L, _P, _I, _I, _I, _I, _I, _F, _P],
     "d3d_ray_points_habitat": [_P, _P, _P, _I, _I] + [ctypes.c_double] * 5 + [_P, _P],
     "d3d_ray_topk": [_P, _P, _I, _I, _I, _F, _I, _P, _P],
     "d3d_gather_samples": [_P, _P, _I, _I, _I, _P, _P],

@@ -3,7 +3,9 @@
 //   S = Qh Kh^T + Ql Kh^T + Qh Kl^T,   O += Ph Vh + Pl Vh + Ph Vl      (mma.sync m16n8k16, fp32 accumulate; the lo x lo terms are ~2^-22)
 // with the online softmax in fp32.  Same packed variable-length contract as d3d_attention_f32 (which it replaces in precise.py: the
 // CUDA-core kernel was ~70 % of a precise step); parity target: <= 1e-3 on the action logits vs the pure-fp32 oracle at full depth.
-// One CTA = 128 queries of one (sequence, head), 8 warps x 16 rows, 64-key tiles; operands are split while they are staged in shared memory.
+// One CTA = 128 queries of one (sequence, head), 8 warps x 16 rows, 64-key tiles.  The operands arrive PRE-SPLIT: d3d_split16 turns the fp32
+// QKV matrix of a layer into [hi | lo] fp16 halves once (instead of once per query tile), and the K / V hi / lo tiles stream through a
+// double-buffered cp.async pipeline like the production mma kernel's.
 #include "common.cuh"
 
 namespace {
@@ -32,34 +34,23 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
   lo = *reinterpret_cast<uint32_t*>(&l);
 }
 
-// stage `rows` fp32 rows (D wide, row r at src + r*ld; rows >= n_valid are zero) as hi / lo fp16 tiles with padded rows
-template <int D>
-__device__ __forceinline__ void stage_split(const float* __restrict__ src, long long ld, int rows, int n_valid, uint16_t* __restrict__ dh,
-                                            uint16_t* __restrict__ dl) {
-  constexpr int LDS = D + 8, C4 = D / 4;
-  for (int i = threadIdx.x; i < rows * C4; i += NTHREADS) {
-    const int r = i / C4, c = i % C4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r < n_valid) v = *reinterpret_cast<const float4*>(src + (size_t)r * ld + c * 4);
-    uint32_t h0, l0, h1, l1;
-    split2(v.x, v.y, h0, l0);
-    split2(v.z, v.w, h1, l1);
-    *reinterpret_cast<uint2*>(&dh[r * LDS + c * 4]) = make_uint2(h0, h1);
-    *reinterpret_cast<uint2*>(&dl[r * LDS + c * 4]) = make_uint2(l0, l1);
-  }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// qkv: [T, ld] fp16 rows = [q | k | v hi halves (3*H*D) ... | lo halves at column lo_off ...]
 template <int D>
-__global__ void __launch_bounds__(NTHREADS) attn_split_kernel(const float* __restrict__ qkv, long long ld, float* __restrict__ out, long long ldo,
-                                                              const int* __restrict__ cu, int H, int causal, float scale_log2) {
-  constexpr int LDS = D + 8, KS = D / 16, DT = D / 8;
+__global__ void __launch_bounds__(NTHREADS) attn_split_kernel(const uint16_t* __restrict__ qkv, long long ld, long long lo_off, float* __restrict__ out,
+                                                              long long ldo, const int* __restrict__ cu, int H, int causal, float scale_log2) {
+  constexpr int LDS = D + 8, KS = D / 16, DT = D / 8, CPR = D / 8;
+  constexpr int STAGE = 4 * BKV * LDS;  // halves per stage: K hi, K lo, V hi, V lo
   extern __shared__ __align__(16) uint16_t smem_split[];
   uint16_t* sQh = smem_split;
   uint16_t* sQl = sQh + BQ * LDS;
-  uint16_t* sKh = sQl + BQ * LDS;
-  uint16_t* sKl = sKh + BKV * LDS;
-  uint16_t* sVh = sKl + BKV * LDS;
-  uint16_t* sVl = sVh + BKV * LDS;
+  uint16_t* sKV = sQl + BQ * LDS;  // 2 stages
 
   const int seq = blockIdx.z, h = blockIdx.y;
   const int b = cu[seq], len = cu[seq + 1] - b;
@@ -70,7 +61,17 @@ __global__ void __launch_bounds__(NTHREADS) attn_split_kernel(const float* __res
   const int g = lane >> 2, t = lane & 3;
   const size_t qoff = (size_t)h * D, koff = (size_t)(H + h) * D, voff = (size_t)(2 * H + h) * D;
 
-  stage_split<D>(qkv + (size_t)(b + q0) * ld + qoff, ld, BQ, len - q0, sQh, sQl);
+  for (int i = threadIdx.x; i < BQ * CPR; i += NTHREADS) {
+    const int r = i / CPR, c = i % CPR;
+    uint4 vh = make_uint4(0, 0, 0, 0), vl = vh;
+    if (q0 + r < len) {
+      const uint16_t* rowp = qkv + (size_t)(b + q0 + r) * ld + qoff + c * 8;
+      vh = *reinterpret_cast<const uint4*>(rowp);
+      vl = *reinterpret_cast<const uint4*>(rowp + lo_off);
+    }
+    *reinterpret_cast<uint4*>(&sQh[r * LDS + c * 8]) = vh;
+    *reinterpret_cast<uint4*>(&sQl[r * LDS + c * 8]) = vl;
+  }
   float o[DT][4];
 #pragma unroll
   for (int i = 0; i < DT; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
@@ -80,13 +81,40 @@ __global__ void __launch_bounds__(NTHREADS) attn_split_kernel(const float* __res
   const int n_tiles = (kmax + BKV - 1) / BKV;
   const int qrow = warp * 16 + (lane & 15), qcolsel = (lane >> 4) * 8;
 
+  auto load_tile = [&](int tile, int stage) {
+    const int c0 = tile * BKV;
+    uint16_t* dKh = sKV + stage * STAGE;
+    uint16_t* dKl = dKh + BKV * LDS;
+    uint16_t* dVh = dKl + BKV * LDS;
+    uint16_t* dVl = dVh + BKV * LDS;
+    for (int i = threadIdx.x; i < BKV * CPR; i += NTHREADS) {
+      const int r = i / CPR, c = i % CPR;
+      const bool ok = c0 + r < len;
+      const uint16_t* rowp = qkv + (size_t)(b + (ok ? c0 + r : 0)) * ld + c * 8;
+      const int nb = ok ? 16 : 0;
+      cp_async16(smem_u32(&dKh[r * LDS + c * 8]), rowp + koff, nb);
+      cp_async16(smem_u32(&dKl[r * LDS + c * 8]), rowp + koff + lo_off, nb);
+      cp_async16(smem_u32(&dVh[r * LDS + c * 8]), rowp + voff, nb);
+      cp_async16(smem_u32(&dVl[r * LDS + c * 8]), rowp + voff + lo_off, nb);
+    }
+    cp_async_commit();
+  };
+  load_tile(0, 0);
   for (int tile = 0; tile < n_tiles; ++tile) {
     const int c0 = tile * BKV;
-    __syncthreads();  // the previous tile's fragments have been consumed (and, first time, Q is staged)
-    stage_split<D>(qkv + (size_t)(b + c0) * ld + koff, ld, BKV, len - c0, sKh, sKl);
-    stage_split<D>(qkv + (size_t)(b + c0) * ld + voff, ld, BKV, len - c0, sVh, sVl);
-    __syncthreads();
-    if (causal && c0 > q0 + warp * 16 + 15) continue;  // whole tile above the diagonal for this warp (warp-uniform; barriers are at the loop top)
+    if (tile + 1 < n_tiles) {
+      load_tile(tile + 1, (tile + 1) & 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();  // tile's K / V (and, first time, Q) are visible to every warp
+    const uint16_t* sKh = sKV + (tile & 1) * STAGE;
+    const uint16_t* sKl = sKh + BKV * LDS;
+    const uint16_t* sVh = sKl + BKV * LDS;
+    const uint16_t* sVl = sVh + BKV * LDS;
+    const bool active = !(causal && c0 > q0 + warp * 16 + 15);  // whole tile above the diagonal for this warp (warp-uniform)
+    if (active) {
     // ---- S = Qh Kh^T + Ql Kh^T + Qh Kl^T (16 x 64 per warp) ----
     float s[8][4];
 #pragma unroll
@@ -165,6 +193,8 @@ __global__ void __launch_bounds__(NTHREADS) attn_split_kernel(const float* __res
         mma16816(o[2 * dp + 1], ph[kk], b2, b3);
       }
     }
+    }  // active
+    __syncthreads();  // everyone is done with this stage before tile + 2 overwrites it
   }
   const float inv0 = l0 > 0.f ? 1.0f / l0 : 0.f, inv1 = l1 > 0.f ? 1.0f / l1 : 0.f;
 #pragma unroll
@@ -176,30 +206,31 @@ __global__ void __launch_bounds__(NTHREADS) attn_split_kernel(const float* __res
 }
 
 template <int D>
-int launch(const float* qkv, long long ld, float* out, long long ldo, const int* cu, int n_seq, int max_len, int H, int causal, float scale,
-           cudaStream_t st) {
+int launch(const uint16_t* qkv, long long ld, long long lo_off, float* out, long long ldo, const int* cu, int n_seq, int max_len, int H, int causal,
+           float scale, cudaStream_t st) {
   dim3 grid(d3d_cdiv(max_len, BQ), H, n_seq);
-  constexpr int SMEM = (2 * BQ + 4 * BKV) * (D + 8) * 2;
+  constexpr int SMEM = (2 * BQ + 8 * BKV) * (D + 8) * 2;
   static bool attr_set = false;
   if (!attr_set) {
     D3D_CHECK_CUDA(cudaFuncSetAttribute(attn_split_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_set = true;
   }
-  attn_split_kernel<D><<<grid, NTHREADS, SMEM, st>>>(qkv, ld, out, ldo, cu, H, causal, scale * 1.4426950408889634f);
+  attn_split_kernel<D><<<grid, NTHREADS, SMEM, st>>>(qkv, ld, lo_off, out, ldo, cu, H, causal, scale * 1.4426950408889634f);
   D3D_CHECK_LAUNCH();
   return 0;
 }
 
 }  // namespace
 
-extern "C" int d3d_attention_split(const float* qkv, int64_t ld, float* out, int64_t ldo, const int* cu_seqlens, int n_seq, int max_len, int H,
-                                   int Dh, int causal, float scale, void* stream) {
+extern "C" int d3d_attention_split(const void* qkv_hl, int64_t ld, int64_t lo_off, float* out, int64_t ldo, const int* cu_seqlens, int n_seq,
+                                   int max_len, int H, int Dh, int causal, float scale, void* stream) {
   if (n_seq == 0 || max_len == 0) return 0;
-  D3D_REQUIRE(qkv && out && cu_seqlens, "args");
+  D3D_REQUIRE(qkv_hl && out && cu_seqlens, "args");
   D3D_REQUIRE(Dh == 64 || Dh == 96, "head_dim 64 or 96");
-  D3D_REQUIRE(ld % 4 == 0 && ldo % 2 == 0 && ((uintptr_t)qkv % 16) == 0 && ((uintptr_t)out % 8) == 0, "16-byte aligned input rows, 8-byte aligned output rows");
+  D3D_REQUIRE(ld % 8 == 0 && lo_off % 8 == 0 && lo_off >= 3LL * H * Dh && ldo % 2 == 0 && ((uintptr_t)qkv_hl % 16) == 0 && ((uintptr_t)out % 8) == 0,
+              "16-byte aligned fp16 rows [hi | lo], 8-byte aligned output rows");
   D3D_REQUIRE(n_seq <= 65535 && H <= 65535, "grid limits");
   cudaStream_t st = (cudaStream_t)stream;
-  if (Dh == 64) return launch<64>(qkv, ld, out, ldo, cu_seqlens, n_seq, max_len, H, causal, scale, st);
-  return launch<96>(qkv, ld, out, ldo, cu_seqlens, n_seq, max_len, H, causal, scale, st);
+  if (Dh == 64) return launch<64>((const uint16_t*)qkv_hl, ld, lo_off, out, ldo, cu_seqlens, n_seq, max_len, H, causal, scale, st);
+  return launch<96>((const uint16_t*)qkv_hl, ld, lo_off, out, ldo, cu_seqlens, n_seq, max_len, H, causal, scale, st);
 }

@@ -52,12 +52,19 @@ SPLIT_ATTENTION = True  # sequences of >= 64 tokens on the tensor cores with spl
 
 
 def attention(qkv32, cu, n_seq, max_len, H, Dh, causal):
-    out = torch.empty((qkv32.shape[0], H * Dh), device=qkv32.device, dtype=torch.float32)
-    fn = L.lib().d3d_attention_split if (SPLIT_ATTENTION and max_len >= 64) else L.lib().d3d_attention_f32
-    work = 4.0 * (qkv32.shape[0] ** 2 / max(n_seq, 1)) * Dh * H * (0.5 if causal else 1.0) * (3.0 if fn is L.lib().d3d_attention_split else 1.0)
+    T, W = qkv32.shape[0], 3 * H * Dh
+    out = torch.empty((T, H * Dh), device=qkv32.device, dtype=torch.float32)
+    split = SPLIT_ATTENTION and max_len >= 64
+    work = 4.0 * (T ** 2 / max(n_seq, 1)) * Dh * H * (0.5 if causal else 1.0) * (3.0 if split else 1.0)
     with ops._Rec("attention_precise", "tensor", work):
-        L.check(fn(L.ptr(qkv32), qkv32.stride(0), L.ptr(out), out.stride(0), L.ptr(cu), n_seq, max_len, H, Dh, int(bool(causal)),
-                   1.0 / math.sqrt(Dh), L.stream_ptr()))
+        if split:  # split the layer's QKV matrix ONCE into [hi | lo] fp16 halves, then the pipelined tensor-core kernel
+            hl = torch.empty((T, 2 * W), device=qkv32.device, dtype=torch.float16)
+            L.check(L.lib().d3d_split16(L.ptr(qkv32), qkv32.stride(0), L.ptr(hl), hl.stride(0), T, W, 2, L.stream_ptr()))
+            L.check(L.lib().d3d_attention_split(L.ptr(hl), hl.stride(0), W, L.ptr(out), out.stride(0), L.ptr(cu), n_seq, max_len, H, Dh,
+                                                int(bool(causal)), 1.0 / math.sqrt(Dh), L.stream_ptr()))
+        else:
+            L.check(L.lib().d3d_attention_f32(L.ptr(qkv32), qkv32.stride(0), L.ptr(out), out.stride(0), L.ptr(cu), n_seq, max_len, H, Dh,
+                                              int(bool(causal)), 1.0 / math.sqrt(Dh), L.stream_ptr()))
     return out
 
 

@@ -500,10 +500,11 @@ int d3d_split16(const float* in, int64_t ldi, void* out16, int64_t ldo, int T, i
 /* fp32-in / fp32-out variant of d3d_attention_simt (no 16-bit rounding of q, k, v or the output). */
 int d3d_attention_f32(const float* qkv, int64_t ld, float* out, int64_t ldo, const int* cu_seqlens, int n_seq, int max_len, int H,
                       int Dh, int causal, float scale, void* stream);
-/* The same contract on the tensor cores with split fp16x2 operands (x = hi + lo; S = Qh Kh + Ql Kh + Qh Kl, O += Ph Vh + Pl Vh + Ph Vl,
- * fp32 softmax): ~22-bit products at mma.sync speed -- the precise mode's attention for sequences of >= 64 tokens. */
-int d3d_attention_split(const float* qkv, int64_t ld, float* out, int64_t ldo, const int* cu_seqlens, int n_seq, int max_len, int H, int Dh,
-                        int causal, float scale, void* stream);
+/* Attention on the tensor cores with split fp16x2 operands (x = hi + lo; S = Qh Kh + Ql Kh + Qh Kl, O += Ph Vh + Pl Vh + Ph Vl, fp32 softmax,
+ * fp32 output): ~22-bit products at mma.sync speed -- the precise mode's attention for sequences of >= 64 tokens.  qkv_hl [T, ld] fp16 is the
+ * packed QKV matrix split by d3d_split16: hi halves in columns [0, 3*H*Dh), lo halves at column lo_off. */
+int d3d_attention_split(const void* qkv_hl, int64_t ld, int64_t lo_off, float* out, int64_t ldo, const int* cu_seqlens, int n_seq, int max_len, int H,
+                        int Dh, int causal, float scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Pretrain novel-view patch renderer, render_view_3d_patch (PFF:494-625), habitat mode.  The two torch_kdtree queries are

@@ -29,7 +29,7 @@ def test_policy_projections_match_oracle(precise):
         want = NN.mlp_ln_gelu(torch.cat([fts, pe], -1), P, proj_name, rnd)
         e = (got - want).abs().max().item()
         print(f"{proj_name} ({'precise' if precise else 'production'}): max abs err {e:.2e} (|y| max {want.abs().max().item():.2f})")
-        assert got.shape == (n, 3072) and e < (2e-5 if precise else 3e-3)
+        assert got.shape == (n, 3072) and e < (1e-4 if precise else 3e-3)
     # patch_position_embedding on the 6-d patch info rows [rel_x, rel_y, rel_z, sin(dir), cos(dir), scale]
     info5 = torch.from_numpy(rng.standard_normal((5, 2, 576)).astype(np.float32)).cuda()
     rows = torch.empty((2 * 576, 8), device="cuda", dtype=torch.float32 if precise else torch.float16)
@@ -40,5 +40,5 @@ def test_policy_projections_match_oracle(precise):
     want = NN.mlp_ln_gelu(feat6, P, "patch_position_embedding", rnd)
     e = (got - want).abs().max().item()
     print(f"patch_position_embedding ({'precise' if precise else 'production'}): max abs err {e:.2e}")
-    assert e < (2e-5 if precise else 3e-3)
+    assert e < (1e-4 if precise else 3e-3)
     assert net._project_tokens(torch.zeros((0, 768), device="cuda"), torch.zeros((0, 3), device="cuda"), PW["inst_pos"], PW["inst_proj"]).shape == (0, 3072)
