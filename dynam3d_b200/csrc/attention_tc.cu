@@ -175,10 +175,13 @@ __device__ __forceinline__ uint32_t make_idesc(int kind, int m, int n, int b_mn_
          ((uint32_t)(m >> 4) << 24);
 }
 
-template <int D>
+// KIND (D3D_F16 / D3D_BF16) is a template parameter: as a run-time argument every P / output pack was emitted for both types and predicated
+// (ncu, round 2: F2FP = 8 % of the issued instructions, half of them predicated off)
+template <int D, int KIND>
 __global__ void __launch_bounds__(NTHREADS, AC<D>::CTAS_PER_SM)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_qkv32, uint16_t* __restrict__ out, long long ldo,
-               const int* __restrict__ cu, const int* __restrict__ lens, int q_tile_begin, int H, int causal, int kind, float scale_log2) {
+               const int* __restrict__ cu, const int* __restrict__ lens, int q_tile_begin, int H, int causal, float scale_log2) {
+  constexpr int kind = KIND;
   using C = AC<D>;
   constexpr int TILE_BYTES = C::TILE_BYTES, SMEM_Q = C::SMEM_Q, SMEM_K = C::SMEM_K, SMEM_V = C::SMEM_V, SMEM_P = C::SMEM_P, SMEM_BAR = C::SMEM_BAR;
   constexpr int TMEM_COLS = C::TMEM_COLS;
@@ -466,14 +469,19 @@ int launch_attn_tc(const CUtensorMap& tm, const CUtensorMap& tm32, void* out, in
                    int max_len, int q_tile_begin, int q_tile_end, int H, int causal, int kind, float scale, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    D3D_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, AC<D>::SMEM_BYTES));
+    D3D_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<D, D3D_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AC<D>::SMEM_BYTES));
+    D3D_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<D, D3D_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AC<D>::SMEM_BYTES));
     attr_set = true;
   }
   const int q_end = q_tile_end < d3d_cdiv(max_len, BQ) ? q_tile_end : d3d_cdiv(max_len, BQ);
   if (q_end <= q_tile_begin) return 0;
   dim3 grid(q_end - q_tile_begin, H, n_seq);
-  attn_tc_kernel<D><<<grid, NTHREADS, AC<D>::SMEM_BYTES, st>>>(tm, tm32, (uint16_t*)out, ldo, cu_seqlens, lens, q_tile_begin, H, causal, kind,
-                                                               scale * 1.4426950408889634f);
+  if (kind == D3D_BF16)
+    attn_tc_kernel<D, D3D_BF16><<<grid, NTHREADS, AC<D>::SMEM_BYTES, st>>>(tm, tm32, (uint16_t*)out, ldo, cu_seqlens, lens, q_tile_begin, H, causal,
+                                                                           scale * 1.4426950408889634f);
+  else
+    attn_tc_kernel<D, D3D_F16><<<grid, NTHREADS, AC<D>::SMEM_BYTES, st>>>(tm, tm32, (uint16_t*)out, ldo, cu_seqlens, lens, q_tile_begin, H, causal,
+                                                                          scale * 1.4426950408889634f);
   D3D_CHECK_LAUNCH();
   return 0;
 }

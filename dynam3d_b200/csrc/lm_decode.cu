@@ -506,7 +506,7 @@ extern "C" int d3d_lm_decode_step(const d3d_lm_model* m, void* const* qkv_layers
   D3D_CHECK_LAUNCH();
   D3D_TRY(d3d_rope_table(pos, inv_freq, n_seq, Dh, rope_tab, stream));
   const long long row0 = (long long)t_prefill + (long long)step * n_seq;
-  const float scale = 1.0f / sqrtf((float)Dh);
+  const float scale = (float)(1.0 / sqrt((double)Dh));  // same rounding as the prefill (double expression rounded once)
   for (int l = 0; l < m->n_layers; ++l) {
     const d3d_lm_layer& L = m->layers[l];
     uint16_t* rows = (uint16_t*)qkv_layers_h[l] + row0 * ld_qkv;
