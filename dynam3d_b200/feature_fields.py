@@ -755,6 +755,9 @@ class Feature_Fields(nn.Module):
         for ix in range(V):
             ws = self._workspace(int(lib.d3d_pool_workspace_bytes(8192, D, D)))  # merged / zone passes; the step pass already sized it
             c.workspace, c.workspace_bytes = ws.data_ptr(), ws.numel()
+            if TRACE is not None:
+                import time
+                t0 = time.perf_counter()
             L.check(lib.d3d_ff_view_pre(self._h, ix, ctypes.addressof(c), ctypes.cast(self._pool_table(rt), ctypes.c_void_p), cen, vf,
                                         ctypes.cast(sizes, ctypes.c_void_p), ctypes.cast(after, ctypes.c_void_p), L.stream_ptr()))
             t_mg, t_zn = int(sizes[2]) + int(sizes[1]), int(sizes[4]) + int(sizes[3])
@@ -769,7 +772,11 @@ class Feature_Fields(nn.Module):
                 ep.inst_pos.ensure(ep.n_inst); ep.inst_fts.ensure(ep.n_inst)
                 ep.zone_pos.ensure(ep.n_zone); ep.zone_fts.ensure(ep.n_zone)
                 ep.tree = ep.n_inst > 0
+            if TRACE is not None:
+                t1 = time.perf_counter()
             L.check(lib.d3d_ff_view_post(self._h, ctypes.addressof(c), ctypes.cast(self._pool_table(rt), ctypes.c_void_p), cen, vf, L.stream_ptr()))
+            if TRACE is not None:  # host wall times: pre (issue + device wait + planner), post (uploads + slot writes + merge pass issue)
+                TRACE.append(((t1 - t0) * 1e3, (time.perf_counter() - t1) * 1e3, int(sizes[0]), int(sizes[1]), t_mg, int(sizes[3]), t_zn))
         L.check(lib.d3d_ff_run_deferred(self._h, ctypes.addressof(c), L.stream_ptr()))
 
     def _run_deferred(self):
