@@ -35,8 +35,8 @@ def _compare_snap(a, b):
     dict(seed=3, n_steps=4, V=1, n_seg=16, kind="voronoi", B=1),
     dict(seed=5, n_steps=6, V=1, n_seg=48, kind="blocks", B=2),
     dict(seed=6, n_steps=2, V=12, n_seg=16, kind="voronoi", B=1),
-    dict(seed=3, n_steps=5, V=1, n_seg=16, kind="voronoi", B=1, merge_bias=0.3),   # the discriminator accepts proposals: merge path, re-encode
-    dict(seed=6, n_steps=2, V=12, n_seg=16, kind="voronoi", B=2, merge_bias=0.3),
+    dict(seed=3, n_steps=6, V=1, n_seg=16, kind="voronoi", B=1, merge_bias=0.6),   # the discriminator accepts proposals: merge path, re-encode
+    dict(seed=6, n_steps=2, V=12, n_seg=16, kind="voronoi", B=2, merge_bias=0.6),
 ])
 def test_engine_matches_oracle(cfg):
     from dynam3d_b200 import ops, synth
@@ -45,7 +45,11 @@ def test_engine_matches_oracle(cfg):
     from oracle import nn_ops as NN
     from oracle.ff_oracle import FeatureFieldsOracle
     B, V = cfg["B"], cfg["V"]
-    sd = _params(cfg["seed"], merge_bias=cfg.get("merge_bias", 0.0))
+    if cfg.get("merge_bias", 0.0) > 0:  # the weights the golden / long-horizon fixtures use: their discriminator does accept proposals at this bias
+        pol = synth.policy_state_dict(7, merge_bias=cfg["merge_bias"])
+        sd = {k[len("feature_fields."):]: v for k, v in pol.items() if k.startswith("feature_fields.")}
+    else:
+        sd = _params(cfg["seed"], merge_bias=0.0)
     eng = Feature_Fields(batch_size=B)
     eng.load_state_dict(sd, strict=True)
     orc = FeatureFieldsOracle(sd, batch_size=B, rnd=NN.round_fp16)
