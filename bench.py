@@ -265,7 +265,8 @@ def run_engine(args):
     # device-resident copies for the kernel-side number, pinned host copies for the end-to-end number
     dev_in = [{"rgb": torch.from_numpy(s["rgb"]).to(dev), "depth": torch.from_numpy(s["depth"]).to(dev), "patch_segm": s["segm"]} for s in steps]
     host_in = [{"rgb": torch.from_numpy(s["rgb"]).pin_memory(), "depth": torch.from_numpy(s["depth"]).pin_memory(), "patch_segm": s["segm"]} for s in steps]
-    pending = []   # in-flight all-gathers: episodes are independent (BASE:770), so the gather of step i overlaps step i+1
+    from dynam3d_b200.sharding import LogitsGather
+    gather_q = LogitsGather(depth=2)   # in-flight all-gathers: episodes are independent (BASE:770), so the gather of step i overlaps step i+1
 
     def one_step(i, inputs, gather=True):
         if args.generate:
@@ -273,15 +274,11 @@ def run_engine(args):
         else:
             lg = net.forward_logits(inputs[i], instr, steps[i]["pos"], steps[i]["head"], num_of_views=VIEWS)
         if world > 1 and gather:
-            out = torch.empty((world * E, lg.shape[1]), device=dev, dtype=lg.dtype)
-            pending.append((dist.all_gather_into_tensor(out, lg, async_op=True), out, lg))
-            while len(pending) > 2:  # at most two gathers in flight: bounds memory, never stalls the step that just finished
-                pending.pop(0)[0].wait()
+            gather_q.post(lg)  # at most two gathers in flight: bounds memory, never stalls the step that just finished
         return lg
 
     def drain():
-        while pending:
-            pending.pop(0)[0].wait()
+        gather_q.drain()
 
     def barrier():
         drain()

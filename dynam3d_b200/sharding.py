@@ -32,6 +32,44 @@ def allgather_last_logits(logits):
     return out
 
 
+class LogitsGather:
+    """The per-step all-gather of the batch's next-action logits, OFF the critical path: episodes are independent (the reference splits
+    trajectories by rank, base_il_trainer.py:770), so the gather of step i only has to be complete when somebody reads it.  `post()` issues
+    the collective asynchronously (NCCL: on its own stream behind the producing kernels; gloo: a background thread) and returns at once;
+    at most `depth` gathers are in flight (older ones are waited first, bounding memory); `drain()` waits for all and returns the results in
+    order.  Without a process group every call degenerates to the identity."""
+
+    def __init__(self, depth=2):
+        self.depth, self.pending, self.done = depth, [], []
+
+    def post(self, logits):
+        w = _world()
+        if w == 1:
+            self.done.append(logits)
+            return
+        out = torch.empty((w * logits.shape[0],) + tuple(logits.shape[1:]), device=logits.device, dtype=logits.dtype)
+        src = logits.contiguous()
+        if logits.is_cuda:
+            work = dist.all_gather_into_tensor(out, src, async_op=True)
+        else:
+            parts = list(out.chunk(w, 0))
+            work = dist.all_gather(parts, src, async_op=True)
+        self.pending.append((work, out, src))
+        while len(self.pending) > self.depth:
+            self._wait_one()
+
+    def _wait_one(self):
+        work, out, _ = self.pending.pop(0)
+        work.wait()
+        self.done.append(out)
+
+    def drain(self):
+        while self.pending:
+            self._wait_one()
+        res, self.done = self.done, []
+        return res
+
+
 def allgather_token_memory(tokens, max_tokens):
     """tokens: list (one per local episode) of [n_i, width] tensors.  Returns (padded [world*E, max_tokens, width], counts [world*E])
     on every rank -- the 'single NCCL all-gather for batched 3D-token memory' of the north star."""

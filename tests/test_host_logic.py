@@ -83,7 +83,12 @@ def _gloo_worker(rank, world, port, q):
     g = sharding.allgather_last_logits(logits)
     toks = [torch.full((3 + rank, 4), float(rank)), torch.full((1, 4), 10.0 + rank)]
     pad, cnt = sharding.allgather_token_memory(toks, max_tokens=6)
-    q.put((rank, mine, g.tolist(), pad.shape, cnt.tolist(), float(pad[2 * 1, 0, 0])))
+    # the bench's asynchronous form: three steps posted, at most two in flight, results in order
+    gq = sharding.LogitsGather(depth=2)
+    for step in range(3):
+        gq.post(torch.full((2, 5), float(10 * step + rank)))
+    outs = [o.tolist() for o in gq.drain()]
+    q.put((rank, mine, g.tolist(), pad.shape, cnt.tolist(), float(pad[2 * 1, 0, 0]), outs))
     dist.destroy_process_group()
 
 
@@ -101,6 +106,7 @@ def test_sharding_and_allgather_over_gloo_world2():
     for r in res:
         assert r[2] == [[0.0] * 5, [0.0] * 5, [1.0] * 5, [1.0] * 5]
         assert tuple(r[3]) == (4, 6, 4) and r[4] == [3, 1, 4, 1] and r[5] == 1.0
+        assert r[6] == [[[10.0 * s] * 5] * 2 + [[10.0 * s + 1] * 5] * 2 for s in range(3)]
 
 
 def test_toy_tokenizer_matches_character_scan():
