@@ -525,7 +525,7 @@ class Feature_Fields(nn.Module):
 
     # ------------------------------------------------------------------ FF:329-396
     def delete_old_features_from_camera_frustum(self, batch_depth, batch_position=None, batch_heading=None, batch_camera_intrinsic=None,
-                                                batch_extrinsic=None, num_of_views=1):
+                                                batch_extrinsic=None, num_of_views=1, _defer=False):
         """Habitat branch (batch_position / batch_heading given): batch_depth [B,V,H,W] metres (device tensor preferred).
         Posed-dataset branch (batch_camera_intrinsic / batch_extrinsic given, FF:343-344): batch_depth[b] [V,H,W] fp32 in the unit of the
         stored points, batch_camera_intrinsic[b][ix] [>=3,>=3], batch_extrinsic[b][ix] [4,4] world->camera; the far plane is
@@ -536,6 +536,22 @@ class Feature_Fields(nn.Module):
             raise ValueError("either batch_position/batch_heading (habitat) or batch_camera_intrinsic/batch_extrinsic (posed datasets) is required")
         V = num_of_views
         lib = L.lib()
+        if _defer and not posed:
+            # the policy step: issue the cull kernel + result copy now, let the caller queue other GPU work (the ViT), and run the host
+            # bookkeeping + tombstone writes from the returned callable -- the host part then overlaps that GPU work
+            with L.stream_scope():
+                if not any(ep.n_patch for ep in self.eps):
+                    L.check(lib.d3d_ffh_set_tree(self._h))
+                    return lambda: None
+                st = self._cull_habitat_issue(batch_depth, batch_position, batch_heading, V)
+
+            def finish():
+                ops.STAGE_TAG = "ff"
+                with L.stream_scope():
+                    pp_i, fp_i, pp_z, fp_z = [], [], [], []
+                    self._cull_habitat_finish(st, pp_i, fp_i, pp_z, fp_z)
+                    self._tombstone_slots(pp_i, fp_i, pp_z, fp_z)
+            return finish
         with L.stream_scope():
             if not any(ep.n_patch for ep in self.eps):
                 L.check(lib.d3d_ffh_set_tree(self._h))
@@ -569,14 +585,18 @@ class Feature_Fields(nn.Module):
                     L.check(lib.d3d_ffh_cull(self._h, b, mk.ctypes.data, ep.n_patch, di.ctypes.data, ctypes.addressof(nd), dz.ctypes.data,
                                              ctypes.addressof(nd) + 4))
                     self._dead_rows(ep, di, dz, nd, pp_i, fp_i, pp_z, fp_z)
-            # tombstone dead instance / zone slots on the device (FF:378-379, 392-393): one batched scatter per tensor kind
-            rows_p, rows_f = pp_i + pp_z, fp_i + fp_z
-            if rows_p:
-                pp, fp = np.concatenate(rows_p), np.concatenate(rows_f)
-                const = self._tomb_rows()
-                pp_d, fp_d, zi_d = self._upload([pp, fp, np.zeros(len(pp), np.int32)])
-                L.check(lib.d3d_scatter_rows_ptr(L.ptr(const[0]), 3, L.ptr(zi_d), L.ptr(pp_d), len(pp), 3, L.stream_ptr()))
-                L.check(lib.d3d_scatter_rows_ptr(L.ptr(const[1]), D, L.ptr(zi_d), L.ptr(fp_d), len(pp), D, L.stream_ptr()))
+            self._tombstone_slots(pp_i, fp_i, pp_z, fp_z)
+
+    def _tombstone_slots(self, pp_i, fp_i, pp_z, fp_z):
+        """Tombstone dead instance / zone slots on the device (FF:378-379, 392-393): one batched scatter per tensor kind."""
+        lib = L.lib()
+        rows_p, rows_f = pp_i + pp_z, fp_i + fp_z
+        if rows_p:
+            pp, fp = np.concatenate(rows_p), np.concatenate(rows_f)
+            const = self._tomb_rows()
+            pp_d, fp_d, zi_d = self._upload([pp, fp, np.zeros(len(pp), np.int32)])
+            L.check(lib.d3d_scatter_rows_ptr(L.ptr(const[0]), 3, L.ptr(zi_d), L.ptr(pp_d), len(pp), 3, L.stream_ptr()))
+            L.check(lib.d3d_scatter_rows_ptr(L.ptr(const[1]), D, L.ptr(zi_d), L.ptr(fp_d), len(pp), D, L.stream_ptr()))
 
     @staticmethod
     def _dead_rows(ep, di, dz, nd, pp_i, fp_i, pp_z, fp_z):
@@ -592,6 +612,10 @@ class Feature_Fields(nn.Module):
     def _cull_habitat(self, batch_depth, batch_position, batch_heading, V, pp_i, fp_i, pp_z, fp_z):
         """Habitat cull of all episodes: one kernel launch, device-side compaction of the culled rows, host bookkeeping over the culled rows
         only (csrc/geometry.cu: frustum_cull_batched_kernel; csrc/ff_host.cu: d3d_ffh_cull_list)."""
+        self._cull_habitat_finish(self._cull_habitat_issue(batch_depth, batch_position, batch_heading, V), pp_i, fp_i, pp_z, fp_z)
+
+    def _cull_habitat_issue(self, batch_depth, batch_position, batch_heading, V):
+        """Device half: the batched cull kernel and the copy of (counts, first culled rows) to pinned memory, followed by an event."""
         lib = L.lib()
         B = self.batch_size
         depth = self._as_dev(batch_depth, torch.float32).contiguous()
@@ -620,7 +644,15 @@ class Feature_Fields(nn.Module):
                                                  L.stream_ptr()))
         cb["cnt_h"].copy_(cb["cnt"], non_blocking=True)
         cb["idx_h"].copy_(cb["idx"][:, : self._CULL_HEAD], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        ev = torch.cuda.Event()
+        ev.record()
+        return cb, ev
+
+    def _cull_habitat_finish(self, state, pp_i, fp_i, pp_z, fp_z):
+        """Host half: wait for the result copy (an event, not the whole stream), then FF:362-393 over the culled rows of every episode."""
+        lib = L.lib()
+        cb, ev = state
+        ev.synchronize()
         cnt = cb["cnt_h"].numpy()
         nd = (ctypes.c_int * 2)()
         for b, ep in enumerate(self.eps):
@@ -656,31 +688,66 @@ class Feature_Fields(nn.Module):
         B = self.batch_size
         V = len(batch_depth[0]) if posed else num_of_views  # FF:520
         P = self.args.input_height * self.args.input_width
-        if batch_patch_segm is None:
+        if posed and batch_patch_segm is None:  # FF:504-506: one FastSAM call per episode
             if self.segmenter is None:
                 raise RuntimeError("no segmentation: pass batch_patch_segm or set .segmenter (FastSAM is not part of this engine)")
-            if posed:  # FF:504-506: one FastSAM call per episode
-                batch_patch_segm = np.stack([np.asarray(torch.as_tensor(self.segmenter(batch_image[b])).cpu()) for b in range(B)], 0)
-            else:
-                batch_patch_segm = self.segmenter(batch_image)
-        segm = np.ascontiguousarray(np.asarray(batch_patch_segm.cpu() if torch.is_tensor(batch_patch_segm) else batch_patch_segm)
-                                    .reshape(B, V, P).transpose(1, 0, 2), dtype=np.int64)  # [V,B,P]
+            batch_patch_segm = np.stack([np.asarray(torch.as_tensor(self.segmenter(batch_image[b])).cpu()) for b in range(B)], 0)
+        segm = self._segm_array(batch_patch_segm, batch_image, B, V, P)
         with L.stream_scope():
             if posed:
                 xyz, direction, scale = self._unproject_posed(batch_depth, batch_camera_intrinsic, batch_rot, batch_trans, depth_scale, depth_trunc, V)
                 if not torch.is_tensor(batch_grid_ft):
                     batch_grid_ft = np.stack([np.asarray(g) for g in batch_grid_ft], 0)
+                prep = self._update_issue(None, None, None, V, unprojected=(xyz, direction, scale))
             else:
+                prep = self._update_issue(batch_depth, batch_position, batch_heading, V)
+            self._update_run(prep, self._update_plan(prep, segm), batch_grid_ft)
+
+    def _segm_array(self, batch_patch_segm, batch_image, B, V, P):
+        """Dense segment labels as the planner wants them: int64 [V,B,P] (host).  None -> `self.segmenter(batch_image)` (FastSAM stand-in, FF:509)."""
+        if batch_patch_segm is None:
+            if self.segmenter is None:
+                raise RuntimeError("no segmentation: pass batch_patch_segm or set .segmenter (FastSAM is not part of this engine)")
+            batch_patch_segm = self.segmenter(batch_image)
+        return np.ascontiguousarray(np.asarray(batch_patch_segm.cpu() if torch.is_tensor(batch_patch_segm) else batch_patch_segm)
+                                    .reshape(B, V, P).transpose(1, 0, 2), dtype=np.int64)
+
+    # The habitat step in three phases, so the policy can queue the ViT between the first and the second and let the host planning overlap it:
+    #   _update_issue : unprojection kernel + copy of the patch positions to pinned memory + event          (device, before the ViT)
+    #   _update_plan  : wait for that event, C++ whole-step planner (needs positions + segmentation only)  (host, while the ViT runs)
+    #   _update_run   : append + centroids + ONE packed pooling pass + the view loop (needs the CLIP grid features: after the ViT)
+    def _update_issue(self, batch_depth, batch_position, batch_heading, V, unprojected=None):
+        B, P = self.batch_size, self.args.input_height * self.args.input_width
+        with L.stream_scope():
+            if unprojected is None:
                 depth = self._as_dev(batch_depth, torch.float32).reshape(B * V, P).contiguous()
                 pose = self._upload([ops.pose_rows(batch_position, batch_heading, V)])[0]
                 xyz, direction, scale = ops.unproject_habitat(depth, pose, self.args.input_hfov, self.args.input_vfov,
                                                               self.args.input_width, self.args.input_height)
+            else:
+                xyz, direction, scale = unprojected
+            n = B * V * P * 3
+            pin = getattr(self, "_xyz_pin", None)
+            if pin is None or pin.numel() < n:
+                pin = self._xyz_pin = torch.empty(max(n, 1), dtype=torch.float32).pin_memory()
+            pin[:n].copy_(xyz.reshape(-1), non_blocking=True)  # host mirror of the step's patch positions (one copy per step)
+            ev = torch.cuda.Event()
+            ev.record()
+        return {"xyz": xyz, "dir": direction, "scale": scale, "pin": pin, "event": ev, "B": B, "V": V, "P": P}
+
+    def _update_plan(self, prep, segm):
+        B, V, P = prep["B"], prep["V"], prep["P"]
+        prep["event"].synchronize()
+        xyz_h = np.ascontiguousarray(prep["pin"][: B * V * P * 3].numpy().reshape(B, V, P, 3).transpose(1, 0, 2, 3))  # [V,B,P,3]
+        return self._plan_step(V, P, segm, xyz_h)
+
+    def _update_run(self, prep, plan_h, batch_grid_ft):
+        B, V, P = prep["B"], prep["V"], prep["P"]
+        ops.STAGE_TAG = "ff"
+        with L.stream_scope():
             grid = self._as_dev(batch_grid_ft, torch.float16).reshape(B * V * P, D).contiguous()
-            xyz_h = xyz.to("cpu", non_blocking=True)  # host mirror of the step's patch positions (one copy per step)
-            torch.cuda.current_stream().synchronize()
-            xyz_h = np.ascontiguousarray(xyz_h.numpy().reshape(B, V, P, 3).transpose(1, 0, 2, 3))  # [V,B,P,3]
-            stage = {"xyz": xyz.view(B * V * P, 3), "dir": direction.view(-1), "scale": scale.view(-1), "fts": grid}
-            plan = self._begin_step(V, P, segm, stage, xyz_h)
+            stage = {"xyz": prep["xyz"].view(B * V * P, 3), "dir": prep["dir"].view(-1), "scale": prep["scale"].view(-1), "fts": grid}
+            plan = self._launch_step(V, P, stage, plan_h)
             if self.precise or os.environ.get("D3D_FF_PYTHON_VIEWS") == "1":
                 for ix in range(V):
                     self._update_view(ix, plan)
@@ -807,14 +874,12 @@ class Feature_Fields(nn.Module):
             raise ValueError(f"{bad} depth pixels are >= depth_trunc after scaling: open3d would drop them (feature_fields.py:55)")
         return xyz, direction, scale
 
-    def _begin_step(self, V, P, segm, stage, xyz_h):
-        """Everything of a step that does not depend on the memory state, for ALL views at once: append the step's patches to the episode
-        pools (FF:557-570) and pool every (view, episode, segment) sequence into its view-instance token (FF:580-601) as ONE packed batch.
-        `stage` holds the step's unprojected patches / CLIP features, unit u = b*V+ix occupying rows [u*P, (u+1)*P).
-        segm [V,B,P] int64, xyz_h [V,B,P,3] fp32 (host)."""
+    def _plan_step(self, V, P, segm, xyz_h):
+        """Host half of a step: everything that does not depend on the memory state NOR on the CLIP features, for ALL views at once (C++
+        planner): the patches are appended to the host mirrors and every (view, episode, segment) sequence of the packed pooling pass is
+        laid out.  segm [V,B,P] int64, xyz_h [V,B,P,3] fp32 (host)."""
         B = self.batch_size
         lib = L.lib()
-        eps = self.eps
         cap = V * B * P
         base_rows = np.zeros(B, np.int64); view_start = np.zeros(V + 1, np.int32)
         seq_owner = np.zeros(cap, np.int32); members = np.zeros(cap, np.int32); cu_m = np.zeros(cap + 1, np.int32)
@@ -823,7 +888,19 @@ class Feature_Fields(nn.Module):
         L.check(lib.d3d_ffh_begin_step(self._h, xyz_h.ctypes.data, segm.ctypes.data, P, V, base_rows.ctypes.data, view_start.ctypes.data,
                                        seq_owner.ctypes.data, members.ctypes.data, cu_m.ctypes.data, tok_src.ctypes.data, tok_seq.ctypes.data,
                                        cu_tok.ctypes.data, info.ctypes.data))
-        n_seq, max_len = int(info[0]), int(info[1])
+        return {"base_rows": base_rows, "view_start": view_start, "seq_owner": seq_owner, "members": members, "cu_m": cu_m, "tok_src": tok_src,
+                "tok_seq": tok_seq, "cu_tok": cu_tok, "n_seq": int(info[0]), "max_len": int(info[1])}
+
+    def _launch_step(self, V, P, stage, h):
+        """Device half: append the step's patches to the episode pools (FF:557-570) and pool every (view, episode, segment) sequence into its
+        view-instance token (FF:580-601) as ONE packed batch.  `stage` holds the step's unprojected patches / CLIP features, unit u = b*V+ix
+        occupying rows [u*P, (u+1)*P)."""
+        B = self.batch_size
+        lib = L.lib()
+        eps = self.eps
+        cap = V * B * P
+        base_rows, view_start, seq_owner, members, cu_m = h["base_rows"], h["view_start"], h["seq_owner"], h["members"], h["cu_m"]
+        tok_src, tok_seq, cu_tok, n_seq, max_len = h["tok_src"], h["tok_seq"], h["cu_tok"], h["n_seq"], h["max_len"]
         T = cap + n_seq
         # ---- append the step's patches to the episode pools: one batched block copy (4 pools x B episodes, V*P rows each) ----
         src, dst, nb = [], [], []
@@ -844,6 +921,9 @@ class Feature_Fields(nn.Module):
         centres = ops.seq_centroid(stage["xyz"], up[7], up[8], n_seq)  # fp64 accumulate, every sequence of the step in one launch
         view_fts = self._pool_tokens(0, up[3], centres, up[1], up[0], up[2], T, n_seq, max_len, 0, False)
         return {"view_start": view_start, "seq_owner": seq_owner[:n_seq], "centres": centres, "view_fts": view_fts}
+
+    def _begin_step(self, V, P, segm, stage, xyz_h):
+        return self._launch_step(V, P, stage, self._plan_step(V, P, segm, xyz_h))
 
     def _update_view(self, ix, plan):
         """The state-dependent part of one panorama view for all episodes in lock step: K-NN proposals, merge discriminator, then the

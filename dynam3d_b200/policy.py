@@ -408,11 +408,19 @@ class Dynam3D_VLN(nn.Module):
         depth = depth.reshape(n_img, H, W).contiguous()
         rgb = observations["rgb"].to(dev, non_blocking=True).contiguous()
         d576 = ops.depth_patch_grid(depth, B, V, ff.args.input_height, ff.args.input_width, literal_q1=not self.q1_fix)  # POL:336-341
-        _, grid = self.rgb_encoder({"rgb": rgb})  # POL:343-345, stays on device
+        # Order of issue (results are those of POL:343-354 in the reference's order: nothing below depends on what it is moved across):
+        # the cull kernel and the unprojection go to the GPU FIRST, the ViT is queued behind them, and the host halves of the cull
+        # (FF:362-393 bookkeeping) and of the update (whole-step planner) then run while the ViT occupies the GPU.
+        finish_cull = None
         if delete_old_features:
             full = ops.depth_preprocess(depth, depth_scale[0], depth_scale[1]).view(B, V, H, W)  # POL:350
-            ff.delete_old_features_from_camera_frustum(full, agent_positions, agent_heading_angles, num_of_views=V)
+            finish_cull = ff.delete_old_features_from_camera_frustum(full, agent_positions, agent_heading_angles, num_of_views=V, _defer=True)
+        prep = ff._update_issue(d576.view(B, V, P), agent_positions, agent_heading_angles, V)
+        _, grid = self.rgb_encoder({"rgb": rgb})  # POL:343-345, stays on device
+        if finish_cull is not None:
+            finish_cull()
         segm = observations.get("patch_segm") if hasattr(observations, "get") else None
+        plan_h = ff._update_plan(prep, ff._segm_array(segm, rgb, B, V, P))  # host planner: runs while the ViT is on the GPU
         # The LLaVA tower + projector of the view the LLM sees (Q13: view 0 of every episode) does not depend on the 3D memory:
         # run it on a side stream so it fills the GPU idle gaps of the (host-synchronised) memory update below.
         sel = torch.arange(B, device=dev) * V
@@ -439,8 +447,7 @@ class Dynam3D_VLN(nn.Module):
         if lm_head_ids is not None:
             L.lib().d3d_gemm_set_sm_limit(self.overlap_sms[1])
         try:
-            ff.update_feature_fields(d576.view(B, V, P), grid.reshape(B, V, P, 768), batch_image=rgb, batch_position=agent_positions,
-                                     batch_heading=agent_heading_angles, num_of_views=V, batch_patch_segm=segm)
+            ff._update_run(prep, plan_h, grid.reshape(B, V, P, 768))  # FF:493-815 (the phases of update_feature_fields)
         finally:
             L.lib().d3d_gemm_set_sm_limit(0)
         env = ff.get_environment_features(agent_positions, agent_heading_angles)
