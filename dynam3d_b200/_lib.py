@@ -140,6 +140,7 @@ SIGNATURES = {
     "d3d_cast16": [_P, _L, _P, _L, _I, _I, _I, _P],
     "d3d_attention_simt": [_P, _L, _P, _L, _P, _I, _I, _I, _I, _I, _I, _F, _P],
     "d3d_attention_mma": [_P, _L, _P, _L, _P, _I, _I, _I, _I, _I, _I, _F, _P],
+    "d3d_attention_mixed": [_P, _L, _P, _L, _P, _I, _I, _I, _I, _I, _F, _P],
     "d3d_attention_tc": [_P, _L, _L, _P, _L, _P, _I, _I, _I, _I, _I, _I, _F, _P],
     "d3d_pool_features": [_P, _P, _P, _P, _P, _P, _I, _I, _P, _I, _P],
     "d3d_pool_assemble": [_P, _P, _I, _P, _P, _P, _I, _I, _P, _P],

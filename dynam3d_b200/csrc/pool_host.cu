@@ -4,6 +4,10 @@
 // Reference: FF:580-597, 662-688, 717-730, 743-756 (one encoder call per segment / zone there).
 #include "common.cuh"
 
+// in-library (C++ linkage): pool_kernels.cu
+int d3d_pool_assemble_cast(const float* emb, const int64_t* seq_fts, int fts_is_f32, const int* tok_seq, const int* tok_src, const float* agg,
+                           int T, int D, float* X, void* X16, int kind, void* stream);
+
 extern "C" {
 int d3d_gemm(const d3d_gemm_args* args_h, void* stream);
 int d3d_layernorm(const float* x, int64_t ldx, const int* row_index, const float* gamma, const float* beta, float eps, int T, int D, int act,
@@ -87,14 +91,15 @@ extern "C" int d3d_pool_tokens(const d3d_pool_level* lvl_h, const int64_t* seq_p
 
   D3D_TRY(d3d_pool_features(seq_ptrs, seq_ptrs + n_seq, seq_ptrs + 2 * (size_t)n_seq, centre, tok_seq, tok_src, T, mode, A0, kind, stream));
   D3D_TRY(d3d_mlp_ln_gelu(&L.mlp, A0, 8, T, h32, h16, emb, D, stream));
-  D3D_TRY(d3d_pool_assemble(emb, seq_ptrs + 3 * (size_t)n_seq, fts_is_f32, tok_seq, tok_src, L.agg, T, D, X, stream));
-  D3D_TRY(d3d_cast16(X, D, A16, D, T, D, kind, stream));
+  D3D_TRY(d3d_pool_assemble_cast(emb, seq_ptrs + 3 * (size_t)n_seq, fts_is_f32, tok_seq, tok_src, L.agg, T, D, X, A16, kind, stream));
   const int Dh = D / L.n_head;
   const float scale = 1.0f / sqrtf((float)Dh);
   for (int l = 0; l < L.n_layers; ++l) {
     const d3d_encoder_layer& e = L.layers[l];
     D3D_TRY(gemm(A16, D, e.w_in, D, qkv, 3 * D, T, 3 * D, D, kind, kind, e.b_in, D3D_ACT_NONE, nullptr, 0, stream));
-    if (max_len >= 64)
+    if (max_len >= 64 && Dh == 64)  // mixed lengths: short sequences one warp per (sequence, head), long ones on the 128-row kernel
+      D3D_TRY(d3d_attention_mixed(qkv, 3 * D, att, D, cu_seqlens, n_seq, max_len, L.n_head, Dh, kind, scale, stream));
+    else if (max_len >= 64)
       D3D_TRY(d3d_attention_mma(qkv, 3 * D, att, D, cu_seqlens, n_seq, max_len, L.n_head, Dh, 0, kind, scale, stream));
     else
       D3D_TRY(d3d_attention_simt(qkv, 3 * D, att, D, cu_seqlens, n_seq, max_len, L.n_head, Dh, 0, kind, scale, stream));

@@ -50,26 +50,38 @@ __global__ void pool_features_kernel(const long long* __restrict__ seq_xyz, cons
   reinterpret_cast<uint4*>(out)[t] = p;
 }
 
-// X[t] = (src < 0) ? agg : emb[t] + fts[src]   (FF:592-593, 674-676, 725-727); fts rows are fp16 (patches) or fp32 (instances)
+// X[t] = (src < 0) ? agg : emb[t] + fts[src]   (FF:592-593, 674-676, 725-727); fts rows are fp16 (patches) or fp32 (instances).
+// X16 (optional) receives the same rows rounded to the GEMM operand type, so the first layer needs no separate cast pass.
 __global__ void pool_assemble_kernel(const float* __restrict__ emb, const long long* __restrict__ seq_fts, int fts_is_f32,
                                      const int* __restrict__ tok_seq, const int* __restrict__ tok_src, const float* __restrict__ agg, int T,
-                                     int D, float* __restrict__ X) {
+                                     int D, float* __restrict__ X, void* __restrict__ X16, int kind) {
   const int t = blockIdx.x;
   if (t >= T) return;
   const int src = tok_src[t];
-  float* dst = X + (size_t)t * D;
-  if (src < 0) {
-    for (int c = threadIdx.x; c < D; c += blockDim.x) dst[c] = agg[c];
-    return;
-  }
-  const int s = tok_seq[t];
-  const float* e = emb + (size_t)t * D;
-  if (fts_is_f32) {
-    const float* f = reinterpret_cast<const float*>(seq_fts[s]) + (size_t)src * D;
-    for (int c = threadIdx.x; c < D; c += blockDim.x) dst[c] = f[c] + e[c];
-  } else {
-    const __half* f = reinterpret_cast<const __half*>(seq_fts[s]) + (size_t)src * D;
-    for (int c = threadIdx.x; c < D; c += blockDim.x) dst[c] = __half2float(f[c]) + e[c];
+  float4* dst = reinterpret_cast<float4*>(X + (size_t)t * D);
+  uint2* dst16 = X16 ? reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(X16) + (size_t)t * D) : nullptr;
+  const int n4 = D >> 2;  // D % 4 == 0 (checked by the entry)
+  const float4* e = reinterpret_cast<const float4*>(emb + (size_t)t * D);
+  const int s = src < 0 ? 0 : tok_seq[t];
+  const float4* f32 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(seq_fts[s]) + (size_t)(src < 0 ? 0 : src) * D);
+  const uint2* f16 = reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(seq_fts[s]) + (size_t)(src < 0 ? 0 : src) * D);
+  for (int c = threadIdx.x; c < n4; c += blockDim.x) {
+    float4 v;
+    if (src < 0) {
+      v = reinterpret_cast<const float4*>(agg)[c];
+    } else {
+      const float4 a = e[c];
+      if (fts_is_f32) {
+        const float4 b = f32[c];
+        v = make_float4(b.x + a.x, b.y + a.y, b.z + a.z, b.w + a.w);
+      } else {
+        const uint2 b = f16[c];
+        const float2 b0 = __half22float2(*reinterpret_cast<const __half2*>(&b.x)), b1 = __half22float2(*reinterpret_cast<const __half2*>(&b.y));
+        v = make_float4(b0.x + a.x, b0.y + a.y, b1.x + a.z, b1.y + a.w);
+      }
+    }
+    dst[c] = v;
+    if (dst16) dst16[c] = make_uint2(pack16x2(v.x, v.y, kind), pack16x2(v.z, v.w, kind));
   }
 }
 
@@ -150,13 +162,20 @@ extern "C" int d3d_pool_features(const int64_t* seq_xyz, const int64_t* seq_dir,
   return 0;
 }
 
-extern "C" int d3d_pool_assemble(const float* emb, const int64_t* seq_fts, int fts_is_f32, const int* tok_seq, const int* tok_src,
-                                 const float* agg, int T, int D, float* X, void* stream) {
+// X16 != nullptr also writes the rows in the 16-bit operand type `kind` (in-library callers; the public entry below keeps its signature)
+int d3d_pool_assemble_cast(const float* emb, const int64_t* seq_fts, int fts_is_f32, const int* tok_seq, const int* tok_src, const float* agg,
+                           int T, int D, float* X, void* X16, int kind, void* stream) {
   if (T == 0) return 0;
   D3D_REQUIRE(emb && seq_fts && tok_seq && tok_src && agg && X, "args");
-  pool_assemble_kernel<<<T, 256, 0, (cudaStream_t)stream>>>(emb, (const long long*)seq_fts, fts_is_f32, tok_seq, tok_src, agg, T, D, X);
+  D3D_REQUIRE(D % 4 == 0 && ((uintptr_t)emb % 16) == 0 && ((uintptr_t)X % 16) == 0 && ((uintptr_t)agg % 16) == 0, "width % 4, 16-byte rows");
+  pool_assemble_kernel<<<T, 192, 0, (cudaStream_t)stream>>>(emb, (const long long*)seq_fts, fts_is_f32, tok_seq, tok_src, agg, T, D, X, X16, kind);
   D3D_CHECK_LAUNCH();
   return 0;
+}
+
+extern "C" int d3d_pool_assemble(const float* emb, const int64_t* seq_fts, int fts_is_f32, const int* tok_seq, const int* tok_src,
+                                 const float* agg, int T, int D, float* X, void* stream) {
+  return d3d_pool_assemble_cast(emb, seq_fts, fts_is_f32, tok_seq, tok_src, agg, T, D, X, nullptr, D3D_F16, stream);
 }
 
 extern "C" int d3d_disc_input(const float* inst_fts, const float* inst_pos, const int* idx, const float* view_fts, const float* centre,

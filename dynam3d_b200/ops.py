@@ -401,7 +401,8 @@ def attention_simt(qkv, out, cu_seqlens, n_seq, max_len, H, Dh, causal=False, sc
 
 
 def attention(qkv, out, cu_seqlens, n_seq, max_len, H, Dh, causal=False, uniform_len=None, impl="auto"):
-    """Self-attention over packed sequences.  `impl`: 'tc' (tcgen05, head_dim 64 / 96), 'mma' (legacy tensor cores), 'simt' (fp32
+    """Self-attention over packed sequences.  `impl`: 'tc' (tcgen05, head_dim 64 / 96), 'mma' (legacy tensor cores), 'mixed' (head_dim 64,
+    non-causal: sequences of <= 64 tokens one warp per (sequence, head), longer ones on the mma kernel -- the pooling passes), 'simt' (fp32
     CUDA cores) or 'auto' (tc for long head_dim-64 / 96 sequences, mma otherwise, simt for very short ones)."""
     scale = 1.0 / math.sqrt(Dh)
     # algorithmic FLOPs of the launch (QK^T + PV), assuming equal-length sequences (exact for the ViT, ~2 % high for the packed LM batch)
@@ -410,6 +411,9 @@ def attention(qkv, out, cu_seqlens, n_seq, max_len, H, Dh, causal=False, uniform
         if impl == "tc" or (impl == "auto" and Dh in (64, 96) and max_len >= 256):
             L.check(L.lib().d3d_attention_tc(L.ptr(qkv), qkv.stride(0), qkv.shape[0], L.ptr(out), out.stride(0), L.ptr(cu_seqlens), n_seq, max_len, H, Dh,
                                              int(bool(causal)), L.kind_of(qkv.dtype), scale, L.stream_ptr()))
+        elif impl == "mixed":
+            L.check(L.lib().d3d_attention_mixed(L.ptr(qkv), qkv.stride(0), L.ptr(out), out.stride(0), L.ptr(cu_seqlens), n_seq, max_len, H, Dh,
+                                                L.kind_of(qkv.dtype), scale, L.stream_ptr()))
         elif impl == "mma" or (impl == "auto" and Dh in (64, 96) and max_len >= 64):
             L.check(L.lib().d3d_attention_mma(L.ptr(qkv), qkv.stride(0), L.ptr(out), out.stride(0), L.ptr(cu_seqlens), n_seq, max_len, H, Dh,
                                               int(bool(causal)), L.kind_of(qkv.dtype), scale, L.stream_ptr()))

@@ -330,6 +330,10 @@ int d3d_attention_simt(const void* qkv, int64_t ld, void* out, int64_t ldo, cons
  * d3d_attention_simt; used for CLIP ViT (CLIPM:181-183) and the causal Phi-3 prefill.  Rows must be 16-byte aligned. */
 int d3d_attention_mma(const void* qkv, int64_t ld, void* out, int64_t ldo, const int* cu_seqlens, int n_seq, int max_len, int H,
                       int Dh, int causal, int kind, float scale, void* stream);
+/* Non-causal, head_dim 64, for packed batches that mix many short sequences with a few long ones (the patch -> instance pooling pass of a
+ * step: ~1 500 sequences of ~37 tokens): sequences of <= 64 tokens run one warp per (sequence, head), the others on the 128-row kernel. */
+int d3d_attention_mixed(const void* qkv, int64_t ld, void* out, int64_t ldo, const int* cu_seqlens, int n_seq, int max_len, int H, int Dh,
+                        int kind, float scale, void* stream);
 
 /* tcgen05 flash attention (S = QK^T and O = PV on the 5th-gen tensor cores, accumulators in TMEM, Q/K/V tiles by TMA), head_dim 64
  * (CLIP ViT / LLaVA tower) or 96 (Phi-3: 64 + 32 column swizzle atoms), non-causal or causal; same packed-QKV contract as

@@ -87,6 +87,31 @@ def test_attention_matches_torch(lens, H, Dh, causal, dtype, impl):
         s += n
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("lens", [[1, 2, 33, 64, 65, 300, 130, 16, 17, 48], [37] * 1500 + [100, 3], [5, 64, 1, 31]])
+def test_attention_mixed_lengths(lens, dtype):
+    """The pooling passes' dispatch (short sequences on the warp-per-(sequence, head) kernel, long ones on the 128-row kernel) vs fp32 torch,
+    and identical within 16-bit rounding to the single-kernel path it replaces."""
+    from dynam3d_b200 import ops
+    H, Dh = 12, 64
+    T = sum(lens)
+    qkv = (torch.randn(T, 3 * H * Dh, device="cuda") * 0.7).to(dtype)
+    out = torch.full((T, H * Dh), float("nan"), device="cuda", dtype=dtype)
+    one = torch.zeros_like(out)
+    cu = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), device="cuda", dtype=torch.int32)
+    ops.attention(qkv, out, cu, len(lens), max(lens), H, Dh, impl="mixed")
+    ops.attention(qkv, one, cu, len(lens), max(lens), H, Dh, impl="mma" if max(lens) >= 64 else "simt")
+    assert torch.isfinite(out.float()).all()
+    tol = 3e-3 if dtype == torch.float16 else 2e-2
+    assert (out.float() - one.float()).abs().max().item() < tol
+    s = 0
+    for n in lens[:12]:
+        q, k, v = [t.view(n, H, Dh).transpose(0, 1).float() for t in qkv[s:s + n].split(H * Dh, -1)]
+        ref = F.scaled_dot_product_attention(q[None], k[None], v[None])[0].transpose(0, 1).reshape(n, H * Dh)
+        assert (out[s:s + n].float() - ref).abs().max().item() < tol, n
+        s += n
+
+
 @pytest.mark.parametrize("size", [336, 224])
 def test_preprocess_im2col(size):
     from dynam3d_b200 import ops
