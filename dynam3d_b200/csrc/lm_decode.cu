@@ -12,6 +12,12 @@
 //                         loads), batched online softmax, 16-way merge in smem.
 //   argmax_kernel       : first maximum of every logit row (torch.argmax / HF greedy tie-break).
 //   d3d_lm_decode_step  : the whole step (32 layers) behind ONE C call, so the host issues ~260 launches without interpreter overhead.
+// Programmatic dependent launch: every kernel of the step is launched with programmaticStreamSerialization and triggers its dependents at
+// once, so kernel i+1 is resident while kernel i still runs: its producer warp streams WEIGHTS (which no kernel writes) into its shared-memory
+// ring, and only the threads that touch activations execute griddepcontrol.wait.  HBM stays busy across the ~260 kernel boundaries of a
+// step instead of draining and refilling at each (a 19..100 MB weight matrix is a 3..15 us stream; the boundary cost was of that order).
+#include <cmath>
+
 #include "common.cuh"
 
 extern "C" int d3d_rmsnorm(const float* x, int64_t ldx, const int* row_index, const float* w, float eps, int T, int D, float* out32,
@@ -20,6 +26,24 @@ extern "C" int d3d_rope_table(const int* pos, const float* inv_freq, int T, int 
 extern "C" int d3d_rope_apply(void* qkv, int64_t ld, const float* tab, int T, int H, int Dh, int kind, void* stream);
 
 namespace {
+
+// PDL device side: no-ops when the kernel was launched without the attribute
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool g_decode_pdl = true;
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_decode_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 constexpr int SK_WARPS = 8;
 // tuning knobs (template parameters of the kernel, chosen per problem in skinny()):
@@ -208,6 +232,7 @@ __global__ void __launch_bounds__(288) skinny_bulk_kernel(const uint16_t* __rest
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (N + BK_ROWS - 1) / BK_ROWS;
   const int n_stages = (K + BK_KC - 1) / BK_KC;
+  pdl_trigger();  // the next kernel of the chain may become resident and start on ITS weights
   if (threadIdx.x == 0) {
     for (int s = 0; s < BK_STAGES; ++s) { bk_mbar_init(bar0 + 8 * s, 1); bk_mbar_init(bar0 + 8 * (BK_STAGES + s), SK_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -234,6 +259,7 @@ __global__ void __launch_bounds__(288) skinny_bulk_kernel(const uint16_t* __rest
     }
   } else {
     // ===== consumers: warp w owns K elements [64w, 64w + 64) of every stage =====
+    pdl_wait();  // A (and the residual / C rows) belong to the kernels before this one; the producer above never touches them
     const int g = lane >> 2, kq = lane & 3;
     const bool lo_ok = g < M, hi_ok = HI && g + 8 < M;
     const uint16_t* a_lo_p = A + (long long)(lo_ok ? g : 0) * lda + warp * 64 + kq * 8;
@@ -301,6 +327,8 @@ __global__ void __launch_bounds__(DA_WARPS * 32, 1) decode_attn_kernel(const uin
                                                                    uint16_t* __restrict__ out, long long ldo) {
   constexpr int ACTIVE = DH / 4;  // lanes that hold 4 consecutive channels (8-byte loads); the other lanes idle (head_dim 96: 24 of 32)
   __shared__ float s_m[DA_WARPS], s_l[DA_WARPS], s_acc[DA_WARPS][DH];
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x, h = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool on = lane < ACTIVE;
@@ -373,9 +401,139 @@ __global__ void __launch_bounds__(DA_WARPS * 32, 1) decode_attn_kernel(const uin
   }
 }
 
+// Staged decode attention: the same arithmetic, but every warp streams ITS key blocks (16 keys = K and V head slices, 4*DH bytes per key)
+// through a private double buffer in shared memory with 16-byte cp.async -- 12 KB in flight per warp instead of the 3 KB the register-
+// staged kernel can hold, 192 KB per SM at two CTAs.  (cp.async.bulk per 192-byte row piece was tried and lost: ~3 000 bulk requests per
+// CTA saturate the copy engine, 4.2 ms per step vs 3.6.)  Under programmatic dependent launch a warp issues its first two blocks -- OLD
+// cache rows, which nothing in flight writes -- before griddepcontrol.wait, i.e. while this step's QKV GEMM / RoPE still run; only the block
+// that holds the newest key and the query row wait for them.
+constexpr int DC_WARPS = 8;
+constexpr int DC_KEYS = 16;
+__device__ __forceinline__ void dc_cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+template <int DH>
+__global__ void __launch_bounds__(DC_WARPS * 32) decode_attn_staged_kernel(const uint16_t* __restrict__ qkv, long long ld, const int* __restrict__ cu,
+                                                                           int n_seq, int t_prefill, int step, int H, int kind, float scale,
+                                                                           uint16_t* __restrict__ out, long long ldo) {
+  constexpr int ACTIVE = DH / 4;
+  constexpr int ROWB = DH * 4;            // K then V head slice of one key, bytes
+  constexpr int CPK = ROWB / 16;          // 16-byte chunks per key
+  constexpr int HALF = CPK / 2;           // ... of which the first half is K
+  constexpr int BLOCK_BYTES = DC_KEYS * ROWB;
+  extern __shared__ __align__(128) uint8_t dc_smem[];
+  __shared__ float s_m[DC_WARPS], s_l[DC_WARPS], s_acc[DC_WARPS][DH];
+  const int b = blockIdx.x, h = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
+  const int p0 = cu[b], n_pre = cu[b + 1] - p0;  // cu_seqlens: uploaded before the prefill, constant during generation
+  const int n_keys = n_pre + step + 1;
+  const int n_blk = (n_keys + DC_KEYS - 1) / DC_KEYS;
+  const uint32_t wbase = smem_u32(dc_smem) + (uint32_t)warp * 2u * BLOCK_BYTES;
+  const long long k_col = (long long)(H + h) * DH, v_col = (long long)(2 * H + h) * DH;
+  bool waited = false;
+  auto issue = [&](int blk, int buf) {  // one commit group per call (possibly empty)
+    if (blk < n_blk) {
+      if (blk == n_blk - 1 && !waited) { pdl_wait(); waited = true; }  // the newest key row comes from this step's QKV GEMM + RoPE
+      for (int c = lane; c < DC_KEYS * CPK; c += 32) {
+        const int key = c / CPK, ch = c - key * CPK;
+        const int j = blk * DC_KEYS + key;
+        if (j < n_keys) {
+          const long long row = j < n_pre ? (long long)(p0 + j) : (long long)t_prefill + (long long)(j - n_pre) * n_seq + b;
+          const uint16_t* src = qkv + row * ld + (ch < HALF ? k_col + ch * 8 : v_col + (ch - HALF) * 8);
+          dc_cp_async16(wbase + (uint32_t)(buf * BLOCK_BYTES + key * ROWB + ch * 16), src);
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  issue(warp, 0);
+  issue(warp + DC_WARPS, 1);
+  if (!waited) { pdl_wait(); waited = true; }
+  const bool on = lane < ACTIVE;
+  const long long q_row = (long long)t_prefill + (long long)step * n_seq + b;
+  float q[4];
+  {
+    const uint2 v = on ? *reinterpret_cast<const uint2*>(qkv + q_row * ld + (long long)h * DH + lane * 4) : make_uint2(0, 0);
+    const float2 a = unpack16x2(v.x, kind), c = unpack16x2(v.y, kind);
+    q[0] = a.x * scale; q[1] = a.y * scale; q[2] = c.x * scale; q[3] = c.y * scale;
+  }
+  float m = -INFINITY, l = 0.f, acc[4] = {0.f, 0.f, 0.f, 0.f};
+  int buf = 0;
+  for (int blk = warp; blk < n_blk; blk += DC_WARPS, buf ^= 1) {
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncwarp();
+    const uint32_t st = wbase + (uint32_t)(buf * BLOCK_BYTES) + (uint32_t)lane * 8u;
+    const int nvalid = min(DC_KEYS, n_keys - blk * DC_KEYS);
+#pragma unroll
+    for (int b8 = 0; b8 < DC_KEYS; b8 += DA_U) {
+      if (b8 >= nvalid) break;  // warp-uniform
+      float kf[DA_U][4], vf[DA_U][4], sc[DA_U];
+#pragma unroll
+      for (int u = 0; u < DA_U; ++u) {
+        uint2 kv = make_uint2(0, 0), vv = make_uint2(0, 0);
+        if (on && b8 + u < nvalid) {  // rows past nvalid were never written
+          asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(kv.x), "=r"(kv.y) : "r"(st + (uint32_t)((b8 + u) * ROWB)));
+          asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(vv.x), "=r"(vv.y) : "r"(st + (uint32_t)((b8 + u) * ROWB + DH * 2)));
+        }
+        const float2 k0 = unpack16x2(kv.x, kind), k1 = unpack16x2(kv.y, kind), v0 = unpack16x2(vv.x, kind), v1 = unpack16x2(vv.y, kind);
+        kf[u][0] = k0.x; kf[u][1] = k0.y; kf[u][2] = k1.x; kf[u][3] = k1.y;
+        vf[u][0] = v0.x; vf[u][1] = v0.y; vf[u][2] = v1.x; vf[u][3] = v1.y;
+      }
+#pragma unroll
+      for (int u = 0; u < DA_U; ++u) sc[u] = (q[0] * kf[u][0] + q[1] * kf[u][1]) + (q[2] * kf[u][2] + q[3] * kf[u][3]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int u = 0; u < DA_U; ++u) sc[u] += __shfl_xor_sync(0xffffffffu, sc[u], o);
+      float mx = m;
+#pragma unroll
+      for (int u = 0; u < DA_U; ++u) {
+        if (b8 + u >= nvalid) sc[u] = -INFINITY;
+        mx = fmaxf(mx, sc[u]);
+      }
+      const float c = __expf(m - mx);  // 0 on the first batch (m = -inf)
+      l *= c;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] *= c;
+#pragma unroll
+      for (int u = 0; u < DA_U; ++u) {
+        const float p = __expf(sc[u] - mx);
+        l += p;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] += p * vf[u][i];
+      }
+      m = mx;
+    }
+    __syncwarp();  // every lane is done with this buffer before it is refilled
+    issue(blk + 2 * DC_WARPS, buf);
+  }
+  if (lane == 0) { s_m[warp] = m; s_l[warp] = l; }
+  if (on) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s_acc[warp][lane * 4 + i] = acc[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < DH) {
+    float gm = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < DC_WARPS; ++w) gm = fmaxf(gm, s_m[w]);
+    float num = 0.f, den = 0.f;
+#pragma unroll
+    for (int w = 0; w < DC_WARPS; ++w) {
+      const float c = s_m[w] == -INFINITY ? 0.f : __expf(s_m[w] - gm);
+      num += c * s_acc[w][threadIdx.x];
+      den += c * s_l[w];
+    }
+    st16(out, (size_t)((long long)b * ldo + (long long)h * DH + threadIdx.x), num / den, kind);
+  }
+}
+
 __global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ x, long long ld, int n, int* __restrict__ out) {
   __shared__ float sv[32];
   __shared__ int si[32];
+  pdl_trigger();
+  pdl_wait();
   const float* r = x + (long long)blockIdx.x * ld;
   float best = -INFINITY;
   int bi = 0x7fffffff;
@@ -406,12 +564,78 @@ __global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ 
 __global__ void decode_prep_kernel(const void* __restrict__ table, int kind, const int* __restrict__ ids, const int* __restrict__ cu, int step, int D,
                                    float* __restrict__ x, int* __restrict__ pos) {
   const int b = blockIdx.x;
+  pdl_trigger();
+  pdl_wait();
   if (threadIdx.x == 0) pos[b] = cu[b + 1] - cu[b] + step;
   const size_t src = (size_t)ids[b] * D;
   for (int c = threadIdx.x; c < D; c += blockDim.x) x[(long long)b * D + c] = ld16(table, src + c, kind);
 }
 
+// rows of the step's tokens: the same arithmetic (and summation order) as rmsnorm_kernel / rope_table_kernel / rope_apply_kernel of
+// nn_kernels.cu, which the prefill uses -- a cache row written by a decode step is bit-identical to the one a prefill would write
+__global__ void __launch_bounds__(256) dec_rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w, float eps, int T, int D,
+                                                          uint16_t* __restrict__ out16, int kind) {
+  pdl_trigger();
+  pdl_wait();
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= T) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * D);
+  const int n4 = D / 128;  // float4 per lane
+  float q = 0.f;
+  for (int i = 0; i < n4; ++i) {
+    const float4 v = xr[lane + 32 * i];
+    q += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+  }
+  const float r = 1.0f / sqrtf(warp_sum(q) / (float)D + eps);
+  for (int i = 0; i < n4; ++i) {
+    const int c4 = lane + 32 * i;
+    const float4 v = xr[c4], g = reinterpret_cast<const float4*>(w)[c4];
+    reinterpret_cast<uint2*>(out16 + (long long)row * D)[c4] =
+        make_uint2(pack16x2(v.x * r * g.x, v.y * r * g.y, kind), pack16x2(v.z * r * g.z, v.w * r * g.w, kind));
+  }
+}
+
+__global__ void dec_rope_table_kernel(const int* __restrict__ pos, const float* __restrict__ inv_freq, int T, int half, float* __restrict__ tab) {
+  pdl_trigger();
+  pdl_wait();
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= T * half) return;
+  const int t = idx / half, i = idx - t * half;
+  float sn, cs;
+  sincosf((float)pos[t] * inv_freq[i], &sn, &cs);
+  tab[(size_t)t * 2 * half + i] = cs;
+  tab[(size_t)t * 2 * half + half + i] = sn;
+}
+
+__global__ void dec_rope_apply_kernel(uint16_t* __restrict__ qkv, long long ld, const float* __restrict__ tab, int T, int H, int Dh, int kind) {
+  pdl_trigger();
+  pdl_wait();
+  const int half = Dh / 2, groups = half / 8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)T * 2 * H * groups) return;
+  const int g = (int)(idx % groups);
+  const int h = (int)((idx / groups) % (2 * H));  // q heads then k heads
+  const int t = (int)(idx / ((long long)groups * 2 * H));
+  uint16_t* base = qkv + (size_t)t * ld + (size_t)h * Dh + g * 8;
+  const float4* cs = reinterpret_cast<const float4*>(tab + (size_t)t * Dh + g * 8);
+  const float4* sn = reinterpret_cast<const float4*>(tab + (size_t)t * Dh + half + g * 8);
+  const float4 c0 = cs[0], c1 = cs[1], s0 = sn[0], s1 = sn[1];
+  const float c[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w}, s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+  const uint4 av = *reinterpret_cast<const uint4*>(base), bv = *reinterpret_cast<const uint4*>(base + half);
+  const uint32_t aw[4] = {av.x, av.y, av.z, av.w}, bw[4] = {bv.x, bv.y, bv.z, bv.w};
+  uint32_t ao[4], bo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 a = unpack16x2(aw[j], kind), b = unpack16x2(bw[j], kind);
+    ao[j] = pack16x2(__fsub_rn(__fmul_rn(a.x, c[2 * j]), __fmul_rn(b.x, s[2 * j])), __fsub_rn(__fmul_rn(a.y, c[2 * j + 1]), __fmul_rn(b.y, s[2 * j + 1])), kind);
+    bo[j] = pack16x2(__fadd_rn(__fmul_rn(b.x, c[2 * j]), __fmul_rn(a.x, s[2 * j])), __fadd_rn(__fmul_rn(b.y, c[2 * j + 1]), __fmul_rn(a.y, s[2 * j + 1])), kind);
+  }
+  *reinterpret_cast<uint4*>(base) = make_uint4(ao[0], ao[1], ao[2], ao[3]);
+  *reinterpret_cast<uint4*>(base + half) = make_uint4(bo[0], bo[1], bo[2], bo[3]);
+}
+
 int g_skinny_cfg = 0;
+int g_decode_attn_impl = 1;  // 1: cp.async-staged, 0: register-staged (A/B)
 
 int skinny(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N, int K, int kind, int out_kind,
            const float* bias, int act, const float* residual, long long ldres, cudaStream_t st) {
@@ -439,6 +663,7 @@ int skinny(const void* A, long long lda, const void* W, long long ldw, void* C, 
     case 8: SK_LAUNCH(4, 1, true); break;
     case 9: SK_LAUNCH(2, 1, true); break;
     case 10:
+    case 11:
     bulk: {  // bulk-copy (cp.async.bulk + mbarrier ring) variant
       static bool attr = false;
       if (!attr) {
@@ -446,9 +671,11 @@ int skinny(const void* A, long long lda, const void* W, long long ldw, void* C, 
         D3D_CHECK_CUDA(cudaFuncSetAttribute(skinny_bulk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM));
         attr = true;
       }
-      const int tiles = d3d_cdiv(N, BK_ROWS), grid = tiles < 2 * d3d_num_sms() ? tiles : 2 * d3d_num_sms();  // two resident CTAs per SM
-      if (M > 8) skinny_bulk_kernel<true><<<grid, 288, BK_SMEM, st>>>(a, lda, w, ldw, M, N, K, kind, ep);
-      else skinny_bulk_kernel<false><<<grid, 288, BK_SMEM, st>>>(a, lda, w, ldw, M, N, K, kind, ep);
+      // two resident CTAs per SM (cfg 11: one, so that the next kernel of a PDL chain is co-resident on every SM)
+      const int cap = (g_skinny_cfg == 11 ? 1 : 2) * d3d_num_sms();
+      const int tiles = d3d_cdiv(N, BK_ROWS), grid = tiles < cap ? tiles : cap;
+      if (M > 8) D3D_CHECK_CUDA(launch_pdl(skinny_bulk_kernel<true>, dim3(grid), dim3(288), BK_SMEM, st, a, lda, w, ldw, M, N, K, kind, ep));
+      else D3D_CHECK_CUDA(launch_pdl(skinny_bulk_kernel<false>, dim3(grid), dim3(288), BK_SMEM, st, a, lda, w, ldw, M, N, K, kind, ep));
       break;
     }
     default: goto bulk;  // tools/skinny_bench.py: the persistent cp.async.bulk kernel streams fastest on every Phi-3 shape
@@ -483,10 +710,35 @@ extern "C" int d3d_decode_attention(const void* qkv, int64_t ld, const int* cu_s
   D3D_REQUIRE(kind == D3D_F16 || kind == D3D_BF16, "16-bit cache");
   dim3 grid(n_seq, H);
   cudaStream_t st = (cudaStream_t)stream;
-  if (Dh == 96) decode_attn_kernel<96><<<grid, DA_WARPS * 32, 0, st>>>((const uint16_t*)qkv, ld, cu_seqlens, n_seq, t_prefill, step, H, kind, scale, (uint16_t*)out, ldo);
-  else if (Dh == 64) decode_attn_kernel<64><<<grid, DA_WARPS * 32, 0, st>>>((const uint16_t*)qkv, ld, cu_seqlens, n_seq, t_prefill, step, H, kind, scale, (uint16_t*)out, ldo);
-  else if (Dh == 128) decode_attn_kernel<128><<<grid, DA_WARPS * 32, 0, st>>>((const uint16_t*)qkv, ld, cu_seqlens, n_seq, t_prefill, step, H, kind, scale, (uint16_t*)out, ldo);
+  const uint16_t* c = (const uint16_t*)qkv;
+  const long long ldl = ld, ldol = ldo;
+  if (g_decode_attn_impl == 0) {  // register-staged kernel (A/B)
+    const dim3 blk(DA_WARPS * 32);
+    if (Dh == 96) D3D_CHECK_CUDA(launch_pdl(decode_attn_kernel<96>, grid, blk, 0, st, c, ldl, cu_seqlens, n_seq, t_prefill, step, H, kind, scale, (uint16_t*)out, ldol));
+    else if (Dh == 64) D3D_CHECK_CUDA(launch_pdl(decode_attn_kernel<64>, grid, blk, 0, st, c, ldl, cu_seqlens, n_seq, t_prefill, step, H, kind, scale, (uint16_t*)out, ldol));
+    else if (Dh == 128) D3D_CHECK_CUDA(launch_pdl(decode_attn_kernel<128>, grid, blk, 0, st, c, ldl, cu_seqlens, n_seq, t_prefill, step, H, kind, scale, (uint16_t*)out, ldol));
+    else { d3d_set_error("decode attention: head_dim %d not built (64, 96, 128)", Dh); return D3D_EINVAL; }
+    D3D_CHECK_LAUNCH();
+    return 0;
+  }
+  D3D_REQUIRE(ld % 8 == 0 && ((uintptr_t)qkv % 16) == 0, "16-byte aligned cache rows (cp.async)");
+  const dim3 blk(DC_WARPS * 32);
+#define DB_LAUNCH(DHV)                                                                                                                    \
+  do {                                                                                                                                    \
+    constexpr int SMEM = DC_WARPS * 2 * DC_KEYS * DHV * 4;                                                                                \
+    static bool attr = false;                                                                                                             \
+    if (!attr) {                                                                                                                          \
+      D3D_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_staged_kernel<DHV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));              \
+      attr = true;                                                                                                                        \
+    }                                                                                                                                     \
+    D3D_CHECK_CUDA(launch_pdl(decode_attn_staged_kernel<DHV>, grid, blk, SMEM, st, c, ldl, cu_seqlens, n_seq, t_prefill, step, H, kind, scale, \
+                              (uint16_t*)out, ldol));                                                                                     \
+  } while (0)
+  if (Dh == 96) DB_LAUNCH(96);
+  else if (Dh == 64) DB_LAUNCH(64);
+  else if (Dh == 128) DB_LAUNCH(128);
   else { d3d_set_error("decode attention: head_dim %d not built (64, 96, 128)", Dh); return D3D_EINVAL; }
+#undef DB_LAUNCH
   D3D_CHECK_LAUNCH();
   return 0;
 }
@@ -502,26 +754,39 @@ extern "C" int d3d_lm_decode_step(const d3d_lm_model* m, void* const* qkv_layers
   cudaStream_t st = (cudaStream_t)stream;
   const int Dm = m->hidden, H = m->n_heads, Dh = m->head_dim, kind = m->kind;
   D3D_REQUIRE(H * Dh == Dm, "hidden = heads * head_dim");
-  decode_prep_kernel<<<n_seq, 256, 0, st>>>(m->embed, kind, tokens_in, cu_seqlens, step, Dm, x32, pos);
-  D3D_CHECK_LAUNCH();
-  D3D_TRY(d3d_rope_table(pos, inv_freq, n_seq, Dh, rope_tab, stream));
+  D3D_REQUIRE(Dm % 128 == 0 && Dh % 16 == 0 && ld_qkv % 8 == 0, "hidden % 128, head_dim % 16, 16-byte cache rows");
+  const void* embed = m->embed;
+  D3D_CHECK_CUDA(launch_pdl(decode_prep_kernel, dim3(n_seq), dim3(256), 0, st, embed, kind, tokens_in, cu_seqlens, step, Dm, x32, pos));
+  D3D_CHECK_CUDA(launch_pdl(dec_rope_table_kernel, dim3(d3d_cdiv(n_seq * (Dh / 2), 256)), dim3(256), 0, st, (const int*)pos, inv_freq, n_seq, Dh / 2, rope_tab));
   const long long row0 = (long long)t_prefill + (long long)step * n_seq;
   const float scale = (float)(1.0 / sqrt((double)Dh));  // same rounding as the prefill (double expression rounded once)
+  const dim3 norm_grid(d3d_cdiv(n_seq * 32, 256));
+  auto rmsnorm = [&](const float* w) {
+    return launch_pdl(dec_rmsnorm_kernel, norm_grid, dim3(256), 0, st, (const float*)x32, w, m->eps, n_seq, Dm, (uint16_t*)a16, kind);
+  };
+  const long long rope_total = (long long)n_seq * 2 * H * (Dh / 16);
   for (int l = 0; l < m->n_layers; ++l) {
     const d3d_lm_layer& L = m->layers[l];
     uint16_t* rows = (uint16_t*)qkv_layers_h[l] + row0 * ld_qkv;
-    D3D_TRY(d3d_rmsnorm(x32, Dm, nullptr, L.rms1, m->eps, n_seq, Dm, nullptr, 0, a16, Dm, kind, stream));
+    D3D_CHECK_CUDA(rmsnorm(L.rms1));
     D3D_TRY(skinny(a16, Dm, L.w_qkv, Dm, rows, ld_qkv, n_seq, 3 * Dm, Dm, kind, kind, nullptr, D3D_ACT_NONE, nullptr, 0, st));
-    D3D_TRY(d3d_rope_apply(rows, ld_qkv, rope_tab, n_seq, H, Dh, kind, stream));
+    D3D_CHECK_CUDA(launch_pdl(dec_rope_apply_kernel, dim3(d3d_cdiv(rope_total, 256)), dim3(256), 0, st, rows, (long long)ld_qkv, (const float*)rope_tab, n_seq, H, Dh, kind));
     D3D_TRY(d3d_decode_attention(qkv_layers_h[l], ld_qkv, cu_seqlens, n_seq, t_prefill, step, H, Dh, kind, scale, att16, Dm, stream));
     D3D_TRY(skinny(att16, Dm, L.w_o, Dm, x32, Dm, n_seq, Dm, Dm, kind, D3D_OUT_F32, nullptr, D3D_ACT_NONE, x32, Dm, st));
-    D3D_TRY(d3d_rmsnorm(x32, Dm, nullptr, L.rms2, m->eps, n_seq, Dm, nullptr, 0, a16, Dm, kind, stream));
+    D3D_CHECK_CUDA(rmsnorm(L.rms2));
     D3D_TRY(skinny(a16, Dm, L.w_gu, Dm, h16, m->ffn, n_seq, 2 * m->ffn, Dm, kind, kind, nullptr, D3D_ACT_SWIGLU, nullptr, 0, st));
     D3D_TRY(skinny(h16, m->ffn, L.w_down, m->ffn, x32, Dm, n_seq, Dm, m->ffn, kind, D3D_OUT_F32, nullptr, D3D_ACT_NONE, x32, Dm, st));
   }
-  D3D_TRY(d3d_rmsnorm(x32, Dm, nullptr, m->norm, m->eps, n_seq, Dm, nullptr, 0, a16, Dm, kind, stream));
+  D3D_CHECK_CUDA(rmsnorm(m->norm));
   D3D_TRY(skinny(a16, Dm, m->lm_head, Dm, logits, m->vocab, n_seq, m->vocab, Dm, kind, D3D_OUT_F32, nullptr, D3D_ACT_NONE, nullptr, 0, st));
-  argmax_kernel<<<n_seq, 1024, 0, st>>>(logits, m->vocab, m->vocab, next_tokens);
+  D3D_CHECK_CUDA(launch_pdl(argmax_kernel, dim3(n_seq), dim3(1024), 0, st, (const float*)logits, (long long)m->vocab, m->vocab, next_tokens));
   D3D_CHECK_LAUNCH();
+  return 0;
+}
+
+// 0: plain stream-ordered launches (A/B of the programmatic-dependent-launch chain; tools/decode_bench.py)
+extern "C" int d3d_lm_decode_set_pdl(int on) {
+  g_decode_pdl = (on & 1) != 0;
+  g_decode_attn_impl = (on & 2) ? 0 : 1;  // bit 1: the register-staged decode attention instead of the cp.async-staged one
   return 0;
 }

@@ -15,6 +15,9 @@ emb = synth.hash_uniform((sum(lens), 3072), 5, 1.0).cuda()
 cu = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int32, device="cuda")
 pos = torch.cat([torch.arange(n, dtype=torch.int32) for n in lens]).cuda()
 last = (cu[1:] - 1).to(torch.int32).contiguous()
+from dynam3d_b200 import _lib as L  # noqa: E402
+L.lib().d3d_lm_decode_set_pdl(int(os.environ.get("PDL", 1)))
+L.lib().d3d_gemm_skinny_set_config(int(os.environ.get("SKCFG", 0)))
 res = {}
 for n_new in (1, 20):
     ts = []
@@ -35,7 +38,8 @@ w = eng.w
 wbytes = layers * (3 * 3072 * 3072 + 3072 * 3072 + 2 * 8192 * 3072 + 3072 * 8192) * 2 + 32064 * 3072 * 2
 kv_bytes = layers * sum(lens) * 2 * 3072 * 2
 out = {"prefill_ms": round(res[1], 2), "generate20_ms": round(res[20], 2), "decode_step_ms": round(step_ms, 3), "weight_GB": round(wbytes / 1e9, 2),
-       "kv_GB_per_step": round(kv_bytes / 1e9, 2), "hbm_GBs": round((wbytes + kv_bytes) / step_ms / 1e6, 1)}
+       "kv_GB_per_step": round(kv_bytes / 1e9, 2), "hbm_GBs": round((wbytes + kv_bytes) / step_ms / 1e6, 1),
+       "pdl": int(os.environ.get("PDL", 1)), "skcfg": int(os.environ.get("SKCFG", 0))}
 print(json.dumps(out))
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(out, open("gpurun_out/decode_bench.json", "w"))
+json.dump(out, open("gpurun_out/decode_bench_pdl%d.json" % out["pdl"], "w"))
