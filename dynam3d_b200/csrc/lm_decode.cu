@@ -17,6 +17,9 @@
 // ring, and only the threads that touch activations execute griddepcontrol.wait.  HBM stays busy across the ~260 kernel boundaries of a
 // step instead of draining and refilling at each (a 19..100 MB weight matrix is a 3..15 us stream; the boundary cost was of that order).
 #include <cmath>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "common.cuh"
 
@@ -32,6 +35,8 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 bool g_decode_pdl = true;
+bool g_decode_prefetch = true;
+int g_decode_dbg = 0;  // timing experiments only (wrong results): 1 = GEMM weights always from rows 0..15 (no HBM traffic), 2 = attention keys always block 0
 
 template <typename... KArgs, typename... Args>
 cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
@@ -67,10 +72,69 @@ __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+// L2 prefetch of the NEXT kernel's weights, issued by the producer warps once their own rows are on their way: the tail of a kernel and
+// the boundary to the next one (~6..8 us with HBM otherwise idle) are spent pulling the next matrix into the 126 MB L2
+struct NextWeights {
+  const void* p;
+  long long bytes;
+  int dbg_same_rows;  // timing experiment: stream rows 0..15 for every tile
+  int stamp_slot;     // debug builds: launch counter
+};
+__device__ __forceinline__ void l2_prefetch_share(const NextWeights& nx, int lane) {
+  if (nx.bytes <= 0) return;
+  constexpr long long CH = 4096;
+  const long long per = ((nx.bytes / gridDim.x) + CH - 1) / CH * CH;
+  const long long beg = per * blockIdx.x;
+  const long long end = beg + per < nx.bytes ? beg + per : nx.bytes;
+  for (long long off = beg + lane * CH; off < end; off += 32 * CH) {
+    const unsigned sz = (unsigned)((end - off < CH ? end - off : CH) & ~15LL);
+    if (sz) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"((const char*)nx.p + off), "r"(sz) : "memory");
+  }
+}
+
+// RMSNorm of one fp32 row by one warp: the arithmetic and summation order of rmsnorm_kernel (nn_kernels.cu; float4 per lane strided by 32,
+// sequential per-lane sum, butterfly), with the loads issued in batches of 8 -- a plain runtime loop serialises 24 L2 round trips per pass
+// (measured: 11 us for 8 rows).  CG: read through L2 (rows written by other CTAs of the same grid).
+template <bool CG>
+__device__ __forceinline__ void warp_rmsnorm_row(const float* __restrict__ x, const float* __restrict__ w, float eps, int D, uint16_t* __restrict__ out16,
+                                                 int kind, int lane) {
+  const float4* xr = reinterpret_cast<const float4*>(x);
+  const float4* wr = reinterpret_cast<const float4*>(w);
+  const int n4 = D / 128;
+  auto ldx = [&](int c4) { return CG ? __ldcg(xr + c4) : xr[c4]; };
+  float q = 0.f;
+  for (int i0 = 0; i0 < n4; i0 += 8) {
+    float4 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = i0 + j < n4 ? ldx(lane + 32 * (i0 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (i0 + j < n4) q += (v[j].x * v[j].x + v[j].y * v[j].y) + (v[j].z * v[j].z + v[j].w * v[j].w);
+  }
+  const float r = 1.0f / sqrtf(warp_sum(q) / (float)D + eps);
+  for (int i0 = 0; i0 < n4; i0 += 8) {
+    float4 v[8], g[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const bool in = i0 + j < n4;
+      v[j] = in ? ldx(lane + 32 * (i0 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      g[j] = in ? wr[lane + 32 * (i0 + j)] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (i0 + j < n4)
+        reinterpret_cast<uint2*>(out16)[lane + 32 * (i0 + j)] =
+            make_uint2(pack16x2(v[j].x * r * g[j].x, v[j].y * r * g[j].y, kind), pack16x2(v[j].z * r * g[j].z, v[j].w * r * g[j].w, kind));
+  }
+}
+
 struct SkinnyEpi {
   void* C; long long ldc;
   const float* bias; const float* residual; long long ldres;
   int act, out_kind;
+  // Fused RMSNorm of the finished fp32 rows C[M, N] (the residual stream) into the 16-bit operand of the next GEMM, done by the LAST CTA to
+  // finish (arrival counter): a separate 1-CTA kernel between two GEMMs cost ~11 us of dependency latency per instance in the step's chain
+  const float* norm_w; uint16_t* norm_out; float norm_eps; int norm_kind; int* norm_counter;
 };
 
 // one thread per (tile, row, column pair): fixed-order sum over the 8 K-slices (deterministic), then bias / activation / residual / store
@@ -193,9 +257,13 @@ __global__ void __launch_bounds__(SK_WARPS * 32) skinny_gemm_kernel(const uint16
 // shared-memory ring -- no LSU wavefronts, no register staging, ~96 KB in flight per CTA -- and 8 consumer warps read their fragments
 // with conflict-free 16-byte LDS (row pitch 1088 B) using the same K-permuted fragment trick.
 constexpr int BK_ROWS = 16;                 // weight rows per CTA (2 n-tiles)
-constexpr int BK_KC = 512;                  // K elements per stage (1 KB per row)
-constexpr int BK_PITCH = BK_KC * 2 + 64;    // 1088 B: consecutive rows start 16 banks apart -> 2 rows x 64 B per LDS wavefront, no conflicts
-constexpr int BK_STAGES = 6;
+// K elements per stage = 2 KB per row and bulk copy.  The copy engine takes ~75 cycles per cp.async.bulk whatever its size (clock stamps,
+// tools/skinny_stamps.py): with 1 KB copies a producer needed 1 250 cycles per 16-row stage -- 13 B / clk, at two CTAs per SM just the
+// SM's share of HBM -- and a decode step whose weights all sat in L2 was hardly faster than one that streamed them.
+constexpr int BK_KC = 1024;
+constexpr int BK_U = BK_KC / 256;           // 32-element K-steps per warp and stage (8 warps split a stage's K)
+constexpr int BK_PITCH = BK_KC * 2 + 64;    // 2112 B: consecutive rows start 16 banks apart -> 2 rows x 64 B per LDS wavefront, no conflicts
+constexpr int BK_STAGES = 3;
 constexpr int BK_STAGE_BYTES = BK_ROWS * BK_PITCH;
 constexpr int BK_SMEM = BK_STAGES * BK_STAGE_BYTES + 128;
 
@@ -222,17 +290,38 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                : "memory");
 }
 
+#ifdef D3D_SK_STAMPS
+// debug build only (make EXTRA=-DD3D_SK_STAMPS): clock stamps of CTA 0 (consumer warp 0 / the producer), read by tools/skinny_stamps.py
+__device__ long long g_sk_stamps[128];
+__device__ unsigned long long g_sk_cta_times[8][320][4];  // [launch % 8][CTA]: globaltimer at CTA start, after pdl_wait, at consumer end; smid
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define SK_GT(slot) do { if ((threadIdx.x & 31) == 0 && (threadIdx.x == 0 || (slot) == 0) && blockIdx.x < 320) g_sk_cta_times[nx.stamp_slot & 7][blockIdx.x][(slot)] = gtime(); } while (0)
+#define SK_STAMP(cond, slot) do { if (cond) g_sk_stamps[(slot)] = clock64(); } while (0)
+#else
+#define SK_STAMP(cond, slot) do { } while (0)
+#define SK_GT(slot) do { } while (0)
+#endif
+
 template <bool HI>
 __global__ void __launch_bounds__(288) skinny_bulk_kernel(const uint16_t* __restrict__ A, long long lda, const uint16_t* __restrict__ W, long long ldw,
-                                                          int M, int N, int K, int kind, SkinnyEpi ep) {
+                                                          int M, int N, int K, int kind, SkinnyEpi ep, NextWeights nx) {
   extern __shared__ __align__(128) uint8_t bk_smem[];
   __shared__ float red[SK_WARPS][2][16][8];
   const uint32_t sbase = smem_u32(bk_smem);
   const uint32_t bar0 = sbase + BK_STAGES * BK_STAGE_BYTES;  // full[s] at +8s, empty[s] at +8(STAGES+s)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tiles = (N + BK_ROWS - 1) / BK_ROWS;
   const int n_stages = (K + BK_KC - 1) / BK_KC;
+  // Every CTA owns a contiguous range of N / gridDim.x (+-1) weight rows, walked in tiles of <= 16 rows: all CTAs stream the same number
+  // of bytes.  (Whole 16-row tiles dealt round-robin left 44 SMs with two tiles and 104 with one on the N = 3072 outputs, and a last
+  // round with 136 of 296 CTAs busy on the gate/up matrix.)  Range ends are even: a SwiGLU column pair never straddles two tiles.
+  const int r0 = (int)(((long long)N * blockIdx.x / gridDim.x) & ~1LL);
+  const int r1 = blockIdx.x + 1 == gridDim.x ? N : (int)(((long long)N * (blockIdx.x + 1) / gridDim.x) & ~1LL);
   pdl_trigger();  // the next kernel of the chain may become resident and start on ITS weights
+  SK_STAMP(blockIdx.x == 0 && threadIdx.x == 0, 0);
+  if (threadIdx.x == 0) { SK_GT(0); }
+#ifdef D3D_SK_STAMPS
+  if (threadIdx.x == 0 && blockIdx.x < 320) { unsigned smid; asm volatile("mov.u32 %0, %smid;" : "=r"(smid)); g_sk_cta_times[nx.stamp_slot & 7][blockIdx.x][3] = smid; }
+#endif
   if (threadIdx.x == 0) {
     for (int s = 0; s < BK_STAGES; ++s) { bk_mbar_init(bar0 + 8 * s, 1); bk_mbar_init(bar0 + 8 * (BK_STAGES + s), SK_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -243,75 +332,118 @@ __global__ void __launch_bounds__(288) skinny_bulk_kernel(const uint16_t* __rest
   if (warp == SK_WARPS) {
     // ===== producer: one row copy per lane =====
     int it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int n_base = tile * BK_ROWS;
-      const int rows = min(BK_ROWS, N - n_base);
+    for (int n_base = r0; n_base < r1; n_base += BK_ROWS) {
+      const int rows = min(BK_ROWS, r1 - n_base);
       for (int ks = 0; ks < n_stages; ++ks, ++it) {
         const int s = it % BK_STAGES;
         const uint32_t ph = (uint32_t)(it / BK_STAGES) & 1u;
         bk_mbar_wait(bar0 + 8 * (BK_STAGES + s), ph ^ 1u);
+        SK_STAMP(blockIdx.x == 0 && lane == 0 && it < 12, 64 + it);
         const int k0 = ks * BK_KC;
         const uint32_t bytes = (uint32_t)min(BK_KC, K - k0) * 2u;
         if (lane == 0) bk_mbar_expect_tx(bar0 + 8 * s, bytes * (uint32_t)rows);
         __syncwarp();
-        if (lane < rows) bulk_g2s(sbase + s * BK_STAGE_BYTES + lane * BK_PITCH, W + (long long)(n_base + lane) * ldw + k0, bytes, bar0 + 8 * s);
+        if (lane < rows) bulk_g2s(sbase + s * BK_STAGE_BYTES + lane * BK_PITCH, W + (long long)((nx.dbg_same_rows ? 0 : n_base) + lane) * ldw + k0, bytes, bar0 + 8 * s);
       }
     }
+    l2_prefetch_share(nx, lane);
   } else {
-    // ===== consumers: warp w owns K elements [64w, 64w + 64) of every stage =====
+    // ===== consumers: warp w owns K elements [128w, 128w + 128) of every stage =====
     pdl_wait();  // A (and the residual / C rows) belong to the kernels before this one; the producer above never touches them
+    SK_STAMP(blockIdx.x == 0 && threadIdx.x == 0, 1);
+    SK_GT(1);
     const int g = lane >> 2, kq = lane & 3;
     const bool lo_ok = g < M, hi_ok = HI && g + 8 < M;
-    const uint16_t* a_lo_p = A + (long long)(lo_ok ? g : 0) * lda + warp * 64 + kq * 8;
-    const uint16_t* a_hi_p = A + (long long)(hi_ok ? g + 8 : 0) * lda + warp * 64 + kq * 8;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int n_base = tile * BK_ROWS;
-      const int rows = min(BK_ROWS, N - n_base);
+    const uint16_t* a_lo_p = A + (long long)(lo_ok ? g : 0) * lda + warp * (BK_U * 32) + kq * 8;
+    const uint16_t* a_hi_p = A + (long long)(hi_ok ? g + 8 : 0) * lda + warp * (BK_U * 32) + kq * 8;
+    // A fragments come from L2 (~700 cycles): the fragments of stage it + 1 are requested before stage it is waited for, so that round trip
+    // runs under a stage's worth of work instead of in front of every stage (clock stamps: 1 900 -> ~? cycles per 32 KB stage)
+    const int total = ((r1 - r0 + BK_ROWS - 1) / BK_ROWS) * n_stages;
+    uint4 al[BK_U], ah[BK_U], nl[BK_U], nh[BK_U];
+    auto load_a = [&](int it_, uint4 (&l)[BK_U], uint4 (&h)[BK_U]) {
+      const int ks_ = it_ % n_stages;
+      const int kb = ks_ * BK_KC + warp * (BK_U * 32);
+#pragma unroll
+      for (int u = 0; u < BK_U; ++u) {
+        const bool in = it_ < total && kb + u * 32 + kq * 8 < K;
+        l[u] = (in && lo_ok) ? __ldg(reinterpret_cast<const uint4*>(a_lo_p + ks_ * BK_KC + u * 32)) : make_uint4(0, 0, 0, 0);
+        h[u] = (HI && in && hi_ok) ? __ldg(reinterpret_cast<const uint4*>(a_hi_p + ks_ * BK_KC + u * 32)) : make_uint4(0, 0, 0, 0);
+      }
+    };
+    load_a(0, al, ah);
+    float acc[4][4];
+    // one stage: `cl / ch` hold its A fragments, `nl_ / nh_` receive the next stage's (the caller alternates the two register sets, so no
+    // register copy -- which would wait for the load -- sits at the end of a stage)
+    auto do_stage = [&](int it, uint4 (&cl)[BK_U], uint4 (&ch)[BK_U], uint4 (&nl_)[BK_U], uint4 (&nh_)[BK_U]) {
+      const int tile = it / n_stages, ks = it - tile * n_stages;
+      const int n_base = r0 + tile * BK_ROWS;
+      const int rows = min(BK_ROWS, r1 - n_base);
       const bool ok0 = g < rows, ok1 = g + 8 < rows;
-      float acc[2][4];
+      if (ks == 0) {
 #pragma unroll
-      for (int t = 0; t < 2; ++t)
+        for (int t = 0; t < 4; ++t)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) acc[t][i] = 0.f;
-      for (int ks = 0; ks < n_stages; ++ks, ++it) {
-        const int s = it % BK_STAGES;
-        const uint32_t ph = (uint32_t)(it / BK_STAGES) & 1u;
-        const int k0 = ks * BK_KC + warp * 64;
-        // A fragments of the two 32-element K-steps of this warp (L1 / L2 resident), issued before the wait
-        uint4 al[2], ah[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const bool in = k0 + u * 32 + kq * 8 < K;
-          al[u] = (in && lo_ok) ? __ldg(reinterpret_cast<const uint4*>(a_lo_p + ks * BK_KC + u * 32)) : make_uint4(0, 0, 0, 0);
-          ah[u] = (HI && in && hi_ok) ? __ldg(reinterpret_cast<const uint4*>(a_hi_p + ks * BK_KC + u * 32)) : make_uint4(0, 0, 0, 0);
-        }
-        bk_mbar_wait(bar0 + 8 * s, ph);
-        const uint32_t st = sbase + s * BK_STAGE_BYTES + (uint32_t)(warp * 128 + kq * 16);
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const bool in = k0 + u * 32 + kq * 8 < K;
-          uint4 w0 = make_uint4(0, 0, 0, 0), w1 = make_uint4(0, 0, 0, 0);
-          if (in && ok0) asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w0.x), "=r"(w0.y), "=r"(w0.z), "=r"(w0.w) : "r"(st + g * BK_PITCH + u * 64));
-          if (in && ok1) asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w1.x), "=r"(w1.y), "=r"(w1.z), "=r"(w1.w) : "r"(st + (g + 8) * BK_PITCH + u * 64));
-          mma16816(acc[0], al[u].x, ah[u].x, al[u].y, ah[u].y, w0.x, w0.y, kind);
-          mma16816(acc[0], al[u].z, ah[u].z, al[u].w, ah[u].w, w0.z, w0.w, kind);
-          mma16816(acc[1], al[u].x, ah[u].x, al[u].y, ah[u].y, w1.x, w1.y, kind);
-          mma16816(acc[1], al[u].z, ah[u].z, al[u].w, ah[u].w, w1.z, w1.w, kind);
-        }
-        __syncwarp();
-        if (lane == 0) bk_mbar_arrive(bar0 + 8 * (BK_STAGES + s));
+          for (int i = 0; i < 4; ++i) acc[t][i] = 0.f;
       }
+      const int s = it % BK_STAGES;
+      const uint32_t ph = (uint32_t)(it / BK_STAGES) & 1u;
+      const int k0 = ks * BK_KC + warp * (BK_U * 32);
+      SK_STAMP(blockIdx.x == 0 && threadIdx.x == 0 && it < 12, 100 + it);
+      load_a(it + 1, nl_, nh_);
+      SK_STAMP(blockIdx.x == 0 && threadIdx.x == 0 && it < 24, 2 + 2 * it);
+      bk_mbar_wait(bar0 + 8 * s, ph);
+      SK_STAMP(blockIdx.x == 0 && threadIdx.x == 0 && it < 24, 3 + 2 * it);
+      const uint32_t st = sbase + s * BK_STAGE_BYTES + (uint32_t)(warp * (BK_U * 64) + kq * 16);
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        red[warp][t][g][kq * 2] = acc[t][0];
-        red[warp][t][g][kq * 2 + 1] = acc[t][1];
-        red[warp][t][g + 8][kq * 2] = acc[t][2];
-        red[warp][t][g + 8][kq * 2 + 1] = acc[t][3];
+      for (int u = 0; u < BK_U; ++u) {
+        const bool in = k0 + u * 32 + kq * 8 < K;
+        uint4 w0 = make_uint4(0, 0, 0, 0), w1 = make_uint4(0, 0, 0, 0);
+        if (in && ok0) asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w0.x), "=r"(w0.y), "=r"(w0.z), "=r"(w0.w) : "r"(st + g * BK_PITCH + u * 64));
+        if (in && ok1) asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w1.x), "=r"(w1.y), "=r"(w1.z), "=r"(w1.w) : "r"(st + (g + 8) * BK_PITCH + u * 64));
+        // four independent accumulator chains (the two 16-element halves of a fragment go to separate sums, added at the tile's end)
+        mma16816(acc[0], cl[u].x, ch[u].x, cl[u].y, ch[u].y, w0.x, w0.y, kind);
+        mma16816(acc[1], cl[u].x, ch[u].x, cl[u].y, ch[u].y, w1.x, w1.y, kind);
+        mma16816(acc[2], cl[u].z, ch[u].z, cl[u].w, ch[u].w, w0.z, w0.w, kind);
+        mma16816(acc[3], cl[u].z, ch[u].z, cl[u].w, ch[u].w, w1.z, w1.w, kind);
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 consumer warps only: the producer keeps streaming the next tile
-      skinny_epilogue<2>(red, n_base, M, N, ep);
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // `red` is rewritten by the next tile
+      SK_STAMP(blockIdx.x == 0 && threadIdx.x == 0 && it < 12, 76 + it);
+      __syncwarp();
+      if (lane == 0) bk_mbar_arrive(bar0 + 8 * (BK_STAGES + s));
+      SK_STAMP(blockIdx.x == 0 && threadIdx.x == 0 && it < 12, 88 + it);
+      if (ks == n_stages - 1) {  // end of a row tile
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          red[warp][t][g][kq * 2] = acc[t][0] + acc[t + 2][0];
+          red[warp][t][g][kq * 2 + 1] = acc[t][1] + acc[t + 2][1];
+          red[warp][t][g + 8][kq * 2] = acc[t][2] + acc[t + 2][2];
+          red[warp][t][g + 8][kq * 2 + 1] = acc[t][3] + acc[t + 2][3];
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 consumer warps only: the producer keeps streaming the next tile
+        SK_STAMP(blockIdx.x == 0 && threadIdx.x == 0, 52 + (tile ? 3 : 0));
+        skinny_epilogue<2>(red, n_base, M, r1, ep);  // columns >= r1 belong to the next CTA
+        SK_STAMP(blockIdx.x == 0 && threadIdx.x == 0, 53 + (tile ? 3 : 0));
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // `red` is rewritten by the next tile
+        SK_STAMP(blockIdx.x == 0 && threadIdx.x == 0, 54 + (tile ? 3 : 0));
+      }
+    };
+    for (int it = 0; it < total; it += 2) {
+      do_stage(it, al, ah, nl, nh);
+      if (it + 1 < total) do_stage(it + 1, nl, nh, al, ah);
+    }
+    SK_GT(2);
+    if (ep.norm_w) {  // kernel-uniform
+      // every CTA (also one with an empty row range) arrives once its rows of C are written; the last one normalises all M rows
+      __shared__ int s_last;
+      __threadfence();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (threadIdx.x == 0) s_last = atomicAdd(ep.norm_counter, 1) == (int)gridDim.x - 1;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (s_last) {
+        __threadfence();
+        if (threadIdx.x == 0) *ep.norm_counter = 0;  // ready for the next launch (stream order)
+        for (int row = warp; row < M; row += SK_WARPS)
+          warp_rmsnorm_row<true>((const float*)ep.C + (long long)row * ep.ldc, ep.norm_w, ep.norm_eps, N, ep.norm_out + (long long)row * N, ep.norm_kind, lane);
+      }
     }
   }
 }
@@ -415,7 +547,7 @@ __device__ __forceinline__ void dc_cp_async16(uint32_t dst, const void* src) {
 template <int DH>
 __global__ void __launch_bounds__(DC_WARPS * 32) decode_attn_staged_kernel(const uint16_t* __restrict__ qkv, long long ld, const int* __restrict__ cu,
                                                                            int n_seq, int t_prefill, int step, int H, int kind, float scale,
-                                                                           uint16_t* __restrict__ out, long long ldo) {
+                                                                           uint16_t* __restrict__ out, long long ldo, int dbg_same_block) {
   constexpr int ACTIVE = DH / 4;
   constexpr int ROWB = DH * 4;            // K then V head slice of one key, bytes
   constexpr int CPK = ROWB / 16;          // 16-byte chunks per key
@@ -437,8 +569,9 @@ __global__ void __launch_bounds__(DC_WARPS * 32) decode_attn_staged_kernel(const
       if (blk == n_blk - 1 && !waited) { pdl_wait(); waited = true; }  // the newest key row comes from this step's QKV GEMM + RoPE
       for (int c = lane; c < DC_KEYS * CPK; c += 32) {
         const int key = c / CPK, ch = c - key * CPK;
-        const int j = blk * DC_KEYS + key;
+        int j = blk * DC_KEYS + key;
         if (j < n_keys) {
+          if (dbg_same_block) j = key;
           const long long row = j < n_pre ? (long long)(p0 + j) : (long long)t_prefill + (long long)(j - n_pre) * n_seq + b;
           const uint16_t* src = qkv + row * ld + (ch < HALF ? k_col + ch * 8 : v_col + (ch - HALF) * 8);
           dc_cp_async16(wbase + (uint32_t)(buf * BLOCK_BYTES + key * ROWB + ch * 16), src);
@@ -579,20 +712,7 @@ __global__ void __launch_bounds__(256) dec_rmsnorm_kernel(const float* __restric
   pdl_wait();
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (row >= T) return;
-  const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * D);
-  const int n4 = D / 128;  // float4 per lane
-  float q = 0.f;
-  for (int i = 0; i < n4; ++i) {
-    const float4 v = xr[lane + 32 * i];
-    q += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-  }
-  const float r = 1.0f / sqrtf(warp_sum(q) / (float)D + eps);
-  for (int i = 0; i < n4; ++i) {
-    const int c4 = lane + 32 * i;
-    const float4 v = xr[c4], g = reinterpret_cast<const float4*>(w)[c4];
-    reinterpret_cast<uint2*>(out16 + (long long)row * D)[c4] =
-        make_uint2(pack16x2(v.x * r * g.x, v.y * r * g.y, kind), pack16x2(v.z * r * g.z, v.w * r * g.w, kind));
-  }
+  warp_rmsnorm_row<false>(x + (long long)row * D, w, eps, D, out16 + (long long)row * D, kind, lane);
 }
 
 __global__ void dec_rope_table_kernel(const int* __restrict__ pos, const float* __restrict__ inv_freq, int T, int half, float* __restrict__ tab) {
@@ -635,16 +755,22 @@ __global__ void dec_rope_apply_kernel(uint16_t* __restrict__ qkv, long long ld, 
 }
 
 int g_skinny_cfg = 0;
+struct FusedNorm {
+  const float* w; uint16_t* out; float eps; int* counter;
+};
 int g_decode_attn_impl = 1;  // 1: cp.async-staged, 0: register-staged (A/B)
 
 int skinny(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N, int K, int kind, int out_kind,
-           const float* bias, int act, const float* residual, long long ldres, cudaStream_t st) {
+           const float* bias, int act, const float* residual, long long ldres, cudaStream_t st, NextWeights nx = NextWeights{nullptr, 0, 0, 0},
+           const FusedNorm* norm = nullptr) {
   D3D_REQUIRE(M >= 1 && M <= 16, "skinny GEMM handles 1..16 activation rows");
   D3D_REQUIRE(K % 32 == 0 && lda % 8 == 0 && ldw % 8 == 0, "K must be a multiple of 32, rows 16-byte aligned");
   D3D_REQUIRE(((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0, "A/W must be 16-byte aligned");
   D3D_REQUIRE(kind == D3D_F16 || kind == D3D_BF16, "16-bit operands");
   D3D_REQUIRE(act != D3D_ACT_SWIGLU || ((N % 2) == 0 && residual == nullptr), "swiglu needs even N, no residual");
-  SkinnyEpi ep{C, ldc, bias, residual, ldres, act, out_kind};
+  D3D_REQUIRE(!norm || (out_kind == D3D_OUT_F32 && act == D3D_ACT_NONE && N % 128 == 0 && ldc % 4 == 0 && (g_skinny_cfg == 0 || g_skinny_cfg >= 10)), "fused norm: fp32 rows, N % 128, bulk kernel");
+  SkinnyEpi ep{C, ldc, bias, residual, ldres, act, out_kind, nullptr, nullptr, 0.f, 0, nullptr};
+  if (norm) { ep.norm_w = norm->w; ep.norm_out = norm->out; ep.norm_eps = norm->eps; ep.norm_kind = kind; ep.norm_counter = norm->counter; }
   const uint16_t* a = (const uint16_t*)A;
   const uint16_t* w = (const uint16_t*)W;
 #define SK_LAUNCH(NT, U, NA)                                                                                                              \
@@ -673,9 +799,13 @@ int skinny(const void* A, long long lda, const void* W, long long ldw, void* C, 
       }
       // two resident CTAs per SM (cfg 11: one, so that the next kernel of a PDL chain is co-resident on every SM)
       const int cap = (g_skinny_cfg == 11 ? 1 : 2) * d3d_num_sms();
-      const int tiles = d3d_cdiv(N, BK_ROWS), grid = tiles < cap ? tiles : cap;
-      if (M > 8) D3D_CHECK_CUDA(launch_pdl(skinny_bulk_kernel<true>, dim3(grid), dim3(288), BK_SMEM, st, a, lda, w, ldw, M, N, K, kind, ep));
-      else D3D_CHECK_CUDA(launch_pdl(skinny_bulk_kernel<false>, dim3(grid), dim3(288), BK_SMEM, st, a, lda, w, ldw, M, N, K, kind, ep));
+      const int tiles = d3d_cdiv(N, 8), grid = tiles < cap ? tiles : cap;  // at least ~8 rows per CTA
+#ifdef D3D_SK_STAMPS
+      static int launch_no = 0;
+      nx.stamp_slot = launch_no++;
+#endif
+      if (M > 8) D3D_CHECK_CUDA(launch_pdl(skinny_bulk_kernel<true>, dim3(grid), dim3(288), BK_SMEM, st, a, lda, w, ldw, M, N, K, kind, ep, nx));
+      else D3D_CHECK_CUDA(launch_pdl(skinny_bulk_kernel<false>, dim3(grid), dim3(288), BK_SMEM, st, a, lda, w, ldw, M, N, K, kind, ep, nx));
       break;
     }
     default: goto bulk;  // tools/skinny_bench.py: the persistent cp.async.bulk kernel streams fastest on every Phi-3 shape
@@ -688,6 +818,19 @@ int skinny(const void* A, long long lda, const void* W, long long ldw, void* C, 
 }  // namespace
 
 extern "C" int d3d_gemm_skinny_set_config(int cfg) { g_skinny_cfg = cfg; return 0; }
+
+#ifdef D3D_SK_STAMPS
+extern "C" int d3d_debug_skinny_stamps(long long* host_out) {
+  D3D_CHECK_CUDA(cudaDeviceSynchronize());
+  D3D_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_sk_stamps, sizeof(long long) * 128));
+  return 0;
+}
+extern "C" int d3d_debug_skinny_cta_times(unsigned long long* host_out) {
+  D3D_CHECK_CUDA(cudaDeviceSynchronize());
+  D3D_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_sk_cta_times, sizeof(unsigned long long) * 8 * 320 * 4));
+  return 0;
+}
+#endif
 
 extern "C" int d3d_gemm_skinny(const d3d_gemm_args* a, void* stream) {
   D3D_REQUIRE(a != nullptr && a->A && a->W && a->C, "args");
@@ -732,7 +875,7 @@ extern "C" int d3d_decode_attention(const void* qkv, int64_t ld, const int* cu_s
       attr = true;                                                                                                                        \
     }                                                                                                                                     \
     D3D_CHECK_CUDA(launch_pdl(decode_attn_staged_kernel<DHV>, grid, blk, SMEM, st, c, ldl, cu_seqlens, n_seq, t_prefill, step, H, kind, scale, \
-                              (uint16_t*)out, ldol));                                                                                     \
+                              (uint16_t*)out, ldol, (g_decode_dbg >> 1) & 1));                                                                                  \
   } while (0)
   if (Dh == 96) DB_LAUNCH(96);
   else if (Dh == 64) DB_LAUNCH(64);
@@ -742,6 +885,23 @@ extern "C" int d3d_decode_attention(const void* qkv, int64_t ld, const int* cu_s
   D3D_CHECK_LAUNCH();
   return 0;
 }
+
+namespace {
+// a zeroed int per (device, stream), owned by the library: the arrival counter of the fused norm (self-resetting)
+int* stream_counter(cudaStream_t st) {
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, int*> m;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  int*& p = m[{dev, st}];
+  if (!p) {
+    if (cudaMalloc(&p, 64) != cudaSuccess) { p = nullptr; return nullptr; }
+    if (cudaMemset(p, 0, 64) != cudaSuccess) return nullptr;
+  }
+  return p;
+}
+}  // namespace
 
 // One greedy decode step for all sequences of the rank.  Feeds tokens_in (the previous step's arg-max), appends their q/k/v rows to the
 // per-layer caches at row t_prefill + step*n_seq + b, and writes the next-token logits and their arg-max.
@@ -765,19 +925,29 @@ extern "C" int d3d_lm_decode_step(const d3d_lm_model* m, void* const* qkv_layers
     return launch_pdl(dec_rmsnorm_kernel, norm_grid, dim3(256), 0, st, (const float*)x32, w, m->eps, n_seq, Dm, (uint16_t*)a16, kind);
   };
   const long long rope_total = (long long)n_seq * 2 * H * (Dh / 16);
+  // what the producers of each GEMM pull into L2 for the kernel after next (capped: two matrices plus a layer's K / V stay below the L2 size)
+  const long long es = 2, cap = 48ll << 20;
+  auto next = [&](const void* w, long long rows_, long long cols_) {
+    const long long b = rows_ * cols_ * es;
+    return NextWeights{g_decode_prefetch ? w : nullptr, g_decode_prefetch ? (b < cap ? b : cap) : 0, g_decode_dbg & 1, 0};
+  };
+  int* counter = stream_counter(st);
+  D3D_REQUIRE(counter != nullptr, "arrival counter allocation");
+  D3D_CHECK_CUDA(rmsnorm(m->layers[0].rms1));  // every later norm rides on the GEMM that completes the residual row
   for (int l = 0; l < m->n_layers; ++l) {
     const d3d_lm_layer& L = m->layers[l];
     uint16_t* rows = (uint16_t*)qkv_layers_h[l] + row0 * ld_qkv;
-    D3D_CHECK_CUDA(rmsnorm(L.rms1));
-    D3D_TRY(skinny(a16, Dm, L.w_qkv, Dm, rows, ld_qkv, n_seq, 3 * Dm, Dm, kind, kind, nullptr, D3D_ACT_NONE, nullptr, 0, st));
+    const bool last = l + 1 == m->n_layers;
+    const FusedNorm n2{L.rms2, (uint16_t*)a16, m->eps, counter};
+    const FusedNorm n1{last ? m->norm : m->layers[last ? l : l + 1].rms1, (uint16_t*)a16, m->eps, counter};
+    D3D_TRY(skinny(a16, Dm, L.w_qkv, Dm, rows, ld_qkv, n_seq, 3 * Dm, Dm, kind, kind, nullptr, D3D_ACT_NONE, nullptr, 0, st, next(L.w_o, Dm, Dm)));
     D3D_CHECK_CUDA(launch_pdl(dec_rope_apply_kernel, dim3(d3d_cdiv(rope_total, 256)), dim3(256), 0, st, rows, (long long)ld_qkv, (const float*)rope_tab, n_seq, H, Dh, kind));
     D3D_TRY(d3d_decode_attention(qkv_layers_h[l], ld_qkv, cu_seqlens, n_seq, t_prefill, step, H, Dh, kind, scale, att16, Dm, stream));
-    D3D_TRY(skinny(att16, Dm, L.w_o, Dm, x32, Dm, n_seq, Dm, Dm, kind, D3D_OUT_F32, nullptr, D3D_ACT_NONE, x32, Dm, st));
-    D3D_CHECK_CUDA(rmsnorm(L.rms2));
-    D3D_TRY(skinny(a16, Dm, L.w_gu, Dm, h16, m->ffn, n_seq, 2 * m->ffn, Dm, kind, kind, nullptr, D3D_ACT_SWIGLU, nullptr, 0, st));
-    D3D_TRY(skinny(h16, m->ffn, L.w_down, m->ffn, x32, Dm, n_seq, Dm, m->ffn, kind, D3D_OUT_F32, nullptr, D3D_ACT_NONE, x32, Dm, st));
+    D3D_TRY(skinny(att16, Dm, L.w_o, Dm, x32, Dm, n_seq, Dm, Dm, kind, D3D_OUT_F32, nullptr, D3D_ACT_NONE, x32, Dm, st, next(L.w_gu, 2 * m->ffn, Dm), &n2));
+    D3D_TRY(skinny(a16, Dm, L.w_gu, Dm, h16, m->ffn, n_seq, 2 * m->ffn, Dm, kind, kind, nullptr, D3D_ACT_SWIGLU, nullptr, 0, st, next(L.w_down, Dm, m->ffn)));
+    D3D_TRY(skinny(h16, m->ffn, L.w_down, m->ffn, x32, Dm, n_seq, Dm, m->ffn, kind, D3D_OUT_F32, nullptr, D3D_ACT_NONE, x32, Dm, st,
+                   last ? next(m->lm_head, m->vocab, Dm) : next(m->layers[l + 1].w_qkv, 3 * Dm, Dm), &n1));
   }
-  D3D_CHECK_CUDA(rmsnorm(m->norm));
   D3D_TRY(skinny(a16, Dm, m->lm_head, Dm, logits, m->vocab, n_seq, m->vocab, Dm, kind, D3D_OUT_F32, nullptr, D3D_ACT_NONE, nullptr, 0, st));
   D3D_CHECK_CUDA(launch_pdl(argmax_kernel, dim3(n_seq), dim3(1024), 0, st, (const float*)logits, (long long)m->vocab, m->vocab, next_tokens));
   D3D_CHECK_LAUNCH();
@@ -788,5 +958,7 @@ extern "C" int d3d_lm_decode_step(const d3d_lm_model* m, void* const* qkv_layers
 extern "C" int d3d_lm_decode_set_pdl(int on) {
   g_decode_pdl = (on & 1) != 0;
   g_decode_attn_impl = (on & 2) ? 0 : 1;  // bit 1: the register-staged decode attention instead of the cp.async-staged one
+  g_decode_prefetch = (on & 4) == 0;      // bit 2: no L2 prefetch of the next kernel's weights
+  g_decode_dbg = (on >> 3) & 3;           // bits 3, 4: timing experiments (results are wrong)
   return 0;
 }

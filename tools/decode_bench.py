@@ -18,6 +18,20 @@ last = (cu[1:] - 1).to(torch.int32).contiguous()
 from dynam3d_b200 import _lib as L  # noqa: E402
 L.lib().d3d_lm_decode_set_pdl(int(os.environ.get("PDL", 1)))
 L.lib().d3d_gemm_skinny_set_config(int(os.environ.get("SKCFG", 0)))
+import time  # noqa: E402
+_lib = L.lib()
+_orig = _lib.d3d_lm_decode_step
+host_s = []
+
+
+def _timed(*a):
+    t = time.perf_counter()
+    r = _orig(*a)
+    host_s.append(time.perf_counter() - t)
+    return r
+
+
+_lib.d3d_lm_decode_step = _timed
 res = {}
 for n_new in (1, 20):
     ts = []
@@ -39,7 +53,7 @@ wbytes = layers * (3 * 3072 * 3072 + 3072 * 3072 + 2 * 8192 * 3072 + 3072 * 8192
 kv_bytes = layers * sum(lens) * 2 * 3072 * 2
 out = {"prefill_ms": round(res[1], 2), "generate20_ms": round(res[20], 2), "decode_step_ms": round(step_ms, 3), "weight_GB": round(wbytes / 1e9, 2),
        "kv_GB_per_step": round(kv_bytes / 1e9, 2), "hbm_GBs": round((wbytes + kv_bytes) / step_ms / 1e6, 1),
-       "pdl": int(os.environ.get("PDL", 1)), "skcfg": int(os.environ.get("SKCFG", 0))}
+       "host_ms_first_calls": [round(1e3 * t, 3) for t in host_s[:3] + host_s[19:22]], "pdl": int(os.environ.get("PDL", 1)), "skcfg": int(os.environ.get("SKCFG", 0))}
 print(json.dumps(out))
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/decode_bench_pdl%d.json" % out["pdl"], "w"))
