@@ -121,6 +121,7 @@ SIGNATURES = {
     "d3d_rope": [_P, _L, _P, _P, _I, _I, _I, _I, _P],
     "d3d_gemm_skinny": [_P, _P], "d3d_gemm_skinny_set_config": [_I], "d3d_argmax_rows": [_P, _L, _I, _I, _P, _P],
     "d3d_decode_attention": [_P, _L, _P, _I, _I, _I, _I, _I, _I, _F, _P, _L, _P],
+    "d3d_decode_attention_rope": [_P, _L, _P, _I, _I, _I, _I, _I, _I, _F, _P, _P, _L, _P],
     "d3d_lm_decode_set_pdl": [_I],
     "d3d_lm_decode_step": [_P, _P, _L, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "d3d_rope_table": [_P, _P, _I, _I, _P, _P], "d3d_rope_apply": [_P, _L, _P, _I, _I, _I, _I, _P],

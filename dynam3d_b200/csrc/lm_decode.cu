@@ -533,48 +533,91 @@ __global__ void __launch_bounds__(DA_WARPS * 32, 1) decode_attn_kernel(const uin
   }
 }
 
-// Staged decode attention: the same arithmetic, but every warp streams ITS key blocks (16 keys = K and V head slices, 4*DH bytes per key)
-// through a private double buffer in shared memory with 16-byte cp.async -- 12 KB in flight per warp instead of the 3 KB the register-
-// staged kernel can hold, 192 KB per SM at two CTAs.  (cp.async.bulk per 192-byte row piece was tried and lost: ~3 000 bulk requests per
-// CTA saturate the copy engine, 4.2 ms per step vs 3.6.)  Under programmatic dependent launch a warp issues its first two blocks -- OLD
-// cache rows, which nothing in flight writes -- before griddepcontrol.wait, i.e. while this step's QKV GEMM / RoPE still run; only the block
-// that holds the newest key and the query row wait for them.
+// Staged decode attention.  Every warp streams ITS key blocks (16 keys = K and V head slices, 4*DH bytes per key) through a private double
+// buffer in shared memory with 16-byte cp.async -- 12 KB in flight per warp instead of the 3 KB the register-staged kernel can hold, 192 KB
+// per SM at two CTAs.  (cp.async.bulk per 192-byte row piece was tried and lost: ~3 000 bulk requests per CTA saturate the copy engine.)
+// The arithmetic of a block runs on the tensor cores in TRANSPOSED form, so that the 16 keys -- not the single query -- fill the M side:
+//   S^T[16 keys x 8] = K[16 x DH] . q^T[DH x 8]     (column 0 = the query, columns 1..7 zero)      DH/16 mma.m16n8k16
+//   O^T[DH x 8]     += V^T[DH x 16 keys] . P^T[16 x 8]                                             DH/16 mma.m16n8k16
+// K fragments by ldmatrix, V^T fragments by ldmatrix.trans (rows padded to 4*DH + 16 bytes: conflict-free), fp32 accumulate, P rounded to
+// 16 bit like in the prefill kernels.  The CUDA-core version (4 channels per lane, shuffle-reduced dot products) issued ~500 instructions
+// per block and warp: with 16 warps per SM the kernel was bound by issue slots, ~3 400 cycles per block, whether or not the keys came
+// from HBM (clock stamps, tools/decode_attn_stamps.py).
+// Under programmatic dependent launch a warp issues its first two blocks -- OLD cache rows, which nothing in flight writes -- before
+// griddepcontrol.wait, i.e. while this step's QKV GEMM / RoPE still run; only the block with the newest key and the query row wait.
 constexpr int DC_WARPS = 8;
 constexpr int DC_KEYS = 16;
-__device__ __forceinline__ void dc_cp_async16(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+__device__ __forceinline__ void dc_cp_async16(uint32_t dst, const void* src, int src_bytes = 16) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void dc_ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void dc_ldsm_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
 }
 template <int DH>
-__global__ void __launch_bounds__(DC_WARPS * 32) decode_attn_staged_kernel(const uint16_t* __restrict__ qkv, long long ld, const int* __restrict__ cu,
-                                                                           int n_seq, int t_prefill, int step, int H, int kind, float scale,
-                                                                           uint16_t* __restrict__ out, long long ldo, int dbg_same_block) {
-  constexpr int ACTIVE = DH / 4;
+__global__ void __launch_bounds__(DC_WARPS * 32) decode_attn_staged_kernel(uint16_t* qkv, long long ld, const int* __restrict__ cu, int n_seq,
+                                                                           int t_prefill, int step, int H, int kind, float scale,
+                                                                           uint16_t* __restrict__ out, long long ldo, const float* __restrict__ rope_tab,
+                                                                           int dbg_same_block) {
+  static_assert(DH % 16 == 0, "head_dim % 16");
   constexpr int ROWB = DH * 4;            // K then V head slice of one key, bytes
+  constexpr int PITCH = ROWB + 16;        // shared-memory row: 8 consecutive rows start 4 banks apart (ldmatrix conflict-free)
   constexpr int CPK = ROWB / 16;          // 16-byte chunks per key
   constexpr int HALF = CPK / 2;           // ... of which the first half is K
-  constexpr int BLOCK_BYTES = DC_KEYS * ROWB;
+  constexpr int BLOCK_BYTES = DC_KEYS * PITCH;
+  constexpr int KS = DH / 16;             // k-steps of S^T = m-tiles of O^T
   extern __shared__ __align__(128) uint8_t dc_smem[];
   __shared__ float s_m[DC_WARPS], s_l[DC_WARPS], s_acc[DC_WARPS][DH];
   const int b = blockIdx.x, h = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_trigger();
+#ifdef D3D_SK_STAMPS
+  const bool st_on = b == 0 && h == 0 && threadIdx.x == 0;
+  if (st_on) g_sk_stamps[0] = clock64();
+  if (threadIdx.x == 0) g_sk_cta_times[0][(b * gridDim.y + h) % 320][0] = gtime();
+#endif
   const int p0 = cu[b], n_pre = cu[b + 1] - p0;  // cu_seqlens: uploaded before the prefill, constant during generation
   const int n_keys = n_pre + step + 1;
   const int n_blk = (n_keys + DC_KEYS - 1) / DC_KEYS;
   const uint32_t wbase = smem_u32(dc_smem) + (uint32_t)warp * 2u * BLOCK_BYTES;
   const long long k_col = (long long)(H + h) * DH, v_col = (long long)(2 * H + h) * DH;
   bool waited = false;
+  // Chunk c = lane + 32 i of a block is (key c / CPK, 16-byte piece c % CPK): the pattern repeats every PER iterations (= KPP keys), so the
+  // per-lane pieces are three constants and a block is 12 address adds -- computed per chunk (divisions, row select, 64-bit multiplies)
+  // the issue of one block cost ~2 800 cycles with 16 warps per SM
+  constexpr int PER = CPK == 24 ? 3 : 1;
+  constexpr int KPP = PER * 32 / CPK;  // keys per pattern: 4 (head_dim 96), 2 (64), 1 (128)
+  static_assert(DC_KEYS % KPP == 0 && (PER * 32) % CPK == 0, "chunk pattern");
+  uint32_t doff[PER];
+  long long soff[PER];
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int c = lane + 32 * i, key = c / CPK, ch = c - key * CPK;
+    doff[i] = (uint32_t)(key * PITCH + ch * 16);
+    soff[i] = (long long)key * ld + (ch < HALF ? k_col + ch * 8 : v_col + (ch - HALF) * 8);
+  }
   auto issue = [&](int blk, int buf) {  // one commit group per call (possibly empty)
     if (blk < n_blk) {
       if (blk == n_blk - 1 && !waited) { pdl_wait(); waited = true; }  // the newest key row comes from this step's QKV GEMM + RoPE
-      for (int c = lane; c < DC_KEYS * CPK; c += 32) {
-        const int key = c / CPK, ch = c - key * CPK;
-        int j = blk * DC_KEYS + key;
-        if (j < n_keys) {
-          if (dbg_same_block) j = key;
+      const int j0 = blk * DC_KEYS;
+      const uint32_t dst0 = wbase + (uint32_t)(buf * BLOCK_BYTES);
+      if (j0 + DC_KEYS <= n_pre && !dbg_same_block) {  // whole block inside the (contiguous) prefill rows
+        const uint16_t* src0 = qkv + (long long)(p0 + j0) * ld;
+#pragma unroll
+        for (int gk = 0; gk < DC_KEYS / KPP; ++gk)
+#pragma unroll
+          for (int i = 0; i < PER; ++i) dc_cp_async16(dst0 + (uint32_t)(gk * KPP * PITCH) + doff[i], src0 + (long long)(gk * KPP) * ld + soff[i]);
+      } else {
+        for (int c = lane; c < DC_KEYS * CPK; c += 32) {
+          const int key = c / CPK, ch = c - key * CPK;
+          int j = j0 + key;
+          const bool ok = j < n_keys;  // rows past the end are zero-filled: 0 * stale shared memory must stay finite
+          if (!ok || dbg_same_block) j = ok ? key : 0;
           const long long row = j < n_pre ? (long long)(p0 + j) : (long long)t_prefill + (long long)(j - n_pre) * n_seq + b;
           const uint16_t* src = qkv + row * ld + (ch < HALF ? k_col + ch * 8 : v_col + (ch - HALF) * 8);
-          dc_cp_async16(wbase + (uint32_t)(buf * BLOCK_BYTES + key * ROWB + ch * 16), src);
+          dc_cp_async16(dst0 + (uint32_t)(key * PITCH + ch * 16), src, ok ? 16 : 0);
         }
       }
     }
@@ -583,70 +626,132 @@ __global__ void __launch_bounds__(DC_WARPS * 32) decode_attn_staged_kernel(const
   issue(warp, 0);
   issue(warp + DC_WARPS, 1);
   if (!waited) { pdl_wait(); waited = true; }
-  const bool on = lane < ACTIVE;
-  const long long q_row = (long long)t_prefill + (long long)step * n_seq + b;
-  float q[4];
+#ifdef D3D_SK_STAMPS
+  if (st_on) g_sk_stamps[1] = clock64();
+  if (threadIdx.x == 0) g_sk_cta_times[0][(b * gridDim.y + h) % 320][1] = gtime();
+#endif
+  const int g = lane >> 2, t = lane & 3;
+  // B fragments of q^T (column 0 only: lanes with g == 0): b0 = dims 16 ks + 2t, +1; b1 = dims 16 ks + 2t + 8, +9
+  uint32_t qb[KS][2];
   {
-    const uint2 v = on ? *reinterpret_cast<const uint2*>(qkv + q_row * ld + (long long)h * DH + lane * 4) : make_uint2(0, 0);
-    const float2 a = unpack16x2(v.x, kind), c = unpack16x2(v.y, kind);
-    q[0] = a.x * scale; q[1] = a.y * scale; q[2] = c.x * scale; q[3] = c.y * scale;
+    const uint16_t* qp = qkv + ((long long)t_prefill + (long long)step * n_seq + b) * ld + (long long)h * DH;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      qb[ks][0] = g == 0 ? *reinterpret_cast<const uint32_t*>(qp + ks * 16 + 2 * t) : 0u;
+      qb[ks][1] = g == 0 ? *reinterpret_cast<const uint32_t*>(qp + ks * 16 + 2 * t + 8) : 0u;
+    }
   }
-  float m = -INFINITY, l = 0.f, acc[4] = {0.f, 0.f, 0.f, 0.f};
+  // RoPE of the step's own row, fused (rope_tab != NULL: the row arrives un-rotated from the QKV GEMM): channel i pairs with i + DH/2, i.e.
+  // k-step ks with ks + KS/2 in the SAME lane; the arithmetic and 16-bit rounding of rope_apply_kernel (nn_kernels.cu), so the cache row
+  // equals what a prefill would have written.  q is rotated in registers; the key is rotated by the warp that owns the last block (below).
+  const float* tb = rope_tab ? rope_tab + (long long)b * DH : nullptr;  // [cos (DH/2) | sin (DH/2)] of this sequence's position
+  auto rot = [&](uint32_t& lo, uint32_t& hi, int i0) {  // channels (i0, i0 + 1) and their partners
+    const float2 a = unpack16x2(lo, kind), bb = unpack16x2(hi, kind);
+    const float c0 = tb[i0], c1 = tb[i0 + 1], s0 = tb[DH / 2 + i0], s1 = tb[DH / 2 + i0 + 1];
+    lo = pack16x2(__fsub_rn(__fmul_rn(a.x, c0), __fmul_rn(bb.x, s0)), __fsub_rn(__fmul_rn(a.y, c1), __fmul_rn(bb.y, s1)), kind);
+    hi = pack16x2(__fadd_rn(__fmul_rn(bb.x, c0), __fmul_rn(a.x, s0)), __fadd_rn(__fmul_rn(bb.y, c1), __fmul_rn(a.y, s1)), kind);
+  };
+  if (tb && g == 0) {
+#pragma unroll
+    for (int ks = 0; ks < KS / 2; ++ks) {
+      rot(qb[ks][0], qb[ks + KS / 2][0], ks * 16 + 2 * t);
+      rot(qb[ks][1], qb[ks + KS / 2][1], ks * 16 + 2 * t + 8);
+    }
+  }
+  float m = -INFINITY, l = 0.f;
+  float o[KS][4];  // O^T tiles: [0] / [2] in lanes t == 0 are channels 16 mt + g / + g + 8
+#pragma unroll
+  for (int i = 0; i < KS; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
   int buf = 0;
   for (int blk = warp; blk < n_blk; blk += DC_WARPS, buf ^= 1) {
+#ifdef D3D_SK_STAMPS
+    if (st_on && blk / DC_WARPS < 10) g_sk_stamps[2 + 3 * (blk / DC_WARPS)] = clock64();
+#endif
     asm volatile("cp.async.wait_group 1;" ::: "memory");
     __syncwarp();
-    const uint32_t st = wbase + (uint32_t)(buf * BLOCK_BYTES) + (uint32_t)lane * 8u;
+#ifdef D3D_SK_STAMPS
+    if (st_on && blk / DC_WARPS < 10) g_sk_stamps[3 + 3 * (blk / DC_WARPS)] = clock64();
+#endif
+    const uint32_t st = wbase + (uint32_t)(buf * BLOCK_BYTES);
     const int nvalid = min(DC_KEYS, n_keys - blk * DC_KEYS);
-#pragma unroll
-    for (int b8 = 0; b8 < DC_KEYS; b8 += DA_U) {
-      if (b8 >= nvalid) break;  // warp-uniform
-      float kf[DA_U][4], vf[DA_U][4], sc[DA_U];
-#pragma unroll
-      for (int u = 0; u < DA_U; ++u) {
-        uint2 kv = make_uint2(0, 0), vv = make_uint2(0, 0);
-        if (on && b8 + u < nvalid) {  // rows past nvalid were never written
-          asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(kv.x), "=r"(kv.y) : "r"(st + (uint32_t)((b8 + u) * ROWB)));
-          asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(vv.x), "=r"(vv.y) : "r"(st + (uint32_t)((b8 + u) * ROWB + DH * 2)));
-        }
-        const float2 k0 = unpack16x2(kv.x, kind), k1 = unpack16x2(kv.y, kind), v0 = unpack16x2(vv.x, kind), v1 = unpack16x2(vv.y, kind);
-        kf[u][0] = k0.x; kf[u][1] = k0.y; kf[u][2] = k1.x; kf[u][3] = k1.y;
-        vf[u][0] = v0.x; vf[u][1] = v0.y; vf[u][2] = v1.x; vf[u][3] = v1.y;
+    if (tb && blk == n_blk - 1) {  // the newest key: rotate it in shared memory and in the cache row (for the steps to come)
+      if (lane < DH / 4) {
+        const uint32_t ka = st + (uint32_t)((nvalid - 1) * PITCH + lane * 4);
+        uint32_t lo, hi;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(lo) : "r"(ka));
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(hi) : "r"(ka + DH));
+        rot(lo, hi, 2 * lane);
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(ka), "r"(lo) : "memory");
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(ka + DH), "r"(hi) : "memory");
+        uint16_t* kr = qkv + ((long long)t_prefill + (long long)step * n_seq + b) * ld + k_col + 2 * lane;
+        *reinterpret_cast<uint32_t*>(kr) = lo;
+        *reinterpret_cast<uint32_t*>(kr + DH / 2) = hi;
       }
+      __syncwarp();
+    }
+    // ---- S^T = K q^T ----
+    float sc[4] = {0.f, 0.f, 0.f, 0.f};
+    {
+      const uint32_t ka = st + (uint32_t)((lane & 15) * PITCH + (lane >> 4) * 16);
 #pragma unroll
-      for (int u = 0; u < DA_U; ++u) sc[u] = (q[0] * kf[u][0] + q[1] * kf[u][1]) + (q[2] * kf[u][2] + q[3] * kf[u][3]);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-        for (int u = 0; u < DA_U; ++u) sc[u] += __shfl_xor_sync(0xffffffffu, sc[u], o);
-      float mx = m;
-#pragma unroll
-      for (int u = 0; u < DA_U; ++u) {
-        if (b8 + u >= nvalid) sc[u] = -INFINITY;
-        mx = fmaxf(mx, sc[u]);
+      for (int ks = 0; ks < KS; ++ks) {
+        uint32_t a0, a1, a2, a3;
+        dc_ldsm_x4(ka + ks * 32, a0, a1, a2, a3);
+        mma16816(sc, a0, a1, a2, a3, qb[ks][0], qb[ks][1], kind);
       }
-      const float c = __expf(m - mx);  // 0 on the first batch (m = -inf)
-      l *= c;
+    }
+    // column 0 lives in the lanes t == 0: sc[0] = key g, sc[2] = key g + 8; broadcast over the 4 lanes of a group, then reduce over g
+    float s_lo = __shfl_sync(0xffffffffu, sc[0], lane & ~3) * scale, s_hi = __shfl_sync(0xffffffffu, sc[2], lane & ~3) * scale;
+    if (g >= nvalid) s_lo = -INFINITY;
+    if (g + 8 >= nvalid) s_hi = -INFINITY;
+    float mx = fmaxf(s_lo, s_hi);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) acc[i] *= c;
+    for (int ofs = 4; ofs < 32; ofs <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, ofs));
+    const float mn = fmaxf(m, mx);  // finite: every block has at least one valid key
+    const float corr = __expf(m - mn);  // 0 on the first block (m = -inf)
+    const float p_lo = __expf(s_lo - mn), p_hi = __expf(s_hi - mn);
+    float ps = p_lo + p_hi;
 #pragma unroll
-      for (int u = 0; u < DA_U; ++u) {
-        const float p = __expf(sc[u] - mx);
-        l += p;
+    for (int ofs = 4; ofs < 32; ofs <<= 1) ps += __shfl_xor_sync(0xffffffffu, ps, ofs);
+    l = l * corr + ps;
+    m = mn;
+    // B fragments of P^T (column 0: lanes g == 0): b0 = keys 2t, 2t+1; b1 = keys 2t+8, 2t+9
+    const float pa = __shfl_sync(0xffffffffu, p_lo, 8 * t), pb = __shfl_sync(0xffffffffu, p_lo, 8 * t + 4);
+    const float pc = __shfl_sync(0xffffffffu, p_hi, 8 * t), pd = __shfl_sync(0xffffffffu, p_hi, 8 * t + 4);
+    const uint32_t pb0 = g == 0 ? pack16x2(pa, pb, kind) : 0u, pb1 = g == 0 ? pack16x2(pc, pd, kind) : 0u;
+    // ---- O^T = O^T * corr + V^T P^T ----
+    {
+      const uint32_t va = st + (uint32_t)(((lane & 7) + ((lane >> 4) << 3)) * PITCH + DH * 2 + ((lane >> 3) & 1) * 16);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) acc[i] += p * vf[u][i];
+      for (int mt = 0; mt < KS; ++mt) {
+        uint32_t a0, a1, a2, a3;
+        dc_ldsm_x4_trans(va + mt * 32, a0, a1, a2, a3);
+        o[mt][0] *= corr; o[mt][1] *= corr; o[mt][2] *= corr; o[mt][3] *= corr;
+        mma16816(o[mt], a0, a1, a2, a3, pb0, pb1, kind);
       }
-      m = mx;
     }
     __syncwarp();  // every lane is done with this buffer before it is refilled
+#ifdef D3D_SK_STAMPS
+    if (st_on && blk / DC_WARPS < 10) g_sk_stamps[4 + 3 * (blk / DC_WARPS)] = clock64();
+#endif
     issue(blk + 2 * DC_WARPS, buf);
   }
+#ifdef D3D_SK_STAMPS
+  if (st_on) g_sk_stamps[40] = clock64();
+#endif
   if (lane == 0) { s_m[warp] = m; s_l[warp] = l; }
-  if (on) {
+  if (t == 0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) s_acc[warp][lane * 4 + i] = acc[i];
+    for (int mt = 0; mt < KS; ++mt) {
+      s_acc[warp][mt * 16 + g] = o[mt][0];
+      s_acc[warp][mt * 16 + g + 8] = o[mt][2];
+    }
   }
   __syncthreads();
+#ifdef D3D_SK_STAMPS
+  if (st_on) g_sk_stamps[41] = clock64();
+  if (threadIdx.x == 0) g_sk_cta_times[0][(b * gridDim.y + h) % 320][2] = gtime();
+#endif
   if (threadIdx.x < DH) {
     float gm = -INFINITY;
 #pragma unroll
@@ -848,6 +953,13 @@ extern "C" int d3d_argmax_rows(const float* x, int64_t ld, int rows, int n, int*
 
 extern "C" int d3d_decode_attention(const void* qkv, int64_t ld, const int* cu_seqlens, int n_seq, int t_prefill, int step, int H, int Dh,
                                     int kind, float scale, void* out, int64_t ldo, void* stream) {
+  return d3d_decode_attention_rope((void*)qkv, ld, cu_seqlens, n_seq, t_prefill, step, H, Dh, kind, scale, nullptr, out, ldo, stream);
+}
+
+// rope_tab != NULL ([n_seq, Dh] fp32: cos | sin of every sequence's position, d3d_rope_table): the step's own rows are still un-rotated; the
+// kernel rotates q in registers and the new key in place (cache row), like d3d_rope_apply would have
+extern "C" int d3d_decode_attention_rope(void* qkv, int64_t ld, const int* cu_seqlens, int n_seq, int t_prefill, int step, int H, int Dh, int kind,
+                                         float scale, const float* rope_tab, void* out, int64_t ldo, void* stream) {
   if (n_seq == 0) return 0;
   D3D_REQUIRE(qkv && cu_seqlens && out && step >= 0, "args");
   D3D_REQUIRE(kind == D3D_F16 || kind == D3D_BF16, "16-bit cache");
@@ -856,6 +968,11 @@ extern "C" int d3d_decode_attention(const void* qkv, int64_t ld, const int* cu_s
   const uint16_t* c = (const uint16_t*)qkv;
   const long long ldl = ld, ldol = ldo;
   if (g_decode_attn_impl == 0) {  // register-staged kernel (A/B)
+    if (rope_tab) {
+      const long long total = (long long)n_seq * 2 * H * (Dh / 16);
+      D3D_CHECK_CUDA(launch_pdl(dec_rope_apply_kernel, dim3(d3d_cdiv(total, 256)), dim3(256), 0, st,
+                                (uint16_t*)qkv + ((long long)t_prefill + (long long)step * n_seq) * ld, (long long)ld, rope_tab, n_seq, H, Dh, kind));
+    }
     const dim3 blk(DA_WARPS * 32);
     if (Dh == 96) D3D_CHECK_CUDA(launch_pdl(decode_attn_kernel<96>, grid, blk, 0, st, c, ldl, cu_seqlens, n_seq, t_prefill, step, H, kind, scale, (uint16_t*)out, ldol));
     else if (Dh == 64) D3D_CHECK_CUDA(launch_pdl(decode_attn_kernel<64>, grid, blk, 0, st, c, ldl, cu_seqlens, n_seq, t_prefill, step, H, kind, scale, (uint16_t*)out, ldol));
@@ -868,14 +985,14 @@ extern "C" int d3d_decode_attention(const void* qkv, int64_t ld, const int* cu_s
   const dim3 blk(DC_WARPS * 32);
 #define DB_LAUNCH(DHV)                                                                                                                    \
   do {                                                                                                                                    \
-    constexpr int SMEM = DC_WARPS * 2 * DC_KEYS * DHV * 4;                                                                                \
+    constexpr int SMEM = DC_WARPS * 2 * DC_KEYS * (DHV * 4 + 16);                                                                              \
     static bool attr = false;                                                                                                             \
     if (!attr) {                                                                                                                          \
       D3D_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_staged_kernel<DHV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));              \
       attr = true;                                                                                                                        \
     }                                                                                                                                     \
-    D3D_CHECK_CUDA(launch_pdl(decode_attn_staged_kernel<DHV>, grid, blk, SMEM, st, c, ldl, cu_seqlens, n_seq, t_prefill, step, H, kind, scale, \
-                              (uint16_t*)out, ldol, (g_decode_dbg >> 1) & 1));                                                                                  \
+    D3D_CHECK_CUDA(launch_pdl(decode_attn_staged_kernel<DHV>, grid, blk, SMEM, st, (uint16_t*)qkv, ldl, cu_seqlens, n_seq, t_prefill, step, H, kind, \
+                              scale, (uint16_t*)out, ldol, rope_tab, (g_decode_dbg >> 1) & 1));                                                                                  \
   } while (0)
   if (Dh == 96) DB_LAUNCH(96);
   else if (Dh == 64) DB_LAUNCH(64);
@@ -924,7 +1041,6 @@ extern "C" int d3d_lm_decode_step(const d3d_lm_model* m, void* const* qkv_layers
   auto rmsnorm = [&](const float* w) {
     return launch_pdl(dec_rmsnorm_kernel, norm_grid, dim3(256), 0, st, (const float*)x32, w, m->eps, n_seq, Dm, (uint16_t*)a16, kind);
   };
-  const long long rope_total = (long long)n_seq * 2 * H * (Dh / 16);
   // what the producers of each GEMM pull into L2 for the kernel after next (capped: two matrices plus a layer's K / V stay below the L2 size)
   const long long es = 2, cap = 48ll << 20;
   auto next = [&](const void* w, long long rows_, long long cols_) {
@@ -941,8 +1057,7 @@ extern "C" int d3d_lm_decode_step(const d3d_lm_model* m, void* const* qkv_layers
     const FusedNorm n2{L.rms2, (uint16_t*)a16, m->eps, counter};
     const FusedNorm n1{last ? m->norm : m->layers[last ? l : l + 1].rms1, (uint16_t*)a16, m->eps, counter};
     D3D_TRY(skinny(a16, Dm, L.w_qkv, Dm, rows, ld_qkv, n_seq, 3 * Dm, Dm, kind, kind, nullptr, D3D_ACT_NONE, nullptr, 0, st, next(L.w_o, Dm, Dm)));
-    D3D_CHECK_CUDA(launch_pdl(dec_rope_apply_kernel, dim3(d3d_cdiv(rope_total, 256)), dim3(256), 0, st, rows, (long long)ld_qkv, (const float*)rope_tab, n_seq, H, Dh, kind));
-    D3D_TRY(d3d_decode_attention(qkv_layers_h[l], ld_qkv, cu_seqlens, n_seq, t_prefill, step, H, Dh, kind, scale, att16, Dm, stream));
+    D3D_TRY(d3d_decode_attention_rope(qkv_layers_h[l], ld_qkv, cu_seqlens, n_seq, t_prefill, step, H, Dh, kind, scale, rope_tab, att16, Dm, stream));
     D3D_TRY(skinny(att16, Dm, L.w_o, Dm, x32, Dm, n_seq, Dm, Dm, kind, D3D_OUT_F32, nullptr, D3D_ACT_NONE, x32, Dm, st, next(L.w_gu, 2 * m->ffn, Dm), &n2));
     D3D_TRY(skinny(a16, Dm, L.w_gu, Dm, h16, m->ffn, n_seq, 2 * m->ffn, Dm, kind, kind, nullptr, D3D_ACT_SWIGLU, nullptr, 0, st, next(L.w_down, Dm, m->ffn)));
     D3D_TRY(skinny(h16, m->ffn, L.w_down, m->ffn, x32, Dm, n_seq, Dm, m->ffn, kind, D3D_OUT_F32, nullptr, D3D_ACT_NONE, x32, Dm, st,

@@ -213,6 +213,11 @@ int d3d_argmax_rows(const float* x, int64_t ld, int rows, int n, int* out, void*
 /* Attention of the step's n_seq new query rows over their sequences' cached keys / values (prefill rows [cu[b], cu[b+1]) + decode rows). */
 int d3d_decode_attention(const void* qkv, int64_t ld, const int* cu_seqlens, int n_seq, int t_prefill, int step, int H, int Dh, int kind,
                          float scale, void* out, int64_t ldo, void* stream);
+/* The same with the RoPE of the step's own rows fused: rope_tab = d3d_rope_table of the sequences' positions ([n_seq, Dh] fp32), the rows
+ * t_prefill + step * n_seq + b still un-rotated.  q is rotated in registers, the new key in place (the cache row ends up as d3d_rope_apply
+ * would have left it).  rope_tab == NULL: rows already rotated (= d3d_decode_attention). */
+int d3d_decode_attention_rope(void* qkv, int64_t ld, const int* cu_seqlens, int n_seq, int t_prefill, int step, int H, int Dh, int kind,
+                              float scale, const float* rope_tab, void* out, int64_t ldo, void* stream);
 /* One decode step for all sequences: embeds tokens_in [n_seq], runs the layers (qkv_layers_h: HOST array of the per-layer cache base
  * pointers), writes logits [n_seq, vocab] fp32 and next_tokens [n_seq].  Scratch: x32 [n_seq,hidden] f32, a16 [n_seq,hidden], att16
  * [n_seq,hidden], h16 [n_seq,ffn] 16-bit, rope_tab [n_seq,head_dim] f32, pos [n_seq] int32. */

@@ -65,6 +65,52 @@ def test_argmax_first_maximum():
     assert out.cpu().tolist() == x.argmax(-1).cpu().tolist() and out[0].item() == 100
 
 
+@pytest.mark.parametrize("H,Dh,lens,dtype", [(32, 96, [735, 745, 16, 1, 33], torch.float16), (8, 64, [40, 3], torch.bfloat16), (4, 128, [17, 300], torch.float16)])
+def test_decode_attention_kernel(H, Dh, lens, dtype):
+    """The decode attention in isolation: (1) vs fp32 torch over [prefill rows || earlier decode rows || own row]; (2) with the RoPE of the
+    step's rows fused the output AND the cache rows are bit-identical to d3d_rope_apply followed by the plain call."""
+    import ctypes
+    from dynam3d_b200 import _lib as L, ops
+    n_seq, step = len(lens), 2
+    T = sum(lens)
+    rows = T + (step + 1) * n_seq
+    g = torch.Generator().manual_seed(H * 1000 + Dh)
+    qkv = (torch.randn(rows, 3 * H * Dh, generator=g) * 0.6).to(dtype).cuda()
+    cu = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), device="cuda", dtype=torch.int32)
+    pos = torch.tensor([n + step for n in lens], device="cuda", dtype=torch.int32)
+    inv_freq = (1.0 / (10000.0 ** (torch.arange(0, Dh, 2, dtype=torch.float32) / Dh))).cuda()
+    tab = ops.rope_table(pos, inv_freq, Dh)
+    scale = ctypes.c_float(Dh ** -0.5)
+    kind = L.kind_of(dtype)
+    own = slice(T + step * n_seq, T + (step + 1) * n_seq)
+    # reference path: rotate the step's rows, then the plain kernel
+    ref_cache = qkv.clone()
+    ops.rope_apply(ref_cache[own], tab, H, Dh)
+    ref = torch.empty(n_seq, H * Dh, device="cuda", dtype=dtype)
+    L.check(L.lib().d3d_decode_attention(L.ptr(ref_cache), ref_cache.stride(0), L.ptr(cu), n_seq, T, step, H, Dh, kind, scale, L.ptr(ref), ref.stride(0),
+                                         L.stream_ptr()))
+    # fused path on the un-rotated rows
+    cache = qkv.clone()
+    out = torch.empty_like(ref)
+    L.check(L.lib().d3d_decode_attention_rope(L.ptr(cache), cache.stride(0), L.ptr(cu), n_seq, T, step, H, Dh, kind, scale, L.ptr(tab), L.ptr(out),
+                                              out.stride(0), L.stream_ptr()))
+    assert torch.equal(out, ref)
+    HD = H * Dh
+    assert torch.equal(cache[own, HD:], ref_cache[own, HD:])          # K rotated in place, V untouched
+    assert torch.equal(cache[:T + step * n_seq], qkv[:T + step * n_seq])  # nothing else written
+    # fp32 torch reference
+    c32 = ref_cache.float()
+    for b, n in enumerate(lens):
+        idx = list(range(int(cu[b]), int(cu[b]) + n)) + [T + s * n_seq + b for s in range(step + 1)]
+        q = c32[T + step * n_seq + b, :HD].view(H, Dh)
+        k = c32[idx, HD:2 * HD].view(-1, H, Dh)
+        v = c32[idx, 2 * HD:].view(-1, H, Dh)
+        p = torch.softmax(torch.einsum("hd,jhd->hj", q, k) * Dh ** -0.5, -1)
+        want = torch.einsum("hj,jhd->hd", p, v).reshape(-1)
+        tol = 3e-3 if dtype == torch.float16 else 2e-2   # 16-bit P and output rounding
+        assert (ref[b].float() - want).abs().max().item() < tol, b
+
+
 @pytest.mark.parametrize("cfg", [dict(hidden=768, layers=3, heads=8, ffn=1536, vocab=2048, lens=[37, 70, 5], dtype=torch.float16, n_new=6),
                                  dict(hidden=768, layers=2, heads=8, ffn=1536, vocab=2048, lens=[33], dtype=torch.bfloat16, n_new=4),
                                  dict(hidden=3072, layers=2, heads=32, ffn=8192, vocab=32064, lens=[90, 41], dtype=torch.float16, n_new=4)])
