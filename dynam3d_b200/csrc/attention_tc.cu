@@ -17,29 +17,39 @@
 namespace {
 
 constexpr int BQ = 128;
-constexpr int BKV = 128;
-constexpr int NTHREADS = 320;  // warp 0: TMEM alloc + TMA; warp 1: MMA issue; warps 2-9: softmax (2 per TMEM lane quadrant); 96 regs at 2 CTAs/SM
-constexpr int NSOFT = 8;
 constexpr int ATOM64 = 128 * 64 * 2;                     // [128 rows x 64 columns] 16-bit, SWIZZLE_128B: 16 KB
 constexpr int ATOM32 = 128 * 32 * 2;                     // [128 rows x 32 columns] 16-bit, SWIZZLE_64B: 8 KB (head_dim 96 = 64 + 32)
-// Per head dim.  D = 64: one atom per tile, 2 CTAs per SM (112 KB smem, 256 TMEM columns each).  D = 96 (Phi-3): every Q/K/V tile is a
-// 64-column atom followed by a 32-column atom, the O accumulators take 2 x 96 columns (512-column allocation), one CTA per SM.
-template <int D>
+// Per (head dim, key halves).  HV = key halves per tile = softmax threads per query row: the key tile has 64 * HV rows.
+//   HV = 2 (round 1/2a): 128-key tiles, two threads per row with independent online softmaxes, 2 CTAs per SM at D = 64.
+//   HV = 1: 64-key tiles, one thread per row, half the shared memory and TMEM (S 64 + O D columns): three CTAs per SM at D = 64, TWO at
+//           D = 96 (where HV = 2 fits only one).  Measured (tools/attn_halves.py): Phi-3 prefill shape 0.113 -> 0.088 ms (default there);
+//           ViT shape 0.353 vs 0.357 ms -- a third resident CTA buys nothing, the per-tile hand-offs double (default stays HV = 2).
+// D = 96 (Phi-3): every tile is a 64-column atom followed by a 32-column atom.
+template <int D, int HV>
 struct AC {
   static_assert(D == 64 || D == 96, "head_dim 64 or 96");
+  static_assert(HV == 1 || HV == 2, "key halves");
   static constexpr bool HAS32 = D == 96;
-  static constexpr int TILE_BYTES = ATOM64 + (HAS32 ? ATOM32 : 0);
+  static constexpr int BKV = 64 * HV;
+  static constexpr int NSOFT = 4 * HV;
+  static constexpr int NTHREADS = 64 + 32 * NSOFT;       // warp 0: TMEM alloc + TMA; warp 1: MMA issue; then the softmax warps
+  static constexpr int Q_BYTES = ATOM64 + (HAS32 ? ATOM32 : 0);
+  static constexpr int KV_ATOM64 = BKV * 64 * 2;         // [BKV rows x 64 columns]
+  static constexpr int KV_ATOM32 = BKV * 32 * 2;
+  static constexpr int KV_BYTES = KV_ATOM64 + (HAS32 ? KV_ATOM32 : 0);
   static constexpr int SMEM_Q = 0;
-  static constexpr int SMEM_K = TILE_BYTES;              // 2 stages
-  static constexpr int SMEM_V = 3 * TILE_BYTES;          // 2 stages
-  static constexpr int SMEM_P = 5 * TILE_BYTES;          // [128 x 128] = 2 atoms of [128 x 64]
-  static constexpr int SMEM_BAR = SMEM_P + 2 * ATOM64;
+  static constexpr int SMEM_K = Q_BYTES;                 // 2 stages
+  static constexpr int SMEM_V = SMEM_K + 2 * KV_BYTES;   // 2 stages
+  static constexpr int SMEM_P = SMEM_V + 2 * KV_BYTES;   // [128 x BKV] = HV atoms of [128 x 64]
+  static constexpr int SMEM_BAR = SMEM_P + HV * ATOM64;
   static constexpr int SMEM_BYTES = SMEM_BAR + 640;
-  static constexpr int TMEM_COLS = HAS32 ? 512 : 256;    // S: [0,128)  O of key half 0: [128,128+D)  O of key half 1: [128+D,128+2D)
-  static constexpr int CTAS_PER_SM = HAS32 ? 1 : 2;
+  static constexpr int TMEM_O = 64 * HV;                 // S: [0, 64 HV)   O of key half h: [64 HV + h D, 64 HV + (h + 1) D)
+  static constexpr int TMEM_NEED = 64 * HV + HV * D;
+  static constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512);
+  static constexpr int CTAS_PER_SM = 512 / TMEM_COLS < (233472 / (SMEM_BYTES + 1024)) ? 512 / TMEM_COLS : (233472 / (SMEM_BYTES + 1024));
 };
-static_assert(2 * (AC<64>::SMEM_BYTES + 1024) <= 233472, "two CTAs per SM at head_dim 64");
-static_assert(AC<96>::SMEM_BYTES + 1024 <= 233472, "head_dim 96 fits one CTA");
+static_assert(AC<64, 2>::CTAS_PER_SM == 2 && AC<64, 1>::CTAS_PER_SM == 3, "CTAs per SM at head_dim 64");
+static_assert(AC<96, 2>::CTAS_PER_SM == 1 && AC<96, 1>::CTAS_PER_SM == 2, "CTAs per SM at head_dim 96");
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -177,13 +187,16 @@ __device__ __forceinline__ uint32_t make_idesc(int kind, int m, int n, int b_mn_
 
 // KIND (D3D_F16 / D3D_BF16) is a template parameter: as a run-time argument every P / output pack was emitted for both types and predicated
 // (ncu, round 2: F2FP = 8 % of the issued instructions, half of them predicated off)
-template <int D, int KIND>
-__global__ void __launch_bounds__(NTHREADS, AC<D>::CTAS_PER_SM)
-attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_qkv32, uint16_t* __restrict__ out, long long ldo,
-               const int* __restrict__ cu, const int* __restrict__ lens, int q_tile_begin, int H, int causal, float scale_log2) {
+template <int D, int KIND, int HV>
+__global__ void __launch_bounds__((AC<D, HV>::NTHREADS), (AC<D, HV>::CTAS_PER_SM))
+attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_qkv32, const __grid_constant__ CUtensorMap tm_kv,
+               const __grid_constant__ CUtensorMap tm_kv32, uint16_t* __restrict__ out, long long ldo, const int* __restrict__ cu,
+               const int* __restrict__ lens, int q_tile_begin, int H, int causal, float scale_log2) {
   constexpr int kind = KIND;
-  using C = AC<D>;
-  constexpr int TILE_BYTES = C::TILE_BYTES, SMEM_Q = C::SMEM_Q, SMEM_K = C::SMEM_K, SMEM_V = C::SMEM_V, SMEM_P = C::SMEM_P, SMEM_BAR = C::SMEM_BAR;
+  using C = AC<D, HV>;
+  constexpr int BKV = C::BKV, NSOFT = C::NSOFT;
+  constexpr int TILE_BYTES = C::KV_BYTES, Q_BYTES = C::Q_BYTES, KV_ATOM64 = C::KV_ATOM64;
+  constexpr int SMEM_Q = C::SMEM_Q, SMEM_K = C::SMEM_K, SMEM_V = C::SMEM_V, SMEM_P = C::SMEM_P, SMEM_BAR = C::SMEM_BAR;
   constexpr int TMEM_COLS = C::TMEM_COLS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t sbase = smem_u32(smem_raw);
@@ -224,23 +237,23 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
-  const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 128;
+  const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + C::TMEM_O;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      mbar_expect_tx(bar(0), TILE_BYTES);
+      mbar_expect_tx(bar(0), Q_BYTES);
       tma_load_2d(sbase + SMEM_Q, &tm_qkv, bar(0), h * D, b + q0);
       if (C::HAS32) tma_load_2d(sbase + SMEM_Q + ATOM64, &tm_qkv32, bar(0), h * D + 64, b + q0);
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j & 1;
         mbar_wait(bar(3 + st), (((uint32_t)j >> 1) & 1u) ^ 1u);
         mbar_expect_tx(bar(1 + st), 2 * TILE_BYTES);
-        tma_load_2d(sbase + SMEM_K + st * TILE_BYTES, &tm_qkv, bar(1 + st), (H + h) * D, b + j * BKV);
-        tma_load_2d(sbase + SMEM_V + st * TILE_BYTES, &tm_qkv, bar(1 + st), (2 * H + h) * D, b + j * BKV);
+        tma_load_2d(sbase + SMEM_K + st * TILE_BYTES, &tm_kv, bar(1 + st), (H + h) * D, b + j * BKV);
+        tma_load_2d(sbase + SMEM_V + st * TILE_BYTES, &tm_kv, bar(1 + st), (2 * H + h) * D, b + j * BKV);
         if (C::HAS32) {
-          tma_load_2d(sbase + SMEM_K + st * TILE_BYTES + ATOM64, &tm_qkv32, bar(1 + st), (H + h) * D + 64, b + j * BKV);
-          tma_load_2d(sbase + SMEM_V + st * TILE_BYTES + ATOM64, &tm_qkv32, bar(1 + st), (2 * H + h) * D + 64, b + j * BKV);
+          tma_load_2d(sbase + SMEM_K + st * TILE_BYTES + KV_ATOM64, &tm_kv32, bar(1 + st), (H + h) * D + 64, b + j * BKV);
+          tma_load_2d(sbase + SMEM_V + st * TILE_BYTES + KV_ATOM64, &tm_kv32, bar(1 + st), (2 * H + h) * D + 64, b + j * BKV);
         }
       }
     }
@@ -250,7 +263,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant
 #ifdef D3D_ATTN_STAMPS
       const bool mst_on = blockIdx.x == 1 && blockIdx.y == 5 && blockIdx.z == 40;
 #endif
-      const uint32_t idesc_s = make_idesc(kind, BQ, BKV, 0);
+      const uint32_t idesc_s = make_idesc(kind, BQ, BKV, 0);  // N = 64 or 128 keys
       const uint32_t idesc_o = make_idesc(kind, BQ, 64, 1);
       const uint32_t idesc_o32 = make_idesc(kind, BQ, 32, 1);
       const uint64_t dq = desc_kmajor(sbase + SMEM_Q);
@@ -263,7 +276,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_f16(tmem_s, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, k ? 1u : 0u);
         if (C::HAS32) {  // head dims 64..95: the 32-column atom (two more K-steps)
-          const uint64_t dk32 = desc_kmajor_sw64(sbase + SMEM_K + st * TILE_BYTES + ATOM64);
+          const uint64_t dk32 = desc_kmajor_sw64(sbase + SMEM_K + st * TILE_BYTES + KV_ATOM64);
 #pragma unroll
           for (int k = 0; k < 2; ++k) umma_f16(tmem_s, dq32 + (uint64_t)(2 * k), dk32 + (uint64_t)(2 * k), idesc_s, 1u);
         }
@@ -285,7 +298,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant
         tc_fence_after();
         const uint64_t dp = desc_kmajor(sbase + SMEM_P);
         const uint64_t dv = desc_mnmajor(sbase + SMEM_V + st * TILE_BYTES);
-        const uint64_t dv32 = desc_mnmajor_sw64(sbase + SMEM_V + st * TILE_BYTES + ATOM64);
+        const uint64_t dv32 = desc_mnmajor_sw64(sbase + SMEM_V + st * TILE_BYTES + KV_ATOM64);
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k) {
           // A = P: 16 keys = 32 B inside a 64-key atom (+2), next atom +16 KB; B = V: 16 key rows = 2048 B (+128).
@@ -303,15 +316,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant
     }
   } else {
     // ===================== softmax / correction / epilogue =====================
-    // 8 warps: warp w owns TMEM lane quadrant w&3 (rows) and column half (w-2)>>2: 64 of the 128 keys of a tile and 32 of the
-    // 64 output channels.  A thread holds its 64 scores in registers (one TMEM read per tile); O stays in TMEM and is only
-    // rescaled when a row's running max moves by more than 2^8 (any consistent base <= max + 8 keeps P within 16-bit range).
+    // 4 HV warps: warp w owns TMEM lane quadrant w&3 (rows) and key half (w-2)>>2 (HV = 2: 64 of the 128 keys of a tile and half of the
+    // output channels; HV = 1: the whole 64-key tile and all channels).  A thread holds its 64 scores in registers (one TMEM read per
+    // tile); O stays in TMEM and is only rescaled when a row's running max moves by more than 2^8 (P stays within 16-bit range).
     const int qd = warp & 3;
-    const int hf = (warp - 2) >> 2;
+    const int hf = HV == 2 ? (warp - 2) >> 2 : 0;
     const int r = qd * 32 + lane;        // row inside the tile == TMEM lane
     const int row = q0 + r;
     const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
-    constexpr int DH = D / 2;
+    constexpr int DH = D / HV;  // output channels written by this thread
     float m = -INFINITY, l = 0.f;
     const uint32_t p_row = sbase + SMEM_P + (uint32_t)hf * (uint32_t)ATOM64 + (uint32_t)r * 128u;  // this half's 64-key atom
     const uint32_t sw = (uint32_t)(r & 7);
@@ -417,29 +430,34 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant
     // epilogue: O / l
     mbar_wait_sleepy(bar(8), (uint32_t)(n_tiles - 1) & 1u);
     tc_fence_after();
-    // merge the two key halves of the row: exchange (base, sum) through the (now free) P buffer, then
+    // HV = 2: merge the two key halves of the row: exchange (base, sum) through the (now free) P buffer, then
     // out = (O_mine * 2^(m_mine - M) + O_other * 2^(m_other - M)) / (l_mine * 2^(m_mine - M) + l_other * 2^(m_other - M))
-    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(xsum_mine), "f"(m), "f"(l) : "memory");
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    float m_other, l_other;
-    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(m_other), "=f"(l_other) : "r"(xsum_other) : "memory");
-    const float mm = fmaxf(m, m_other);
-    const float a_mine = (m == -INFINITY) ? 0.f : ex2_approx(m - mm);
-    const float a_other = (m_other == -INFINITY) ? 0.f : ex2_approx(m_other - mm);
-    const float lt = l * a_mine + l_other * a_other;
-    const float inv = lt > 0.f ? 1.0f / lt : 0.f;
-    const float w1 = a_mine * inv, w2 = a_other * inv;
+    float w1, w2 = 0.f;
+    if (HV == 2) {
+      asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(xsum_mine), "f"(m), "f"(l) : "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      float m_other, l_other;
+      asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(m_other), "=f"(l_other) : "r"(xsum_other) : "memory");
+      const float mm = fmaxf(m, m_other);
+      const float a_mine = (m == -INFINITY) ? 0.f : ex2_approx(m - mm);
+      const float a_other = (m_other == -INFINITY) ? 0.f : ex2_approx(m_other - mm);
+      const float lt = l * a_mine + l_other * a_other;
+      const float inv = lt > 0.f ? 1.0f / lt : 0.f;
+      w1 = a_mine * inv; w2 = a_other * inv;
+    } else {
+      w1 = l > 0.f ? 1.0f / l : 0.f;
+    }
     uint4* dst = reinterpret_cast<uint4*>(out + (size_t)(b + row) * ldo + (size_t)h * D + hf * DH);
 #pragma unroll
-    for (int c = 0; c < DH; c += 16) {  // 16 channels at a time (register budget of 2 CTAs / SM)
+    for (int c = 0; c < DH; c += 16) {  // 16 channels at a time (register budget)
       uint32_t o[16], o2[16];
       tmem_ld16(tmem_o + lane_off + (uint32_t)(hf * D + hf * DH + c), o);           // my key half's accumulator, my output channels
-      tmem_ld16(tmem_o + lane_off + (uint32_t)((hf ^ 1) * D + hf * DH + c), o2);    // the other key half's accumulator, same channels
+      if (HV == 2) tmem_ld16(tmem_o + lane_off + (uint32_t)((hf ^ 1) * D + hf * DH + c), o2);  // the other key half's accumulator, same channels
       tmem_ld_wait();
       if (row < len) {
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-          auto f = [&](int k) { return __uint_as_float(o[8 * i + k]) * w1 + __uint_as_float(o2[8 * i + k]) * w2; };
+          auto f = [&](int k) { return HV == 2 ? __uint_as_float(o[8 * i + k]) * w1 + __uint_as_float(o2[8 * i + k]) * w2 : __uint_as_float(o[8 * i + k]) * w1; };
           dst[c / 8 + i] = make_uint4(pack16x2(f(0), f(1), kind), pack16x2(f(2), f(3), kind), pack16x2(f(4), f(5), kind), pack16x2(f(6), f(7), kind));
         }
       }
@@ -464,28 +482,40 @@ extern "C" int d3d_debug_attn_stamps(long long* host_out) {
 #endif
 
 namespace {
-template <int D>
-int launch_attn_tc(const CUtensorMap& tm, const CUtensorMap& tm32, void* out, int64_t ldo, const int* cu_seqlens, const int* lens, int n_seq,
-                   int max_len, int q_tile_begin, int q_tile_end, int H, int causal, int kind, float scale, cudaStream_t st) {
+int g_attn_tc_halves[2] = {2, 1};  // key halves per tile for head_dim 64 / 96 (d3d_attention_tc_set_halves): measured, tools/attn_halves.py
+
+template <int D, int HV>
+int launch_attn_tc(const CUtensorMap& tm, const CUtensorMap& tm32, const CUtensorMap& tmkv, const CUtensorMap& tmkv32, void* out, int64_t ldo,
+                   const int* cu_seqlens, const int* lens, int n_seq, int max_len, int q_tile_begin, int q_tile_end, int H, int causal, int kind,
+                   float scale, cudaStream_t st) {
+  using C = AC<D, HV>;
   static bool attr_set = false;
   if (!attr_set) {
-    D3D_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<D, D3D_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AC<D>::SMEM_BYTES));
-    D3D_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<D, D3D_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AC<D>::SMEM_BYTES));
+    D3D_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<D, D3D_F16, HV>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    D3D_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<D, D3D_BF16, HV>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
   const int q_end = q_tile_end < d3d_cdiv(max_len, BQ) ? q_tile_end : d3d_cdiv(max_len, BQ);
   if (q_end <= q_tile_begin) return 0;
   dim3 grid(q_end - q_tile_begin, H, n_seq);
   if (kind == D3D_BF16)
-    attn_tc_kernel<D, D3D_BF16><<<grid, NTHREADS, AC<D>::SMEM_BYTES, st>>>(tm, tm32, (uint16_t*)out, ldo, cu_seqlens, lens, q_tile_begin, H, causal,
-                                                                           scale * 1.4426950408889634f);
+    attn_tc_kernel<D, D3D_BF16, HV><<<grid, C::NTHREADS, C::SMEM_BYTES, st>>>(tm, tm32, tmkv, tmkv32, (uint16_t*)out, ldo, cu_seqlens, lens, q_tile_begin, H,
+                                                                             causal, scale * 1.4426950408889634f);
   else
-    attn_tc_kernel<D, D3D_F16><<<grid, NTHREADS, AC<D>::SMEM_BYTES, st>>>(tm, tm32, (uint16_t*)out, ldo, cu_seqlens, lens, q_tile_begin, H, causal,
-                                                                          scale * 1.4426950408889634f);
+    attn_tc_kernel<D, D3D_F16, HV><<<grid, C::NTHREADS, C::SMEM_BYTES, st>>>(tm, tm32, tmkv, tmkv32, (uint16_t*)out, ldo, cu_seqlens, lens, q_tile_begin, H,
+                                                                            causal, scale * 1.4426950408889634f);
   D3D_CHECK_LAUNCH();
   return 0;
 }
 }  // namespace
+
+// key halves per tile (1: 64-key tiles, one softmax thread per row, more CTAs per SM; 2: 128-key tiles, two threads per row) per head dim
+extern "C" int d3d_attention_tc_set_halves(int halves_d64, int halves_d96) {
+  D3D_REQUIRE((halves_d64 == 1 || halves_d64 == 2) && (halves_d96 == 1 || halves_d96 == 2), "halves are 1 or 2");
+  g_attn_tc_halves[0] = halves_d64;
+  g_attn_tc_halves[1] = halves_d96;
+  return 0;
+}
 
 extern "C" int d3d_attention_tc(const void* qkv, int64_t ld, int64_t n_rows, void* out, int64_t ldo, const int* cu_seqlens, int n_seq,
                                 int max_len, int H, int Dh, int causal, int kind, float scale, void* stream) {
@@ -512,24 +542,34 @@ extern "C" int d3d_attention_tc_ex(const void* qkv, int64_t ld, int64_t n_rows, 
     }
     fn = (EncodeTiledFn)p;
   }
-  CUtensorMap tm, tm32;
+  const int hv = g_attn_tc_halves[Dh == 96 ? 1 : 0];
+  CUtensorMap tm, tm32, tmkv, tmkv32;
   cuuint64_t dims[2] = {(cuuint64_t)(3 * H * Dh), (cuuint64_t)n_rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
   cuuint32_t estr[2] = {1, 1};
   const CUtensorMapDataType dt = kind == D3D_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-  cuuint32_t box[2] = {64, 128};
-  CUresult r = fn(&tm, dt, 2, (void*)qkv, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r == CUDA_SUCCESS) {  // the 32-column atom of head_dim 96 (unused at 64, but the kernel signature is shared)
-    cuuint32_t box32[2] = {32, 128};
-    r = fn(&tm32, dt, 2, (void*)qkv, dims, strides, box32, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
-           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  }
+  // query tiles: 128 rows; key / value tiles: 64 * halves rows; each as a 64-column (SWIZZLE_128B) and, for head_dim 96, a 32-column atom
+  auto encode = [&](CUtensorMap* m, cuuint32_t cols, cuuint32_t rows) {
+    cuuint32_t box[2] = {cols, rows};
+    return fn(m, dt, 2, (void*)qkv, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  };
+  CUresult r = encode(&tm, 64, 128);
+  if (r == CUDA_SUCCESS) r = encode(&tm32, 32, 128);  // unused at head_dim 64, but the kernel signature is shared
+  if (r == CUDA_SUCCESS) r = encode(&tmkv, 64, 64 * hv);
+  if (r == CUDA_SUCCESS) r = encode(&tmkv32, 32, 64 * hv);
   if (r != CUDA_SUCCESS) {
     d3d_set_error("cuTensorMapEncodeTiled(qkv) failed (%d)", (int)r);
     return D3D_ECUDA;
   }
-  if (Dh == 96)
-    return launch_attn_tc<96>(tm, tm32, out, ldo, cu_seqlens, seq_len, n_seq, max_len, q_tile_begin, q_tile_end, H, causal, kind, scale, (cudaStream_t)stream);
-  return launch_attn_tc<64>(tm, tm32, out, ldo, cu_seqlens, seq_len, n_seq, max_len, q_tile_begin, q_tile_end, H, causal, kind, scale, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+#define ATT_GO(DV, HVV) \
+  return launch_attn_tc<DV, HVV>(tm, tm32, tmkv, tmkv32, out, ldo, cu_seqlens, seq_len, n_seq, max_len, q_tile_begin, q_tile_end, H, causal, kind, scale, st)
+  if (Dh == 96) {
+    if (hv == 1) ATT_GO(96, 1);
+    ATT_GO(96, 2);
+  }
+  if (hv == 1) ATT_GO(64, 1);
+  ATT_GO(64, 2);
+#undef ATT_GO
 }

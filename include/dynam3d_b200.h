@@ -353,6 +353,9 @@ int d3d_attention_tc(const void* qkv, int64_t ld, int64_t n_rows, void* out, int
  * cache (d3d_phi3_prefill_chunk): keys [0, len) of the sequence, queries of the selected tiles. */
 int d3d_attention_tc_ex(const void* qkv, int64_t ld, int64_t n_rows, void* out, int64_t ldo, const int* seq_start, const int* seq_len,
                         int n_seq, int max_len, int q_tile_begin, int q_tile_end, int H, int Dh, int causal, int kind, float scale, void* stream);
+/* Tile shape of the tcgen05 attention per head dim: key halves per tile = softmax threads per query row.  1: 64-key tiles, one thread per
+ * row, more resident CTAs per SM (default at head_dim 96: two CTAs instead of one); 2: 128-key tiles, two threads per row (default at 64). */
+int d3d_attention_tc_set_halves(int halves_d64, int halves_d96);
 
 /* ------------------------------------------------------------------------------------------------
  * Token builders for the layer-wise pooling (patch -> instance -> zone) and the merge discriminator.

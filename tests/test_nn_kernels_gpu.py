@@ -87,6 +87,36 @@ def test_attention_matches_torch(lens, H, Dh, causal, dtype, impl):
         s += n
 
 
+@pytest.mark.parametrize("halves", [1, 2])
+@pytest.mark.parametrize("lens,H,Dh,causal,dtype", [
+    ([577, 577, 64, 65, 1], 16, 64, False, torch.float16),
+    ([700, 130, 128, 5], 3, 64, True, torch.bfloat16),
+    ([735, 745, 300, 129, 63], 8, 96, True, torch.float16),
+    ([200, 65], 2, 96, False, torch.bfloat16),
+])
+def test_attention_tc_tile_shapes(lens, H, Dh, causal, dtype, halves):
+    """Both tile shapes of the tcgen05 attention (64- and 128-key tiles) at both head dims vs fp32 torch."""
+    from dynam3d_b200 import ops, _lib as L
+    T = sum(lens)
+    g = torch.Generator().manual_seed(T + Dh)
+    qkv = (torch.randn(T, 3 * H * Dh, generator=g) * 0.7).to(dtype).cuda()
+    out = torch.zeros(T, H * Dh, device="cuda", dtype=dtype)
+    cu = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), device="cuda", dtype=torch.int32)
+    L.check(L.lib().d3d_attention_tc_set_halves(halves, halves))
+    try:
+        ops.attention(qkv, out, cu, len(lens), max(lens), H, Dh, causal=causal, impl="tc")
+        torch.cuda.synchronize()
+    finally:
+        L.check(L.lib().d3d_attention_tc_set_halves(2, 1))  # the defaults
+    s = 0
+    for n in lens:
+        q, k, v = [t.view(n, H, Dh).transpose(0, 1).float() for t in qkv[s:s + n].split(H * Dh, -1)]
+        ref = F.scaled_dot_product_attention(q[None], k[None], v[None], is_causal=causal)[0].transpose(0, 1).reshape(n, H * Dh)
+        tol = 3e-3 if dtype == torch.float16 else 2e-2
+        assert (out[s:s + n].float() - ref).abs().max().item() < tol, (n, halves)
+        s += n
+
+
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("lens", [[1, 2, 33, 64, 65, 300, 130, 16, 17, 48], [37] * 1500 + [100, 3], [5, 64, 1, 31]])
 def test_attention_mixed_lengths(lens, dtype):
