@@ -46,6 +46,42 @@ def peaks():
     return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def decode_roofline(net, seq_lens, peak_hbm):
+    """The decode token step of the --generate line on its own (POL:463): (prefill + 20 tokens) - (prefill) over 19 steps at the
+    step's own prompt lengths, CUDA events; algorithmic bytes per token step = every language-model weight once + the K / V rows of the prompts."""
+    lm = net.llava.lm
+    w = lm.w
+    dev = net.device
+    lens = [int(n) for n in seq_lens]
+    x = torch.randn((sum(lens), w.hidden), device=dev, dtype=torch.float32) * 0.05
+    cu = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int32, device=dev)
+    pos = torch.cat([torch.arange(n, dtype=torch.int32) for n in lens]).to(dev)
+    last = (cu[1:] - 1).to(torch.int32).contiguous()
+    res = {}
+    for n_new in (1, 20):
+        ts = []
+        for _ in range(3):
+            xi = x.clone()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            if n_new == 1:
+                lm.prefill(xi, cu, pos, len(lens), max(lens), last)
+            else:
+                lm.generate(xi, cu, pos, len(lens), max(lens), last, max_new_tokens=n_new, eos_ids=())
+            b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        res[n_new] = sorted(ts)[1]
+    step_ms = (res[20] - res[1]) / 19
+    n_layers = len(w.layers)
+    wbytes = n_layers * (4 * w.hidden * w.hidden + 3 * w.ffn * w.hidden) * 2 + w.vocab * w.hidden * 2
+    kvbytes = n_layers * sum(lens) * 2 * w.hidden * 2
+    gbs = (wbytes + kvbytes) / step_ms / 1e6
+    return {"ms_per_token_step": step_ms, "sequences": len(lens), "weight_bytes": wbytes, "kv_bytes": kvbytes, "achieved": gbs, "peak": peak_hbm,
+            "unit": "GB/s", "frac": gbs / peak_hbm, "bound": "hbm",
+            "note": "round 1: 3.86 ms (39 %); the chain of ~200 dependent kernels per token is latency-, not bandwidth-limited (DESIGN.md, Decode)"}
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clocks / throttle reasons with nvidia-smi during the timed region."""
 
@@ -365,6 +401,8 @@ def run_engine(args):
                          "all_tcgen05_gemms": {"achieved": all_flops / (all_ms / 1000.0) / 1e12 if all_ms > 0 else 0.0, "share_of_step": all_ms / ms, "launches": all_n,
                                                "note": "incl. gemm_tcgen05_kernel<128|256> on the small shapes (pooled encoders of merged instances / zones, discriminator, projections)"}},
         }
+        if args.generate:
+            line["decode"] = decode_roofline(net, seq_lens, peak_hbm)
         if world == 1 and not args.no_parity:
             if mode == "production" and not args.generate:
                 # the <= 1e-3 mode on the same engine, same workload, device-timed (split fp16x2 operands / fp32 activations in every stage whose
