@@ -391,7 +391,10 @@ def run_engine(args):
                        "l2": "weights 8.9 GB >> 126 MB L2 are streamed every step (no explicit flush needed)",
                        "precision": ("fp16 GEMM operands (reference: fp16 autocast, TR:385), fp32 accumulate / residual / norm statistics" if not parts else
                                      "split fp16x2 tensor-core operands (A_hi W + A_lo W), fp32 activations / attention in: " + "+".join(parts))},
-            "e2e": {"value": e2e, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(E * 32064 * 4), "logits_finite": finite},
+            "e2e": {"value": e2e, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(E * 32064 * 4), "logits_finite": finite,
+                    "episode_steps": [args.warmup + args.steps, n_total - 1],
+                    "note": "timed on the episode steps AFTER those of `value` (the rollout continues: the 3D memory and the prompts are longer), "
+                            "so e2e < value also measures that growth, not only the copies"},
             "gpu_launches": int(launches),
             "stages": stages,  # one extra profiled step: per-stage algorithmic FLOPs or bytes / CUDA-event time vs the measured peaks
             "clocks": sampler.summary(),

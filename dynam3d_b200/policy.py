@@ -393,6 +393,27 @@ class Dynam3D_VLN(nn.Module):
     def build_prompt(n_image_tokens, instruction, history):
         return build_prompt(n_image_tokens, instruction, history)
 
+    def _to_device(self, t):
+        """Host observations -> device.  Pinned host tensors are copied on a dedicated copy stream (the compute stream waits on an event):
+        the caller is a step ahead of the GPU (the previous step's prefill is still queued), so the PCIe transfer of this step's 12 RGB-D views
+        runs under those kernels instead of behind them on the compute stream (end-to-end bench: the gap to the device-resident number)."""
+        if not torch.is_tensor(t):
+            t = torch.as_tensor(np.asarray(t))
+        if t.is_cuda:
+            return t
+        if not t.is_pinned():
+            return t.to(self.device)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        cur = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self._copy_stream):
+            d = t.to(self.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        cur.wait_event(ev)
+        d.record_stream(cur)
+        return d
+
     def encode_step(self, observations, agent_positions, agent_heading_angles, depth_scale=(0.0, 10.0), delete_old_features=True, num_of_views=1,
                     lm_head_ids=None):
         """Stages a1-a14 (POL:336-363, 432-435): returns per-episode projected tokens (patch, instance, zone), all fp32 [*, 3072].
@@ -402,11 +423,10 @@ class Dynam3D_VLN(nn.Module):
         B, V = ff.batch_size, num_of_views
         P = ff.args.input_height * ff.args.input_width
         dev = self.device
-        depth = observations["depth"]
-        depth = depth.to(dev, dtype=torch.float32, non_blocking=True)
+        depth = self._to_device(observations["depth"]).to(torch.float32)
         n_img, H, W = depth.shape[0], depth.shape[1], depth.shape[2]
         depth = depth.reshape(n_img, H, W).contiguous()
-        rgb = observations["rgb"].to(dev, non_blocking=True).contiguous()
+        rgb = self._to_device(observations["rgb"]).contiguous()
         d576 = ops.depth_patch_grid(depth, B, V, ff.args.input_height, ff.args.input_width, literal_q1=not self.q1_fix)  # POL:336-341
         # Order of issue (results are those of POL:343-354 in the reference's order: nothing below depends on what it is moved across):
         # the cull kernel and the unprojection go to the GPU FIRST, the ViT is queued behind them, and the host halves of the cull
