@@ -1049,6 +1049,7 @@ extern "C" int d3d_lm_decode_step(const d3d_lm_model* m, void* const* qkv_layers
   };
   int* counter = stream_counter(st);
   D3D_REQUIRE(counter != nullptr, "arrival counter allocation");
+  D3D_CHECK_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));  // a step that died half-way must not poison the next one
   D3D_CHECK_CUDA(rmsnorm(m->layers[0].rms1));  // every later norm rides on the GEMM that completes the residual row
   for (int l = 0; l < m->n_layers; ++l) {
     const d3d_lm_layer& L = m->layers[l];
