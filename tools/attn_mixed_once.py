@@ -1,5 +1,7 @@
 """Time the pooling passes' attention dispatch on the step-level shape (1536 sequences of ~37 tokens + a few long ones)."""
+import sys
 import numpy as np, torch
+sys.path.insert(0, ".")
 from dynam3d_b200 import ops
 rng = np.random.default_rng(0)
 lens = list(rng.integers(8, 64, 1500)) + [100, 130, 77, 90] * 9
