@@ -224,8 +224,10 @@ int d3d_decode_attention_rope(void* qkv, int64_t ld, const int* cu_seqlens, int 
 int d3d_lm_decode_step(const d3d_lm_model* m_h, void* const* qkv_layers_h, int64_t ld_qkv, const int* cu_seqlens, int n_seq, int t_prefill,
                        int step, const int* tokens_in, const float* inv_freq, float* x32, void* a16, void* att16, void* h16, float* rope_tab,
                        int* pos, float* logits, int* next_tokens, void* stream);
-/* 1 (default): the kernels of a decode step are chained with programmatic dependent launch (weights of kernel i+1 stream while kernel i
- * runs); 0: plain stream order.  For A/B measurements. */
+/* Switches of the decode step, for A/B measurements (default 1).  bit 0: the kernels of a step are chained with programmatic dependent
+ * launch (weights of kernel i+1 stream while kernel i runs); bit 1: the register-staged CUDA-core decode attention + separate RoPE kernel
+ * instead of the staged tensor-core one; bit 2: no L2 prefetch of the next kernel's weights; bits 3, 4: TIMING EXPERIMENTS ONLY (results are
+ * wrong): every weight tile / key block is read from the same rows, i.e. the step without its HBM traffic. */
 int d3d_lm_decode_set_pdl(int on);
 
 /* dst[r, :D] = src[idx[r], :D] for n 16-bit rows (last-token rows of the final Phi-3 layer). */

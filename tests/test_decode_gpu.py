@@ -143,6 +143,31 @@ def test_decode_matches_cache_free_oracle(cfg):
             assert want[s, b, toks[b][s]] >= want[s, b].max() - 2 * tol, (s, b)
 
 
+def test_decode_launch_modes_agree():
+    """Programmatic dependent launch on / off and the two decode-attention kernels: same tokens; the PDL switch alone is bit-identical
+    (it only changes WHEN kernels start), the attention kernels differ by 16-bit rounding of P."""
+    from dynam3d_b200 import synth, _lib as L
+    from dynam3d_b200.phi3 import LMEngine, LMWeights
+    lens = [70, 33, 5]
+    sd = synth.lm_state_dict(11, 768, 3, 1536, 2048, round_to=torch.float16)
+    emb = synth.hash_uniform((sum(lens), 768), 78, 1.0).cuda()
+    eng = LMEngine(LMWeights.from_state_dict(sd, dtype=torch.float16), n_heads=8, max_tokens=sum(lens))
+    cu = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int32, device="cuda")
+    pos = torch.cat([torch.arange(n, dtype=torch.int32) for n in lens]).cuda()
+    last = (cu[1:] - 1).to(torch.int32).contiguous()
+    res = {}
+    try:
+        for mode in (1, 0, 3):
+            L.check(L.lib().d3d_lm_decode_set_pdl(mode))
+            steps = []
+            _, toks = eng.generate(emb.clone(), cu, pos, len(lens), max(lens), last, max_new_tokens=6, eos_ids=(), step_logits=steps)
+            res[mode] = (toks, torch.stack(steps).cpu())
+    finally:
+        L.check(L.lib().d3d_lm_decode_set_pdl(1))
+    assert res[0][0] == res[1][0] and torch.equal(res[0][1], res[1][1])
+    assert (res[3][1][0] - res[1][1][0]).abs().max().item() < 5e-3  # first decode step (later ones depend on the tokens chosen)
+
+
 def test_generate_stops_at_eos():
     from dynam3d_b200 import synth
     from dynam3d_b200.phi3 import LMEngine, LMWeights
