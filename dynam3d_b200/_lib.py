@@ -132,6 +132,7 @@ SIGNATURES = {
     "d3d_vit_forward": [_P, _P, _I, _I, _I, _I, _I, _P, _P],
     "d3d_phi3_prefill": [_P, _P, _I, _P, _P, _I, _I, _P, _P, _P, _L, _P, _I, _P, _P],
     "d3d_scatter_rows16": [_P, _L, _P, _L, _P, _I, _I, _P],
+    "d3d_attention_split_tc": [_P, _L, _L, _L, _P, _L, _P, _I, _I, _I, _I, _I, _F, _P],
     "d3d_attention_tc_set_halves": [_I, _I],
     "d3d_attention_tc_ex": [_P, _L, _L, _P, _L, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     "d3d_phi3_prefill_chunk": [_P, _P, _I, _I, _I, _P, _P, _L, _L, _P, _P, _P, _P, _I, _P, _P],

@@ -25,10 +25,16 @@ constexpr int ATOM32 = 128 * 32 * 2;                     // [128 rows x 32 colum
 //           D = 96 (where HV = 2 fits only one).  Measured (tools/attn_halves.py): Phi-3 prefill shape 0.113 -> 0.088 ms (default there);
 //           ViT shape 0.353 vs 0.357 ms -- a third resident CTA buys nothing, the per-tile hand-offs double (default stays HV = 2).
 // D = 96 (Phi-3): every tile is a 64-column atom followed by a 32-column atom.
-template <int D, int HV>
+// SPLIT = 1 (the <= 1e-3 "precise" mode): every operand is a pair of fp16 matrices (hi | lo, x ~ hi + lo to ~2^-22), so that
+//   S = Qh Kh^T + Ql Kh^T + Qh Kl^T   and   O += Ph Vh + Pl Vh + Ph Vl
+// accumulate in fp32 in the SAME TMEM columns: three MMA groups instead of one, twice the operand tiles in shared memory, P written as
+// (hi, lo) by the softmax warps, fp32 output.  HV = 1 only.  Replaces the mma.sync kernel of attention_split.cu for sequences >= 256.
+template <int D, int HV, int SPLIT = 0>
 struct AC {
   static_assert(D == 64 || D == 96, "head_dim 64 or 96");
   static_assert(HV == 1 || HV == 2, "key halves");
+  static_assert(SPLIT == 0 || HV == 1, "split operands: 64-key tiles");
+  static constexpr int NP = SPLIT ? 2 : 1;               // operand parts (hi, lo)
   static constexpr bool HAS32 = D == 96;
   static constexpr int BKV = 64 * HV;
   static constexpr int NSOFT = 4 * HV;
@@ -37,11 +43,11 @@ struct AC {
   static constexpr int KV_ATOM64 = BKV * 64 * 2;         // [BKV rows x 64 columns]
   static constexpr int KV_ATOM32 = BKV * 32 * 2;
   static constexpr int KV_BYTES = KV_ATOM64 + (HAS32 ? KV_ATOM32 : 0);
-  static constexpr int SMEM_Q = 0;
-  static constexpr int SMEM_K = Q_BYTES;                 // 2 stages
-  static constexpr int SMEM_V = SMEM_K + 2 * KV_BYTES;   // 2 stages
-  static constexpr int SMEM_P = SMEM_V + 2 * KV_BYTES;   // [128 x BKV] = HV atoms of [128 x 64]
-  static constexpr int SMEM_BAR = SMEM_P + HV * ATOM64;
+  static constexpr int SMEM_Q = 0;                       // NP parts
+  static constexpr int SMEM_K = NP * Q_BYTES;            // 2 stages x NP parts
+  static constexpr int SMEM_V = SMEM_K + 2 * NP * KV_BYTES;
+  static constexpr int SMEM_P = SMEM_V + 2 * NP * KV_BYTES;  // [128 x BKV] = HV atoms of [128 x 64], x NP parts
+  static constexpr int SMEM_BAR = SMEM_P + NP * HV * ATOM64;
   static constexpr int SMEM_BYTES = SMEM_BAR + 640;
   static constexpr int TMEM_O = 64 * HV;                 // S: [0, 64 HV)   O of key half h: [64 HV + h D, 64 HV + (h + 1) D)
   static constexpr int TMEM_NEED = 64 * HV + HV * D;
@@ -50,6 +56,7 @@ struct AC {
 };
 static_assert(AC<64, 2>::CTAS_PER_SM == 2 && AC<64, 1>::CTAS_PER_SM == 3, "CTAs per SM at head_dim 64");
 static_assert(AC<96, 2>::CTAS_PER_SM == 1 && AC<96, 1>::CTAS_PER_SM == 2, "CTAs per SM at head_dim 96");
+static_assert(AC<96, 1, 1>::CTAS_PER_SM == 1 && AC<64, 1, 1>::CTAS_PER_SM == 1, "split operands: one CTA per SM");
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -187,14 +194,14 @@ __device__ __forceinline__ uint32_t make_idesc(int kind, int m, int n, int b_mn_
 
 // KIND (D3D_F16 / D3D_BF16) is a template parameter: as a run-time argument every P / output pack was emitted for both types and predicated
 // (ncu, round 2: F2FP = 8 % of the issued instructions, half of them predicated off)
-template <int D, int KIND, int HV>
-__global__ void __launch_bounds__((AC<D, HV>::NTHREADS), (AC<D, HV>::CTAS_PER_SM))
+template <int D, int KIND, int HV, int SPLIT>
+__global__ void __launch_bounds__((AC<D, HV, SPLIT>::NTHREADS), (AC<D, HV, SPLIT>::CTAS_PER_SM))
 attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_qkv32, const __grid_constant__ CUtensorMap tm_kv,
                const __grid_constant__ CUtensorMap tm_kv32, uint16_t* __restrict__ out, long long ldo, const int* __restrict__ cu,
-               const int* __restrict__ lens, int q_tile_begin, int H, int causal, float scale_log2) {
+               const int* __restrict__ lens, int q_tile_begin, int H, int causal, float scale_log2, int lo_off, float* __restrict__ out32) {
   constexpr int kind = KIND;
-  using C = AC<D, HV>;
-  constexpr int BKV = C::BKV, NSOFT = C::NSOFT;
+  using C = AC<D, HV, SPLIT>;
+  constexpr int BKV = C::BKV, NSOFT = C::NSOFT, NP = C::NP;
   constexpr int TILE_BYTES = C::KV_BYTES, Q_BYTES = C::Q_BYTES, KV_ATOM64 = C::KV_ATOM64;
   constexpr int SMEM_Q = C::SMEM_Q, SMEM_K = C::SMEM_K, SMEM_V = C::SMEM_V, SMEM_P = C::SMEM_P, SMEM_BAR = C::SMEM_BAR;
   constexpr int TMEM_COLS = C::TMEM_COLS;
@@ -242,18 +249,26 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      mbar_expect_tx(bar(0), Q_BYTES);
-      tma_load_2d(sbase + SMEM_Q, &tm_qkv, bar(0), h * D, b + q0);
-      if (C::HAS32) tma_load_2d(sbase + SMEM_Q + ATOM64, &tm_qkv32, bar(0), h * D + 64, b + q0);
+      // operand part p (0 = hi, 1 = lo of the split mode) lives lo_off columns to the right in the packed matrix
+      mbar_expect_tx(bar(0), NP * Q_BYTES);
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        tma_load_2d(sbase + SMEM_Q + p * Q_BYTES, &tm_qkv, bar(0), p * lo_off + h * D, b + q0);
+        if (C::HAS32) tma_load_2d(sbase + SMEM_Q + p * Q_BYTES + ATOM64, &tm_qkv32, bar(0), p * lo_off + h * D + 64, b + q0);
+      }
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j & 1;
         mbar_wait(bar(3 + st), (((uint32_t)j >> 1) & 1u) ^ 1u);
-        mbar_expect_tx(bar(1 + st), 2 * TILE_BYTES);
-        tma_load_2d(sbase + SMEM_K + st * TILE_BYTES, &tm_kv, bar(1 + st), (H + h) * D, b + j * BKV);
-        tma_load_2d(sbase + SMEM_V + st * TILE_BYTES, &tm_kv, bar(1 + st), (2 * H + h) * D, b + j * BKV);
-        if (C::HAS32) {
-          tma_load_2d(sbase + SMEM_K + st * TILE_BYTES + KV_ATOM64, &tm_kv32, bar(1 + st), (H + h) * D + 64, b + j * BKV);
-          tma_load_2d(sbase + SMEM_V + st * TILE_BYTES + KV_ATOM64, &tm_kv32, bar(1 + st), (2 * H + h) * D + 64, b + j * BKV);
+        mbar_expect_tx(bar(1 + st), 2 * NP * TILE_BYTES);
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+          const uint32_t ko = sbase + SMEM_K + (st * NP + p) * TILE_BYTES, vo = sbase + SMEM_V + (st * NP + p) * TILE_BYTES;
+          tma_load_2d(ko, &tm_kv, bar(1 + st), p * lo_off + (H + h) * D, b + j * BKV);
+          tma_load_2d(vo, &tm_kv, bar(1 + st), p * lo_off + (2 * H + h) * D, b + j * BKV);
+          if (C::HAS32) {
+            tma_load_2d(ko + KV_ATOM64, &tm_kv32, bar(1 + st), p * lo_off + (H + h) * D + 64, b + j * BKV);
+            tma_load_2d(vo + KV_ATOM64, &tm_kv32, bar(1 + st), p * lo_off + (2 * H + h) * D + 64, b + j * BKV);
+          }
         }
       }
     }
@@ -266,19 +281,25 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant
       const uint32_t idesc_s = make_idesc(kind, BQ, BKV, 0);  // N = 64 or 128 keys
       const uint32_t idesc_o = make_idesc(kind, BQ, 64, 1);
       const uint32_t idesc_o32 = make_idesc(kind, BQ, 32, 1);
-      const uint64_t dq = desc_kmajor(sbase + SMEM_Q);
-      const uint64_t dq32 = desc_kmajor_sw64(sbase + SMEM_Q + ATOM64);
+      // operand-part pairs (A part, B part): plain mode (hi, hi); split mode (hi, hi), (lo, hi), (hi, lo) -- for S the parts of (Q, K),
+      // for O the parts of (P, V); all pairs accumulate into the same TMEM columns
+      constexpr int NPAIR = SPLIT ? 3 : 1;
+      constexpr int PA[3] = {0, 1, 0}, PB[3] = {0, 0, 1};
       auto issue_s = [&](int j) {
         const int st = j & 1;
         mbar_wait(bar(1 + st), ((uint32_t)j >> 1) & 1u);  // K_j, V_j landed
         tc_fence_after();
-        const uint64_t dk = desc_kmajor(sbase + SMEM_K + st * TILE_BYTES);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16(tmem_s, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, k ? 1u : 0u);
-        if (C::HAS32) {  // head dims 64..95: the 32-column atom (two more K-steps)
-          const uint64_t dk32 = desc_kmajor_sw64(sbase + SMEM_K + st * TILE_BYTES + KV_ATOM64);
+        for (int pr = 0; pr < NPAIR; ++pr) {
+          const uint32_t qs = sbase + SMEM_Q + PA[pr] * Q_BYTES, ks = sbase + SMEM_K + (st * NP + PB[pr]) * TILE_BYTES;
+          const uint64_t dq = desc_kmajor(qs), dk = desc_kmajor(ks);
 #pragma unroll
-          for (int k = 0; k < 2; ++k) umma_f16(tmem_s, dq32 + (uint64_t)(2 * k), dk32 + (uint64_t)(2 * k), idesc_s, 1u);
+          for (int k = 0; k < 4; ++k) umma_f16(tmem_s, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, (pr | k) ? 1u : 0u);
+          if (C::HAS32) {  // head dims 64..95: the 32-column atom (two more K-steps)
+            const uint64_t dq32 = desc_kmajor_sw64(qs + ATOM64), dk32 = desc_kmajor_sw64(ks + KV_ATOM64);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) umma_f16(tmem_s, dq32 + (uint64_t)(2 * k), dk32 + (uint64_t)(2 * k), idesc_s, 1u);
+          }
         }
         umma_commit(bar(5));
       };
@@ -296,18 +317,23 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant
         mbar_wait(bar(7), (uint32_t)j & 1u);  // P_j is in shared memory and O has been rescaled where the running max moved
         STAMP(mst_on && j < 8, 64 + j * 8 + 2);
         tc_fence_after();
-        const uint64_t dp = desc_kmajor(sbase + SMEM_P);
-        const uint64_t dv = desc_mnmajor(sbase + SMEM_V + st * TILE_BYTES);
-        const uint64_t dv32 = desc_mnmajor_sw64(sbase + SMEM_V + st * TILE_BYTES + KV_ATOM64);
 #pragma unroll
-        for (int k = 0; k < BKV / 16; ++k) {
-          // A = P: 16 keys = 32 B inside a 64-key atom (+2), next atom +16 KB; B = V: 16 key rows = 2048 B (+128).
-          // O accumulates in TMEM over all key tiles (the tensor pipe executes the products in issue order).
-          const uint64_t a = dp + (uint64_t)((k & 3) * 2 + (k >> 2) * (ATOM64 >> 4));
-          // keys 0..63 of the tile (k < 4) accumulate into O half 0, keys 64..127 into O half 1 (independent softmax bases)
-          umma_f16(tmem_o + (uint32_t)((k >> 2) * D), a, dv + (uint64_t)(k * 128), idesc_o, (j | (k & 3)) ? 1u : 0u);
-          // channels 64..95: 16 key rows of the 32-column atom = 1024 B (+64)
-          if (C::HAS32) umma_f16(tmem_o + (uint32_t)((k >> 2) * D + 64), a, dv32 + (uint64_t)(k * 64), idesc_o32, (j | (k & 3)) ? 1u : 0u);
+        for (int pr = 0; pr < NPAIR; ++pr) {
+          const uint32_t vs = sbase + SMEM_V + (st * NP + PB[pr]) * TILE_BYTES;
+          const uint64_t dp = desc_kmajor(sbase + SMEM_P + PA[pr] * HV * ATOM64);
+          const uint64_t dv = desc_mnmajor(vs);
+          const uint64_t dv32 = desc_mnmajor_sw64(vs + KV_ATOM64);
+#pragma unroll
+          for (int k = 0; k < BKV / 16; ++k) {
+            // A = P: 16 keys = 32 B inside a 64-key atom (+2), next atom +16 KB; B = V: 16 key rows = 2048 B (+128).
+            // O accumulates in TMEM over all key tiles (the tensor pipe executes the products in issue order).
+            const uint64_t a = dp + (uint64_t)((k & 3) * 2 + (k >> 2) * (ATOM64 >> 4));
+            const uint32_t acc = (j | pr | (k & 3)) ? 1u : 0u;
+            // keys 0..63 of the tile (k < 4) accumulate into O half 0, keys 64..127 into O half 1 (independent softmax bases)
+            umma_f16(tmem_o + (uint32_t)((k >> 2) * D), a, dv + (uint64_t)(k * 128), idesc_o, acc);
+            // channels 64..95: 16 key rows of the 32-column atom = 1024 B (+64)
+            if (C::HAS32) umma_f16(tmem_o + (uint32_t)((k >> 2) * D + 64), a, dv32 + (uint64_t)(k * 64), idesc_o32, acc);
+          }
         }
         umma_commit(bar(3 + st));  // K_j / V_j stage free
         umma_commit(bar(8));       // O += P_j V_j done: P buffer free, O readable
@@ -384,10 +410,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant
       const float nbase = (m == -INFINITY) ? 0.f : -m;
       // P = 2^(S*scale - m) -> 16 bit (in place over the score registers); partial row sum
       float rs0 = 0.f, rs1 = 0.f;
+      uint32_t plo[SPLIT ? 32 : 1];
 #pragma unroll
       for (int i = 0; i < 64; i += 2) {
         if (EDGE && i >= nvv) {  // both keys masked: no exponentials
           v[i >> 1] = 0u;
+          if constexpr (SPLIT != 0) plo[i >> 1] = 0u;
           continue;
         }
         float t0, t1;
@@ -395,7 +423,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant
         float p0 = ex2_approx(t0), p1 = ex2_approx(t1);
         if (EDGE) p1 = (i + 1 < nvv) ? p1 : 0.f;
         fadd2(rs0, rs1, rs0, rs1, p0, p1);
-        v[i >> 1] = pack16x2(p0, p1, kind);
+        const uint32_t hi = pack16x2(p0, p1, kind);
+        v[i >> 1] = hi;
+        if constexpr (SPLIT != 0) {  // P = hi + lo: the residual of the 16-bit rounding, itself rounded to 16 bit
+          const float2 hf2 = unpack16x2(hi, kind);
+          plo[i >> 1] = pack16x2(p0 - hf2.x, p1 - hf2.y, kind);
+        }
       }
       l += rs0 + rs1;
       STAMP(st_on && j < 8, j * 8 + 4);
@@ -411,6 +444,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[4 * q]), "r"(v[4 * q + 1]), "r"(v[4 * q + 2]),
                      "r"(v[4 * q + 3])
                      : "memory");
+        if constexpr (SPLIT != 0)  // the lo part: the next [128 x 64] atom
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr + (uint32_t)(HV * ATOM64)), "r"(plo[4 * q]), "r"(plo[4 * q + 1]),
+                       "r"(plo[4 * q + 2]), "r"(plo[4 * q + 3])
+                       : "memory");
       }
     };
     for (int j = 0; j < n_tiles; ++j) {
@@ -458,7 +495,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           auto f = [&](int k) { return HV == 2 ? __uint_as_float(o[8 * i + k]) * w1 + __uint_as_float(o2[8 * i + k]) * w2 : __uint_as_float(o[8 * i + k]) * w1; };
-          dst[c / 8 + i] = make_uint4(pack16x2(f(0), f(1), kind), pack16x2(f(2), f(3), kind), pack16x2(f(4), f(5), kind), pack16x2(f(6), f(7), kind));
+          if constexpr (SPLIT != 0) {  // fp32 rows
+            float4* d32 = reinterpret_cast<float4*>(out32 + (size_t)(b + row) * ldo + (size_t)h * D + hf * DH + c + 8 * i);
+            d32[0] = make_float4(f(0), f(1), f(2), f(3));
+            d32[1] = make_float4(f(4), f(5), f(6), f(7));
+          } else {
+            dst[c / 8 + i] = make_uint4(pack16x2(f(0), f(1), kind), pack16x2(f(2), f(3), kind), pack16x2(f(4), f(5), kind), pack16x2(f(6), f(7), kind));
+          }
         }
       }
     }
@@ -484,27 +527,63 @@ extern "C" int d3d_debug_attn_stamps(long long* host_out) {
 namespace {
 int g_attn_tc_halves[2] = {2, 1};  // key halves per tile for head_dim 64 / 96 (d3d_attention_tc_set_halves): measured, tools/attn_halves.py
 
-template <int D, int HV>
+template <int D, int HV, int SPLIT>
 int launch_attn_tc(const CUtensorMap& tm, const CUtensorMap& tm32, const CUtensorMap& tmkv, const CUtensorMap& tmkv32, void* out, int64_t ldo,
                    const int* cu_seqlens, const int* lens, int n_seq, int max_len, int q_tile_begin, int q_tile_end, int H, int causal, int kind,
-                   float scale, cudaStream_t st) {
-  using C = AC<D, HV>;
+                   float scale, int lo_off, cudaStream_t st) {
+  using C = AC<D, HV, SPLIT>;
   static bool attr_set = false;
   if (!attr_set) {
-    D3D_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<D, D3D_F16, HV>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    D3D_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<D, D3D_BF16, HV>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    D3D_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<D, D3D_F16, HV, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    D3D_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<D, D3D_BF16, HV, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
   const int q_end = q_tile_end < d3d_cdiv(max_len, BQ) ? q_tile_end : d3d_cdiv(max_len, BQ);
   if (q_end <= q_tile_begin) return 0;
   dim3 grid(q_end - q_tile_begin, H, n_seq);
+  uint16_t* o16 = SPLIT ? nullptr : (uint16_t*)out;
+  float* o32 = SPLIT ? (float*)out : nullptr;
   if (kind == D3D_BF16)
-    attn_tc_kernel<D, D3D_BF16, HV><<<grid, C::NTHREADS, C::SMEM_BYTES, st>>>(tm, tm32, tmkv, tmkv32, (uint16_t*)out, ldo, cu_seqlens, lens, q_tile_begin, H,
-                                                                             causal, scale * 1.4426950408889634f);
+    attn_tc_kernel<D, D3D_BF16, HV, SPLIT><<<grid, C::NTHREADS, C::SMEM_BYTES, st>>>(tm, tm32, tmkv, tmkv32, o16, ldo, cu_seqlens, lens, q_tile_begin, H, causal,
+                                                                                    scale * 1.4426950408889634f, lo_off, o32);
   else
-    attn_tc_kernel<D, D3D_F16, HV><<<grid, C::NTHREADS, C::SMEM_BYTES, st>>>(tm, tm32, tmkv, tmkv32, (uint16_t*)out, ldo, cu_seqlens, lens, q_tile_begin, H,
-                                                                            causal, scale * 1.4426950408889634f);
+    attn_tc_kernel<D, D3D_F16, HV, SPLIT><<<grid, C::NTHREADS, C::SMEM_BYTES, st>>>(tm, tm32, tmkv, tmkv32, o16, ldo, cu_seqlens, lens, q_tile_begin, H, causal,
+                                                                                   scale * 1.4426950408889634f, lo_off, o32);
   D3D_CHECK_LAUNCH();
+  return 0;
+}
+
+// tensor maps over a packed [n_rows, n_cols] 16-bit matrix: query tiles 128 rows, key / value tiles kv_rows rows; each as a 64-column
+// (SWIZZLE_128B) and a 32-column (SWIZZLE_64B; head_dim 96) atom
+int attn_tc_maps(const void* base, int64_t ld, int64_t n_rows, int64_t n_cols, int kind, int kv_rows, CUtensorMap* tm, CUtensorMap* tm32, CUtensorMap* tmkv,
+                 CUtensorMap* tmkv32) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess) {
+      d3d_set_error("cuTensorMapEncodeTiled entry point not available");
+      return D3D_ECUDA;
+    }
+    fn = (EncodeTiledFn)p;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)n_cols, (cuuint64_t)n_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapDataType dt = kind == D3D_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  auto encode = [&](CUtensorMap* m, cuuint32_t cols, cuuint32_t rows) {
+    cuuint32_t box[2] = {cols, rows};
+    return fn(m, dt, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  };
+  CUresult r = encode(tm, 64, 128);
+  if (r == CUDA_SUCCESS) r = encode(tm32, 32, 128);  // unused at head_dim 64, but the kernel signature is shared
+  if (r == CUDA_SUCCESS) r = encode(tmkv, 64, (cuuint32_t)kv_rows);
+  if (r == CUDA_SUCCESS) r = encode(tmkv32, 32, (cuuint32_t)kv_rows);
+  if (r != CUDA_SUCCESS) {
+    d3d_set_error("cuTensorMapEncodeTiled(qkv) failed (%d)", (int)r);
+    return D3D_ECUDA;
+  }
   return 0;
 }
 }  // namespace
@@ -532,39 +611,12 @@ extern "C" int d3d_attention_tc_ex(const void* qkv, int64_t ld, int64_t n_rows, 
   D3D_REQUIRE(Dh == 64 || Dh == 96, "tcgen05 attention is built for head_dim 64 and 96");
   D3D_REQUIRE(ld % 8 == 0 && ldo % 8 == 0 && ((uintptr_t)qkv % 16) == 0 && ((uintptr_t)out % 16) == 0, "16-byte aligned rows");
   D3D_REQUIRE(n_seq <= 65535 && H <= 65535, "grid limits");
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess) {
-      d3d_set_error("cuTensorMapEncodeTiled entry point not available");
-      return D3D_ECUDA;
-    }
-    fn = (EncodeTiledFn)p;
-  }
   const int hv = g_attn_tc_halves[Dh == 96 ? 1 : 0];
   CUtensorMap tm, tm32, tmkv, tmkv32;
-  cuuint64_t dims[2] = {(cuuint64_t)(3 * H * Dh), (cuuint64_t)n_rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t estr[2] = {1, 1};
-  const CUtensorMapDataType dt = kind == D3D_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-  // query tiles: 128 rows; key / value tiles: 64 * halves rows; each as a 64-column (SWIZZLE_128B) and, for head_dim 96, a 32-column atom
-  auto encode = [&](CUtensorMap* m, cuuint32_t cols, cuuint32_t rows) {
-    cuuint32_t box[2] = {cols, rows};
-    return fn(m, dt, 2, (void*)qkv, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-              cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  };
-  CUresult r = encode(&tm, 64, 128);
-  if (r == CUDA_SUCCESS) r = encode(&tm32, 32, 128);  // unused at head_dim 64, but the kernel signature is shared
-  if (r == CUDA_SUCCESS) r = encode(&tmkv, 64, 64 * hv);
-  if (r == CUDA_SUCCESS) r = encode(&tmkv32, 32, 64 * hv);
-  if (r != CUDA_SUCCESS) {
-    d3d_set_error("cuTensorMapEncodeTiled(qkv) failed (%d)", (int)r);
-    return D3D_ECUDA;
-  }
+  D3D_TRY(attn_tc_maps(qkv, ld, n_rows, 3LL * H * Dh, kind, 64 * hv, &tm, &tm32, &tmkv, &tmkv32));
   cudaStream_t st = (cudaStream_t)stream;
 #define ATT_GO(DV, HVV) \
-  return launch_attn_tc<DV, HVV>(tm, tm32, tmkv, tmkv32, out, ldo, cu_seqlens, seq_len, n_seq, max_len, q_tile_begin, q_tile_end, H, causal, kind, scale, st)
+  return launch_attn_tc<DV, HVV, 0>(tm, tm32, tmkv, tmkv32, out, ldo, cu_seqlens, seq_len, n_seq, max_len, q_tile_begin, q_tile_end, H, causal, kind, scale, 0, st)
   if (Dh == 96) {
     if (hv == 1) ATT_GO(96, 1);
     ATT_GO(96, 2);
@@ -572,4 +624,24 @@ extern "C" int d3d_attention_tc_ex(const void* qkv, int64_t ld, int64_t n_rows, 
   if (hv == 1) ATT_GO(64, 1);
   ATT_GO(64, 2);
 #undef ATT_GO
+}
+
+// The <= 1e-3 "precise" mode on the tensor cores (tcgen05): qkv_hl = [T, lo_off + 3 H Dh] fp16, the hi parts of [q | k | v] in columns
+// [0, 3 H Dh) and the lo parts lo_off columns to the right (d3d_split16 with 2 terms); out = fp32 [T, H Dh].  Same contract as
+// d3d_attention_split (the mma.sync kernel, which stays for sequences < 256 tokens).
+extern "C" int d3d_attention_split_tc(const void* qkv_hl, int64_t ld, int64_t n_rows, int64_t lo_off, float* out, int64_t ldo, const int* cu_seqlens,
+                                      int n_seq, int max_len, int H, int Dh, int causal, float scale, void* stream) {
+  if (n_seq == 0 || max_len == 0) return 0;
+  D3D_REQUIRE(qkv_hl && out && cu_seqlens, "args");
+  D3D_REQUIRE(Dh == 64 || Dh == 96, "tcgen05 attention is built for head_dim 64 and 96");
+  D3D_REQUIRE(ld % 8 == 0 && ldo % 4 == 0 && lo_off % 8 == 0 && lo_off >= 3LL * H * Dh && ld >= lo_off + 3LL * H * Dh &&
+                  ((uintptr_t)qkv_hl % 16) == 0 && ((uintptr_t)out % 16) == 0,
+              "16-byte aligned rows, lo part behind the hi part");
+  D3D_REQUIRE(n_seq <= 65535 && H <= 65535, "grid limits");
+  CUtensorMap tm, tm32, tmkv, tmkv32;
+  D3D_TRY(attn_tc_maps(qkv_hl, ld, n_rows, lo_off + 3LL * H * Dh, D3D_F16, 64, &tm, &tm32, &tmkv, &tmkv32));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (Dh == 96)
+    return launch_attn_tc<96, 1, 1>(tm, tm32, tmkv, tmkv32, out, ldo, cu_seqlens, nullptr, n_seq, max_len, 0, 1 << 30, H, causal, D3D_F16, scale, (int)lo_off, st);
+  return launch_attn_tc<64, 1, 1>(tm, tm32, tmkv, tmkv32, out, ldo, cu_seqlens, nullptr, n_seq, max_len, 0, 1 << 30, H, causal, D3D_F16, scale, (int)lo_off, st);
 }

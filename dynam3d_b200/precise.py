@@ -48,6 +48,7 @@ def linear(x32, w, bias=None, act=L.ACT_NONE, residual=None, out=None, w_prepare
     return ops.gemm(a, wx, out=out, bias=bias, act=act, residual=residual)
 
 
+SPLIT_TC = True  # split attention of sequences >= 256 tokens (head_dim 64 / 96) on tcgen05 (csrc/attention_tc.cu, SPLIT); False = the mma.sync kernel
 SPLIT_ATTENTION = True  # sequences of >= 64 tokens on the tensor cores with split fp16x2 operands (csrc/attention_split.cu); False = fp32 CUDA cores
 
 
@@ -60,8 +61,12 @@ def attention(qkv32, cu, n_seq, max_len, H, Dh, causal):
         if split:  # split the layer's QKV matrix ONCE into [hi | lo] fp16 halves, then the pipelined tensor-core kernel
             hl = torch.empty((T, 2 * W), device=qkv32.device, dtype=torch.float16)
             L.check(L.lib().d3d_split16(L.ptr(qkv32), qkv32.stride(0), L.ptr(hl), hl.stride(0), T, W, 2, L.stream_ptr()))
-            L.check(L.lib().d3d_attention_split(L.ptr(hl), hl.stride(0), W, L.ptr(out), out.stride(0), L.ptr(cu), n_seq, max_len, H, Dh,
-                                                int(bool(causal)), 1.0 / math.sqrt(Dh), L.stream_ptr()))
+            if SPLIT_TC and Dh in (64, 96) and max_len >= 256:
+                L.check(L.lib().d3d_attention_split_tc(L.ptr(hl), hl.stride(0), T, W, L.ptr(out), out.stride(0), L.ptr(cu), n_seq, max_len, H, Dh,
+                                                       int(bool(causal)), 1.0 / math.sqrt(Dh), L.stream_ptr()))
+            else:
+                L.check(L.lib().d3d_attention_split(L.ptr(hl), hl.stride(0), W, L.ptr(out), out.stride(0), L.ptr(cu), n_seq, max_len, H, Dh,
+                                                    int(bool(causal)), 1.0 / math.sqrt(Dh), L.stream_ptr()))
         else:
             L.check(L.lib().d3d_attention_f32(L.ptr(qkv32), qkv32.stride(0), L.ptr(out), out.stride(0), L.ptr(cu), n_seq, max_len, H, Dh,
                                               int(bool(causal)), 1.0 / math.sqrt(Dh), L.stream_ptr()))

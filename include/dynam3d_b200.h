@@ -358,6 +358,11 @@ int d3d_attention_tc_ex(const void* qkv, int64_t ld, int64_t n_rows, void* out, 
 /* Tile shape of the tcgen05 attention per head dim: key halves per tile = softmax threads per query row.  1: 64-key tiles, one thread per
  * row, more resident CTAs per SM (default at head_dim 96: two CTAs instead of one); 2: 128-key tiles, two threads per row (default at 64). */
 int d3d_attention_tc_set_halves(int halves_d64, int halves_d96);
+/* Split-operand ("precise", <= 1e-3 logits) attention on tcgen05: S = Qh Kh^T + Ql Kh^T + Qh Kl^T, O += Ph Vh + Pl Vh + Ph Vl, fp32
+ * accumulate and output.  qkv_hl: [n_rows, >= lo_off + 3 H Dh] fp16, hi parts in columns [0, 3 H Dh), lo parts lo_off columns to the right
+ * (d3d_split16, 2 terms); out: fp32 [n_rows, H Dh], ldo in floats.  head_dim 64 / 96; sequences of any length (built for >= 256). */
+int d3d_attention_split_tc(const void* qkv_hl, int64_t ld, int64_t n_rows, int64_t lo_off, float* out, int64_t ldo, const int* cu_seqlens, int n_seq,
+                           int max_len, int H, int Dh, int causal, float scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Token builders for the layer-wise pooling (patch -> instance -> zone) and the merge discriminator.

@@ -94,11 +94,13 @@ def test_split_attention_matches_fp64_reference(case):
     g = torch.Generator().manual_seed(3)
     qkv = (torch.randn(T, 3 * H * Dh, generator=g) * 1.5).cuda()
     cu = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int32, device="cuda")
-    PR.SPLIT_ATTENTION = True
-    got = PR.attention(qkv, cu, len(lens), max(lens), H, Dh, causal)
+    PR.SPLIT_ATTENTION, PR.SPLIT_TC = True, True
+    got_tc = PR.attention(qkv, cu, len(lens), max(lens), H, Dh, causal)   # tcgen05, split operands
+    PR.SPLIT_TC = False
+    got = PR.attention(qkv, cu, len(lens), max(lens), H, Dh, causal)      # mma.sync, split operands
     PR.SPLIT_ATTENTION = False
     simt = PR.attention(qkv, cu, len(lens), max(lens), H, Dh, causal)
-    PR.SPLIT_ATTENTION = True
+    PR.SPLIT_ATTENTION, PR.SPLIT_TC = True, True
     q, k, v = qkv.double().split(H * Dh, dim=-1)
     want = torch.empty(T, H * Dh, dtype=torch.float64, device="cuda")
     s = 0
@@ -110,6 +112,7 @@ def test_split_attention_matches_fp64_reference(case):
         want[s:s + n] = (torch.softmax(a, -1) @ vs).transpose(0, 1).reshape(n, H * Dh)
         s += n
     e_split = (got.double() - want).abs().max().item()
+    e_tc = (got_tc.double() - want).abs().max().item()
     e_simt = (simt.double() - want).abs().max().item()
-    print(f"split attention err {e_split:.2e}, fp32 CUDA-core kernel err {e_simt:.2e} (|out| max {want.abs().max().item():.2f})")
-    assert e_split < 2e-5 and e_simt < 2e-5
+    print(f"split attention err: tcgen05 {e_tc:.2e}, mma.sync {e_split:.2e}, fp32 CUDA-core kernel {e_simt:.2e} (|out| max {want.abs().max().item():.2f})")
+    assert e_split < 2e-5 and e_simt < 2e-5 and e_tc < 2e-5
