@@ -133,6 +133,9 @@ SIGNATURES = {
     "d3d_phi3_prefill": [_P, _P, _I, _P, _P, _I, _I, _P, _P, _P, _L, _P, _I, _P, _P],
     "d3d_scatter_rows16": [_P, _L, _P, _L, _P, _I, _I, _P],
     "d3d_attention_split_tc": [_P, _L, _L, _L, _P, _L, _P, _I, _I, _I, _I, _I, _F, _P],
+    "d3d_wp_relu": [_P, _L, _P],
+    "d3d_wp_neighbor_attention": [_P, _P, _I, _I, _I, _I, _F, _P, _P],
+    "d3d_wp_heatmap_nms": [_P, _I, _I, _I, _I, _F, _F, _P, _P, _P],
     "d3d_attention_tc_set_halves": [_I, _I],
     "d3d_attention_tc_ex": [_P, _L, _L, _P, _L, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     "d3d_phi3_prefill_chunk": [_P, _P, _I, _I, _I, _P, _P, _L, _L, _P, _P, _P, _P, _I, _P, _P],

@@ -318,3 +318,38 @@ def nerf_state_dict(seed, width=768, K=4, layers=4):
         "nerf_encoder.params": hash_uniform((n_enc,), s + 9, (3.0 / width) ** 0.5).to(torch.float16).to(torch.float32),
         "nerf_decoder.params": hash_uniform((n_dec,), s + 10, (3.0 / width) ** 0.5).to(torch.float16).to(torch.float32),
     }
+
+
+def waypoint_state_dict(seed, device="cpu"):
+    """State dict of the reference's BinaryDistPredictor_TRM (TRM_net.py: key names and shapes) with seeded uniform weights, fp32.  LayerNorm
+    weights near 1, biases small; scales chosen so that the heat-map logits spread over a few units (a peaked softmax like a trained model)."""
+    H, I = 768, 3072
+    s = seed * 7919
+    sd = {}
+    n = [0]
+
+    def u(shape, std):
+        n[0] += 1
+        return _u(shape, s + n[0], std, device)
+
+    sd["visual_fc_depth.1.weight"], sd["visual_fc_depth.1.bias"] = u((H, 2048), 2048 ** -0.5), u((H,), 0.02)
+    sd["visual_merge.0.weight"], sd["visual_merge.0.bias"] = u((H, 2 * H), (2 * H) ** -0.5), u((H,), 0.02)
+    for l in range(2):
+        p = f"waypoint_TRM.bert.encoder.layer.{l}."
+        for nm in ("query", "key", "value"):
+            sd[p + f"attention.self.{nm}.weight"], sd[p + f"attention.self.{nm}.bias"] = u((H, H), 1.5 * H ** -0.5), u((H,), 0.02)
+        sd[p + "attention.output.dense.weight"], sd[p + "attention.output.dense.bias"] = u((H, H), H ** -0.5), u((H,), 0.02)
+        sd[p + "attention.output.LayerNorm.weight"], sd[p + "attention.output.LayerNorm.bias"] = 1.0 + u((H,), 0.05), u((H,), 0.02)
+        sd[p + "intermediate.dense.weight"], sd[p + "intermediate.dense.bias"] = u((I, H), H ** -0.5), u((I,), 0.02)
+        sd[p + "output.dense.weight"], sd[p + "output.dense.bias"] = u((H, I), I ** -0.5), u((H,), 0.02)
+        sd[p + "output.LayerNorm.weight"], sd[p + "output.LayerNorm.bias"] = 1.0 + u((H,), 0.05), u((H,), 0.02)
+    sd["mergefeats_LayerNorm.weight"], sd["mergefeats_LayerNorm.bias"] = 1.0 + u((H,), 0.05), u((H,), 0.02)
+    sd["vis_classifier.0.weight"], sd["vis_classifier.0.bias"] = u((H, H), 2.0 * H ** -0.5), u((H,), 0.02)
+    sd["vis_classifier.2.weight"], sd["vis_classifier.2.bias"] = u((120, H), 3.0 * H ** -0.5), u((120,), 0.1)
+    return sd
+
+
+def waypoint_depth_embedding(seed, episodes, device="cpu"):
+    """Stand-in for the depth encoder's output (POL:207): [episodes * 12, 128, 4, 4], non-negative like a post-ReLU feature map."""
+    import torch
+    return torch.relu(hash_uniform((episodes * 12, 128, 4, 4), seed * 31 + 5, 1.5, device) + 0.25)

@@ -551,6 +551,21 @@ int d3d_add_half(const float* a32, const void* b16, void* out16, int64_t n, void
 int d3d_volume_render(const float* feat, const float* density, const int* topk, const float* rel_dist, int n_rays, int n_samples,
                       int n_top, int D, float* feature_map, float* depth_map, void* stream);
 
+/* ---- candidate-waypoint predictor: BinaryDistPredictor_TRM (TRM_net.py:9-88) + heat-map NMS (POL:226-247,
+ * waypoint_pred/utils.py:37-66).  The depth-encoder embeddings ([B*12, 128, 4, 4], ENC:15-109) are an INPUT.  Linear layers: d3d_gemm on
+ * split operands (fp32-class accuracy), LayerNorm: d3d_layernorm (eps 1e-12). ---- */
+/* in-place ReLU on n fp32 values */
+int d3d_wp_relu(float* x, int64_t n, void* stream);
+/* BERT self-attention over the n_img <= 12 views of every episode with an additive mask ([n_img, n_img] fp32, 0 / -10000 as
+ * WBERT:184-185 builds it from utils.py:90-102): qkv [n_episodes*n_img, 3*H*Dh] fp32 rows = [q | k | v], out [n_episodes*n_img, H*Dh]. Dh = 64. */
+int d3d_wp_neighbor_attention(const float* qkv, const float* add_mask, int n_episodes, int n_img, int H, int Dh, float scale, float* out, void* stream);
+/* logits [n_episodes, n_angles, n_classes] fp32 (after the HEATMAP_OFFSET roll, TRM:84-86) -> prob (softmax over the whole map; may be NULL)
+ * and nms [n_episodes, n_angles, n_classes]: the map wrapped by one angle row, `max_predictions` rounds of {first arg-max; keep its
+ * probability; zero the box |dx| <= sigma_x (circular over the class axis), |dy| <= sigma_y around (x, y = index / n_classes as a FLOAT)},
+ * un-wrapped.  Non-zero cells of nms are the candidate waypoints. */
+int d3d_wp_heatmap_nms(const float* logits, int n_episodes, int n_angles, int n_classes, int max_predictions, float sigma_x, float sigma_y,
+                       float* prob, float* nms, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

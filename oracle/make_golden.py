@@ -212,8 +212,31 @@ def make_render():
     print("wrote render", f_ref.shape, float(np.linalg.norm(f_ref, axis=-1).max()))
 
 
+WAYPOINT_SEEDS = (3, 4, 3)  # (weights, depth embedding, episodes)
+
+
+def make_waypoint():
+    """8(f) rank 3: heat-map logits of the reference's own BinaryDistPredictor_TRM (TRM_net.py) and the NMS map of its `nms` (waypoint_pred/utils.py)
+    applied as POL:226-247 does, on seeded weights (synth.waypoint_state_dict) and a seeded depth embedding: only the OUTPUTS are stored, the
+    inputs are regenerated from the seeds."""
+    import torch
+    trm, utils = ref_shim.load_reference_waypoint_predictor()
+    net = trm.BinaryDistPredictor_TRM(device="cpu").eval()
+    net.load_state_dict(synth.waypoint_state_dict(WAYPOINT_SEEDS[0]), strict=True)
+    x = synth.waypoint_depth_embedding(WAYPOINT_SEEDS[1], WAYPOINT_SEEDS[2])
+    with torch.no_grad():
+        lg = net(None, x)
+        B = lg.shape[0]
+        bx = torch.softmax(lg.reshape(B, -1), 1).reshape(B, 120, 12)
+        wrap = torch.cat((bx[:, -1:], bx, bx[:, :1]), 1)
+        nms_map = utils.nms(wrap.unsqueeze(1), max_predictions=5, sigma=(7.0, 5.0)).squeeze(1)[:, 1:-1, :]
+    np.savez_compressed(os.path.join(OUT, "waypoint.npz"), logits=lg.numpy().astype(np.float32), nms=nms_map.numpy().astype(np.float32))
+    print("wrote waypoint", tuple(lg.shape), [nms_map[b].nonzero().tolist() for b in range(B)])
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    make_waypoint()
     make_render()
     make_geometry()
     make_posed()

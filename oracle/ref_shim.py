@@ -304,3 +304,45 @@ def reference_render_view(ff, patch_pos, patch_dir, patch_scale, patch_fts16, po
     with torch.no_grad(), torch.autocast("cpu", dtype=torch.float16):
         fts, pos, _ = ff.render_view_3d_patch(batch_position=[np.asarray(position_hab, np.float32).copy()], batch_heading=[float(heading)])
     return fts[0].reshape(-1, fts.shape[-1]).float().numpy(), pos[0].reshape(-1, 3).float().numpy()
+
+
+def load_reference_waypoint_predictor():
+    """The reference's candidate-waypoint predictor, unmodified: returns (TRM_net module, waypoint_pred.utils module).  Its vendored
+    `pytorch_transformer` package wants boto3 (download helpers, unused) and the pip name `pytorch_transformers` (TRM_net.py:7): both are
+    satisfied with empty stand-ins / an alias of the vendored modeling_bert."""
+    _install_stubs()
+    for stub in ("boto3", "botocore", "botocore.exceptions"):
+        if stub not in sys.modules:
+            sys.modules[stub] = types.ModuleType(stub)
+    if not hasattr(sys.modules["botocore.exceptions"], "ClientError"):
+        sys.modules["botocore.exceptions"].ClientError = Exception
+    base = os.path.join(REF_ROOT, "Dynam3D_VLN", "vlnce_baselines", "waypoint_pred")
+    pk = "vlnce_baselines.waypoint_pred"
+    for name, sub in ((pk, ""), (pk + ".transformer", "transformer"), (pk + ".transformer.pytorch_transformer", os.path.join("transformer", "pytorch_transformer"))):
+        if name not in sys.modules:
+            pkg = types.ModuleType(name)
+            pkg.__path__ = [os.path.join(base, sub)]
+            sys.modules[name] = pkg
+
+    def load(name, rel):
+        if name in sys.modules and getattr(sys.modules[name], "__file__", None):
+            return sys.modules[name]
+        spec = importlib.util.spec_from_file_location(name, os.path.join(base, rel))
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[name] = m
+        spec.loader.exec_module(m)
+        return m
+
+    pt = pk + ".transformer.pytorch_transformer."
+    load(pt + "file_utils", os.path.join("transformer", "pytorch_transformer", "file_utils.py"))
+    load(pt + "modeling_utils", os.path.join("transformer", "pytorch_transformer", "modeling_utils.py"))
+    mb = load(pt + "modeling_bert", os.path.join("transformer", "pytorch_transformer", "modeling_bert.py"))
+    if "pytorch_transformers" not in sys.modules:
+        alias = types.ModuleType("pytorch_transformers")
+        alias.BertConfig = mb.BertConfig
+        sys.modules["pytorch_transformers"] = alias
+    utils = load(pk + ".utils", "utils.py")
+    sys.modules[pk].utils = utils
+    load(pk + ".transformer.waypoint_bert", os.path.join("transformer", "waypoint_bert.py"))
+    trm = load(pk + ".TRM_net", "TRM_net.py")
+    return trm, utils

@@ -77,3 +77,20 @@ def test_render_oracle_vs_reference_renderer_output():
     assert valid.sum() > 100
     assert np.array_equal(z["positions"][valid], want["positions"][valid])
     assert np.abs(z["feature_map"].astype(np.float32) - want["feature_map"]).max() < 1e-3  # stored as fp16 (the reference's output dtype)
+
+
+def test_waypoint_oracle_vs_reference_vectors():
+    """8(f) rank 3: oracle/waypoint_oracle.py vs the stored outputs of the reference's own predictor and NMS (tests/golden/waypoint.npz;
+    inputs regenerated from the seeds of oracle/make_golden.py)."""
+    from dynam3d_b200 import synth
+    from oracle import waypoint_oracle as WO
+    from oracle.make_golden import WAYPOINT_SEEDS
+    g = np.load(os.path.join(GOLD, "waypoint.npz"))
+    sd = {k: v.numpy() for k, v in synth.waypoint_state_dict(WAYPOINT_SEEDS[0]).items()}
+    x = synth.waypoint_depth_embedding(WAYPOINT_SEEDS[1], WAYPOINT_SEEDS[2]).numpy()
+    lg = WO.predictor_logits(sd, x)
+    assert np.abs(lg - g["logits"]).max() < 1e-4 * max(1.0, float(np.abs(g["logits"]).max()))
+    _, nms_map = WO.heatmap_nms(lg)
+    assert np.array_equal(nms_map != 0, g["nms"] != 0) and np.abs(nms_map - g["nms"]).max() < 1e-5
+    c = WO.candidates_from_map(nms_map[0])
+    assert len(c["cand_angles"]) == 5 and all(0.25 <= d <= 3.0 for d in c["cand_distances"]) and all(0 <= i < 12 for i in c["cand_img_idxes"])

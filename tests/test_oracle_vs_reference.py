@@ -173,3 +173,39 @@ def test_render_oracle_matches_reference_renderer():
     assert valid.sum() > 100
     assert np.array_equal(p_ref[valid], want["positions"][valid])  # rays without neighbours tie over all samples: topk order unspecified
     assert np.abs(f_ref - want["feature_map"]).max() < 5e-4
+
+
+def test_waypoint_oracle_matches_reference():
+    """8(f) rank 3: oracle/waypoint_oracle.py vs the reference's own BinaryDistPredictor_TRM (TRM_net.py:66-88) and `nms` (waypoint_pred/utils.py:37-66,
+    applied as POL:226-247): logits to fp32 round-off, identical candidate cells, probabilities to 1e-5 relative."""
+    import torch
+    from dynam3d_b200 import synth
+    from oracle import waypoint_oracle as WO
+    trm, utils = ref_shim.load_reference_waypoint_predictor()
+    for wseed, xseed, B in ((3, 4, 3), (8, 9, 2)):
+        sd = synth.waypoint_state_dict(wseed)
+        net = trm.BinaryDistPredictor_TRM(device="cpu").eval()
+        net.load_state_dict(sd, strict=True)
+        x = synth.waypoint_depth_embedding(xseed, B)
+        with torch.no_grad():
+            ref = net(None, x)
+            bx = torch.softmax(ref.reshape(B, -1), 1).reshape(B, 120, 12)
+            wrap = torch.cat((bx[:, -1:], bx, bx[:, :1]), 1)
+            ref_map = utils.nms(wrap.unsqueeze(1), max_predictions=5, sigma=(7.0, 5.0)).squeeze(1)[:, 1:-1, :].numpy()
+        got = WO.predictor_logits({k: v.numpy() for k, v in sd.items()}, x.numpy())
+        assert np.abs(got - ref.numpy()).max() < 1e-4 * max(1.0, float(ref.abs().max()))
+        prob, nms_map = WO.heatmap_nms(got)
+        assert np.abs(prob - bx.numpy()).max() < 1e-5
+        assert np.array_equal(nms_map != 0, ref_map != 0)
+        assert np.abs(nms_map - ref_map).max() < 1e-5
+        assert np.array_equal(WO.attention_mask(), utils.get_attention_mask(12, 1).numpy().reshape(12, 12))
+    # the literal quirks of the post-processing on a hand-made map: float row coordinate of the box, circular class axis, exhausted map -> index 0
+    lg = np.full((1, 120, 12), -30.0, dtype=np.float32)
+    lg[0, 40, 3] = 5.0
+    lg[0, 44, 9] = 4.0   # inside the box of the first peak in y (|44 - 40.25| <= 5) and in x through the wrap (|9 - 3 - 12| = 6 <= 7)
+    t = torch.from_numpy(lg)
+    bx = torch.softmax(t.reshape(1, -1), 1).reshape(1, 120, 12)
+    wrap = torch.cat((bx[:, -1:], bx, bx[:, :1]), 1)
+    ref_map = utils.nms(wrap.unsqueeze(1), max_predictions=5, sigma=(7.0, 5.0)).squeeze(1)[:, 1:-1, :].numpy()
+    _, nms_map = WO.heatmap_nms(lg)
+    assert np.array_equal(nms_map != 0, ref_map != 0) and np.abs(nms_map - ref_map).max() < 1e-7
