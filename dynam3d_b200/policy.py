@@ -8,7 +8,8 @@ template and splice (POL:436,456), `get_gt_text` / `convert_text_to_action` (POL
 
 Differences that are deliberate and documented in DESIGN.md:
   * weights come from state dicts handed to `load_*` (no network here: the reference downloads CLIP / LLaVA from hubs);
-  * FastSAM, the depth ResNet / waypoint predictor and the training branch (`is_train=True`) are SURVEY.md 8(f) "next" rows;
+  * FastSAM, the depth ResNet of the waypoint branch and the training branch (`is_train=True`) are SURVEY.md 8(f) "next" rows that are
+    not built (the waypoint predictor + heat-map NMS are: `get_candidate_waypoints` below takes the depth encoder as a user-attached callable);
     segmentation is an input (`observations['patch_segm']` or `feature_fields.segmenter`);
   * Q13: for num_of_views > 1 the reference's splice is shape-inconsistent; the LLM sees the 576 patch tokens of view 0
     plus all instance / zone tokens, and the prompt reserves exactly that many `<image>` slots.
@@ -189,7 +190,9 @@ class Dynam3D_VLN(nn.Module):
         for p in self.parameters():
             p.requires_grad_(False)
         self.rgb_encoder = CLIPEncoder("ViT-L/14@336px", self.device, precise=precise)
-        self.depth_encoder = None  # SURVEY.md 8(f) rank 3 (waypoint branch), not part of this step
+        # SURVEY.md 8(f) rank 3 (waypoint branch): the DD-PPO depth ResNet is not built -- attach the reference's VlnResnetDepthEncoder (or any
+        # callable {"depth": [B*12, H, W, 1]} -> [B*12, 128, 4, 4]) here to use get_candidate_waypoints without passing depth_embedding
+        self.depth_encoder = None
         self.llava = _Llava(precise=precise, device=self.device)
         self.tokenize = None      # callable(str) -> list[int]; the real one is the llava-phi-3 tokenizer (POL:131)
         self.detokenize = None    # callable(list[int]) -> str
@@ -392,6 +395,51 @@ class Dynam3D_VLN(nn.Module):
     @staticmethod
     def build_prompt(n_image_tokens, instruction, history):
         return build_prompt(n_image_tokens, instruction, history)
+
+    def get_candidate_waypoints(self, waypoint_predictor=None, observations=None, depth_embedding=None):
+        """POL:188-292 with the reference's signature (plus `depth_embedding`, for callers that already ran the depth encoder).
+        `waypoint_predictor`: a `dynam3d_b200.waypoint.WaypointPredictor`.  `observations`: every key containing 'depth' is one view
+        ([B, H, W, 1], counter-clockwise order as the simulator delivers them); they are re-ordered clockwise for the predictor
+        (POL:197-205) and the depth features are flipped back afterwards (POL:216-221).  Returns the reference's dict."""
+        from copy import deepcopy
+        NUM_IMGS = 12
+        if waypoint_predictor is None:
+            raise ValueError("waypoint_predictor (dynam3d_b200.waypoint.WaypointPredictor) is required")
+        if depth_embedding is None:
+            if self.depth_encoder is None:
+                raise L.D3DLibraryError("the DD-PPO depth ResNet (ENC:15-109) is not built: attach the reference's VlnResnetDepthEncoder as "
+                                        "`net.depth_encoder` or pass depth_embedding=[B*12, 128, 4, 4]")
+            first = observations["depth"]
+            batch_size = first.shape[0]
+            depth_batch = torch.zeros_like(first).repeat(NUM_IMGS, 1, 1, 1)
+            a_count = 0
+            for k, v in observations.items():                                     # POL:198-204: reverse the view order to clockwise
+                if "depth" in k:
+                    for bi in range(v.size(0)):
+                        depth_batch[(NUM_IMGS - a_count) % NUM_IMGS + bi * NUM_IMGS] = v[bi]
+                    a_count += 1
+            depth_embedding = self.depth_encoder({"depth": depth_batch})           # POL:205-207
+        depth_embedding = depth_embedding.to(self.device, torch.float32)
+        batch_size = depth_embedding.shape[0] // NUM_IMGS
+        logits = waypoint_predictor(depth_embedding)                               # POL:210-211
+        cands = waypoint_predictor.candidates(logits, max_predictions=5, sigma=(7.0, 5.0))   # POL:226-247, 253-270
+        emb = depth_embedding.reshape(batch_size, NUM_IMGS, 128, 4, 4)
+        depth_feats = torch.cat((emb[:, 0:1], torch.flip(emb[:, 1:], [1])), dim=1)  # POL:216-221: back to counter-clockwise
+        depth_feats = depth_feats.mean(dim=(3, 4))                                 # space_pool_depth (POL:144, 249): AdaptiveAvgPool2d(1) + Flatten
+        pano_img_idxes = np.arange(0, 12, dtype=np.int64)                          # POL:147-149
+        pano_rad_c = (1 - pano_img_idxes / 12) * 2 * math.pi
+        h = torch.from_numpy(pano_rad_c)
+        pano_angle_fts = torch.stack([torch.sin(h), torch.cos(h), torch.sin(torch.zeros_like(h)), torch.cos(torch.zeros_like(h))]).float().T
+        return {
+            "cand_depth": [depth_feats[j, torch.from_numpy(c["cand_img_idxes"]).to(depth_feats.device)] for j, c in enumerate(cands)],   # [K x 128]
+            "cand_angle_fts": [torch.from_numpy(c["cand_angle_fts"]) for c in cands],   # [K x 4], clockwise
+            "cand_img_idxes": [c["cand_img_idxes"] for c in cands],
+            "cand_angles": [c["cand_angles"] for c in cands],                           # counter-clockwise
+            "cand_distances": [c["cand_distances"] for c in cands],
+            "pano_depth": depth_feats,                                                  # B x 12 x 128
+            "pano_angle_fts": deepcopy(pano_angle_fts),                                 # 12 x 4
+            "pano_img_idxes": deepcopy(pano_img_idxes),
+        }
 
     def _to_device(self, t):
         """Host observations -> device.  Pinned host tensors are copied on a dedicated copy stream (the compute stream waits on an event):

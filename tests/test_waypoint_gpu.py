@@ -93,6 +93,44 @@ def test_neighbor_attention_vs_torch():
     assert float((out - want).abs().max()) < 1e-5
 
 
+def test_get_candidate_waypoints_reference_signature():
+    """`Dynam3D_VLN.get_candidate_waypoints(waypoint_predictor, observations)` (POL:188-292) with a stand-in depth encoder attached: view
+    re-ordering, flip back, pooling and the candidate lists vs a direct restatement with the oracle."""
+    from dynam3d_b200 import synth
+    from dynam3d_b200.policy import Dynam3D_VLN
+    from oracle import waypoint_oracle as WO
+    from oracle.make_golden import WAYPOINT_SEEDS
+    B = 2
+    net = Dynam3D_VLN()
+    proj = synth.hash_uniform((128 * 16, 64), 77, 0.3).cuda()
+
+    def depth_encoder(obs):  # stand-in for VlnResnetDepthEncoder: [B*12, 16, 16, 1] -> [B*12, 128, 4, 4], any deterministic map will do
+        d = obs["depth"].cuda().float().reshape(obs["depth"].shape[0], -1)[:, :64]
+        return torch.relu(d @ proj.T).reshape(-1, 128, 4, 4)
+
+    net.depth_encoder = depth_encoder
+    obs = {("depth" if i == 0 else f"depth_{i}"): synth.hash_uniform((B, 16, 16, 1), 100 + i, 1.0) + 1.0 for i in range(12)}
+    p = _predictor(WAYPOINT_SEEDS[0])
+    out = net.get_candidate_waypoints(p, obs)
+    # restatement: clockwise order for the predictor
+    dep = torch.zeros(B * 12, 16, 16, 1)
+    for a, k in enumerate(obs):
+        for bi in range(B):
+            dep[(12 - a) % 12 + bi * 12] = obs[k][bi]
+    emb = depth_encoder({"depth": dep})
+    sd = {k: v.numpy() for k, v in synth.waypoint_state_dict(WAYPOINT_SEEDS[0]).items()}
+    _, want_map = WO.heatmap_nms(WO.predictor_logits(sd, emb.cpu().numpy()))
+    e5 = emb.reshape(B, 12, 128, 4, 4)
+    feats = torch.cat((e5[:, 0:1], torch.flip(e5[:, 1:], [1])), 1).mean(dim=(3, 4))
+    assert torch.allclose(out["pano_depth"], feats, atol=1e-6) and out["pano_angle_fts"].shape == (12, 4)
+    for j in range(B):
+        w = WO.candidates_from_map(want_map[j])
+        assert out["cand_angles"][j] == w["cand_angles"] and out["cand_distances"][j] == w["cand_distances"]
+        assert np.array_equal(out["cand_img_idxes"][j], w["cand_img_idxes"])
+        assert torch.allclose(out["cand_depth"][j], feats[j, torch.from_numpy(w["cand_img_idxes"]).cuda()], atol=1e-6)
+        assert np.array_equal(out["cand_angle_fts"][j].numpy(), w["cand_angle_fts"])
+
+
 def test_waypoint_timing_print():
     """Not an assertion on speed: prints the device time of predictor + NMS for 8 episodes (the bench's batch) for DESIGN.md."""
     from dynam3d_b200 import synth
