@@ -311,11 +311,24 @@ def load_reference_waypoint_predictor():
     `pytorch_transformer` package wants boto3 (download helpers, unused) and the pip name `pytorch_transformers` (TRM_net.py:7): both are
     satisfied with empty stand-ins / an alias of the vendored modeling_bert."""
     _install_stubs()
-    for stub in ("boto3", "botocore", "botocore.exceptions"):
-        if stub not in sys.modules:
-            sys.modules[stub] = types.ModuleType(stub)
-    if not hasattr(sys.modules["botocore.exceptions"], "ClientError"):
-        sys.modules["botocore.exceptions"].ClientError = Exception
+    import importlib.machinery
+
+    def absent(top):
+        return top not in sys.modules and importlib.util.find_spec(top) is None
+
+    def stand_in(name, package=False):
+        m = types.ModuleType(name)
+        m.__spec__ = importlib.machinery.ModuleSpec(name, None, is_package=package)  # with a spec: importlib.util.find_spec() on it must not raise
+        if package:
+            m.__path__ = []
+        sys.modules[name] = m
+        return m
+
+    if absent("boto3"):
+        stand_in("boto3")
+    if absent("botocore"):
+        stand_in("botocore", package=True)
+        stand_in("botocore.exceptions").ClientError = Exception
     base = os.path.join(REF_ROOT, "Dynam3D_VLN", "vlnce_baselines", "waypoint_pred")
     pk = "vlnce_baselines.waypoint_pred"
     for name, sub in ((pk, ""), (pk + ".transformer", "transformer"), (pk + ".transformer.pytorch_transformer", os.path.join("transformer", "pytorch_transformer"))):
@@ -339,6 +352,7 @@ def load_reference_waypoint_predictor():
     mb = load(pt + "modeling_bert", os.path.join("transformer", "pytorch_transformer", "modeling_bert.py"))
     if "pytorch_transformers" not in sys.modules:
         alias = types.ModuleType("pytorch_transformers")
+        alias.__spec__ = importlib.machinery.ModuleSpec("pytorch_transformers", None)
         alias.BertConfig = mb.BertConfig
         sys.modules["pytorch_transformers"] = alias
     utils = load(pk + ".utils", "utils.py")
